@@ -1,0 +1,326 @@
+"""ctypes doorway onto the CPU oracle -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / ``--impl reference`` legs
+may import this module.  The product package ``ascent_b200`` never does.
+
+liboracle.so          = oracle/raycast_oracle.c + oracle/composite_oracle.c (our restatement)
+_ref/libapcomp_ref.so = the reference's own apcomp sources (src/libs/apcomp/*.cpp) compiled in
+                        place by oracle/Makefile; optional at run time (absent -> ``ref`` is None).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class Camera(C.Structure):
+    """Field-for-field the same as ``vr_camera`` in include/vr_b200.h."""
+    _fields_ = [("position", C.c_float * 3), ("look_at", C.c_float * 3), ("up", C.c_float * 3),
+                ("fov", C.c_float), ("zoom", C.c_float), ("xpan", C.c_float), ("ypan", C.c_float),
+                ("near_plane", C.c_float), ("far_plane", C.c_float)]
+
+
+class Block(C.Structure):
+    _fields_ = [("kind", C.c_int), ("dims", C.c_int * 3), ("origin", C.c_float * 3),
+                ("spacing", C.c_float * 3), ("ax", C.c_void_p * 3), ("field", C.c_void_p),
+                ("field_f64", C.c_int), ("cell_assoc", C.c_int)]
+
+
+class Rays(C.Structure):
+    _fields_ = [("n", C.c_int), ("subset", C.c_int * 4), ("dir", C.POINTER(C.c_float)),
+                ("min_dist", C.POINTER(C.c_float)), ("max_dist", C.POINTER(C.c_float)),
+                ("dist", C.POINTER(C.c_float)), ("rgba", C.POINTER(C.c_float)),
+                ("pixel", C.POINTER(C.c_int64)), ("origin", C.c_float * 3),
+                ("n_samples", C.c_int64)]
+
+
+PARTIAL_DTYPE = np.dtype([("pixel_id", "<i4"), ("depth", "<f4"), ("rgb", "<f4", (3,)),
+                          ("alpha", "<f4")])
+assert PARTIAL_DTYPE.itemsize == 24
+
+
+def build(force=False):
+    """Compile liboracle.so (and _ref/ when /root/reference is present)."""
+    if force or not os.path.exists(os.path.join(_HERE, "liboracle.so")) or (
+            os.path.isdir("/root/reference")
+            and not os.path.exists(os.path.join(_HERE, "_ref", "libapcomp_ref.so"))):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+build()
+lib = C.CDLL(os.path.join(_HERE, "liboracle.so"))
+_ref_path = os.path.join(_HERE, "_ref", "libapcomp_ref.so")
+ref = C.CDLL(_ref_path) if os.path.exists(_ref_path) else None
+
+lib.orc_correct_opacity.restype = C.c_double
+lib.orc_correct_opacity.argtypes = [C.c_double, C.c_float]
+lib.orc_sample_distance.restype = C.c_float
+lib.orc_sample_distance.argtypes = [C.POINTER(C.c_double), C.c_float]
+lib.orc_extract_partials.restype = C.c_int64
+lib.orc_composite_partials.restype = C.c_int64
+lib.orc_composite_partials.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+lib.orc_partial_owner.restype = C.c_int
+lib.orc_num_threads.restype = C.c_int
+if ref is not None:
+    ref.ref_composite_partials.restype = C.c_longlong
+
+
+def num_threads():
+    return int(lib.orc_num_threads())
+
+
+# ----------------------------------------------------------------------------- camera (K0)
+def make_camera(position, look_at, up, fov=60.0, zoom=1.0, near=0.01, far=1000.0, xpan=0., ypan=0.):
+    c = Camera()
+    c.position[:] = [float(v) for v in position]
+    c.look_at[:] = [float(v) for v in look_at]
+    c.up[:] = [float(v) for v in up]
+    c.fov, c.zoom, c.xpan, c.ypan = fov, zoom, xpan, ypan
+    c.near_plane, c.far_plane = near, far
+    return c
+
+
+def camera_default():
+    c = Camera()
+    lib.orc_camera_default(C.byref(c))
+    return c
+
+
+def camera_reset_to_bounds(bounds, cam=None):
+    c = camera_default() if cam is None else cam
+    b = (C.c_double * 6)(*[float(v) for v in bounds])
+    lib.orc_camera_reset_to_bounds(C.byref(c), b)
+    return c
+
+
+def camera_azimuth(c, deg):
+    lib.orc_camera_azimuth(C.byref(c), C.c_float(deg))
+
+
+def camera_elevation(c, deg):
+    lib.orc_camera_elevation(C.byref(c), C.c_float(deg))
+
+
+def camera_zoom(c, z):
+    lib.orc_camera_zoom(C.byref(c), C.c_float(z))
+
+
+def projview(c, w, h):
+    m = np.zeros(16, np.float32)
+    lib.orc_projview(C.byref(c), w, h, _ptr(m, C.c_float))
+    return m.reshape(4, 4)
+
+
+def find_subset(c, w, h, bounds):
+    out = (C.c_int * 4)()
+    b = (C.c_double * 6)(*[float(v) for v in bounds])
+    lib.orc_find_subset(C.byref(c), w, h, b, out)
+    return tuple(out)
+
+
+# ----------------------------------------------------------------------------- blocks
+class OracleBlock:
+    """Keeps the numpy arrays alive next to the C struct."""
+
+    def __init__(self, dims, field, origin=None, spacing=None, axes=None, cell_assoc=False):
+        self.b = Block()
+        self.b.dims[:] = [int(d) for d in dims]
+        self.field = np.ascontiguousarray(field)
+        assert self.field.dtype in (np.float32, np.float64)
+        self.b.field = self.field.ctypes.data
+        self.b.field_f64 = int(self.field.dtype == np.float64)
+        self.b.cell_assoc = int(cell_assoc)
+        if axes is None:
+            self.b.kind = 0
+            self.b.origin[:] = [float(np.float32(v)) for v in origin]
+            self.b.spacing[:] = [float(np.float32(v)) for v in spacing]
+        else:
+            self.b.kind = 1
+            self.axes = [np.ascontiguousarray(a, dtype=np.float64) for a in axes]
+            for k in range(3):
+                assert self.axes[k].size == dims[k]
+                self.b.ax[k] = self.axes[k].ctypes.data
+        n_expected = (np.prod([d - 1 for d in dims]) if cell_assoc else np.prod(dims))
+        assert self.field.size == n_expected, (self.field.size, n_expected)
+
+    def bounds(self):
+        out = (C.c_double * 6)()
+        lib.orc_block_bounds(C.byref(self.b), out)
+        return np.array(out[:], np.float64)
+
+
+def sample_distance(global_bounds, samples):
+    b = (C.c_double * 6)(*[float(v) for v in global_bounds])
+    return float(lib.orc_sample_distance(b, C.c_float(samples)))
+
+
+def correct_opacity(alpha, samples):
+    return float(lib.orc_correct_opacity(float(alpha), C.c_float(samples)))
+
+
+class TraceResult:
+    def __init__(self, rays):
+        n = rays.n
+        self.subset = tuple(rays.subset)
+        self.n = n
+        self.rgba = np.ctypeslib.as_array(rays.rgba, (n, 4)).copy()
+        self.pixel = np.ctypeslib.as_array(rays.pixel, (n,)).copy()
+        self.min_dist = np.ctypeslib.as_array(rays.min_dist, (n,)).copy()
+        self.max_dist = np.ctypeslib.as_array(rays.max_dist, (n,)).copy()
+        self.dist = np.ctypeslib.as_array(rays.dist, (n,)).copy()
+        self.dir = np.ctypeslib.as_array(rays.dir, (n, 3)).copy()
+        self.n_samples = int(rays.n_samples)
+
+
+def trace_block(block, cam, W, H, lut, sample_dist, rmin, rmax, canvas_depth=None, keep=True):
+    """K1+K2+K3+K4/5/6 for one block.  Returns (Rays struct, TraceResult|None); free with
+    rays_free()."""
+    lut = np.ascontiguousarray(lut, np.float32)
+    rays = Rays()
+    dptr = None if canvas_depth is None else _ptr(canvas_depth, C.c_float)
+    lib.orc_trace_block(C.byref(block.b), C.byref(cam), W, H, _ptr(lut, C.c_float),
+                        int(lut.shape[0]), C.c_float(sample_dist), C.c_float(rmin),
+                        C.c_float(rmax), dptr, C.byref(rays))
+    return rays, (TraceResult(rays) if keep else None)
+
+
+def rays_free(rays):
+    lib.orc_rays_free(C.byref(rays))
+
+
+def new_canvas(W, H):
+    """Canvas::Clear: colour 0, depth 1.001."""
+    return np.zeros((H * W, 4), np.float32), np.full(H * W, 1.001, np.float32)
+
+
+def render_to_canvas(block, cam, W, H, lut, sample_dist, rmin, rmax, rgba, depth, use_depth=True):
+    """MapperVolume::RenderCells (path A per-domain body): trace + WriteToCanvas, in place."""
+    rays, _ = trace_block(block, cam, W, H, lut, sample_dist, rmin, rmax,
+                          depth if use_depth else None, keep=False)
+    ns = int(rays.n_samples)
+    lib.orc_write_to_canvas(C.byref(rays), C.byref(cam), W, H, _ptr(rgba, C.c_float),
+                            _ptr(depth, C.c_float))
+    rays_free(rays)
+    return ns
+
+
+def render_partials(block, cam, W, H, lut, sample_dist, rmin, rmax, canvas_depth):
+    """StructuredWrapper::render (path B per-domain body): trace + partial extraction."""
+    rays, _ = trace_block(block, cam, W, H, lut, sample_dist, rmin, rmax, canvas_depth, keep=False)
+    out = np.zeros(rays.n, PARTIAL_DTYPE)
+    n = lib.orc_extract_partials(C.byref(rays), out.ctypes.data_as(C.c_void_p))
+    rays_free(rays)
+    return out[:n].copy()
+
+
+def partials_to_canvas(partials, cam, W, H, rgba, depth):
+    p = np.ascontiguousarray(partials)
+    lib.orc_partials_to_canvas(p.ctypes.data_as(C.c_void_p), C.c_int64(p.size), C.byref(cam), W, H,
+                               _ptr(rgba, C.c_float), _ptr(depth, C.c_float))
+
+
+def visibility_order(domain_bounds, cam):
+    db = np.ascontiguousarray(domain_bounds, np.float64).reshape(-1, 6)
+    n = db.shape[0]
+    order = np.zeros(n, np.int32)
+    depths = np.zeros(n, np.float32)
+    lib.orc_visibility_order(_ptr(db, C.c_double), n, C.byref(cam), _ptr(order, C.c_int),
+                             _ptr(depths, C.c_float))
+    return order, depths
+
+
+# ----------------------------------------------------------------------------- compositing
+def image_init(rgba, depth, depth_mode=0):
+    rgba = np.ascontiguousarray(rgba, np.float32).reshape(-1, 4)
+    depth = np.ascontiguousarray(depth, np.float32).reshape(-1)
+    n = depth.size
+    out = np.zeros((n, 4), np.uint8)
+    od = np.zeros(n, np.float32)
+    lib.orc_image_init(_ptr(rgba, C.c_float), _ptr(depth, C.c_float), n, depth_mode,
+                       _ptr(out, C.c_uint8), _ptr(od, C.c_float))
+    return out, od
+
+
+def ordered_composite(layers_rgba, layers_depth, vis_order):
+    lr = np.ascontiguousarray(layers_rgba, np.uint8)
+    ld = np.ascontiguousarray(layers_depth, np.float32)
+    n_img = lr.shape[0]
+    n = ld.reshape(n_img, -1).shape[1]
+    vo = np.ascontiguousarray(vis_order, np.int32)
+    out = np.zeros((n, 4), np.uint8)
+    od = np.zeros(n, np.float32)
+    lib.orc_ordered_composite(_ptr(lr, C.c_uint8), _ptr(ld, C.c_float), _ptr(vo, C.c_int), n_img, n,
+                              _ptr(out, C.c_uint8), _ptr(od, C.c_float))
+    return out, od
+
+
+def zbuffer_composite(front_rgba, front_depth, img_rgba, img_depth, gl_depth=False):
+    n = front_depth.size
+    lib.orc_zbuffer_composite(_ptr(front_rgba, C.c_uint8), _ptr(front_depth, C.c_float),
+                              _ptr(img_rgba, C.c_uint8), _ptr(img_depth, C.c_float), n,
+                              int(gl_depth))
+
+
+def image_to_canvas(rgba_u8, depth):
+    n = depth.size
+    out = np.zeros((n, 4), np.float32)
+    od = np.zeros(n, np.float32)
+    lib.orc_image_to_canvas(_ptr(np.ascontiguousarray(rgba_u8), C.c_uint8),
+                            _ptr(np.ascontiguousarray(depth), C.c_float), n, _ptr(out, C.c_float),
+                            _ptr(od, C.c_float))
+    return out, od
+
+
+def composite_partials(partial_lists):
+    """PartialCompositor::composite for a list of per-domain partial arrays (single rank)."""
+    allp = (np.concatenate(partial_lists) if len(partial_lists) else np.zeros(0, PARTIAL_DTYPE))
+    allp = np.ascontiguousarray(allp)
+    out = np.zeros(allp.size, PARTIAL_DTYPE)
+    n = lib.orc_composite_partials(allp.ctypes.data_as(C.c_void_p), C.c_int64(allp.size),
+                                   out.ctypes.data_as(C.c_void_p))
+    return out[:n].copy()
+
+
+def partial_owner(pixel_id, min_pixel, max_pixel, n_ranks):
+    return int(lib.orc_partial_owner(int(pixel_id), int(min_pixel), int(max_pixel), int(n_ranks)))
+
+
+# ----------------------------------------------------------------------------- _ref (real apcomp)
+def ref_composite_vis_order(rgba_f32, depth, vis_order, W, H):
+    assert ref is not None
+    r = np.ascontiguousarray(rgba_f32, np.float32)
+    d = np.ascontiguousarray(depth, np.float32)
+    vo = np.ascontiguousarray(vis_order, np.int32)
+    out = np.zeros((H * W, 4), np.uint8)
+    od = np.zeros(H * W, np.float32)
+    ref.ref_composite_vis_order(_ptr(r, C.c_float), _ptr(d, C.c_float), _ptr(vo, C.c_int),
+                                int(vo.size), W, H, _ptr(out, C.c_uint8), _ptr(od, C.c_float))
+    return out, od
+
+
+def ref_composite_zbuffer(rgba_f32, depth, n_images, W, H):
+    assert ref is not None
+    r = np.ascontiguousarray(rgba_f32, np.float32)
+    d = np.ascontiguousarray(depth, np.float32)
+    out = np.zeros((H * W, 4), np.uint8)
+    od = np.zeros(H * W, np.float32)
+    ref.ref_composite_zbuffer(_ptr(r, C.c_float), _ptr(d, C.c_float), n_images, W, H,
+                              _ptr(out, C.c_uint8), _ptr(od, C.c_float))
+    return out, od
+
+
+def ref_composite_partials(partial_lists):
+    assert ref is not None
+    counts = np.array([p.size for p in partial_lists], np.int64)
+    allp = np.ascontiguousarray(np.concatenate(partial_lists))
+    out = np.zeros(allp.size, PARTIAL_DTYPE)
+    n = ref.ref_composite_partials(allp.ctypes.data_as(C.c_void_p), _ptr(counts, C.c_longlong),
+                                   int(counts.size), out.ctypes.data_as(C.c_void_p))
+    return out[:n].copy()

@@ -1,0 +1,948 @@
+/*
+ * raycast_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement (plain C, float32, compiled -ffp-contract=off) of the ray-cast half
+ * of Ascent's `volume` plot hot path.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load this file's shared object.
+ *
+ * The arithmetic of this half lives in VTK-m v2.1.0 (pinned at
+ * scripts/build_ascent/build_ascent.sh:564, + scripts/build_ascent/
+ * 2024_07_02_vtkm-mr3246-raysubset_bugfix.patch), an external dependency that is
+ * ABSENT from /root/reference and from this container.  Every function below
+ * therefore restates VTK-m's published algorithm from its call sites in
+ *   src/libs/vtkh/rendering/VolumeRenderer.cpp:199-216,239-258,516-528
+ * and from the in-tree mirrors of the same math
+ *   src/libs/vtkh/rendering/VolumeRenderer.cpp:64-91   (LUT -> float4)
+ *   src/libs/vtkh/rendering/VolumeRenderer.cpp:287-391 (ray dir, projection, over)
+ *   src/libs/dray/rendering/camera.cpp:402-514         (ray gen, reset_to_bounds)
+ *
+ * PARITY PIN: kernel-level (K1-K7) outputs are "parity unpinned" (no VTK-m here);
+ * the whole-image behaviour IS pinned against the reference's own golden PNGs
+ * src/tests/_baseline_images/{render_0100,render_1100,tout_render_mpi_3d_diy_volume100}.png
+ * (tests/test_oracle_golden.py) at the reference's own PNGCompare tolerance
+ * (src/libs/png_utils/ascent_png_compare.cpp:35,138-141).
+ *
+ * Ids (K0..K8, V3..V10) refer to SURVEY.md section 8(a).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_API __attribute__((visibility("default")))
+
+typedef struct
+{
+  float position[3];
+  float look_at[3];
+  float up[3];
+  float fov;  /* degrees (vertical) */
+  float zoom; /* vtkm zoom factor, 1 = none */
+  float xpan, ypan;
+  float near_plane, far_plane;
+} orc_camera;
+
+/* VolumePartial<float>, src/libs/vtkh/compositing/VolumePartial.hpp:48-56 (24 B POD) */
+typedef struct
+{
+  int32_t pixel_id;
+  float depth;
+  float rgb[3];
+  float alpha;
+} orc_partial;
+
+/* ------------------------------------------------------------------ small vec math */
+static const float PI_180F = (float)0.01745329251994329547437168059786927;
+
+/* [VTK-m] vtkm::DifferenceOfProducts (Math.h): a*b - c*d with one compensation step */
+static float diff_of_products(float a, float b, float c, float d)
+{
+  float cd = c * d;
+  float err = fmaf(-c, d, cd);
+  float dop = fmaf(a, b, -cd);
+  return dop + err;
+}
+static void v_cross(const float x[3], const float y[3], float out[3])
+{
+  float r0 = diff_of_products(x[1], y[2], x[2], y[1]);
+  float r1 = diff_of_products(x[2], y[0], x[0], y[2]);
+  float r2 = diff_of_products(x[0], y[1], x[1], y[0]);
+  out[0] = r0; out[1] = r1; out[2] = r2;
+}
+static float v_dot(const float a[3], const float b[3])
+{
+  return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+}
+static float v_mag(const float a[3]) { return sqrtf(v_dot(a, a)); }
+/* [VTK-m] Normalize(x): x = x * RSqrt(Dot(x,x)); host RSqrt = 1/sqrt */
+static void v_normalize(float a[3])
+{
+  float r = 1.0f / sqrtf(v_dot(a, a));
+  a[0] = r * a[0]; a[1] = r * a[1]; a[2] = r * a[2];
+}
+
+/* row-major 4x4 */
+static void m_identity(float m[16])
+{
+  memset(m, 0, 16 * sizeof(float));
+  m[0] = m[5] = m[10] = m[15] = 1.f;
+}
+/* [VTK-m] MatrixMultiply: sum starts at k=0 product, then adds k=1..3 */
+static void m_mul(const float a[16], const float b[16], float out[16])
+{
+  float r[16];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j)
+    {
+      float sum = a[i * 4 + 0] * b[0 * 4 + j];
+      for (int k = 1; k < 4; ++k) sum = sum + a[i * 4 + k] * b[k * 4 + j];
+      r[i * 4 + j] = sum;
+    }
+  memcpy(out, r, sizeof(r));
+}
+static void m_mulv(const float m[16], const float v[4], float out[4])
+{
+  float r[4];
+  for (int i = 0; i < 4; ++i)
+    r[i] = m[i * 4 + 0] * v[0] + m[i * 4 + 1] * v[1] + m[i * 4 + 2] * v[2] + m[i * 4 + 3] * v[3];
+  memcpy(out, r, sizeof(r));
+}
+/* [VTK-m] MatrixInverse = LUP factor (unit-diagonal U) + solve per identity column */
+static int m_inverse(const float in[16], float out[16])
+{
+  float A[16];
+  int perm[4] = { 0, 1, 2, 3 };
+  memcpy(A, in, sizeof(A));
+  int valid = 1;
+  for (int top = 0; top < 4; ++top)
+  {
+    /* pivot */
+    float maxv = fabsf(A[top * 4 + top]);
+    int maxr = top;
+    for (int r = top + 1; r < 4; ++r)
+    {
+      float v = fabsf(A[r * 4 + top]);
+      if (maxv < v) { maxv = v; maxr = r; }
+    }
+    if (maxv < 1.1920929e-07f) valid = 0; /* vtkm::Epsilon<float>() */
+    if (maxr != top)
+    {
+      for (int c = 0; c < 4; ++c)
+      {
+        float t = A[maxr * 4 + c]; A[maxr * 4 + c] = A[top * 4 + c]; A[top * 4 + c] = t;
+      }
+      int t = perm[top]; perm[top] = perm[maxr]; perm[maxr] = t;
+    }
+    /* upper-triangle row */
+    for (int c = top + 1; c < 4; ++c) A[top * 4 + c] /= A[top * 4 + top];
+    for (int r = top + 1; r < 4; ++r)
+      for (int c = top + 1; c < 4; ++c) A[r * 4 + c] -= A[r * 4 + top] * A[top * 4 + c];
+  }
+  for (int col = 0; col < 4; ++col)
+  {
+    float y[4], x[4];
+    /* forward: L y = P e_col */
+    for (int r = 0; r < 4; ++r)
+    {
+      float b = (perm[r] == col) ? 1.f : 0.f;
+      for (int c = 0; c < r; ++c) b -= A[r * 4 + c] * y[c];
+      y[r] = b / A[r * 4 + r];
+    }
+    /* backward: U x = y, unit diagonal */
+    for (int r = 3; r >= 0; --r)
+    {
+      float b = y[r];
+      for (int c = r + 1; c < 4; ++c) b -= A[r * 4 + c] * x[c];
+      x[r] = b;
+    }
+    for (int r = 0; r < 4; ++r) out[r * 4 + col] = x[r];
+  }
+  return valid;
+}
+
+/* ------------------------------------------------------------------ K0: camera */
+/* [VTK-m] vtkm::rendering::Camera defaults */
+ORC_API void orc_camera_default(orc_camera* c)
+{
+  c->look_at[0] = 0; c->look_at[1] = 0; c->look_at[2] = 0;
+  c->position[0] = 0; c->position[1] = 0; c->position[2] = 1;
+  c->up[0] = 0; c->up[1] = 1; c->up[2] = 0;
+  c->fov = 60.f; c->zoom = 1.f; c->xpan = 0; c->ypan = 0;
+  c->near_plane = 0.01f; c->far_plane = 1000.f;
+}
+
+/* [VTK-m] Camera::ResetToBounds(bounds) (called Render.cpp:324, rendering_filters.cpp:922);
+ * same formula in src/libs/dray/rendering/camera.cpp:485-514.  b = xmin,xmax,ymin,ymax,zmin,zmax */
+ORC_API void orc_camera_reset_to_bounds(orc_camera* c, const double b[6])
+{
+  float dir[3] = { c->position[0] - c->look_at[0], c->position[1] - c->look_at[1],
+                   c->position[2] - c->look_at[2] };
+  v_normalize(dir);
+  float center[3] = { (float)((b[0] + b[1]) / 2.0), (float)((b[2] + b[3]) / 2.0),
+                      (float)((b[4] + b[5]) / 2.0) };
+  float ext[3] = { (float)(b[1] - b[0]), (float)(b[3] - b[2]), (float)(b[5] - b[4]) };
+  float diag = v_mag(ext);
+  for (int i = 0; i < 3; ++i)
+  {
+    c->look_at[i] = center[i];
+    c->position[i] = center[i] + dir[i] * diag * 1.0f;
+  }
+  c->fov = 60.f;
+  c->near_plane = 0.1f * diag;
+  c->far_plane = diag * 10.0f;
+  c->xpan = 0; c->ypan = 0; c->zoom = 1.f;
+}
+
+/* [VTK-m] Transform3DRotate(angleDegrees, axis) */
+static void m_rotate(float deg, const float axis_in[3], float m[16])
+{
+  float ang = PI_180F * deg;
+  float n[3] = { axis_in[0], axis_in[1], axis_in[2] };
+  v_normalize(n);
+  float s = sinf(ang), co = cosf(ang);
+  m_identity(m);
+  m[0] = n[0] * n[0] * (1 - co) + co;
+  m[1] = n[0] * n[1] * (1 - co) - n[2] * s;
+  m[2] = n[0] * n[2] * (1 - co) + n[1] * s;
+  m[4] = n[1] * n[0] * (1 - co) + n[2] * s;
+  m[5] = n[1] * n[1] * (1 - co) + co;
+  m[6] = n[1] * n[2] * (1 - co) - n[0] * s;
+  m[8] = n[2] * n[0] * (1 - co) - n[1] * s;
+  m[9] = n[2] * n[1] * (1 - co) + n[0] * s;
+  m[10] = n[2] * n[2] * (1 - co) + co;
+}
+static void m_translate(float x, float y, float z, float m[16])
+{
+  m_identity(m);
+  m[3] = x; m[7] = y; m[11] = z;
+}
+static void rotate_about_lookat(orc_camera* c, float deg, const float axis[3])
+{
+  float T[16], R[16], Ti[16], M[16];
+  m_translate(c->look_at[0], c->look_at[1], c->look_at[2], T);
+  m_rotate(deg, axis, R);
+  m_translate(-c->look_at[0], -c->look_at[1], -c->look_at[2], Ti);
+  m_mul(T, R, M);
+  m_mul(M, Ti, M);
+  float p[4] = { c->position[0], c->position[1], c->position[2], 1.f }, q[4];
+  m_mulv(M, p, q);
+  /* Transform3DPoint: no perspective divide */
+  c->position[0] = q[0]; c->position[1] = q[1]; c->position[2] = q[2];
+}
+/* [VTK-m] Camera::Azimuth / Elevation (parsing.cpp:163-173 call sites) */
+ORC_API void orc_camera_azimuth(orc_camera* c, float deg)
+{
+  rotate_about_lookat(c, deg, c->up);
+}
+ORC_API void orc_camera_elevation(orc_camera* c, float deg)
+{
+  float d[3] = { c->position[0] - c->look_at[0], c->position[1] - c->look_at[1],
+                 c->position[2] - c->look_at[2] };
+  float axis[3];
+  v_cross(d, c->up, axis);
+  rotate_about_lookat(c, deg, axis);
+}
+/* [VTK-m] Camera::Zoom(z): zoom *= 4^z  (parsing.cpp:59-69) */
+ORC_API void orc_camera_zoom(orc_camera* c, float z)
+{
+  float factor = powf(4.0f, z);
+  c->zoom *= factor;
+}
+
+/* [VTK-m] Camera3DStruct::CreateViewMatrix */
+ORC_API void orc_view_matrix(const orc_camera* c, float m[16])
+{
+  float vd[3] = { c->position[0] - c->look_at[0], c->position[1] - c->look_at[1],
+                  c->position[2] - c->look_at[2] };
+  float right[3], ru[3];
+  v_cross(c->up, vd, right);
+  v_cross(vd, right, ru);
+  v_normalize(vd); v_normalize(right); v_normalize(ru);
+  m_identity(m);
+  m[0] = right[0]; m[1] = right[1]; m[2] = right[2];
+  m[4] = ru[0];    m[5] = ru[1];    m[6] = ru[2];
+  m[8] = vd[0];    m[9] = vd[1];    m[10] = vd[2];
+  m[3] = -v_dot(right, c->position);
+  m[7] = -v_dot(ru, c->position);
+  m[11] = -v_dot(vd, c->position);
+}
+
+/* [VTK-m] Camera3DStruct::CreateProjectionMatrix(width,height,near,far) */
+ORC_API void orc_projection_matrix(const orc_camera* c, int width, int height, float m[16])
+{
+  float nearp = c->near_plane, farp = c->far_plane;
+  m_identity(m);
+  float aspect = (float)width / (float)height;
+  float fovRad = c->fov * PI_180F;
+  fovRad = tanf(fovRad * 0.5f);
+  float size = nearp * fovRad;
+  float left = -size * aspect, right = size * aspect, bottom = -size, top = size;
+  m[0] = 2.f * nearp / (right - left);
+  m[5] = 2.f * nearp / (top - bottom);
+  m[2] = (right + left) / (right - left);
+  m[6] = (top + bottom) / (top - bottom);
+  m[10] = -(farp + nearp) / (farp - nearp);
+  m[14] = -1.f;
+  m[11] = -(2.f * farp * nearp) / (farp - nearp);
+  m[15] = 0.f;
+  float T[16], Z[16], TM[16];
+  m_translate(c->xpan, c->ypan, 0.f, T);
+  m_identity(Z);
+  Z[0] = c->zoom; Z[5] = c->zoom; Z[10] = 1.f;
+  m_mul(T, m, TM);
+  m_mul(Z, TM, m);
+}
+
+ORC_API void orc_projview(const orc_camera* c, int w, int h, float pv[16])
+{
+  float P[16], V[16];
+  orc_projection_matrix(c, w, h, P);
+  orc_view_matrix(c, V);
+  m_mul(P, V, pv);
+}
+
+/* ------------------------------------------------------------------ K1: ray camera */
+typedef struct
+{
+  float nlook[3], delta_x[3], delta_y[3];
+  float fov_x, fov_y;
+} orc_raygen;
+
+/* [VTK-m] raytracing::Camera::SetFieldOfView + PerspectiveRayGen ctor;
+ * in-tree mirror VolumeRenderer.cpp:304-339 */
+ORC_API void orc_raygen_setup(const orc_camera* c, int width, int height, orc_raygen* g)
+{
+  float fov_y = c->fov, fov_x = c->fov;
+  if (width != height)
+  {
+    float fovyRad = fov_y * PI_180F;
+    float verticalDistance = tanf(0.5f * fovyRad);
+    float aspectRatio = (float)width / (float)height;
+    float horizontalDistance = aspectRatio * verticalDistance;
+    float fovxRad = 2.0f * atanf(horizontalDistance);
+    fov_x = fovxRad / PI_180F;
+  }
+  g->fov_x = fov_x; g->fov_y = fov_y;
+  float look[3] = { c->look_at[0] - c->position[0], c->look_at[1] - c->position[1],
+                    c->look_at[2] - c->position[2] };
+  v_normalize(look); /* CreateRaysImpl normalises Look before the functor */
+  float thx = tanf((fov_x * PI_180F) * .5f);
+  float thy = tanf((fov_y * PI_180F) * .5f);
+  float ru[3], rv[3];
+  v_cross(look, c->up, ru);
+  v_normalize(ru);
+  v_cross(ru, look, rv);
+  v_normalize(rv);
+  float sx = 2 * thx / (float)width, sy = 2 * thy / (float)height;
+  for (int i = 0; i < 3; ++i) { g->delta_x[i] = ru[i] * sx; g->delta_y[i] = rv[i] * sy; }
+  if (c->zoom > 0)
+    for (int i = 0; i < 3; ++i)
+    {
+      g->delta_x[i] = g->delta_x[i] / c->zoom;
+      g->delta_y[i] = g->delta_y[i] / c->zoom;
+    }
+  g->nlook[0] = look[0]; g->nlook[1] = look[1]; g->nlook[2] = look[2];
+  v_normalize(g->nlook);
+}
+
+/* per-pixel direction, PerspectiveRayGen::operator() */
+static void ray_dir(const orc_raygen* g, int w, int h, int i, int j, float d[3])
+{
+  float fx = (2.f * (float)i - (float)w) / 2.0f;
+  float fy = (2.f * (float)j - (float)h) / 2.0f;
+  for (int k = 0; k < 3; ++k) d[k] = g->nlook[k] + g->delta_x[k] * fx + g->delta_y[k] * fy;
+  for (int k = 0; k < 3; ++k)
+    if (d[k] == 0.f) d[k] += 0.0000001f;
+  float dot = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+  float sq = sqrtf(dot);
+  d[0] = d[0] / sq; d[1] = d[1] / sq; d[2] = d[2] / sq;
+}
+
+/* [VTK-m] raytracing::Camera::FindSubset, with the clip-range behaviour of
+ * scripts/build_ascent/2024_07_02_vtkm-mr3246-raysubset_bugfix.patch:14-40.
+ * bounds = xmin,xmax,ymin,ymax,zmin,zmax (f64, cast to f32 like VTK-m).
+ * out = {minx, miny, width, height} */
+ORC_API void orc_find_subset(const orc_camera* c, int W, int H, const double bounds[6],
+                             int out[4])
+{
+  float x[2] = { (float)bounds[0], (float)bounds[1] };
+  float y[2] = { (float)bounds[2], (float)bounds[3] };
+  float z[2] = { (float)bounds[4], (float)bounds[5] };
+  const float* P = c->position;
+  if (P[0] >= x[0] && P[0] <= x[1] && P[1] >= y[0] && P[1] <= y[1] && P[2] >= z[0] && P[2] <= z[1])
+  {
+    out[0] = 0; out[1] = 0; out[2] = W; out[3] = H;
+    return;
+  }
+  float pv[16];
+  orc_projview(c, W, H, pv);
+  float xmin = INFINITY, ymin = INFINITY, zmin = INFINITY;
+  float xmax = -INFINITY, ymax = -INFINITY, zmax = -INFINITY;
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j)
+      for (int k = 0; k < 2; ++k)
+      {
+        float e[4] = { x[i], y[j], z[k], 1.f }, t[4];
+        m_mulv(pv, e, t);
+        for (int a = 0; a < 3; ++a) t[a] = t[a] / t[3];
+        t[0] = (t[0] * 0.5f + 0.5f) * (float)W;
+        t[1] = (t[1] * 0.5f + 0.5f) * (float)H;
+        t[2] = (t[2] * 0.5f + 0.5f);
+        zmin = fminf(zmin, t[2]);
+        zmax = fmaxf(zmax, t[2]);
+        if (t[2] < 0 || t[2] > 1) continue;
+        xmin = fminf(xmin, t[0]); ymin = fminf(ymin, t[1]);
+        xmax = fmaxf(xmax, t[0]); ymax = fmaxf(ymax, t[1]);
+      }
+  xmin -= .001f; xmax += .001f; ymin -= .001f; ymax += .001f;
+  xmin = floorf(fminf(fmaxf(0.f, xmin), (float)W));
+  xmax = ceilf(fminf(fmaxf(0.f, xmax), (float)W));
+  ymin = floorf(fminf(fmaxf(0.f, ymin), (float)H));
+  ymax = ceilf(fminf(fmaxf(0.f, ymax), (float)H));
+  int dx = (int)xmax - (int)xmin;
+  int dy = (int)ymax - (int)ymin;
+  if (zmax < 0 || xmin >= xmax || ymin >= ymax)
+  {
+    out[0] = 0; out[1] = 0; out[2] = 1; out[3] = 1;
+  }
+  else
+  {
+    out[0] = (int)xmin; out[1] = (int)ymin; out[2] = dx; out[3] = dy;
+  }
+}
+
+/* ------------------------------------------------------------------ block description */
+typedef struct
+{
+  int kind;           /* 0 uniform, 1 rectilinear */
+  int dims[3];        /* POINT dims */
+  float origin[3];    /* uniform: f32 (ascent_vtkh_data_adapter.cpp:1264-1270) */
+  float spacing[3];
+  const double* ax[3]; /* rectilinear axes, f64 (ascent_vtkh_data_adapter.cpp:1336-1395) */
+  const void* field;
+  int field_f64;      /* 0: f32, 1: f64 (cast per load) */
+  int cell_assoc;     /* 0: point field, 1: cell field (K6) */
+} orc_block;
+
+static inline float fld(const orc_block* b, int64_t i)
+{
+  return b->field_f64 ? (float)((const double*)b->field)[i] : ((const float*)b->field)[i];
+}
+
+/* block coordinate bounds as f64 (CoordinateSystem::GetBounds) */
+ORC_API void orc_block_bounds(const orc_block* b, double out[6])
+{
+  for (int a = 0; a < 3; ++a)
+  {
+    if (b->kind == 0)
+    {
+      /* ArrayHandleUniformPointCoordinates bounds: origin + spacing*(dim-1) in FloatDefault=f64 */
+      out[2 * a] = (double)b->origin[a];
+      out[2 * a + 1] = (double)b->origin[a] + (double)b->spacing[a] * (double)(b->dims[a] - 1);
+    }
+    else
+    {
+      out[2 * a] = b->ax[a][0];
+      out[2 * a + 1] = b->ax[a][b->dims[a] - 1];
+    }
+  }
+}
+
+typedef struct
+{
+  float min_point[3], max_point[3], inv_spacing[3];
+} locator;
+
+static void locator_init(const orc_block* b, locator* L)
+{
+  for (int a = 0; a < 3; ++a)
+  {
+    if (b->kind == 0)
+    {
+      /* UniformLocator ctor: MaxPoint = Origin + spacing*unitLength (f32) */
+      L->min_point[a] = b->origin[a];
+      L->max_point[a] = b->origin[a] + b->spacing[a] * (float)(b->dims[a] - 1);
+      L->inv_spacing[a] = 1.f / b->spacing[a];
+    }
+    else
+    {
+      L->min_point[a] = (float)b->ax[a][0];
+      L->max_point[a] = (float)b->ax[a][b->dims[a] - 1];
+      L->inv_spacing[a] = 0.f;
+    }
+  }
+}
+static inline int is_inside(const locator* L, const float p[3])
+{
+  int inside = 1;
+  if (p[0] < L->min_point[0] || p[0] > L->max_point[0]) inside = 0;
+  if (p[1] < L->min_point[1] || p[1] > L->max_point[1]) inside = 0;
+  if (p[2] < L->min_point[2] || p[2] > L->max_point[2]) inside = 0;
+  return inside;
+}
+/* UniformLocator::LocateCell / RectilinearLocator::LocateCell */
+static inline void locate_cell(const orc_block* b, const locator* L, int64_t cell[3],
+                               const float p[3], float inv_sp[3])
+{
+  if (b->kind == 0)
+  {
+    for (int a = 0; a < 3; ++a)
+    {
+      float t = p[a] - L->min_point[a];
+      t = t * L->inv_spacing[a];
+      if (t == (float)(b->dims[a] - 1)) t = (float)(b->dims[a] - 2);
+      cell[a] = (int64_t)t;
+      inv_sp[a] = L->inv_spacing[a];
+    }
+  }
+  else
+  {
+    for (int a = 0; a < 3; ++a)
+    {
+      if (p[a] == L->max_point[a])
+      {
+        cell[a] = b->dims[a] - 2;
+        continue; /* invSpacing[a] keeps its previous value, as in VTK-m */
+      }
+      const double* ax = b->ax[a];
+      int found = 0;
+      float minVal = (float)ax[cell[a]];
+      const int64_t searchDir = (p[a] - minVal >= 0.f) ? 1 : -1;
+      float maxVal = (float)ax[cell[a] + 1];
+      while (!found)
+      {
+        if (p[a] >= minVal && p[a] < maxVal) { found = 1; continue; }
+        cell[a] += searchDir;
+        int64_t nextCellId = searchDir == 1 ? cell[a] + 1 : cell[a];
+        float next = (float)ax[nextCellId];
+        if (searchDir == 1) { minVal = maxVal; maxVal = next; }
+        else                { maxVal = minVal; minVal = next; }
+      }
+      inv_sp[a] = 1.f / (maxVal - minVal);
+    }
+  }
+}
+/* Locator::GetPoint(cellIndices[0]) : lower-left corner of the cell as Vec3f_32.
+ * uniform: ArrayPortalUniformPointCoordinates::Get computes origin + spacing*ijk in
+ * FloatDefault (f64 in Ascent builds) and the result is narrowed to f32. */
+static inline void cell_min_point(const orc_block* b, const int64_t cell[3], float bl[3])
+{
+  for (int a = 0; a < 3; ++a)
+  {
+    if (b->kind == 0)
+      bl[a] = (float)((double)b->origin[a] + (double)b->spacing[a] * (double)cell[a]);
+    else
+      bl[a] = (float)b->ax[a][cell[a]];
+  }
+}
+
+/* ------------------------------------------------------------------ rays */
+typedef struct
+{
+  int n;            /* rays = subset w*h */
+  int subset[4];    /* minx, miny, w, h */
+  float* dir;       /* 3*n */
+  float* min_dist;  /* n */
+  float* max_dist;  /* n */
+  float* dist;      /* n : Ray::Distance */
+  float* rgba;      /* 4*n : Buffers[0] */
+  int64_t* pixel;   /* n */
+  float origin[3];
+  int64_t n_samples; /* total samples taken (bench accounting) */
+} orc_rays;
+
+ORC_API void orc_rays_free(orc_rays* r)
+{
+  free(r->dir); free(r->min_dist); free(r->max_dist); free(r->dist); free(r->rgba); free(r->pixel);
+  memset(r, 0, sizeof(*r));
+}
+
+static inline float rcp_safe(float f) { return 1.0f / ((fabsf(f) < 1e-8f) ? 1e-8f : f); }
+
+/*
+ * One block, one camera: K1 (CreateRays over the block's screen subset), K2
+ * (MapCanvasToRays, only if canvas_depth != NULL), K3 (CalcRayStart), K4/K5/K6 (Sampler).
+ * This is the body shared by MapperVolume::RenderCells (VolumeRenderer.cpp:523-528)
+ * and StructuredWrapper::render (VolumeRenderer.cpp:239-258).
+ *
+ * lut          : 1024 x float4 (K8 output; VolumeRenderer.cpp:64-91)
+ * sample_dist  : V4, VolumeRenderer.cpp:606-611
+ * canvas_depth : W*H f32 or NULL (NULL == cleared canvas, depth 1.001 -> no clamp computed)
+ */
+ORC_API void orc_trace_block(const orc_block* b, const orc_camera* cam, int W, int H,
+                             const float* lut, int lut_size, float sample_dist,
+                             float range_min, float range_max, const float* canvas_depth,
+                             orc_rays* rays)
+{
+  double bounds[6];
+  orc_block_bounds(b, bounds);
+  orc_find_subset(cam, W, H, bounds, rays->subset);
+  const int sx = rays->subset[0], sy = rays->subset[1], sw = rays->subset[2], sh = rays->subset[3];
+  const int n = sw * sh;
+  rays->n = n;
+  rays->dir = (float*)malloc(sizeof(float) * 3 * (size_t)n);
+  rays->min_dist = (float*)malloc(sizeof(float) * (size_t)n);
+  rays->max_dist = (float*)malloc(sizeof(float) * (size_t)n);
+  rays->dist = (float*)malloc(sizeof(float) * (size_t)n);
+  rays->rgba = (float*)calloc((size_t)n * 4, sizeof(float)); /* Buffers.at(0).InitConst(0.f) */
+  rays->pixel = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+  for (int a = 0; a < 3; ++a) rays->origin[a] = cam->position[a];
+
+  orc_raygen g;
+  orc_raygen_setup(cam, W, H, &g);
+
+  float inv_pv[16];
+  if (canvas_depth)
+  {
+    float pv[16];
+    orc_projview(cam, W, H, pv);
+    m_inverse(pv, inv_pv);
+  }
+  const float dbl_inv_w = 2.f / (float)W, dbl_inv_h = 2.f / (float)H;
+
+  /* CalcRayStart bounds: SpatialExtent = coords.GetBounds() narrowed to f32 */
+  const float Xmin = (float)bounds[0], Xmax = (float)bounds[1];
+  const float Ymin = (float)bounds[2], Ymax = (float)bounds[3];
+  const float Zmin = (float)bounds[4], Zmax = (float)bounds[5];
+
+  /* RenderOnDevice: meshEpsilon = |extent| * 1e-4 */
+  float ext[3] = { (float)(bounds[1] - bounds[0]), (float)(bounds[3] - bounds[2]),
+                   (float)(bounds[5] - bounds[4]) };
+  const float mag_extent = v_mag(ext);
+  const float mesh_eps = mag_extent * 0.0001f;
+  if (sample_dist <= 0.f) sample_dist = mag_extent / 200.f;
+
+  locator L;
+  locator_init(b, &L);
+
+  /* Sampler ctor */
+  const int64_t color_map_size = lut_size - 1;
+  float inv_delta_scalar = range_min;
+  if ((range_max - range_min) != 0.f) inv_delta_scalar = 1.f / (range_max - range_min);
+
+  const int64_t Nx = b->dims[0], Ny = b->dims[1];
+  const float* o = rays->origin;
+  int64_t total_samples = 0;
+
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : total_samples)
+  for (int idx = 0; idx < n; ++idx)
+  {
+    /* ---- K1 */
+    int i = idx % sw, j = idx / sw;
+    i += sx; j += sy;
+    const int64_t pixel = (int64_t)j * W + i;
+    rays->pixel[idx] = pixel;
+    float d[3];
+    ray_dir(&g, W, H, i, j, d);
+    rays->dir[3 * idx + 0] = d[0]; rays->dir[3 * idx + 1] = d[1]; rays->dir[3 * idx + 2] = d[2];
+    float min_distance = 0.f, max_distance = INFINITY, distance0 = 0.f;
+
+    /* ---- K2: RayMapCanvas */
+    if (canvas_depth)
+    {
+      float pos[4];
+      pos[0] = (float)(pixel % W);
+      pos[1] = (float)(pixel / W);
+      pos[2] = canvas_depth[pixel];
+      pos[3] = 1;
+      pos[0] = pos[0] * dbl_inv_w - 1.f;
+      pos[1] = pos[1] * dbl_inv_h - 1.f;
+      pos[2] = 2.f * pos[2] - 1.f;
+      pos[2] -= 0.00001f;
+      float q[4];
+      m_mulv(inv_pv, pos, q);
+      float p[3] = { q[0] / q[3], q[1] / q[3], q[2] / q[3] };
+      p[0] = p[0] - o[0]; p[1] = p[1] - o[1]; p[2] = p[2] - o[2];
+      max_distance = v_mag(p);
+    }
+
+    /* ---- K3: CalcRayStart */
+    {
+      float invDirx = rcp_safe(d[0]), invDiry = rcp_safe(d[1]), invDirz = rcp_safe(d[2]);
+      float odirx = o[0] * invDirx, odiry = o[1] * invDiry, odirz = o[2] * invDirz;
+      float xmin = Xmin * invDirx - odirx, ymin = Ymin * invDiry - odiry, zmin = Zmin * invDirz - odirz;
+      float xmax = Xmax * invDirx - odirx, ymax = Ymax * invDiry - odiry, zmax = Zmax * invDirz - odirz;
+      min_distance = fmaxf(
+        fmaxf(fmaxf(fminf(ymin, ymax), fminf(xmin, xmax)), fminf(zmin, zmax)), min_distance);
+      float exit_distance = fminf(fminf(fmaxf(ymin, ymax), fmaxf(xmin, xmax)), fmaxf(zmin, zmax));
+      max_distance = fminf(max_distance, exit_distance);
+      if (max_distance < min_distance) min_distance = -1.f;
+      else distance0 = min_distance;
+    }
+    rays->min_dist[idx] = min_distance;
+    rays->max_dist[idx] = max_distance;
+    rays->dist[idx] = distance0;
+
+    /* ---- K4/K5/K6: Sampler */
+    float color[4] = { 0.f, 0.f, 0.f, 0.f };
+    if (min_distance == -1.f) continue; /* buffer stays 0 */
+
+    float p[3];
+    float distance = min_distance + mesh_eps;
+    p[0] = o[0] + distance * d[0]; p[1] = o[1] + distance * d[1]; p[2] = o[2] + distance * d[2];
+    while (!is_inside(&L, p) && distance < max_distance)
+    {
+      distance += sample_dist;
+      p[0] = o[0] + distance * d[0]; p[1] = o[1] + distance * d[1]; p[2] = o[2] + distance * d[2];
+    }
+    float bl[3] = { 0.f, 0.f, 0.f };
+    int new_cell = 1;
+    float tx = 0.f, ty = 0.f, tz = 0.f;
+    float s0 = 0.f, s1m0 = 0.f, s2m3 = 0.f, s3 = 0.f, s4 = 0.f, s5m4 = 0.f, s6m7 = 0.f, s7 = 0.f;
+    float cell_scalar = 0.f;
+    int64_t cell[3] = { 0, 0, 0 };
+    float inv_sp[3] = { 0.f, 0.f, 0.f };
+    int64_t ns = 0;
+
+    while (is_inside(&L, p) && distance < max_distance)
+    {
+      float mint = fminf(tx, fminf(ty, tz));
+      float maxt = fmaxf(tx, fmaxf(ty, tz));
+      if (maxt > 1.f || mint < 0.f) new_cell = 1;
+      if (new_cell)
+      {
+        locate_cell(b, &L, cell, p, inv_sp);
+        cell_min_point(b, cell, bl);
+        if (!b->cell_assoc)
+        {
+          int64_t i0 = (cell[2] * Ny + cell[1]) * Nx + cell[0];
+          int64_t i1 = i0 + 1, i2 = i1 + Nx, i3 = i2 - 1;
+          int64_t i4 = i0 + Nx * Ny, i5 = i4 + 1, i6 = i5 + Nx, i7 = i6 - 1;
+          s0 = fld(b, i0);
+          float s1 = fld(b, i1), s2 = fld(b, i2);
+          s3 = fld(b, i3);
+          s4 = fld(b, i4);
+          float s5 = fld(b, i5), s6 = fld(b, i6);
+          s7 = fld(b, i7);
+          s6m7 = s6 - s7; s5m4 = s5 - s4; s1m0 = s1 - s0; s2m3 = s2 - s3;
+        }
+        else
+        {
+          /* SamplerCellAssoc: Locator::GetCellIndex */
+          int64_t ci = (cell[2] * (Ny - 1) + cell[1]) * (Nx - 1) + cell[0];
+          cell_scalar = fld(b, ci);
+        }
+        tx = (p[0] - bl[0]) * inv_sp[0];
+        ty = (p[1] - bl[1]) * inv_sp[1];
+        tz = (p[2] - bl[2]) * inv_sp[2];
+        new_cell = 0;
+      }
+      float v;
+      if (!b->cell_assoc)
+      {
+        float l76 = s7 + tx * s6m7;
+        float l45 = s4 + tx * s5m4;
+        float ltop = l45 + ty * (l76 - l45);
+        float l01 = s0 + tx * s1m0;
+        float l32 = s3 + tx * s2m3;
+        float lbot = l01 + ty * (l32 - l01);
+        v = lbot + tz * (ltop - lbot);
+      }
+      else
+        v = cell_scalar;
+      v = (v - range_min) * inv_delta_scalar;
+      int64_t ci = (int64_t)(v * (float)color_map_size);
+      if (ci < 0) ci = 0;
+      if (ci > color_map_size) ci = color_map_size;
+      const float* sc = lut + 4 * ci;
+      float alpha = sc[3] * (1.f - color[3]);
+      color[0] = color[0] + sc[0] * alpha;
+      color[1] = color[1] + sc[1] * alpha;
+      color[2] = color[2] + sc[2] * alpha;
+      color[3] = alpha + color[3];
+      ++ns;
+      if (color[3] >= 1.f) break;
+      distance += sample_dist;
+      p[0] = p[0] + sample_dist * d[0];
+      p[1] = p[1] + sample_dist * d[1];
+      p[2] = p[2] + sample_dist * d[2];
+      tx = (p[0] - bl[0]) * inv_sp[0];
+      ty = (p[1] - bl[1]) * inv_sp[1];
+      tz = (p[2] - bl[2]) * inv_sp[2];
+    }
+    total_samples += ns;
+    rays->rgba[4 * idx + 0] = fminf(color[0], 1.f);
+    rays->rgba[4 * idx + 1] = fminf(color[1], 1.f);
+    rays->rgba[4 * idx + 2] = fminf(color[2], 1.f);
+    rays->rgba[4 * idx + 3] = fminf(color[3], 1.f);
+  }
+  rays->n_samples = total_samples;
+}
+
+/* ---- K7: CanvasRayTracer::WriteToCanvas (SurfaceConverter); in-tree mirror
+ * VolumeRenderer.cpp:359-388 (which uses 0.49 instead of 0.5).  canvas in/out. */
+ORC_API void orc_write_to_canvas(const orc_rays* rays, const orc_camera* cam, int W, int H,
+                                 float* canvas_rgba, float* canvas_depth)
+{
+  float pv[16];
+  orc_projview(cam, W, H, pv);
+  const float* o = rays->origin;
+#pragma omp parallel for
+  for (int idx = 0; idx < rays->n; ++idx)
+  {
+    const int64_t pixel = rays->pixel[idx];
+    const float* d = rays->dir + 3 * idx;
+    const float t = rays->dist[idx];
+    float pt[4] = { o[0] + t * d[0], o[1] + t * d[1], o[2] + t * d[2], 1.f }, np[4];
+    m_mulv(pv, pt, np);
+    np[0] = np[0] / np[3]; np[1] = np[1] / np[3]; np[2] = np[2] / np[3];
+    float depth = 0.5f * np[2] + 0.5f;
+    float color[4] = { rays->rgba[4 * idx], rays->rgba[4 * idx + 1], rays->rgba[4 * idx + 2],
+                       rays->rgba[4 * idx + 3] };
+    const float* in = canvas_rgba + 4 * pixel;
+    float alpha = 1.f - color[3];
+    color[0] = color[0] + in[0] * alpha;
+    color[1] = color[1] + in[1] * alpha;
+    color[2] = color[2] + in[2] * alpha;
+    color[3] = in[3] * alpha + color[3];
+    for (int k = 0; k < 4; ++k) color[k] = fminf(1.f, fmaxf(color[k], 0.f));
+    canvas_depth[pixel] = depth;
+    for (int k = 0; k < 4; ++k) canvas_rgba[4 * pixel + k] = color[k];
+  }
+}
+
+/* ---- V8: StructuredWrapper::render partial extraction, VolumeRenderer.cpp:260-283.
+ * Serial, in ray order; depth = rays.MaxDistance.  out must hold rays->n entries. */
+ORC_API int64_t orc_extract_partials(const orc_rays* rays, orc_partial* out)
+{
+  int64_t n = 0;
+  for (int i = 0; i < rays->n; ++i)
+  {
+    float alpha = rays->rgba[4 * i + 3];
+    if (alpha < 0.001f) continue;
+    out[n].rgb[0] = rays->rgba[4 * i + 0];
+    out[n].rgb[1] = rays->rgba[4 * i + 1];
+    out[n].rgb[2] = rays->rgba[4 * i + 2];
+    out[n].alpha = alpha;
+    out[n].pixel_id = (int32_t)rays->pixel[i];
+    out[n].depth = rays->max_dist[i];
+    ++n;
+  }
+  return n;
+}
+
+/* ---- V9: partials_to_canvas, VolumeRenderer.cpp:287-391, including the delta_y-from-ru
+ * quirk at :328. */
+ORC_API void orc_partials_to_canvas(const orc_partial* partials, int64_t n, const orc_camera* cam,
+                                    int width, int height, float* canvas_rgba, float* canvas_depth)
+{
+  float pv[16];
+  orc_projview(cam, width, height, pv);
+  const float* origin = cam->position;
+  float fov_y = cam->fov, fov_x = fov_y;
+  if (width != height)
+  {
+    float fovyRad = fov_y * PI_180F;
+    float verticalDistance = tanf(0.5f * fovyRad);
+    float aspectRatio = (float)width / (float)height;
+    float horizontalDistance = aspectRatio * verticalDistance;
+    float fovxRad = 2.0f * atanf(horizontalDistance);
+    fov_x = fovxRad / PI_180F;
+  }
+  float look[3] = { cam->look_at[0] - origin[0], cam->look_at[1] - origin[1],
+                    cam->look_at[2] - origin[2] };
+  v_normalize(look);
+  const float thx = tanf((fov_x * PI_180F) * .5f);
+  const float thy = tanf((fov_y * PI_180F) * .5f);
+  float ru[3], rv[3];
+  v_cross(look, cam->up, ru);
+  v_normalize(ru);
+  v_cross(ru, look, rv);
+  v_normalize(rv);
+  float dxv[3], dyv[3];
+  for (int k = 0; k < 3; ++k)
+  {
+    dxv[k] = ru[k] * (2 * thx / (float)width);
+    dyv[k] = ru[k] * (2 * thy / (float)height); /* :328 builds delta_y from ru */
+  }
+  if (cam->zoom > 0)
+    for (int k = 0; k < 3; ++k) { dxv[k] = dxv[k] / cam->zoom; dyv[k] = dyv[k] / cam->zoom; }
+#pragma omp parallel for
+  for (int64_t p = 0; p < n; ++p)
+  {
+    const int pixel_id = partials[p].pixel_id;
+    const int i = pixel_id % width, j = pixel_id / width;
+    float dir[3];
+    float fx = (2.f * (float)i - (float)width) / 2.0f, fy = (2.f * (float)j - (float)height) / 2.0f;
+    for (int k = 0; k < 3; ++k) dir[k] = look[k] + dxv[k] * fx + dyv[k] * fy;
+    v_normalize(dir);
+    const float wd = partials[p].depth;
+    float pt[4] = { origin[0] + wd * dir[0], origin[1] + wd * dir[1], origin[2] + wd * dir[2], 1.f };
+    float np[4];
+    m_mulv(pv, pt, np);
+    const float image_depth = 0.5f * (np[2] / np[3]) + 0.49f;
+    float color[4] = { partials[p].rgb[0], partials[p].rgb[1], partials[p].rgb[2],
+                       partials[p].alpha };
+    const float* in = canvas_rgba + 4 * (int64_t)pixel_id;
+    float alpha = 1.f - color[3];
+    color[0] = color[0] + in[0] * alpha;
+    color[1] = color[1] + in[1] * alpha;
+    color[2] = color[2] + in[2] * alpha;
+    color[3] = in[3] * alpha + color[3];
+    for (int k = 0; k < 4; ++k) canvas_rgba[4 * (int64_t)pixel_id + k] = color[k];
+    canvas_depth[pixel_id] = image_depth;
+  }
+}
+
+/* ---- V3: CorrectOpacity, VolumeRenderer.cpp:448-466 (per alpha control point, f64) */
+ORC_API double orc_correct_opacity(double alpha, float samples)
+{
+  const float correction_scalar = 10.f; /* VTKH_OPACITY_CORRECTION, VolumeRenderer.cpp:25 */
+  float ratio = correction_scalar / samples;
+  return 1. - pow((1. - alpha), (double)ratio);
+}
+
+/* ---- V4: sample distance, VolumeRenderer.cpp:606-611 (global bounds, f32) */
+ORC_API float orc_sample_distance(const double gb[6], float samples)
+{
+  float ext[3] = { (float)(gb[1] - gb[0]), (float)(gb[3] - gb[2]), (float)(gb[5] - gb[4]) };
+  return v_mag(ext) / samples;
+}
+
+/* ---- V7: FindMinDepth + DepthSort, VolumeRenderer.cpp:637-650,690-831.
+ * domain_bounds: n x 6 f64 in (rank, domain) order; out_order[i] = visibility index.
+ * std::sort is unstable on ties; this restatement uses a stable sort (ties keep
+ * (rank,domain) order) -- documented tie-break, SURVEY D7. */
+ORC_API void orc_visibility_order(const double* domain_bounds, int n, const orc_camera* cam,
+                                  int* out_order, float* out_depths)
+{
+  float* depth = (float*)malloc(sizeof(float) * (size_t)n);
+  int* idx = (int*)malloc(sizeof(int) * (size_t)n);
+  for (int i = 0; i < n; ++i)
+  {
+    const double* b = domain_bounds + 6 * i;
+    /* center in f64, narrowed per component to f32 (stored back into an f64 vec, then
+     * subtracted from the f32 position: the arithmetic is f64 with f32-valued operands,
+     * Magnitude on Vec<Float64,3>, narrowed to f32 at :648) */
+    double c[3] = { (double)(float)((b[0] + b[1]) / 2.0), (double)(float)((b[2] + b[3]) / 2.0),
+                    (double)(float)((b[4] + b[5]) / 2.0) };
+    double dx = c[0] - (double)cam->position[0];
+    double dy = c[1] - (double)cam->position[1];
+    double dz = c[2] - (double)cam->position[2];
+    depth[i] = (float)sqrt(dx * dx + dy * dy + dz * dz);
+    idx[i] = i;
+  }
+  /* stable insertion sort ascending by depth */
+  for (int i = 1; i < n; ++i)
+  {
+    int k = idx[i];
+    int j = i - 1;
+    while (j >= 0 && depth[idx[j]] > depth[k]) { idx[j + 1] = idx[j]; --j; }
+    idx[j + 1] = k;
+  }
+  for (int i = 0; i < n; ++i) out_order[idx[i]] = i;
+  if (out_depths) memcpy(out_depths, depth, sizeof(float) * (size_t)n);
+  free(depth); free(idx);
+}
+
+ORC_API int orc_num_threads(void)
+{
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}

@@ -1,0 +1,50 @@
+"""Pin the ray-cast oracle (oracle/raycast_oracle.c) against the reference's own golden images.
+
+The goldens are whole Ascent renders with annotations burned in, so the comparison runs over
+hand-picked annotation-free crops (tests/golden/make_golden.py) with the reference's own metric:
+a pixel differs if any channel is off by more than 4/255 (ascent_png_compare.cpp:35,138-141),
+and the test fails if the differing fraction exceeds the tolerance the reference test used
+(check_test_image default 0.001; 0.01 where the test passes 0.01f)."""
+import os
+
+import numpy as np
+import pytest
+
+import scenes
+
+
+def crop_stats(mine, gold, rects):
+    bad = tot = 0
+    for (y0, y1, x0, x1) in rects:
+        d = np.abs(mine[y0:y1, x0:x1, :3].astype(int) - gold[y0:y1, x0:x1].astype(int)).max(axis=2)
+        bad += int((d > 4).sum())
+        tot += d.size
+    return bad / tot
+
+
+@pytest.mark.parametrize("which,name,tol", [(0, "render_0100", 0.001), (1, "render_1100", 0.01)])
+def test_multi_render_golden(golden_dir, which, name, tol):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    sc = scenes.multi_render_scene(which)
+    _, _, canvas = scenes.oracle_path_a(sc)
+    mine = scenes.png_bytes(canvas, sc["W"], sc["H"])
+    assert crop_stats(mine, g["rgb"], g["rects"]) <= tol
+
+
+def test_mpi_volume_golden(golden_dir):
+    """2-rank path A: rectilinear sampler, visibility order, uint8 ordered fold."""
+    g = np.load(os.path.join(golden_dir, "tout_render_mpi_3d_diy_volume100.npz"))
+    sc = scenes.mpi_volume_scene()
+    _, _, canvas = scenes.oracle_path_a(sc)
+    mine = scenes.png_bytes(canvas, sc["W"], sc["H"])
+    assert crop_stats(mine, g["rgb"], g["rects"]) <= 0.01
+
+
+def test_default_camera_geometry():
+    """SURVEY K0 corroboration: in render_0100.png the cube's front face spans
+    10/(24.64*tan30) = 0.703 of the image -> subset rect of the 20^3 braid at 512^2."""
+    from oracle import oracle as O
+    sc = scenes.multi_render_scene(0)
+    sx, sy, sw, sh = O.find_subset(sc["cam"], 512, 512, sc["bounds"])
+    assert abs(sw / 512.0 - 0.703) < 0.01 and abs(sh / 512.0 - 0.703) < 0.01
+    assert abs((sx + sw / 2) - 256) <= 1 and abs((sy + sh / 2) - 256) <= 1
