@@ -1,0 +1,392 @@
+"""ctypes binding of libvr_b200.so (include/vr_b200.h).
+
+The product path has no CPU fallback: if the shared object is missing or no B200 is visible,
+loading / vr_create raises.  Nothing here imports the oracle.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvr_b200.so")
+
+VR_OK = 0
+VR_F32, VR_F64 = 0, 1
+VR_POINT, VR_CELL = 0, 1
+VR_HOST, VR_DEVICE = 0, 1
+IPC_HANDLE_BYTES = 64
+
+# every symbol include/vr_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "vr_create", "vr_destroy", "vr_last_error", "vr_set_stream", "vr_synchronize",
+    "vr_kernel_launches", "vr_block_uniform", "vr_block_rectilinear", "vr_block_free",
+    "vr_block_bounds", "vr_set_tf", "vr_canvas_clear", "vr_canvas_upload", "vr_canvas_download",
+    "vr_canvas_ptrs", "vr_trace_to_canvas", "vr_render_image", "vr_partials_begin",
+    "vr_trace_to_partials", "vr_partials_count", "vr_partials_download", "vr_render_partials",
+    "vr_free", "vr_image_from_canvas", "vr_image_download", "vr_fold_images_dev",
+    "vr_composite_images", "vr_zbuffer_composite_dev", "vr_image_to_canvas_dev",
+    "vr_partials_composite", "vr_partials_to_canvas", "vr_composite_partials", "vr_comm_init",
+    "vr_comm_connect", "vr_comm_composite_images", "vr_image_result_download",
+    "vr_image_result_to_canvas", "vr_comm_composite_partials", "vr_image_ptrs",
+    "vr_sample_distance", "vr_visibility_order", "vr_find_subset", "vr_synth_braid_dev",
+]
+
+
+class VRError(RuntimeError):
+    """Raised for any non-zero vr_status (the vtk-h wrapper would throw vtkh::Error)."""
+
+
+class CameraStruct(C.Structure):
+    """vr_camera"""
+    _fields_ = [("position", C.c_float * 3), ("look_at", C.c_float * 3), ("up", C.c_float * 3),
+                ("fov", C.c_float), ("zoom", C.c_float), ("xpan", C.c_float), ("ypan", C.c_float),
+                ("near_plane", C.c_float), ("far_plane", C.c_float)]
+
+
+PARTIAL_DTYPE = np.dtype([("pixel_id", "<i4"), ("depth", "<f4"), ("rgb", "<f4", (3,)),
+                          ("alpha", "<f4")])
+
+_lib = None
+
+
+def load():
+    """Load the shared object (building is __graft_entry__.build()'s / ascent_b200.build's job)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VRError("libvr_b200.so is not built (python -m ascent_b200.build); "
+                      "there is no CPU fallback for the volume-render path")
+    lib = C.CDLL(LIB_PATH)
+    vp, ip, fp, dp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_double)
+    cam = C.POINTER(CameraStruct)
+    sz = C.c_size_t
+    sig = {
+        "vr_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "vr_destroy": (None, [vp]),
+        "vr_last_error": (C.c_char_p, [vp]),
+        "vr_set_stream": (C.c_int, [vp, vp]),
+        "vr_synchronize": (C.c_int, [vp]),
+        "vr_kernel_launches": (C.c_uint64, [vp]),
+        "vr_block_uniform": (C.c_int, [vp, C.c_int, ip, fp, fp, vp, C.c_int, C.c_int, C.c_int]),
+        "vr_block_rectilinear": (C.c_int, [vp, C.c_int, ip, dp, dp, dp, vp, C.c_int, C.c_int, C.c_int]),
+        "vr_block_free": (C.c_int, [vp, C.c_int]),
+        "vr_block_bounds": (C.c_int, [vp, C.c_int, dp]),
+        "vr_set_tf": (C.c_int, [vp, fp, C.c_int]),
+        "vr_canvas_clear": (C.c_int, [vp, C.c_int, C.c_int]),
+        "vr_canvas_upload": (C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
+        "vr_canvas_download": (C.c_int, [vp, vp, vp]),
+        "vr_canvas_ptrs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
+        "vr_trace_to_canvas": (C.c_int, [vp, C.c_int, cam, C.c_float, C.c_float, C.c_float, C.c_int]),
+        "vr_render_image": (C.c_int, [vp, C.c_int, cam, C.c_int, C.c_int, C.c_float, C.c_float,
+                                      C.c_float, vp, vp]),
+        "vr_partials_begin": (C.c_int, [vp, C.c_int, C.c_int]),
+        "vr_trace_to_partials": (C.c_int, [vp, C.c_int, cam, C.c_float, C.c_float, C.c_float, C.c_int]),
+        "vr_partials_count": (C.c_int, [vp, C.POINTER(sz)]),
+        "vr_partials_download": (C.c_int, [vp, vp, sz, C.POINTER(sz)]),
+        "vr_render_partials": (C.c_int, [vp, C.c_int, cam, C.c_int, C.c_int, C.c_float, C.c_float,
+                                         C.c_float, vp, C.POINTER(vp), C.POINTER(sz)]),
+        "vr_free": (None, [vp]),
+        "vr_image_from_canvas": (C.c_int, [vp]),
+        "vr_image_download": (C.c_int, [vp, vp, vp]),
+        "vr_fold_images_dev": (C.c_int, [vp, vp, vp, sz, ip, C.c_int, sz, vp, vp]),
+        "vr_composite_images": (C.c_int, [vp, vp, vp, ip, C.c_int, C.c_int, C.c_int, vp, vp]),
+        "vr_zbuffer_composite_dev": (C.c_int, [vp, vp, vp, vp, vp, sz]),
+        "vr_image_to_canvas_dev": (C.c_int, [vp, vp, vp]),
+        "vr_partials_composite": (C.c_int, [vp]),
+        "vr_partials_to_canvas": (C.c_int, [vp, cam]),
+        "vr_composite_partials": (C.c_int, [vp, vp, sz, C.c_int, C.c_int, vp, C.POINTER(sz)]),
+        "vr_comm_init": (C.c_int, [vp, C.c_int, C.c_int, sz, sz, vp]),
+        "vr_comm_connect": (C.c_int, [vp, vp]),
+        "vr_comm_composite_images": (C.c_int, [vp, ip]),
+        "vr_image_result_download": (C.c_int, [vp, vp, vp]),
+        "vr_image_result_to_canvas": (C.c_int, [vp]),
+        "vr_comm_composite_partials": (C.c_int, [vp]),
+        "vr_image_ptrs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
+        "vr_sample_distance": (C.c_float, [dp, C.c_float]),
+        "vr_visibility_order": (None, [dp, C.c_int, cam, ip]),
+        "vr_find_subset": (None, [cam, C.c_int, C.c_int, dp, ip]),
+        "vr_synth_braid_dev": (C.c_int, [vp, vp, C.c_int, ip, ip, ip]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _i3(v):
+    return (C.c_int * 3)(*[int(x) for x in v])
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(x) for x in v])
+
+
+def _d6(v):
+    return (C.c_double * 6)(*[float(x) for x in v])
+
+
+def as_camera(cam):
+    """Accept a CameraStruct, any ctypes struct with the same layout (the oracle's), or an object
+    with a ``to_struct()`` method."""
+    if isinstance(cam, CameraStruct):
+        return cam
+    if hasattr(cam, "to_struct"):
+        return cam.to_struct()
+    out = CameraStruct()
+    C.memmove(C.byref(out), C.byref(cam), C.sizeof(CameraStruct))
+    return out
+
+
+def sample_distance(global_bounds, samples):
+    return float(load().vr_sample_distance(_d6(global_bounds), C.c_float(samples)))
+
+
+def visibility_order(domain_bounds, cam):
+    db = np.ascontiguousarray(domain_bounds, np.float64).reshape(-1, 6)
+    out = np.zeros(db.shape[0], np.int32)
+    load().vr_visibility_order(db.ctypes.data_as(C.POINTER(C.c_double)), db.shape[0],
+                               C.byref(as_camera(cam)), out.ctypes.data_as(C.POINTER(C.c_int)))
+    return out
+
+
+def find_subset(cam, W, H, bounds):
+    out = (C.c_int * 4)()
+    load().vr_find_subset(C.byref(as_camera(cam)), W, H, _d6(bounds), out)
+    return tuple(out)
+
+
+class Context:
+    """One vr_ctx == one GPU.  Thin, explicit wrapper: one method per C entry point."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        st = self.lib.vr_create(int(device), C.byref(h))
+        if st != VR_OK:
+            raise VRError(self.lib.vr_last_error(None).decode())
+        self.h = h
+        self.device = device
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st):
+        if st != VR_OK:
+            raise VRError(self.lib.vr_last_error(self.h).decode())
+
+    # -- context
+    def set_stream(self, cuda_stream):
+        self._ck(self.lib.vr_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._ck(self.lib.vr_synchronize(self.h))
+
+    def kernel_launches(self):
+        return int(self.lib.vr_kernel_launches(self.h))
+
+    # -- blocks
+    def block_uniform(self, block_id, dims, origin, spacing, field, assoc=VR_POINT, device_ptr=None,
+                      dtype=None):
+        if device_ptr is not None:
+            ptr, dt, where = C.c_void_p(device_ptr), dtype, VR_DEVICE
+        else:
+            field = np.ascontiguousarray(field)
+            assert field.dtype in (np.float32, np.float64), "fields are f32 or f64"
+            ptr, dt, where = C.c_void_p(field.ctypes.data), (VR_F64 if field.dtype == np.float64 else VR_F32), VR_HOST
+        self._ck(self.lib.vr_block_uniform(self.h, block_id, _i3(dims), _f3(origin), _f3(spacing), ptr,
+                                           dt, assoc, where))
+
+    def block_rectilinear(self, block_id, dims, axes, field, assoc=VR_POINT, device_ptr=None,
+                          dtype=None):
+        ax = [np.ascontiguousarray(a, np.float64) for a in axes]
+        if device_ptr is not None:
+            ptr, dt, where = C.c_void_p(device_ptr), dtype, VR_DEVICE
+        else:
+            field = np.ascontiguousarray(field)
+            assert field.dtype in (np.float32, np.float64), "fields are f32 or f64"
+            ptr, dt, where = C.c_void_p(field.ctypes.data), (VR_F64 if field.dtype == np.float64 else VR_F32), VR_HOST
+        dpp = C.POINTER(C.c_double)
+        self._ck(self.lib.vr_block_rectilinear(self.h, block_id, _i3(dims), ax[0].ctypes.data_as(dpp),
+                                               ax[1].ctypes.data_as(dpp), ax[2].ctypes.data_as(dpp),
+                                               ptr, dt, assoc, where))
+
+    def block_from_domain(self, block_id, dom):
+        assoc = VR_CELL if dom.get("assoc") == "cell" else VR_POINT
+        if dom["kind"] == "uniform":
+            self.block_uniform(block_id, dom["dims"], dom["origin"], dom["spacing"], dom["field"], assoc)
+        else:
+            self.block_rectilinear(block_id, dom["dims"], dom["axes"], dom["field"], assoc)
+
+    def block_free(self, block_id):
+        self._ck(self.lib.vr_block_free(self.h, block_id))
+
+    def block_bounds(self, block_id):
+        out = (C.c_double * 6)()
+        self._ck(self.lib.vr_block_bounds(self.h, block_id, out))
+        return np.array(out[:], np.float64)
+
+    # -- transfer function
+    def set_tf(self, lut):
+        lut = np.ascontiguousarray(lut, np.float32)
+        assert lut.ndim == 2 and lut.shape[1] == 4
+        self._ck(self.lib.vr_set_tf(self.h, lut.ctypes.data_as(C.POINTER(C.c_float)), lut.shape[0]))
+
+    # -- canvas
+    def canvas_clear(self, W, H):
+        self._ck(self.lib.vr_canvas_clear(self.h, W, H))
+
+    def canvas_upload(self, W, H, rgba, depth):
+        rgba = np.ascontiguousarray(rgba, np.float32)
+        depth = np.ascontiguousarray(depth, np.float32)
+        self._ck(self.lib.vr_canvas_upload(self.h, W, H, rgba.ctypes.data, depth.ctypes.data))
+
+    def canvas_download(self, W, H, rgba=None, depth=None):
+        rgba = np.empty((H * W, 4), np.float32) if rgba is None else rgba
+        depth = np.empty(H * W, np.float32) if depth is None else depth
+        self._ck(self.lib.vr_canvas_download(self.h, rgba.ctypes.data, depth.ctypes.data))
+        return rgba, depth
+
+    def canvas_ptrs(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.vr_canvas_ptrs(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # -- path A
+    def trace_to_canvas(self, block_id, cam, sample_dist, rmin, rmax, use_canvas_depth=False):
+        self._ck(self.lib.vr_trace_to_canvas(self.h, block_id, C.byref(as_camera(cam)), sample_dist,
+                                             rmin, rmax, int(use_canvas_depth)))
+
+    def render_image(self, block_id, cam, W, H, sample_dist, rmin, rmax, rgba, depth):
+        assert rgba.dtype == np.float32 and depth.dtype == np.float32
+        self._ck(self.lib.vr_render_image(self.h, block_id, C.byref(as_camera(cam)), W, H, sample_dist,
+                                          rmin, rmax, rgba.ctypes.data, depth.ctypes.data))
+
+    # -- path B
+    def partials_begin(self, W, H):
+        self._ck(self.lib.vr_partials_begin(self.h, W, H))
+
+    def trace_to_partials(self, block_id, cam, sample_dist, rmin, rmax, use_canvas_depth=False):
+        self._ck(self.lib.vr_trace_to_partials(self.h, block_id, C.byref(as_camera(cam)), sample_dist,
+                                               rmin, rmax, int(use_canvas_depth)))
+
+    def partials_count(self):
+        n = C.c_size_t()
+        self._ck(self.lib.vr_partials_count(self.h, C.byref(n)))
+        return int(n.value)
+
+    def partials_download(self):
+        n = self.partials_count()
+        out = np.zeros(max(n, 1), PARTIAL_DTYPE)
+        got = C.c_size_t()
+        self._ck(self.lib.vr_partials_download(self.h, out.ctypes.data, n, C.byref(got)))
+        return out[:got.value]
+
+    def render_partials(self, block_id, cam, W, H, sample_dist, rmin, rmax, depth_in=None):
+        p, n = C.c_void_p(), C.c_size_t()
+        dptr = None if depth_in is None else np.ascontiguousarray(depth_in, np.float32).ctypes.data
+        self._ck(self.lib.vr_render_partials(self.h, block_id, C.byref(as_camera(cam)), W, H,
+                                             sample_dist, rmin, rmax, dptr, C.byref(p), C.byref(n)))
+        out = np.zeros(n.value, PARTIAL_DTYPE)
+        if n.value:
+            C.memmove(out.ctypes.data, p.value, n.value * 24)
+        self.lib.vr_free(p)
+        return out
+
+    # -- image compositing
+    def image_from_canvas(self):
+        self._ck(self.lib.vr_image_from_canvas(self.h))
+
+    def image_download(self, W, H):
+        rgba = np.empty((H * W, 4), np.uint8)
+        depth = np.empty(H * W, np.float32)
+        self._ck(self.lib.vr_image_download(self.h, rgba.ctypes.data, depth.ctypes.data))
+        return rgba, depth
+
+    def image_ptrs(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.vr_image_ptrs(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def fold_images_dev(self, rgba_ptr, depth_ptr, layer_stride_px, vis_order, n_pixels, out_rgba_ptr,
+                        out_depth_ptr):
+        vo = np.ascontiguousarray(vis_order, np.int32)
+        self._ck(self.lib.vr_fold_images_dev(self.h, rgba_ptr, depth_ptr, layer_stride_px,
+                                             vo.ctypes.data_as(C.POINTER(C.c_int)), vo.size, n_pixels,
+                                             out_rgba_ptr, out_depth_ptr))
+
+    def composite_images(self, rgba, depth, vis_order, W, H):
+        rgba = np.ascontiguousarray(rgba, np.float32)
+        depth = np.ascontiguousarray(depth, np.float32)
+        vo = np.ascontiguousarray(vis_order, np.int32)
+        out = np.empty((H * W, 4), np.uint8)
+        od = np.empty(H * W, np.float32)
+        self._ck(self.lib.vr_composite_images(self.h, rgba.ctypes.data, depth.ctypes.data,
+                                              vo.ctypes.data_as(C.POINTER(C.c_int)), vo.size, W, H,
+                                              out.ctypes.data, od.ctypes.data))
+        return out, od
+
+    def zbuffer_composite_dev(self, front_rgba, front_depth, rgba, depth, n_pixels):
+        self._ck(self.lib.vr_zbuffer_composite_dev(self.h, front_rgba, front_depth, rgba, depth, n_pixels))
+
+    def image_to_canvas_dev(self, rgba_ptr, depth_ptr):
+        self._ck(self.lib.vr_image_to_canvas_dev(self.h, rgba_ptr, depth_ptr))
+
+    # -- partial compositing
+    def partials_composite(self):
+        self._ck(self.lib.vr_partials_composite(self.h))
+
+    def partials_to_canvas(self, cam):
+        self._ck(self.lib.vr_partials_to_canvas(self.h, C.byref(as_camera(cam))))
+
+    def composite_partials(self, partials, W, H):
+        p = np.ascontiguousarray(partials)
+        assert p.dtype == PARTIAL_DTYPE
+        out = np.zeros(max(p.size, 1), PARTIAL_DTYPE)
+        n = C.c_size_t()
+        self._ck(self.lib.vr_composite_partials(self.h, p.ctypes.data, p.size, W, H, out.ctypes.data,
+                                                C.byref(n)))
+        return out[:n.value]
+
+    # -- multi-GPU
+    def comm_init(self, rank, size, max_pixels, max_partials=0):
+        h = (C.c_ubyte * IPC_HANDLE_BYTES)()
+        self._ck(self.lib.vr_comm_init(self.h, rank, size, max_pixels, max_partials, h))
+        return bytes(h)
+
+    def comm_connect(self, all_handles):
+        buf = (C.c_ubyte * len(all_handles)).from_buffer_copy(all_handles)
+        self._ck(self.lib.vr_comm_connect(self.h, buf))
+
+    def comm_composite_images(self, vis_order):
+        vo = np.ascontiguousarray(vis_order, np.int32)
+        self._ck(self.lib.vr_comm_composite_images(self.h, vo.ctypes.data_as(C.POINTER(C.c_int))))
+
+    def image_result_download(self, W, H):
+        rgba = np.empty((H * W, 4), np.uint8)
+        depth = np.empty(H * W, np.float32)
+        self._ck(self.lib.vr_image_result_download(self.h, rgba.ctypes.data, depth.ctypes.data))
+        return rgba, depth
+
+    def image_result_to_canvas(self):
+        self._ck(self.lib.vr_image_result_to_canvas(self.h))
+
+    def comm_composite_partials(self):
+        self._ck(self.lib.vr_comm_composite_partials(self.h))
+
+    # -- bench input
+    def synth_braid_dev(self, dev_ptr, dtype, n, start, glob):
+        self._ck(self.lib.vr_synth_braid_dev(self.h, C.c_void_p(dev_ptr), dtype, _i3(n), _i3(start),
+                                             _i3(glob)))

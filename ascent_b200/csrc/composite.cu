@@ -1,0 +1,491 @@
+// composite.cu -- sort-last compositing kernels (single device) for sm_100a.
+//
+// Path A (uint8 images): Image::Init quantisation, the visibility-ordered truncating-uint8 fold
+// of ImageCompositor::Blend/OrderedComposite, ZBufferComposite and ImageToCanvas
+// (src/libs/vtkh/compositing/Image.hpp:80-113, ImageCompositor.hpp:15-86,
+//  src/libs/vtkh/rendering/Renderer.cpp:265-283).
+// Path B (float partials): PartialCompositor::composite_partials
+// (src/libs/vtkh/compositing/PartialCompositor.cpp:329-488) re-thought for the GPU: the
+// reference's serial std::sort over (pixel, depth) becomes a counting sort by pixel id
+// (histogram -> exclusive scan -> scatter) followed by a per-pixel insertion sort on depth and
+// the front-to-back VolumePartial::blend fold (VolumePartial.hpp:86-95), one thread per pixel.
+//
+// All of these are HBM-streaming integer/byte kernels: 16-byte vector loads/stores, grids sized
+// in multiples of the SM count, no shared-memory staging needed (no reuse).
+//
+// Compiled with --fmad=false: the float fold must round like the reference's scalar code.
+#include "vr_internal.h"
+
+namespace vr
+{
+namespace
+{
+
+constexpr int kT = 256;
+
+inline int grid_for(size_t work_items, int per_block, int max_blocks = 148 * 16)
+{
+  size_t b = (work_items + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > (size_t)max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+// ---------------------------------------------------------------- canvas clear
+__global__ void canvas_clear_kernel(float4* rgba, float* depth, size_t n)
+{
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    rgba[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    depth[i] = 1.001f; // VTKM_DEFAULT_CANVAS_DEPTH
+  }
+}
+
+// ---------------------------------------------------------------- C1 Image::Init
+__device__ __forceinline__ unsigned char f2uc(float c)
+{
+  // static_cast<unsigned char>(c * 255.f) on x86: cvttss2si then low byte
+  return (unsigned char)(__float2int_rz(c * 255.f) & 0xff);
+}
+__global__ void quantize_kernel(const float4* __restrict__ rgba, const float* __restrict__ depth,
+                                size_t n, uchar4* __restrict__ out, float* __restrict__ out_depth)
+{
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    const float4 c = rgba[i];
+    out[i] = make_uchar4(f2uc(c.x), f2uc(c.y), f2uc(c.z), f2uc(c.w));
+    float d = depth[i];
+    d = d < 0 ? fabsf(d) : d; // vtk-h rule, Image.hpp:110
+    out_depth[i] = d;
+  }
+}
+
+// ---------------------------------------------------------------- C2 ordered fold
+struct FoldOrder
+{
+  int layer[64];
+};
+
+__device__ __forceinline__ unsigned blend_u8x4(unsigned front, unsigned back)
+{
+  const unsigned opacity = 255u - (front >> 24);
+  unsigned r = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+  {
+    const unsigned f = (front >> (8 * c)) & 0xffu;
+    const unsigned b = (back >> (8 * c)) & 0xffu;
+    const unsigned v = (f + ((opacity * b / 255u) & 0xffu)) & 0xffu; // wrapping uint8 +=
+    r |= v << (8 * c);
+  }
+  return r;
+}
+__device__ __forceinline__ float std_min(float a, float b) { return (b < a) ? b : a; }
+__device__ __forceinline__ float blend_depth(float f, float b)
+{
+  const float d1 = std_min(f, 1.001f), d2 = std_min(b, 1.001f);
+  return std_min(d1, d2);
+}
+
+// 4 pixels per thread: one 16-byte load per layer for colour, one for depth
+__global__ void fold_images_kernel(const uint4* __restrict__ rgba, const float4* __restrict__ depth,
+                                   size_t layer_stride4, const __grid_constant__ FoldOrder ord,
+                                   int n_layers, size_t n4, uint4* __restrict__ out,
+                                   float4* __restrict__ out_depth)
+{
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
+  {
+    uint4 f = __ldg(rgba + (size_t)ord.layer[0] * layer_stride4 + i);
+    float4 fd = __ldg(depth + (size_t)ord.layer[0] * layer_stride4 + i);
+    for (int l = 1; l < n_layers; ++l)
+    {
+      const uint4 b = __ldg(rgba + (size_t)ord.layer[l] * layer_stride4 + i);
+      const float4 bd = __ldg(depth + (size_t)ord.layer[l] * layer_stride4 + i);
+      f.x = blend_u8x4(f.x, b.x); f.y = blend_u8x4(f.y, b.y);
+      f.z = blend_u8x4(f.z, b.z); f.w = blend_u8x4(f.w, b.w);
+      fd.x = blend_depth(fd.x, bd.x); fd.y = blend_depth(fd.y, bd.y);
+      fd.z = blend_depth(fd.z, bd.z); fd.w = blend_depth(fd.w, bd.w);
+    }
+    out[i] = f;
+    out_depth[i] = fd;
+  }
+}
+// scalar tail / unaligned fallback
+__global__ void fold_images_scalar_kernel(const unsigned* __restrict__ rgba,
+                                          const float* __restrict__ depth, size_t layer_stride,
+                                          const __grid_constant__ FoldOrder ord, int n_layers,
+                                          size_t begin, size_t n, unsigned* __restrict__ out,
+                                          float* __restrict__ out_depth)
+{
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    unsigned f = rgba[(size_t)ord.layer[0] * layer_stride + i];
+    float fd = depth[(size_t)ord.layer[0] * layer_stride + i];
+    for (int l = 1; l < n_layers; ++l)
+    {
+      f = blend_u8x4(f, rgba[(size_t)ord.layer[l] * layer_stride + i]);
+      fd = blend_depth(fd, depth[(size_t)ord.layer[l] * layer_stride + i]);
+    }
+    out[i] = f;
+    out_depth[i] = fd;
+  }
+}
+
+// ---------------------------------------------------------------- C4 z-buffer select
+__global__ void zbuffer_kernel(unsigned* __restrict__ front, float* __restrict__ fdepth,
+                               const unsigned* __restrict__ img, const float* __restrict__ depth,
+                               size_t n)
+{
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    const float d = depth[i];
+    if (fdepth[i] < d) continue; // ImageCompositor.hpp:63-66
+    fdepth[i] = d;
+    front[i] = img[i];
+  }
+}
+
+// ---------------------------------------------------------------- V10 ImageToCanvas
+__global__ void image_to_canvas_kernel(const uchar4* __restrict__ rgba,
+                                       const float* __restrict__ depth, size_t n,
+                                       float4* __restrict__ canvas, float* __restrict__ cdepth)
+{
+  const float one_over_255 = 1.f / 255.f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    const uchar4 c = rgba[i];
+    canvas[i] = make_float4((float)c.x * one_over_255, (float)c.y * one_over_255,
+                            (float)c.z * one_over_255, (float)c.w * one_over_255);
+    cdepth[i] = depth[i];
+  }
+}
+
+// ---------------------------------------------------------------- synthetic braid (bench input)
+template <typename T>
+__global__ void braid_kernel(T* out, int nx, int ny, int nz, int i0, int j0, int k0, double dx,
+                             double dy, double dz)
+{
+  const double PI = 3.14159265359;
+  const size_t n = (size_t)nx * ny * nz;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride)
+  {
+    const int i = (int)(idx % nx), j = (int)((idx / nx) % ny), k = (int)(idx / ((size_t)nx * ny));
+    const double cx = ((i0 + i) * dx) + (2.0 * PI);
+    const double cy = ((j0 + j) * dy) - PI;
+    const double cz = ((k0 + k) * dz) - (1.5 * PI);
+    double cv = sin(cx) + sin(cy) + 2 * cos(sqrt((cx * cx) / 2.0 + cy * cy) / .75) +
+      4 * cos(cx * cy / 4.0);
+    cv += sin(cz) + 1.5 * cos(sqrt(cx * cx + cy * cy + cz * cz) / .75);
+    out[idx] = (T)cv;
+  }
+}
+
+// ---------------------------------------------------------------- P4 partial composite
+__global__ void px_count_kernel(const vr_partial* __restrict__ p, size_t n, int* __restrict__ cnt)
+{
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    atomicAdd(cnt + p[i].pixel_id, 1);
+}
+
+// exclusive scan, three phases, 2048 elements per block
+constexpr int kScanT = 256, kScanPer = 8, kScanTile = kScanT * kScanPer;
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total)
+{
+  __shared__ int warp_sums[kScanT / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[w] = inc;
+  __syncthreads();
+  if (w == 0)
+  {
+    int s = lane < kScanT / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < kScanT / 32; o <<= 1)
+    {
+      const int t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    if (lane < kScanT / 32) warp_sums[lane] = s;
+  }
+  __syncthreads();
+  const int base = w ? warp_sums[w - 1] : 0;
+  *total = warp_sums[kScanT / 32 - 1];
+  __syncthreads();
+  return base + inc - v;
+}
+__global__ void scan_reduce_kernel(const int* __restrict__ in, size_t n, int* __restrict__ block_sums)
+{
+  const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanPer;
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanPer; ++k)
+    if (base + k < n) s += in[base + k];
+  int total;
+  block_exclusive_scan(s, &total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void scan_blocks_kernel(int* block_sums, int nb)
+{
+  // single block, serial over chunks of kScanT
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b = 0; b < nb; b += kScanT)
+  {
+    const int i = b + threadIdx.x;
+    const int v = i < nb ? block_sums[i] : 0;
+    int total;
+    const int ex = block_exclusive_scan(v, &total);
+    if (i < nb) block_sums[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += total;
+    __syncthreads();
+  }
+}
+__global__ void scan_apply_kernel(const int* __restrict__ in, size_t n,
+                                  const int* __restrict__ block_sums, int* __restrict__ out)
+{
+  const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanPer;
+  int v[kScanPer];
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanPer; ++k)
+  {
+    v[k] = base + k < n ? in[base + k] : 0;
+    s += v[k];
+  }
+  int total;
+  int ex = block_exclusive_scan(s, &total) + block_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kScanPer; ++k)
+  {
+    if (base + k < n) out[base + k] = ex;
+    ex += v[k];
+  }
+}
+
+__global__ void px_scatter_kernel(const vr_partial* __restrict__ p, size_t n,
+                                  const int* __restrict__ off, int* __restrict__ fill,
+                                  int* __restrict__ sorted)
+{
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    const int px = p[i].pixel_id;
+    const int slot = off[px] + atomicAdd(fill + px, 1);
+    sorted[slot] = (int)i;
+  }
+}
+
+__device__ __forceinline__ void partial_blend(vr_partial& a, const vr_partial& o)
+{
+  if (a.alpha >= 1.f || o.alpha == 0.f) return;
+  const float opacity = (1.f - a.alpha);
+  a.rgb[0] += opacity * o.rgb[0];
+  a.rgb[1] += opacity * o.rgb[1];
+  a.rgb[2] += opacity * o.rgb[2];
+  a.alpha += opacity * o.alpha;
+  a.alpha = a.alpha > 1.f ? 1.f : a.alpha;
+}
+
+// one thread per pixel: order the pixel's segment by (depth, list index) -- the (pixel, depth)
+// key of VolumePartial::operator< with list order as the documented tie-break -- then fold.
+__global__ void px_fold_kernel(const vr_partial* __restrict__ p, size_t n_pixels,
+                               const int* __restrict__ cnt, const int* __restrict__ off,
+                               int* __restrict__ sorted, vr_partial* __restrict__ out,
+                               unsigned long long* __restrict__ out_count)
+{
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n_pixels; base += stride)
+  {
+    const size_t px = base + threadIdx.x;
+    const int c = px < n_pixels ? cnt[px] : 0;
+    vr_partial result;
+    if (c > 0)
+    {
+      int* seg = sorted + off[px];
+      // insertion sort of the index segment (segments are short: depth complexity of the scene)
+      for (int a = 1; a < c; ++a)
+      {
+        const int ia = seg[a];
+        const float da = p[ia].depth;
+        int b = a - 1;
+        while (b >= 0)
+        {
+          const int ib = seg[b];
+          const float db = p[ib].depth;
+          if (db > da || (db == da && ib > ia)) { seg[b + 1] = ib; --b; }
+          else break;
+        }
+        seg[b + 1] = ia;
+      }
+      result = p[seg[0]];
+      for (int a = 1; a < c; ++a) partial_blend(result, p[seg[a]]);
+    }
+    // warp-aggregated append
+    const unsigned mask = __ballot_sync(0xffffffffu, c > 0);
+    if (mask)
+    {
+      unsigned long long b0 = 0;
+      if (lane == 0) b0 = atomicAdd(out_count, (unsigned long long)__popc(mask));
+      b0 = __shfl_sync(0xffffffffu, b0, 0);
+      if (c > 0) out[b0 + __popc(mask & ((1u << lane) - 1u))] = result;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- V9 partials_to_canvas
+__global__ void partials_to_canvas_kernel(const vr_partial* __restrict__ p,
+                                          const unsigned long long* __restrict__ count_dev,
+                                          size_t max_n, const __grid_constant__ ToCanvasParams T,
+                                          float4* __restrict__ canvas, float* __restrict__ cdepth)
+{
+  size_t n = (size_t)*count_dev;
+  if (n > max_n) n = max_n;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
+  {
+    const vr_partial part = p[q];
+    const int pixel_id = part.pixel_id;
+    const int i = pixel_id % T.W, j = pixel_id / T.W;
+    const float fx = (2.f * (float)i - (float)T.W) / 2.0f;
+    const float fy = (2.f * (float)j - (float)T.H) / 2.0f;
+    float dx = T.look[0] + T.delta_x[0] * fx + T.delta_y[0] * fy;
+    float dy = T.look[1] + T.delta_x[1] * fx + T.delta_y[1] * fy;
+    float dz = T.look[2] + T.delta_x[2] * fx + T.delta_y[2] * fy;
+    const float r = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz); // vtkm::Normalize
+    dx = r * dx; dy = r * dy; dz = r * dz;
+    const float wd = part.depth;
+    const float x = T.origin[0] + wd * dx, y = T.origin[1] + wd * dy, z = T.origin[2] + wd * dz;
+    const float* m = T.pv;
+    const float n2 = m[8] * x + m[9] * y + m[10] * z + m[11] * 1.f;
+    const float n3 = m[12] * x + m[13] * y + m[14] * z + m[15] * 1.f;
+    const float image_depth = 0.5f * (n2 / n3) + 0.49f;
+    const float4 in = canvas[pixel_id];
+    const float a = 1.f - part.alpha;
+    float4 o;
+    o.x = part.rgb[0] + in.x * a;
+    o.y = part.rgb[1] + in.y * a;
+    o.z = part.rgb[2] + in.z * a;
+    o.w = in.w * a + part.alpha;
+    canvas[pixel_id] = o;
+    cdepth[pixel_id] = image_depth;
+  }
+}
+
+} // namespace
+
+// ================================================================= launchers
+cudaError_t launch_canvas_clear(float4* rgba, float* depth, size_t n, cudaStream_t s)
+{
+  canvas_clear_kernel<<<grid_for(n, kT), kT, 0, s>>>(rgba, depth, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_quantize(const float4* rgba, const float* depth, size_t n, uchar4* out,
+                            float* out_depth, cudaStream_t s)
+{
+  quantize_kernel<<<grid_for(n, kT), kT, 0, s>>>(rgba, depth, n, out, out_depth);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fold_images(const uchar4* rgba, const float* depth, size_t layer_stride,
+                               const int* order, int n_layers, size_t n, uchar4* out,
+                               float* out_depth, cudaStream_t s)
+{
+  if (n_layers < 1 || n_layers > 64) return cudaErrorInvalidValue;
+  FoldOrder ord;
+  for (int i = 0; i < n_layers; ++i) ord.layer[i] = order[i];
+  const bool aligned = (layer_stride % 4 == 0) && (((uintptr_t)rgba | (uintptr_t)depth |
+                                                    (uintptr_t)out | (uintptr_t)out_depth) % 16 == 0);
+  size_t n4 = aligned ? n / 4 : 0;
+  if (n4)
+    fold_images_kernel<<<grid_for(n4, kT), kT, 0, s>>>(
+      reinterpret_cast<const uint4*>(rgba), reinterpret_cast<const float4*>(depth), layer_stride / 4,
+      ord, n_layers, n4, reinterpret_cast<uint4*>(out), reinterpret_cast<float4*>(out_depth));
+  if (n4 * 4 < n)
+    fold_images_scalar_kernel<<<grid_for(n - n4 * 4, kT), kT, 0, s>>>(
+      reinterpret_cast<const unsigned*>(rgba), depth, layer_stride, ord, n_layers, n4 * 4, n,
+      reinterpret_cast<unsigned*>(out), out_depth);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_zbuffer(uchar4* front, float* fdepth, const uchar4* img, const float* depth,
+                           size_t n, cudaStream_t s)
+{
+  zbuffer_kernel<<<grid_for(n, kT), kT, 0, s>>>(reinterpret_cast<unsigned*>(front), fdepth,
+                                                 reinterpret_cast<const unsigned*>(img), depth, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_image_to_canvas(const uchar4* rgba, const float* depth, size_t n, float4* canvas,
+                                   float* cdepth, cudaStream_t s)
+{
+  image_to_canvas_kernel<<<grid_for(n, kT), kT, 0, s>>>(rgba, depth, n, canvas, cdepth);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_synth_braid(void* field, int dtype, const int n[3], const int start[3],
+                               const int global[3], cudaStream_t s)
+{
+  const double PI = 3.14159265359;
+  const double dx = (double)(float)(4.0 * PI) / (double)(global[0] - 1);
+  const double dy = (double)(float)(2.0 * PI) / (double)(global[1] - 1);
+  const double dz = (double)(float)(3.0 * PI) / (double)(global[2] - 1);
+  const size_t total = (size_t)n[0] * n[1] * n[2];
+  if (dtype == VR_F32)
+    braid_kernel<float><<<grid_for(total, kT), kT, 0, s>>>((float*)field, n[0], n[1], n[2], start[0],
+                                                           start[1], start[2], dx, dy, dz);
+  else
+    braid_kernel<double><<<grid_for(total, kT), kT, 0, s>>>((double*)field, n[0], n[1], n[2],
+                                                            start[0], start[1], start[2], dx, dy, dz);
+  return cudaGetLastError();
+}
+
+int launch_partials_composite(const vr_partial* in, size_t n, size_t n_pixels,
+                              const PartialScratch& sc, vr_partial* out,
+                              unsigned long long* out_count, cudaStream_t s, cudaError_t* err)
+{
+  int launches = 0;
+  *err = cudaMemsetAsync(out_count, 0, sizeof(unsigned long long), s);
+  if (*err != cudaSuccess || n == 0) return launches;
+  cudaMemsetAsync(sc.px_count, 0, n_pixels * sizeof(int), s);
+  cudaMemsetAsync(sc.px_fill, 0, n_pixels * sizeof(int), s);
+  px_count_kernel<<<grid_for(n, kT), kT, 0, s>>>(in, n, sc.px_count);
+  const int nb = (int)((n_pixels + kScanTile - 1) / kScanTile);
+  scan_reduce_kernel<<<nb, kScanT, 0, s>>>(sc.px_count, n_pixels, sc.scan_blocks);
+  scan_blocks_kernel<<<1, kScanT, 0, s>>>(sc.scan_blocks, nb);
+  scan_apply_kernel<<<nb, kScanT, 0, s>>>(sc.px_count, n_pixels, sc.scan_blocks, sc.px_offset);
+  px_scatter_kernel<<<grid_for(n, kT), kT, 0, s>>>(in, n, sc.px_offset, sc.px_fill, sc.sorted_idx);
+  px_fold_kernel<<<grid_for(n_pixels, kT), kT, 0, s>>>(in, n_pixels, sc.px_count, sc.px_offset,
+                                                       sc.sorted_idx, out, out_count);
+  launches = 6;
+  *err = cudaGetLastError();
+  return launches;
+}
+
+cudaError_t launch_partials_to_canvas(const vr_partial* p, const unsigned long long* count_dev,
+                                      size_t max_n, const ToCanvasParams& tp, float4* canvas,
+                                      float* cdepth, cudaStream_t s)
+{
+  partials_to_canvas_kernel<<<grid_for(max_n ? max_n : 1, kT), kT, 0, s>>>(p, count_dev, max_n, tp,
+                                                                            canvas, cdepth);
+  return cudaGetLastError();
+}
+
+} // namespace vr

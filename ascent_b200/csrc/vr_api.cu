@@ -1,0 +1,887 @@
+// vr_api.cu -- the C ABI of libvr_b200.so (include/vr_b200.h): context, block upload, frame
+// buffers and the host-side driver logic around the kernels in sampler.cu / composite.cu /
+// comm.cu.  No CPU fallback: every compute entry point launches CUDA kernels or fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "vr_host_math.hpp"
+#include "vr_internal.h"
+
+using namespace vr;
+
+static std::string g_create_error;
+
+static vr_status fail(vr_ctx* c, vr_status st, const char* fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  else g_create_error = buf;
+  return st;
+}
+
+#define CK(call)                                                                                   \
+  do                                                                                               \
+  {                                                                                                \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? VR_ERR_NOMEM : VR_ERR_CUDA, "%s: %s",     \
+                  #call, cudaGetErrorString(e_));                                                  \
+  } while (0)
+
+#define REQUIRE(cond, ...)                                                                         \
+  do                                                                                               \
+  {                                                                                                \
+    if (!(cond)) return fail(ctx, VR_ERR_INVALID, __VA_ARGS__);                                    \
+  } while (0)
+
+static vr_status ensure_frame(vr_ctx* ctx, int W, int H);
+
+// ================================================================= context
+extern "C" vr_status vr_create(int device, vr_ctx** out)
+{
+  vr_ctx* ctx = nullptr;
+  if (!out) return fail(nullptr, VR_ERR_INVALID, "vr_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(nullptr, VR_ERR_CUDA, "vr_create: no CUDA device (%s); this library has no CPU path",
+                cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(nullptr, VR_ERR_INVALID, "vr_create: bad device %d", device);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return fail(nullptr, VR_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, VR_ERR_CUDA, "vr_create: device %d is sm_%d%d; built for sm_100a only", device,
+                prop.major, prop.minor);
+  if ((e = cudaSetDevice(device)) != cudaSuccess)
+    return fail(nullptr, VR_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  ctx = new vr_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
+  {
+    delete ctx;
+    return fail(nullptr, VR_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  }
+  ctx->stream = ctx->own_stream;
+  cudaMalloc(&ctx->tile_counter, sizeof(unsigned int));
+  cudaMalloc(&ctx->sample_counter, sizeof(unsigned long long));
+  cudaMalloc(&ctx->partial_count, sizeof(unsigned long long));
+  cudaMalloc(&ctx->lut, 1024 * sizeof(float4));
+  if ((e = cudaGetLastError()) != cudaSuccess || !ctx->lut)
+  {
+    delete ctx;
+    return fail(nullptr, VR_ERR_NOMEM, "vr_create: small allocations failed: %s", cudaGetErrorString(e));
+  }
+  cudaMemset(ctx->partial_count, 0, sizeof(unsigned long long));
+  cudaMemset(ctx->sample_counter, 0, sizeof(unsigned long long));
+  *out = ctx;
+  return VR_OK;
+}
+
+static void free_block(Block& b)
+{
+  if (b.owned_field) cudaFree(b.owned_field);
+  if (b.owned_axes) cudaFree(b.owned_axes);
+  b.owned_field = nullptr;
+  b.owned_axes = nullptr;
+}
+
+namespace vr { void comm_destroy(vr_ctx* ctx); }
+
+extern "C" void vr_destroy(vr_ctx* ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->blocks) free_block(kv.second);
+  comm_destroy(ctx);
+  cudaFree(ctx->lut);
+  cudaFree(ctx->canvas_rgba);
+  cudaFree(ctx->canvas_depth);
+  if (!ctx->img_in_arena)
+  {
+    cudaFree(ctx->img_rgba);
+    cudaFree(ctx->img_depth);
+    cudaFree(ctx->res_rgba);
+    cudaFree(ctx->res_depth);
+  }
+  cudaFree(ctx->partials);
+  cudaFree(ctx->partials_tmp);
+  cudaFree(ctx->partial_count);
+  cudaFree(ctx->px_count);
+  cudaFree(ctx->px_offset);
+  cudaFree(ctx->px_fill);
+  cudaFree(ctx->sorted_idx);
+  cudaFree(ctx->scan_blocks);
+  cudaFree(ctx->tile_counter);
+  cudaFree(ctx->sample_counter);
+  cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+extern "C" const char* vr_last_error(const vr_ctx* ctx)
+{
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" vr_status vr_set_stream(vr_ctx* ctx, void* cuda_stream)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return VR_OK;
+}
+
+extern "C" vr_status vr_synchronize(vr_ctx* ctx)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VR_OK;
+}
+
+extern "C" uint64_t vr_kernel_launches(const vr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ================================================================= blocks
+static size_t field_bytes(const BlockDev& d)
+{
+  const size_t n = d.assoc == VR_POINT ? (size_t)d.dims[0] * d.dims[1] * d.dims[2]
+                                       : (size_t)(d.dims[0] - 1) * (d.dims[1] - 1) * (d.dims[2] - 1);
+  return n * (d.dtype == VR_F32 ? 4 : 8);
+}
+
+// `old`: the block this upload replaces (same id), or null.  A re-publish of a same-sized field
+// (the in-situ steady state: one upload per simulation cycle) reuses the device allocation.
+static vr_status upload_field(vr_ctx* ctx, Block& b, const void* field, int dtype, int assoc, int where,
+                              Block* old)
+{
+  REQUIRE(field != nullptr, "block: field is NULL");
+  REQUIRE(dtype == VR_F32 || dtype == VR_F64, "block: dtype must be VR_F32 or VR_F64");
+  REQUIRE(assoc == VR_POINT || assoc == VR_CELL, "block: assoc must be VR_POINT or VR_CELL");
+  REQUIRE(where == VR_HOST || where == VR_DEVICE, "block: where must be VR_HOST or VR_DEVICE");
+  const int* d = b.dev.dims;
+  REQUIRE(d[0] >= 2 && d[1] >= 2 && d[2] >= 2, "block: point dims must be >= 2 (got %d %d %d)", d[0],
+          d[1], d[2]);
+  const size_t n = assoc == VR_POINT ? (size_t)d[0] * d[1] * d[2]
+                                     : (size_t)(d[0] - 1) * (d[1] - 1) * (d[2] - 1);
+  const size_t bytes = n * (dtype == VR_F32 ? 4 : 8);
+  b.dev.dtype = dtype;
+  b.dev.assoc = assoc;
+  if (where == VR_DEVICE)
+    b.dev.field = field;
+  else
+  {
+    if (old && old->owned_field && field_bytes(old->dev) == bytes)
+    {
+      b.owned_field = old->owned_field; // stream order keeps earlier renders ahead of the copy
+      old->owned_field = nullptr;
+    }
+    else
+      CK(cudaMalloc(&b.owned_field, bytes));
+    CK(cudaMemcpyAsync(b.owned_field, field, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    b.dev.field = b.owned_field;
+  }
+  return VR_OK;
+}
+
+extern "C" vr_status vr_block_uniform(vr_ctx* ctx, int block_id, const int dims[3],
+                                      const float origin[3], const float spacing[3],
+                                      const void* field, int dtype, int assoc, int where)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(dims && origin && spacing, "vr_block_uniform: NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  Block b;
+  std::memset(&b.dev, 0, sizeof(b.dev));
+  b.dev.kind = 0;
+  for (int a = 0; a < 3; ++a)
+  {
+    REQUIRE(spacing[a] > 0.f, "vr_block_uniform: spacing must be positive");
+    b.dev.dims[a] = dims[a];
+    b.dev.origin[a] = origin[a];
+    b.dev.spacing[a] = spacing[a];
+    // UniformLocator: MaxPoint = Origin + spacing * (dims - 1) in f32
+    b.dev.min_point[a] = origin[a];
+    b.dev.max_point[a] = origin[a] + spacing[a] * (float)(dims[a] - 1);
+    b.dev.inv_spacing[a] = 1.f / spacing[a];
+    // coords.GetBounds(): f64 arithmetic on the f32-valued origin/spacing
+    b.bounds[2 * a] = (double)origin[a];
+    b.bounds[2 * a + 1] = (double)origin[a] + (double)spacing[a] * (double)(dims[a] - 1);
+  }
+  auto it = ctx->blocks.find(block_id);
+  Block* old = it != ctx->blocks.end() ? &it->second : nullptr;
+  vr_status st = upload_field(ctx, b, field, dtype, assoc, where, old);
+  if (st != VR_OK) { free_block(b); return st; }
+  if (old && (old->owned_field || old->owned_axes))
+  {
+    cudaStreamSynchronize(ctx->stream);
+    free_block(*old);
+  }
+  ctx->blocks[block_id] = b;
+  return VR_OK;
+}
+
+extern "C" vr_status vr_block_rectilinear(vr_ctx* ctx, int block_id, const int dims[3],
+                                          const double* x, const double* y, const double* z,
+                                          const void* field, int dtype, int assoc, int where)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(dims && x && y && z, "vr_block_rectilinear: NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  Block b;
+  std::memset(&b.dev, 0, sizeof(b.dev));
+  b.dev.kind = 1;
+  const double* ax[3] = { x, y, z };
+  const size_t total = (size_t)dims[0] + dims[1] + dims[2];
+  std::vector<float> host(total);
+  size_t off = 0;
+  for (int a = 0; a < 3; ++a)
+  {
+    REQUIRE(dims[a] >= 2, "vr_block_rectilinear: point dims must be >= 2");
+    b.dev.dims[a] = dims[a];
+    for (int i = 0; i < dims[a]; ++i)
+    {
+      host[off + i] = (float)ax[a][i]; // RectilinearLocator reads f64 axes and narrows per access
+      REQUIRE(i == 0 || ax[a][i] > ax[a][i - 1], "vr_block_rectilinear: axis %d not increasing", a);
+    }
+    b.dev.min_point[a] = (float)ax[a][0];
+    b.dev.max_point[a] = (float)ax[a][dims[a] - 1];
+    b.bounds[2 * a] = ax[a][0];
+    b.bounds[2 * a + 1] = ax[a][dims[a] - 1];
+    off += dims[a];
+  }
+  CK(cudaMalloc(&b.owned_axes, total * sizeof(float)));
+  // staged through pageable memory: sync copy is fine for a few KiB
+  CK(cudaMemcpy(b.owned_axes, host.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+  b.dev.axis[0] = b.owned_axes;
+  b.dev.axis[1] = b.owned_axes + dims[0];
+  b.dev.axis[2] = b.owned_axes + dims[0] + dims[1];
+  auto it = ctx->blocks.find(block_id);
+  Block* old = it != ctx->blocks.end() ? &it->second : nullptr;
+  vr_status st = upload_field(ctx, b, field, dtype, assoc, where, old);
+  if (st != VR_OK) { free_block(b); return st; }
+  if (old && (old->owned_field || old->owned_axes))
+  {
+    cudaStreamSynchronize(ctx->stream);
+    free_block(*old);
+  }
+  ctx->blocks[block_id] = b;
+  return VR_OK;
+}
+
+extern "C" vr_status vr_block_free(vr_ctx* ctx, int block_id)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  auto it = ctx->blocks.find(block_id);
+  REQUIRE(it != ctx->blocks.end(), "vr_block_free: unknown block %d", block_id);
+  CK(cudaStreamSynchronize(ctx->stream));
+  free_block(it->second);
+  ctx->blocks.erase(it);
+  return VR_OK;
+}
+
+extern "C" vr_status vr_block_bounds(vr_ctx* ctx, int block_id, double out[6])
+{
+  if (!ctx) return VR_ERR_INVALID;
+  auto it = ctx->blocks.find(block_id);
+  REQUIRE(it != ctx->blocks.end() && out, "vr_block_bounds: unknown block %d", block_id);
+  std::memcpy(out, it->second.bounds, sizeof(double) * 6);
+  return VR_OK;
+}
+
+// ================================================================= transfer function
+extern "C" vr_status vr_set_tf(vr_ctx* ctx, const float* rgba, int n_entries)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(rgba && n_entries >= 2 && n_entries <= 1024, "vr_set_tf: need 2..1024 entries (got %d)",
+          n_entries);
+  CK(cudaSetDevice(ctx->device));
+  // small pageable copy: synchronous w.r.t. the host, ordered on the stream
+  CK(cudaMemcpyAsync(ctx->lut, rgba, (size_t)n_entries * sizeof(float4), cudaMemcpyHostToDevice,
+                     ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->lut_size = n_entries;
+  return VR_OK;
+}
+
+// ================================================================= frame buffers
+namespace vr { vr_status comm_bind_frame(vr_ctx* ctx, size_t n_pixels); }
+
+static vr_status ensure_frame(vr_ctx* ctx, int W, int H)
+{
+  REQUIRE(W > 0 && H > 0 && (long long)W * H < (1ll << 31), "bad image size %d x %d", W, H);
+  const size_t n = (size_t)W * H;
+  if (n > ctx->cap_pixels)
+  {
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->canvas_rgba);
+    cudaFree(ctx->canvas_depth);
+    ctx->canvas_rgba = nullptr;
+    ctx->canvas_depth = nullptr;
+    CK(cudaMalloc(&ctx->canvas_rgba, n * sizeof(float4)));
+    CK(cudaMalloc(&ctx->canvas_depth, n * sizeof(float)));
+    if (!ctx->comm.on)
+    {
+      cudaFree(ctx->img_rgba); cudaFree(ctx->img_depth); cudaFree(ctx->res_rgba); cudaFree(ctx->res_depth);
+      ctx->img_rgba = ctx->res_rgba = nullptr;
+      ctx->img_depth = ctx->res_depth = nullptr;
+      CK(cudaMalloc(&ctx->img_rgba, n * sizeof(uchar4)));
+      CK(cudaMalloc(&ctx->img_depth, n * sizeof(float)));
+      CK(cudaMalloc(&ctx->res_rgba, n * sizeof(uchar4)));
+      CK(cudaMalloc(&ctx->res_depth, n * sizeof(float)));
+    }
+    ctx->cap_pixels = n;
+  }
+  if (ctx->comm.on)
+  {
+    vr_status st = comm_bind_frame(ctx, n);
+    if (st != VR_OK) return st;
+  }
+  ctx->W = W;
+  ctx->H = H;
+  return VR_OK;
+}
+
+extern "C" vr_status vr_canvas_clear(vr_ctx* ctx, int width, int height)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  vr_status st = ensure_frame(ctx, width, height);
+  if (st != VR_OK) return st;
+  CK(launch_canvas_clear(ctx->canvas_rgba, ctx->canvas_depth, (size_t)width * height, ctx->stream));
+  ctx->launches++;
+  return VR_OK;
+}
+
+extern "C" vr_status vr_canvas_upload(vr_ctx* ctx, int width, int height, const float* rgba,
+                                      const float* depth)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(rgba && depth, "vr_canvas_upload: NULL buffer");
+  CK(cudaSetDevice(ctx->device));
+  vr_status st = ensure_frame(ctx, width, height);
+  if (st != VR_OK) return st;
+  const size_t n = (size_t)width * height;
+  CK(cudaMemcpyAsync(ctx->canvas_rgba, rgba, n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->canvas_depth, depth, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  return VR_OK;
+}
+
+extern "C" vr_status vr_canvas_download(vr_ctx* ctx, float* rgba, float* depth)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(ctx->W > 0, "vr_canvas_download: no canvas yet");
+  const size_t n = (size_t)ctx->W * ctx->H;
+  if (rgba) CK(cudaMemcpyAsync(rgba, ctx->canvas_rgba, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  if (depth) CK(cudaMemcpyAsync(depth, ctx->canvas_depth, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VR_OK;
+}
+
+extern "C" vr_status vr_canvas_ptrs(vr_ctx* ctx, void** rgba_dev, void** depth_dev)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(ctx->W > 0, "vr_canvas_ptrs: no canvas yet");
+  if (rgba_dev) *rgba_dev = ctx->canvas_rgba;
+  if (depth_dev) *depth_dev = ctx->canvas_depth;
+  return VR_OK;
+}
+
+// ================================================================= tracing
+static vr_status fill_trace_params(vr_ctx* ctx, int block_id, const vr_camera* cam, float sample_dist,
+                                   float range_min, float range_max, int use_depth, int W, int H,
+                                   TraceParams& p)
+{
+  REQUIRE(cam != nullptr, "trace: camera is NULL");
+  auto it = ctx->blocks.find(block_id);
+  REQUIRE(it != ctx->blocks.end(), "trace: unknown block %d", block_id);
+  REQUIRE(ctx->lut_size >= 2, "trace: no transfer function set (vr_set_tf)");
+  const Block& b = it->second;
+  std::memset(&p, 0, sizeof(p));
+  p.blk = b.dev;
+  int sub[4];
+  hm::find_subset(*cam, W, H, b.bounds, sub);
+  p.W = W; p.H = H;
+  p.sx = sub[0]; p.sy = sub[1]; p.sw = sub[2]; p.sh = sub[3];
+  p.tiles_x = (p.sw + 7) / 8;
+  p.tiles_y = (p.sh + 3) / 4;
+  const hm::RayGen g = hm::raygen(*cam, W, H, false);
+  for (int k = 0; k < 3; ++k)
+  {
+    p.origin[k] = cam->position[k];
+    p.nlook[k] = g.nlook[k];
+    p.delta_x[k] = g.delta_x[k];
+    p.delta_y[k] = g.delta_y[k];
+    p.bmin[k] = (float)b.bounds[2 * k];
+    p.bmax[k] = (float)b.bounds[2 * k + 1];
+  }
+  const hm::Mat4 pv = hm::projview(*cam, W, H);
+  std::memcpy(p.pv, pv.m, sizeof(p.pv));
+  p.use_depth = use_depth ? 1 : 0;
+  if (use_depth)
+  {
+    const hm::Mat4 inv = hm::inverse(pv);
+    std::memcpy(p.inv_pv, inv.m, sizeof(p.inv_pv));
+  }
+  p.dbl_inv_w = 2.f / (float)W;
+  p.dbl_inv_h = 2.f / (float)H;
+  // VolumeRendererStructured::RenderOnDevice: meshEpsilon = |block extent| * 1e-4
+  const hm::Vec3 ext = { { (float)(b.bounds[1] - b.bounds[0]), (float)(b.bounds[3] - b.bounds[2]),
+                           (float)(b.bounds[5] - b.bounds[4]) } };
+  const float mag = hm::magnitude(ext);
+  p.mesh_eps = mag * 0.0001f;
+  p.sample_dist = sample_dist > 0.f ? sample_dist : mag / 200.f;
+  p.range_min = range_min;
+  p.inv_delta_scalar = (range_max - range_min) != 0.f ? 1.f / (range_max - range_min) : range_min;
+  p.lut = ctx->lut;
+  p.lut_size = ctx->lut_size;
+  p.canvas_rgba = ctx->canvas_rgba;
+  p.canvas_depth = ctx->canvas_depth;
+  p.tile_counter = ctx->tile_counter;
+  p.sample_counter = ctx->sample_counter;
+  return VR_OK;
+}
+
+extern "C" vr_status vr_trace_to_canvas(vr_ctx* ctx, int block_id, const vr_camera* cam,
+                                        float sample_dist, float range_min, float range_max,
+                                        int use_canvas_depth)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(ctx->W > 0, "vr_trace_to_canvas: call vr_canvas_clear/upload first");
+  CK(cudaSetDevice(ctx->device));
+  TraceParams p;
+  vr_status st = fill_trace_params(ctx, block_id, cam, sample_dist, range_min, range_max,
+                                   use_canvas_depth, ctx->W, ctx->H, p);
+  if (st != VR_OK) return st;
+  CK(launch_trace(p, 0, ctx->sm_count, ctx->stream));
+  ctx->launches++;
+  return VR_OK;
+}
+
+extern "C" vr_status vr_render_image(vr_ctx* ctx, int block_id, const vr_camera* cam, int width,
+                                     int height, float sample_dist, float range_min,
+                                     float range_max, float* rgba_inout, float* depth_inout)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(rgba_inout && depth_inout, "vr_render_image: NULL canvas");
+  vr_status st = vr_canvas_upload(ctx, width, height, rgba_inout, depth_inout);
+  if (st != VR_OK) return st;
+  st = vr_trace_to_canvas(ctx, block_id, cam, sample_dist, range_min, range_max, 1);
+  if (st != VR_OK) return st;
+  return vr_canvas_download(ctx, rgba_inout, depth_inout);
+}
+
+// ----------------------------------------------------------------- partial list
+static vr_status ensure_partials(vr_ctx* ctx, size_t need)
+{
+  if (need <= ctx->partial_cap) return VR_OK;
+  size_t cap = std::max(need, ctx->partial_cap * 2);
+  vr_partial* np = nullptr;
+  CK(cudaMalloc(&np, cap * sizeof(vr_partial)));
+  if (ctx->partials)
+  {
+    unsigned long long n = 0;
+    CK(cudaMemcpyAsync(&n, ctx->partial_count, sizeof(n), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    n = std::min<unsigned long long>(n, ctx->partial_cap);
+    if (n) CK(cudaMemcpyAsync(np, ctx->partials, n * sizeof(vr_partial), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->partials);
+  }
+  ctx->partials = np;
+  ctx->partial_cap = cap;
+  return VR_OK;
+}
+
+extern "C" vr_status vr_partials_begin(vr_ctx* ctx, int width, int height)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(width > 0 && height > 0 && (long long)width * height < (1ll << 31), "bad image size");
+  CK(cudaSetDevice(ctx->device));
+  ctx->pW = width;
+  ctx->pH = height;
+  ctx->n_partials_host = 0;
+  CK(cudaMemsetAsync(ctx->partial_count, 0, sizeof(unsigned long long), ctx->stream));
+  return VR_OK;
+}
+
+extern "C" vr_status vr_trace_to_partials(vr_ctx* ctx, int block_id, const vr_camera* cam,
+                                          float sample_dist, float range_min, float range_max,
+                                          int use_canvas_depth)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(ctx->pW > 0, "vr_trace_to_partials: call vr_partials_begin first");
+  REQUIRE(!use_canvas_depth || (ctx->W == ctx->pW && ctx->H == ctx->pH),
+          "vr_trace_to_partials: canvas depth requested but canvas size differs");
+  CK(cudaSetDevice(ctx->device));
+  TraceParams p;
+  vr_status st = fill_trace_params(ctx, block_id, cam, sample_dist, range_min, range_max,
+                                   use_canvas_depth, ctx->pW, ctx->pH, p);
+  if (st != VR_OK) return st;
+  // worst case every ray of the subset emits: reserve before launching (no overflow possible)
+  // the list can only be bounded from the host by the sum of subset sizes so far
+  static_assert(sizeof(vr_partial) == 24, "vr_partial must be 24 bytes");
+  ctx->n_partials_host += (size_t)p.sw * p.sh; // upper bound bookkeeping
+  st = ensure_partials(ctx, ctx->n_partials_host);
+  if (st != VR_OK) return st;
+  p.partials = ctx->partials;
+  p.partial_count = ctx->partial_count;
+  p.partial_capacity = ctx->partial_cap;
+  CK(launch_trace(p, 1, ctx->sm_count, ctx->stream));
+  ctx->launches++;
+  return VR_OK;
+}
+
+extern "C" vr_status vr_partials_count(vr_ctx* ctx, size_t* n)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(n, "vr_partials_count: NULL");
+  unsigned long long c = 0;
+  CK(cudaMemcpyAsync(&c, ctx->partial_count, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *n = (size_t)std::min<unsigned long long>(c, ctx->partial_cap);
+  return VR_OK;
+}
+
+extern "C" vr_status vr_partials_download(vr_ctx* ctx, vr_partial* out, size_t capacity, size_t* n)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  size_t c = 0;
+  vr_status st = vr_partials_count(ctx, &c);
+  if (st != VR_OK) return st;
+  if (n) *n = c;
+  REQUIRE(c <= capacity, "vr_partials_download: capacity %zu < %zu partials", capacity, c);
+  if (c && out)
+  {
+    CK(cudaMemcpyAsync(out, ctx->partials, c * sizeof(vr_partial), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return VR_OK;
+}
+
+extern "C" vr_status vr_render_partials(vr_ctx* ctx, int block_id, const vr_camera* cam, int width,
+                                        int height, float sample_dist, float range_min,
+                                        float range_max, const float* depth_in, vr_partial** out,
+                                        size_t* n)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(out && n, "vr_render_partials: NULL output");
+  *out = nullptr;
+  *n = 0;
+  vr_status st;
+  if (depth_in)
+  {
+    CK(cudaSetDevice(ctx->device));
+    st = ensure_frame(ctx, width, height);
+    if (st != VR_OK) return st;
+    CK(cudaMemcpyAsync(ctx->canvas_depth, depth_in, (size_t)width * height * sizeof(float),
+                       cudaMemcpyHostToDevice, ctx->stream));
+  }
+  st = vr_partials_begin(ctx, width, height);
+  if (st != VR_OK) return st;
+  ctx->n_partials_host = 0;
+  st = vr_trace_to_partials(ctx, block_id, cam, sample_dist, range_min, range_max, depth_in != nullptr);
+  if (st != VR_OK) return st;
+  size_t c = 0;
+  st = vr_partials_count(ctx, &c);
+  if (st != VR_OK) return st;
+  vr_partial* host = (vr_partial*)std::malloc(std::max<size_t>(c, 1) * sizeof(vr_partial));
+  if (!host) return fail(ctx, VR_ERR_NOMEM, "vr_render_partials: host allocation failed");
+  st = vr_partials_download(ctx, host, c, &c);
+  if (st != VR_OK) { std::free(host); return st; }
+  *out = host;
+  *n = c;
+  return VR_OK;
+}
+
+extern "C" void vr_free(void* p) { std::free(p); }
+
+// ================================================================= image compositing
+extern "C" vr_status vr_image_from_canvas(vr_ctx* ctx)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(ctx->W > 0, "vr_image_from_canvas: no canvas yet");
+  CK(cudaSetDevice(ctx->device));
+  CK(launch_quantize(ctx->canvas_rgba, ctx->canvas_depth, (size_t)ctx->W * ctx->H, ctx->img_rgba,
+                     ctx->img_depth, ctx->stream));
+  ctx->launches++;
+  return VR_OK;
+}
+
+extern "C" vr_status vr_image_download(vr_ctx* ctx, uint8_t* rgba, float* depth)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(ctx->W > 0, "vr_image_download: no image yet");
+  const size_t n = (size_t)ctx->W * ctx->H;
+  if (rgba) CK(cudaMemcpyAsync(rgba, ctx->img_rgba, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (depth) CK(cudaMemcpyAsync(depth, ctx->img_depth, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VR_OK;
+}
+
+extern "C" vr_status vr_image_ptrs(vr_ctx* ctx, void** rgba8_dev, void** depth_dev)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(ctx->W > 0, "vr_image_ptrs: no image yet");
+  if (rgba8_dev) *rgba8_dev = ctx->img_rgba;
+  if (depth_dev) *depth_dev = ctx->img_depth;
+  return VR_OK;
+}
+
+// stable ascending order of the layers by vis_order (CompositeOrderSort, Image.hpp:325-331)
+static void layer_order(const int* vis_order, int n, int* out)
+{
+  for (int i = 0; i < n; ++i) out[i] = i;
+  std::stable_sort(out, out + n, [&](int a, int b) { return vis_order[a] < vis_order[b]; });
+}
+
+extern "C" vr_status vr_fold_images_dev(vr_ctx* ctx, const uint8_t* rgba, const float* depth,
+                                        size_t layer_stride_px, const int* vis_order_host,
+                                        int n_layers, size_t n_pixels, uint8_t* out_rgba,
+                                        float* out_depth)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(rgba && depth && vis_order_host && out_rgba && out_depth, "vr_fold_images_dev: NULL argument");
+  REQUIRE(n_layers >= 1 && n_layers <= 64, "vr_fold_images_dev: 1..64 layers supported (got %d)", n_layers);
+  CK(cudaSetDevice(ctx->device));
+  int order[64];
+  layer_order(vis_order_host, n_layers, order);
+  CK(launch_fold_images((const uchar4*)rgba, depth, layer_stride_px, order, n_layers, n_pixels,
+                        (uchar4*)out_rgba, out_depth, ctx->stream));
+  ctx->launches++;
+  return VR_OK;
+}
+
+extern "C" vr_status vr_composite_images(vr_ctx* ctx, const float* rgba, const float* depth,
+                                         const int* vis_order, int n_images, int width, int height,
+                                         uint8_t* out_rgba, float* out_depth)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(rgba && depth && vis_order && out_rgba && out_depth, "vr_composite_images: NULL argument");
+  REQUIRE(n_images >= 1 && n_images <= 64, "vr_composite_images: 1..64 images supported");
+  CK(cudaSetDevice(ctx->device));
+  vr_status st = ensure_frame(ctx, width, height);
+  if (st != VR_OK) return st;
+  const size_t n = (size_t)width * height;
+  uchar4* layers = nullptr;
+  float* ldepth = nullptr;
+  CK(cudaMalloc(&layers, n * n_images * sizeof(uchar4)));
+  cudaError_t e = cudaMalloc(&ldepth, n * n_images * sizeof(float));
+  if (e != cudaSuccess) { cudaFree(layers); return fail(ctx, VR_ERR_NOMEM, "vr_composite_images: out of memory"); }
+  vr_status rc = VR_OK;
+  for (int i = 0; i < n_images && rc == VR_OK; ++i)
+  {
+    // AddImage(float*...) -> Image::Init: stage each float image through the device canvas
+    e = cudaMemcpyAsync(ctx->canvas_rgba, rgba + i * n * 4, n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(ctx->canvas_depth, depth + i * n, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+      e = launch_quantize(ctx->canvas_rgba, ctx->canvas_depth, n, layers + i * n, ldepth + i * n, ctx->stream);
+    ctx->launches++;
+    if (e != cudaSuccess) rc = fail(ctx, VR_ERR_CUDA, "vr_composite_images: %s", cudaGetErrorString(e));
+  }
+  if (rc == VR_OK)
+  {
+    int order[64];
+    layer_order(vis_order, n_images, order);
+    e = launch_fold_images(layers, ldepth, n, order, n_images, n, ctx->res_rgba, ctx->res_depth, ctx->stream);
+    ctx->launches++;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_rgba, ctx->res_rgba, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_depth, ctx->res_depth, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, VR_ERR_CUDA, "vr_composite_images: %s", cudaGetErrorString(e));
+  }
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(layers);
+  cudaFree(ldepth);
+  return rc;
+}
+
+extern "C" vr_status vr_zbuffer_composite_dev(vr_ctx* ctx, uint8_t* front_rgba, float* front_depth,
+                                              const uint8_t* rgba, const float* depth,
+                                              size_t n_pixels)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(front_rgba && front_depth && rgba && depth, "vr_zbuffer_composite_dev: NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  CK(launch_zbuffer((uchar4*)front_rgba, front_depth, (const uchar4*)rgba, depth, n_pixels, ctx->stream));
+  ctx->launches++;
+  return VR_OK;
+}
+
+extern "C" vr_status vr_image_to_canvas_dev(vr_ctx* ctx, const uint8_t* rgba, const float* depth)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(ctx->W > 0 && rgba && depth, "vr_image_to_canvas_dev: no canvas or NULL argument");
+  CK(cudaSetDevice(ctx->device));
+  CK(launch_image_to_canvas((const uchar4*)rgba, depth, (size_t)ctx->W * ctx->H, ctx->canvas_rgba,
+                            ctx->canvas_depth, ctx->stream));
+  ctx->launches++;
+  return VR_OK;
+}
+
+// ================================================================= partial compositing
+static vr_status ensure_partial_scratch(vr_ctx* ctx, size_t n_pixels, size_t n_parts)
+{
+  if (n_pixels > ctx->scratch_px)
+  {
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->px_count); cudaFree(ctx->px_offset); cudaFree(ctx->px_fill); cudaFree(ctx->scan_blocks);
+    ctx->px_count = ctx->px_offset = ctx->px_fill = ctx->scan_blocks = nullptr;
+    CK(cudaMalloc(&ctx->px_count, n_pixels * sizeof(int)));
+    CK(cudaMalloc(&ctx->px_offset, n_pixels * sizeof(int)));
+    CK(cudaMalloc(&ctx->px_fill, n_pixels * sizeof(int)));
+    CK(cudaMalloc(&ctx->scan_blocks, (n_pixels / 2048 + 2) * sizeof(int)));
+    ctx->scratch_px = n_pixels;
+  }
+  if (n_parts > ctx->scratch_parts)
+  {
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->sorted_idx);
+    ctx->sorted_idx = nullptr;
+    CK(cudaMalloc(&ctx->sorted_idx, n_parts * sizeof(int)));
+    ctx->scratch_parts = n_parts;
+  }
+  if (n_parts > ctx->partial_tmp_cap)
+  {
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->partials_tmp);
+    ctx->partials_tmp = nullptr;
+    CK(cudaMalloc(&ctx->partials_tmp, n_parts * sizeof(vr_partial)));
+    ctx->partial_tmp_cap = n_parts;
+  }
+  return VR_OK;
+}
+
+extern "C" vr_status vr_partials_composite(vr_ctx* ctx)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(ctx->pW > 0, "vr_partials_composite: call vr_partials_begin first");
+  CK(cudaSetDevice(ctx->device));
+  size_t n = 0;
+  vr_status st = vr_partials_count(ctx, &n); // syncs: the list length sizes the launches
+  if (st != VR_OK) return st;
+  const size_t n_pixels = (size_t)ctx->pW * ctx->pH;
+  st = ensure_partial_scratch(ctx, n_pixels, std::max<size_t>(n, 1));
+  if (st != VR_OK) return st;
+  PartialScratch sc{ ctx->px_count, ctx->px_offset, ctx->px_fill, ctx->sorted_idx, ctx->scan_blocks };
+  cudaError_t e;
+  // fold into the tmp list, then swap: the context's list becomes the composited one
+  ctx->launches += launch_partials_composite(ctx->partials, n, n_pixels, sc, ctx->partials_tmp,
+                                             ctx->partial_count, ctx->stream, &e);
+  CK(e);
+  std::swap(ctx->partials, ctx->partials_tmp);
+  std::swap(ctx->partial_cap, ctx->partial_tmp_cap);
+  ctx->n_partials_host = 0;
+  return VR_OK;
+}
+
+extern "C" vr_status vr_partials_to_canvas(vr_ctx* ctx, const vr_camera* cam)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(cam, "vr_partials_to_canvas: camera is NULL");
+  REQUIRE(ctx->W == ctx->pW && ctx->H == ctx->pH && ctx->W > 0,
+          "vr_partials_to_canvas: canvas (%dx%d) and partial frame (%dx%d) differ", ctx->W, ctx->H,
+          ctx->pW, ctx->pH);
+  CK(cudaSetDevice(ctx->device));
+  ToCanvasParams tp;
+  const hm::RayGen g = hm::raygen(*cam, ctx->W, ctx->H, true);
+  const hm::Mat4 pv = hm::projview(*cam, ctx->W, ctx->H);
+  for (int k = 0; k < 3; ++k)
+  {
+    tp.origin[k] = cam->position[k];
+    tp.look[k] = g.nlook[k];
+    tp.delta_x[k] = g.delta_x[k];
+    tp.delta_y[k] = g.delta_y[k];
+  }
+  std::memcpy(tp.pv, pv.m, sizeof(tp.pv));
+  tp.W = ctx->W;
+  tp.H = ctx->H;
+  if (ctx->partial_cap == 0) return VR_OK;
+  CK(launch_partials_to_canvas(ctx->partials, ctx->partial_count, ctx->partial_cap, tp,
+                               ctx->canvas_rgba, ctx->canvas_depth, ctx->stream));
+  ctx->launches++;
+  return VR_OK;
+}
+
+extern "C" vr_status vr_composite_partials(vr_ctx* ctx, const vr_partial* in, size_t n_in, int width,
+                                           int height, vr_partial* out, size_t* n_out)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(out && n_out && (in || n_in == 0), "vr_composite_partials: NULL argument");
+  vr_status st = vr_partials_begin(ctx, width, height);
+  if (st != VR_OK) return st;
+  for (size_t i = 0; i < n_in; ++i)
+    REQUIRE(in[i].pixel_id >= 0 && (long long)in[i].pixel_id < (long long)width * height,
+            "vr_composite_partials: pixel id %d outside %dx%d", in[i].pixel_id, width, height);
+  ctx->n_partials_host = 0;
+  st = ensure_partials(ctx, std::max<size_t>(n_in, 1));
+  if (st != VR_OK) return st;
+  if (n_in)
+    CK(cudaMemcpyAsync(ctx->partials, in, n_in * sizeof(vr_partial), cudaMemcpyHostToDevice, ctx->stream));
+  unsigned long long c = n_in;
+  CK(cudaMemcpyAsync(ctx->partial_count, &c, sizeof(c), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  st = vr_partials_composite(ctx);
+  if (st != VR_OK) return st;
+  return vr_partials_download(ctx, out, n_in, n_out);
+}
+
+// ================================================================= host-side helpers
+extern "C" float vr_sample_distance(const double gb[6], float samples)
+{
+  // VolumeRenderer::PreExecute, VolumeRenderer.cpp:606-611
+  const hm::Vec3 ext = { { (float)(gb[1] - gb[0]), (float)(gb[3] - gb[2]), (float)(gb[5] - gb[4]) } };
+  return hm::magnitude(ext) / samples;
+}
+
+extern "C" void vr_visibility_order(const double* domain_bounds, int n, const vr_camera* cam,
+                                    int* order_out)
+{
+  // FindMinDepth + DepthSort, VolumeRenderer.cpp:637-650,690-831: distance from the camera to each
+  // domain's bounds centre, ascending; ties keep (rank, domain) order (stable).
+  std::vector<float> depth(n);
+  std::vector<int> idx(n);
+  for (int i = 0; i < n; ++i)
+  {
+    const double* b = domain_bounds + 6 * i;
+    double d2 = 0;
+    for (int a = 0; a < 3; ++a)
+    {
+      const double c = (double)(float)((b[2 * a] + b[2 * a + 1]) / 2.0);
+      const double d = c - (double)cam->position[a];
+      d2 += d * d;
+    }
+    depth[i] = (float)std::sqrt(d2);
+    idx[i] = i;
+  }
+  std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return depth[a] < depth[b]; });
+  for (int i = 0; i < n; ++i) order_out[idx[i]] = i;
+}
+
+extern "C" void vr_find_subset(const vr_camera* cam, int width, int height, const double bounds[6],
+                               int out[4])
+{
+  hm::find_subset(*cam, width, height, bounds, out);
+}
+
+extern "C" vr_status vr_synth_braid_dev(vr_ctx* ctx, void* field_dev, int dtype, const int n[3],
+                                        const int start[3], const int global[3])
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(field_dev && n && start && global, "vr_synth_braid_dev: NULL argument");
+  REQUIRE(dtype == VR_F32 || dtype == VR_F64, "vr_synth_braid_dev: bad dtype");
+  CK(cudaSetDevice(ctx->device));
+  CK(launch_synth_braid(field_dev, dtype, n, start, global, ctx->stream));
+  ctx->launches++;
+  return VR_OK;
+}

@@ -1,0 +1,183 @@
+// vr_internal.h -- shared declarations of libvr_b200.so (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/vr_b200.h"
+
+namespace vr
+{
+
+// ---------------------------------------------------------------- device-side descriptors
+struct BlockDev
+{
+  int kind;      // 0 uniform, 1 rectilinear
+  int dtype;     // VR_F32 / VR_F64
+  int assoc;     // VR_POINT / VR_CELL
+  int dims[3];   // point dims
+  float origin[3], spacing[3]; // uniform (f32, as Ascent hands them to VTK-m)
+  float min_point[3], max_point[3], inv_spacing[3];
+  const float* axis[3];        // rectilinear: axes narrowed to f32 once on upload
+  const void* field;
+};
+
+// Everything one trace launch needs; passed by value as a __grid_constant__.
+struct TraceParams
+{
+  BlockDev blk;
+  // K1
+  float origin[3], nlook[3], delta_x[3], delta_y[3];
+  int W, H, sx, sy, sw, sh;
+  int tiles_x, tiles_y;
+  // K2
+  int use_depth;
+  float inv_pv[16];
+  float dbl_inv_w, dbl_inv_h;
+  // K3 (block bounds narrowed to f32)
+  float bmin[3], bmax[3];
+  // K4
+  float mesh_eps, sample_dist, range_min, inv_delta_scalar;
+  int lut_size;
+  const float4* lut;
+  // K7
+  float pv[16];
+  float4* canvas_rgba;
+  float* canvas_depth;
+  // partial emission (path B)
+  vr_partial* partials;
+  unsigned long long* partial_count;
+  unsigned long long partial_capacity;
+  // dynamic tile scheduler + sample counter
+  unsigned int* tile_counter;
+  unsigned long long* sample_counter; // may be null
+};
+
+// ---------------------------------------------------------------- host-side state
+struct Block
+{
+  BlockDev dev;
+  void* owned_field = nullptr; // device copy we own (null when adopted)
+  float* owned_axes = nullptr;
+  double bounds[6];
+};
+
+struct Comm
+{
+  bool on = false;
+  int rank = 0, size = 1;
+  size_t max_pixels = 0, max_partials = 0;
+  size_t arena_bytes = 0;
+  unsigned char* arena = nullptr;               // own arena (cudaMalloc, IPC-exported)
+  std::vector<unsigned char*> peer;             // mapped arenas, peer[rank] == arena
+  unsigned char** peer_dev = nullptr;           // device copy of the pointer table
+  unsigned int epoch = 0;
+};
+
+} // namespace vr
+
+struct vr_ctx
+{
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  int sm_count = 148;
+
+  std::map<int, vr::Block> blocks;
+  float4* lut = nullptr;
+  int lut_size = 0;
+
+  // frame buffers (sized W x H, grown on demand)
+  int W = 0, H = 0;
+  size_t cap_pixels = 0;
+  float4* canvas_rgba = nullptr;
+  float* canvas_depth = nullptr;
+  uchar4* img_rgba = nullptr;  // quantised own image (lives in the arena when comm is on)
+  float* img_depth = nullptr;
+  uchar4* res_rgba = nullptr;  // composited result (rank 0)
+  float* res_depth = nullptr;
+  bool img_in_arena = false;
+
+  // partial list
+  vr_partial* partials = nullptr;
+  size_t partial_cap = 0;
+  unsigned long long* partial_count = nullptr; // device counter
+  size_t n_partials_host = 0;                  // valid after a sync'ing call
+  int pW = 0, pH = 0;
+  // partial composite scratch
+  int* px_count = nullptr;   // per pixel
+  int* px_offset = nullptr;
+  int* px_fill = nullptr;
+  int* sorted_idx = nullptr;
+  int* scan_blocks = nullptr;
+  size_t scratch_px = 0, scratch_parts = 0, scratch_blocks = 0;
+  vr_partial* partials_tmp = nullptr;
+  size_t partial_tmp_cap = 0;
+
+  unsigned int* tile_counter = nullptr;
+  unsigned long long* sample_counter = nullptr;
+
+  vr::Comm comm;
+};
+
+namespace vr
+{
+// sampler.cu
+cudaError_t launch_trace(const TraceParams& p, int mode_partials, int sm_count, cudaStream_t s);
+
+// composite.cu
+cudaError_t launch_canvas_clear(float4* rgba, float* depth, size_t n, cudaStream_t s);
+cudaError_t launch_quantize(const float4* rgba, const float* depth, size_t n, uchar4* out,
+                            float* out_depth, cudaStream_t s);
+cudaError_t launch_fold_images(const uchar4* rgba, const float* depth, size_t layer_stride,
+                               const int* order /* layer index per fold step, by value */,
+                               int n_layers, size_t n, uchar4* out, float* out_depth,
+                               cudaStream_t s);
+cudaError_t launch_zbuffer(uchar4* front, float* fdepth, const uchar4* img, const float* depth,
+                           size_t n, cudaStream_t s);
+cudaError_t launch_image_to_canvas(const uchar4* rgba, const float* depth, size_t n, float4* canvas,
+                                   float* cdepth, cudaStream_t s);
+cudaError_t launch_synth_braid(void* field, int dtype, const int n[3], const int start[3],
+                               const int global[3], cudaStream_t s);
+
+struct PartialScratch
+{
+  int* px_count;
+  int* px_offset;
+  int* px_fill;
+  int* sorted_idx;
+  int* scan_blocks;
+};
+// composite the list `in` (n partials, pixel ids in [0, n_pixels)) into `out` (<= 1 per pixel);
+// *out_count (device) receives the number written.  Returns number of kernels launched.
+int launch_partials_composite(const vr_partial* in, size_t n, size_t n_pixels,
+                              const PartialScratch& sc, vr_partial* out,
+                              unsigned long long* out_count, cudaStream_t s, cudaError_t* err);
+
+struct ToCanvasParams
+{
+  float origin[3], look[3], delta_x[3], delta_y[3];
+  float pv[16];
+  int W, H;
+};
+cudaError_t launch_partials_to_canvas(const vr_partial* p, const unsigned long long* count_dev,
+                                      size_t max_n, const ToCanvasParams& tp, float4* canvas,
+                                      float* cdepth, cudaStream_t s);
+
+// comm.cu
+struct FoldP2PParams
+{
+  unsigned char* const* peers; // device table of arena base pointers
+  int rank, size;
+  unsigned int epoch;
+  size_t n_pixels;
+  size_t off_img_rgba, off_img_depth, off_res_rgba, off_res_depth, off_flags;
+  int order[16]; // rank index per fold step (front to back)
+};
+cudaError_t launch_fold_p2p(const FoldP2PParams& p, int sm_count, cudaStream_t s);
+} // namespace vr

@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- Ascent `volume` plot hot path on B200: Mrays/s, frames/s, composite ms/frame.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c3]
+
+One "step" = one frame of the hot path.
+  N == 1 : BASELINE config 2 -- braid uniform 512^3 f32, one domain, 1920x1080, default camera,
+           samples = 100, path A of vtkh::VolumeRenderer (clear canvas, trace [K1-K7], Image::Init
+           quantise, ImageToCanvas), field resident in HBM.
+  N  > 1 : BASELINE config 3 -- braid 1023^3 split into 8 blocks of 512^3 spread over N ranks
+           (8/N blocks per rank), 3840x2160, sort-last render + composite to rank 0 (strong
+           scaling; N == 8 is path A/direct-send, N < 8 path B/partials like the reference).
+`value` = primary rays of the final image (W*H) x frames / time, device-timed (CUDA events on the
+launching stream, max over ranks), inputs resident.  `e2e` = same frame through the host-buffer
+C ABI a vtk-h caller uses: field uploaded from pinned host memory, canvas read back, every step.
+`--impl reference` times the CPU oracle (the restatement of the reference's OpenMP path, see
+oracle/) on the same workload with every host thread.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RAMP_TF = {"name": "cool to warm", "control_points": [
+    {"type": "alpha", "position": 0., "alpha": 0.}, {"type": "alpha", "position": 1., "alpha": 1.}]}
+SAMPLES = 100
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- workloads
+def workload_c2():
+    return dict(name="c2: braid uniform 512^3 f32, 1 domain, 1920x1080, default camera, samples=100",
+                n_block=512, per_axis=1, W=1920, H=1080)
+
+
+def workload_c3():
+    return dict(name="c3: braid 1023^3 as 8 blocks of 512^3 f32, 3840x2160, default camera, "
+                     "samples=100, sort-last composite to rank 0",
+                n_block=512, per_axis=2, W=3840, H=2160)
+
+
+def block_layout(wl):
+    """origin/spacing/start index of every block of the workload (same as
+    ascent_b200.datasets.braid_uniform_blocks)."""
+    nb, b = wl["n_block"], wl["per_axis"]
+    g = b * (nb - 1) + 1
+    sp = 20.0 / (g - 1)
+    out = []
+    for kz in range(b):
+        for jy in range(b):
+            for ix in range(b):
+                st = (ix * (nb - 1), jy * (nb - 1), kz * (nb - 1))
+                out.append(dict(dims=(nb,) * 3, start=st, glob=(g,) * 3, spacing=[sp] * 3,
+                                origin=[-10.0 + st[0] * sp, -10.0 + st[1] * sp, -10.0 + st[2] * sp]))
+    return out
+
+
+def scene_params(wl, blocks, rng_minmax):
+    """Host-side driver values of VolumeRenderer::PreExecute for the workload."""
+    from ascent_b200 import _lib, camera, color_table, datasets
+    bl = [datasets.domain_bounds(dict(kind="uniform", dims=b["dims"], origin=b["origin"],
+                                      spacing=b["spacing"])) for b in blocks]
+    gb = datasets.union_bounds(bl)
+    cam = camera.Camera()
+    cam.reset_to_bounds(gb)
+    lut = color_table.parse_color_table(RAMP_TF).corrected_opacity(SAMPLES).lut()
+    return dict(bounds=bl, gb=gb, cam=cam.to_struct(), lut=lut,
+                sample_dist=_lib.sample_distance(gb, SAMPLES), rmin=rng_minmax[0], rmax=rng_minmax[1])
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def run_reference(args, wl):
+    """The reference's CPU path (oracle restatement, all host threads) on the same workload."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from ascent_b200 import datasets
+    from oracle import oracle as O
+    blocks = block_layout(wl)
+    W, H = wl["W"], wl["H"]
+    t0 = time.time()
+    doms = []
+    for b in blocks:
+        f = datasets.braid_values(*b["dims"], *b["start"], *b["glob"], dtype=np.float32)
+        doms.append(dict(kind="uniform", dims=b["dims"], origin=b["origin"], spacing=b["spacing"], field=f))
+    rmin = min(float(d["field"].min()) for d in doms)
+    rmax = max(float(d["field"].max()) for d in doms)
+    sp = scene_params(wl, blocks, (rmin, rmax))
+    cam = O.Camera.from_buffer_copy(bytes(sp["cam"]))
+    oblocks = [O.OracleBlock(d["dims"], d["field"], origin=d["origin"], spacing=d["spacing"]) for d in doms]
+    gen_s = time.time() - t0
+
+    def frame():
+        rgba, depth = O.new_canvas(W, H)
+        if len(oblocks) == 1:
+            O.render_to_canvas(oblocks[0], cam, W, H, sp["lut"], sp["sample_dist"], rmin, rmax, rgba, depth)
+            u8, d = O.image_init(rgba, depth, 0)
+            O.image_to_canvas(u8, d)
+        else:
+            pl = [O.render_partials(ob, cam, W, H, sp["lut"], sp["sample_dist"], rmin, rmax, depth)
+                  for ob in oblocks]
+            O.partials_to_canvas(O.composite_partials(pl), cam, W, H, rgba, depth)
+
+    for _ in range(args.warmup):
+        frame()
+    t0 = time.time()
+    for _ in range(args.steps):
+        frame()
+    dt = (time.time() - t0) / args.steps
+    val = W * H / dt / 1e6
+    line = {"impl": "reference", "metric": "volume_render_mrays_per_s", "value": val, "unit": "Mrays/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "image": [W, H], "samples": SAMPLES},
+            "frames_per_s": 1.0 / dt,
+            "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": O.num_threads(), "kind": "port",
+                             "sample": "whole frame(s) of the workload, oracle/raycast_oracle.c + "
+                                       "composite_oracle.c with OpenMP (VTK-m/OpenMP reference is not "
+                                       "buildable here); field generation %.1fs excluded" % gen_s},
+            "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm, N == 1
+def run_single(args, wl):
+    import torch
+    from ascent_b200 import _lib
+    torch.cuda.set_device(0)
+    ctx = _lib.Context(0)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    blocks = block_layout(wl)
+    W, H = wl["W"], wl["H"]
+    nvox = int(np.prod(blocks[0]["dims"]))
+    fields = []
+    with torch.cuda.stream(stream):
+        for i, b in enumerate(blocks):
+            t = torch.empty(nvox, dtype=torch.float32, device="cuda")
+            ctx.synth_braid_dev(t.data_ptr(), _lib.VR_F32, b["dims"], b["start"], b["glob"])
+            fields.append(t)
+        stream.synchronize()
+        rmin = min(float(t.min()) for t in fields)
+        rmax = max(float(t.max()) for t in fields)
+    sp = scene_params(wl, blocks, (rmin, rmax))
+    ctx.set_tf(sp["lut"])
+    for i, b in enumerate(blocks):
+        ctx.block_uniform(i, b["dims"], b["origin"], b["spacing"], None, device_ptr=fields[i].data_ptr(),
+                          dtype=_lib.VR_F32)
+    cam = sp["cam"]
+    multi = len(blocks) > 1
+
+    def frame(ev=None):
+        ctx.canvas_clear(W, H)
+        if not multi:
+            if ev:
+                ev[0].record(stream)
+            ctx.trace_to_canvas(0, cam, sp["sample_dist"], rmin, rmax, False)
+            if ev:
+                ev[1].record(stream)
+            ctx.image_from_canvas()
+            rp, dp = ctx.image_ptrs()
+            ctx.image_to_canvas_dev(rp, dp)
+        else:
+            ctx.partials_begin(W, H)
+            if ev:
+                ev[0].record(stream)
+            for i in range(len(blocks)):
+                ctx.trace_to_partials(i, cam, sp["sample_dist"], rmin, rmax, True)
+            if ev:
+                ev[1].record(stream)
+            ctx.partials_composite()
+            ctx.partials_to_canvas(cam)
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            frame()
+        stream.synchronize()
+        l0 = ctx.kernel_launches()
+        clocks = ClockSampler(0)
+        clocks.start()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range(args.steps)]
+        t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t_begin.record(stream)
+        for k in range(args.steps):
+            frame(evs[k])
+        t_end.record(stream)
+        torch.cuda.synchronize()
+        clk = clocks.stop()
+        launches = ctx.kernel_launches() - l0
+        total_ms = t_begin.elapsed_time(t_end)
+        trace_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    ms = total_ms / args.steps
+    value = W * H / (ms * 1e-3) / 1e6
+
+    # ---- e2e: host buffers through the ABI a vtk-h caller uses, H2D + D2H inside the timed region
+    e2e = None
+    if not multi:
+        host_field = torch.empty(nvox, dtype=torch.float32, pin_memory=True)
+        host_field.copy_(fields[0])
+        rgba_h = torch.zeros(H * W * 4, dtype=torch.float32, pin_memory=True)
+        depth_h = torch.full((H * W,), 1.001, dtype=torch.float32, pin_memory=True)
+        hf, hr, hd = host_field.numpy(), rgba_h.numpy(), depth_h.numpy()
+        b = blocks[0]
+
+        def e2e_frame():
+            hr.fill(0.0)
+            hd.fill(1.001)
+            ctx.block_uniform(100, b["dims"], b["origin"], b["spacing"], hf)    # publish (H2D)
+            ctx.render_image(100, cam, W, H, sp["sample_dist"], rmin, rmax, hr, hd)  # canvas in/out
+        for _ in range(2):
+            e2e_frame()
+        t0 = time.perf_counter()
+        n_e2e = max(3, min(args.steps, 10))
+        for _ in range(n_e2e):
+            e2e_frame()
+        dt = (time.perf_counter() - t0) / n_e2e
+        e2e = {"value": W * H / dt / 1e6, "unit": "Mrays/s", "ms_per_step": dt * 1e3,
+               "h2d_bytes_per_step": nvox * 4 + W * H * 20, "d2h_bytes_per_step": W * H * 20,
+               "what": "vr_block_uniform(host field) + vr_render_image(host canvas in/out) per step"}
+        ctx.block_free(100)
+
+    # ---- roofline of the dominant kernel (trace), algorithmic bytes per launch
+    pk, pk_src = peaks()
+    n_launch = len(blocks)
+    alg_bytes = nvox * 4 * len(blocks) + W * H * 20  # N_vox*4 + W*H*20 per frame
+    achieved = alg_bytes / (trace_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "trace_kernel (sampler.cu)", "achieved": achieved,
+            "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+            "traffic": None, "algorithmic_bytes_per_frame": alg_bytes, "kernel_ms_per_frame": trace_ms,
+            "launches_per_frame": n_launch}
+
+    # ---- CPU baseline beside it: bounded sample of the same workload (rank 0, N == 1)
+    cpu = cpu_baseline_sample(wl, blocks, fields, sp, rmin, rmax) if not args.no_cpu else None
+
+    line = {"metric": "volume_render_mrays_per_s", "value": value, "unit": "Mrays/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "image": [W, H], "samples": SAMPLES,
+                       "path": "B (partials)" if multi else "A (image)",
+                       "l2": "inputs (%.0f MB field) larger than the 126 MB L2" % (nvox * 4 * len(blocks) / 1e6)},
+            "frames_per_s": 1e3 / ms, "composite_ms_per_frame": ms - trace_ms,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    ctx.close()
+
+
+def cpu_baseline_sample(wl, blocks, fields, sp, rmin, rmax):
+    from oracle import oracle as O
+    W, H = wl["W"], wl["H"]
+    cam = O.Camera.from_buffer_copy(bytes(sp["cam"]))
+    obs = [O.OracleBlock(b["dims"], f.cpu().numpy(), origin=b["origin"], spacing=b["spacing"])
+           for b, f in zip(blocks, fields)]
+    t0 = time.time()
+    n = 0
+    while True:
+        rgba, depth = O.new_canvas(W, H)
+        if len(obs) == 1:
+            O.render_to_canvas(obs[0], cam, W, H, sp["lut"], sp["sample_dist"], rmin, rmax, rgba, depth)
+            u8, d = O.image_init(rgba, depth, 0)
+            O.image_to_canvas(u8, d)
+        else:
+            pl = [O.render_partials(ob, cam, W, H, sp["lut"], sp["sample_dist"], rmin, rmax, depth) for ob in obs]
+            O.partials_to_canvas(O.composite_partials(pl), cam, W, H, rgba, depth)
+        n += 1
+        if time.time() - t0 > 10.0 or n >= 20:
+            break
+    dt = (time.time() - t0) / n
+    return {"value": W * H / dt / 1e6, "unit": "Mrays/s", "cores": O.num_threads(), "kind": "port",
+            "ms_per_step": dt * 1e3,
+            "sample": "%d whole frame(s) of the same workload on the host cores (oracle port of the "
+                      "reference's VTK-m/OpenMP algorithm; the reference itself is not buildable here)" % n}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, choices=[None, "c2", "c3"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
+    args = ap.parse_args()
+    wname = args.workload or ("c2" if args.gpus == 1 else "c3")
+    wl = workload_c2() if wname == "c2" else workload_c3()
+    if args.impl == "reference":
+        if args.steps > 5:
+            args.steps = 5
+        args.warmup = min(args.warmup, 1)
+        return run_reference(args, wl)
+    if args.gpus == 1:
+        return run_single(args, wl)
+    from ascent_b200 import distributed
+    return distributed.run_bench(args, wl, sys.modules[__name__])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,226 @@
+/*
+ * vr_b200.h -- C ABI of the B200-native volume-render backend (libvr_b200.so).
+ *
+ * Drop-in boundary for Ascent's `volume` plot hot path.  The
+ * reference has no FFI for this path today; these entry points are what
+ * vtkh::VolumeRenderer would bind at its four private call sites
+ *   (1) m_mapper->RenderCells            src/libs/vtkh/rendering/VolumeRenderer.cpp:516-528
+ *   (2) StructuredWrapper::render        src/libs/vtkh/rendering/VolumeRenderer.cpp:230-284
+ *   (3) m_compositor->AddImage/Composite src/libs/vtkh/rendering/VolumeRenderer.cpp:652-688
+ *   (4) PartialCompositor::composite +   src/libs/vtkh/rendering/VolumeRenderer.cpp:580-595
+ *       partials_to_canvas               src/libs/vtkh/rendering/VolumeRenderer.cpp:287-391
+ * (see INTEGRATION.md for the vtk-h side of the binding).
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Every call returns a vr_status;
+ * vr_last_error(ctx) gives the message (the vtk-h wrapper rethrows it as vtkh::Error).  The
+ * caller owns every host buffer; the library owns device copies.  One context drives one GPU
+ * from one host thread (Ascent: one MPI rank per GPU, ascent_main_runtime.cpp:190-192).
+ * All work is queued on the context's CUDA stream; entry points that fill HOST memory
+ * synchronise that stream before returning, `_dev`/async ones do not.
+ * There is no CPU fallback: without a usable sm_100 device vr_create fails.
+ */
+#ifndef VR_B200_H
+#define VR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VR_API __attribute__((visibility("default")))
+
+typedef struct vr_ctx vr_ctx;
+
+typedef enum
+{
+  VR_OK = 0,
+  VR_ERR_INVALID = 1, /* bad argument (vtk-h: Error thrown by the caller-side checks) */
+  VR_ERR_CUDA = 2,    /* CUDA runtime failure */
+  VR_ERR_NOMEM = 3,
+  VR_ERR_STATE = 4    /* call made in the wrong order (e.g. composite before render) */
+} vr_status;
+
+enum { VR_F32 = 0, VR_F64 = 1 };     /* field scalar type (ascent_vtkh_data_adapter.cpp:1843-1887) */
+enum { VR_POINT = 0, VR_CELL = 1 };  /* field association */
+enum { VR_HOST = 0, VR_DEVICE = 1 }; /* where a caller-supplied pointer lives */
+
+/* vtkm::rendering::Camera as parse_camera fills it
+ * (ascent_runtime_conduit_to_vtkm_parsing.cpp:97-173); f32 like VTK-m's. */
+typedef struct
+{
+  float position[3];
+  float look_at[3];
+  float up[3];
+  float fov;  /* vertical, degrees */
+  float zoom; /* vtkm zoom factor (1 = none) */
+  float xpan, ypan;
+  float near_plane, far_plane;
+} vr_camera;
+
+/* vtkh::VolumePartial<float>, src/libs/vtkh/compositing/VolumePartial.hpp:48-56 (24-byte POD) */
+typedef struct
+{
+  int32_t pixel_id;
+  float depth;
+  float rgb[3];
+  float alpha;
+} vr_partial;
+
+/* ------------------------------------------------------------------ context */
+VR_API vr_status vr_create(int device, vr_ctx** out);
+VR_API void vr_destroy(vr_ctx* ctx);
+VR_API const char* vr_last_error(const vr_ctx* ctx); /* ctx may be NULL: last vr_create error */
+/* Use a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the own stream. */
+VR_API vr_status vr_set_stream(vr_ctx* ctx, void* cuda_stream);
+VR_API vr_status vr_synchronize(vr_ctx* ctx);
+/* Number of this library's kernels launched on this context since creation (bench evidence). */
+VR_API uint64_t vr_kernel_launches(const vr_ctx* ctx);
+
+/* ------------------------------------------------------------------ blocks (domains)
+ * Replaces the vtkm::cont::DataSet a StructuredWrapper holds (VolumeRenderer.cpp:223-229,
+ * SetInput :868-907).  dims are POINT dims, x fastest: index (k*ny + j)*nx + i.  A cell field
+ * has (nx-1)(ny-1)(nz-1) values.  The field is copied (or adopted, see below) once per publish
+ * and reused by every render of the batch.
+ *   where == VR_HOST   : `field` is host memory, copied to the device.
+ *   where == VR_DEVICE : `field` is device memory on this GPU and is used in place (zero copy;
+ *                        must outlive the block).                                            */
+VR_API vr_status vr_block_uniform(vr_ctx* ctx, int block_id, const int dims[3],
+                                  const float origin[3], const float spacing[3], const void* field,
+                                  int dtype, int assoc, int where);
+VR_API vr_status vr_block_rectilinear(vr_ctx* ctx, int block_id, const int dims[3], const double* x,
+                                      const double* y, const double* z, const void* field,
+                                      int dtype, int assoc, int where);
+VR_API vr_status vr_block_free(vr_ctx* ctx, int block_id);
+/* coords.GetBounds(): xmin,xmax,ymin,ymax,zmin,zmax */
+VR_API vr_status vr_block_bounds(vr_ctx* ctx, int block_id, double out[6]);
+
+/* ------------------------------------------------------------------ transfer function
+ * The 1024 x float4 table Mapper::SetActiveColorTable / convert_table build on the host
+ * (VolumeRenderer.cpp:64-91, :518): already opacity-corrected and uint8-rounded.             */
+VR_API vr_status vr_set_tf(vr_ctx* ctx, const float* rgba, int n_entries);
+
+/* ------------------------------------------------------------------ device canvas
+ * The context keeps one float canvas (RGBA f32 + depth f32, W x H) in HBM: the stand-in for
+ * vtkm::rendering::CanvasRayTracer's buffers (Render.hpp:80).                                 */
+VR_API vr_status vr_canvas_clear(vr_ctx* ctx, int width, int height); /* colour 0, depth 1.001 */
+VR_API vr_status vr_canvas_upload(vr_ctx* ctx, int width, int height, const float* rgba,
+                                  const float* depth);
+VR_API vr_status vr_canvas_download(vr_ctx* ctx, float* rgba, float* depth); /* syncs */
+VR_API vr_status vr_canvas_ptrs(vr_ctx* ctx, void** rgba_dev, void** depth_dev);
+
+/* ------------------------------------------------------------------ (1) path A render
+ * MapperVolume::RenderCells for one block and one camera: ray generation over the block's
+ * screen subset, canvas-depth clamp, bounds intersection, sampling, blend over the canvas and
+ * projected entry depth (K1-K7 fused in one kernel), on the DEVICE canvas.
+ * use_canvas_depth: 0 = canvas is known to be cleared (skip the per-ray un-projection, result
+ * identical); 1 = clamp rays at the canvas depth (opaque plots rendered before the volume,
+ * Scene.cpp:200-207).                                                                          */
+VR_API vr_status vr_trace_to_canvas(vr_ctx* ctx, int block_id, const vr_camera* cam,
+                                    float sample_dist, float range_min, float range_max,
+                                    int use_canvas_depth);
+/* Host-buffer form of the same call, exactly what VolumeRenderer.cpp:516-528 needs: canvas in,
+ * canvas out (uploads, traces, downloads, syncs).                                              */
+VR_API vr_status vr_render_image(vr_ctx* ctx, int block_id, const vr_camera* cam, int width,
+                                 int height, float sample_dist, float range_min, float range_max,
+                                 float* rgba_inout, float* depth_inout);
+
+/* ------------------------------------------------------------------ (2) path B render
+ * StructuredWrapper::render: same trace on a zeroed ray buffer, then keep rays with
+ * alpha >= 0.001 as partials {pixel, exit distance, rgb, alpha}.  Partials are APPENDED to the
+ * context's device partial list (one list per frame, all local domains).                       */
+VR_API vr_status vr_partials_begin(vr_ctx* ctx, int width, int height);
+VR_API vr_status vr_trace_to_partials(vr_ctx* ctx, int block_id, const vr_camera* cam,
+                                      float sample_dist, float range_min, float range_max,
+                                      int use_canvas_depth);
+VR_API vr_status vr_partials_count(vr_ctx* ctx, size_t* n); /* syncs */
+VR_API vr_status vr_partials_download(vr_ctx* ctx, vr_partial* out, size_t capacity, size_t* n);
+/* Host-buffer form: library-allocated array, release with vr_free.  Order within the array is
+ * unspecified (the reference's is ray order; compositing sorts anyway).                        */
+VR_API vr_status vr_render_partials(vr_ctx* ctx, int block_id, const vr_camera* cam, int width,
+                                    int height, float sample_dist, float range_min,
+                                    float range_max, const float* depth_in, vr_partial** out,
+                                    size_t* n);
+VR_API void vr_free(void* p);
+
+/* ------------------------------------------------------------------ (3) image compositing
+ * Image::Init (Image.hpp:80-113): quantise the device canvas to RGBA8 (truncation) + depth
+ * (negative -> |d|) into the context's exchange image.                                         */
+VR_API vr_status vr_image_from_canvas(vr_ctx* ctx);
+VR_API vr_status vr_image_download(vr_ctx* ctx, uint8_t* rgba, float* depth); /* syncs */
+/* ImageCompositor::OrderedComposite over n_layers images resident on THIS device
+ * (layer l at rgba + l*layer_stride_px*4, depth + l*layer_stride_px): sort by vis_order, fold
+ * front-to-back with the truncating uint8 over operator, per pixel, in one pass.  All pointers
+ * are device pointers; out may alias layer 0.                                                  */
+VR_API vr_status vr_fold_images_dev(vr_ctx* ctx, const uint8_t* rgba, const float* depth,
+                                    size_t layer_stride_px, const int* vis_order_host,
+                                    int n_layers, size_t n_pixels, uint8_t* out_rgba,
+                                    float* out_depth);
+/* Host-buffer form of Compositor::{AddImage x n, Composite} in VIS_ORDER_BLEND mode
+ * (Compositor.cpp:146-183,221-234): n float images -> composited RGBA8 + depth.               */
+VR_API vr_status vr_composite_images(vr_ctx* ctx, const float* rgba, const float* depth,
+                                     const int* vis_order, int n_images, int width, int height,
+                                     uint8_t* out_rgba, float* out_depth);
+/* ImageCompositor::ZBufferComposite (ImageCompositor.hpp:49-76), device pointers, in place.   */
+VR_API vr_status vr_zbuffer_composite_dev(vr_ctx* ctx, uint8_t* front_rgba, float* front_depth,
+                                          const uint8_t* rgba, const float* depth,
+                                          size_t n_pixels);
+/* Renderer::ImageToCanvas (Renderer.cpp:265-283): composited RGBA8 (device) -> device canvas.  */
+VR_API vr_status vr_image_to_canvas_dev(vr_ctx* ctx, const uint8_t* rgba, const float* depth);
+
+/* ------------------------------------------------------------------ (4) partial compositing
+ * PartialCompositor::composite_partials (PartialCompositor.cpp:329-488) on the context's
+ * device partial list: order by (pixel, depth) [ties: list order], fold front-to-back per
+ * pixel with VolumePartial::blend; leaves <= 1 partial per covered pixel.                      */
+VR_API vr_status vr_partials_composite(vr_ctx* ctx);
+/* partials_to_canvas (VolumeRenderer.cpp:287-391) from the composited list onto the device
+ * canvas (which must have the frame's width/height).                                           */
+VR_API vr_status vr_partials_to_canvas(vr_ctx* ctx, const vr_camera* cam);
+/* Host-buffer form of PartialCompositor::composite for one rank: n_in partials in (any order),
+ * composited partials out (capacity n_in).                                                     */
+VR_API vr_status vr_composite_partials(vr_ctx* ctx, const vr_partial* in, size_t n_in, int width,
+                                       int height, vr_partial* out, size_t* n_out);
+
+/* ------------------------------------------------------------------ multi-GPU exchange
+ * One process per GPU.  Every rank allocates one exchange arena, publishes its CUDA IPC handle
+ * through whatever transport the host has (MPI_Allgather in Ascent, torch.distributed in the
+ * harness) and maps its peers' arenas; after that images/partials move GPU-to-GPU over NVLink
+ * inside the compositing kernels themselves (direct-send: DirectSendCompositor.cpp:121-181,
+ * vtkh_diy_partial_redistribute.hpp:58-152) -- no host staging, no MPI in the data path.       */
+#define VR_IPC_HANDLE_BYTES 64
+VR_API vr_status vr_comm_init(vr_ctx* ctx, int rank, int n_ranks, size_t max_pixels,
+                              size_t max_partials, void* handle_out /* VR_IPC_HANDLE_BYTES */);
+VR_API vr_status vr_comm_connect(vr_ctx* ctx, const void* all_handles /* n_ranks * 64 B */);
+/* Path A, all ranks call collectively once per image: direct-send exchange of the quantised
+ * images + visibility-ordered fold + gather to rank 0, fused in one kernel per rank (peer
+ * loads of the owned tile from every rank, peer store of the folded tile into rank 0).
+ * vis_order[r] = composite order of rank r's image (VolumeRenderer.cpp:833-867).
+ * On rank 0 the composited image is left in the context (vr_image_result_*).                   */
+VR_API vr_status vr_comm_composite_images(vr_ctx* ctx, const int* vis_order);
+VR_API vr_status vr_image_result_download(vr_ctx* ctx, uint8_t* rgba, float* depth); /* syncs */
+VR_API vr_status vr_image_result_to_canvas(vr_ctx* ctx);
+/* Path B, collective: redistribute partials by pixel-range owner, sort+fold on the owner,
+ * gather to rank 0 (P2-P5).  On rank 0 the result replaces the context's partial list.        */
+VR_API vr_status vr_comm_composite_partials(vr_ctx* ctx);
+/* Device pointers into this rank's arena for transports that move the bytes themselves
+ * (NCCL send/recv baseline in the harness).                                                    */
+VR_API vr_status vr_image_ptrs(vr_ctx* ctx, void** rgba8_dev, void** depth_dev);
+
+/* ------------------------------------------------------------------ host-side helpers
+ * The driver logic of VolumeRenderer that stays on the CPU and the camera
+ * subset used by the tracer (K1), exported so hosts need not re-derive them.                   */
+VR_API float vr_sample_distance(const double global_bounds[6], float samples);
+VR_API void vr_visibility_order(const double* domain_bounds /* n x 6 */, int n_domains,
+                                const vr_camera* cam, int* order_out);
+VR_API void vr_find_subset(const vr_camera* cam, int width, int height, const double bounds[6],
+                           int out_minx_miny_w_h[4]);
+/* Synthetic braid field (Conduit blueprint::mesh::examples::braid) written straight into device
+ * memory: window (i0,j0,k0)+(nx,ny,nz) of a (gx,gy,gz) global grid.  Bench input generator.    */
+VR_API vr_status vr_synth_braid_dev(vr_ctx* ctx, void* field_dev, int dtype, const int n[3],
+                                    const int start[3], const int global[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VR_B200_H */

@@ -21,6 +21,7 @@
 #include <string.h>
 
 #define ORC_API __attribute__((visibility("default")))
+#define STD_MIN(a, b) (((b) < (a)) ? (b) : (a))
 
 typedef struct
 {
@@ -66,9 +67,10 @@ ORC_API void orc_blend(uint8_t* front_rgba, float* front_depth, const uint8_t* b
     front_rgba[o + 1] += (unsigned char)(opacity * back_rgba[o + 1] / 255);
     front_rgba[o + 2] += (unsigned char)(opacity * back_rgba[o + 2] / 255);
     front_rgba[o + 3] += (unsigned char)(opacity * back_rgba[o + 3] / 255);
-    float d1 = fminf(front_depth[i], 1.001f);
-    float d2 = fminf(back_depth[i], 1.001f);
-    front_depth[i] = fminf(d1, d2);
+    /* std::min(a,b) = (b < a) ? b : a  -- NOT fminf: a NaN first argument survives */
+    float d1 = STD_MIN(front_depth[i], 1.001f);
+    float d2 = STD_MIN(back_depth[i], 1.001f);
+    front_depth[i] = STD_MIN(d1, d2);
   }
 }
 
@@ -199,6 +201,7 @@ ORC_API int64_t orc_composite_partials(orc_partial* partials, int64_t n, orc_par
 ORC_API int orc_partial_owner(int pixel_id, int min_pixel, int max_pixel, int n_ranks)
 {
   int width = (max_pixel - min_pixel + 1) / n_ranks;
+  if (width < 1) width = 1; /* fewer pixels than ranks divides by zero in DIY; guard */
   int res = (pixel_id - min_pixel) / width;
   if (res >= n_ranks) res = n_ranks - 1;
   if (res < 0) res = 0;

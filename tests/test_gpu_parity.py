@@ -1,0 +1,426 @@
+"""Parity of the CUDA path (through the C ABI, include/vr_b200.h) against the CPU oracle.
+
+Tolerance (BASELINE.json north_star): >= 99.9 % of pixels within 1/255 per RGBA channel, every
+pixel within 3/255, PSNR >= 50 dB; integer/index work (uint8 fold, visibility order, partial sort
+order, pixel ids) bit-exact.  Because sampler.cu is compiled without FMA contraction the float
+canvas is in fact expected to be bit-identical; that stronger property is asserted too."""
+import numpy as np
+import pytest
+
+import scenes
+from ascent_b200 import _lib, color_table, datasets
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+def check_tolerance(mine, ref, exact=True):
+    """mine/ref float RGBA in [0,1], shape (N,4)."""
+    d = np.abs(mine.astype(np.float64) - ref.astype(np.float64)).max(axis=1)
+    assert (d <= 1.0 / 255.0).mean() >= 0.999
+    assert d.max() <= 3.0 / 255.0
+    mse = ((mine.astype(np.float64) - ref.astype(np.float64)) ** 2).mean()
+    psnr = 99.0 if mse == 0 else 10.0 * np.log10(1.0 / mse)
+    assert psnr >= 50.0
+    if exact:
+        assert (mine.view(np.uint32) == ref.view(np.uint32)).all(axis=1).mean() >= 0.9999
+
+
+def gpu_path_a_canvas(ctx, dom, sc, use_depth=False, canvas=None):
+    W, H = sc["W"], sc["H"]
+    ctx.block_from_domain(0, dom)
+    ctx.set_tf(sc["lut"])
+    if canvas is None:
+        ctx.canvas_clear(W, H)
+    else:
+        ctx.canvas_upload(W, H, canvas[0], canvas[1])
+    ctx.trace_to_canvas(0, sc["cam"], sc["sample_dist"], sc["rmin"], sc["rmax"], use_depth)
+    return ctx.canvas_download(W, H)
+
+
+def oracle_canvas(dom, sc, canvas=None, use_depth=True):
+    W, H = sc["W"], sc["H"]
+    if canvas is None:
+        rgba, depth = O.new_canvas(W, H)
+    else:
+        rgba, depth = canvas[0].copy(), canvas[1].copy()
+    ns = O.render_to_canvas(scenes.oracle_block(dom), sc["cam"], W, H, sc["lut"], sc["sample_dist"],
+                            sc["rmin"], sc["rmax"], rgba, depth, use_depth=use_depth)
+    return rgba, depth, ns
+
+
+def depth_equal(a, b, where):
+    a, b = a[where], b[where]
+    return np.array_equal(a, b, equal_nan=True)
+
+
+# ------------------------------------------------------------------ config c1 and friends
+@pytest.mark.parametrize("res", [(256, 256), (1024, 1024), (640, 360)])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_c1_braid_uniform(ctx, res, dtype):
+    """BASELINE config 1: braid uniform 32^3, default camera, S=100 (1024^2 is the named size)."""
+    dom = datasets.braid_uniform(32, dtype=dtype)
+    b = datasets.domain_bounds(dom)
+    sc = dict(W=res[0], H=res[1], cam=O.camera_reset_to_bounds(b),
+              lut=color_table.parse_color_table(scenes.RAMP_TF).corrected_opacity(100).lut(),
+              sample_dist=O.sample_distance(b, 100))
+    sc["rmin"], sc["rmax"] = scenes.field_range([dom])
+    rgba, depth = gpu_path_a_canvas(ctx, dom, sc)
+    o_rgba, o_depth, _ = oracle_canvas(dom, sc)
+    check_tolerance(rgba, o_rgba)
+    assert depth_equal(depth, o_depth, o_rgba[:, 3] > 0)
+    # pixels outside the block's screen subset are untouched
+    assert np.array_equal(depth == np.float32(1.001), o_depth == np.float32(1.001))
+
+
+def test_default_transfer_function(ctx):
+    """the reference's default TF (VolumeRenderer.cpp:395-408) on c1."""
+    dom = datasets.braid_uniform(32)
+    b = datasets.domain_bounds(dom)
+    sc = dict(W=300, H=300, cam=O.camera_reset_to_bounds(b),
+              lut=color_table.default_volume_table().corrected_opacity(100).lut(),
+              sample_dist=O.sample_distance(b, 100))
+    sc["rmin"], sc["rmax"] = scenes.field_range([dom])
+    rgba, _ = gpu_path_a_canvas(ctx, dom, sc)
+    check_tolerance(rgba, oracle_canvas(dom, sc)[0])
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_golden_scenes_multi_render(ctx, which):
+    sc = scenes.multi_render_scene(which)
+    rgba, depth = gpu_path_a_canvas(ctx, sc["doms"][0], sc)
+    o_rgba, o_depth, _ = oracle_canvas(sc["doms"][0], sc)
+    check_tolerance(rgba, o_rgba)
+
+
+@pytest.mark.parametrize("samples", [1, 7, 100, 887])
+def test_sample_counts(ctx, samples):
+    """SetNumberOfSamples extremes: 1 sample per diagonal up to ~voxel-sized steps."""
+    dom = datasets.braid_uniform(24, dtype=np.float32)
+    b = datasets.domain_bounds(dom)
+    cam = O.camera_reset_to_bounds(b)
+    O.camera_azimuth(cam, 30.0)
+    O.camera_elevation(cam, 20.0)
+    sc = dict(W=200, H=160, cam=cam,
+              lut=color_table.parse_color_table(scenes.RAMP_TF).corrected_opacity(samples).lut(),
+              sample_dist=O.sample_distance(b, samples))
+    sc["rmin"], sc["rmax"] = scenes.field_range([dom])
+    rgba, _ = gpu_path_a_canvas(ctx, dom, sc)
+    check_tolerance(rgba, oracle_canvas(dom, sc)[0])
+
+
+def test_early_termination(ctx):
+    """opaque TF: rays stop at alpha >= 1 after the same number of samples."""
+    dom = datasets.braid_uniform(20, dtype=np.float32)
+    b = datasets.domain_bounds(dom)
+    tf = color_table.ColorTable("cool to warm")
+    tf.add_point_alpha(0.0, 1.0)
+    tf.add_point_alpha(1.0, 1.0)
+    sc = dict(W=128, H=128, cam=O.camera_reset_to_bounds(b), lut=tf.lut(),
+              sample_dist=O.sample_distance(b, 100))
+    sc["rmin"], sc["rmax"] = scenes.field_range([dom])
+    rgba, _ = gpu_path_a_canvas(ctx, dom, sc)
+    o = oracle_canvas(dom, sc)[0]
+    check_tolerance(rgba, o)
+    assert o[:, 3].max() == 1.0
+
+
+def test_camera_inside_volume_and_zoom(ctx):
+    dom = datasets.braid_uniform(20, dtype=np.float32)
+    b = datasets.domain_bounds(dom)
+    for zoom, pos in [(1.0, [1., 2., 3.]), (2.5, None), (0.5, None)]:
+        cam = O.camera_reset_to_bounds(b)
+        cam.zoom = zoom
+        if pos is not None:
+            cam.position[:] = pos
+            cam.look_at[:] = [0., 0., -1.]
+        sc = dict(W=160, H=120, cam=cam,
+                  lut=color_table.parse_color_table(scenes.RAMP_TF).corrected_opacity(100).lut(),
+                  sample_dist=O.sample_distance(b, 100))
+        sc["rmin"], sc["rmax"] = scenes.field_range([dom])
+        rgba, _ = gpu_path_a_canvas(ctx, dom, sc)
+        check_tolerance(rgba, oracle_canvas(dom, sc)[0])
+
+
+def test_volume_behind_camera_is_a_no_op(ctx):
+    dom = datasets.braid_uniform(8, dtype=np.float32)
+    b = datasets.domain_bounds(dom)
+    cam = O.make_camera([0, 0, 40], [0, 0, 80], [0, 1, 0], near=0.1, far=500.)
+    sc = dict(W=64, H=64, cam=cam, lut=color_table.default_volume_table().lut(), sample_dist=0.3,
+              rmin=-10., rmax=10.)
+    rgba, depth = gpu_path_a_canvas(ctx, dom, sc)
+    o_rgba, o_depth, _ = oracle_canvas(dom, sc)
+    assert np.array_equal(rgba, o_rgba) and rgba.max() == 0.0
+
+
+# ------------------------------------------------------------------ rectilinear / cell fields
+@pytest.mark.parametrize("power", [1.0, 1.5, 0.6])
+def test_rectilinear(ctx, power):
+    """config c4 in small: rectilinear braid with warped axes, cinema cameras."""
+    dom = datasets.braid_rectilinear(40, 36, 44, power=power, dtype=np.float32)
+    b = datasets.domain_bounds(dom)
+    lut = color_table.parse_color_table(scenes.RAMP_TF).corrected_opacity(100).lut()
+    rmin, rmax = scenes.field_range([dom])
+    for phi, theta in [(-180., 0.), (-45., 22.5), (90., 67.5), (135., 157.5)]:
+        cam = scenes.cinema_camera(b, phi, theta)
+        sc = dict(W=192, H=192, cam=cam, lut=lut, sample_dist=O.sample_distance(b, 100), rmin=rmin,
+                  rmax=rmax)
+        rgba, _ = gpu_path_a_canvas(ctx, dom, sc)
+        check_tolerance(rgba, oracle_canvas(dom, sc)[0])
+
+
+def test_mpi_golden_scene_rectilinear_f64(ctx):
+    sc = scenes.mpi_volume_scene()
+    for dom in sc["doms"]:
+        rgba, _ = gpu_path_a_canvas(ctx, dom, sc)
+        check_tolerance(rgba, oracle_canvas(dom, sc)[0])
+
+
+@pytest.mark.parametrize("kind", ["uniform", "rectilinear"])
+def test_cell_centred_field(ctx, kind):
+    if kind == "uniform":
+        dom = datasets.braid_uniform(21, dtype=np.float32)
+    else:
+        dom = datasets.braid_rectilinear(21, power=1.3, dtype=np.float32)
+    n = 20
+    pts = dom["field"].reshape(21, 21, 21)
+    dom = dict(dom, field=np.ascontiguousarray(pts[:n, :n, :n]).reshape(-1), assoc="cell")
+    b = datasets.domain_bounds(dom)
+    cam = O.camera_reset_to_bounds(b)
+    O.camera_azimuth(cam, -25.0)
+    sc = dict(W=150, H=150, cam=cam,
+              lut=color_table.parse_color_table(scenes.RAMP_TF).corrected_opacity(100).lut(),
+              sample_dist=O.sample_distance(b, 100))
+    sc["rmin"], sc["rmax"] = scenes.field_range([dom])
+    rgba, _ = gpu_path_a_canvas(ctx, dom, sc)
+    check_tolerance(rgba, oracle_canvas(dom, sc)[0])
+
+
+# ------------------------------------------------------------------ K2 / K7 with a live canvas
+def test_existing_canvas_depth_and_colour(ctx):
+    """opaque geometry already on the canvas: rays stop at its depth, colour blends over it."""
+    dom = datasets.braid_uniform(24, dtype=np.float32)
+    b = datasets.domain_bounds(dom)
+    W, H = 160, 128
+    cam = O.camera_reset_to_bounds(b)
+    rng = np.random.default_rng(3)
+    rgba0, depth0 = O.new_canvas(W, H)
+    yy, xx = np.mgrid[0:H, 0:W]
+    disk = ((xx - 80) ** 2 + (yy - 64) ** 2) < 40 ** 2
+    # image-space depths between near and far that land inside the volume
+    pv = O.projview(cam, W, H)
+    zs = []
+    for z in (-5.0, 5.0):
+        q = pv @ np.array([0, 0, z, 1], np.float32)
+        zs.append(0.5 * q[2] / q[3] + 0.5)
+    dvals = rng.uniform(min(zs), max(zs), disk.sum()).astype(np.float32)
+    depth0.reshape(H, W)[disk] = dvals
+    rgba0.reshape(H, W, 4)[disk] = [0.2, 0.4, 0.6, 1.0]
+    sc = dict(W=W, H=H, cam=cam,
+              lut=color_table.parse_color_table(scenes.RAMP_TF).corrected_opacity(100).lut(),
+              sample_dist=O.sample_distance(b, 100))
+    sc["rmin"], sc["rmax"] = scenes.field_range([dom])
+    rgba, depth = gpu_path_a_canvas(ctx, dom, sc, use_depth=True, canvas=(rgba0, depth0))
+    o_rgba, o_depth, _ = oracle_canvas(dom, sc, canvas=(rgba0, depth0))
+    check_tolerance(rgba, o_rgba)
+    # and through the host-buffer entry point vtk-h would call
+    r2, d2 = rgba0.copy(), depth0.copy()
+    ctx.render_image(0, cam, W, H, sc["sample_dist"], sc["rmin"], sc["rmax"], r2, d2)
+    assert np.array_equal(r2, rgba)
+
+
+# ------------------------------------------------------------------ path B (partials)
+def partial_sets_equal(a, b):
+    a = np.sort(a, order=["pixel_id", "depth"])
+    b = np.sort(b, order=["pixel_id", "depth"])
+    assert a.size == b.size
+    assert np.array_equal(a["pixel_id"], b["pixel_id"])
+    assert np.array_equal(a["depth"], b["depth"])
+    return a, b
+
+
+def test_render_partials_single_block(ctx):
+    dom = datasets.braid_uniform(24, dtype=np.float32)
+    b = datasets.domain_bounds(dom)
+    W, H = 200, 150
+    cam = O.camera_reset_to_bounds(b)
+    O.camera_azimuth(cam, 15.0)
+    lut = color_table.parse_color_table(scenes.RAMP_TF).corrected_opacity(100).lut()
+    rmin, rmax = scenes.field_range([dom])
+    sd = O.sample_distance(b, 100)
+    ctx.block_from_domain(0, dom)
+    ctx.set_tf(lut)
+    mine = ctx.render_partials(0, cam, W, H, sd, rmin, rmax, None)
+    _, depth = O.new_canvas(W, H)
+    ref = O.render_partials(scenes.oracle_block(dom), cam, W, H, lut, sd, rmin, rmax, depth)
+    a, r = partial_sets_equal(mine, ref)
+    assert np.array_equal(a["rgb"], r["rgb"]) and np.array_equal(a["alpha"], r["alpha"])
+    assert ref["alpha"].min() >= 0.001
+
+
+@pytest.mark.parametrize("n_block,per_axis,az", [(12, 2, 0.0), (9, 3, 37.0)])
+def test_multi_domain_path_b(ctx, n_block, per_axis, az):
+    """configs c3(N=1)/c5 in small: several uniform blocks on one GPU -> partial compositing."""
+    doms = datasets.braid_uniform_blocks(n_block, per_axis, dtype=np.float32)
+    gb = datasets.union_bounds([datasets.domain_bounds(d) for d in doms])
+    W, H = 240, 200
+    cam = O.camera_reset_to_bounds(gb)
+    O.camera_azimuth(cam, az)
+    O.camera_elevation(cam, az / 3.0)
+    sc = dict(doms=doms, cam=cam, W=W, H=H,
+              lut=color_table.parse_color_table(scenes.RAMP_TF).corrected_opacity(100).lut(),
+              sample_dist=O.sample_distance(gb, 100))
+    sc["rmin"], sc["rmax"] = scenes.field_range(doms)
+    ref_partials, ref_rgba, ref_depth = scenes.oracle_path_b(sc)
+
+    ctx.set_tf(sc["lut"])
+    for i, d in enumerate(doms):
+        ctx.block_from_domain(i, d)
+    ctx.canvas_clear(W, H)
+    ctx.partials_begin(W, H)
+    for i in range(len(doms)):
+        ctx.trace_to_partials(i, cam, sc["sample_dist"], sc["rmin"], sc["rmax"], True)
+    ctx.partials_composite()
+    mine = ctx.partials_download()
+    ctx.partials_to_canvas(cam)
+    rgba, depth = ctx.canvas_download(W, H)
+    for i in range(len(doms)):
+        ctx.block_free(i)
+
+    a = np.sort(mine, order="pixel_id")
+    r = np.sort(ref_partials, order="pixel_id")
+    assert np.array_equal(a["pixel_id"], r["pixel_id"])       # pixel ownership: exact
+    assert np.array_equal(a["depth"], r["depth"])             # front partial's depth survives: exact
+    assert np.abs(a["rgb"] - r["rgb"]).max() <= 1e-6 and np.abs(a["alpha"] - r["alpha"]).max() <= 1e-6
+    check_tolerance(rgba, ref_rgba, exact=False)
+    cov = ref_rgba[:, 3] > 0
+    assert np.allclose(depth[cov], ref_depth[cov], rtol=0, atol=1e-6)
+
+
+# ------------------------------------------------------------------ compositing kernels
+def test_quantise_and_fold_bit_exact(ctx):
+    rng = np.random.default_rng(11)
+    W, H, n_img = 333, 77, 5
+    alpha = rng.random((n_img, H * W, 1), dtype=np.float32)
+    rgba = np.concatenate([rng.random((n_img, H * W, 3), dtype=np.float32) * alpha, alpha], axis=2)
+    rgba[rng.random((n_img, H * W)) < 0.25] = 0
+    rgba[0, :10] = 1.0
+    depth = (rng.random((n_img, H * W), dtype=np.float32) * 1.3 - 0.1).astype(np.float32)
+    depth[1, :5] = np.nan
+    depth[2, 5:9] = np.inf
+    order = rng.permutation(n_img).astype(np.int32)
+    out, od = ctx.composite_images(rgba, depth, order, W, H)
+    q = [O.image_init(rgba[i], depth[i], 0) for i in range(n_img)]
+    ref, rd = O.ordered_composite(np.stack([x[0] for x in q]), np.stack([x[1] for x in q]), order)
+    assert np.array_equal(out, ref)
+    assert np.array_equal(od, rd, equal_nan=True)
+
+
+def test_apcomp_known_answer_scene_through_abi(ctx, golden_dir):
+    """the reference's own c_order scene and golden (t_apcomp_c_order.cpp) on the GPU path."""
+    import os
+    g = np.load(os.path.join(golden_dir, "apcomp_goldens.npz"))["apcomp_c_order"]
+    imgs = [scenes.apcomp_image(i) for i in range(4)]
+    out, _ = ctx.composite_images(np.stack([i[0] for i in imgs]), np.stack([i[1] for i in imgs]),
+                                  np.arange(4, dtype=np.int32), 1024, 1024)
+    out = out.reshape(1024, 1024, 4)
+    assert np.array_equal(out, g)
+    assert tuple(out[600, 450]) == (255, 128, 65, 222)
+
+
+def test_apcomp_partial_scene_through_abi(ctx, golden_dir):
+    import os
+    g = np.load(os.path.join(golden_dir, "apcomp_goldens.npz"))["apcomp_volume_partial"]
+    lists = [scenes.apcomp_partials(i) for i in range(4)]
+    res = ctx.composite_partials(np.concatenate(lists), 1024, 1024)
+    img = scenes.partials_to_image(res, 1024, 1024)
+    assert np.array_equal(img, g)
+    assert tuple(img[600, 450]) == (255, 127, 63, 223)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_partial_composite_random_with_ties(ctx, seed):
+    """random partial lists incl. equal (pixel, depth) keys: order = list order (documented
+    tie-break), empty/alpha-1/alpha-0 edge cases of VolumePartial::blend."""
+    rng = np.random.default_rng(seed)
+    W, H = 64, 48
+    n = 20000
+    p = np.zeros(n, O.PARTIAL_DTYPE)
+    p["pixel_id"] = rng.integers(0, W * H // 2, n)
+    p["depth"] = rng.integers(0, 6, n).astype(np.float32)  # many ties
+    a = rng.random(n, dtype=np.float32)
+    a[rng.random(n) < 0.1] = 1.0
+    a[rng.random(n) < 0.1] = 0.0
+    p["alpha"] = a
+    p["rgb"] = rng.random((n, 3), dtype=np.float32) * a[:, None]
+    mine = np.sort(ctx.composite_partials(p, W, H), order="pixel_id")
+    ref = np.sort(O.composite_partials([p]), order="pixel_id")
+    assert mine.tobytes() == ref.tobytes()
+    assert ctx.composite_partials(p[:0], W, H).size == 0
+    one = ctx.composite_partials(p[:1], W, H)
+    assert one.tobytes() == p[:1].tobytes()
+
+
+def test_path_a_single_rank_roundtrip(ctx):
+    """Image::Init -> (single image, no blend) -> ImageToCanvas: canvas becomes k/255."""
+    sc = scenes.multi_render_scene(0)
+    dom = sc["doms"][0]
+    gpu_path_a_canvas(ctx, dom, sc)
+    ctx.image_from_canvas()
+    u8, d = ctx.image_download(sc["W"], sc["H"])
+    rp, dp = ctx.image_ptrs()
+    ctx.image_to_canvas_dev(rp, dp)
+    can, cd = ctx.canvas_download(sc["W"], sc["H"])
+    o_u8, o_d, o_can = scenes.oracle_path_a(sc)
+    assert np.array_equal(u8, o_u8)
+    assert np.array_equal(can, o_can)
+
+
+def test_two_rank_path_a_on_one_gpu(ctx, golden_dir):
+    """the reference's 2-rank MPI volume scene: each rank's image rendered and quantised on the
+    GPU, folded in visibility order on the GPU; uint8 result bit-exact vs the oracle, and inside
+    the reference golden's tolerance."""
+    import os
+    sc = scenes.mpi_volume_scene()
+    W, H = sc["W"], sc["H"]
+    layers, depths = [], []
+    for dom in sc["doms"]:
+        gpu_path_a_canvas(ctx, dom, sc)
+        ctx.image_from_canvas()
+        u8, d = ctx.image_download(W, H)
+        layers.append(u8)
+        depths.append(d)
+    order = _lib.visibility_order(sc["dom_bounds"], sc["cam"])
+    import torch
+    lr = torch.from_numpy(np.stack(layers)).cuda()
+    ld = torch.from_numpy(np.stack(depths)).cuda()
+    out = torch.empty((H * W, 4), dtype=torch.uint8, device="cuda")
+    od = torch.empty(H * W, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.fold_images_dev(lr.data_ptr(), ld.data_ptr(), H * W, order, H * W, out.data_ptr(), od.data_ptr())
+    ctx.synchronize()
+    o_u8, o_d, o_can = scenes.oracle_path_a(sc)
+    assert np.array_equal(out.cpu().numpy(), o_u8)
+    g = np.load(os.path.join(golden_dir, "tout_render_mpi_3d_diy_volume100.npz"))
+    can, _ = O.image_to_canvas(out.cpu().numpy(), od.cpu().numpy())
+    png = scenes.png_bytes(can, W, H)
+    from test_oracle_golden import crop_stats
+    assert crop_stats(png, g["rgb"], g["rects"]) <= 0.01
+
+
+def test_errors_are_reported_not_thrown(ctx):
+    with pytest.raises(_lib.VRError):
+        ctx.block_free(12345)
+    with pytest.raises(_lib.VRError):
+        ctx.trace_to_canvas(999, O.camera_default(), 0.1, 0., 1.)
+    with pytest.raises(_lib.VRError):
+        ctx.set_tf(np.zeros((1, 4), np.float32))
+    with pytest.raises(_lib.VRError):
+        ctx.block_uniform(0, (1, 4, 4), [0, 0, 0], [1, 1, 1], np.zeros(16, np.float32))
