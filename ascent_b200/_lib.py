@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvr_b200.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("VR_LIB_NAME", "libvr_b200.so"))
 
 VR_OK = 0
 VR_F32, VR_F64 = 0, 1

@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libvr_b200.so")
+OUT = os.path.join(HERE, os.environ.get("VR_LIB_NAME", "libvr_b200.so"))
 HOST_OUT = os.path.join(HERE, "libvtkh_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOSTCXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
@@ -19,7 +19,8 @@ HOSTCXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # --fmad=false: the sampler and the float fold must round like the reference's scalar x86 code
 # (every decision bit-identical to the oracle); explicit __fmaf_rn is used where fusion is wanted.
-COMMON = ["-O3", "-lineinfo", "-std=c++17", "--fmad=false", "-ccbin", HOSTCXX, "-Xcompiler",
+EXTRA = os.environ.get("VR_NVCC_EXTRA", "").split()
+COMMON = EXTRA + ["-O3", "-lineinfo", "-std=c++17", "--fmad=false", "-ccbin", HOSTCXX, "-Xcompiler",
           "-fPIC,-ffp-contract=off,-fvisibility=hidden", "-Xptxas", "-v"]
 SOURCES = ["sampler.cu", "composite.cu", "comm.cu", "vr_api.cu"]
 HEADERS = ["vr_internal.h", "vr_host_math.hpp", os.path.join("..", "..", "include", "vr_b200.h")]

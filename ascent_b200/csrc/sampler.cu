@@ -14,10 +14,16 @@
 // decision, cell index, colour index and termination test bit-identical to the oracle; where a
 // fused multiply-add is wanted it is written explicitly (__fmaf_rn).
 //
-// Mapping to the machine: a warp owns an 8x4 pixel tile (rays of a tile walk through
-// neighbouring cells, so the eight corner gathers of a warp fall into a handful of 32-byte
-// sectors); warps pull tiles from a global counter (persistent CTAs, grid = SMs x resident
-// CTAs) so long and short rays balance; the 16 KiB transfer function sits in shared memory.
+// Mapping to the machine (evidence: profiles/r1_*):
+//  * a warp owns an 8x4 pixel tile: rays of a tile walk through neighbouring cells, so the eight
+//    corner gathers of a warp fall into a handful of 32-byte sectors (L1 hit rate ~2/3);
+//  * warps pull tiles from a global counter (persistent CTAs, grid = SMs x resident CTAs) so long
+//    and short rays balance;
+//  * the march is software-pipelined: the cell lookup and the eight gathers of sample k+1 are
+//    issued before sample k is interpolated and blended.  The kernel is latency-bound (the sparse
+//    default sampling touches ~1/4 of the block: DRAM runs at <10 % of peak), so doubling the loads
+//    in flight per warp is what shortens a ray;
+//  * the 16 KiB transfer function sits in shared memory (one LDS.128 per sample).
 #include "vr_internal.h"
 
 namespace vr
@@ -26,22 +32,21 @@ namespace vr
 namespace
 {
 
+#ifndef VR_MIN_BLOCKS
+#define VR_MIN_BLOCKS 9
+#endif
 constexpr int kThreads = 128;
 constexpr int kTileW = 8, kTileH = 4;
 
 template <typename FT>
-__device__ __forceinline__ float load_scalar(const void* field, long long i)
+__device__ __forceinline__ float load_scalar(const void* field, int i)
 {
   return (float)__ldg(reinterpret_cast<const FT*>(field) + i);
 }
-
-__device__ __forceinline__ bool is_inside(const BlockDev& b, float px, float py, float pz)
+template <typename FT>
+__device__ __forceinline__ float load_scalar(const void* field, long long i)
 {
-  bool inside = true;
-  if (px < b.min_point[0] || px > b.max_point[0]) inside = false;
-  if (py < b.min_point[1] || py > b.max_point[1]) inside = false;
-  if (pz < b.min_point[2] || pz > b.max_point[2]) inside = false;
-  return inside;
+  return (float)__ldg(reinterpret_cast<const FT*>(field) + i);
 }
 
 __device__ __forceinline__ float rcp_safe(float f)
@@ -73,8 +78,72 @@ __device__ __forceinline__ void locate_axis_rect(const float* __restrict__ ax, i
   inv_sp = 1.f / (maxVal - minVal);
 }
 
-template <int KIND, typename FT, int ASSOC, int MODE>
-__global__ void __launch_bounds__(kThreads)
+// the state of "the cell the ray is in": corner scalars in the pre-differenced form the
+// reference keeps them in, the cell's lower-left point and inverse spacing
+struct Cell
+{
+  float s0, s1m0, s2m3, s3, s4, s5m4, s6m7, s7; // point field (s0 doubles as the cell scalar)
+  float blx, bly, blz;
+  float isx, isy, isz;
+  int cx, cy, cz;
+};
+
+template <int KIND, typename FT, int ASSOC, typename IDX>
+__device__ __forceinline__ void locate_and_load(const BlockDev& B, float px, float py, float pz,
+                                                Cell& c)
+{
+  if (KIND == 0)
+  {
+    // UniformLocator::LocateCell
+    float t0 = (px - B.min_point[0]) * B.inv_spacing[0];
+    float t1 = (py - B.min_point[1]) * B.inv_spacing[1];
+    float t2 = (pz - B.min_point[2]) * B.inv_spacing[2];
+    if (t0 == (float)(B.dims[0] - 1)) t0 = (float)(B.dims[0] - 2);
+    if (t1 == (float)(B.dims[1] - 1)) t1 = (float)(B.dims[1] - 2);
+    if (t2 == (float)(B.dims[2] - 1)) t2 = (float)(B.dims[2] - 2);
+    c.cx = (int)t0; c.cy = (int)t1; c.cz = (int)t2;
+    c.isx = B.inv_spacing[0]; c.isy = B.inv_spacing[1]; c.isz = B.inv_spacing[2];
+    // GetPoint(cellIndices[0]): origin + spacing*ijk evaluated in f64 and narrowed to f32 by
+    // VTK-m; a single-rounding f32 fma gives the same bits whenever the exact sum fits in 53
+    // bits (any grid whose |origin|/spacing ratio is below 2^18).
+    c.blx = __fmaf_rn(B.spacing[0], (float)c.cx, B.origin[0]);
+    c.bly = __fmaf_rn(B.spacing[1], (float)c.cy, B.origin[1]);
+    c.blz = __fmaf_rn(B.spacing[2], (float)c.cz, B.origin[2]);
+  }
+  else
+  {
+    locate_axis_rect(B.axis[0], B.dims[0], B.max_point[0], px, c.cx, c.isx);
+    locate_axis_rect(B.axis[1], B.dims[1], B.max_point[1], py, c.cy, c.isy);
+    locate_axis_rect(B.axis[2], B.dims[2], B.max_point[2], pz, c.cz, c.isz);
+    c.blx = __ldg(B.axis[0] + c.cx);
+    c.bly = __ldg(B.axis[1] + c.cy);
+    c.blz = __ldg(B.axis[2] + c.cz);
+  }
+  if (ASSOC == VR_POINT)
+  {
+    const IDX Nx = (IDX)B.dims[0], NxNy = (IDX)B.dims[0] * (IDX)B.dims[1];
+    const IDX i0 = ((IDX)c.cz * (IDX)B.dims[1] + (IDX)c.cy) * Nx + (IDX)c.cx;
+    const IDX i3 = i0 + Nx, i4 = i0 + NxNy, i7 = i4 + Nx;
+    const float s0 = load_scalar<FT>(B.field, i0);
+    const float s1 = load_scalar<FT>(B.field, i0 + 1);
+    const float s3 = load_scalar<FT>(B.field, i3);
+    const float s2 = load_scalar<FT>(B.field, i3 + 1);
+    const float s4 = load_scalar<FT>(B.field, i4);
+    const float s5 = load_scalar<FT>(B.field, i4 + 1);
+    const float s7 = load_scalar<FT>(B.field, i7);
+    const float s6 = load_scalar<FT>(B.field, i7 + 1);
+    c.s0 = s0; c.s3 = s3; c.s4 = s4; c.s7 = s7;
+    c.s6m7 = s6 - s7; c.s5m4 = s5 - s4; c.s1m0 = s1 - s0; c.s2m3 = s2 - s3;
+  }
+  else
+  {
+    const IDX ci = ((IDX)c.cz * (IDX)(B.dims[1] - 1) + (IDX)c.cy) * (IDX)(B.dims[0] - 1) + (IDX)c.cx;
+    c.s0 = load_scalar<FT>(B.field, ci);
+  }
+}
+
+template <int KIND, typename FT, int ASSOC, int MODE, typename IDX>
+__global__ void __launch_bounds__(kThreads, VR_MIN_BLOCKS)
 trace_kernel(const __grid_constant__ TraceParams P)
 {
   __shared__ float4 s_lut[1024];
@@ -85,9 +154,14 @@ trace_kernel(const __grid_constant__ TraceParams P)
   const int lane = threadIdx.x & 31;
   const int lx = lane & (kTileW - 1), ly = lane >> 3;
   const unsigned n_tiles = (unsigned)(P.tiles_x * P.tiles_y);
-  const long long Nx = B.dims[0], Ny = B.dims[1];
-  const int color_map_size = P.lut_size - 1;
-  unsigned long long my_samples = 0;
+  const float cms_f = (float)(P.lut_size - 1);
+  const float minx = B.min_point[0], miny = B.min_point[1], minz = B.min_point[2];
+  const float maxx = B.max_point[0], maxy = B.max_point[1], maxz = B.max_point[2];
+  const float sd = P.sample_dist;
+  unsigned my_samples = 0;
+
+#define VR_INSIDE(x, y, z) \
+  (!((x) < minx || (x) > maxx) && !((y) < miny || (y) > maxy) && !((z) < minz || (z) > maxz))
 
   for (;;)
   {
@@ -104,187 +178,156 @@ trace_kernel(const __grid_constant__ TraceParams P)
     float max_distance = __int_as_float(0x7f800000);
     if (in_subset)
     {
-    // ---------------- K1: PerspectiveRayGen
-    float dx, dy, dz;
-    {
-      const float fx = (2.f * (float)i - (float)P.W) / 2.0f;
-      const float fy = (2.f * (float)j - (float)P.H) / 2.0f;
-      dx = P.nlook[0] + P.delta_x[0] * fx + P.delta_y[0] * fy;
-      dy = P.nlook[1] + P.delta_x[1] * fx + P.delta_y[1] * fy;
-      dz = P.nlook[2] + P.delta_x[2] * fx + P.delta_y[2] * fy;
-      if (dx == 0.f) dx += 0.0000001f;
-      if (dy == 0.f) dy += 0.0000001f;
-      if (dz == 0.f) dz += 0.0000001f;
-      const float dot = dx * dx + dy * dy + dz * dz;
-      const float sq = sqrtf(dot);
-      dx = dx / sq; dy = dy / sq; dz = dz / sq;
-    }
-    const float ox = P.origin[0], oy = P.origin[1], oz = P.origin[2];
-    float min_distance = 0.f, distance0 = 0.f;
-
-    // ---------------- K2: RayMapCanvas
-    if (P.use_depth)
-    {
-      float p0 = (float)(pixel % P.W), p1 = (float)(pixel / P.W);
-      float p2 = P.canvas_depth[pixel];
-      p0 = p0 * P.dbl_inv_w - 1.f;
-      p1 = p1 * P.dbl_inv_h - 1.f;
-      p2 = 2.f * p2 - 1.f;
-      p2 -= 0.00001f;
-      const float* m = P.inv_pv;
-      const float q0 = m[0] * p0 + m[1] * p1 + m[2] * p2 + m[3] * 1.f;
-      const float q1 = m[4] * p0 + m[5] * p1 + m[6] * p2 + m[7] * 1.f;
-      const float q2 = m[8] * p0 + m[9] * p1 + m[10] * p2 + m[11] * 1.f;
-      const float q3 = m[12] * p0 + m[13] * p1 + m[14] * p2 + m[15] * 1.f;
-      const float rx = q0 / q3 - ox, ry = q1 / q3 - oy, rz = q2 / q3 - oz;
-      max_distance = sqrtf(rx * rx + ry * ry + rz * rz);
-    }
-
-    // ---------------- K3: CalcRayStart
-    {
-      const float ix = rcp_safe(dx), iy = rcp_safe(dy), iz = rcp_safe(dz);
-      const float odx = ox * ix, ody = oy * iy, odz = oz * iz;
-      const float xmin = P.bmin[0] * ix - odx, ymin = P.bmin[1] * iy - ody, zmin = P.bmin[2] * iz - odz;
-      const float xmax = P.bmax[0] * ix - odx, ymax = P.bmax[1] * iy - ody, zmax = P.bmax[2] * iz - odz;
-      min_distance =
-        fmaxf(fmaxf(fmaxf(fminf(ymin, ymax), fminf(xmin, xmax)), fminf(zmin, zmax)), min_distance);
-      const float exit_distance = fminf(fminf(fmaxf(ymin, ymax), fmaxf(xmin, xmax)), fmaxf(zmin, zmax));
-      max_distance = fminf(max_distance, exit_distance);
-      if (max_distance < min_distance) min_distance = -1.f;
-      else distance0 = min_distance;
-    }
-
-    // ---------------- K4/K5/K6: Sampler
-    if (min_distance != -1.f)
-    {
-      float distance = min_distance + P.mesh_eps;
-      float px = ox + distance * dx, py = oy + distance * dy, pz = oz + distance * dz;
-      while (!is_inside(B, px, py, pz) && distance < max_distance)
+      // ---------------- K1: PerspectiveRayGen
+      float dx, dy, dz;
       {
-        distance += P.sample_dist;
-        px = ox + distance * dx; py = oy + distance * dy; pz = oz + distance * dz;
+        const float fx = (2.f * (float)i - (float)P.W) / 2.0f;
+        const float fy = (2.f * (float)j - (float)P.H) / 2.0f;
+        dx = P.nlook[0] + P.delta_x[0] * fx + P.delta_y[0] * fy;
+        dy = P.nlook[1] + P.delta_x[1] * fx + P.delta_y[1] * fy;
+        dz = P.nlook[2] + P.delta_x[2] * fx + P.delta_y[2] * fy;
+        if (dx == 0.f) dx += 0.0000001f;
+        if (dy == 0.f) dy += 0.0000001f;
+        if (dz == 0.f) dz += 0.0000001f;
+        const float dot = dx * dx + dy * dy + dz * dz;
+        const float sq = sqrtf(dot);
+        dx = dx / sq; dy = dy / sq; dz = dz / sq;
       }
-      const float stepx = P.sample_dist * dx, stepy = P.sample_dist * dy, stepz = P.sample_dist * dz;
-      float blx = 0.f, bly = 0.f, blz = 0.f;
-      float tx = 0.f, ty = 0.f, tz = 0.f;
-      float s0 = 0.f, s1m0 = 0.f, s2m3 = 0.f, s3 = 0.f, s4 = 0.f, s5m4 = 0.f, s6m7 = 0.f, s7 = 0.f;
-      float cell_scalar = 0.f;
-      int cx = 0, cy = 0, cz = 0;
-      float isx = 0.f, isy = 0.f, isz = 0.f;
-      bool new_cell = true;
+      const float ox = P.origin[0], oy = P.origin[1], oz = P.origin[2];
+      float min_distance = 0.f, distance0 = 0.f;
 
-      while (is_inside(B, px, py, pz) && distance < max_distance)
+      // ---------------- K2: RayMapCanvas
+      if (P.use_depth)
       {
-        const float mint = fminf(tx, fminf(ty, tz));
-        const float maxt = fmaxf(tx, fmaxf(ty, tz));
-        if (maxt > 1.f || mint < 0.f) new_cell = true;
-        if (new_cell)
-        {
-          if (KIND == 0)
-          {
-            // UniformLocator::LocateCell
-            float t0 = (px - B.min_point[0]) * B.inv_spacing[0];
-            float t1 = (py - B.min_point[1]) * B.inv_spacing[1];
-            float t2 = (pz - B.min_point[2]) * B.inv_spacing[2];
-            if (t0 == (float)(B.dims[0] - 1)) t0 = (float)(B.dims[0] - 2);
-            if (t1 == (float)(B.dims[1] - 1)) t1 = (float)(B.dims[1] - 2);
-            if (t2 == (float)(B.dims[2] - 1)) t2 = (float)(B.dims[2] - 2);
-            cx = (int)t0; cy = (int)t1; cz = (int)t2;
-            isx = B.inv_spacing[0]; isy = B.inv_spacing[1]; isz = B.inv_spacing[2];
-            // GetPoint(cellIndices[0]): origin + spacing*ijk evaluated in f64 and narrowed to
-            // f32 by VTK-m; a single-rounding f32 fma gives the same bits whenever the exact
-            // sum fits in 53 bits (any grid whose |origin|/spacing ratio is below 2^18).
-            blx = __fmaf_rn(B.spacing[0], (float)cx, B.origin[0]);
-            bly = __fmaf_rn(B.spacing[1], (float)cy, B.origin[1]);
-            blz = __fmaf_rn(B.spacing[2], (float)cz, B.origin[2]);
-          }
-          else
-          {
-            locate_axis_rect(B.axis[0], B.dims[0], B.max_point[0], px, cx, isx);
-            locate_axis_rect(B.axis[1], B.dims[1], B.max_point[1], py, cy, isy);
-            locate_axis_rect(B.axis[2], B.dims[2], B.max_point[2], pz, cz, isz);
-            blx = __ldg(B.axis[0] + cx);
-            bly = __ldg(B.axis[1] + cy);
-            blz = __ldg(B.axis[2] + cz);
-          }
-          if (ASSOC == VR_POINT)
-          {
-            const long long i0 = ((long long)cz * Ny + cy) * Nx + cx;
-            const long long i4 = i0 + Nx * Ny;
-            s0 = load_scalar<FT>(B.field, i0);
-            const float s1 = load_scalar<FT>(B.field, i0 + 1);
-            const float s2 = load_scalar<FT>(B.field, i0 + 1 + Nx);
-            s3 = load_scalar<FT>(B.field, i0 + Nx);
-            s4 = load_scalar<FT>(B.field, i4);
-            const float s5 = load_scalar<FT>(B.field, i4 + 1);
-            const float s6 = load_scalar<FT>(B.field, i4 + 1 + Nx);
-            s7 = load_scalar<FT>(B.field, i4 + Nx);
-            s6m7 = s6 - s7; s5m4 = s5 - s4; s1m0 = s1 - s0; s2m3 = s2 - s3;
-          }
-          else
-          {
-            const long long ci = ((long long)cz * (Ny - 1) + cy) * (Nx - 1) + cx;
-            cell_scalar = load_scalar<FT>(B.field, ci);
-          }
-          tx = (px - blx) * isx; ty = (py - bly) * isy; tz = (pz - blz) * isz;
-          new_cell = false;
-        }
-        float v;
-        if (ASSOC == VR_POINT)
-        {
-          const float l76 = s7 + tx * s6m7;
-          const float l45 = s4 + tx * s5m4;
-          const float ltop = l45 + ty * (l76 - l45);
-          const float l01 = s0 + tx * s1m0;
-          const float l32 = s3 + tx * s2m3;
-          const float lbot = l01 + ty * (l32 - l01);
-          v = lbot + tz * (ltop - lbot);
-        }
-        else
-          v = cell_scalar;
-        v = (v - P.range_min) * P.inv_delta_scalar;
-        // static_cast<vtkm::Id>(float): x86 cvttss2si gives INT64_MIN for NaN/overflow, which the
-        // clamp below turns into 0; mirror that (CUDA's cast would give 0 / saturate).
-        const float fidx = v * (float)color_map_size;
-        int ci = (fidx >= 9.2233720e18f || fidx != fidx) ? -1 : (int)fmaxf(fminf(fidx, 2.0e9f), -2.0e9f);
-        ci = max(0, min(ci, color_map_size));
-        const float4 sc = s_lut[ci];
-        const float alpha = sc.w * (1.f - c3);
-        c0 = c0 + sc.x * alpha;
-        c1 = c1 + sc.y * alpha;
-        c2 = c2 + sc.z * alpha;
-        c3 = alpha + c3;
-        ++my_samples;
-        if (c3 >= 1.f) break;
-        distance += P.sample_dist;
-        px = px + stepx; py = py + stepy; pz = pz + stepz;
-        tx = (px - blx) * isx; ty = (py - bly) * isy; tz = (pz - blz) * isz;
+        float p0 = (float)(pixel % P.W), p1 = (float)(pixel / P.W);
+        float p2 = P.canvas_depth[pixel];
+        p0 = p0 * P.dbl_inv_w - 1.f;
+        p1 = p1 * P.dbl_inv_h - 1.f;
+        p2 = 2.f * p2 - 1.f;
+        p2 -= 0.00001f;
+        const float* m = P.inv_pv;
+        const float q0 = m[0] * p0 + m[1] * p1 + m[2] * p2 + m[3] * 1.f;
+        const float q1 = m[4] * p0 + m[5] * p1 + m[6] * p2 + m[7] * 1.f;
+        const float q2 = m[8] * p0 + m[9] * p1 + m[10] * p2 + m[11] * 1.f;
+        const float q3 = m[12] * p0 + m[13] * p1 + m[14] * p2 + m[15] * 1.f;
+        const float rx = q0 / q3 - ox, ry = q1 / q3 - oy, rz = q2 / q3 - oz;
+        max_distance = sqrtf(rx * rx + ry * ry + rz * rz);
       }
-      c0 = fminf(c0, 1.f); c1 = fminf(c1, 1.f); c2 = fminf(c2, 1.f); c3 = fminf(c3, 1.f);
-    }
 
-    if (MODE == 0)
-    {
-      // ---------------- K7: SurfaceConverter (blend over canvas, projected entry depth)
-      const float ix_ = ox + distance0 * dx, iy_ = oy + distance0 * dy, iz_ = oz + distance0 * dz;
-      const float* m = P.pv;
-      const float n2 = m[8] * ix_ + m[9] * iy_ + m[10] * iz_ + m[11] * 1.f;
-      const float n3 = m[12] * ix_ + m[13] * iy_ + m[14] * iz_ + m[15] * 1.f;
-      const float depth = 0.5f * (n2 / n3) + 0.5f;
-      const float4 in = P.canvas_rgba[pixel];
-      const float a = 1.f - c3;
-      float4 out;
-      out.x = c0 + in.x * a;
-      out.y = c1 + in.y * a;
-      out.z = c2 + in.z * a;
-      out.w = in.w * a + c3;
-      out.x = fminf(1.f, fmaxf(out.x, 0.f));
-      out.y = fminf(1.f, fmaxf(out.y, 0.f));
-      out.z = fminf(1.f, fmaxf(out.z, 0.f));
-      out.w = fminf(1.f, fmaxf(out.w, 0.f));
-      P.canvas_depth[pixel] = depth;
-      P.canvas_rgba[pixel] = out;
-    }
+      // ---------------- K3: CalcRayStart
+      {
+        const float ix = rcp_safe(dx), iy = rcp_safe(dy), iz = rcp_safe(dz);
+        const float odx = ox * ix, ody = oy * iy, odz = oz * iz;
+        const float xmin = P.bmin[0] * ix - odx, ymin = P.bmin[1] * iy - ody, zmin = P.bmin[2] * iz - odz;
+        const float xmax = P.bmax[0] * ix - odx, ymax = P.bmax[1] * iy - ody, zmax = P.bmax[2] * iz - odz;
+        min_distance =
+          fmaxf(fmaxf(fmaxf(fminf(ymin, ymax), fminf(xmin, xmax)), fminf(zmin, zmax)), min_distance);
+        const float exit_distance = fminf(fminf(fmaxf(ymin, ymax), fmaxf(xmin, xmax)), fmaxf(zmin, zmax));
+        max_distance = fminf(max_distance, exit_distance);
+        if (max_distance < min_distance) min_distance = -1.f;
+        else distance0 = min_distance;
+      }
+
+      // ---------------- K4/K5/K6: Sampler
+      if (min_distance != -1.f)
+      {
+        float distance = min_distance + P.mesh_eps;
+        float px = ox + distance * dx, py = oy + distance * dy, pz = oz + distance * dz;
+        while (!VR_INSIDE(px, py, pz) && distance < max_distance)
+        {
+          distance += sd;
+          px = ox + distance * dx; py = oy + distance * dy; pz = oz + distance * dz;
+        }
+        if (VR_INSIDE(px, py, pz) && distance < max_distance)
+        {
+          const float stepx = sd * dx, stepy = sd * dy, stepz = sd * dz;
+          // first sample: the reference enters its loop with newCell = true
+          Cell cur;
+          cur.cx = cur.cy = cur.cz = 0;
+          cur.isx = cur.isy = cur.isz = 0.f;
+          locate_and_load<KIND, FT, ASSOC, IDX>(B, px, py, pz, cur);
+          float tx = (px - cur.blx) * cur.isx, ty = (py - cur.bly) * cur.isy, tz = (pz - cur.blz) * cur.isz;
+          for (;;)
+          {
+            // ---- sample k+1: position, loop condition, cell change, gathers (issued early)
+            const float npx = px + stepx, npy = py + stepy, npz = pz + stepz;
+            const float ndist = distance + sd;
+            const bool next_ok = VR_INSIDE(npx, npy, npz) && ndist < max_distance;
+            Cell nxt = cur;
+            float ntx = (npx - cur.blx) * cur.isx, nty = (npy - cur.bly) * cur.isy,
+                  ntz = (npz - cur.blz) * cur.isz;
+            if (next_ok)
+            {
+              const float mint = fminf(ntx, fminf(nty, ntz));
+              const float maxt = fmaxf(ntx, fmaxf(nty, ntz));
+              if (maxt > 1.f || mint < 0.f)
+              {
+                locate_and_load<KIND, FT, ASSOC, IDX>(B, npx, npy, npz, nxt);
+                ntx = (npx - nxt.blx) * nxt.isx;
+                nty = (npy - nxt.bly) * nxt.isy;
+                ntz = (npz - nxt.blz) * nxt.isz;
+              }
+            }
+            // ---- sample k: interpolate, classify, blend
+            float v;
+            if (ASSOC == VR_POINT)
+            {
+              const float l76 = cur.s7 + tx * cur.s6m7;
+              const float l45 = cur.s4 + tx * cur.s5m4;
+              const float ltop = l45 + ty * (l76 - l45);
+              const float l01 = cur.s0 + tx * cur.s1m0;
+              const float l32 = cur.s3 + tx * cur.s2m3;
+              const float lbot = l01 + ty * (l32 - l01);
+              v = lbot + tz * (ltop - lbot);
+            }
+            else
+              v = cur.s0;
+            v = (v - P.range_min) * P.inv_delta_scalar;
+            // static_cast<vtkm::Id>(v * size) then clamp to [0, size]: trunc and clamp commute;
+            // x86's cvttss2si turns NaN and >= 2^63 into INT64_MIN, which the clamp maps to 0.
+            const float raw = v * cms_f;
+            float fidx = fminf(fmaxf(raw, 0.f), cms_f);
+            if (raw >= 9.2233720e18f) fidx = 0.f;
+            const float4 sc = s_lut[(int)fidx];
+            const float alpha = sc.w * (1.f - c3);
+            c0 = c0 + sc.x * alpha;
+            c1 = c1 + sc.y * alpha;
+            c2 = c2 + sc.z * alpha;
+            c3 = alpha + c3;
+            ++my_samples;
+            if (c3 >= 1.f) break;
+            if (!next_ok) break;
+            cur = nxt;
+            px = npx; py = npy; pz = npz;
+            distance = ndist;
+            tx = ntx; ty = nty; tz = ntz;
+          }
+        }
+        c0 = fminf(c0, 1.f); c1 = fminf(c1, 1.f); c2 = fminf(c2, 1.f); c3 = fminf(c3, 1.f);
+      }
+
+      if (MODE == 0)
+      {
+        // ---------------- K7: SurfaceConverter (blend over canvas, projected entry depth)
+        const float ix_ = ox + distance0 * dx, iy_ = oy + distance0 * dy, iz_ = oz + distance0 * dz;
+        const float* m = P.pv;
+        const float n2 = m[8] * ix_ + m[9] * iy_ + m[10] * iz_ + m[11] * 1.f;
+        const float n3 = m[12] * ix_ + m[13] * iy_ + m[14] * iz_ + m[15] * 1.f;
+        const float depth = 0.5f * (n2 / n3) + 0.5f;
+        const float4 in = P.canvas_rgba[pixel];
+        const float a = 1.f - c3;
+        float4 out;
+        out.x = c0 + in.x * a;
+        out.y = c1 + in.y * a;
+        out.z = c2 + in.z * a;
+        out.w = in.w * a + c3;
+        out.x = fminf(1.f, fmaxf(out.x, 0.f));
+        out.y = fminf(1.f, fmaxf(out.y, 0.f));
+        out.z = fminf(1.f, fmaxf(out.z, 0.f));
+        out.w = fminf(1.f, fmaxf(out.w, 0.f));
+        P.canvas_depth[pixel] = depth;
+        P.canvas_rgba[pixel] = out;
+      }
     } // in_subset
 
     if (MODE == 1)
@@ -311,21 +354,38 @@ trace_kernel(const __grid_constant__ TraceParams P)
       }
     }
   }
-  if (P.sample_counter && my_samples) atomicAdd(P.sample_counter, my_samples);
+#undef VR_INSIDE
+  if (P.sample_counter)
+  {
+    // one atomic per warp
+    unsigned long long s = my_samples;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0 && s) atomicAdd(P.sample_counter, s);
+  }
 }
 
-template <int KIND, typename FT, int ASSOC>
+template <int KIND, typename FT, int ASSOC, typename IDX>
 cudaError_t launch_mode(const TraceParams& p, int mode, int grid, cudaStream_t s)
 {
-  if (mode == 0) trace_kernel<KIND, FT, ASSOC, 0><<<grid, kThreads, 0, s>>>(p);
-  else           trace_kernel<KIND, FT, ASSOC, 1><<<grid, kThreads, 0, s>>>(p);
+  if (mode == 0) trace_kernel<KIND, FT, ASSOC, 0, IDX><<<grid, kThreads, 0, s>>>(p);
+  else           trace_kernel<KIND, FT, ASSOC, 1, IDX><<<grid, kThreads, 0, s>>>(p);
   return cudaGetLastError();
+}
+template <int KIND, typename FT, int ASSOC>
+cudaError_t launch_idx(const TraceParams& p, int mode, int grid, cudaStream_t s)
+{
+  // 32-bit element indices whenever the block has fewer than 2^31 points (saves the 64-bit
+  // multiply-add chains in the gather address arithmetic)
+  const long long n = (long long)p.blk.dims[0] * p.blk.dims[1] * p.blk.dims[2];
+  return n < (1ll << 31) ? launch_mode<KIND, FT, ASSOC, int>(p, mode, grid, s)
+                         : launch_mode<KIND, FT, ASSOC, long long>(p, mode, grid, s);
 }
 template <int KIND, typename FT>
 cudaError_t launch_assoc(const TraceParams& p, int mode, int grid, cudaStream_t s)
 {
-  return p.blk.assoc == VR_POINT ? launch_mode<KIND, FT, VR_POINT>(p, mode, grid, s)
-                                 : launch_mode<KIND, FT, VR_CELL>(p, mode, grid, s);
+  return p.blk.assoc == VR_POINT ? launch_idx<KIND, FT, VR_POINT>(p, mode, grid, s)
+                                 : launch_idx<KIND, FT, VR_CELL>(p, mode, grid, s);
 }
 template <int KIND>
 cudaError_t launch_dtype(const TraceParams& p, int mode, int grid, cudaStream_t s)
@@ -341,7 +401,7 @@ cudaError_t launch_trace(const TraceParams& p, int mode_partials, int sm_count, 
   const long long n_tiles = (long long)p.tiles_x * p.tiles_y;
   if (n_tiles <= 0) return cudaSuccess;
   // persistent grid: SMs x resident CTAs (4 warps each), capped by the work available
-  const int ctas_per_sm = 8;
+  const int ctas_per_sm = p.ctas_per_sm > 0 ? p.ctas_per_sm : VR_MIN_BLOCKS;
   long long grid = (long long)sm_count * ctas_per_sm;
   const long long need = (n_tiles + 3) / 4;
   if (grid > need) grid = need;

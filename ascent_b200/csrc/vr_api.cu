@@ -73,6 +73,8 @@ extern "C" vr_status vr_create(int device, vr_ctx** out)
     return fail(nullptr, VR_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
   }
   ctx->stream = ctx->own_stream;
+  if (const char* e = std::getenv("VR_CTAS_PER_SM")) ctx->ctas_per_sm = std::atoi(e); // tuning knob
+  if (const char* e = std::getenv("VR_COUNT_SAMPLES")) ctx->count_samples = std::atoi(e) != 0;
   cudaMalloc(&ctx->tile_counter, sizeof(unsigned int));
   cudaMalloc(&ctx->sample_counter, sizeof(unsigned long long));
   cudaMalloc(&ctx->partial_count, sizeof(unsigned long long));
@@ -447,7 +449,8 @@ static vr_status fill_trace_params(vr_ctx* ctx, int block_id, const vr_camera* c
   p.canvas_rgba = ctx->canvas_rgba;
   p.canvas_depth = ctx->canvas_depth;
   p.tile_counter = ctx->tile_counter;
-  p.sample_counter = ctx->sample_counter;
+  p.sample_counter = ctx->count_samples ? ctx->sample_counter : nullptr;
+  p.ctas_per_sm = ctx->ctas_per_sm;
   return VR_OK;
 }
 

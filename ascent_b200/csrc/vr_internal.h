@@ -54,6 +54,7 @@ struct TraceParams
   // dynamic tile scheduler + sample counter
   unsigned int* tile_counter;
   unsigned long long* sample_counter; // may be null
+  int ctas_per_sm;                    // 0 = default
 };
 
 // ---------------------------------------------------------------- host-side state
@@ -87,6 +88,8 @@ struct vr_ctx
   std::string err;
   uint64_t launches = 0;
   int sm_count = 148;
+  int ctas_per_sm = 0;        // trace kernel residency (0 = built-in default)
+  bool count_samples = false; // accumulate the number of samples taken (debug/bench)
 
   std::map<int, vr::Block> blocks;
   float4* lut = nullptr;
