@@ -86,13 +86,13 @@ class ClockSampler:
 # ----------------------------------------------------------------------------- workloads
 def workload_c2():
     return dict(name="c2: braid uniform 512^3 f32, 1 domain, 1920x1080, default camera, samples=100",
-                n_block=512, per_axis=1, W=1920, H=1080)
+                n_block=512, per_axis=1, W=1920, H=1080, key="c2")
 
 
 def workload_c3():
     return dict(name="c3: braid 1023^3 as 8 blocks of 512^3 f32, 3840x2160, default camera, "
                      "samples=100, sort-last composite to rank 0",
-                n_block=512, per_axis=2, W=3840, H=2160)
+                n_block=512, per_axis=2, W=3840, H=2160, key="c3")
 
 
 def block_layout(wl):
@@ -284,9 +284,15 @@ def run_single(args, wl):
     n_launch = len(blocks)
     alg_bytes = nvox * 4 * len(blocks) + W * H * 20  # N_vox*4 + W*H*20 per frame
     achieved = alg_bytes / (trace_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        t = json.load(open(tp)).get(wl["key"])
+        if t:
+            traffic, traffic_src = t["traffic_bytes"] * n_launch, t["source"]
     roof = {"bound": "hbm", "kernel": "trace_kernel (sampler.cu)", "achieved": achieved,
             "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-            "traffic": None, "algorithmic_bytes_per_frame": alg_bytes, "kernel_ms_per_frame": trace_ms,
+            "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_frame": alg_bytes, "kernel_ms_per_frame": trace_ms,
             "launches_per_frame": n_launch}
 
     # ---- CPU baseline beside it: bounded sample of the same workload (rank 0, N == 1)
