@@ -10,10 +10,19 @@
 // kernel; cross-GPU ordering uses epoch flags in the peers' arenas (system-scope release/acquire),
 // no host round trip and no MPI barrier.
 //
+// The float-partial path (vtkh_diy_partial_redistribute.hpp:58-152 all-to-all, PartialCompositor.cpp
+// :329-488 serial std::sort + fold, vtkh_diy_partial_collect.hpp:57-141 gather) becomes: every rank
+// orders its own list by (pixel, depth) in its arena, then ONE kernel per rank pulls, for each pixel
+// of the range it owns, that pixel's run from every rank's list over NVLink, merges the N runs by
+// depth in registers, folds front to back and appends the result to rank 0's list.  No receive
+// buffers, no second sort, no host in the loop.
+//
 // Arena layout per rank (one cudaMalloc, exported through CUDA IPC):
-//   [flags 4 KiB][img rgba8 x2][img depth x2][result rgba8 x2][result depth x2][partial area]
-// Images are double-buffered by epoch parity so a rank may start quantising frame e+1 while a
+//   [flags 4 KiB][img rgba8 x2][img depth x2][result rgba8 x2][result depth x2]
+//   [partial offsets x2][sorted partials x2][composited partials (rank 0)]
+// Buffers are double-buffered by epoch parity so a rank may start producing frame e+1 while a
 // slower peer still reads frame e.
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 
@@ -32,7 +41,18 @@ struct Flags
   unsigned int ready[kMaxRanks]; // ready[r] = last epoch for which rank r's image is complete
   unsigned int done[kMaxRanks];  // (rank 0 only) done[r] = last epoch rank r finished storing
   unsigned int cta_done;         // local: CTAs of the current fold kernel that have finished
+  // partial path
+  unsigned int p_ready[kMaxRanks]; // p_ready[r] = last epoch for which rank r's sorted list is complete
+  unsigned int p_done[kMaxRanks];  // (rank 0 only) ranks whose composited range has landed
+  int p_minmax[2][kMaxRanks][2];   // [epoch parity][rank] = {min,max} pixel id of that rank's list
+  unsigned int p_cta_done;
+  unsigned int p_overflow;         // set when a list did not fit max_partials
+  unsigned long long p_out_count;  // (rank 0) length of the composited list
+  // geometry of this arena: every rank must have been initialised with the same values, because
+  // a rank addresses its peers' arenas with its own layout (checked in vr_comm_connect)
+  unsigned long long cfg_max_pixels, cfg_max_partials;
 };
+static_assert(sizeof(Flags) <= 4096, "flag block");
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v)
 {
@@ -148,13 +168,205 @@ __global__ void wait_done_kernel(const unsigned int* done, int size, unsigned in
     while (ld_acquire_sys(done + threadIdx.x) < epoch) __nanosleep(64);
 }
 
+
+// ------------------------------------------------------------------ partial path: pull + merge + fold
+struct MergeP2PParams
+{
+  unsigned char* const* peers;
+  int rank, size;
+  unsigned int epoch;
+  size_t n_pixels;
+  size_t off_flags, off_poff, off_psorted, off_pout;
+  size_t sorted_cap, out_cap;
+};
+
+__device__ __forceinline__ void partial_blend(vr_partial& a, const vr_partial& o)
+{
+  // VolumePartial::blend, VolumePartial.hpp:86-95
+  if (a.alpha >= 1.f || o.alpha == 0.f) return;
+  const float opacity = (1.f - a.alpha);
+  a.rgb[0] += opacity * o.rgb[0];
+  a.rgb[1] += opacity * o.rgb[1];
+  a.rgb[2] += opacity * o.rgb[2];
+  a.alpha += opacity * o.alpha;
+  a.alpha = a.alpha > 1.f ? 1.f : a.alpha;
+}
+
+// vr_partial is 24 bytes, 8-byte aligned in the arena: three 8-byte loads
+__device__ __forceinline__ vr_partial load_partial(const vr_partial* p)
+{
+  const uint2* q = reinterpret_cast<const uint2*>(p);
+  const uint2 a = q[0], b = q[1], c = q[2];
+  vr_partial r;
+  r.pixel_id = (int)a.x; r.depth = __uint_as_float(a.y);
+  r.rgb[0] = __uint_as_float(b.x); r.rgb[1] = __uint_as_float(b.y);
+  r.rgb[2] = __uint_as_float(c.x); r.alpha = __uint_as_float(c.y);
+  return r;
+}
+
+// One thread per owned pixel.  NR = number of ranks rounded up to a power of two: the per-source
+// cursors live in registers (all loops over sources are fully unrolled).
+template <int NR>
+__global__ void __launch_bounds__(256) merge_fold_p2p_kernel(const __grid_constant__ MergeP2PParams P)
+{
+  Flags* my_flags = reinterpret_cast<Flags*>(P.peers[P.rank] + P.off_flags);
+  const int par = P.epoch & 1;
+  // ---- announce my sorted list (written by the previous kernels on this stream), then wait for all
+  if (blockIdx.x == 0 && threadIdx.x < P.size)
+  {
+    Flags* f = reinterpret_cast<Flags*>(P.peers[threadIdx.x] + P.off_flags);
+    __threadfence_system();
+    st_release_sys(&f->p_ready[P.rank], P.epoch);
+  }
+  if (threadIdx.x < P.size)
+    while (ld_acquire_sys(&my_flags->p_ready[threadIdx.x]) < P.epoch) __nanosleep(64);
+  __syncthreads();
+
+  // ---- global pixel bounds and my range: RegularDecomposer<DiscreteBounds>, 1-D
+  // (vtkh_diy_partial_redistribute.hpp:133-150, decomposition.hpp:37-46,648-666)
+  int gmin = 0x7fffffff, gmax = -1;
+  for (int r = 0; r < P.size; ++r)
+  {
+    const int lo = ((volatile int*)my_flags->p_minmax[par][r])[0];
+    const int hi = ((volatile int*)my_flags->p_minmax[par][r])[1];
+    if (hi >= 0) { gmin = min(gmin, lo); gmax = max(gmax, hi); }
+  }
+  long long lo_px = 0, hi_px = 0; // [lo, hi)
+  if (gmax >= 0)
+  {
+    long long width = ((long long)gmax - gmin + 1) / P.size;
+    if (width < 1) width = 1;
+    lo_px = (long long)gmin + width * P.rank;
+    hi_px = (P.rank == P.size - 1) ? (long long)gmax + 1 : lo_px + width;
+    if (lo_px > (long long)gmax + 1) lo_px = (long long)gmax + 1;
+    if (hi_px > (long long)gmax + 1) hi_px = (long long)gmax + 1;
+  }
+
+  const int* off[NR];
+  const vr_partial* list[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+  {
+    const int rr = r < P.size ? r : 0;
+    off[r] = reinterpret_cast<const int*>(P.peers[rr] + P.off_poff);
+    list[r] = reinterpret_cast<const vr_partial*>(P.peers[rr] + P.off_psorted);
+  }
+  Flags* root = reinterpret_cast<Flags*>(P.peers[0] + P.off_flags);
+  vr_partial* out = reinterpret_cast<vr_partial*>(P.peers[0] + P.off_pout);
+
+  __shared__ unsigned long long s_base;
+  __shared__ int s_warp[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long base = lo_px + (long long)blockIdx.x * blockDim.x; base < hi_px; base += stride)
+  {
+    const long long px = base + threadIdx.x;
+    int cur[NR], end[NR];
+    float head[NR];
+    int total = 0;
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+    {
+      cur[r] = end[r] = 0;
+      if (r < P.size && px < hi_px)
+      {
+        cur[r] = off[r][px];
+        end[r] = off[r][px + 1];
+        if ((size_t)end[r] > P.sorted_cap) end[r] = cur[r]; // overflowed list: dropped, flagged by its owner
+      }
+      total += end[r] - cur[r];
+    }
+    vr_partial result;
+    if (total > 0)
+    {
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+        head[r] = cur[r] < end[r] ? list[r][cur[r]].depth : 0.f;
+      bool first = true;
+      for (int k = 0; k < total; ++k)
+      {
+        // next partial in (depth, rank) order; within a rank the run is already ordered
+        int sel = -1;
+        float best = 0.f;
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+          if (cur[r] < end[r] && (sel < 0 || head[r] < best)) { sel = r; best = head[r]; }
+        vr_partial q;
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+          if (r == sel)
+          {
+            q = load_partial(list[r] + cur[r]);
+            cur[r] += 1;
+            if (cur[r] < end[r]) head[r] = list[r][cur[r]].depth;
+          }
+        if (first) { result = q; first = false; }
+        else partial_blend(result, q);
+      }
+    }
+    // block-aggregated append to rank 0's list: one NVLink atomic per CTA iteration
+    const unsigned mask = __ballot_sync(0xffffffffu, total > 0);
+    if (lane == 0) s_warp[warp] = __popc(mask);
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      int sum = 0;
+      for (int w = 0; w < 8; ++w) { const int c = s_warp[w]; s_warp[w] = sum; sum += c; }
+      s_base = sum ? atomicAdd(&root->p_out_count, (unsigned long long)sum) : 0ull;
+    }
+    __syncthreads();
+    if (total > 0)
+    {
+      const unsigned long long slot = s_base + s_warp[warp] + __popc(mask & ((1u << lane) - 1u));
+      if (slot < P.out_cap) out[slot] = result;
+    }
+    __syncthreads();
+  }
+
+  // ---- last CTA out tells rank 0 that my range has landed
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    __threadfence_system();
+    const unsigned prev = atomicAdd(&my_flags->p_cta_done, 1u);
+    if (prev == gridDim.x - 1)
+    {
+      my_flags->p_cta_done = 0;
+      __threadfence_system();
+      st_release_sys(&root->p_done[P.rank], P.epoch);
+    }
+  }
+}
+
+// publish {min,max} of my list into every peer's flag block (parity slot of this epoch) and reset
+// rank 0's output counter; runs after the pixel sort, before the merge kernel, on the same stream
+__global__ void publish_minmax_kernel(unsigned char* const* peers, int rank, int size, size_t off_flags,
+                                      int par, const int* minmax, const unsigned long long* count_dev,
+                                      size_t sorted_cap)
+{
+  const int t = threadIdx.x;
+  if (t < size)
+  {
+    Flags* f = reinterpret_cast<Flags*>(peers[t] + off_flags);
+    ((volatile int*)f->p_minmax[par][rank])[0] = minmax[0];
+    ((volatile int*)f->p_minmax[par][rank])[1] = minmax[1];
+  }
+  if (t == 0)
+  {
+    Flags* mine = reinterpret_cast<Flags*>(peers[rank] + off_flags);
+    if (*count_dev > sorted_cap) mine->p_overflow = 1u;
+    if (rank == 0) mine->p_out_count = 0ull;
+  }
+}
+
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout
 {
-  size_t off_flags, off_img_rgba[2], off_img_depth[2], off_res_rgba[2], off_res_depth[2], total;
+  size_t off_flags, off_img_rgba[2], off_img_depth[2], off_res_rgba[2], off_res_depth[2];
+  size_t off_poff[2], off_psorted[2], off_pout, total;
 };
-Layout make_layout(size_t max_pixels)
+Layout make_layout(size_t max_pixels, size_t max_partials, bool is_root)
 {
   Layout L;
   const size_t px = align_up(max_pixels, 64);
@@ -164,6 +376,10 @@ Layout make_layout(size_t max_pixels)
   for (int b = 0; b < 2; ++b) { L.off_img_depth[b] = o; o += px * 4; }
   for (int b = 0; b < 2; ++b) { L.off_res_rgba[b] = o; o += px * 4; }
   for (int b = 0; b < 2; ++b) { L.off_res_depth[b] = o; o += px * 4; }
+  for (int b = 0; b < 2; ++b) { L.off_poff[b] = o; o += max_partials ? align_up((max_pixels + 1) * 4, 256) : 0; }
+  for (int b = 0; b < 2; ++b) { L.off_psorted[b] = o; o += align_up(max_partials * sizeof(vr_partial), 256); }
+  L.off_pout = o;
+  if (is_root && max_partials) o += align_up(max_pixels * sizeof(vr_partial), 256); // <= 1 per pixel
   L.total = align_up(o, 2 << 20);
   return L;
 }
@@ -183,6 +399,7 @@ void comm_destroy(vr_ctx* ctx)
   for (int r = 0; r < (int)c.peer.size(); ++r)
     if (r != c.rank && c.peer[r]) cudaIpcCloseMemHandle(c.peer[r]);
   cudaFree(c.peer_dev);
+  cudaFree(c.minmax_dev);
   cudaFree(c.arena);
   c.on = false;
 }
@@ -196,7 +413,7 @@ vr_status comm_bind_frame(vr_ctx* ctx, size_t n_pixels)
     ctx->err = "image larger than the max_pixels given to vr_comm_init";
     return VR_ERR_INVALID;
   }
-  const Layout L = make_layout(c.max_pixels);
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
   const int b = (c.epoch + 1) & 1;
   ctx->img_rgba = reinterpret_cast<uchar4*>(c.arena + L.off_img_rgba[b]);
   ctx->img_depth = reinterpret_cast<float*>(c.arena + L.off_img_depth[b]);
@@ -230,11 +447,16 @@ extern "C" vr_status vr_comm_init(vr_ctx* ctx, int rank, int n_ranks, size_t max
   c.size = n_ranks;
   c.max_pixels = max_pixels;
   c.max_partials = max_partials;
-  const Layout L = make_layout(max_pixels);
+  const Layout L = make_layout(max_pixels, max_partials, rank == 0);
   c.arena_bytes = L.total;
   cudaError_t e = cudaMalloc(&c.arena, c.arena_bytes);
   if (e != cudaSuccess) return cfail(ctx, VR_ERR_NOMEM, "vr_comm_init: arena", e);
   cudaMemset(c.arena, 0, kFlagBytes);
+  {
+    const unsigned long long cfg[2] = { max_pixels, max_partials };
+    cudaMemcpy(c.arena + offsetof(Flags, cfg_max_pixels), cfg, sizeof(cfg), cudaMemcpyHostToDevice);
+  }
+  if (cudaMalloc(&c.minmax_dev, 2 * sizeof(int)) != cudaSuccess) return cfail(ctx, VR_ERR_NOMEM, "vr_comm_init", cudaErrorMemoryAllocation);
   cudaIpcMemHandle_t h;
   e = cudaIpcGetMemHandle(&h, c.arena);
   if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "cudaIpcGetMemHandle", e);
@@ -272,6 +494,17 @@ extern "C" vr_status vr_comm_connect(vr_ctx* ctx, const void* all_handles)
     cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
     if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "cudaIpcOpenMemHandle (peer access over NVLink)", e);
     c.peer[r] = static_cast<unsigned char*>(p);
+    unsigned long long cfg[2] = { 0, 0 };
+    e = cudaMemcpy(cfg, c.peer[r] + offsetof(Flags, cfg_max_pixels), sizeof(cfg), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "vr_comm_connect: reading a peer arena", e);
+    if (cfg[0] != c.max_pixels || cfg[1] != c.max_partials)
+    {
+      char buf[200];
+      snprintf(buf, sizeof(buf), "vr_comm_connect: rank %d was initialised with max_pixels/max_partials = %llu/%llu, "
+               "this rank with %zu/%zu; they must be identical on all ranks", r, cfg[0], cfg[1], c.max_pixels, c.max_partials);
+      ctx->err = buf;
+      return VR_ERR_INVALID;
+    }
   }
   cudaError_t e = cudaMalloc(&c.peer_dev, sizeof(unsigned char*) * kMaxRanks);
   if (e != cudaSuccess) return cfail(ctx, VR_ERR_NOMEM, "vr_comm_connect", e);
@@ -289,7 +522,7 @@ extern "C" vr_status vr_comm_composite_images(vr_ctx* ctx, const int* vis_order)
   if (!c.on || !c.peer_dev) return cfail(ctx, VR_ERR_STATE, "vr_comm_composite_images: not connected", cudaSuccess);
   if (!vis_order || ctx->W <= 0) return cfail(ctx, VR_ERR_INVALID, "vr_comm_composite_images: no image / NULL order", cudaSuccess);
   cudaSetDevice(ctx->device);
-  const Layout L = make_layout(c.max_pixels);
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
   c.epoch += 1; // the image was quantised into parity (epoch+1)&1 by vr_image_from_canvas
   const int b = c.epoch & 1;
   FoldP2PParams p;
@@ -353,9 +586,89 @@ extern "C" vr_status vr_image_result_to_canvas(vr_ctx* ctx)
   return vr_image_to_canvas_dev(ctx, reinterpret_cast<const uint8_t*>(ctx->res_rgba), ctx->res_depth);
 }
 
+namespace vr { vr_status ensure_partial_scratch_pub(vr_ctx* ctx, size_t n_pixels, size_t n_parts); }
+
 extern "C" vr_status vr_comm_composite_partials(vr_ctx* ctx)
 {
   if (!ctx) return VR_ERR_INVALID;
-  return cfail(ctx, VR_ERR_STATE, "vr_comm_composite_partials: multi-GPU partial exchange not built yet",
-               cudaSuccess);
+  Comm& c = ctx->comm;
+  if (!c.on || !c.peer_dev) return cfail(ctx, VR_ERR_STATE, "vr_comm_composite_partials: not connected", cudaSuccess);
+  if (ctx->pW <= 0) return cfail(ctx, VR_ERR_STATE, "vr_comm_composite_partials: call vr_partials_begin first", cudaSuccess);
+  const size_t n_pixels = (size_t)ctx->pW * ctx->pH;
+  if (c.max_partials == 0 || n_pixels > c.max_pixels)
+    return cfail(ctx, VR_ERR_INVALID, "vr_comm_composite_partials: frame larger than the max_pixels/max_partials given to vr_comm_init", cudaSuccess);
+  if (ctx->n_partials_host > c.max_partials)
+  {
+    char buf[200];
+    snprintf(buf, sizeof(buf), "vr_comm_composite_partials: up to %zu partials this frame but max_partials = %zu",
+             ctx->n_partials_host, c.max_partials);
+    ctx->err = buf;
+    return VR_ERR_NOMEM;
+  }
+  cudaSetDevice(ctx->device);
+  vr_status st = ensure_partial_scratch_pub(ctx, n_pixels, ctx->partial_cap ? ctx->partial_cap : 1);
+  if (st != VR_OK) return st;
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
+  c.pepoch += 1;
+  const int par = c.pepoch & 1;
+  PartialScratch sc{ ctx->px_count, ctx->px_offset, ctx->px_fill, ctx->sorted_idx, ctx->scan_blocks };
+  cudaError_t e = cudaSuccess;
+  // (1) local: order my list by (pixel, depth, list index) into the arena + per-pixel offsets
+  vr_partial* sorted = reinterpret_cast<vr_partial*>(c.arena + L.off_psorted[par]);
+  int* poff = reinterpret_cast<int*>(c.arena + L.off_poff[par]);
+  if (ctx->partial_cap)
+    ctx->launches += launch_partials_pixel_sort(ctx->partials, ctx->partial_count, ctx->partial_cap, n_pixels, sc,
+                                                sorted, c.max_partials, poff, c.minmax_dev, ctx->stream, &e);
+  else
+  {
+    // a rank without any block this frame: empty list
+    cudaMemsetAsync(poff, 0, (n_pixels + 1) * sizeof(int), ctx->stream);
+    const int mm[2] = { 0x7fffffff, -1 };
+    e = cudaMemcpyAsync(c.minmax_dev, mm, sizeof(mm), cudaMemcpyHostToDevice, ctx->stream);
+  }
+  if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "partial pixel sort", e);
+  publish_minmax_kernel<<<1, 32, 0, ctx->stream>>>(c.peer_dev, c.rank, c.size, L.off_flags, par, c.minmax_dev,
+                                                   ctx->partial_count, c.max_partials);
+  // (2) fused pull + merge + fold + gather
+  MergeP2PParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.peers = c.peer_dev;
+  p.rank = c.rank;
+  p.size = c.size;
+  p.epoch = c.pepoch;
+  p.n_pixels = n_pixels;
+  p.off_flags = L.off_flags;
+  p.off_poff = L.off_poff[par];
+  p.off_psorted = L.off_psorted[par];
+  p.off_pout = L.off_pout;
+  p.sorted_cap = c.max_partials;
+  p.out_cap = c.max_pixels;
+  const int grid = ctx->sm_count * 4;
+  if (c.size <= 1) merge_fold_p2p_kernel<1><<<grid, 256, 0, ctx->stream>>>(p);
+  else if (c.size <= 2) merge_fold_p2p_kernel<2><<<grid, 256, 0, ctx->stream>>>(p);
+  else if (c.size <= 4) merge_fold_p2p_kernel<4><<<grid, 256, 0, ctx->stream>>>(p);
+  else if (c.size <= 8) merge_fold_p2p_kernel<8><<<grid, 256, 0, ctx->stream>>>(p);
+  else merge_fold_p2p_kernel<16><<<grid, 256, 0, ctx->stream>>>(p);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "merge_fold_p2p launch", e);
+  ctx->launches += 2;
+  Flags* f = reinterpret_cast<Flags*>(c.arena + L.off_flags);
+  if (c.rank == 0)
+  {
+    wait_done_kernel<<<1, 32, 0, ctx->stream>>>(f->p_done, c.size, c.pepoch);
+    ctx->launches++;
+    // root-only result (PartialCompositor.cpp:580-595): the read side now sees the composited list
+    ctx->plist = reinterpret_cast<const vr_partial*>(c.arena + L.off_pout);
+    ctx->plist_count = &f->p_out_count;
+    ctx->plist_cap = c.max_pixels;
+  }
+  else
+  {
+    // non-root ranks end with an empty result, their own list stays intact (re-usable)
+    ctx->plist = ctx->partials ? ctx->partials : reinterpret_cast<const vr_partial*>(c.arena);
+    ctx->plist_count = ctx->partial_count;
+    ctx->plist_cap = 0;
+  }
+  ctx->n_partials_host = 0;
+  return VR_OK;
 }

@@ -188,11 +188,50 @@ __global__ void braid_kernel(T* out, int nx, int ny, int nz, int i0, int j0, int
 }
 
 // ---------------------------------------------------------------- P4 partial composite
-__global__ void px_count_kernel(const vr_partial* __restrict__ p, size_t n, int* __restrict__ cnt)
+// Every kernel of this pipeline reads the list length from device memory (*count_dev, clamped
+// to cap): no host round trip between the tracer that appends partials and the compositor.
+__device__ __forceinline__ size_t list_len(const unsigned long long* count_dev, size_t cap)
 {
+  const unsigned long long c = *count_dev;
+  return c < cap ? (size_t)c : cap;
+}
+
+__global__ void partial_init_kernel(int* minmax, unsigned long long* out_count)
+{
+  if (minmax) { minmax[0] = 0x7fffffff; minmax[1] = -1; }
+  if (out_count) *out_count = 0ull;
+}
+
+// histogram of partials per pixel + the list's min/max pixel id (PartialCompositor::merge,
+// PartialCompositor.cpp:242-326 computes the same bounds for the redistribute step)
+__global__ void px_count_kernel(const vr_partial* __restrict__ p,
+                                const unsigned long long* __restrict__ count_dev, size_t cap,
+                                int* __restrict__ cnt, int* __restrict__ minmax)
+{
+  const size_t n = list_len(count_dev, cap);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
+  int lo = 0x7fffffff, hi = -1;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    atomicAdd(cnt + p[i].pixel_id, 1);
+  {
+    const int px = p[i].pixel_id;
+    atomicAdd(cnt + px, 1);
+    lo = min(lo, px);
+    hi = max(hi, px);
+  }
+  if (minmax)
+  {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0 && hi >= 0)
+    {
+      atomicMin(minmax, lo);
+      atomicMax(minmax + 1, hi);
+    }
+  }
 }
 
 // exclusive scan, three phases, 2048 elements per block
@@ -238,9 +277,9 @@ __global__ void scan_reduce_kernel(const int* __restrict__ in, size_t n, int* __
   block_exclusive_scan(s, &total);
   if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
-__global__ void scan_blocks_kernel(int* block_sums, int nb)
+// single block, serial over chunks of kScanT; also writes the grand total to *total_out
+__global__ void scan_blocks_kernel(int* block_sums, int nb, int* total_out)
 {
-  // single block, serial over chunks of kScanT
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
@@ -255,6 +294,7 @@ __global__ void scan_blocks_kernel(int* block_sums, int nb)
     if (threadIdx.x == 0) carry += total;
     __syncthreads();
   }
+  if (threadIdx.x == 0 && total_out) *total_out = carry;
 }
 __global__ void scan_apply_kernel(const int* __restrict__ in, size_t n,
                                   const int* __restrict__ block_sums, int* __restrict__ out)
@@ -278,10 +318,12 @@ __global__ void scan_apply_kernel(const int* __restrict__ in, size_t n,
   }
 }
 
-__global__ void px_scatter_kernel(const vr_partial* __restrict__ p, size_t n,
+__global__ void px_scatter_kernel(const vr_partial* __restrict__ p,
+                                  const unsigned long long* __restrict__ count_dev, size_t cap,
                                   const int* __restrict__ off, int* __restrict__ fill,
                                   int* __restrict__ sorted)
 {
+  const size_t n = list_len(count_dev, cap);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
   {
@@ -302,8 +344,28 @@ __device__ __forceinline__ void partial_blend(vr_partial& a, const vr_partial& o
   a.alpha = a.alpha > 1.f ? 1.f : a.alpha;
 }
 
-// one thread per pixel: order the pixel's segment by (depth, list index) -- the (pixel, depth)
-// key of VolumePartial::operator< with list order as the documented tie-break -- then fold.
+// order one pixel's index segment by (depth, list index): the (pixel, depth) key of
+// VolumePartial::operator< with list order as the documented tie-break.  Segments are as long as
+// the depth complexity of the scene (a handful), so an insertion sort in place is the right tool.
+__device__ __forceinline__ void sort_segment(const vr_partial* __restrict__ p, int* seg, int c)
+{
+  for (int a = 1; a < c; ++a)
+  {
+    const int ia = seg[a];
+    const float da = p[ia].depth;
+    int b = a - 1;
+    while (b >= 0)
+    {
+      const int ib = seg[b];
+      const float db = p[ib].depth;
+      if (db > da || (db == da && ib > ia)) { seg[b + 1] = ib; --b; }
+      else break;
+    }
+    seg[b + 1] = ia;
+  }
+}
+
+// one thread per pixel: sort the pixel's segment, fold it front to back, append the result
 __global__ void px_fold_kernel(const vr_partial* __restrict__ p, size_t n_pixels,
                                const int* __restrict__ cnt, const int* __restrict__ off,
                                int* __restrict__ sorted, vr_partial* __restrict__ out,
@@ -319,21 +381,7 @@ __global__ void px_fold_kernel(const vr_partial* __restrict__ p, size_t n_pixels
     if (c > 0)
     {
       int* seg = sorted + off[px];
-      // insertion sort of the index segment (segments are short: depth complexity of the scene)
-      for (int a = 1; a < c; ++a)
-      {
-        const int ia = seg[a];
-        const float da = p[ia].depth;
-        int b = a - 1;
-        while (b >= 0)
-        {
-          const int ib = seg[b];
-          const float db = p[ib].depth;
-          if (db > da || (db == da && ib > ia)) { seg[b + 1] = ib; --b; }
-          else break;
-        }
-        seg[b + 1] = ia;
-      }
+      sort_segment(p, seg, c);
       result = p[seg[0]];
       for (int a = 1; a < c; ++a) partial_blend(result, p[seg[a]]);
     }
@@ -346,6 +394,26 @@ __global__ void px_fold_kernel(const vr_partial* __restrict__ p, size_t n_pixels
       b0 = __shfl_sync(0xffffffffu, b0, 0);
       if (c > 0) out[b0 + __popc(mask & ((1u << lane) - 1u))] = result;
     }
+  }
+}
+
+// one thread per pixel: sort the pixel's segment and materialise it, so that the whole list
+// becomes ordered by (pixel, depth, list index) -- the form the multi-GPU merge pulls from
+__global__ void px_sort_emit_kernel(const vr_partial* __restrict__ p, size_t n_pixels,
+                                    const int* __restrict__ cnt, const int* __restrict__ off,
+                                    int* __restrict__ sorted, vr_partial* __restrict__ out,
+                                    size_t out_cap)
+{
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t px = (size_t)blockIdx.x * blockDim.x + threadIdx.x; px < n_pixels; px += stride)
+  {
+    const int c = cnt[px];
+    if (c == 0) continue;
+    const int o = off[px];
+    int* seg = sorted + o;
+    if (c > 1) sort_segment(p, seg, c);
+    for (int a = 0; a < c; ++a)
+      if ((size_t)(o + a) < out_cap) out[o + a] = p[seg[a]];
   }
 }
 
@@ -457,24 +525,51 @@ cudaError_t launch_synth_braid(void* field, int dtype, const int n[3], const int
   return cudaGetLastError();
 }
 
-int launch_partials_composite(const vr_partial* in, size_t n, size_t n_pixels,
-                              const PartialScratch& sc, vr_partial* out,
+// shared front half: histogram -> exclusive scan -> scatter of list indices by pixel
+static int partials_bin_by_pixel(const vr_partial* in, const unsigned long long* count_dev, size_t cap,
+                                 size_t n_pixels, const PartialScratch& sc, int* off /* n_pixels+1 */,
+                                 int* minmax, unsigned long long* out_count, cudaStream_t s)
+{
+  partial_init_kernel<<<1, 1, 0, s>>>(minmax, out_count);
+  cudaMemsetAsync(sc.px_count, 0, n_pixels * sizeof(int), s);
+  cudaMemsetAsync(sc.px_fill, 0, n_pixels * sizeof(int), s);
+  px_count_kernel<<<grid_for(cap, kT), kT, 0, s>>>(in, count_dev, cap, sc.px_count, minmax);
+  const int nb = (int)((n_pixels + kScanTile - 1) / kScanTile);
+  scan_reduce_kernel<<<nb, kScanT, 0, s>>>(sc.px_count, n_pixels, sc.scan_blocks);
+  scan_blocks_kernel<<<1, kScanT, 0, s>>>(sc.scan_blocks, nb, off + n_pixels);
+  scan_apply_kernel<<<nb, kScanT, 0, s>>>(sc.px_count, n_pixels, sc.scan_blocks, off);
+  px_scatter_kernel<<<grid_for(cap, kT), kT, 0, s>>>(in, count_dev, cap, off, sc.px_fill, sc.sorted_idx);
+  return 6;
+}
+
+int launch_partials_composite(const vr_partial* in, const unsigned long long* count_dev, size_t cap,
+                              size_t n_pixels, const PartialScratch& sc, vr_partial* out,
                               unsigned long long* out_count, cudaStream_t s, cudaError_t* err)
 {
   int launches = 0;
-  *err = cudaMemsetAsync(out_count, 0, sizeof(unsigned long long), s);
-  if (*err != cudaSuccess || n == 0) return launches;
-  cudaMemsetAsync(sc.px_count, 0, n_pixels * sizeof(int), s);
-  cudaMemsetAsync(sc.px_fill, 0, n_pixels * sizeof(int), s);
-  px_count_kernel<<<grid_for(n, kT), kT, 0, s>>>(in, n, sc.px_count);
-  const int nb = (int)((n_pixels + kScanTile - 1) / kScanTile);
-  scan_reduce_kernel<<<nb, kScanT, 0, s>>>(sc.px_count, n_pixels, sc.scan_blocks);
-  scan_blocks_kernel<<<1, kScanT, 0, s>>>(sc.scan_blocks, nb);
-  scan_apply_kernel<<<nb, kScanT, 0, s>>>(sc.px_count, n_pixels, sc.scan_blocks, sc.px_offset);
-  px_scatter_kernel<<<grid_for(n, kT), kT, 0, s>>>(in, n, sc.px_offset, sc.px_fill, sc.sorted_idx);
+  if (cap == 0)
+  {
+    partial_init_kernel<<<1, 1, 0, s>>>(nullptr, out_count);
+    *err = cudaGetLastError();
+    return 1;
+  }
+  launches += partials_bin_by_pixel(in, count_dev, cap, n_pixels, sc, sc.px_offset, nullptr, out_count, s);
   px_fold_kernel<<<grid_for(n_pixels, kT), kT, 0, s>>>(in, n_pixels, sc.px_count, sc.px_offset,
                                                        sc.sorted_idx, out, out_count);
-  launches = 6;
+  launches += 1;
+  *err = cudaGetLastError();
+  return launches;
+}
+
+int launch_partials_pixel_sort(const vr_partial* in, const unsigned long long* count_dev, size_t cap,
+                               size_t n_pixels, const PartialScratch& sc, vr_partial* sorted_out,
+                               size_t sorted_cap, int* off_out, int* minmax, cudaStream_t s,
+                               cudaError_t* err)
+{
+  int launches = partials_bin_by_pixel(in, count_dev, cap, n_pixels, sc, off_out, minmax, nullptr, s);
+  px_sort_emit_kernel<<<grid_for(n_pixels, kT), kT, 0, s>>>(in, n_pixels, sc.px_count, off_out,
+                                                            sc.sorted_idx, sorted_out, sorted_cap);
+  launches += 1;
   *err = cudaGetLastError();
   return launches;
 }

@@ -78,6 +78,7 @@ extern "C" vr_status vr_create(int device, vr_ctx** out)
   cudaMalloc(&ctx->tile_counter, sizeof(unsigned int));
   cudaMalloc(&ctx->sample_counter, sizeof(unsigned long long));
   cudaMalloc(&ctx->partial_count, sizeof(unsigned long long));
+  cudaMalloc(&ctx->partial_count_tmp, sizeof(unsigned long long));
   cudaMalloc(&ctx->lut, 1024 * sizeof(float4));
   if ((e = cudaGetLastError()) != cudaSuccess || !ctx->lut)
   {
@@ -85,6 +86,7 @@ extern "C" vr_status vr_create(int device, vr_ctx** out)
     return fail(nullptr, VR_ERR_NOMEM, "vr_create: small allocations failed: %s", cudaGetErrorString(e));
   }
   cudaMemset(ctx->partial_count, 0, sizeof(unsigned long long));
+  cudaMemset(ctx->partial_count_tmp, 0, sizeof(unsigned long long));
   cudaMemset(ctx->sample_counter, 0, sizeof(unsigned long long));
   *out = ctx;
   return VR_OK;
@@ -120,6 +122,7 @@ extern "C" void vr_destroy(vr_ctx* ctx)
   cudaFree(ctx->partials);
   cudaFree(ctx->partials_tmp);
   cudaFree(ctx->partial_count);
+  cudaFree(ctx->partial_count_tmp);
   cudaFree(ctx->px_count);
   cudaFree(ctx->px_offset);
   cudaFree(ctx->px_fill);
@@ -513,6 +516,7 @@ extern "C" vr_status vr_partials_begin(vr_ctx* ctx, int width, int height)
   ctx->pW = width;
   ctx->pH = height;
   ctx->n_partials_host = 0;
+  ctx->plist = nullptr; // read side sees the own list again
   CK(cudaMemsetAsync(ctx->partial_count, 0, sizeof(unsigned long long), ctx->stream));
   return VR_OK;
 }
@@ -549,9 +553,11 @@ extern "C" vr_status vr_partials_count(vr_ctx* ctx, size_t* n)
   if (!ctx) return VR_ERR_INVALID;
   REQUIRE(n, "vr_partials_count: NULL");
   unsigned long long c = 0;
-  CK(cudaMemcpyAsync(&c, ctx->partial_count, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+  const unsigned long long* src = ctx->plist ? ctx->plist_count : ctx->partial_count;
+  const size_t cap = ctx->plist ? ctx->plist_cap : ctx->partial_cap;
+  CK(cudaMemcpyAsync(&c, src, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  *n = (size_t)std::min<unsigned long long>(c, ctx->partial_cap);
+  *n = (size_t)std::min<unsigned long long>(c, cap);
   return VR_OK;
 }
 
@@ -565,7 +571,8 @@ extern "C" vr_status vr_partials_download(vr_ctx* ctx, vr_partial* out, size_t c
   REQUIRE(c <= capacity, "vr_partials_download: capacity %zu < %zu partials", capacity, c);
   if (c && out)
   {
-    CK(cudaMemcpyAsync(out, ctx->partials, c * sizeof(vr_partial), cudaMemcpyDeviceToHost, ctx->stream));
+    const vr_partial* src = ctx->plist ? ctx->plist : ctx->partials;
+    CK(cudaMemcpyAsync(out, src, c * sizeof(vr_partial), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
   }
   return VR_OK;
@@ -741,7 +748,7 @@ static vr_status ensure_partial_scratch(vr_ctx* ctx, size_t n_pixels, size_t n_p
     cudaFree(ctx->px_count); cudaFree(ctx->px_offset); cudaFree(ctx->px_fill); cudaFree(ctx->scan_blocks);
     ctx->px_count = ctx->px_offset = ctx->px_fill = ctx->scan_blocks = nullptr;
     CK(cudaMalloc(&ctx->px_count, n_pixels * sizeof(int)));
-    CK(cudaMalloc(&ctx->px_offset, n_pixels * sizeof(int)));
+    CK(cudaMalloc(&ctx->px_offset, (n_pixels + 1) * sizeof(int)));
     CK(cudaMalloc(&ctx->px_fill, n_pixels * sizeof(int)));
     CK(cudaMalloc(&ctx->scan_blocks, (n_pixels / 2048 + 2) * sizeof(int)));
     ctx->scratch_px = n_pixels;
@@ -765,26 +772,36 @@ static vr_status ensure_partial_scratch(vr_ctx* ctx, size_t n_pixels, size_t n_p
   return VR_OK;
 }
 
+namespace vr
+{
+vr_status ensure_partial_scratch_pub(vr_ctx* ctx, size_t n_pixels, size_t n_parts)
+{
+  return ensure_partial_scratch(ctx, n_pixels, n_parts);
+}
+}
+
 extern "C" vr_status vr_partials_composite(vr_ctx* ctx)
 {
   if (!ctx) return VR_ERR_INVALID;
   REQUIRE(ctx->pW > 0, "vr_partials_composite: call vr_partials_begin first");
   CK(cudaSetDevice(ctx->device));
-  size_t n = 0;
-  vr_status st = vr_partials_count(ctx, &n); // syncs: the list length sizes the launches
-  if (st != VR_OK) return st;
+  // no host sync: every kernel reads the list length from the device counter; the scratch is
+  // sized by the list's capacity, which the host knows
   const size_t n_pixels = (size_t)ctx->pW * ctx->pH;
-  st = ensure_partial_scratch(ctx, n_pixels, std::max<size_t>(n, 1));
+  vr_status st = ensure_partial_scratch(ctx, n_pixels, std::max<size_t>(ctx->partial_cap, 1));
   if (st != VR_OK) return st;
   PartialScratch sc{ ctx->px_count, ctx->px_offset, ctx->px_fill, ctx->sorted_idx, ctx->scan_blocks };
   cudaError_t e;
-  // fold into the tmp list, then swap: the context's list becomes the composited one
-  ctx->launches += launch_partials_composite(ctx->partials, n, n_pixels, sc, ctx->partials_tmp,
-                                             ctx->partial_count, ctx->stream, &e);
+  // fold into the tmp list (<= 1 partial per pixel), then swap: the context's list becomes the
+  // composited one.  The tmp counter is a second device scalar so the input count stays readable.
+  ctx->launches += launch_partials_composite(ctx->partials, ctx->partial_count, ctx->partial_cap, n_pixels,
+                                             sc, ctx->partials_tmp, ctx->partial_count_tmp, ctx->stream, &e);
   CK(e);
   std::swap(ctx->partials, ctx->partials_tmp);
   std::swap(ctx->partial_cap, ctx->partial_tmp_cap);
+  std::swap(ctx->partial_count, ctx->partial_count_tmp);
   ctx->n_partials_host = 0;
+  ctx->plist = nullptr;
   return VR_OK;
 }
 
@@ -809,8 +826,11 @@ extern "C" vr_status vr_partials_to_canvas(vr_ctx* ctx, const vr_camera* cam)
   std::memcpy(tp.pv, pv.m, sizeof(tp.pv));
   tp.W = ctx->W;
   tp.H = ctx->H;
-  if (ctx->partial_cap == 0) return VR_OK;
-  CK(launch_partials_to_canvas(ctx->partials, ctx->partial_count, ctx->partial_cap, tp,
+  const vr_partial* list = ctx->plist ? ctx->plist : ctx->partials;
+  const unsigned long long* list_count = ctx->plist ? ctx->plist_count : ctx->partial_count;
+  const size_t list_cap = ctx->plist ? ctx->plist_cap : ctx->partial_cap;
+  if (list_cap == 0) return VR_OK;
+  CK(launch_partials_to_canvas(list, list_count, list_cap, tp,
                                ctx->canvas_rgba, ctx->canvas_depth, ctx->stream));
   ctx->launches++;
   return VR_OK;
@@ -826,7 +846,7 @@ extern "C" vr_status vr_composite_partials(vr_ctx* ctx, const vr_partial* in, si
   for (size_t i = 0; i < n_in; ++i)
     REQUIRE(in[i].pixel_id >= 0 && (long long)in[i].pixel_id < (long long)width * height,
             "vr_composite_partials: pixel id %d outside %dx%d", in[i].pixel_id, width, height);
-  ctx->n_partials_host = 0;
+  ctx->n_partials_host = n_in;
   st = ensure_partials(ctx, std::max<size_t>(n_in, 1));
   if (st != VR_OK) return st;
   if (n_in)

@@ -75,7 +75,9 @@ struct Comm
   unsigned char* arena = nullptr;               // own arena (cudaMalloc, IPC-exported)
   std::vector<unsigned char*> peer;             // mapped arenas, peer[rank] == arena
   unsigned char** peer_dev = nullptr;           // device copy of the pointer table
-  unsigned int epoch = 0;
+  unsigned int epoch = 0;                       // image path frames composited so far
+  unsigned int pepoch = 0;                      // partial path frames
+  int* minmax_dev = nullptr;                    // {min,max} pixel id of the current list
 };
 
 } // namespace vr
@@ -110,6 +112,12 @@ struct vr_ctx
   vr_partial* partials = nullptr;
   size_t partial_cap = 0;
   unsigned long long* partial_count = nullptr; // device counter
+  unsigned long long* partial_count_tmp = nullptr;
+  // the list the read-side entry points (count/download/to_canvas) see: the own list above, or
+  // the composited list in the exchange arena after vr_comm_composite_partials on rank 0
+  const vr_partial* plist = nullptr;
+  const unsigned long long* plist_count = nullptr;
+  size_t plist_cap = 0;
   size_t n_partials_host = 0;                  // valid after a sync'ing call
   int pW = 0, pH = 0;
   // partial composite scratch
@@ -151,16 +159,23 @@ cudaError_t launch_synth_braid(void* field, int dtype, const int n[3], const int
 struct PartialScratch
 {
   int* px_count;
-  int* px_offset;
+  int* px_offset; // n_pixels + 1
   int* px_fill;
   int* sorted_idx;
   int* scan_blocks;
 };
 // composite the list `in` (n partials, pixel ids in [0, n_pixels)) into `out` (<= 1 per pixel);
 // *out_count (device) receives the number written.  Returns number of kernels launched.
-int launch_partials_composite(const vr_partial* in, size_t n, size_t n_pixels,
-                              const PartialScratch& sc, vr_partial* out,
+// The list length is read on the device (*count_dev, clamped to cap).
+int launch_partials_composite(const vr_partial* in, const unsigned long long* count_dev, size_t cap,
+                              size_t n_pixels, const PartialScratch& sc, vr_partial* out,
                               unsigned long long* out_count, cudaStream_t s, cudaError_t* err);
+// Reorder the list by (pixel, depth, list index) into sorted_out and write the exclusive
+// per-pixel offsets (n_pixels + 1 ints) and the list's {min,max} pixel id.
+int launch_partials_pixel_sort(const vr_partial* in, const unsigned long long* count_dev, size_t cap,
+                               size_t n_pixels, const PartialScratch& sc, vr_partial* sorted_out,
+                               size_t sorted_cap, int* off_out, int* minmax, cudaStream_t s,
+                               cudaError_t* err);
 
 struct ToCanvasParams
 {

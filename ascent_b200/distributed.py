@@ -1,0 +1,327 @@
+"""One process per GPU: the host-side plumbing of the sort-last path.
+
+What vtk-h does with MPI around the volume renderer (global bounds / scalar range Allreduce,
+Renderer.cpp:144-179; visibility ordering gather + sort + scatter, VolumeRenderer.cpp:690-867;
+"one domain per rank?" Allreduce, :468-480) is done here with ``torch.distributed`` -- NCCL on the
+GPU box, gloo in the CPU tests.  Only O(ranks) scalars travel this way; pixels and partials move
+GPU-to-GPU inside the compositing kernels (csrc/comm.cu) through the IPC-mapped exchange arenas
+whose handles are all-gathered once at start-up.
+"""
+import os
+import time
+
+import numpy as np
+
+from . import _lib
+
+
+# ----------------------------------------------------------------------------- pure host logic
+def assign_blocks(n_blocks, world_size):
+    """Contiguous block sets, one per rank (ContiguousAssigner-style): rank r owns
+    [r*n/world, (r+1)*n/world)."""
+    return [list(range(r * n_blocks // world_size, (r + 1) * n_blocks // world_size))
+            for r in range(world_size)]
+
+
+def one_domain_per_rank(n_local, dist=None):
+    """VolumeRenderer::DoExecute's path switch (VolumeRenderer.cpp:468-480, OneDomainPerRank):
+    path A only when EVERY rank holds exactly one domain."""
+    flag = 1 if n_local == 1 else 0
+    if dist is None:
+        return bool(flag)
+    import torch
+    t = torch.tensor([flag], dtype=torch.int32, device=_dist_device(dist))
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(int(t.item()))
+
+
+def _dist_device(dist):
+    import torch
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def all_gather_array(arr, dist):
+    """all-gather a small fixed-shape numpy array; returns (world, *shape)."""
+    import torch
+    a = np.ascontiguousarray(arr)
+    t = torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).to(_dist_device(dist))
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return np.stack([o.cpu().numpy().view(a.dtype).reshape(a.shape) for o in out])
+
+
+def global_range(local_min, local_max, dist):
+    """Renderer::PreExecute: global scalar range (two Allreduces in the reference)."""
+    import torch
+    t = torch.tensor([local_min, -local_max], dtype=torch.float64, device=_dist_device(dist))
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return float(t[0].item()), float(-t[1].item())
+
+
+def global_bounds(local_bounds, dist):
+    """vtkh::DataSet::GetGlobalBounds: union over ranks of the union of local domain bounds."""
+    import torch
+    lb = np.asarray(local_bounds, np.float64).reshape(-1, 6)
+    if lb.shape[0] == 0:
+        v = np.array([np.inf, np.inf, np.inf, np.inf, np.inf, np.inf])
+    else:
+        v = np.array([lb[:, 0].min(), -lb[:, 1].max(), lb[:, 2].min(), -lb[:, 3].max(), lb[:, 4].min(),
+                      -lb[:, 5].max()])
+    t = torch.from_numpy(v).to(_dist_device(dist))
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    v = t.cpu().numpy()
+    return np.array([v[0], -v[1], v[2], -v[3], v[4], -v[5]])
+
+
+def global_visibility_order(local_bounds, cam, dist):
+    """FindVisibilityOrdering + DepthSort (VolumeRenderer.cpp:690-867) for one camera: every rank's
+    domain depths are gathered, sorted ascending (ties keep (rank, domain) order) and each rank gets
+    the order index of its own domains.  The reference gathers to rank 0 and scatters; all-gather +
+    the same sort on every rank gives the identical integers without the second hop.
+    Every rank must hold the same number of domains (the bench and the reference's path A do)."""
+    lb = np.asarray(local_bounds, np.float64).reshape(-1, 6)
+    allb = all_gather_array(lb, dist).reshape(-1, 6)  # (rank, domain) order
+    order = _lib.visibility_order(allb, cam)
+    n = lb.shape[0]
+    r = dist.get_rank()
+    return order.reshape(dist.get_world_size(), n), order.reshape(dist.get_world_size(), n)[r]
+
+
+def connect(ctx, dist, max_pixels, max_partials):
+    """Allocate this rank's exchange arena, all-gather the CUDA IPC handles, map the peers."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    # the arena geometry must be the same on every rank: agree on the largest request
+    t = torch.tensor([max_pixels, max_partials], dtype=torch.int64, device=_dist_device(dist))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_pixels, max_partials = int(t[0].item()), int(t[1].item())
+    h = ctx.comm_init(rank, world, max_pixels, max_partials)
+    hs = all_gather_array(np.frombuffer(h, np.uint8), dist)
+    dist.barrier()
+    ctx.comm_connect(hs.tobytes())
+    dist.barrier()
+
+
+# ----------------------------------------------------------------------------- bench (N > 1)
+def run_bench(args, wl, bench):
+    """BASELINE config 3 on N ranks (one per GPU): 8 blocks of 512^3 over N GPUs, 3840x2160,
+    sort-last render + composite to rank 0.  N == 8 -> path A (uint8 image, direct-send fused in
+    one P2P kernel); N < 8 -> path B (float partials, pull + merge + fold fused in one P2P kernel),
+    exactly the reference's switch."""
+    import json
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = _lib.Context(local)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    blocks = bench.block_layout(wl)
+    mine = assign_blocks(len(blocks), world)[rank]
+    W, H = wl["W"], wl["H"]
+    nvox = int(np.prod(blocks[0]["dims"]))
+    fields = {}
+    with torch.cuda.stream(stream):
+        for i in mine:
+            b = blocks[i]
+            t = torch.empty(nvox, dtype=torch.float32, device="cuda")
+            ctx.synth_braid_dev(t.data_ptr(), _lib.VR_F32, b["dims"], b["start"], b["glob"])
+            fields[i] = t
+        stream.synchronize()
+        lmin = min(float(t.min()) for t in fields.values())
+        lmax = max(float(t.max()) for t in fields.values())
+    rmin, rmax = global_range(lmin, lmax, dist)
+    sp = bench.scene_params(wl, blocks, (rmin, rmax))
+    ctx.set_tf(sp["lut"])
+    for i in mine:
+        b = blocks[i]
+        ctx.block_uniform(i, b["dims"], b["origin"], b["spacing"], None, device_ptr=fields[i].data_ptr(),
+                          dtype=_lib.VR_F32)
+    cam = sp["cam"]
+    path_a = one_domain_per_rank(len(mine), dist)
+    # upper bound of partials per rank: every ray of every local block's screen subset
+    max_partials = 0
+    if not path_a:
+        for i in mine:
+            s = _lib.find_subset(cam, W, H, sp["bounds"][i])
+            max_partials += s[2] * s[3]
+    connect(ctx, dist, W * H, max_partials)
+    vis_all, _ = global_visibility_order([sp["bounds"][i] for i in mine], cam, dist)
+    vis_rank = np.ascontiguousarray(vis_all[:, 0], np.int32)  # path A: one domain per rank
+
+    def render():
+        if path_a:
+            ctx.canvas_clear(W, H)
+            ctx.trace_to_canvas(mine[0], cam, sp["sample_dist"], rmin, rmax, False)
+        else:
+            ctx.partials_begin(W, H)
+            for i in mine:
+                ctx.trace_to_partials(i, cam, sp["sample_dist"], rmin, rmax, False)
+
+    def composite():
+        if path_a:
+            ctx.image_from_canvas()
+            ctx.comm_composite_images(vis_rank)
+            if rank == 0:
+                ctx.image_result_to_canvas()
+        else:
+            if rank == 0:
+                ctx.canvas_clear(W, H)
+            ctx.comm_composite_partials()
+            if rank == 0:
+                ctx.partials_to_canvas(cam)
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    warm = max(args.warmup, 3)
+    with torch.cuda.stream(stream):
+        for _ in range(warm):
+            render()
+            composite()
+        torch.cuda.synchronize()
+        dist.barrier()
+        l0 = ctx.kernel_launches()
+        clocks = bench.ClockSampler(local) if rank == 0 else None
+        if clocks:
+            clocks.start()
+        marks = [(ev(), ev(), ev()) for _ in range(args.steps)]
+        t0, t1 = ev(), ev()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0.record(stream)
+        for k in range(args.steps):
+            marks[k][0].record(stream)
+            render()
+            marks[k][1].record(stream)
+            composite()
+            marks[k][2].record(stream)
+        t1.record(stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        clk = clocks.stop() if clocks else None
+        launches = ctx.kernel_launches() - l0
+        total_ms = t0.elapsed_time(t1)
+        render_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in marks]))
+        tail_ms = float(np.mean([b.elapsed_time(c) for _, b, c in marks]))
+
+        # composite alone: all local images/partials resident, ranks aligned by a barrier
+        comp = []
+        for _ in range(min(args.steps, 10)):
+            render()
+            torch.cuda.synchronize()
+            dist.barrier()
+            a, b = ev(), ev()
+            a.record(stream)
+            composite()
+            b.record(stream)
+            torch.cuda.synchronize()
+            comp.append(a.elapsed_time(b))
+        comp_ms = float(np.median(comp))
+        n_partials = 0 if path_a else _count_local_partials(ctx, render)
+
+    t = torch.tensor([total_ms, render_ms, tail_ms, comp_ms, float(launches), float(n_partials)],
+                     dtype=torch.float64, device="cuda")
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tsum = t.clone()
+    dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    total_ms, render_ms, tail_ms, comp_ms = [float(x) for x in tmax[:4]]
+    ms = total_ms / args.steps
+
+    # ---- e2e: every rank publishes its blocks from pinned host memory, root reads the canvas back
+    e2e = _e2e(ctx, dist, stream, blocks, mine, fields, sp, cam, W, H, rmin, rmax, render, composite,
+               rank, max(3, min(args.steps, 5)))
+
+    if rank == 0:
+        pk, pk_src = bench.peaks()
+        alg = nvox * 4 * len(blocks) / world + W * H * 20  # per GPU per frame
+        if path_a:
+            nv_bytes = (world - 1) / world * W * H * 8 * 2  # pulled in + pushed to root, per GPU
+        else:
+            nv_bytes = float(tsum[5]) / world * 24.0 * (world - 1) / world
+        line = {"metric": "volume_render_mrays_per_s", "value": W * H / (ms * 1e-3) / 1e6, "unit": "Mrays/s",
+                "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": wl["name"], "image": [W, H], "samples": bench.SAMPLES,
+                           "path": "A (uint8 image, P2P direct-send fold)" if path_a else
+                                   "B (float partials, P2P pull+merge+fold)",
+                           "blocks_per_gpu": len(mine),
+                           "l2": "inputs (%.0f MB of field per GPU) larger than the 126 MB L2" % (
+                               nvox * 4 * len(mine) / 1e6)},
+                "frames_per_s": 1e3 / ms, "render_ms_per_frame": render_ms,
+                "composite_ms_per_frame": comp_ms, "composite_in_step_ms": tail_ms,
+                "partials_total": int(tsum[5]),
+                "nvlink": {"bytes_per_gpu_per_frame": nv_bytes,
+                           "achieved_gbs": nv_bytes / (comp_ms * 1e-3) / 1e9, "peak_gbs": 770.0,
+                           "peak_source": "measured peer copy per direction (B200_PROFILING.md)"},
+                "e2e": e2e, "gpu_launches": int(tsum[4]), "clocks": clk,
+                "roofline": {"bound": "hbm", "kernel": "trace_kernel (sampler.cu)",
+                             "achieved": alg / (render_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+                             "peak_source": pk_src, "unit": "GB/s",
+                             "frac": alg / (render_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                             "algorithmic_bytes_per_gpu_per_frame": alg,
+                             "kernel_ms_per_frame": render_ms, "launches_per_frame": len(mine)},
+                "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def _count_local_partials(ctx, render):
+    render()
+    return ctx.partials_count()
+
+
+def _e2e(ctx, dist, stream, blocks, mine, fields, sp, cam, W, H, rmin, rmax, render, composite, rank, n):
+    import torch
+    nvox = int(np.prod(blocks[0]["dims"]))
+    host = {}
+    for i in mine:
+        h = torch.empty(nvox, dtype=torch.float32, pin_memory=True)
+        h.copy_(fields[i])
+        host[i] = h.numpy()
+    rgba_h = torch.zeros(H * W * 4, dtype=torch.float32, pin_memory=True).numpy() if rank == 0 else None
+    depth_h = torch.zeros(H * W, dtype=torch.float32, pin_memory=True).numpy() if rank == 0 else None
+
+    def frame():
+        for i in mine:
+            b = blocks[i]
+            ctx.block_uniform(i, b["dims"], b["origin"], b["spacing"], host[i])  # publish (H2D)
+        render()
+        composite()
+        if rank == 0:
+            ctx.canvas_download(W, H, rgba_h, depth_h)
+        else:
+            ctx.synchronize()
+
+    with torch.cuda.stream(stream):
+        frame()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            frame()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dt = (time.perf_counter() - t0) / n
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    # restore the zero-copy device blocks
+    for i in mine:
+        b = blocks[i]
+        ctx.block_uniform(i, b["dims"], b["origin"], b["spacing"], None, device_ptr=fields[i].data_ptr(),
+                          dtype=_lib.VR_F32)
+    return {"value": W * H / dt / 1e6, "unit": "Mrays/s", "ms_per_step": dt * 1e3,
+            "h2d_bytes_per_step": nvox * 4 * len(blocks), "d2h_bytes_per_step": W * H * 20,
+            "what": "every rank: vr_block_uniform(host field) per local block, render, P2P composite; "
+                    "rank 0: vr_canvas_download"}

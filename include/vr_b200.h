@@ -187,7 +187,10 @@ VR_API vr_status vr_composite_partials(vr_ctx* ctx, const vr_partial* in, size_t
  * through whatever transport the host has (MPI_Allgather in Ascent, torch.distributed in the
  * harness) and maps its peers' arenas; after that images/partials move GPU-to-GPU over NVLink
  * inside the compositing kernels themselves (direct-send: DirectSendCompositor.cpp:121-181,
- * vtkh_diy_partial_redistribute.hpp:58-152) -- no host staging, no MPI in the data path.       */
+ * vtkh_diy_partial_redistribute.hpp:58-152) -- no host staging, no MPI in the data path.
+ * max_pixels / max_partials size the arena (largest frame, longest per-rank partial list; 0
+ * partials = image path only) and MUST be identical on every rank: a rank addresses its peers'
+ * arenas with its own layout (vr_comm_connect checks and fails otherwise).                     */
 #define VR_IPC_HANDLE_BYTES 64
 VR_API vr_status vr_comm_init(vr_ctx* ctx, int rank, int n_ranks, size_t max_pixels,
                               size_t max_partials, void* handle_out /* VR_IPC_HANDLE_BYTES */);

@@ -1,0 +1,176 @@
+"""Worker run under ``python -m torch.distributed.run`` by test_multi_rank.py.
+
+mode "host" (gloo, CPU): the host-side plumbing of ascent_b200.distributed against the oracle.
+mode "gpu"  (nccl, one GPU per rank): sort-last path A (uint8 images, P2P fold) and path B (float
+partials, P2P pull+merge+fold) against the oracle at the same rank/block layout (SURVEY 8(d):
+"parity is always vs the oracle at the same layout").  Exit code 0 = all checks passed."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from ascent_b200 import _lib, color_table, datasets, distributed as D  # noqa: E402
+
+
+def scene(world, per_axis=2, n_block=12, az=25.0, W=320, H=200):
+    from oracle import oracle as O
+    doms = datasets.braid_uniform_blocks(n_block, per_axis, dtype=np.float32)
+    bounds = [datasets.domain_bounds(d) for d in doms]
+    gb = datasets.union_bounds(bounds)
+    cam = O.camera_reset_to_bounds(gb)
+    O.camera_azimuth(cam, az)
+    O.camera_elevation(cam, az / 2.0)
+    lut = color_table.parse_color_table({"name": "cool to warm", "control_points": [
+        {"type": "alpha", "position": 0., "alpha": 0.},
+        {"type": "alpha", "position": 1., "alpha": 1.}]}).corrected_opacity(100).lut()
+    return dict(doms=doms, bounds=bounds, gb=gb, cam=cam, lut=lut, W=W, H=H,
+                sample_dist=O.sample_distance(gb, 100))
+
+
+def host_checks(rank, world):
+    from oracle import oracle as O
+    sc = scene(world)
+    owners = D.assign_blocks(len(sc["doms"]), world)
+    assert sorted(sum(owners, [])) == list(range(len(sc["doms"])))
+    mine = owners[rank]
+    # global scalar range / bounds == the serial values
+    lmin = min(float(sc["doms"][i]["field"].min()) for i in mine)
+    lmax = max(float(sc["doms"][i]["field"].max()) for i in mine)
+    rmin, rmax = D.global_range(lmin, lmax, dist)
+    assert rmin == min(float(d["field"].min()) for d in sc["doms"])
+    assert rmax == max(float(d["field"].max()) for d in sc["doms"])
+    gb = D.global_bounds([sc["bounds"][i] for i in mine], dist)
+    assert np.array_equal(gb, sc["gb"])
+    # path switch
+    assert D.one_domain_per_rank(len(mine), dist) == (len(mine) == 1)
+    assert D.one_domain_per_rank(1 if rank == 0 else 2, dist) is False
+    # visibility order: identical integers to the oracle's serial DepthSort over (rank, domain)
+    vis_all, vis_mine = D.global_visibility_order([sc["bounds"][i] for i in mine], sc["cam"], dist)
+    ref, _ = O.visibility_order(np.array([sc["bounds"][i] for r in range(world) for i in owners[r]]), sc["cam"])
+    assert np.array_equal(vis_all.reshape(-1), ref), (vis_all, ref)
+    assert np.array_equal(vis_mine, ref.reshape(world, -1)[rank])
+    # handle all-gather plumbing (bytes in, bytes out, rank order)
+    hs = D.all_gather_array(np.full(64, rank, np.uint8), dist)
+    assert hs.shape == (world, 64) and all((hs[r] == r).all() for r in range(world))
+    # partial ownership formula of the merge kernel == oracle's RegularDecomposer restatement
+    for (lo, hi) in [(0, 63999), (17, 1000), (5, 5), (100, 100 + world - 2)]:
+        width = max((hi - lo + 1) // world, 1)
+        for px in {lo, hi, (lo + hi) // 2, min(lo + width, hi), min(lo + width - 1, hi)}:
+            own = [r for r in range(world)
+                   if min(lo + width * r, hi + 1) <= px < (hi + 1 if r == world - 1 else min(lo + width * (r + 1), hi + 1))]
+            assert own == [O.partial_owner(px, lo, hi, world)], (px, lo, hi, own)
+
+
+def gpu_checks(rank, world):
+    from oracle import oracle as O
+    import scenes
+    ctx = _lib.Context(torch.cuda.current_device())
+    try:
+        # ---------------- path B: 8 blocks over `world` ranks
+        sc = scene(world)
+        W, H = sc["W"], sc["H"]
+        owners = D.assign_blocks(len(sc["doms"]), world)
+        mine = owners[rank]
+        rmin = min(float(d["field"].min()) for d in sc["doms"])
+        rmax = max(float(d["field"].max()) for d in sc["doms"])
+        ctx.set_tf(sc["lut"])
+        for i in mine:
+            ctx.block_from_domain(i, sc["doms"][i])
+        D.connect(ctx, dist, W * H, W * H * len(mine))
+        for rep in range(3):  # several frames: epoch parity / double buffering, moving camera
+            cam = sc["cam"]
+            if rep:
+                O.camera_azimuth(cam, 7.0)
+            ctx.partials_begin(W, H)
+            for i in mine:
+                ctx.trace_to_partials(i, cam, sc["sample_dist"], rmin, rmax, False)
+            if rank == 0:
+                ctx.canvas_clear(W, H)
+            ctx.comm_composite_partials()
+            if rank == 0:
+                got = ctx.partials_download()
+                ctx.partials_to_canvas(cam)
+                rgba, depth = ctx.canvas_download(W, H)
+                o_rgba, o_depth = O.new_canvas(W, H)
+                pl = [O.render_partials(scenes.oracle_block(sc["doms"][i]), cam, W, H, sc["lut"],
+                                        sc["sample_dist"], rmin, rmax, o_depth)
+                      for r in range(world) for i in owners[r]]
+                ref = O.composite_partials(pl)
+                a = np.sort(got, order="pixel_id")
+                b = np.sort(ref, order="pixel_id")
+                assert a.size == b.size and a.size > 1000, (a.size, b.size)
+                assert a.tobytes() == b.tobytes(), "path B: composited partials differ from the oracle"
+                O.partials_to_canvas(ref, cam, W, H, o_rgba, o_depth)
+                assert np.array_equal(rgba, o_rgba), "path B canvas differs"
+            else:
+                assert ctx.partials_count() == 0  # root-only result
+            dist.barrier()
+        for i in mine:
+            ctx.block_free(i)
+
+        # ---------------- path A: one block per rank
+        doms = datasets.braid_uniform_blocks(14, 2, dtype=np.float32)[:world]
+        bounds = [datasets.domain_bounds(d) for d in doms]
+        gb = datasets.union_bounds(bounds)
+        rmin = min(float(d["field"].min()) for d in doms)
+        rmax = max(float(d["field"].max()) for d in doms)
+        sd = O.sample_distance(gb, 100)
+        ctx.block_from_domain(0, doms[rank])
+        for rep, (az, el) in enumerate([(0., 0.), (160., 10.), (-70., 45.)]):
+            cam = O.camera_reset_to_bounds(gb)
+            O.camera_azimuth(cam, az)
+            O.camera_elevation(cam, el)
+            _, vis_mine = D.global_visibility_order([bounds[rank]], cam, dist)
+            vis_all, _ = D.global_visibility_order([bounds[rank]], cam, dist)
+            ctx.canvas_clear(W, H)
+            ctx.trace_to_canvas(0, cam, sd, rmin, rmax, False)
+            ctx.image_from_canvas()
+            ctx.comm_composite_images(np.ascontiguousarray(vis_all[:, 0], np.int32))
+            if rank == 0:
+                u8, d = ctx.image_result_download(W, H)
+                layers, depths = [], []
+                for dom in doms:
+                    r, dd = O.new_canvas(W, H)
+                    O.render_to_canvas(scenes.oracle_block(dom), cam, W, H, sc["lut"], sd, rmin, rmax, r, dd)
+                    q = O.image_init(r, dd, 0)
+                    layers.append(q[0])
+                    depths.append(q[1])
+                order, _ = O.visibility_order(np.array(bounds), cam)
+                ref, rd = O.ordered_composite(np.stack(layers), np.stack(depths), order)
+                assert np.array_equal(u8, ref), "path A: composited uint8 image differs (rep %d)" % rep
+                cov = ref[:, 3] > 0
+                assert np.array_equal(d[cov], rd[cov])
+                assert cov.sum() > 1000
+            else:
+                ctx.synchronize()
+            dist.barrier()
+    finally:
+        ctx.close()
+
+
+def main():
+    mode = sys.argv[1]
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    if mode == "host":
+        dist.init_process_group("gloo")
+        host_checks(rank, world)
+    else:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+        gpu_checks(rank, world)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("multi-rank %s checks OK (world=%d)" % (mode, world))
+
+
+if __name__ == "__main__":
+    main()
