@@ -16,13 +16,14 @@ VR_F32, VR_F64 = 0, 1
 VR_POINT, VR_CELL = 0, 1
 VR_HOST, VR_DEVICE = 0, 1
 IPC_HANDLE_BYTES = 64
+FRAME_WRITE_CANVAS, FRAME_NO_CLEAR = 1, 2
 
 # every symbol include/vr_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "vr_create", "vr_destroy", "vr_last_error", "vr_set_stream", "vr_synchronize",
     "vr_kernel_launches", "vr_block_uniform", "vr_block_rectilinear", "vr_block_free",
     "vr_block_bounds", "vr_set_tf", "vr_canvas_clear", "vr_canvas_upload", "vr_canvas_download",
-    "vr_canvas_ptrs", "vr_trace_to_canvas", "vr_render_image", "vr_partials_begin",
+    "vr_canvas_ptrs", "vr_trace_to_canvas", "vr_render_image", "vr_trace_to_image", "vr_partials_begin",
     "vr_trace_to_partials", "vr_partials_count", "vr_partials_download", "vr_render_partials",
     "vr_free", "vr_image_from_canvas", "vr_image_download", "vr_fold_images_dev",
     "vr_composite_images", "vr_zbuffer_composite_dev", "vr_image_to_canvas_dev",
@@ -81,6 +82,8 @@ def load():
         "vr_trace_to_canvas": (C.c_int, [vp, C.c_int, cam, C.c_float, C.c_float, C.c_float, C.c_int]),
         "vr_render_image": (C.c_int, [vp, C.c_int, cam, C.c_int, C.c_int, C.c_float, C.c_float,
                                       C.c_float, vp, vp]),
+        "vr_trace_to_image": (C.c_int, [vp, C.c_int, cam, C.c_int, C.c_int, C.c_float, C.c_float,
+                                        C.c_float, C.c_int]),
         "vr_partials_begin": (C.c_int, [vp, C.c_int, C.c_int]),
         "vr_trace_to_partials": (C.c_int, [vp, C.c_int, cam, C.c_float, C.c_float, C.c_float, C.c_int]),
         "vr_partials_count": (C.c_int, [vp, C.POINTER(sz)]),
@@ -273,6 +276,12 @@ class Context:
         assert rgba.dtype == np.float32 and depth.dtype == np.float32
         self._ck(self.lib.vr_render_image(self.h, block_id, C.byref(as_camera(cam)), W, H, sample_dist,
                                           rmin, rmax, rgba.ctypes.data, depth.ctypes.data))
+
+    def trace_to_image(self, block_id, cam, W, H, sample_dist, rmin, rmax, write_canvas=False,
+                       no_clear=False):
+        flags = (FRAME_WRITE_CANVAS if write_canvas else 0) | (FRAME_NO_CLEAR if no_clear else 0)
+        self._ck(self.lib.vr_trace_to_image(self.h, block_id, C.byref(as_camera(cam)), W, H, sample_dist,
+                                            rmin, rmax, flags))
 
     # -- path B
     def partials_begin(self, W, H):

@@ -48,6 +48,9 @@ struct Flags
   unsigned int p_cta_done;
   unsigned int p_overflow;         // set when a list did not fit max_partials
   unsigned long long p_out_count;  // (rank 0) length of the composited list
+  // image path: the rectangle {x0,y0,x1,y1} (x in multiples of 4) outside of which rank r's image
+  // of that epoch parity is empty (colour 0, depth 1.001) and need not be read
+  int img_rect[2][kMaxRanks][4];
   // geometry of this arena: every rank must have been initialised with the same values, because
   // a rank addresses its peers' arenas with its own layout (checked in vr_comm_connect)
   unsigned long long cfg_max_pixels, cfg_max_partials;
@@ -85,13 +88,23 @@ __device__ __forceinline__ float blend_depth(float f, float b)
 }
 
 // grid: persistent, multiple of the SM count.  16 bytes (4 pixels) per lane per layer.
+// Ownership is round-robin in chunks of 1024 pixels (balanced even when the covered region is a
+// band of rows).  A rank's image is only read inside the rectangle it announced: outside it the
+// layer is colour 0 / depth 1.001, which ImageCompositor::Blend treats as the identity for colour
+// and as the constant 1.001 for depth -- folded in without touching NVLink.  Groups no rank covers
+// are written by rank 0 itself.
+constexpr int kChunkGroups = 256; // 4-pixel groups per ownership chunk
+
 __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ FoldP2PParams P)
 {
   Flags* my_flags = reinterpret_cast<Flags*>(P.peers[P.rank] + P.off_flags);
+  const int par = P.epoch & 1;
   // ---- announce: my image for this epoch is complete (previous kernel on this stream wrote it)
   if (blockIdx.x == 0 && threadIdx.x < P.size)
   {
     Flags* f = reinterpret_cast<Flags*>(P.peers[threadIdx.x] + P.off_flags);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ((volatile int*)f->img_rect[par][P.rank])[k] = P.rect[k];
     __threadfence_system();
     st_release_sys(&f->ready[P.rank], P.epoch);
   }
@@ -100,11 +113,13 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
     while (ld_acquire_sys(&my_flags->ready[threadIdx.x]) < P.epoch) __nanosleep(64);
   __syncthreads();
 
-  // my pixel range (in units of 4 pixels)
-  const size_t n4 = (P.n_pixels + 3) / 4;
-  const size_t chunk4 = (n4 + P.size - 1) / P.size;
-  const size_t lo = chunk4 * P.rank;
-  const size_t hi = lo + chunk4 < n4 ? lo + chunk4 : n4;
+  __shared__ int s_rect[kMaxRanks][4]; // in fold order
+  if (threadIdx.x < P.size * 4)
+  {
+    const int l = threadIdx.x >> 2, k = threadIdx.x & 3;
+    s_rect[l][k] = ((volatile int*)my_flags->img_rect[par][P.order[l]])[k];
+  }
+  __syncthreads();
 
   const uint4* layer_rgba[kMaxRanks];
   const float4* layer_depth[kMaxRanks];
@@ -118,18 +133,51 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
   uint4* out_rgba = reinterpret_cast<uint4*>(P.peers[0] + P.off_res_rgba);
   float4* out_depth = reinterpret_cast<float4*>(P.peers[0] + P.off_res_depth);
 
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride)
+  // when W % 4 != 0 the host announces an unbounded rectangle, so x/y below are never compared
+  const size_t n4 = (P.n_pixels + 3) / 4;
+  const int w4 = P.W >= 4 ? P.W / 4 : 1;
+  const size_t n_chunks = (n4 + kChunkGroups - 1) / kChunkGroups;
+  // my chunks: rank, rank + size, ...; rank 0 also walks the others' chunks for uncovered groups
+  for (size_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x)
   {
-    // issue all layer loads first (they are independent: N outstanding 16-byte NVLink reads)
+    const bool mine = (int)(chunk % (size_t)P.size) == P.rank;
+    if (!mine && P.rank != 0) continue;
+    const size_t i = chunk * kChunkGroups + threadIdx.x;
+    if (i >= n4) continue;
+    const int y = (int)(i / (size_t)w4), x = (int)(i % (size_t)w4) * 4;
+    unsigned cover = 0;
+#pragma unroll
+    for (int l = 0; l < kMaxRanks; ++l)
+      if (l < P.size && y >= s_rect[l][1] && y < s_rect[l][3] && x >= s_rect[l][0] && x < s_rect[l][2])
+        cover |= 1u << l;
+    if (cover == 0)
+    {
+      if (P.rank == 0)
+      {
+        out_rgba[i] = make_uint4(0u, 0u, 0u, 0u);
+        // N >= 2 all-clear layers fold to min(min(1.001,1.001), ...) = 1.001; one layer is copied
+        out_depth[i] = make_float4(1.001f, 1.001f, 1.001f, 1.001f);
+      }
+      continue;
+    }
+    if (!mine) continue;
+    // issue all covering layer loads first (independent 16-byte NVLink reads)
     uint4 c[kMaxRanks];
     float4 d[kMaxRanks];
 #pragma unroll
     for (int l = 0; l < kMaxRanks; ++l)
       if (l < P.size)
       {
-        c[l] = layer_rgba[l][i];
-        d[l] = layer_depth[l][i];
+        if (cover & (1u << l))
+        {
+          c[l] = layer_rgba[l][i];
+          d[l] = layer_depth[l][i];
+        }
+        else
+        {
+          c[l] = make_uint4(0u, 0u, 0u, 0u);
+          d[l] = make_float4(1.001f, 1.001f, 1.001f, 1.001f);
+        }
       }
     uint4 f = c[0];
     float4 fd = d[0];
@@ -137,8 +185,11 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
     for (int l = 1; l < kMaxRanks; ++l)
       if (l < P.size)
       {
-        f.x = blend_u8x4(f.x, c[l].x); f.y = blend_u8x4(f.y, c[l].y);
-        f.z = blend_u8x4(f.z, c[l].z); f.w = blend_u8x4(f.w, c[l].w);
+        if (cover & (1u << l))
+        {
+          f.x = blend_u8x4(f.x, c[l].x); f.y = blend_u8x4(f.y, c[l].y);
+          f.z = blend_u8x4(f.z, c[l].z); f.w = blend_u8x4(f.w, c[l].w);
+        }
         fd.x = blend_depth(fd.x, d[l].x); fd.y = blend_depth(fd.y, d[l].y);
         fd.z = blend_depth(fd.z, d[l].z); fd.w = blend_depth(fd.w, d[l].w);
       }
@@ -532,6 +583,9 @@ extern "C" vr_status vr_comm_composite_images(vr_ctx* ctx, const int* vis_order)
   p.size = c.size;
   p.epoch = c.epoch;
   p.n_pixels = (size_t)ctx->W * ctx->H;
+  p.W = ctx->W;
+  for (int k = 0; k < 4; ++k) p.rect[k] = ctx->img_rect[k];
+  if (ctx->W % 4 != 0) { p.rect[0] = p.rect[1] = 0; p.rect[2] = p.rect[3] = 0x7fffffff; }
   p.off_img_rgba = L.off_img_rgba[b];
   p.off_img_depth = L.off_img_depth[b];
   p.off_res_rgba = L.off_res_rgba[b];

@@ -6,7 +6,10 @@
 // (:239-258): K1 ray generation over the block's screen subset, K2 canvas-depth clamp, K3
 // bounds intersection, K4/K5/K6 march + trilinear/nearest sample + transfer function +
 // front-to-back accumulation with early termination, then either K7 (blend over the canvas,
-// projected entry depth) or the alpha >= 0.001 partial emission of :260-283.
+// projected entry depth), the alpha >= 0.001 partial emission of :260-283, or -- for a frame that
+// starts from a cleared canvas, the normal case of RenderOneDomainPerRank (:482-536) -- K7 fused
+// with Canvas::Clear, Image::Init (Image.hpp:80-113) and ImageToCanvas (Renderer.cpp:265-283),
+// so that one launch produces the rank's final uint8 image (and canvas).
 //
 // Numerics: this translation unit is compiled with --fmad=false so every +,* below is a
 // separately rounded IEEE f32 operation, exactly like the x86 build of VTK-m the reference's
@@ -76,6 +79,55 @@ __device__ __forceinline__ void locate_axis_rect(const float* __restrict__ ax, i
     else          { maxVal = minVal; minVal = next; }
   }
   inv_sp = 1.f / (maxVal - minVal);
+}
+
+__device__ __forceinline__ unsigned char quant_u8(float c)
+{
+  // static_cast<unsigned char>(c * 255.f) on x86: cvttss2si then low byte
+  return (unsigned char)(__float2int_rz(c * 255.f) & 0xff);
+}
+
+// 512 pixels per chunk: 4 x (32 lanes x 4 consecutive pixels).  A group of 4 pixels is either
+// entirely inside the traced rectangle (tx0/tx1 are multiples of 4 when vec_ok) or outside it.
+__device__ __forceinline__ void clear_chunk(const TraceParams& P, unsigned chunk, int lane)
+{
+  const long long n = (long long)P.W * P.H;
+#pragma unroll
+  for (int it = 0; it < 4; ++it)
+  {
+    const long long base = (long long)chunk * 512 + it * 128 + lane * 4;
+    if (base >= n) continue;
+    if (P.vec_ok)
+    {
+      const int j = (int)(base / P.W), i = (int)(base % P.W);
+      if (j >= P.sy && j < P.sy + P.sh && i >= P.tx0 && i < P.tx1) continue;
+      *reinterpret_cast<uint4*>(P.img_rgba + base) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<float4*>(P.img_depth + base) = make_float4(1.001f, 1.001f, 1.001f, 1.001f);
+      if (P.write_canvas)
+      {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) P.canvas_rgba[base + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(P.canvas_depth + base) = make_float4(1.001f, 1.001f, 1.001f, 1.001f);
+      }
+    }
+    else
+    {
+      for (int k = 0; k < 4; ++k)
+      {
+        const long long px = base + k;
+        if (px >= n) break;
+        const int j = (int)(px / P.W), i = (int)(px % P.W);
+        if (j >= P.sy && j < P.sy + P.sh && i >= P.tx0 && i < P.tx1) continue;
+        P.img_rgba[px] = make_uchar4(0, 0, 0, 0);
+        P.img_depth[px] = 1.001f;
+        if (P.write_canvas)
+        {
+          P.canvas_rgba[px] = make_float4(0.f, 0.f, 0.f, 0.f);
+          P.canvas_depth[px] = 1.001f;
+        }
+      }
+    }
+  }
 }
 
 // the state of "the cell the ray is in": corner scalars in the pre-differenced form the
@@ -154,6 +206,7 @@ trace_kernel(const __grid_constant__ TraceParams P)
   const int lane = threadIdx.x & 31;
   const int lx = lane & (kTileW - 1), ly = lane >> 3;
   const unsigned n_tiles = (unsigned)(P.tiles_x * P.tiles_y);
+  const unsigned n_work = n_tiles + (MODE == 2 ? (unsigned)P.n_clear_chunks : 0u);
   const float cms_f = (float)(P.lut_size - 1);
   const float minx = B.min_point[0], miny = B.min_point[1], minz = B.min_point[2];
   const float maxx = B.max_point[0], maxy = B.max_point[1], maxz = B.max_point[2];
@@ -168,11 +221,21 @@ trace_kernel(const __grid_constant__ TraceParams P)
     unsigned tile = 0;
     if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
     tile = __shfl_sync(0xffffffffu, tile, 0);
-    if (tile >= n_tiles) break;
+    if (tile >= n_work) break;
+    if (MODE == 2 && tile >= n_tiles)
+    {
+      // ---------------- Canvas::Clear for everything outside the traced rectangle, in the
+      // frame's final formats (Image::Init of a cleared canvas: colour 0, depth 1.001)
+      clear_chunk(P, tile - n_tiles, lane);
+      continue;
+    }
     const int ti = (int)(tile % (unsigned)P.tiles_x), tj = (int)(tile / (unsigned)P.tiles_x);
-    const int i = P.sx + ti * kTileW + lx;
+    const int i = P.tx0 + ti * kTileW + lx;
     const int j = P.sy + tj * kTileH + ly;
-    const bool in_subset = (i < P.sx + P.sw) && (j < P.sy + P.sh);
+    // tx0 <= sx: in MODE 2 the traced rectangle is widened to 4-pixel boundaries so that its
+    // complement can be cleared (and, across GPUs, skipped) in 16-byte groups
+    const bool in_rect = (i < P.tx1) && (j < P.sy + P.sh);
+    const bool in_subset = in_rect && (i >= P.sx) && (i < P.sx + P.sw);
     const long long pixel = (long long)j * P.W + i;
     float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
     float max_distance = __int_as_float(0x7f800000);
@@ -328,7 +391,44 @@ trace_kernel(const __grid_constant__ TraceParams P)
         P.canvas_depth[pixel] = depth;
         P.canvas_rgba[pixel] = out;
       }
+      if (MODE == 2)
+      {
+        // ---------------- K7 over a cleared canvas (in = 0), fused with Image::Init
+        // (Image.hpp:80-113: truncating uint8, depth < 0 -> |d|) and, for a single rank,
+        // Renderer::ImageToCanvas (Renderer.cpp:265-283: k * (1/255))
+        const float ix_ = ox + distance0 * dx, iy_ = oy + distance0 * dy, iz_ = oz + distance0 * dz;
+        const float* m = P.pv;
+        const float n2 = m[8] * ix_ + m[9] * iy_ + m[10] * iz_ + m[11] * 1.f;
+        const float n3 = m[12] * ix_ + m[13] * iy_ + m[14] * iz_ + m[15] * 1.f;
+        float depth = 0.5f * (n2 / n3) + 0.5f;
+        const float a = 1.f - c3;
+        float4 out; // same expressions as the unfused path so every bit agrees (0*a may be NaN for a = inf only)
+        out.x = fminf(1.f, fmaxf(c0 + 0.f * a, 0.f));
+        out.y = fminf(1.f, fmaxf(c1 + 0.f * a, 0.f));
+        out.z = fminf(1.f, fmaxf(c2 + 0.f * a, 0.f));
+        out.w = fminf(1.f, fmaxf(0.f * a + c3, 0.f));
+        const uchar4 q = make_uchar4(quant_u8(out.x), quant_u8(out.y), quant_u8(out.z), quant_u8(out.w));
+        depth = depth < 0.f ? fabsf(depth) : depth;
+        P.img_rgba[pixel] = q;
+        P.img_depth[pixel] = depth;
+        if (P.write_canvas)
+        {
+          const float k = 1.f / 255.f;
+          P.canvas_rgba[pixel] = make_float4((float)q.x * k, (float)q.y * k, (float)q.z * k, (float)q.w * k);
+          P.canvas_depth[pixel] = depth;
+        }
+      }
     } // in_subset
+    else if (MODE == 2 && in_rect)
+    {
+      P.img_rgba[pixel] = make_uchar4(0, 0, 0, 0);
+      P.img_depth[pixel] = 1.001f;
+      if (P.write_canvas)
+      {
+        P.canvas_rgba[pixel] = make_float4(0.f, 0.f, 0.f, 0.f);
+        P.canvas_depth[pixel] = 1.001f;
+      }
+    }
 
     if (MODE == 1)
     {
@@ -368,8 +468,9 @@ trace_kernel(const __grid_constant__ TraceParams P)
 template <int KIND, typename FT, int ASSOC, typename IDX>
 cudaError_t launch_mode(const TraceParams& p, int mode, int grid, cudaStream_t s)
 {
-  if (mode == 0) trace_kernel<KIND, FT, ASSOC, 0, IDX><<<grid, kThreads, 0, s>>>(p);
-  else           trace_kernel<KIND, FT, ASSOC, 1, IDX><<<grid, kThreads, 0, s>>>(p);
+  if (mode == 0)      trace_kernel<KIND, FT, ASSOC, 0, IDX><<<grid, kThreads, 0, s>>>(p);
+  else if (mode == 1) trace_kernel<KIND, FT, ASSOC, 1, IDX><<<grid, kThreads, 0, s>>>(p);
+  else                trace_kernel<KIND, FT, ASSOC, 2, IDX><<<grid, kThreads, 0, s>>>(p);
   return cudaGetLastError();
 }
 template <int KIND, typename FT, int ASSOC>
@@ -398,7 +499,7 @@ cudaError_t launch_dtype(const TraceParams& p, int mode, int grid, cudaStream_t 
 
 cudaError_t launch_trace(const TraceParams& p, int mode_partials, int sm_count, cudaStream_t s)
 {
-  const long long n_tiles = (long long)p.tiles_x * p.tiles_y;
+  const long long n_tiles = (long long)p.tiles_x * p.tiles_y + (mode_partials == 2 ? p.n_clear_chunks : 0);
   if (n_tiles <= 0) return cudaSuccess;
   // persistent grid: SMs x resident CTAs (4 warps each), capped by the work available
   const int ctas_per_sm = p.ctas_per_sm > 0 ? p.ctas_per_sm : VR_MIN_BLOCKS;

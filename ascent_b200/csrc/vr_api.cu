@@ -417,6 +417,8 @@ static vr_status fill_trace_params(vr_ctx* ctx, int block_id, const vr_camera* c
   hm::find_subset(*cam, W, H, b.bounds, sub);
   p.W = W; p.H = H;
   p.sx = sub[0]; p.sy = sub[1]; p.sw = sub[2]; p.sh = sub[3];
+  p.tx0 = p.sx;
+  p.tx1 = p.sx + p.sw;
   p.tiles_x = (p.sw + 7) / 8;
   p.tiles_y = (p.sh + 3) / 4;
   const hm::RayGen g = hm::raygen(*cam, W, H, false);
@@ -484,6 +486,37 @@ extern "C" vr_status vr_render_image(vr_ctx* ctx, int block_id, const vr_camera*
   st = vr_trace_to_canvas(ctx, block_id, cam, sample_dist, range_min, range_max, 1);
   if (st != VR_OK) return st;
   return vr_canvas_download(ctx, rgba_inout, depth_inout);
+}
+
+extern "C" vr_status vr_trace_to_image(vr_ctx* ctx, int block_id, const vr_camera* cam, int width,
+                                       int height, float sample_dist, float range_min,
+                                       float range_max, int flags)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  vr_status st = ensure_frame(ctx, width, height);
+  if (st != VR_OK) return st;
+  TraceParams p;
+  st = fill_trace_params(ctx, block_id, cam, sample_dist, range_min, range_max, 0, width, height, p);
+  if (st != VR_OK) return st;
+  p.vec_ok = (width % 4 == 0) ? 1 : 0;
+  if (p.vec_ok && p.sw > 0)
+  {
+    p.tx0 = p.sx & ~3;
+    p.tx1 = std::min(width, (p.sx + p.sw + 3) & ~3);
+    p.tiles_x = (p.tx1 - p.tx0 + 7) / 8;
+  }
+  p.img_rgba = ctx->img_rgba;
+  p.img_depth = ctx->img_depth;
+  p.write_canvas = (flags & VR_FRAME_WRITE_CANVAS) ? 1 : 0;
+  p.n_clear_chunks = (flags & VR_FRAME_NO_CLEAR) ? 0 : (int)(((size_t)width * height + 511) / 512);
+  CK(launch_trace(p, 2, ctx->sm_count, ctx->stream));
+  ctx->launches++;
+  // what the multi-GPU fold needs to know: outside this rectangle my image is empty
+  ctx->img_rect[0] = p.tx0; ctx->img_rect[1] = p.sy;
+  ctx->img_rect[2] = p.tx1; ctx->img_rect[3] = p.sy + p.sh;
+  if (p.sw <= 0 || p.sh <= 0) ctx->img_rect[0] = ctx->img_rect[1] = ctx->img_rect[2] = ctx->img_rect[3] = 0;
+  return VR_OK;
 }
 
 // ----------------------------------------------------------------- partial list
@@ -624,6 +657,8 @@ extern "C" vr_status vr_image_from_canvas(vr_ctx* ctx)
   CK(launch_quantize(ctx->canvas_rgba, ctx->canvas_depth, (size_t)ctx->W * ctx->H, ctx->img_rgba,
                      ctx->img_depth, ctx->stream));
   ctx->launches++;
+  ctx->img_rect[0] = ctx->img_rect[1] = 0; // a canvas of unknown history: the whole image counts
+  ctx->img_rect[2] = ctx->img_rect[3] = 0x7fffffff;
   return VR_OK;
 }
 

@@ -33,6 +33,11 @@ struct TraceParams
   float origin[3], nlook[3], delta_x[3], delta_y[3];
   int W, H, sx, sy, sw, sh;
   int tiles_x, tiles_y;
+  int tx0, tx1;        // traced x-range [tx0, tx1) >= [sx, sx+sw): widened to 4-pixel groups in mode 2
+  // fused frame (mode 2): uint8 image out, optional float canvas, clear of the complement
+  uchar4* img_rgba;
+  float* img_depth;
+  int write_canvas, vec_ok, n_clear_chunks;
   // K2
   int use_depth;
   float inv_pv[16];
@@ -107,6 +112,7 @@ struct vr_ctx
   uchar4* res_rgba = nullptr;  // composited result (rank 0)
   float* res_depth = nullptr;
   bool img_in_arena = false;
+  int img_rect[4] = { 0, 0, 0x7fffffff, 0x7fffffff }; // where the quantised image may be non-empty
 
   // partial list
   vr_partial* partials = nullptr;
@@ -194,6 +200,8 @@ struct FoldP2PParams
   int rank, size;
   unsigned int epoch;
   size_t n_pixels;
+  int W;
+  int rect[4]; // {x0,y0,x1,y1}: my image is empty (colour 0, depth 1.001) outside of it
   size_t off_img_rgba, off_img_depth, off_res_rgba, off_res_depth, off_flags;
   int order[16]; // rank index per fold step (front to back)
 };

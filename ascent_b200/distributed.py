@@ -157,8 +157,8 @@ def run_bench(args, wl, bench):
 
     def render():
         if path_a:
-            ctx.canvas_clear(W, H)
-            ctx.trace_to_canvas(mine[0], cam, sp["sample_dist"], rmin, rmax, False)
+            # Canvas::Clear + RenderCells + Image::Init in one launch, straight into the exchange arena
+            ctx.trace_to_image(mine[0], cam, W, H, sp["sample_dist"], rmin, rmax, no_clear=True)
         else:
             ctx.partials_begin(W, H)
             for i in mine:
@@ -166,7 +166,6 @@ def run_bench(args, wl, bench):
 
     def composite():
         if path_a:
-            ctx.image_from_canvas()
             ctx.comm_composite_images(vis_rank)
             if rank == 0:
                 ctx.image_result_to_canvas()

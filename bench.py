@@ -208,22 +208,21 @@ def run_single(args, wl):
     multi = len(blocks) > 1
 
     def frame(ev=None):
-        ctx.canvas_clear(W, H)
         if not multi:
+            # RenderOneDomainPerRank on a cleared canvas: Canvas::Clear + RenderCells + Image::Init +
+            # ImageToCanvas in one launch (vr_trace_to_image)
             if ev:
                 ev[0].record(stream)
-            ctx.trace_to_canvas(0, cam, sp["sample_dist"], rmin, rmax, False)
+            ctx.trace_to_image(0, cam, W, H, sp["sample_dist"], rmin, rmax, write_canvas=True)
             if ev:
                 ev[1].record(stream)
-            ctx.image_from_canvas()
-            rp, dp = ctx.image_ptrs()
-            ctx.image_to_canvas_dev(rp, dp)
         else:
+            ctx.canvas_clear(W, H)
             ctx.partials_begin(W, H)
             if ev:
                 ev[0].record(stream)
             for i in range(len(blocks)):
-                ctx.trace_to_partials(i, cam, sp["sample_dist"], rmin, rmax, True)
+                ctx.trace_to_partials(i, cam, sp["sample_dist"], rmin, rmax, False)
             if ev:
                 ev[1].record(stream)
             ctx.partials_composite()
@@ -282,7 +281,9 @@ def run_single(args, wl):
     # ---- roofline of the dominant kernel (trace), algorithmic bytes per launch
     pk, pk_src = peaks()
     n_launch = len(blocks)
-    alg_bytes = nvox * 4 * len(blocks) + W * H * 20  # N_vox*4 + W*H*20 per frame
+    # N_vox*4 + W*H*20 per frame (the fused kernel really writes W*H*28: RGBA8 + depth
+    # image and the float canvas; the extra 8 B/pixel are not claimed)
+    alg_bytes = nvox * 4 * len(blocks) + W * H * 20
     achieved = alg_bytes / (trace_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")

@@ -126,6 +126,20 @@ VR_API vr_status vr_render_image(vr_ctx* ctx, int block_id, const vr_camera* cam
                                  int height, float sample_dist, float range_min, float range_max,
                                  float* rgba_inout, float* depth_inout);
 
+/* The whole per-rank body of RenderOneDomainPerRank (VolumeRenderer.cpp:482-536) for a frame
+ * that starts from a CLEARED canvas -- Canvas::Clear, RenderCells (K1-K7), Image::Init
+ * (Image.hpp:80-113) and, with VR_FRAME_WRITE_CANVAS, Renderer::ImageToCanvas
+ * (Renderer.cpp:265-283) -- fused into ONE kernel launch.  Leaves the rank's quantised RGBA8 +
+ * depth image in the context (vr_image_download / vr_comm_composite_images) and, if asked, the
+ * k/255 float canvas.  Results are bit-identical to vr_canvas_clear + vr_trace_to_canvas(.., 0) +
+ * vr_image_from_canvas [+ vr_image_to_canvas_dev].
+ * VR_FRAME_NO_CLEAR: do not write the pixels outside the block's screen rectangle (they are left
+ * undefined); only for images handed to vr_comm_composite_images, which never reads them.       */
+enum { VR_FRAME_WRITE_CANVAS = 1, VR_FRAME_NO_CLEAR = 2 };
+VR_API vr_status vr_trace_to_image(vr_ctx* ctx, int block_id, const vr_camera* cam, int width,
+                                   int height, float sample_dist, float range_min, float range_max,
+                                   int flags);
+
 /* ------------------------------------------------------------------ (2) path B render
  * StructuredWrapper::render: same trace on a zeroed ray buffer, then keep rays with
  * alpha >= 0.001 as partials {pixel, exit distance, rgb, alpha}.  Partials are APPENDED to the

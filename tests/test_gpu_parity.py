@@ -383,6 +383,77 @@ def test_path_a_single_rank_roundtrip(ctx):
     assert np.array_equal(can, o_can)
 
 
+@pytest.mark.parametrize("res", [(256, 256), (1024, 1024), (642, 360), (1920, 1080), (37, 19)])
+@pytest.mark.parametrize("az", [0.0, 33.0])
+def test_fused_frame_equals_unfused_path_a(ctx, res, az):
+    """vr_trace_to_image (clear + K1-K7 + Image::Init + ImageToCanvas in one launch) against the
+    four separate calls and against the oracle: uint8 image, depth and canvas bit-identical."""
+    dom = datasets.braid_uniform(32, dtype=np.float32)
+    b = datasets.domain_bounds(dom)
+    W, H = res
+    cam = O.camera_reset_to_bounds(b)
+    O.camera_azimuth(cam, az)
+    O.camera_elevation(cam, az / 2)
+    if az:
+        cam.zoom = 1.7  # part of the volume leaves the screen
+    lut = color_table.parse_color_table(scenes.RAMP_TF).corrected_opacity(100).lut()
+    sd = O.sample_distance(b, 100)
+    rmin, rmax = scenes.field_range([dom])
+    ctx.block_from_domain(0, dom)
+    ctx.set_tf(lut)
+    # unfused
+    ctx.canvas_clear(W, H)
+    ctx.trace_to_canvas(0, cam, sd, rmin, rmax, False)
+    ctx.image_from_canvas()
+    u8_a, d_a = ctx.image_download(W, H)
+    rp, dp = ctx.image_ptrs()
+    ctx.image_to_canvas_dev(rp, dp)
+    can_a, cd_a = ctx.canvas_download(W, H)
+    # poison the buffers, then fused
+    ctx.canvas_upload(W, H, np.full((H * W, 4), 0.37, np.float32), np.full(H * W, 0.5, np.float32))
+    ctx.image_from_canvas()
+    ctx.trace_to_image(0, cam, W, H, sd, rmin, rmax, write_canvas=True)
+    u8_b, d_b = ctx.image_download(W, H)
+    can_b, cd_b = ctx.canvas_download(W, H)
+    assert np.array_equal(u8_a, u8_b)
+    assert np.array_equal(d_a, d_b, equal_nan=True)
+    assert np.array_equal(can_a, can_b)
+    assert np.array_equal(cd_a, cd_b, equal_nan=True)
+    # and the oracle's path A for one rank
+    sc = dict(doms=[dom], W=W, H=H, cam=cam, lut=lut, sample_dist=sd, rmin=rmin, rmax=rmax,
+              dom_bounds=[b])
+    o_u8, o_d, o_can = scenes.oracle_path_a(sc)
+    assert np.array_equal(u8_b, o_u8)
+    assert np.array_equal(can_b, o_can)
+
+
+def test_fused_frame_no_clear_leaves_outside_untouched(ctx):
+    dom = datasets.braid_uniform(16, dtype=np.float32)
+    b = datasets.domain_bounds(dom)
+    W, H = 400, 300
+    cam = O.camera_reset_to_bounds(b)
+    lut = color_table.parse_color_table(scenes.RAMP_TF).corrected_opacity(100).lut()
+    sd = O.sample_distance(b, 100)
+    rmin, rmax = scenes.field_range([dom])
+    ctx.block_from_domain(0, dom)
+    ctx.set_tf(lut)
+    ctx.canvas_upload(W, H, np.full((H * W, 4), 0.5, np.float32), np.full(H * W, 0.25, np.float32))
+    ctx.image_from_canvas()                      # image = (127,127,127,127), depth .25 everywhere
+    ctx.trace_to_image(0, cam, W, H, sd, rmin, rmax, no_clear=True)
+    u8, d = ctx.image_download(W, H)
+    ctx.trace_to_image(0, cam, W, H, sd, rmin, rmax)
+    u8_full, d_full = ctx.image_download(W, H)
+    sx, sy, sw, sh = _lib.find_subset(cam, W, H, b)
+    x0, x1 = sx & ~3, min(W, (sx + sw + 3) & ~3)
+    inside = np.zeros((H, W), bool)
+    inside[sy:sy + sh, x0:x1] = True
+    inside = inside.reshape(-1)
+    assert np.array_equal(u8[inside], u8_full[inside])
+    assert np.array_equal(d[inside], d_full[inside], equal_nan=True)
+    assert (u8[~inside] == 127).all() and (d[~inside] == 0.25).all()
+    assert (u8_full[~inside] == 0).all() and (d_full[~inside] == np.float32(1.001)).all()
+
+
 def test_two_rank_path_a_on_one_gpu(ctx, golden_dir):
     """the reference's 2-rank MPI volume scene: each rank's image rendered and quantised on the
     GPU, folded in visibility order on the GPU; uint8 result bit-exact vs the oracle, and inside
