@@ -26,10 +26,12 @@ SYMBOLS = [
     "vr_canvas_ptrs", "vr_trace_to_canvas", "vr_render_image", "vr_trace_to_image", "vr_partials_begin",
     "vr_trace_to_partials", "vr_partials_count", "vr_partials_download", "vr_render_partials",
     "vr_free", "vr_image_from_canvas", "vr_image_download", "vr_fold_images_dev",
-    "vr_composite_images", "vr_zbuffer_composite_dev", "vr_image_to_canvas_dev",
-    "vr_partials_composite", "vr_partials_to_canvas", "vr_composite_partials", "vr_comm_init",
-    "vr_comm_connect", "vr_comm_composite_images", "vr_image_result_download",
-    "vr_image_result_to_canvas", "vr_comm_composite_partials", "vr_image_ptrs",
+    "vr_composite_images", "vr_composite_zbuffer", "vr_zbuffer_composite_dev", "vr_image_to_canvas_dev",
+    "vr_partials_composite", "vr_partials_composite_to_canvas", "vr_partials_to_canvas", "vr_composite_partials", "vr_comm_init",
+    "vr_comm_connect", "vr_comm_composite_images", "vr_comm_composite_images_to_canvas",
+    "vr_image_result_download",
+    "vr_image_result_to_canvas", "vr_comm_composite_partials", "vr_comm_composite_partials_to_canvas",
+    "vr_image_ptrs",
     "vr_sample_distance", "vr_visibility_order", "vr_find_subset", "vr_synth_braid_dev",
 ]
 
@@ -95,17 +97,21 @@ def load():
         "vr_image_download": (C.c_int, [vp, vp, vp]),
         "vr_fold_images_dev": (C.c_int, [vp, vp, vp, sz, ip, C.c_int, sz, vp, vp]),
         "vr_composite_images": (C.c_int, [vp, vp, vp, ip, C.c_int, C.c_int, C.c_int, vp, vp]),
+        "vr_composite_zbuffer": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
         "vr_zbuffer_composite_dev": (C.c_int, [vp, vp, vp, vp, vp, sz]),
         "vr_image_to_canvas_dev": (C.c_int, [vp, vp, vp]),
         "vr_partials_composite": (C.c_int, [vp]),
+        "vr_partials_composite_to_canvas": (C.c_int, [vp, cam, C.c_int]),
         "vr_partials_to_canvas": (C.c_int, [vp, cam]),
         "vr_composite_partials": (C.c_int, [vp, vp, sz, C.c_int, C.c_int, vp, C.POINTER(sz)]),
         "vr_comm_init": (C.c_int, [vp, C.c_int, C.c_int, sz, sz, vp]),
         "vr_comm_connect": (C.c_int, [vp, vp]),
         "vr_comm_composite_images": (C.c_int, [vp, ip]),
+        "vr_comm_composite_images_to_canvas": (C.c_int, [vp, ip]),
         "vr_image_result_download": (C.c_int, [vp, vp, vp]),
         "vr_image_result_to_canvas": (C.c_int, [vp]),
         "vr_comm_composite_partials": (C.c_int, [vp]),
+        "vr_comm_composite_partials_to_canvas": (C.c_int, [vp, cam]),
         "vr_image_ptrs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "vr_sample_distance": (C.c_float, [dp, C.c_float]),
         "vr_visibility_order": (None, [dp, C.c_int, cam, ip]),
@@ -347,6 +353,16 @@ class Context:
                                               out.ctypes.data, od.ctypes.data))
         return out, od
 
+    def composite_zbuffer(self, rgba, depth, W, H):
+        rgba = np.ascontiguousarray(rgba, np.float32)
+        depth = np.ascontiguousarray(depth, np.float32)
+        out = np.empty((H * W, 4), np.uint8)
+        od = np.empty(H * W, np.float32)
+        self._ck(self.lib.vr_composite_zbuffer(self.h, rgba.ctypes.data, depth.ctypes.data,
+                                               depth.reshape(-1, H * W).shape[0], W, H,
+                                               out.ctypes.data, od.ctypes.data))
+        return out, od
+
     def zbuffer_composite_dev(self, front_rgba, front_depth, rgba, depth, n_pixels):
         self._ck(self.lib.vr_zbuffer_composite_dev(self.h, front_rgba, front_depth, rgba, depth, n_pixels))
 
@@ -356,6 +372,9 @@ class Context:
     # -- partial compositing
     def partials_composite(self):
         self._ck(self.lib.vr_partials_composite(self.h))
+
+    def partials_composite_to_canvas(self, cam, canvas_is_clear=True):
+        self._ck(self.lib.vr_partials_composite_to_canvas(self.h, C.byref(as_camera(cam)), int(canvas_is_clear)))
 
     def partials_to_canvas(self, cam):
         self._ck(self.lib.vr_partials_to_canvas(self.h, C.byref(as_camera(cam))))
@@ -383,6 +402,10 @@ class Context:
         vo = np.ascontiguousarray(vis_order, np.int32)
         self._ck(self.lib.vr_comm_composite_images(self.h, vo.ctypes.data_as(C.POINTER(C.c_int))))
 
+    def comm_composite_images_to_canvas(self, vis_order):
+        vo = np.ascontiguousarray(vis_order, np.int32)
+        self._ck(self.lib.vr_comm_composite_images_to_canvas(self.h, vo.ctypes.data_as(C.POINTER(C.c_int))))
+
     def image_result_download(self, W, H):
         rgba = np.empty((H * W, 4), np.uint8)
         depth = np.empty(H * W, np.float32)
@@ -394,6 +417,9 @@ class Context:
 
     def comm_composite_partials(self):
         self._ck(self.lib.vr_comm_composite_partials(self.h))
+
+    def comm_composite_partials_to_canvas(self, cam):
+        self._ck(self.lib.vr_comm_composite_partials_to_canvas(self.h, C.byref(as_camera(cam))))
 
     # -- bench input
     def synth_braid_dev(self, dev_ptr, dtype, n, start, glob):

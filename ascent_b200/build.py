@@ -59,7 +59,34 @@ def build(force=False, verbose=False):
             f.write("\n".join(logs))
     if verbose:
         print("\n".join(logs))
+    build_host(force)
     return OUT
+
+
+def build_host(force=False):
+    """libvtkh_b200.so: the C++ host mirror of vtkh::VolumeRenderer & co. over the C ABI, and the
+    C++ test driver that reads like the reference's t_vtk-h_volume_renderer.cpp."""
+    hdir = os.path.join(CSRC, "host")
+    src = os.path.join(hdir, "vtkh_b200.cpp")
+    deps = [src, os.path.join(hdir, "vtkh_b200.hpp"), os.path.join(CSRC, "..", "..", "include", "vr_b200.h")]
+    common = [HOSTCXX, "-O2", "-std=c++17", "-fPIC", "-Wall", "-ffp-contract=off"]
+    if force or _newer(HOST_OUT, deps + [OUT]):
+        cmd = common + ["-shared", "-o", HOST_OUT, src, "-L" + HERE, "-l:" + os.path.basename(OUT),
+                        "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stderr)
+            raise RuntimeError("host library build failed")
+    tsrc = os.path.join(hdir, "t_vtkh_b200_volume_renderer.cpp")
+    texe = os.path.join(HERE, "t_vtkh_b200_volume_renderer")
+    if os.path.exists(tsrc) and (force or _newer(texe, deps + [tsrc, HOST_OUT])):
+        cmd = common + ["-o", texe, tsrc, "-L" + HERE, "-l:libvtkh_b200.so", "-l:" + os.path.basename(OUT),
+                        "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stderr)
+            raise RuntimeError("host test driver build failed")
+    return HOST_OUT
 
 
 if __name__ == "__main__":

@@ -95,6 +95,10 @@ __device__ __forceinline__ float blend_depth(float f, float b)
 // are written by rank 0 itself.
 constexpr int kChunkGroups = 256; // 4-pixel groups per ownership chunk
 
+// TO_CANVAS: rank 0 also produces its float canvas (Renderer::ImageToCanvas, Renderer.cpp:265-283):
+// the groups no rank covers are written here, while the peers' pixels are still in flight; the
+// covered ones are converted by covered_to_canvas_kernel once they have landed.
+template <bool TO_CANVAS>
 __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ FoldP2PParams P)
 {
   Flags* my_flags = reinterpret_cast<Flags*>(P.peers[P.rank] + P.off_flags);
@@ -157,6 +161,12 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
         out_rgba[i] = make_uint4(0u, 0u, 0u, 0u);
         // N >= 2 all-clear layers fold to min(min(1.001,1.001), ...) = 1.001; one layer is copied
         out_depth[i] = make_float4(1.001f, 1.001f, 1.001f, 1.001f);
+        if (TO_CANVAS)
+        {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) P.canvas_rgba[4 * i + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          reinterpret_cast<float4*>(P.canvas_depth)[i] = make_float4(1.001f, 1.001f, 1.001f, 1.001f);
+        }
       }
       continue;
     }
@@ -213,6 +223,37 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
   }
 }
 
+// rank 0, after every rank's range has landed: ImageToCanvas for the groups some rank covers
+__global__ void __launch_bounds__(256) covered_to_canvas_kernel(const __grid_constant__ FoldP2PParams P)
+{
+  const Flags* my_flags = reinterpret_cast<const Flags*>(P.peers[0] + P.off_flags);
+  const int par = P.epoch & 1;
+  __shared__ int s_rect[kMaxRanks][4];
+  if (threadIdx.x < P.size * 4) s_rect[threadIdx.x >> 2][threadIdx.x & 3] = my_flags->img_rect[par][threadIdx.x >> 2][threadIdx.x & 3];
+  __syncthreads();
+  const uint4* res_rgba = reinterpret_cast<const uint4*>(P.peers[0] + P.off_res_rgba);
+  const float4* res_depth = reinterpret_cast<const float4*>(P.peers[0] + P.off_res_depth);
+  const size_t n4 = (P.n_pixels + 3) / 4;
+  const int w4 = P.W >= 4 ? P.W / 4 : 1;
+  const float k = 1.f / 255.f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
+  {
+    const int y = (int)(i / (size_t)w4), x = (int)(i % (size_t)w4) * 4;
+    bool cover = false;
+    for (int l = 0; l < P.size; ++l)
+      cover = cover || (y >= s_rect[l][1] && y < s_rect[l][3] && x >= s_rect[l][0] && x < s_rect[l][2]);
+    if (!cover) continue;
+    const uint4 c = res_rgba[i];
+    const unsigned w[4] = { c.x, c.y, c.z, c.w };
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      P.canvas_rgba[4 * i + q] = make_float4((float)(w[q] & 0xffu) * k, (float)((w[q] >> 8) & 0xffu) * k,
+                                             (float)((w[q] >> 16) & 0xffu) * k, (float)(w[q] >> 24) * k);
+    reinterpret_cast<float4*>(P.canvas_depth)[i] = res_depth[i];
+  }
+}
+
 __global__ void wait_done_kernel(const unsigned int* done, int size, unsigned int epoch)
 {
   if (threadIdx.x < size)
@@ -229,6 +270,9 @@ struct MergeP2PParams
   size_t n_pixels;
   size_t off_flags, off_poff, off_psorted, off_pout;
   size_t sorted_cap, out_cap;
+  // fused partials_to_canvas (frame starts from a cleared canvas): owners write rank 0's canvas
+  size_t off_canvas_rgba, off_canvas_depth;
+  ToCanvasParams tp;
 };
 
 __device__ __forceinline__ void partial_blend(vr_partial& a, const vr_partial& o)
@@ -257,7 +301,7 @@ __device__ __forceinline__ vr_partial load_partial(const vr_partial* p)
 
 // One thread per owned pixel.  NR = number of ranks rounded up to a power of two: the per-source
 // cursors live in registers (all loops over sources are fully unrolled).
-template <int NR>
+template <int NR, bool TO_CANVAS>
 __global__ void __launch_bounds__(256) merge_fold_p2p_kernel(const __grid_constant__ MergeP2PParams P)
 {
   Flags* my_flags = reinterpret_cast<Flags*>(P.peers[P.rank] + P.off_flags);
@@ -321,8 +365,8 @@ __global__ void __launch_bounds__(256) merge_fold_p2p_kernel(const __grid_consta
       cur[r] = end[r] = 0;
       if (r < P.size && px < hi_px)
       {
-        cur[r] = off[r][px];
-        end[r] = off[r][px + 1];
+        cur[r] = px > 0 ? off[r][px - 1] : 0; // the arrays hold each pixel's END offset
+        end[r] = off[r][px];
         if ((size_t)end[r] > P.sorted_cap) end[r] = cur[r]; // overflowed list: dropped, flagged by its owner
       }
       total += end[r] - cur[r];
@@ -354,6 +398,20 @@ __global__ void __launch_bounds__(256) merge_fold_p2p_kernel(const __grid_consta
         if (first) { result = q; first = false; }
         else partial_blend(result, q);
       }
+    }
+    if (TO_CANVAS)
+    {
+      // partials_to_canvas over a cleared canvas (in = 0), stored into rank 0's canvas: 20 bytes per
+      // covered pixel over NVLink instead of a 24-byte partial, no list, no atomics
+      if (total > 0)
+      {
+        float4 o;
+        float d;
+        partial_to_canvas(result, P.tp, make_float4(0.f, 0.f, 0.f, 0.f), o, d);
+        reinterpret_cast<float4*>(P.peers[0] + P.off_canvas_rgba)[px] = o;
+        reinterpret_cast<float*>(P.peers[0] + P.off_canvas_depth)[px] = d;
+      }
+      continue;
     }
     // block-aggregated append to rank 0's list: one NVLink atomic per CTA iteration
     const unsigned mask = __ballot_sync(0xffffffffu, total > 0);
@@ -415,7 +473,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 struct Layout
 {
   size_t off_flags, off_img_rgba[2], off_img_depth[2], off_res_rgba[2], off_res_depth[2];
-  size_t off_poff[2], off_psorted[2], off_pout, total;
+  size_t off_poff[2], off_psorted[2], off_pout, off_canvas_rgba, off_canvas_depth, total;
 };
 Layout make_layout(size_t max_pixels, size_t max_partials, bool is_root)
 {
@@ -427,10 +485,18 @@ Layout make_layout(size_t max_pixels, size_t max_partials, bool is_root)
   for (int b = 0; b < 2; ++b) { L.off_img_depth[b] = o; o += px * 4; }
   for (int b = 0; b < 2; ++b) { L.off_res_rgba[b] = o; o += px * 4; }
   for (int b = 0; b < 2; ++b) { L.off_res_depth[b] = o; o += px * 4; }
-  for (int b = 0; b < 2; ++b) { L.off_poff[b] = o; o += max_partials ? align_up((max_pixels + 1) * 4, 256) : 0; }
+  for (int b = 0; b < 2; ++b) { L.off_poff[b] = o; o += max_partials ? align_up(partial_scan_padded(max_pixels) * 4, 256) : 0; }
   for (int b = 0; b < 2; ++b) { L.off_psorted[b] = o; o += align_up(max_partials * sizeof(vr_partial), 256); }
+  // regions only rank 0 allocates; their OFFSETS are the same on every rank (peers address them)
+  const size_t common_end = o;
   L.off_pout = o;
-  if (is_root && max_partials) o += align_up(max_pixels * sizeof(vr_partial), 256); // <= 1 per pixel
+  if (max_partials) o += align_up(max_pixels * sizeof(vr_partial), 256); // <= 1 per pixel
+  // rank 0's canvas for the fused partial path: owners store finished pixels straight into it
+  L.off_canvas_rgba = o;
+  if (max_partials) o += align_up(max_pixels * sizeof(float4), 256);
+  L.off_canvas_depth = o;
+  if (max_partials) o += align_up(max_pixels * sizeof(float), 256);
+  if (!is_root) o = common_end;
   L.total = align_up(o, 2 << 20);
   return L;
 }
@@ -439,7 +505,8 @@ Layout make_layout(size_t max_pixels, size_t max_partials, bool is_root)
 
 cudaError_t launch_fold_p2p(const FoldP2PParams& p, int sm_count, cudaStream_t s)
 {
-  fold_p2p_kernel<<<sm_count * 2, 256, 0, s>>>(p);
+  if (p.canvas_rgba) fold_p2p_kernel<true><<<sm_count * 2, 256, 0, s>>>(p);
+  else fold_p2p_kernel<false><<<sm_count * 2, 256, 0, s>>>(p);
   return cudaGetLastError();
 }
 
@@ -470,6 +537,20 @@ vr_status comm_bind_frame(vr_ctx* ctx, size_t n_pixels)
   ctx->img_depth = reinterpret_cast<float*>(c.arena + L.off_img_depth[b]);
   ctx->res_rgba = reinterpret_cast<uchar4*>(c.arena + L.off_res_rgba[b]);
   ctx->res_depth = reinterpret_cast<float*>(c.arena + L.off_res_depth[b]);
+  if (c.rank == 0 && c.max_partials)
+  {
+    // rank 0's canvas lives in the arena so that peers can store finished pixels into it
+    if (!ctx->canvas_in_arena)
+    {
+      cudaStreamSynchronize(ctx->stream);
+      cudaFree(ctx->canvas_rgba);
+      cudaFree(ctx->canvas_depth);
+      ctx->canvas_in_arena = true;
+    }
+    ctx->canvas_rgba = reinterpret_cast<float4*>(c.arena + L.off_canvas_rgba);
+    ctx->canvas_depth = reinterpret_cast<float*>(c.arena + L.off_canvas_depth);
+    if (ctx->cap_pixels < c.max_pixels) ctx->cap_pixels = c.max_pixels;
+  }
   return VR_OK;
 }
 
@@ -566,9 +647,8 @@ extern "C" vr_status vr_comm_connect(vr_ctx* ctx, const void* all_handles)
   return VR_OK;
 }
 
-extern "C" vr_status vr_comm_composite_images(vr_ctx* ctx, const int* vis_order)
+static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, bool to_canvas)
 {
-  if (!ctx) return VR_ERR_INVALID;
   Comm& c = ctx->comm;
   if (!c.on || !c.peer_dev) return cfail(ctx, VR_ERR_STATE, "vr_comm_composite_images: not connected", cudaSuccess);
   if (!vis_order || ctx->W <= 0) return cfail(ctx, VR_ERR_INVALID, "vr_comm_composite_images: no image / NULL order", cudaSuccess);
@@ -601,6 +681,11 @@ extern "C" vr_status vr_comm_composite_images(vr_ctx* ctx, const int* vis_order)
     idx[j + 1] = k;
   }
   for (int i = 0; i < c.size; ++i) p.order[i] = idx[i];
+  if (to_canvas && c.rank == 0 && ctx->W % 4 == 0)
+  {
+    p.canvas_rgba = ctx->canvas_rgba;
+    p.canvas_depth = ctx->canvas_depth;
+  }
   cudaError_t e = launch_fold_p2p(p, ctx->sm_count, ctx->stream);
   if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "fold_p2p launch", e);
   ctx->launches++;
@@ -612,6 +697,16 @@ extern "C" vr_status vr_comm_composite_images(vr_ctx* ctx, const int* vis_order)
     // result of this epoch (res_* currently points at parity b)
     ctx->res_rgba = reinterpret_cast<uchar4*>(c.arena + L.off_res_rgba[b]);
     ctx->res_depth = reinterpret_cast<float*>(c.arena + L.off_res_depth[b]);
+    if (p.canvas_rgba)
+    {
+      covered_to_canvas_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(p);
+      ctx->launches++;
+    }
+    else if (to_canvas)
+    {
+      vr_status st = vr_image_result_to_canvas(ctx);
+      if (st != VR_OK) return st;
+    }
   }
   // next frame quantises into the other parity
   const int nb = (c.epoch + 1) & 1;
@@ -640,11 +735,14 @@ extern "C" vr_status vr_image_result_to_canvas(vr_ctx* ctx)
   return vr_image_to_canvas_dev(ctx, reinterpret_cast<const uint8_t*>(ctx->res_rgba), ctx->res_depth);
 }
 
-namespace vr { vr_status ensure_partial_scratch_pub(vr_ctx* ctx, size_t n_pixels, size_t n_parts); }
-
-extern "C" vr_status vr_comm_composite_partials(vr_ctx* ctx)
+namespace vr
 {
-  if (!ctx) return VR_ERR_INVALID;
+vr_status ensure_partial_scratch_pub(vr_ctx* ctx, size_t n_pixels, size_t n_parts);
+void fill_to_canvas_params_pub(const vr_camera* cam, int W, int H, ToCanvasParams& tp);
+}
+
+static vr_status comm_composite_partials_impl(vr_ctx* ctx, const vr_camera* cam)
+{
   Comm& c = ctx->comm;
   if (!c.on || !c.peer_dev) return cfail(ctx, VR_ERR_STATE, "vr_comm_composite_partials: not connected", cudaSuccess);
   if (ctx->pW <= 0) return cfail(ctx, VR_ERR_STATE, "vr_comm_composite_partials: call vr_partials_begin first", cudaSuccess);
@@ -665,7 +763,7 @@ extern "C" vr_status vr_comm_composite_partials(vr_ctx* ctx)
   const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
   c.pepoch += 1;
   const int par = c.pepoch & 1;
-  PartialScratch sc{ ctx->px_count, ctx->px_offset, ctx->px_fill, ctx->sorted_idx, ctx->scan_blocks };
+  PartialScratch sc{ ctx->px_count, ctx->px_end, ctx->sidx, ctx->rec, ctx->scan_blocks };
   cudaError_t e = cudaSuccess;
   // (1) local: order my list by (pixel, depth, list index) into the arena + per-pixel offsets
   vr_partial* sorted = reinterpret_cast<vr_partial*>(c.arena + L.off_psorted[par]);
@@ -676,7 +774,7 @@ extern "C" vr_status vr_comm_composite_partials(vr_ctx* ctx)
   else
   {
     // a rank without any block this frame: empty list
-    cudaMemsetAsync(poff, 0, (n_pixels + 1) * sizeof(int), ctx->stream);
+    cudaMemsetAsync(poff, 0, n_pixels * sizeof(int), ctx->stream);
     const int mm[2] = { 0x7fffffff, -1 };
     e = cudaMemcpyAsync(c.minmax_dev, mm, sizeof(mm), cudaMemcpyHostToDevice, ctx->stream);
   }
@@ -697,12 +795,30 @@ extern "C" vr_status vr_comm_composite_partials(vr_ctx* ctx)
   p.off_pout = L.off_pout;
   p.sorted_cap = c.max_partials;
   p.out_cap = c.max_pixels;
+  p.off_canvas_rgba = L.off_canvas_rgba;
+  p.off_canvas_depth = L.off_canvas_depth;
   const int grid = ctx->sm_count * 4;
-  if (c.size <= 1) merge_fold_p2p_kernel<1><<<grid, 256, 0, ctx->stream>>>(p);
-  else if (c.size <= 2) merge_fold_p2p_kernel<2><<<grid, 256, 0, ctx->stream>>>(p);
-  else if (c.size <= 4) merge_fold_p2p_kernel<4><<<grid, 256, 0, ctx->stream>>>(p);
-  else if (c.size <= 8) merge_fold_p2p_kernel<8><<<grid, 256, 0, ctx->stream>>>(p);
-  else merge_fold_p2p_kernel<16><<<grid, 256, 0, ctx->stream>>>(p);
+  if (cam)
+  {
+    fill_to_canvas_params_pub(cam, ctx->pW, ctx->pH, p.tp);
+    if (c.rank == 0)
+    {
+      // Canvas::Clear of the frame, on rank 0's arena canvas, before this rank announces "ready"
+      // (peers store their finished pixels only after that)
+      vr_status st2 = vr_canvas_clear(ctx, ctx->pW, ctx->pH);
+      if (st2 != VR_OK) return st2;
+    }
+    if (c.size <= 1) merge_fold_p2p_kernel<1, true><<<grid, 256, 0, ctx->stream>>>(p);
+    else if (c.size <= 2) merge_fold_p2p_kernel<2, true><<<grid, 256, 0, ctx->stream>>>(p);
+    else if (c.size <= 4) merge_fold_p2p_kernel<4, true><<<grid, 256, 0, ctx->stream>>>(p);
+    else if (c.size <= 8) merge_fold_p2p_kernel<8, true><<<grid, 256, 0, ctx->stream>>>(p);
+    else merge_fold_p2p_kernel<16, true><<<grid, 256, 0, ctx->stream>>>(p);
+  }
+  else if (c.size <= 1) merge_fold_p2p_kernel<1, false><<<grid, 256, 0, ctx->stream>>>(p);
+  else if (c.size <= 2) merge_fold_p2p_kernel<2, false><<<grid, 256, 0, ctx->stream>>>(p);
+  else if (c.size <= 4) merge_fold_p2p_kernel<4, false><<<grid, 256, 0, ctx->stream>>>(p);
+  else if (c.size <= 8) merge_fold_p2p_kernel<8, false><<<grid, 256, 0, ctx->stream>>>(p);
+  else merge_fold_p2p_kernel<16, false><<<grid, 256, 0, ctx->stream>>>(p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "merge_fold_p2p launch", e);
   ctx->launches += 2;
@@ -712,9 +828,10 @@ extern "C" vr_status vr_comm_composite_partials(vr_ctx* ctx)
     wait_done_kernel<<<1, 32, 0, ctx->stream>>>(f->p_done, c.size, c.pepoch);
     ctx->launches++;
     // root-only result (PartialCompositor.cpp:580-595): the read side now sees the composited list
+    // (fused canvas mode: the pixels went straight to the canvas, the list is empty)
     ctx->plist = reinterpret_cast<const vr_partial*>(c.arena + L.off_pout);
     ctx->plist_count = &f->p_out_count;
-    ctx->plist_cap = c.max_pixels;
+    ctx->plist_cap = cam ? 0 : c.max_pixels;
   }
   else
   {
@@ -725,4 +842,29 @@ extern "C" vr_status vr_comm_composite_partials(vr_ctx* ctx)
   }
   ctx->n_partials_host = 0;
   return VR_OK;
+}
+
+extern "C" vr_status vr_comm_composite_partials(vr_ctx* ctx)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  return comm_composite_partials_impl(ctx, nullptr);
+}
+
+extern "C" vr_status vr_comm_composite_partials_to_canvas(vr_ctx* ctx, const vr_camera* cam)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  if (!cam) return cfail(ctx, VR_ERR_INVALID, "vr_comm_composite_partials_to_canvas: camera is NULL", cudaSuccess);
+  return comm_composite_partials_impl(ctx, cam);
+}
+
+extern "C" vr_status vr_comm_composite_images(vr_ctx* ctx, const int* vis_order)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  return comm_composite_images_impl(ctx, vis_order, false);
+}
+
+extern "C" vr_status vr_comm_composite_images_to_canvas(vr_ctx* ctx, const int* vis_order)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  return comm_composite_images_impl(ctx, vis_order, true);
 }

@@ -14,6 +14,8 @@
 // in multiples of the SM count, no shared-memory staging needed (no reuse).
 //
 // Compiled with --fmad=false: the float fold must round like the reference's scalar code.
+#include <cstring>
+
 #include "vr_internal.h"
 
 namespace vr
@@ -234,8 +236,8 @@ __global__ void px_count_kernel(const vr_partial* __restrict__ p,
   }
 }
 
-// exclusive scan, three phases, 2048 elements per block
-constexpr int kScanT = 256, kScanPer = 8, kScanTile = kScanT * kScanPer;
+// exclusive scan in three launches, 4096 elements per block, 16-byte loads/stores
+constexpr int kScanT = 256, kScanPer = 16, kScanTile = kScanT * kScanPer;
 __device__ __forceinline__ int block_exclusive_scan(int v, int* total)
 {
   __shared__ int warp_sums[kScanT / 32];
@@ -266,19 +268,32 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total)
   __syncthreads();
   return base + inc - v;
 }
-__global__ void scan_reduce_kernel(const int* __restrict__ in, size_t n, int* __restrict__ block_sums)
+// a thread's 16 consecutive elements as four int4 (n is padded: arrays are allocated to a multiple
+// of kScanTile, the tail past n reads as whatever the memset left there -- zero)
+__device__ __forceinline__ void load16(const int* __restrict__ in, size_t base, int v[kScanPer])
+{
+#pragma unroll
+  for (int q = 0; q < kScanPer / 4; ++q)
+  {
+    const int4 t = *reinterpret_cast<const int4*>(in + base + 4 * q);
+    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+  }
+}
+__global__ void __launch_bounds__(kScanT) scan_reduce_kernel(const int* __restrict__ in,
+                                                            int* __restrict__ block_sums)
 {
   const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanPer;
+  int v[kScanPer];
+  load16(in, base, v);
   int s = 0;
 #pragma unroll
-  for (int k = 0; k < kScanPer; ++k)
-    if (base + k < n) s += in[base + k];
+  for (int k = 0; k < kScanPer; ++k) s += v[k];
   int total;
   block_exclusive_scan(s, &total);
   if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
-// single block, serial over chunks of kScanT; also writes the grand total to *total_out
-__global__ void scan_blocks_kernel(int* block_sums, int nb, int* total_out)
+// single block, serial over chunks of kScanT
+__global__ void __launch_bounds__(kScanT) scan_blocks_kernel(int* block_sums, int nb)
 {
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
@@ -294,42 +309,47 @@ __global__ void scan_blocks_kernel(int* block_sums, int nb, int* total_out)
     if (threadIdx.x == 0) carry += total;
     __syncthreads();
   }
-  if (threadIdx.x == 0 && total_out) *total_out = carry;
 }
-__global__ void scan_apply_kernel(const int* __restrict__ in, size_t n,
-                                  const int* __restrict__ block_sums, int* __restrict__ out)
+__global__ void __launch_bounds__(kScanT) scan_apply_kernel(const int* __restrict__ in,
+                                                           const int* __restrict__ block_sums,
+                                                           int* __restrict__ out)
 {
   const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanPer;
   int v[kScanPer];
+  load16(in, base, v);
   int s = 0;
 #pragma unroll
-  for (int k = 0; k < kScanPer; ++k)
-  {
-    v[k] = base + k < n ? in[base + k] : 0;
-    s += v[k];
-  }
+  for (int k = 0; k < kScanPer; ++k) s += v[k];
   int total;
   int ex = block_exclusive_scan(s, &total) + block_sums[blockIdx.x];
 #pragma unroll
-  for (int k = 0; k < kScanPer; ++k)
+  for (int q = 0; q < kScanPer / 4; ++q)
   {
-    if (base + k < n) out[base + k] = ex;
-    ex += v[k];
+    int4 o;
+    o.x = ex; ex += v[4 * q];
+    o.y = ex; ex += v[4 * q + 1];
+    o.z = ex; ex += v[4 * q + 2];
+    o.w = ex; ex += v[4 * q + 3];
+    *reinterpret_cast<int4*>(out + base + 4 * q) = o;
   }
 }
 
+// counting-sort scatter: the record itself moves to its pixel's segment (one coalesced read, one
+// 24-byte write), so that everything downstream reads a pixel's partials contiguously.  `end`
+// holds each pixel's start offset on entry and its END offset on exit (start = end - count).
 __global__ void px_scatter_kernel(const vr_partial* __restrict__ p,
                                   const unsigned long long* __restrict__ count_dev, size_t cap,
-                                  const int* __restrict__ off, int* __restrict__ fill,
-                                  int* __restrict__ sorted)
+                                  int* __restrict__ end, vr_partial* __restrict__ rec,
+                                  int* __restrict__ sidx)
 {
   const size_t n = list_len(count_dev, cap);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
   {
-    const int px = p[i].pixel_id;
-    const int slot = off[px] + atomicAdd(fill + px, 1);
-    sorted[slot] = (int)i;
+    const vr_partial q = p[i];
+    const int slot = atomicAdd(end + q.pixel_id, 1);
+    rec[slot] = q;
+    sidx[slot] = (int)i;
   }
 }
 
@@ -344,32 +364,70 @@ __device__ __forceinline__ void partial_blend(vr_partial& a, const vr_partial& o
   a.alpha = a.alpha > 1.f ? 1.f : a.alpha;
 }
 
-// order one pixel's index segment by (depth, list index): the (pixel, depth) key of
+// Order of one pixel's segment by (depth, list index): the (pixel, depth) key of
 // VolumePartial::operator< with list order as the documented tie-break.  Segments are as long as
-// the depth complexity of the scene (a handful), so an insertion sort in place is the right tool.
-__device__ __forceinline__ void sort_segment(const vr_partial* __restrict__ p, int* seg, int c)
+// the depth complexity of the scene, so the keys are insertion-sorted in a small local array;
+// perm[a] = position in the segment of the a-th partial front to back.
+constexpr int kMaxLocalSeg = 32;
+__device__ __forceinline__ void order_segment(const vr_partial* __restrict__ rec,
+                                              const int* __restrict__ sidx, int start, int c,
+                                              unsigned char perm[kMaxLocalSeg])
+{
+  float kd[kMaxLocalSeg];
+  int ks[kMaxLocalSeg];
+  for (int a = 0; a < c; ++a)
+  {
+    const float da = rec[start + a].depth;
+    const int ia = sidx[start + a];
+    int b = a - 1;
+    while (b >= 0 && (kd[b] > da || (kd[b] == da && ks[b] > ia)))
+    {
+      kd[b + 1] = kd[b]; ks[b + 1] = ks[b]; perm[b + 1] = perm[b];
+      --b;
+    }
+    kd[b + 1] = da; ks[b + 1] = ia; perm[b + 1] = (unsigned char)a;
+  }
+}
+// fallback for very deep pixels: sort the segment in place in global memory
+__device__ __noinline__ void sort_segment_global(vr_partial* rec, int* sidx, int start, int c)
 {
   for (int a = 1; a < c; ++a)
   {
-    const int ia = seg[a];
-    const float da = p[ia].depth;
+    const vr_partial qa = rec[start + a];
+    const int ia = sidx[start + a];
     int b = a - 1;
     while (b >= 0)
     {
-      const int ib = seg[b];
-      const float db = p[ib].depth;
-      if (db > da || (db == da && ib > ia)) { seg[b + 1] = ib; --b; }
+      const float db = rec[start + b].depth;
+      const int ib = sidx[start + b];
+      if (db > qa.depth || (db == qa.depth && ib > ia))
+      {
+        rec[start + b + 1] = rec[start + b];
+        sidx[start + b + 1] = ib;
+        --b;
+      }
       else break;
     }
-    seg[b + 1] = ia;
+    rec[start + b + 1] = qa;
+    sidx[start + b + 1] = ia;
   }
 }
 
-// one thread per pixel: sort the pixel's segment, fold it front to back, append the result
-__global__ void px_fold_kernel(const vr_partial* __restrict__ p, size_t n_pixels,
-                               const int* __restrict__ cnt, const int* __restrict__ off,
-                               int* __restrict__ sorted, vr_partial* __restrict__ out,
-                               unsigned long long* __restrict__ out_count)
+struct FoldCanvas
+{
+  // partials_to_canvas (VolumeRenderer.cpp:287-391) fused into the fold; canvas == nullptr: off
+  float4* canvas;
+  float* cdepth;
+  int clear; // 1: the canvas is to be treated as cleared (every pixel is written)
+  ToCanvasParams tp;
+};
+
+// one thread per pixel: order the pixel's segment, fold it front to back, append the result to
+// the composited list and (optionally) write the pixel of the final canvas
+__global__ void px_fold_kernel(vr_partial* __restrict__ rec, int* __restrict__ sidx, size_t n_pixels,
+                               const int* __restrict__ cnt, const int* __restrict__ end,
+                               vr_partial* __restrict__ out, unsigned long long* __restrict__ out_count,
+                               const __grid_constant__ FoldCanvas C)
 {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
@@ -380,10 +438,39 @@ __global__ void px_fold_kernel(const vr_partial* __restrict__ p, size_t n_pixels
     vr_partial result;
     if (c > 0)
     {
-      int* seg = sorted + off[px];
-      sort_segment(p, seg, c);
-      result = p[seg[0]];
-      for (int a = 1; a < c; ++a) partial_blend(result, p[seg[a]]);
+      const int start = end[px] - c;
+      if (c == 1)
+        result = rec[start];
+      else if (c <= kMaxLocalSeg)
+      {
+        unsigned char perm[kMaxLocalSeg];
+        order_segment(rec, sidx, start, c, perm);
+        result = rec[start + perm[0]];
+        for (int a = 1; a < c; ++a) partial_blend(result, rec[start + perm[a]]);
+      }
+      else
+      {
+        sort_segment_global(rec, sidx, start, c);
+        result = rec[start];
+        for (int a = 1; a < c; ++a) partial_blend(result, rec[start + a]);
+      }
+    }
+    if (C.canvas && px < n_pixels)
+    {
+      if (c > 0)
+      {
+        const float4 in = C.clear ? make_float4(0.f, 0.f, 0.f, 0.f) : C.canvas[px];
+        float4 o;
+        float d;
+        partial_to_canvas(result, C.tp, in, o, d);
+        C.canvas[px] = o;
+        C.cdepth[px] = d;
+      }
+      else if (C.clear)
+      {
+        C.canvas[px] = make_float4(0.f, 0.f, 0.f, 0.f);
+        C.cdepth[px] = 1.001f;
+      }
     }
     // warp-aggregated append
     const unsigned mask = __ballot_sync(0xffffffffu, c > 0);
@@ -397,11 +484,11 @@ __global__ void px_fold_kernel(const vr_partial* __restrict__ p, size_t n_pixels
   }
 }
 
-// one thread per pixel: sort the pixel's segment and materialise it, so that the whole list
-// becomes ordered by (pixel, depth, list index) -- the form the multi-GPU merge pulls from
-__global__ void px_sort_emit_kernel(const vr_partial* __restrict__ p, size_t n_pixels,
-                                    const int* __restrict__ cnt, const int* __restrict__ off,
-                                    int* __restrict__ sorted, vr_partial* __restrict__ out,
+// one thread per pixel: materialise the pixel's segment in front-to-back order, so that the whole
+// list becomes ordered by (pixel, depth, list index) -- the form the multi-GPU merge pulls from
+__global__ void px_sort_emit_kernel(vr_partial* __restrict__ rec, int* __restrict__ sidx,
+                                    size_t n_pixels, const int* __restrict__ cnt,
+                                    const int* __restrict__ end, vr_partial* __restrict__ out,
                                     size_t out_cap)
 {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -409,11 +496,21 @@ __global__ void px_sort_emit_kernel(const vr_partial* __restrict__ p, size_t n_p
   {
     const int c = cnt[px];
     if (c == 0) continue;
-    const int o = off[px];
-    int* seg = sorted + o;
-    if (c > 1) sort_segment(p, seg, c);
-    for (int a = 0; a < c; ++a)
-      if ((size_t)(o + a) < out_cap) out[o + a] = p[seg[a]];
+    const int start = end[px] - c;
+    if ((size_t)(start + c) > out_cap) continue; // overflow is flagged by publish_minmax_kernel
+    if (c == 1)
+      out[start] = rec[start];
+    else if (c <= kMaxLocalSeg)
+    {
+      unsigned char perm[kMaxLocalSeg];
+      order_segment(rec, sidx, start, c, perm);
+      for (int a = 0; a < c; ++a) out[start + a] = rec[start + perm[a]];
+    }
+    else
+    {
+      sort_segment_global(rec, sidx, start, c);
+      for (int a = 0; a < c; ++a) out[start + a] = rec[start + a];
+    }
   }
 }
 
@@ -429,30 +526,11 @@ __global__ void partials_to_canvas_kernel(const vr_partial* __restrict__ p,
   for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += stride)
   {
     const vr_partial part = p[q];
-    const int pixel_id = part.pixel_id;
-    const int i = pixel_id % T.W, j = pixel_id / T.W;
-    const float fx = (2.f * (float)i - (float)T.W) / 2.0f;
-    const float fy = (2.f * (float)j - (float)T.H) / 2.0f;
-    float dx = T.look[0] + T.delta_x[0] * fx + T.delta_y[0] * fy;
-    float dy = T.look[1] + T.delta_x[1] * fx + T.delta_y[1] * fy;
-    float dz = T.look[2] + T.delta_x[2] * fx + T.delta_y[2] * fy;
-    const float r = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz); // vtkm::Normalize
-    dx = r * dx; dy = r * dy; dz = r * dz;
-    const float wd = part.depth;
-    const float x = T.origin[0] + wd * dx, y = T.origin[1] + wd * dy, z = T.origin[2] + wd * dz;
-    const float* m = T.pv;
-    const float n2 = m[8] * x + m[9] * y + m[10] * z + m[11] * 1.f;
-    const float n3 = m[12] * x + m[13] * y + m[14] * z + m[15] * 1.f;
-    const float image_depth = 0.5f * (n2 / n3) + 0.49f;
-    const float4 in = canvas[pixel_id];
-    const float a = 1.f - part.alpha;
     float4 o;
-    o.x = part.rgb[0] + in.x * a;
-    o.y = part.rgb[1] + in.y * a;
-    o.z = part.rgb[2] + in.z * a;
-    o.w = in.w * a + part.alpha;
-    canvas[pixel_id] = o;
-    cdepth[pixel_id] = image_depth;
+    float d;
+    partial_to_canvas(part, T, canvas[part.pixel_id], o, d);
+    canvas[part.pixel_id] = o;
+    cdepth[part.pixel_id] = d;
   }
 }
 
@@ -525,37 +603,59 @@ cudaError_t launch_synth_braid(void* field, int dtype, const int n[3], const int
   return cudaGetLastError();
 }
 
-// shared front half: histogram -> exclusive scan -> scatter of list indices by pixel
+// shared front half: histogram -> exclusive scan -> scatter of the records by pixel.
+// On exit sc.px_end[px] is the END offset of pixel px's segment in sc.rec (start = end - count).
 static int partials_bin_by_pixel(const vr_partial* in, const unsigned long long* count_dev, size_t cap,
-                                 size_t n_pixels, const PartialScratch& sc, int* off /* n_pixels+1 */,
-                                 int* minmax, unsigned long long* out_count, cudaStream_t s)
+                                 size_t n_pixels, const PartialScratch& sc, int* px_end, int* minmax,
+                                 unsigned long long* out_count, cudaStream_t s)
 {
-  partial_init_kernel<<<1, 1, 0, s>>>(minmax, out_count);
-  cudaMemsetAsync(sc.px_count, 0, n_pixels * sizeof(int), s);
-  cudaMemsetAsync(sc.px_fill, 0, n_pixels * sizeof(int), s);
-  px_count_kernel<<<grid_for(cap, kT), kT, 0, s>>>(in, count_dev, cap, sc.px_count, minmax);
   const int nb = (int)((n_pixels + kScanTile - 1) / kScanTile);
-  scan_reduce_kernel<<<nb, kScanT, 0, s>>>(sc.px_count, n_pixels, sc.scan_blocks);
-  scan_blocks_kernel<<<1, kScanT, 0, s>>>(sc.scan_blocks, nb, off + n_pixels);
-  scan_apply_kernel<<<nb, kScanT, 0, s>>>(sc.px_count, n_pixels, sc.scan_blocks, off);
-  px_scatter_kernel<<<grid_for(cap, kT), kT, 0, s>>>(in, count_dev, cap, off, sc.px_fill, sc.sorted_idx);
+  partial_init_kernel<<<1, 1, 0, s>>>(minmax, out_count);
+  cudaMemsetAsync(sc.px_count, 0, (size_t)nb * kScanTile * sizeof(int), s); // incl. the scan padding
+  px_count_kernel<<<grid_for(cap, kT), kT, 0, s>>>(in, count_dev, cap, sc.px_count, minmax);
+  scan_reduce_kernel<<<nb, kScanT, 0, s>>>(sc.px_count, sc.scan_blocks);
+  scan_blocks_kernel<<<1, kScanT, 0, s>>>(sc.scan_blocks, nb);
+  scan_apply_kernel<<<nb, kScanT, 0, s>>>(sc.px_count, sc.scan_blocks, px_end);
+  px_scatter_kernel<<<grid_for(cap, kT), kT, 0, s>>>(in, count_dev, cap, px_end, sc.rec, sc.sidx);
   return 6;
+}
+
+size_t partial_scan_padded(size_t n_pixels)
+{
+  return (n_pixels + kScanTile - 1) / kScanTile * kScanTile;
 }
 
 int launch_partials_composite(const vr_partial* in, const unsigned long long* count_dev, size_t cap,
                               size_t n_pixels, const PartialScratch& sc, vr_partial* out,
-                              unsigned long long* out_count, cudaStream_t s, cudaError_t* err)
+                              unsigned long long* out_count, const ToCanvasParams* to_canvas,
+                              float4* canvas, float* cdepth, int canvas_clear, cudaStream_t s,
+                              cudaError_t* err)
 {
   int launches = 0;
+  FoldCanvas fc;
+  memset(&fc, 0, sizeof(fc));
+  if (to_canvas)
+  {
+    fc.canvas = canvas;
+    fc.cdepth = cdepth;
+    fc.clear = canvas_clear;
+    fc.tp = *to_canvas;
+  }
   if (cap == 0)
   {
     partial_init_kernel<<<1, 1, 0, s>>>(nullptr, out_count);
+    launches = 1;
+    if (to_canvas && canvas_clear)
+    {
+      canvas_clear_kernel<<<grid_for(n_pixels, kT), kT, 0, s>>>(canvas, cdepth, n_pixels);
+      launches++;
+    }
     *err = cudaGetLastError();
-    return 1;
+    return launches;
   }
-  launches += partials_bin_by_pixel(in, count_dev, cap, n_pixels, sc, sc.px_offset, nullptr, out_count, s);
-  px_fold_kernel<<<grid_for(n_pixels, kT), kT, 0, s>>>(in, n_pixels, sc.px_count, sc.px_offset,
-                                                       sc.sorted_idx, out, out_count);
+  launches += partials_bin_by_pixel(in, count_dev, cap, n_pixels, sc, sc.px_end, nullptr, out_count, s);
+  px_fold_kernel<<<grid_for(n_pixels, kT), kT, 0, s>>>(sc.rec, sc.sidx, n_pixels, sc.px_count, sc.px_end,
+                                                       out, out_count, fc);
   launches += 1;
   *err = cudaGetLastError();
   return launches;
@@ -563,12 +663,12 @@ int launch_partials_composite(const vr_partial* in, const unsigned long long* co
 
 int launch_partials_pixel_sort(const vr_partial* in, const unsigned long long* count_dev, size_t cap,
                                size_t n_pixels, const PartialScratch& sc, vr_partial* sorted_out,
-                               size_t sorted_cap, int* off_out, int* minmax, cudaStream_t s,
+                               size_t sorted_cap, int* end_out, int* minmax, cudaStream_t s,
                                cudaError_t* err)
 {
-  int launches = partials_bin_by_pixel(in, count_dev, cap, n_pixels, sc, off_out, minmax, nullptr, s);
-  px_sort_emit_kernel<<<grid_for(n_pixels, kT), kT, 0, s>>>(in, n_pixels, sc.px_count, off_out,
-                                                            sc.sorted_idx, sorted_out, sorted_cap);
+  int launches = partials_bin_by_pixel(in, count_dev, cap, n_pixels, sc, end_out, minmax, nullptr, s);
+  px_sort_emit_kernel<<<grid_for(n_pixels, kT), kT, 0, s>>>(sc.rec, sc.sidx, n_pixels, sc.px_count, end_out,
+                                                            sorted_out, sorted_cap);
   launches += 1;
   *err = cudaGetLastError();
   return launches;

@@ -43,6 +43,7 @@ static vr_status fail(vr_ctx* c, vr_status st, const char* fmt, ...)
   } while (0)
 
 static vr_status ensure_frame(vr_ctx* ctx, int W, int H);
+static void fill_to_canvas_params(const vr_camera* cam, int W, int H, ToCanvasParams& tp);
 
 // ================================================================= context
 extern "C" vr_status vr_create(int device, vr_ctx** out)
@@ -110,8 +111,11 @@ extern "C" void vr_destroy(vr_ctx* ctx)
   for (auto& kv : ctx->blocks) free_block(kv.second);
   comm_destroy(ctx);
   cudaFree(ctx->lut);
-  cudaFree(ctx->canvas_rgba);
-  cudaFree(ctx->canvas_depth);
+  if (!ctx->canvas_in_arena)
+  {
+    cudaFree(ctx->canvas_rgba);
+    cudaFree(ctx->canvas_depth);
+  }
   if (!ctx->img_in_arena)
   {
     cudaFree(ctx->img_rgba);
@@ -124,9 +128,9 @@ extern "C" void vr_destroy(vr_ctx* ctx)
   cudaFree(ctx->partial_count);
   cudaFree(ctx->partial_count_tmp);
   cudaFree(ctx->px_count);
-  cudaFree(ctx->px_offset);
-  cudaFree(ctx->px_fill);
-  cudaFree(ctx->sorted_idx);
+  cudaFree(ctx->px_end);
+  cudaFree(ctx->sidx);
+  cudaFree(ctx->rec);
   cudaFree(ctx->scan_blocks);
   cudaFree(ctx->tile_counter);
   cudaFree(ctx->sample_counter);
@@ -328,6 +332,7 @@ static vr_status ensure_frame(vr_ctx* ctx, int W, int H)
   if (n > ctx->cap_pixels)
   {
     CK(cudaStreamSynchronize(ctx->stream));
+    REQUIRE(!ctx->canvas_in_arena, "image larger than the max_pixels given to vr_comm_init");
     cudaFree(ctx->canvas_rgba);
     cudaFree(ctx->canvas_depth);
     ctx->canvas_rgba = nullptr;
@@ -751,6 +756,38 @@ extern "C" vr_status vr_composite_images(vr_ctx* ctx, const float* rgba, const f
   return rc;
 }
 
+extern "C" vr_status vr_composite_zbuffer(vr_ctx* ctx, const float* rgba, const float* depth, int n_images,
+                                          int width, int height, uint8_t* out_rgba, float* out_depth)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(rgba && depth && out_rgba && out_depth, "vr_composite_zbuffer: NULL argument");
+  REQUIRE(n_images >= 1, "vr_composite_zbuffer: no images");
+  CK(cudaSetDevice(ctx->device));
+  vr_status st = ensure_frame(ctx, width, height);
+  if (st != VR_OK) return st;
+  const size_t n = (size_t)width * height;
+  // serial Compositor in Z_BUFFER_SURFACE mode composites as images are added (Compositor.cpp:146-160):
+  // the first image initialises the result, every further one is Image::Init'ed and z-selected in
+  for (int i = 0; i < n_images; ++i)
+  {
+    CK(cudaMemcpyAsync(ctx->canvas_rgba, rgba + i * n * 4, n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->canvas_depth, depth + i * n, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (i == 0)
+      CK(launch_quantize(ctx->canvas_rgba, ctx->canvas_depth, n, ctx->res_rgba, ctx->res_depth, ctx->stream));
+    else
+    {
+      CK(launch_quantize(ctx->canvas_rgba, ctx->canvas_depth, n, ctx->img_rgba, ctx->img_depth, ctx->stream));
+      CK(launch_zbuffer(ctx->res_rgba, ctx->res_depth, ctx->img_rgba, ctx->img_depth, n, ctx->stream));
+      ctx->launches++;
+    }
+    ctx->launches++;
+  }
+  CK(cudaMemcpyAsync(out_rgba, ctx->res_rgba, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out_depth, ctx->res_depth, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VR_OK;
+}
+
 extern "C" vr_status vr_zbuffer_composite_dev(vr_ctx* ctx, uint8_t* front_rgba, float* front_depth,
                                               const uint8_t* rgba, const float* depth,
                                               size_t n_pixels)
@@ -780,20 +817,23 @@ static vr_status ensure_partial_scratch(vr_ctx* ctx, size_t n_pixels, size_t n_p
   if (n_pixels > ctx->scratch_px)
   {
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->px_count); cudaFree(ctx->px_offset); cudaFree(ctx->px_fill); cudaFree(ctx->scan_blocks);
-    ctx->px_count = ctx->px_offset = ctx->px_fill = ctx->scan_blocks = nullptr;
-    CK(cudaMalloc(&ctx->px_count, n_pixels * sizeof(int)));
-    CK(cudaMalloc(&ctx->px_offset, (n_pixels + 1) * sizeof(int)));
-    CK(cudaMalloc(&ctx->px_fill, n_pixels * sizeof(int)));
-    CK(cudaMalloc(&ctx->scan_blocks, (n_pixels / 2048 + 2) * sizeof(int)));
+    cudaFree(ctx->px_count); cudaFree(ctx->px_end); cudaFree(ctx->scan_blocks);
+    ctx->px_count = ctx->px_end = ctx->scan_blocks = nullptr;
+    const size_t padded = partial_scan_padded(n_pixels);
+    CK(cudaMalloc(&ctx->px_count, padded * sizeof(int)));
+    CK(cudaMalloc(&ctx->px_end, padded * sizeof(int)));
+    CK(cudaMalloc(&ctx->scan_blocks, (padded / 1024 + 2) * sizeof(int)));
     ctx->scratch_px = n_pixels;
   }
   if (n_parts > ctx->scratch_parts)
   {
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->sorted_idx);
-    ctx->sorted_idx = nullptr;
-    CK(cudaMalloc(&ctx->sorted_idx, n_parts * sizeof(int)));
+    cudaFree(ctx->sidx);
+    cudaFree(ctx->rec);
+    ctx->sidx = nullptr;
+    ctx->rec = nullptr;
+    CK(cudaMalloc(&ctx->sidx, n_parts * sizeof(int)));
+    CK(cudaMalloc(&ctx->rec, n_parts * sizeof(vr_partial)));
     ctx->scratch_parts = n_parts;
   }
   if (n_parts > ctx->partial_tmp_cap)
@@ -813,11 +853,30 @@ vr_status ensure_partial_scratch_pub(vr_ctx* ctx, size_t n_pixels, size_t n_part
 {
   return ensure_partial_scratch(ctx, n_pixels, n_parts);
 }
+void fill_to_canvas_params_pub(const vr_camera* cam, int W, int H, ToCanvasParams& tp)
+{
+  fill_to_canvas_params(cam, W, H, tp);
+}
 }
 
-extern "C" vr_status vr_partials_composite(vr_ctx* ctx)
+static void fill_to_canvas_params(const vr_camera* cam, int W, int H, ToCanvasParams& tp)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  const hm::RayGen g = hm::raygen(*cam, W, H, true);
+  const hm::Mat4 pv = hm::projview(*cam, W, H);
+  for (int k = 0; k < 3; ++k)
+  {
+    tp.origin[k] = cam->position[k];
+    tp.look[k] = g.nlook[k];
+    tp.delta_x[k] = g.delta_x[k];
+    tp.delta_y[k] = g.delta_y[k];
+  }
+  std::memcpy(tp.pv, pv.m, sizeof(tp.pv));
+  tp.W = W;
+  tp.H = H;
+}
+
+static vr_status partials_composite_impl(vr_ctx* ctx, const vr_camera* cam, int canvas_is_clear)
+{
   REQUIRE(ctx->pW > 0, "vr_partials_composite: call vr_partials_begin first");
   CK(cudaSetDevice(ctx->device));
   // no host sync: every kernel reads the list length from the device counter; the scratch is
@@ -825,12 +884,25 @@ extern "C" vr_status vr_partials_composite(vr_ctx* ctx)
   const size_t n_pixels = (size_t)ctx->pW * ctx->pH;
   vr_status st = ensure_partial_scratch(ctx, n_pixels, std::max<size_t>(ctx->partial_cap, 1));
   if (st != VR_OK) return st;
-  PartialScratch sc{ ctx->px_count, ctx->px_offset, ctx->px_fill, ctx->sorted_idx, ctx->scan_blocks };
+  ToCanvasParams tp;
+  if (cam)
+  {
+    if (canvas_is_clear)
+    {
+      st = ensure_frame(ctx, ctx->pW, ctx->pH);
+      if (st != VR_OK) return st;
+    }
+    REQUIRE(ctx->W == ctx->pW && ctx->H == ctx->pH, "vr_partials_composite_to_canvas: canvas (%dx%d) and partial "
+            "frame (%dx%d) differ", ctx->W, ctx->H, ctx->pW, ctx->pH);
+    fill_to_canvas_params(cam, ctx->W, ctx->H, tp);
+  }
+  PartialScratch sc{ ctx->px_count, ctx->px_end, ctx->sidx, ctx->rec, ctx->scan_blocks };
   cudaError_t e;
   // fold into the tmp list (<= 1 partial per pixel), then swap: the context's list becomes the
   // composited one.  The tmp counter is a second device scalar so the input count stays readable.
   ctx->launches += launch_partials_composite(ctx->partials, ctx->partial_count, ctx->partial_cap, n_pixels,
-                                             sc, ctx->partials_tmp, ctx->partial_count_tmp, ctx->stream, &e);
+                                             sc, ctx->partials_tmp, ctx->partial_count_tmp, cam ? &tp : nullptr,
+                                             ctx->canvas_rgba, ctx->canvas_depth, canvas_is_clear, ctx->stream, &e);
   CK(e);
   std::swap(ctx->partials, ctx->partials_tmp);
   std::swap(ctx->partial_cap, ctx->partial_tmp_cap);
@@ -838,6 +910,19 @@ extern "C" vr_status vr_partials_composite(vr_ctx* ctx)
   ctx->n_partials_host = 0;
   ctx->plist = nullptr;
   return VR_OK;
+}
+
+extern "C" vr_status vr_partials_composite(vr_ctx* ctx)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  return partials_composite_impl(ctx, nullptr, 0);
+}
+
+extern "C" vr_status vr_partials_composite_to_canvas(vr_ctx* ctx, const vr_camera* cam, int canvas_is_clear)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(cam, "vr_partials_composite_to_canvas: camera is NULL");
+  return partials_composite_impl(ctx, cam, canvas_is_clear ? 1 : 0);
 }
 
 extern "C" vr_status vr_partials_to_canvas(vr_ctx* ctx, const vr_camera* cam)
@@ -849,18 +934,7 @@ extern "C" vr_status vr_partials_to_canvas(vr_ctx* ctx, const vr_camera* cam)
           ctx->pW, ctx->pH);
   CK(cudaSetDevice(ctx->device));
   ToCanvasParams tp;
-  const hm::RayGen g = hm::raygen(*cam, ctx->W, ctx->H, true);
-  const hm::Mat4 pv = hm::projview(*cam, ctx->W, ctx->H);
-  for (int k = 0; k < 3; ++k)
-  {
-    tp.origin[k] = cam->position[k];
-    tp.look[k] = g.nlook[k];
-    tp.delta_x[k] = g.delta_x[k];
-    tp.delta_y[k] = g.delta_y[k];
-  }
-  std::memcpy(tp.pv, pv.m, sizeof(tp.pv));
-  tp.W = ctx->W;
-  tp.H = ctx->H;
+  fill_to_canvas_params(cam, ctx->W, ctx->H, tp);
   const vr_partial* list = ctx->plist ? ctx->plist : ctx->partials;
   const unsigned long long* list_count = ctx->plist ? ctx->plist_count : ctx->partial_count;
   const size_t list_cap = ctx->plist ? ctx->plist_cap : ctx->partial_cap;

@@ -112,6 +112,7 @@ struct vr_ctx
   uchar4* res_rgba = nullptr;  // composited result (rank 0)
   float* res_depth = nullptr;
   bool img_in_arena = false;
+  bool canvas_in_arena = false;
   int img_rect[4] = { 0, 0, 0x7fffffff, 0x7fffffff }; // where the quantised image may be non-empty
 
   // partial list
@@ -127,10 +128,10 @@ struct vr_ctx
   size_t n_partials_host = 0;                  // valid after a sync'ing call
   int pW = 0, pH = 0;
   // partial composite scratch
-  int* px_count = nullptr;   // per pixel
-  int* px_offset = nullptr;
-  int* px_fill = nullptr;
-  int* sorted_idx = nullptr;
+  int* px_count = nullptr;   // per pixel (padded)
+  int* px_end = nullptr;
+  int* sidx = nullptr;
+  vr_partial* rec = nullptr;
   int* scan_blocks = nullptr;
   size_t scratch_px = 0, scratch_parts = 0, scratch_blocks = 0;
   vr_partial* partials_tmp = nullptr;
@@ -164,31 +165,64 @@ cudaError_t launch_synth_braid(void* field, int dtype, const int n[3], const int
 
 struct PartialScratch
 {
-  int* px_count;
-  int* px_offset; // n_pixels + 1
-  int* px_fill;
-  int* sorted_idx;
+  int* px_count;   // per pixel, padded to partial_scan_padded(n_pixels)
+  int* px_end;     // per pixel segment end offset (same padding)
+  int* sidx;       // original list index of each binned record
+  vr_partial* rec; // records binned by pixel
   int* scan_blocks;
 };
-// composite the list `in` (n partials, pixel ids in [0, n_pixels)) into `out` (<= 1 per pixel);
-// *out_count (device) receives the number written.  Returns number of kernels launched.
-// The list length is read on the device (*count_dev, clamped to cap).
-int launch_partials_composite(const vr_partial* in, const unsigned long long* count_dev, size_t cap,
-                              size_t n_pixels, const PartialScratch& sc, vr_partial* out,
-                              unsigned long long* out_count, cudaStream_t s, cudaError_t* err);
-// Reorder the list by (pixel, depth, list index) into sorted_out and write the exclusive
-// per-pixel offsets (n_pixels + 1 ints) and the list's {min,max} pixel id.
-int launch_partials_pixel_sort(const vr_partial* in, const unsigned long long* count_dev, size_t cap,
-                               size_t n_pixels, const PartialScratch& sc, vr_partial* sorted_out,
-                               size_t sorted_cap, int* off_out, int* minmax, cudaStream_t s,
-                               cudaError_t* err);
-
+size_t partial_scan_padded(size_t n_pixels);
 struct ToCanvasParams
 {
   float origin[3], look[3], delta_x[3], delta_y[3];
   float pv[16];
   int W, H;
 };
+#ifdef __CUDACC__
+// one pixel of partials_to_canvas (VolumeRenderer.cpp:287-391): recompute the ray like K1 (with the
+// reference's delta_y-from-ru quirk baked into T by the host), project origin + depth*dir, blend
+// the partial over the canvas value `in`
+__device__ __forceinline__ void partial_to_canvas(const vr_partial& part, const ToCanvasParams& T,
+                                                  float4 in, float4& o, float& image_depth)
+{
+  const int pixel_id = part.pixel_id;
+  const int i = pixel_id % T.W, j = pixel_id / T.W;
+  const float fx = (2.f * (float)i - (float)T.W) / 2.0f;
+  const float fy = (2.f * (float)j - (float)T.H) / 2.0f;
+  float dx = T.look[0] + T.delta_x[0] * fx + T.delta_y[0] * fy;
+  float dy = T.look[1] + T.delta_x[1] * fx + T.delta_y[1] * fy;
+  float dz = T.look[2] + T.delta_x[2] * fx + T.delta_y[2] * fy;
+  const float r = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz); // vtkm::Normalize
+  dx = r * dx; dy = r * dy; dz = r * dz;
+  const float wd = part.depth;
+  const float x = T.origin[0] + wd * dx, y = T.origin[1] + wd * dy, z = T.origin[2] + wd * dz;
+  const float* m = T.pv;
+  const float n2 = m[8] * x + m[9] * y + m[10] * z + m[11] * 1.f;
+  const float n3 = m[12] * x + m[13] * y + m[14] * z + m[15] * 1.f;
+  image_depth = 0.5f * (n2 / n3) + 0.49f;
+  const float a = 1.f - part.alpha;
+  o.x = part.rgb[0] + in.x * a;
+  o.y = part.rgb[1] + in.y * a;
+  o.z = part.rgb[2] + in.z * a;
+  o.w = in.w * a + part.alpha;
+}
+#endif
+
+// composite the list `in` (length *count_dev clamped to cap, pixel ids in [0, n_pixels)) into `out`
+// (<= 1 per pixel); *out_count (device) receives the number written.  With to_canvas != nullptr the
+// fold also writes the final canvas (partials_to_canvas fused).  Returns the number of launches.
+int launch_partials_composite(const vr_partial* in, const unsigned long long* count_dev, size_t cap,
+                              size_t n_pixels, const PartialScratch& sc, vr_partial* out,
+                              unsigned long long* out_count, const ToCanvasParams* to_canvas,
+                              float4* canvas, float* cdepth, int canvas_clear, cudaStream_t s,
+                              cudaError_t* err);
+// Reorder the list by (pixel, depth, list index) into sorted_out and write each pixel's segment END
+// offset (padded array) and the list's {min,max} pixel id.
+int launch_partials_pixel_sort(const vr_partial* in, const unsigned long long* count_dev, size_t cap,
+                               size_t n_pixels, const PartialScratch& sc, vr_partial* sorted_out,
+                               size_t sorted_cap, int* end_out, int* minmax, cudaStream_t s,
+                               cudaError_t* err);
+
 cudaError_t launch_partials_to_canvas(const vr_partial* p, const unsigned long long* count_dev,
                                       size_t max_n, const ToCanvasParams& tp, float4* canvas,
                                       float* cdepth, cudaStream_t s);
@@ -204,6 +238,8 @@ struct FoldP2PParams
   int rect[4]; // {x0,y0,x1,y1}: my image is empty (colour 0, depth 1.001) outside of it
   size_t off_img_rgba, off_img_depth, off_res_rgba, off_res_depth, off_flags;
   int order[16]; // rank index per fold step (front to back)
+  float4* canvas_rgba; // rank 0, fused ImageToCanvas (null: off)
+  float* canvas_depth;
 };
 cudaError_t launch_fold_p2p(const FoldP2PParams& p, int sm_count, cudaStream_t s);
 } // namespace vr

@@ -166,15 +166,11 @@ def run_bench(args, wl, bench):
 
     def composite():
         if path_a:
-            ctx.comm_composite_images(vis_rank)
-            if rank == 0:
-                ctx.image_result_to_canvas()
+            ctx.comm_composite_images_to_canvas(vis_rank)
         else:
-            if rank == 0:
-                ctx.canvas_clear(W, H)
-            ctx.comm_composite_partials()
-            if rank == 0:
-                ctx.partials_to_canvas(cam)
+            # redistribute + sort + fold + collect + partials_to_canvas: per rank one pixel-sort
+            # pipeline and ONE P2P kernel that stores finished pixels into rank 0's canvas
+            ctx.comm_composite_partials_to_canvas(cam)
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
@@ -241,10 +237,26 @@ def run_bench(args, wl, bench):
     if rank == 0:
         pk, pk_src = bench.peaks()
         alg = nvox * 4 * len(blocks) / world + W * H * 20  # per GPU per frame
+        # NVLink bytes that reach the busiest GPU (rank 0) per frame: what it pulls for the pixels it
+        # owns plus what the other owners store into its result
+        rects = []
+        for b in sp["bounds"]:
+            sx, sy, sw, sh = _lib.find_subset(cam, W, H, b)
+            rects.append((sx & ~3, sy, min(W, (sx + sw + 3) & ~3), sy + sh))
+        cover = np.zeros((H, W), np.uint8)
+        layer_px = 0
+        for (x0, y0, x1, y1) in rects:
+            cover[y0:y1, x0:x1] = 1
+            layer_px += max(0, x1 - x0) * max(0, y1 - y0)
+        covered = int(cover.sum())
         if path_a:
-            nv_bytes = (world - 1) / world * W * H * 8 * 2  # pulled in + pushed to root, per GPU
+            pulled = layer_px / world * (world - 1) / world * 8.0   # RGBA8 + depth of the covering layers
+            pushed = covered * (world - 1) / world * 8.0            # folded pixels stored into rank 0
         else:
-            nv_bytes = float(tsum[5]) / world * 24.0 * (world - 1) / world
+            pulled = float(tsum[5]) / world * 24.0 * (world - 1) / world + \
+                W * H / world * 4.0 * (world - 1)                   # partial runs + per-pixel end offsets
+            pushed = covered * (world - 1) / world * 20.0           # finished canvas pixels into rank 0
+        nv_bytes = pulled + pushed
         line = {"metric": "volume_render_mrays_per_s", "value": W * H / (ms * 1e-3) / 1e6, "unit": "Mrays/s",
                 "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -258,7 +270,7 @@ def run_bench(args, wl, bench):
                 "frames_per_s": 1e3 / ms, "render_ms_per_frame": render_ms,
                 "composite_ms_per_frame": comp_ms, "composite_in_step_ms": tail_ms,
                 "partials_total": int(tsum[5]),
-                "nvlink": {"bytes_per_gpu_per_frame": nv_bytes,
+                "nvlink": {"bytes_into_rank0_per_frame": nv_bytes, "pulled": pulled, "pushed_into_rank0": pushed,
                            "achieved_gbs": nv_bytes / (comp_ms * 1e-3) / 1e9, "peak_gbs": 770.0,
                            "peak_source": "measured peer copy per direction (B200_PROFILING.md)"},
                 "e2e": e2e, "gpu_launches": int(tsum[4]), "clocks": clk,

@@ -217,7 +217,6 @@ def run_single(args, wl):
             if ev:
                 ev[1].record(stream)
         else:
-            ctx.canvas_clear(W, H)
             ctx.partials_begin(W, H)
             if ev:
                 ev[0].record(stream)
@@ -225,8 +224,8 @@ def run_single(args, wl):
                 ctx.trace_to_partials(i, cam, sp["sample_dist"], rmin, rmax, False)
             if ev:
                 ev[1].record(stream)
-            ctx.partials_composite()
-            ctx.partials_to_canvas(cam)
+            # PartialCompositor::composite + partials_to_canvas over a cleared canvas, fused
+            ctx.partials_composite_to_canvas(cam, canvas_is_clear=True)
 
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):

@@ -180,6 +180,11 @@ VR_API vr_status vr_composite_images(vr_ctx* ctx, const float* rgba, const float
 VR_API vr_status vr_zbuffer_composite_dev(vr_ctx* ctx, uint8_t* front_rgba, float* front_depth,
                                           const uint8_t* rgba, const float* depth,
                                           size_t n_pixels);
+/* Host-buffer form of Compositor::{AddImage x n, Composite} in Z_BUFFER_SURFACE mode for one rank
+ * (Compositor.cpp:146-160: images are z-selected into the first one as they are added).         */
+VR_API vr_status vr_composite_zbuffer(vr_ctx* ctx, const float* rgba, const float* depth,
+                                      int n_images, int width, int height, uint8_t* out_rgba,
+                                      float* out_depth);
 /* Renderer::ImageToCanvas (Renderer.cpp:265-283): composited RGBA8 (device) -> device canvas.  */
 VR_API vr_status vr_image_to_canvas_dev(vr_ctx* ctx, const uint8_t* rgba, const float* depth);
 
@@ -188,6 +193,12 @@ VR_API vr_status vr_image_to_canvas_dev(vr_ctx* ctx, const uint8_t* rgba, const 
  * device partial list: order by (pixel, depth) [ties: list order], fold front-to-back per
  * pixel with VolumePartial::blend; leaves <= 1 partial per covered pixel.                      */
 VR_API vr_status vr_partials_composite(vr_ctx* ctx);
+/* The two calls above and below fused for one rank (the body of the render loop at
+ * VolumeRenderer.cpp:580-595): the fold writes the canvas pixel as it finishes it.
+ * canvas_is_clear != 0: the frame starts from Canvas::Clear -- every pixel is written, no prior
+ * vr_canvas_clear needed; 0: blend over the context's canvas as it is.  The composited list is
+ * left in the context as after vr_partials_composite.                                          */
+VR_API vr_status vr_partials_composite_to_canvas(vr_ctx* ctx, const vr_camera* cam, int canvas_is_clear);
 /* partials_to_canvas (VolumeRenderer.cpp:287-391) from the composited list onto the device
  * canvas (which must have the frame's width/height).                                           */
 VR_API vr_status vr_partials_to_canvas(vr_ctx* ctx, const vr_camera* cam);
@@ -215,11 +226,18 @@ VR_API vr_status vr_comm_connect(vr_ctx* ctx, const void* all_handles /* n_ranks
  * vis_order[r] = composite order of rank r's image (VolumeRenderer.cpp:833-867).
  * On rank 0 the composited image is left in the context (vr_image_result_*).                   */
 VR_API vr_status vr_comm_composite_images(vr_ctx* ctx, const int* vis_order);
+/* The same plus Renderer::ImageToCanvas on rank 0 (vr_image_result_to_canvas) folded into the
+ * exchange: rank 0 converts the pixels no rank covers while the others are still in flight.    */
+VR_API vr_status vr_comm_composite_images_to_canvas(vr_ctx* ctx, const int* vis_order);
 VR_API vr_status vr_image_result_download(vr_ctx* ctx, uint8_t* rgba, float* depth); /* syncs */
 VR_API vr_status vr_image_result_to_canvas(vr_ctx* ctx);
 /* Path B, collective: redistribute partials by pixel-range owner, sort+fold on the owner,
  * gather to rank 0 (P2-P5).  On rank 0 the result replaces the context's partial list.        */
 VR_API vr_status vr_comm_composite_partials(vr_ctx* ctx);
+/* Path B with partials_to_canvas fused in, for a frame that starts from a cleared canvas: the owner
+ * of a pixel stores the finished canvas pixel straight into rank 0's canvas (20 B per covered pixel
+ * over NVLink; no list, no gather).  On rank 0 the context's canvas holds the final image.       */
+VR_API vr_status vr_comm_composite_partials_to_canvas(vr_ctx* ctx, const vr_camera* cam);
 /* Device pointers into this rank's arena for transports that move the bytes themselves
  * (NCCL send/recv baseline in the harness).                                                    */
 VR_API vr_status vr_image_ptrs(vr_ctx* ctx, void** rgba8_dev, void** depth_dev);

@@ -91,12 +91,17 @@ def gpu_checks(rank, world):
             ctx.partials_begin(W, H)
             for i in mine:
                 ctx.trace_to_partials(i, cam, sc["sample_dist"], rmin, rmax, False)
-            if rank == 0:
-                ctx.canvas_clear(W, H)
-            ctx.comm_composite_partials()
+            fused = rep == 1   # pixels stored straight into rank 0's canvas, no list
+            if fused:
+                ctx.comm_composite_partials_to_canvas(cam)
+            else:
+                if rank == 0:
+                    ctx.canvas_clear(W, H)
+                ctx.comm_composite_partials()
             if rank == 0:
                 got = ctx.partials_download()
-                ctx.partials_to_canvas(cam)
+                if not fused:
+                    ctx.partials_to_canvas(cam)
                 rgba, depth = ctx.canvas_download(W, H)
                 o_rgba, o_depth = O.new_canvas(W, H)
                 pl = [O.render_partials(scenes.oracle_block(sc["doms"][i]), cam, W, H, sc["lut"],
@@ -105,10 +110,15 @@ def gpu_checks(rank, world):
                 ref = O.composite_partials(pl)
                 a = np.sort(got, order="pixel_id")
                 b = np.sort(ref, order="pixel_id")
-                assert a.size == b.size and a.size > 1000, (a.size, b.size)
-                assert a.tobytes() == b.tobytes(), "path B: composited partials differ from the oracle"
+                if fused:
+                    assert a.size == 0
+                else:
+                    assert a.size == b.size and a.size > 1000, (a.size, b.size)
+                    assert a.tobytes() == b.tobytes(), "path B: composited partials differ from the oracle"
                 O.partials_to_canvas(ref, cam, W, H, o_rgba, o_depth)
-                assert np.array_equal(rgba, o_rgba), "path B canvas differs"
+                assert np.array_equal(rgba, o_rgba), "path B canvas differs (rep %d)" % rep
+                cov = o_rgba[:, 3] > 0
+                assert np.array_equal(depth[cov], o_depth[cov]) and cov.sum() > 1000
             else:
                 assert ctx.partials_count() == 0  # root-only result
             dist.barrier()
@@ -135,9 +145,16 @@ def gpu_checks(rank, world):
                 ctx.image_from_canvas()
             else:          # ... or the fused frame kernel, outside of the block's rectangle unwritten
                 ctx.trace_to_image(0, cam, W, H, sd, rmin, rmax, no_clear=(rep == 2))
-            ctx.comm_composite_images(np.ascontiguousarray(vis_all[:, 0], np.int32))
+            vo = np.ascontiguousarray(vis_all[:, 0], np.int32)
+            if rep == 1:
+                ctx.comm_composite_images_to_canvas(vo)   # ImageToCanvas folded into the exchange
+            else:
+                ctx.comm_composite_images(vo)
+                if rank == 0:
+                    ctx.image_result_to_canvas()
             if rank == 0:
                 u8, d = ctx.image_result_download(W, H)
+                can, cd = ctx.canvas_download(W, H)
                 layers, depths = [], []
                 for dom in doms:
                     r, dd = O.new_canvas(W, H)
@@ -149,6 +166,8 @@ def gpu_checks(rank, world):
                 ref, rd = O.ordered_composite(np.stack(layers), np.stack(depths), order)
                 assert np.array_equal(u8, ref), "path A: composited uint8 image differs (rep %d)" % rep
                 assert np.array_equal(d, rd, equal_nan=True), "path A: composited depth differs (rep %d)" % rep
+                o_can, o_cd = O.image_to_canvas(ref, rd)
+                assert np.array_equal(can, o_can) and np.array_equal(cd, o_cd, equal_nan=True), "path A canvas (rep %d)" % rep
                 cov = ref[:, 3] > 0
                 assert cov.sum() > 1000
             else:

@@ -304,6 +304,65 @@ def test_multi_domain_path_b(ctx, n_block, per_axis, az):
     assert np.allclose(depth[cov], ref_depth[cov], rtol=0, atol=1e-6)
 
 
+@pytest.mark.parametrize("clear", [True, False])
+def test_fused_partial_composite_to_canvas(ctx, clear):
+    """vr_partials_composite_to_canvas == vr_partials_composite + vr_partials_to_canvas, bit for bit,
+    over a cleared canvas and over a canvas that already holds opaque geometry."""
+    doms = datasets.braid_uniform_blocks(10, 2, dtype=np.float32)
+    gb = datasets.union_bounds([datasets.domain_bounds(d) for d in doms])
+    W, H = 260, 180
+    cam = O.camera_reset_to_bounds(gb)
+    O.camera_azimuth(cam, 21.0)
+    lut = color_table.parse_color_table(scenes.RAMP_TF).corrected_opacity(100).lut()
+    sd = O.sample_distance(gb, 100)
+    rmin, rmax = scenes.field_range(doms)
+    ctx.set_tf(lut)
+    for i, d in enumerate(doms):
+        ctx.block_from_domain(i, d)
+    rng = np.random.default_rng(5)
+    rgba0 = rng.random((H * W, 4), dtype=np.float32)
+    depth0 = np.full(H * W, 1.001, np.float32)
+    if clear:
+        rgba0[:] = 0
+
+    def run(fused):
+        ctx.canvas_upload(W, H, rgba0, depth0)
+        ctx.partials_begin(W, H)
+        for i in range(len(doms)):
+            ctx.trace_to_partials(i, cam, sd, rmin, rmax, False)
+        if fused:
+            if clear:  # poison: the fused call must overwrite every pixel
+                ctx.canvas_upload(W, H, np.full((H * W, 4), 7., np.float32), np.full(H * W, 7., np.float32))
+            ctx.partials_composite_to_canvas(cam, canvas_is_clear=clear)
+        else:
+            ctx.partials_composite()
+            ctx.partials_to_canvas(cam)
+        return ctx.canvas_download(W, H), np.sort(ctx.partials_download(), order="pixel_id")
+
+    (c_a, d_a), p_a = run(False)
+    (c_b, d_b), p_b = run(True)
+    for i in range(len(doms)):
+        ctx.block_free(i)
+    assert np.array_equal(c_a, c_b) and np.array_equal(d_a, d_b)
+    assert p_a.tobytes() == p_b.tobytes() and p_a.size > 1000
+
+
+def test_deep_pixels_local_and_global_sort(ctx):
+    """segments longer than the in-register sort limit (32) take the in-place global path"""
+    rng = np.random.default_rng(9)
+    W, H = 16, 8
+    n = 6000
+    p = np.zeros(n, O.PARTIAL_DTYPE)
+    p["pixel_id"] = rng.integers(0, 40, n)          # ~150 partials per pixel
+    p["depth"] = rng.random(n, dtype=np.float32)
+    a = rng.random(n, dtype=np.float32) * 0.05
+    p["alpha"] = a
+    p["rgb"] = rng.random((n, 3), dtype=np.float32) * a[:, None]
+    mine = np.sort(ctx.composite_partials(p, W, H), order="pixel_id")
+    ref = np.sort(O.composite_partials([p]), order="pixel_id")
+    assert mine.tobytes() == ref.tobytes()
+
+
 # ------------------------------------------------------------------ compositing kernels
 def test_quantise_and_fold_bit_exact(ctx):
     rng = np.random.default_rng(11)
