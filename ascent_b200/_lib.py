@@ -25,7 +25,8 @@ SYMBOLS = [
     "vr_block_bounds", "vr_set_tf", "vr_canvas_clear", "vr_canvas_upload", "vr_canvas_download",
     "vr_canvas_ptrs", "vr_trace_to_canvas", "vr_render_image", "vr_trace_to_image", "vr_partials_begin",
     "vr_trace_to_partials", "vr_partials_count", "vr_partials_download", "vr_render_partials",
-    "vr_free", "vr_image_from_canvas", "vr_image_download", "vr_fold_images_dev",
+    "vr_free", "vr_layers_begin", "vr_trace_to_layer", "vr_layers_composite_to_canvas",
+    "vr_layers_to_partials", "vr_comm_layers_composite_to_canvas", "vr_image_from_canvas", "vr_image_download", "vr_fold_images_dev",
     "vr_composite_images", "vr_composite_zbuffer", "vr_zbuffer_composite_dev", "vr_image_to_canvas_dev",
     "vr_partials_composite", "vr_partials_composite_to_canvas", "vr_partials_to_canvas", "vr_composite_partials", "vr_comm_init",
     "vr_comm_connect", "vr_comm_composite_images", "vr_comm_composite_images_to_canvas",
@@ -93,6 +94,11 @@ def load():
         "vr_render_partials": (C.c_int, [vp, C.c_int, cam, C.c_int, C.c_int, C.c_float, C.c_float,
                                          C.c_float, vp, C.POINTER(vp), C.POINTER(sz)]),
         "vr_free": (None, [vp]),
+        "vr_layers_begin": (C.c_int, [vp, C.c_int, C.c_int]),
+        "vr_trace_to_layer": (C.c_int, [vp, C.c_int, cam, C.c_float, C.c_float, C.c_float, C.c_int]),
+        "vr_layers_composite_to_canvas": (C.c_int, [vp, cam, C.c_int]),
+        "vr_layers_to_partials": (C.c_int, [vp]),
+        "vr_comm_layers_composite_to_canvas": (C.c_int, [vp, cam]),
         "vr_image_from_canvas": (C.c_int, [vp]),
         "vr_image_download": (C.c_int, [vp, vp, vp]),
         "vr_fold_images_dev": (C.c_int, [vp, vp, vp, sz, ip, C.c_int, sz, vp, vp]),
@@ -319,6 +325,23 @@ class Context:
             C.memmove(out.ctypes.data, p.value, n.value * 24)
         self.lib.vr_free(p)
         return out
+
+    # -- path B on dense ray layers
+    def layers_begin(self, W, H):
+        self._ck(self.lib.vr_layers_begin(self.h, W, H))
+
+    def trace_to_layer(self, block_id, cam, sample_dist, rmin, rmax, use_canvas_depth=False):
+        self._ck(self.lib.vr_trace_to_layer(self.h, block_id, C.byref(as_camera(cam)), sample_dist, rmin,
+                                            rmax, int(use_canvas_depth)))
+
+    def layers_composite_to_canvas(self, cam, canvas_is_clear=True):
+        self._ck(self.lib.vr_layers_composite_to_canvas(self.h, C.byref(as_camera(cam)), int(canvas_is_clear)))
+
+    def layers_to_partials(self):
+        self._ck(self.lib.vr_layers_to_partials(self.h))
+
+    def comm_layers_composite_to_canvas(self, cam):
+        self._ck(self.lib.vr_comm_layers_composite_to_canvas(self.h, C.byref(as_camera(cam))))
 
     # -- image compositing
     def image_from_canvas(self):

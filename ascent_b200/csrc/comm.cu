@@ -474,6 +474,7 @@ struct Layout
 {
   size_t off_flags, off_img_rgba[2], off_img_depth[2], off_res_rgba[2], off_res_depth[2];
   size_t off_poff[2], off_psorted[2], off_pout, off_canvas_rgba, off_canvas_depth, total;
+  size_t off_lflags, off_ltab[2], off_lpool_rgba[2], off_lpool_depth[2];
 };
 Layout make_layout(size_t max_pixels, size_t max_partials, bool is_root)
 {
@@ -487,6 +488,11 @@ Layout make_layout(size_t max_pixels, size_t max_partials, bool is_root)
   for (int b = 0; b < 2; ++b) { L.off_res_depth[b] = o; o += px * 4; }
   for (int b = 0; b < 2; ++b) { L.off_poff[b] = o; o += max_partials ? align_up(partial_scan_padded(max_pixels) * 4, 256) : 0; }
   for (int b = 0; b < 2; ++b) { L.off_psorted[b] = o; o += align_up(max_partials * sizeof(vr_partial), 256); }
+  // dense ray layers (layers.cu): flags, layer tables and pools, double-buffered
+  L.off_lflags = o; o += max_partials ? kFlagBytes : 0;
+  for (int b = 0; b < 2; ++b) { L.off_ltab[b] = o; o += max_partials ? align_up(sizeof(LayerTable), 256) : 0; }
+  for (int b = 0; b < 2; ++b) { L.off_lpool_rgba[b] = o; o += align_up(max_partials * sizeof(float4), 256); }
+  for (int b = 0; b < 2; ++b) { L.off_lpool_depth[b] = o; o += align_up(max_partials * sizeof(float), 256); }
   // regions only rank 0 allocates; their OFFSETS are the same on every rank (peers address them)
   const size_t common_end = o;
   L.off_pout = o;
@@ -554,6 +560,27 @@ vr_status comm_bind_frame(vr_ctx* ctx, size_t n_pixels)
   return VR_OK;
 }
 
+// point the context's layer table/pools at the arena halves of the NEXT layer frame's parity
+vr_status comm_bind_layers(vr_ctx* ctx)
+{
+  Comm& c = ctx->comm;
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
+  const int b = (c.lepoch + 1) & 1;
+  if (!ctx->layers_in_arena)
+  {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->ltab); cudaFree(ctx->lpool_rgba); cudaFree(ctx->lpool_depth);
+    ctx->layers_in_arena = true;
+  }
+  ctx->ltab = reinterpret_cast<LayerTable*>(c.arena + L.off_ltab[b]);
+  ctx->lpool_rgba = reinterpret_cast<float4*>(c.arena + L.off_lpool_rgba[b]);
+  ctx->lpool_depth = reinterpret_cast<float*>(c.arena + L.off_lpool_depth[b]);
+  ctx->lpool_cap = c.max_partials;
+  return VR_OK;
+}
+
+vr_status upload_layer_table_pub(vr_ctx* ctx);
+
 } // namespace vr
 
 using namespace vr;
@@ -584,6 +611,7 @@ extern "C" vr_status vr_comm_init(vr_ctx* ctx, int rank, int n_ranks, size_t max
   cudaError_t e = cudaMalloc(&c.arena, c.arena_bytes);
   if (e != cudaSuccess) return cfail(ctx, VR_ERR_NOMEM, "vr_comm_init: arena", e);
   cudaMemset(c.arena, 0, kFlagBytes);
+  if (max_partials) cudaMemset(c.arena + L.off_lflags, 0, kFlagBytes);
   {
     const unsigned long long cfg[2] = { max_pixels, max_partials };
     cudaMemcpy(c.arena + offsetof(Flags, cfg_max_pixels), cfg, sizeof(cfg), cudaMemcpyHostToDevice);
@@ -867,4 +895,67 @@ extern "C" vr_status vr_comm_composite_images_to_canvas(vr_ctx* ctx, const int* 
 {
   if (!ctx) return VR_ERR_INVALID;
   return comm_composite_images_impl(ctx, vis_order, true);
+}
+
+extern "C" vr_status vr_comm_layers_composite_to_canvas(vr_ctx* ctx, const vr_camera* cam)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  Comm& c = ctx->comm;
+  if (!c.on || !c.peer_dev) return cfail(ctx, VR_ERR_STATE, "vr_comm_layers_composite_to_canvas: not connected", cudaSuccess);
+  if (!cam) return cfail(ctx, VR_ERR_INVALID, "vr_comm_layers_composite_to_canvas: camera is NULL", cudaSuccess);
+  if (ctx->lW <= 0 || !ctx->layers_in_arena)
+    return cfail(ctx, VR_ERR_STATE, "vr_comm_layers_composite_to_canvas: call vr_layers_begin (after vr_comm_connect) first", cudaSuccess);
+  if ((size_t)ctx->lW * ctx->lH > c.max_pixels)
+    return cfail(ctx, VR_ERR_INVALID, "vr_comm_layers_composite_to_canvas: frame larger than max_pixels", cudaSuccess);
+  if (ctx->ltab_host->n > kMaxSmemLayers / c.size)
+  {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "vr_comm_layers_composite_to_canvas: %d layers on this rank, at most %d with %d ranks",
+             ctx->ltab_host->n, kMaxSmemLayers / c.size, c.size);
+    ctx->err = buf;
+    return VR_ERR_INVALID;
+  }
+  cudaSetDevice(ctx->device);
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
+  c.lepoch += 1;
+  const int par = c.lepoch & 1;
+  vr_status st = upload_layer_table_pub(ctx); // into the arena table of this parity (bound at vr_layers_begin)
+  if (st != VR_OK) return st;
+  if (c.rank == 0)
+  {
+    // Canvas::Clear of the frame on rank 0's arena canvas, before this rank announces "ready"
+    st = vr_canvas_clear(ctx, ctx->lW, ctx->lH);
+    if (st != VR_OK) return st;
+  }
+  LayerFoldParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.rank = c.rank;
+  p.size = c.size;
+  p.epoch = c.lepoch;
+  p.W = ctx->lW;
+  p.H = ctx->lH;
+  p.clear = 1;
+  p.smem_layers = kMaxSmemLayers;
+  for (int r = 0; r < c.size; ++r)
+  {
+    p.table[r] = reinterpret_cast<const LayerTable*>(c.peer[r] + L.off_ltab[par]);
+    p.pool_rgba[r] = reinterpret_cast<const float4*>(c.peer[r] + L.off_lpool_rgba[par]);
+    p.pool_depth[r] = reinterpret_cast<const float*>(c.peer[r] + L.off_lpool_depth[par]);
+    p.flags[r] = c.peer[r] + L.off_lflags;
+  }
+  p.canvas_rgba = reinterpret_cast<float4*>(c.peer[0] + L.off_canvas_rgba);
+  p.canvas_depth = reinterpret_cast<float*>(c.peer[0] + L.off_canvas_depth);
+  fill_to_canvas_params_pub(cam, ctx->lW, ctx->lH, p.tp);
+  cudaError_t e = launch_layers_fold(p, true, ctx->sm_count, ctx->stream);
+  if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "layers_fold launch", e);
+  ctx->launches++;
+  if (c.rank == 0)
+  {
+    const LayerFlags* f = reinterpret_cast<const LayerFlags*>(c.arena + L.off_lflags);
+    e = launch_layers_wait_done(f->done, c.size, c.lepoch, ctx->stream);
+    if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "layers wait launch", e);
+    ctx->launches++;
+  }
+  ctx->lW = ctx->lH = 0; // the frame is consumed: vr_layers_begin starts the next one
+  return VR_OK;
 }

@@ -631,15 +631,17 @@ void VolumeRenderer::RenderMultipleDomainsPerRank()
     const vr_camera cam = r.GetCamera().ToVR();
     if (!r.IsCleared())
       m_ctx->Check(vr_canvas_upload(m_ctx->h, W, H, r.GetColorBuffer().data(), r.GetDepthBuffer().data()));
-    m_ctx->Check(vr_partials_begin(m_ctx->h, W, H));
+    // wrapper->render(camera, canvas, partials) per domain (VolumeRenderer.cpp:561-577): the rays of
+    // each structured block stay in a dense layer on the device
+    m_ctx->Check(vr_layers_begin(m_ctx->h, W, H));
     for (int i = 0; i < m_input->GetNumberOfDomains(); ++i)
     {
       const DataSet::Domain& d = m_input->GetDomain(i);
       if (!d.Find(m_field_name)) continue;
-      m_ctx->Check(vr_trace_to_partials(m_ctx->h, d.id, &cam, m_sample_dist, rmin, rmax, r.IsCleared() ? 0 : 1));
+      m_ctx->Check(vr_trace_to_layer(m_ctx->h, d.id, &cam, m_sample_dist, rmin, rmax, r.IsCleared() ? 0 : 1));
     }
-    // PartialCompositor::composite + partials_to_canvas (VolumeRenderer.cpp:580-595), one pipeline
-    m_ctx->Check(vr_partials_composite_to_canvas(m_ctx->h, &cam, r.IsCleared() ? 1 : 0));
+    // PartialCompositor::composite + partials_to_canvas (VolumeRenderer.cpp:580-595), one kernel
+    m_ctx->Check(vr_layers_composite_to_canvas(m_ctx->h, &cam, r.IsCleared() ? 1 : 0));
     m_ctx->Check(vr_canvas_download(m_ctx->h, r.GetColorBuffer().data(), r.GetDepthBuffer().data()));
     r.Touch();
   }

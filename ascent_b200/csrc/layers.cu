@@ -1,0 +1,368 @@
+// layers.cu -- path B of the volume plot without lists: dense per-block ray layers.
+//
+// The reference turns every structured block's rays into a compact std::vector<VolumePartial>
+// (StructuredWrapper::render, src/libs/vtkh/rendering/VolumeRenderer.cpp:260-283, a serial
+// push_back loop), concatenates the vectors, redistributes them by pixel range over MPI
+// (vtkh_diy_partial_redistribute.hpp:58-152), std::sort's them by (pixel, depth)
+// (PartialCompositor.cpp:343), folds each pixel's run front to back (:56-95, VolumePartial.hpp:86-95),
+// gathers the result on rank 0 (vtkh_diy_partial_collect.hpp:57-141) and splats it onto the canvas
+// (partials_to_canvas, VolumeRenderer.cpp:287-391).
+//
+// A structured block contributes AT MOST ONE partial per pixel, and only inside the screen
+// rectangle its rays were generated for.  So the B200 formulation keeps each block's rays where
+// they fall: the sampler stores {rgba, exit distance} of every ray of the block's rectangle into a
+// dense "layer" (coalesced 16 + 4 byte stores, no atomics, no compaction; alpha = 0 marks a ray the
+// reference would have dropped with its alpha < 0.001 test).  Compositing is then ONE kernel: a CTA
+// owns a 32x8 pixel tile, finds the layers (of every rank) that overlap it, and each thread gathers
+// its pixel's <= depth-complexity entries -- straight out of the peers' HBM over NVLink when they
+// are remote -- orders them by (exit distance, rank, block) in registers/local memory, folds them
+// with VolumePartial::blend and stores the finished canvas pixel (into rank 0's canvas).  No
+// histogram, scan, scatter, sort or gather passes; traffic = the layer entries that are read once
+// + the canvas pixels that are written once.  Results are bit-identical to the list pipeline
+// (same entries, same order, same arithmetic), which is what tests/ check.
+//
+// Compiled with --fmad=false like the rest of the float fold.
+#include <cstdio>
+#include <cstring>
+
+#include "vr_internal.h"
+
+namespace vr
+{
+namespace
+{
+
+constexpr int kTileW = 32, kTileH = 8;           // 256 threads
+constexpr int kMaxTileLayers = 192;              // layers overlapping one tile (smem list)
+constexpr int kMaxSeg = 32;                      // entries per pixel ordered in local memory
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v)
+{
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p)
+{
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void blend(float4& a, const float4 o)
+{
+  // VolumePartial::blend, VolumePartial.hpp:86-95 (rgb in xyz, alpha in w)
+  if (a.w >= 1.f || o.w == 0.f) return;
+  const float opacity = (1.f - a.w);
+  a.x += opacity * o.x;
+  a.y += opacity * o.y;
+  a.z += opacity * o.z;
+  a.w += opacity * o.w;
+  a.w = a.w > 1.f ? 1.f : a.w;
+}
+
+struct TileLayer
+{
+  int x0, y0, x1, y1;       // rectangle, exclusive upper corner
+  int w;                    // row pitch of the layer
+  int order;                // rank * kMaxLayers + index: the (rank, domain) tie-break
+  const float4* rgba;       // entry (0,0) of the layer
+  const float* depth;
+};
+
+// COMM: flags/peers are live, only covered pixels are written (rank 0 cleared its canvas before
+// announcing); !COMM: one rank, every pixel of the frame is written (cleared or blended over).
+template <bool COMM>
+__global__ void __launch_bounds__(kTileW* kTileH) layers_fold_kernel(const __grid_constant__ LayerFoldParams P)
+{
+  extern __shared__ unsigned char smem_raw[];
+  LayerDesc* s_desc = reinterpret_cast<LayerDesc*>(smem_raw);          // all ranks' tables
+  __shared__ int s_first[kMaxCommRanks + 1];                          // table offsets per rank
+  __shared__ TileLayer s_tile[kMaxTileLayers];
+  __shared__ int s_ntile;
+  __shared__ int s_total;
+
+  if (COMM)
+  {
+    LayerFlags* my_flags = reinterpret_cast<LayerFlags*>(P.flags[P.rank]);
+    if (blockIdx.x == 0 && threadIdx.x < P.size)
+    {
+      LayerFlags* f = reinterpret_cast<LayerFlags*>(P.flags[threadIdx.x]);
+      __threadfence_system();
+      st_release_sys(&f->ready[P.rank], P.epoch);
+    }
+    if (threadIdx.x < P.size)
+      while (ld_acquire_sys(&my_flags->ready[threadIdx.x]) < P.epoch) __nanosleep(64);
+    __syncthreads();
+  }
+
+  // ---- every rank's layer table into shared memory (once per CTA)
+  if (threadIdx.x == 0)
+  {
+    int total = 0;
+    for (int r = 0; r < P.size; ++r)
+    {
+      s_first[r] = total;
+      int n = P.table[r]->n;
+      if (n > kMaxLayers) n = kMaxLayers;
+      if (total + n > P.smem_layers) n = P.smem_layers - total; // flagged on the host side
+      total += n;
+    }
+    s_first[P.size] = total;
+    s_total = total;
+  }
+  __syncthreads();
+  for (int r = 0; r < P.size; ++r)
+  {
+    const int n = s_first[r + 1] - s_first[r];
+    for (int k = threadIdx.x; k < n; k += blockDim.x) s_desc[s_first[r] + k] = P.table[r]->d[k];
+  }
+  __syncthreads();
+
+  const int tiles_x = (P.W + kTileW - 1) / kTileW, tiles_y = (P.H + kTileH - 1) / kTileH;
+  const long long n_tiles = (long long)tiles_x * tiles_y;
+  const int lx = threadIdx.x % kTileW, ly = threadIdx.x / kTileW;
+  float4* canvas = P.canvas_rgba;
+  float* cdepth = P.canvas_depth;
+
+  // tiles are dealt round-robin to the ranks, then to the CTAs of a rank
+  for (long long t = (long long)P.rank + (long long)blockIdx.x * P.size; t < n_tiles;
+       t += (long long)gridDim.x * P.size)
+  {
+    const int tx0 = (int)(t % tiles_x) * kTileW, ty0 = (int)(t / tiles_x) * kTileH;
+    if (threadIdx.x == 0) s_ntile = 0;
+    __syncthreads();
+    // ---- layers overlapping this tile
+    for (int r = 0; r < P.size; ++r)
+      for (int k = s_first[r] + threadIdx.x; k < s_first[r + 1]; k += blockDim.x)
+      {
+        const LayerDesc d = s_desc[k];
+        if (d.x0 < tx0 + kTileW && d.x0 + d.w > tx0 && d.y0 < ty0 + kTileH && d.y0 + d.h > ty0)
+        {
+          const int slot = atomicAdd(&s_ntile, 1);
+          if (slot < kMaxTileLayers)
+          {
+            TileLayer L;
+            L.x0 = d.x0; L.y0 = d.y0; L.x1 = d.x0 + d.w; L.y1 = d.y0 + d.h; L.w = d.w;
+            L.order = r * kMaxLayers + (k - s_first[r]);
+            L.rgba = P.pool_rgba[r] + d.base;
+            L.depth = P.pool_depth[r] + d.base;
+            s_tile[slot] = L;
+          }
+        }
+      }
+    __syncthreads();
+    // more overlapping layers than the tile list holds: walk the full table instead (slow, exact)
+    const bool over = s_ntile > kMaxTileLayers;
+    const int nt = over ? s_total : s_ntile;
+    auto fetch = [&](int l) -> TileLayer {
+      if (!over) return s_tile[l];
+      int r = 0;
+      while (l >= s_first[r + 1]) ++r;
+      const LayerDesc d = s_desc[l];
+      TileLayer L;
+      L.x0 = d.x0; L.y0 = d.y0; L.x1 = d.x0 + d.w; L.y1 = d.y0 + d.h; L.w = d.w;
+      L.order = r * kMaxLayers + (l - s_first[r]);
+      L.rgba = P.pool_rgba[r] + d.base;
+      L.depth = P.pool_depth[r] + d.base;
+      return L;
+    };
+
+    const int x = tx0 + lx, y = ty0 + ly;
+    if (x < P.W && y < P.H)
+    {
+      // ---- gather this pixel's entries, insertion-sorted by (exit distance, rank, block)
+      float kd[kMaxSeg];
+      int ko[kMaxSeg];
+      unsigned short kl[kMaxSeg];
+      int c = 0;
+      bool deep = false;
+      for (int l = 0; l < nt; ++l)
+      {
+        const TileLayer L = fetch(l);
+        if (x < L.x0 || x >= L.x1 || y < L.y0 || y >= L.y1) continue;
+        const size_t e = (size_t)(y - L.y0) * L.w + (x - L.x0);
+        const float alpha = L.rgba[e].w;
+        if (alpha < 0.001f) continue; // the reference's `if(alpha < 0.001f) continue;` (:270-272)
+        if (c == kMaxSeg) { deep = true; break; }
+        const float d = L.depth[e];
+        int b = c - 1;
+        while (b >= 0 && (kd[b] > d || (kd[b] == d && ko[b] > L.order)))
+        {
+          kd[b + 1] = kd[b]; ko[b + 1] = ko[b]; kl[b + 1] = kl[b];
+          --b;
+        }
+        kd[b + 1] = d; ko[b + 1] = L.order; kl[b + 1] = (unsigned short)l;
+        ++c;
+      }
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float first_depth = 0.f;
+      bool any = false;
+      if (!deep)
+      {
+        for (int a = 0; a < c; ++a)
+        {
+          const TileLayer L = fetch(kl[a]);
+          const float4 q = L.rgba[(size_t)(y - L.y0) * L.w + (x - L.x0)];
+          if (a == 0) { acc = q; first_depth = kd[0]; any = true; }
+          else blend(acc, q);
+        }
+      }
+      else
+      {
+        // more than kMaxSeg entries on this pixel: repeated selection of the next key, no storage
+        float last_d = 0.f;
+        int last_o = -1;
+        for (;;)
+        {
+          int best = -1, best_o = 0;
+          float best_d = 0.f;
+          for (int l = 0; l < nt; ++l)
+          {
+            const TileLayer L = fetch(l);
+            if (x < L.x0 || x >= L.x1 || y < L.y0 || y >= L.y1) continue;
+            const size_t e = (size_t)(y - L.y0) * L.w + (x - L.x0);
+            if (L.rgba[e].w < 0.001f) continue;
+            const float d = L.depth[e];
+            const bool after = !any || d > last_d || (d == last_d && L.order > last_o);
+            if (!after) continue;
+            if (best < 0 || d < best_d || (d == best_d && L.order < best_o)) { best = l; best_d = d; best_o = L.order; }
+          }
+          if (best < 0) break;
+          const TileLayer L = fetch(best);
+          const float4 q = L.rgba[(size_t)(y - L.y0) * L.w + (x - L.x0)];
+          if (!any) { acc = q; first_depth = best_d; any = true; }
+          else blend(acc, q);
+          last_d = best_d; last_o = best_o;
+        }
+      }
+      const size_t px = (size_t)y * P.W + x;
+      if (any)
+      {
+        vr_partial part;
+        part.pixel_id = (int)px;
+        part.depth = first_depth;
+        part.rgb[0] = acc.x; part.rgb[1] = acc.y; part.rgb[2] = acc.z;
+        part.alpha = acc.w;
+        const float4 in = (COMM || P.clear) ? make_float4(0.f, 0.f, 0.f, 0.f) : canvas[px];
+        float4 o;
+        float dimg;
+        partial_to_canvas(part, P.tp, in, o, dimg);
+        canvas[px] = o;
+        cdepth[px] = dimg;
+      }
+      else if (!COMM && P.clear)
+      {
+        canvas[px] = make_float4(0.f, 0.f, 0.f, 0.f);
+        cdepth[px] = 1.001f;
+      }
+    }
+    __syncthreads();
+  }
+
+  if (COMM)
+  {
+    // ---- last CTA out tells rank 0 that my tiles have landed
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      LayerFlags* my_flags = reinterpret_cast<LayerFlags*>(P.flags[P.rank]);
+      __threadfence_system();
+      const unsigned prev = atomicAdd(&my_flags->cta_done, 1u);
+      if (prev == gridDim.x - 1)
+      {
+        my_flags->cta_done = 0;
+        LayerFlags* root = reinterpret_cast<LayerFlags*>(P.flags[0]);
+        __threadfence_system();
+        st_release_sys(&root->done[P.rank], P.epoch);
+      }
+    }
+  }
+}
+
+__global__ void layers_wait_done_kernel(const unsigned int* done, int size, unsigned int epoch)
+{
+  if (threadIdx.x < size)
+    while (ld_acquire_sys(done + threadIdx.x) < epoch) __nanosleep(64);
+}
+
+// layers -> the reference's compact list (StructuredWrapper::render :260-283), for callers that
+// want vectors and for the parity tests: one warp-aggregated append per 32 entries
+__global__ void layers_to_partials_kernel(const LayerTable* __restrict__ table,
+                                          const float4* __restrict__ pool_rgba,
+                                          const float* __restrict__ pool_depth, int W,
+                                          vr_partial* __restrict__ out, unsigned long long* __restrict__ count,
+                                          size_t cap)
+{
+  const int lane = threadIdx.x & 31;
+  const int n = table->n;
+  for (int l = blockIdx.y; l < n; l += gridDim.y)
+  {
+    const LayerDesc d = table->d[l];
+    const size_t area = (size_t)d.w * d.h;
+    for (size_t base = (size_t)blockIdx.x * blockDim.x; base < area; base += (size_t)gridDim.x * blockDim.x)
+    {
+      const size_t e = base + threadIdx.x;
+      bool emit = false;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < area)
+      {
+        q = pool_rgba[d.base + e];
+        emit = !(q.w < 0.001f);
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, emit);
+      if (!mask) continue;
+      unsigned long long b0 = 0;
+      if (lane == 0) b0 = atomicAdd(count, (unsigned long long)__popc(mask));
+      b0 = __shfl_sync(0xffffffffu, b0, 0);
+      const unsigned long long slot = b0 + __popc(mask & ((1u << lane) - 1u));
+      if (emit && slot < cap)
+      {
+        vr_partial p;
+        const int y = d.y0 + (int)(e / d.w), x = d.x0 + (int)(e % d.w);
+        p.pixel_id = y * W + x;
+        p.depth = pool_depth[d.base + e];
+        p.rgb[0] = q.x; p.rgb[1] = q.y; p.rgb[2] = q.z;
+        p.alpha = q.w;
+        out[slot] = p;
+      }
+    }
+  }
+}
+
+} // namespace
+
+cudaError_t launch_layers_fold(const LayerFoldParams& p, bool comm, int sm_count, cudaStream_t s)
+{
+  const size_t smem = (size_t)p.smem_layers * sizeof(LayerDesc);
+  static bool attr_set = false;
+  if (!attr_set)
+  {
+    cudaFuncSetAttribute(layers_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(layers_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set = true;
+  }
+  const long long tiles = (long long)((p.W + kTileW - 1) / kTileW) * ((p.H + kTileH - 1) / kTileH);
+  long long grid = (long long)sm_count * 4;
+  const long long mine = (tiles + p.size - 1) / p.size;
+  if (grid > mine) grid = mine > 0 ? mine : 1;
+  if (comm) layers_fold_kernel<true><<<(int)grid, kTileW * kTileH, smem, s>>>(p);
+  else layers_fold_kernel<false><<<(int)grid, kTileW * kTileH, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_layers_wait_done(const unsigned int* done, int size, unsigned int epoch, cudaStream_t s)
+{
+  layers_wait_done_kernel<<<1, 32, 0, s>>>(done, size, epoch);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_layers_to_partials(const LayerTable* table, int n_layers, const float4* pool_rgba,
+                                      const float* pool_depth, int W, vr_partial* out,
+                                      unsigned long long* count, size_t cap, cudaStream_t s)
+{
+  if (n_layers <= 0) return cudaSuccess;
+  dim3 grid(64, n_layers < 64 ? n_layers : 64);
+  layers_to_partials_kernel<<<grid, 256, 0, s>>>(table, pool_rgba, pool_depth, W, out, count, cap);
+  return cudaGetLastError();
+}
+
+} // namespace vr

@@ -430,6 +430,18 @@ trace_kernel(const __grid_constant__ TraceParams P)
       }
     }
 
+    if (MODE == 3)
+    {
+      // ---------------- path B without lists: the ray's result goes to its place in the block's
+      // dense layer; alpha = 0 marks what the reference drops (alpha < 0.001, VolumeRenderer.cpp:270)
+      if (in_subset)
+      {
+        const size_t e = P.layer_base + (size_t)(j - P.sy) * P.sw + (size_t)(i - P.sx);
+        const bool keep = !(c3 < 0.001f);
+        P.layer_rgba[e] = keep ? make_float4(c0, c1, c2, c3) : make_float4(0.f, 0.f, 0.f, 0.f);
+        P.layer_depth[e] = max_distance; // rays.MaxDistance: the exit distance (:262-263)
+      }
+    }
     if (MODE == 1)
     {
       // ---------------- path B: keep rays with alpha >= 0.001 (VolumeRenderer.cpp:270-283);
@@ -470,7 +482,8 @@ cudaError_t launch_mode(const TraceParams& p, int mode, int grid, cudaStream_t s
 {
   if (mode == 0)      trace_kernel<KIND, FT, ASSOC, 0, IDX><<<grid, kThreads, 0, s>>>(p);
   else if (mode == 1) trace_kernel<KIND, FT, ASSOC, 1, IDX><<<grid, kThreads, 0, s>>>(p);
-  else                trace_kernel<KIND, FT, ASSOC, 2, IDX><<<grid, kThreads, 0, s>>>(p);
+  else if (mode == 2) trace_kernel<KIND, FT, ASSOC, 2, IDX><<<grid, kThreads, 0, s>>>(p);
+  else                trace_kernel<KIND, FT, ASSOC, 3, IDX><<<grid, kThreads, 0, s>>>(p);
   return cudaGetLastError();
 }
 template <int KIND, typename FT, int ASSOC>

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -123,6 +124,13 @@ extern "C" void vr_destroy(vr_ctx* ctx)
     cudaFree(ctx->res_rgba);
     cudaFree(ctx->res_depth);
   }
+  if (!ctx->layers_in_arena)
+  {
+    cudaFree(ctx->ltab);
+    cudaFree(ctx->lpool_rgba);
+    cudaFree(ctx->lpool_depth);
+  }
+  delete ctx->ltab_host;
   cudaFree(ctx->partials);
   cudaFree(ctx->partials_tmp);
   cudaFree(ctx->partial_count);
@@ -652,6 +660,147 @@ extern "C" vr_status vr_render_partials(vr_ctx* ctx, int block_id, const vr_came
 }
 
 extern "C" void vr_free(void* p) { std::free(p); }
+
+// ================================================================= ray layers (path B without lists)
+namespace vr { vr_status comm_bind_layers(vr_ctx* ctx); }
+
+static vr_status ensure_layer_pool(vr_ctx* ctx, size_t need)
+{
+  if (need <= ctx->lpool_cap) return VR_OK;
+  REQUIRE(!ctx->layers_in_arena, "ray layers need %zu entries this frame but max_partials = %zu (vr_comm_init)",
+          need, ctx->lpool_cap);
+  const size_t cap = std::max(need, ctx->lpool_cap * 2);
+  float4* nr = nullptr;
+  float* nd = nullptr;
+  CK(cudaMalloc(&nr, cap * sizeof(float4)));
+  CK(cudaMalloc(&nd, cap * sizeof(float)));
+  if (ctx->lpool_used)
+  {
+    // layers traced earlier in this frame move along (rare: only while the pool is still growing)
+    CK(cudaMemcpyAsync(nr, ctx->lpool_rgba, ctx->lpool_used * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(nd, ctx->lpool_depth, ctx->lpool_used * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(ctx->lpool_rgba);
+  cudaFree(ctx->lpool_depth);
+  ctx->lpool_rgba = nr;
+  ctx->lpool_depth = nd;
+  ctx->lpool_cap = cap;
+  return VR_OK;
+}
+
+extern "C" vr_status vr_layers_begin(vr_ctx* ctx, int width, int height)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(width > 0 && height > 0 && (long long)width * height < (1ll << 31), "bad image size");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->ltab_host) ctx->ltab_host = new LayerTable(); // pageable on purpose: async copies stage it
+  if (ctx->comm.on && ctx->comm.max_partials)
+  {
+    vr_status st = comm_bind_layers(ctx);
+    if (st != VR_OK) return st;
+  }
+  else if (!ctx->ltab)
+    CK(cudaMalloc(&ctx->ltab, sizeof(LayerTable)));
+  ctx->ltab_host->n = 0;
+  ctx->lpool_used = 0;
+  ctx->lW = width;
+  ctx->lH = height;
+  return VR_OK;
+}
+
+extern "C" vr_status vr_trace_to_layer(vr_ctx* ctx, int block_id, const vr_camera* cam, float sample_dist,
+                                       float range_min, float range_max, int use_canvas_depth)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(ctx->lW > 0, "vr_trace_to_layer: call vr_layers_begin first");
+  REQUIRE(!use_canvas_depth || (ctx->W == ctx->lW && ctx->H == ctx->lH),
+          "vr_trace_to_layer: canvas depth requested but canvas size differs");
+  CK(cudaSetDevice(ctx->device));
+  TraceParams p;
+  vr_status st = fill_trace_params(ctx, block_id, cam, sample_dist, range_min, range_max, use_canvas_depth,
+                                   ctx->lW, ctx->lH, p);
+  if (st != VR_OK) return st;
+  if (p.sw <= 0 || p.sh <= 0) return VR_OK; // block off screen: no rays, no layer
+  LayerTable& T = *ctx->ltab_host;
+  REQUIRE(T.n < kMaxLayers, "vr_trace_to_layer: more than %d layers in one frame", kMaxLayers);
+  const size_t area = (size_t)p.sw * p.sh;
+  // keep 16-byte alignment of every layer's first float4/float4-group
+  const size_t base = (ctx->lpool_used + 3) & ~(size_t)3;
+  st = ensure_layer_pool(ctx, base + area);
+  if (st != VR_OK) return st;
+  p.layer_rgba = ctx->lpool_rgba;
+  p.layer_depth = ctx->lpool_depth;
+  p.layer_base = base;
+  CK(launch_trace(p, 3, ctx->sm_count, ctx->stream));
+  ctx->launches++;
+  LayerDesc& d = T.d[T.n++];
+  d.x0 = p.sx; d.y0 = p.sy; d.w = p.sw; d.h = p.sh;
+  d.base = base;
+  ctx->lpool_used = base + area;
+  return VR_OK;
+}
+
+static vr_status upload_layer_table(vr_ctx* ctx)
+{
+  const LayerTable& T = *ctx->ltab_host;
+  const size_t bytes = offsetof(LayerTable, d) + (size_t)T.n * sizeof(LayerDesc);
+  CK(cudaMemcpyAsync(ctx->ltab, &T, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return VR_OK;
+}
+namespace vr { vr_status upload_layer_table_pub(vr_ctx* ctx) { return upload_layer_table(ctx); } }
+
+extern "C" vr_status vr_layers_composite_to_canvas(vr_ctx* ctx, const vr_camera* cam, int canvas_is_clear)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(cam, "vr_layers_composite_to_canvas: camera is NULL");
+  REQUIRE(ctx->lW > 0, "vr_layers_composite_to_canvas: call vr_layers_begin first");
+  CK(cudaSetDevice(ctx->device));
+  vr_status st;
+  if (canvas_is_clear)
+  {
+    st = ensure_frame(ctx, ctx->lW, ctx->lH);
+    if (st != VR_OK) return st;
+  }
+  REQUIRE(ctx->W == ctx->lW && ctx->H == ctx->lH, "vr_layers_composite_to_canvas: canvas (%dx%d) and layer frame "
+          "(%dx%d) differ", ctx->W, ctx->H, ctx->lW, ctx->lH);
+  st = upload_layer_table(ctx);
+  if (st != VR_OK) return st;
+  LayerFoldParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.rank = 0;
+  p.size = 1;
+  p.W = ctx->lW;
+  p.H = ctx->lH;
+  p.clear = canvas_is_clear ? 1 : 0;
+  p.smem_layers = std::max(ctx->ltab_host->n, 1);
+  p.table[0] = ctx->ltab;
+  p.pool_rgba[0] = ctx->lpool_rgba;
+  p.pool_depth[0] = ctx->lpool_depth;
+  p.canvas_rgba = ctx->canvas_rgba;
+  p.canvas_depth = ctx->canvas_depth;
+  fill_to_canvas_params(cam, ctx->lW, ctx->lH, p.tp);
+  CK(launch_layers_fold(p, false, ctx->sm_count, ctx->stream));
+  ctx->launches++;
+  return VR_OK;
+}
+
+extern "C" vr_status vr_layers_to_partials(vr_ctx* ctx)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(ctx->lW > 0, "vr_layers_to_partials: call vr_layers_begin first");
+  vr_status st = vr_partials_begin(ctx, ctx->lW, ctx->lH);
+  if (st != VR_OK) return st;
+  ctx->n_partials_host = ctx->lpool_used;
+  st = ensure_partials(ctx, std::max<size_t>(ctx->lpool_used, 1));
+  if (st != VR_OK) return st;
+  st = upload_layer_table(ctx);
+  if (st != VR_OK) return st;
+  CK(launch_layers_to_partials(ctx->ltab, ctx->ltab_host->n, ctx->lpool_rgba, ctx->lpool_depth, ctx->lW,
+                               ctx->partials, ctx->partial_count, ctx->partial_cap, ctx->stream));
+  ctx->launches++;
+  return VR_OK;
+}
 
 // ================================================================= image compositing
 extern "C" vr_status vr_image_from_canvas(vr_ctx* ctx)

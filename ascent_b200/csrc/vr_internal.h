@@ -52,6 +52,10 @@ struct TraceParams
   float pv[16];
   float4* canvas_rgba;
   float* canvas_depth;
+  // dense layer store (path B without lists, mode 3)
+  float4* layer_rgba;
+  float* layer_depth;
+  unsigned long long layer_base;
   // partial emission (path B)
   vr_partial* partials;
   unsigned long long* partial_count;
@@ -71,6 +75,8 @@ struct Block
   double bounds[6];
 };
 
+struct LayerTable; // layers.cu section below
+
 struct Comm
 {
   bool on = false;
@@ -82,6 +88,7 @@ struct Comm
   unsigned char** peer_dev = nullptr;           // device copy of the pointer table
   unsigned int epoch = 0;                       // image path frames composited so far
   unsigned int pepoch = 0;                      // partial path frames
+  unsigned int lepoch = 0;                      // layer path frames
   int* minmax_dev = nullptr;                    // {min,max} pixel id of the current list
 };
 
@@ -136,6 +143,15 @@ struct vr_ctx
   size_t scratch_px = 0, scratch_parts = 0, scratch_blocks = 0;
   vr_partial* partials_tmp = nullptr;
   size_t partial_tmp_cap = 0;
+
+  // ray layers of the current frame
+  vr::LayerTable* ltab_host = nullptr;   // pinned host copy (filled as layers are traced)
+  vr::LayerTable* ltab = nullptr;        // device table (own allocation, or the arena's by parity)
+  float4* lpool_rgba = nullptr;          // layer pool (own allocation or arena)
+  float* lpool_depth = nullptr;
+  size_t lpool_cap = 0, lpool_used = 0;
+  bool layers_in_arena = false;
+  int lW = 0, lH = 0;
 
   unsigned int* tile_counter = nullptr;
   unsigned long long* sample_counter = nullptr;
@@ -226,6 +242,48 @@ int launch_partials_pixel_sort(const vr_partial* in, const unsigned long long* c
 cudaError_t launch_partials_to_canvas(const vr_partial* p, const unsigned long long* count_dev,
                                       size_t max_n, const ToCanvasParams& tp, float4* canvas,
                                       float* cdepth, cudaStream_t s);
+
+// layers.cu -- dense per-block ray layers (path B without lists)
+constexpr int kMaxCommRanks = 16;
+constexpr int kMaxLayers = 1024;      // per rank and frame
+constexpr int kMaxSmemLayers = 2048;  // all ranks' tables together (shared memory of the fold kernel)
+struct LayerDesc
+{
+  int x0, y0, w, h;            // the block's ray rectangle on screen (K1 "subset")
+  unsigned long long base;     // first entry in the rank's layer pool
+};
+struct LayerTable
+{
+  int n;
+  int pad[3];
+  LayerDesc d[kMaxLayers];
+};
+struct LayerFlags
+{
+  unsigned int ready[kMaxCommRanks];
+  unsigned int done[kMaxCommRanks];
+  unsigned int cta_done;
+};
+struct LayerFoldParams
+{
+  int rank, size;
+  unsigned int epoch;
+  int W, H;
+  int clear;        // single rank: treat the canvas as cleared (every pixel written)
+  int smem_layers;  // capacity of the shared-memory table copy
+  const LayerTable* table[kMaxCommRanks];
+  const float4* pool_rgba[kMaxCommRanks];
+  const float* pool_depth[kMaxCommRanks];
+  unsigned char* flags[kMaxCommRanks];
+  float4* canvas_rgba; // where finished pixels go (rank 0's canvas)
+  float* canvas_depth;
+  ToCanvasParams tp;
+};
+cudaError_t launch_layers_fold(const LayerFoldParams& p, bool comm, int sm_count, cudaStream_t s);
+cudaError_t launch_layers_wait_done(const unsigned int* done, int size, unsigned int epoch, cudaStream_t s);
+cudaError_t launch_layers_to_partials(const LayerTable* table, int n_layers, const float4* pool_rgba,
+                                      const float* pool_depth, int W, vr_partial* out,
+                                      unsigned long long* count, size_t cap, cudaStream_t s);
 
 // comm.cu
 struct FoldP2PParams

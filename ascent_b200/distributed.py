@@ -150,7 +150,7 @@ def run_bench(args, wl, bench):
     if not path_a:
         for i in mine:
             s = _lib.find_subset(cam, W, H, sp["bounds"][i])
-            max_partials += s[2] * s[3]
+            max_partials += s[2] * s[3] + 4  # layers start on 4-entry boundaries
     connect(ctx, dist, W * H, max_partials)
     vis_all, _ = global_visibility_order([sp["bounds"][i] for i in mine], cam, dist)
     vis_rank = np.ascontiguousarray(vis_all[:, 0], np.int32)  # path A: one domain per rank
@@ -160,17 +160,18 @@ def run_bench(args, wl, bench):
             # Canvas::Clear + RenderCells + Image::Init in one launch, straight into the exchange arena
             ctx.trace_to_image(mine[0], cam, W, H, sp["sample_dist"], rmin, rmax, no_clear=True)
         else:
-            ctx.partials_begin(W, H)
+            ctx.layers_begin(W, H)
             for i in mine:
-                ctx.trace_to_partials(i, cam, sp["sample_dist"], rmin, rmax, False)
+                ctx.trace_to_layer(i, cam, sp["sample_dist"], rmin, rmax, False)
 
     def composite():
         if path_a:
             ctx.comm_composite_images_to_canvas(vis_rank)
         else:
-            # redistribute + sort + fold + collect + partials_to_canvas: per rank one pixel-sort
-            # pipeline and ONE P2P kernel that stores finished pixels into rank 0's canvas
-            ctx.comm_composite_partials_to_canvas(cam)
+            # redistribute + sort + fold + collect + partials_to_canvas: ONE P2P kernel per rank that
+            # gathers each owned pixel's entries from every rank's ray layers over NVLink, folds
+            # them in depth order and stores finished pixels into rank 0's canvas
+            ctx.comm_layers_composite_to_canvas(cam)
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
@@ -253,8 +254,7 @@ def run_bench(args, wl, bench):
             pulled = layer_px / world * (world - 1) / world * 8.0   # RGBA8 + depth of the covering layers
             pushed = covered * (world - 1) / world * 8.0            # folded pixels stored into rank 0
         else:
-            pulled = float(tsum[5]) / world * 24.0 * (world - 1) / world + \
-                W * H / world * 4.0 * (world - 1)                   # partial runs + per-pixel end offsets
+            pulled = layer_px / world * (world - 1) / world * 20.0  # layer entries (rgba + depth)
             pushed = covered * (world - 1) / world * 20.0           # finished canvas pixels into rank 0
         nv_bytes = pulled + pushed
         line = {"metric": "volume_render_mrays_per_s", "value": W * H / (ms * 1e-3) / 1e6, "unit": "Mrays/s",
@@ -263,7 +263,7 @@ def run_bench(args, wl, bench):
                 "data": "synthetic",
                 "config": {"workload": wl["name"], "image": [W, H], "samples": bench.SAMPLES,
                            "path": "A (uint8 image, P2P direct-send fold)" if path_a else
-                                   "B (float partials, P2P pull+merge+fold)",
+                                   "B (float partials as dense ray layers, P2P gather+fold)",
                            "blocks_per_gpu": len(mine),
                            "l2": "inputs (%.0f MB of field per GPU) larger than the 126 MB L2" % (
                                nvox * 4 * len(mine) / 1e6)},
@@ -289,6 +289,7 @@ def run_bench(args, wl, bench):
 
 def _count_local_partials(ctx, render):
     render()
+    ctx.layers_to_partials()
     return ctx.partials_count()
 
 

@@ -217,15 +217,16 @@ def run_single(args, wl):
             if ev:
                 ev[1].record(stream)
         else:
-            ctx.partials_begin(W, H)
+            # RenderMultipleDomainsPerRank on dense ray layers: one sampler launch per block, then
+            # PartialCompositor::composite + partials_to_canvas over a cleared canvas in ONE kernel
+            ctx.layers_begin(W, H)
             if ev:
                 ev[0].record(stream)
             for i in range(len(blocks)):
-                ctx.trace_to_partials(i, cam, sp["sample_dist"], rmin, rmax, False)
+                ctx.trace_to_layer(i, cam, sp["sample_dist"], rmin, rmax, False)
             if ev:
                 ev[1].record(stream)
-            # PartialCompositor::composite + partials_to_canvas over a cleared canvas, fused
-            ctx.partials_composite_to_canvas(cam, canvas_is_clear=True)
+            ctx.layers_composite_to_canvas(cam, canvas_is_clear=True)
 
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
@@ -302,7 +303,7 @@ def run_single(args, wl):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "image": [W, H], "samples": SAMPLES,
-                       "path": "B (partials)" if multi else "A (image)",
+                       "path": "B (ray layers)" if multi else "A (image)",
                        "l2": "inputs (%.0f MB field) larger than the 126 MB L2" % (nvox * 4 * len(blocks) / 1e6)},
             "frames_per_s": 1e3 / ms, "composite_ms_per_frame": ms - trace_ms,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}

@@ -158,6 +158,24 @@ VR_API vr_status vr_render_partials(vr_ctx* ctx, int block_id, const vr_camera* 
                                     size_t* n);
 VR_API void vr_free(void* p);
 
+/* ------------------------------------------------------------------ (2'+4') path B without lists
+ * Same result as (2) + (4) for structured blocks, a different data structure: a block adds at most
+ * one partial per pixel and only inside its screen rectangle, so every block's rays are kept as a
+ * dense "layer" {rgba, exit distance} over that rectangle (alpha = 0 where the reference's
+ * alpha < 0.001 test drops the ray) and composited by ONE kernel that gathers, per pixel, the
+ * entries of the layers covering it, orders them by (exit distance, rank, block), folds them with
+ * VolumePartial::blend and writes the canvas pixel (partials_to_canvas).  No compaction, sort,
+ * scan or gather passes.                                                                        */
+VR_API vr_status vr_layers_begin(vr_ctx* ctx, int width, int height);
+VR_API vr_status vr_trace_to_layer(vr_ctx* ctx, int block_id, const vr_camera* cam, float sample_dist,
+                                   float range_min, float range_max, int use_canvas_depth);
+/* One rank: PartialCompositor::composite + partials_to_canvas (VolumeRenderer.cpp:580-595).
+ * canvas_is_clear as for vr_partials_composite_to_canvas.                                       */
+VR_API vr_status vr_layers_composite_to_canvas(vr_ctx* ctx, const vr_camera* cam, int canvas_is_clear);
+/* The layers as the reference's compact list (what StructuredWrapper::render returns): replaces
+ * the context's partial list; order unspecified.                                                */
+VR_API vr_status vr_layers_to_partials(vr_ctx* ctx);
+
 /* ------------------------------------------------------------------ (3) image compositing
  * Image::Init (Image.hpp:80-113): quantise the device canvas to RGBA8 (truncation) + depth
  * (negative -> |d|) into the context's exchange image.                                         */
@@ -213,7 +231,8 @@ VR_API vr_status vr_composite_partials(vr_ctx* ctx, const vr_partial* in, size_t
  * harness) and maps its peers' arenas; after that images/partials move GPU-to-GPU over NVLink
  * inside the compositing kernels themselves (direct-send: DirectSendCompositor.cpp:121-181,
  * vtkh_diy_partial_redistribute.hpp:58-152) -- no host staging, no MPI in the data path.
- * max_pixels / max_partials size the arena (largest frame, longest per-rank partial list; 0
+ * max_pixels / max_partials size the arena (largest frame; longest per-rank partial list, resp.
+ * the sum over a rank's blocks of (screen-rectangle area + 4) when ray layers are used; 0
  * partials = image path only) and MUST be identical on every rank: a rank addresses its peers'
  * arenas with its own layout (vr_comm_connect checks and fails otherwise).                     */
 #define VR_IPC_HANDLE_BYTES 64
@@ -238,6 +257,11 @@ VR_API vr_status vr_comm_composite_partials(vr_ctx* ctx);
  * of a pixel stores the finished canvas pixel straight into rank 0's canvas (20 B per covered pixel
  * over NVLink; no list, no gather).  On rank 0 the context's canvas holds the final image.       */
 VR_API vr_status vr_comm_composite_partials_to_canvas(vr_ctx* ctx, const vr_camera* cam);
+/* Path B on layers, collective, frame starts from a cleared canvas: every rank owns a round-robin
+ * share of 32x8 pixel tiles, pulls the covering layers' entries out of every rank's arena over
+ * NVLink, folds and stores finished pixels into rank 0's canvas.  vr_layers_begin must have been
+ * called after vr_comm_connect (the layers then live in the exchange arena).                     */
+VR_API vr_status vr_comm_layers_composite_to_canvas(vr_ctx* ctx, const vr_camera* cam);
 /* Device pointers into this rank's arena for transports that move the bytes themselves
  * (NCCL send/recv baseline in the harness).                                                    */
 VR_API vr_status vr_image_ptrs(vr_ctx* ctx, void** rgba8_dev, void** depth_dev);

@@ -84,22 +84,31 @@ def gpu_checks(rank, world):
         for i in mine:
             ctx.block_from_domain(i, sc["doms"][i])
         D.connect(ctx, dist, W * H, W * H * len(mine))
-        for rep in range(3):  # several frames: epoch parity / double buffering, moving camera
+        for rep in range(5):  # several frames: epoch parity / double buffering, moving camera
             cam = sc["cam"]
             if rep:
                 O.camera_azimuth(cam, 7.0)
-            ctx.partials_begin(W, H)
-            for i in mine:
-                ctx.trace_to_partials(i, cam, sc["sample_dist"], rmin, rmax, False)
-            fused = rep == 1   # pixels stored straight into rank 0's canvas, no list
-            if fused:
+            layers = rep >= 3  # dense ray layers instead of lists
+            fused = rep == 1 or layers  # pixels stored straight into rank 0's canvas, no list
+            if layers:
+                ctx.layers_begin(W, H)
+                for i in mine:
+                    ctx.trace_to_layer(i, cam, sc["sample_dist"], rmin, rmax, False)
+                ctx.comm_layers_composite_to_canvas(cam)
+            else:
+                ctx.partials_begin(W, H)
+                for i in mine:
+                    ctx.trace_to_partials(i, cam, sc["sample_dist"], rmin, rmax, False)
+            if layers:
+                pass
+            elif fused:
                 ctx.comm_composite_partials_to_canvas(cam)
             else:
                 if rank == 0:
                     ctx.canvas_clear(W, H)
                 ctx.comm_composite_partials()
             if rank == 0:
-                got = ctx.partials_download()
+                got = ctx.partials_download() if not layers else np.zeros(0, O.PARTIAL_DTYPE)
                 if not fused:
                     ctx.partials_to_canvas(cam)
                 rgba, depth = ctx.canvas_download(W, H)
@@ -119,7 +128,7 @@ def gpu_checks(rank, world):
                 assert np.array_equal(rgba, o_rgba), "path B canvas differs (rep %d)" % rep
                 cov = o_rgba[:, 3] > 0
                 assert np.array_equal(depth[cov], o_depth[cov]) and cov.sum() > 1000
-            else:
+            elif not layers:
                 assert ctx.partials_count() == 0  # root-only result
             dist.barrier()
         for i in mine:

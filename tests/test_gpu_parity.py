@@ -347,6 +347,103 @@ def test_fused_partial_composite_to_canvas(ctx, clear):
     assert p_a.tobytes() == p_b.tobytes() and p_a.size > 1000
 
 
+# ------------------------------------------------------------------ path B on dense ray layers
+def layer_frame(ctx, doms, cam, W, H, sd, rmin, rmax):
+    ctx.layers_begin(W, H)
+    for i in range(len(doms)):
+        ctx.trace_to_layer(i, cam, sd, rmin, rmax, False)
+
+
+@pytest.mark.parametrize("n_block,per_axis,az,res", [(12, 2, 0.0, (240, 200)), (9, 3, 37.0, (333, 250)),
+                                                     (6, 4, -120.0, (160, 90))])
+def test_layers_equal_list_pipeline(ctx, n_block, per_axis, az, res):
+    """vr_trace_to_layer + vr_layers_composite_to_canvas against the list pipeline and the oracle:
+    same partials (as a set), same canvas, bit for bit."""
+    doms = datasets.braid_uniform_blocks(n_block, per_axis, dtype=np.float32)
+    gb = datasets.union_bounds([datasets.domain_bounds(d) for d in doms])
+    W, H = res
+    cam = O.camera_reset_to_bounds(gb)
+    O.camera_azimuth(cam, az)
+    O.camera_elevation(cam, az / 4.0)
+    sc = dict(doms=doms, cam=cam, W=W, H=H,
+              lut=color_table.parse_color_table(scenes.RAMP_TF).corrected_opacity(100).lut(),
+              sample_dist=O.sample_distance(gb, 100))
+    sc["rmin"], sc["rmax"] = scenes.field_range(doms)
+    ctx.set_tf(sc["lut"])
+    for i, d in enumerate(doms):
+        ctx.block_from_domain(i, d)
+    # the reference's lists
+    ctx.partials_begin(W, H)
+    for i in range(len(doms)):
+        ctx.trace_to_partials(i, cam, sc["sample_dist"], sc["rmin"], sc["rmax"], False)
+    lst = np.sort(ctx.partials_download(), order=["pixel_id", "depth"])
+    # layers -> list
+    layer_frame(ctx, doms, cam, W, H, sc["sample_dist"], sc["rmin"], sc["rmax"])
+    ctx.layers_to_partials()
+    lay = np.sort(ctx.partials_download(), order=["pixel_id", "depth"])
+    assert lay.size == lst.size > 1000
+    assert np.array_equal(lay["pixel_id"], lst["pixel_id"]) and np.array_equal(lay["depth"], lst["depth"])
+    assert np.array_equal(np.sort(lay.view(np.uint8).reshape(-1, 24), axis=0),
+                          np.sort(lst.view(np.uint8).reshape(-1, 24), axis=0))
+    # layers -> canvas, cleared and over existing colours
+    ref_partials, ref_rgba, ref_depth = scenes.oracle_path_b(sc)
+    ctx.canvas_upload(W, H, np.full((H * W, 4), 9., np.float32), np.full(H * W, 9., np.float32))  # poison
+    ctx.layers_composite_to_canvas(cam, canvas_is_clear=True)
+    rgba, depth = ctx.canvas_download(W, H)
+    assert np.array_equal(rgba, ref_rgba)
+    cov = ref_rgba[:, 3] > 0
+    assert np.array_equal(depth[cov], ref_depth[cov]) and (depth[~cov] == np.float32(1.001)).all()
+    rng = np.random.default_rng(2)
+    rgba0 = rng.random((H * W, 4), dtype=np.float32)
+    depth0 = np.full(H * W, 1.001, np.float32)
+    o_rgba, o_depth = rgba0.copy(), depth0.copy()
+    O.partials_to_canvas(ref_partials, cam, W, H, o_rgba, o_depth)
+    ctx.canvas_upload(W, H, rgba0, depth0)
+    layer_frame(ctx, doms, cam, W, H, sc["sample_dist"], sc["rmin"], sc["rmax"])
+    ctx.layers_composite_to_canvas(cam, canvas_is_clear=False)
+    rgba, depth = ctx.canvas_download(W, H)
+    assert np.array_equal(rgba, o_rgba) and np.array_equal(depth[cov], o_depth[cov])
+    for i in range(len(doms)):
+        ctx.block_free(i)
+
+
+@pytest.mark.parametrize("n_slabs", [40, 200])
+def test_layers_deep_pixels(ctx, n_slabs):
+    """more entries per pixel than the in-register ordering holds (32) and more layers over one
+    tile than the tile list holds (192): the exact fallbacks."""
+    nx = 6
+    doms = []
+    z = np.linspace(-10.0, 10.0, n_slabs + 1).astype(np.float32)
+    rng = np.random.default_rng(4)
+    for k in range(n_slabs):
+        sp = [20.0 / (nx - 1), 20.0 / (nx - 1), float(z[k + 1] - z[k])]
+        doms.append(dict(kind="uniform", dims=(nx, nx, 2), origin=[-10., -10., float(z[k])], spacing=sp,
+                         field=rng.random(nx * nx * 2, dtype=np.float32) * 0.3 + 0.2, assoc="point"))
+    gb = datasets.union_bounds([datasets.domain_bounds(d) for d in doms])
+    W, H = 64, 40
+    cam = O.camera_reset_to_bounds(gb)
+    O.camera_azimuth(cam, 3.0)
+    sc = dict(doms=doms, cam=cam, W=W, H=H,
+              lut=color_table.parse_color_table(scenes.RAMP_TF).corrected_opacity(400).lut(),
+              sample_dist=O.sample_distance(gb, 400), rmin=0.0, rmax=1.0)
+    ref_partials, ref_rgba, ref_depth = scenes.oracle_path_b(sc)
+    ctx.set_tf(sc["lut"])
+    for i, d in enumerate(doms):
+        ctx.block_from_domain(1000 + i, d)
+    ctx.layers_begin(W, H)
+    for i in range(len(doms)):
+        ctx.trace_to_layer(1000 + i, cam, sc["sample_dist"], 0.0, 1.0, False)
+    ctx.layers_composite_to_canvas(cam, canvas_is_clear=True)
+    rgba, depth = ctx.canvas_download(W, H)
+    for i in range(len(doms)):
+        ctx.block_free(1000 + i)
+    per_px = np.bincount(np.concatenate([O.render_partials(scenes.oracle_block(d), cam, W, H, sc["lut"],
+                                                           sc["sample_dist"], 0.0, 1.0, ref_depth * 0 + 1.001)["pixel_id"]
+                                         for d in doms]), minlength=W * H)
+    assert per_px.max() > 32
+    assert np.array_equal(rgba, ref_rgba)
+
+
 def test_deep_pixels_local_and_global_sort(ctx):
     """segments longer than the in-register sort limit (32) take the in-place global path"""
     rng = np.random.default_rng(9)
