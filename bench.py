@@ -95,6 +95,18 @@ def workload_c3():
                 n_block=512, per_axis=2, W=3840, H=2160, key="c3")
 
 
+def workload_c4():
+    return dict(name="c4: braid rectilinear 768^3 f32 (axes warped, power 1.5), 64-view cinema orbit "
+                     "(phi=8, theta=8), 1024x1024, samples=100; one step = all 64 views",
+                n_block=768, per_axis=1, W=1024, H=1024, key="c4", rectilinear=True, views=64)
+
+
+def workload_c5():
+    return dict(name="c5: 512 uniform domains of 128^3 f32 (global 1017^3), 4096x4096, default camera, "
+                     "samples=100, partial compositing (ray layers)",
+                n_block=128, per_axis=8, W=4096, H=4096, key="c5")
+
+
 def block_layout(wl):
     """origin/spacing/start index of every block of the workload (same as
     ascent_b200.datasets.braid_uniform_blocks)."""
@@ -119,8 +131,11 @@ def scene_params(wl, blocks, rng_minmax):
     gb = datasets.union_bounds(bl)
     cam = camera.Camera()
     cam.reset_to_bounds(gb)
+    cams = None
+    if wl.get("views"):
+        cams = [c.to_struct() for c in camera.cinema_cameras(gb, *camera.cinema_angles(8, 8))]
     lut = color_table.parse_color_table(RAMP_TF).corrected_opacity(SAMPLES).lut()
-    return dict(bounds=bl, gb=gb, cam=cam.to_struct(), lut=lut,
+    return dict(bounds=bl, gb=gb, cam=cam.to_struct(), cams=cams, lut=lut,
                 sample_dist=_lib.sample_distance(gb, SAMPLES), rmin=rng_minmax[0], rmax=rng_minmax[1])
 
 
@@ -202,18 +217,26 @@ def run_single(args, wl):
     sp = scene_params(wl, blocks, (rmin, rmax))
     ctx.set_tf(sp["lut"])
     for i, b in enumerate(blocks):
-        ctx.block_uniform(i, b["dims"], b["origin"], b["spacing"], None, device_ptr=fields[i].data_ptr(),
-                          dtype=_lib.VR_F32)
+        if wl.get("rectilinear"):
+            from ascent_b200 import datasets
+            axes = [datasets.warp_axis(n, 1.5) for n in b["dims"]]
+            ctx.block_rectilinear(i, b["dims"], axes, None, device_ptr=fields[i].data_ptr(), dtype=_lib.VR_F32)
+        else:
+            ctx.block_uniform(i, b["dims"], b["origin"], b["spacing"], None, device_ptr=fields[i].data_ptr(),
+                              dtype=_lib.VR_F32)
     cam = sp["cam"]
     multi = len(blocks) > 1
+    views = sp["cams"] or [cam]
 
     def frame(ev=None):
         if not multi:
             # RenderOneDomainPerRank on a cleared canvas: Canvas::Clear + RenderCells + Image::Init +
-            # ImageToCanvas in one launch (vr_trace_to_image)
+            # ImageToCanvas in one launch (vr_trace_to_image); the cinema workload renders all its
+            # views back to back (the reference batches <= 10 renders per Update, Scene.cpp:133-149)
             if ev:
                 ev[0].record(stream)
-            ctx.trace_to_image(0, cam, W, H, sp["sample_dist"], rmin, rmax, write_canvas=True)
+            for v in views:
+                ctx.trace_to_image(0, v, W, H, sp["sample_dist"], rmin, rmax, write_canvas=True)
             if ev:
                 ev[1].record(stream)
         else:
@@ -249,7 +272,7 @@ def run_single(args, wl):
         total_ms = t_begin.elapsed_time(t_end)
         trace_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
     ms = total_ms / args.steps
-    value = W * H / (ms * 1e-3) / 1e6
+    value = W * H * len(views) / (ms * 1e-3) / 1e6
 
     # ---- e2e: host buffers through the ABI a vtk-h caller uses, H2D + D2H inside the timed region
     e2e = None
@@ -258,14 +281,21 @@ def run_single(args, wl):
         host_field.copy_(fields[0])
         rgba_h = torch.zeros(H * W * 4, dtype=torch.float32, pin_memory=True)
         depth_h = torch.full((H * W,), 1.001, dtype=torch.float32, pin_memory=True)
-        hf, hr, hd = host_field.numpy(), rgba_h.numpy(), depth_h.numpy()
+        hf = host_field.numpy()
+        hr, hd = rgba_h.numpy().reshape(-1, 4), depth_h.numpy()
         b = blocks[0]
 
         def e2e_frame():
-            hr.fill(0.0)
-            hd.fill(1.001)
-            ctx.block_uniform(100, b["dims"], b["origin"], b["spacing"], hf)    # publish (H2D)
-            ctx.render_image(100, cam, W, H, sp["sample_dist"], rmin, rmax, hr, hd)  # canvas in/out
+            # publish: the simulation's field (pinned host memory) -> device, every step
+            if wl.get("rectilinear"):
+                ctx.block_rectilinear(100, b["dims"], axes, hf)
+            else:
+                ctx.block_uniform(100, b["dims"], b["origin"], b["spacing"], hf)
+            # the volume-only scene of the config: the frame starts from a cleared canvas, so the
+            # whole per-rank body is one launch; the result comes back as the float canvas
+            for v in views:
+                ctx.trace_to_image(100, v, W, H, sp["sample_dist"], rmin, rmax, write_canvas=True)
+                ctx.canvas_download(W, H, hr, hd)
         for _ in range(2):
             e2e_frame()
         t0 = time.perf_counter()
@@ -273,9 +303,20 @@ def run_single(args, wl):
         for _ in range(n_e2e):
             e2e_frame()
         dt = (time.perf_counter() - t0) / n_e2e
-        e2e = {"value": W * H / dt / 1e6, "unit": "Mrays/s", "ms_per_step": dt * 1e3,
-               "h2d_bytes_per_step": nvox * 4 + W * H * 20, "d2h_bytes_per_step": W * H * 20,
-               "what": "vr_block_uniform(host field) + vr_render_image(host canvas in/out) per step"}
+        # the same frame through the canvas-in/canvas-out form vtk-h's RenderCells seam needs when
+        # opaque geometry is already on the canvas (upload + K2 depth clamp + blend over + download)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            hr.fill(0.0)
+            hd.fill(1.001)
+            ctx.render_image(100, cam, W, H, sp["sample_dist"], rmin, rmax, hr, hd)
+        dt_inout = (time.perf_counter() - t0) / 3
+        e2e = {"value": W * H * len(views) / dt / 1e6, "unit": "Mrays/s", "ms_per_step": dt * 1e3,
+               "h2d_bytes_per_step": nvox * 4, "d2h_bytes_per_step": W * H * 20 * len(views),
+               "h2d_gbs_if_copy_bound": nvox * 4 / dt / 1e9,
+               "what": "vr_block_uniform(pinned host field) + vr_trace_to_image + vr_canvas_download(host "
+                       "canvas) per view; bound by the PCIe upload of the field",
+               "render_image_canvas_inout_ms": dt_inout * 1e3}
         ctx.block_free(100)
 
     # ---- roofline of the dominant kernel (trace), algorithmic bytes per launch
@@ -312,14 +353,22 @@ def run_single(args, wl):
 
 
 def cpu_baseline_sample(wl, blocks, fields, sp, rmin, rmax):
+    """The oracle port of the reference's CPU path on the host cores, bounded to ~10 s: whole frames
+    of the same workload (for the 64-view cinema workload: as many views as fit the budget)."""
+    from ascent_b200 import datasets
     from oracle import oracle as O
     W, H = wl["W"], wl["H"]
-    cam = O.Camera.from_buffer_copy(bytes(sp["cam"]))
-    obs = [O.OracleBlock(b["dims"], f.cpu().numpy(), origin=b["origin"], spacing=b["spacing"])
-           for b, f in zip(blocks, fields)]
+    cams = [O.Camera.from_buffer_copy(bytes(c)) for c in (sp["cams"] or [sp["cam"]])]
+    if wl.get("rectilinear"):
+        obs = [O.OracleBlock(b["dims"], f.cpu().numpy(), axes=[datasets.warp_axis(n, 1.5) for n in b["dims"]])
+               for b, f in zip(blocks, fields)]
+    else:
+        obs = [O.OracleBlock(b["dims"], f.cpu().numpy(), origin=b["origin"], spacing=b["spacing"])
+               for b, f in zip(blocks, fields)]
     t0 = time.time()
     n = 0
     while True:
+        cam = cams[n % len(cams)]
         rgba, depth = O.new_canvas(W, H)
         if len(obs) == 1:
             O.render_to_canvas(obs[0], cam, W, H, sp["lut"], sp["sample_dist"], rmin, rmax, rgba, depth)
@@ -333,8 +382,8 @@ def cpu_baseline_sample(wl, blocks, fields, sp, rmin, rmax):
             break
     dt = (time.time() - t0) / n
     return {"value": W * H / dt / 1e6, "unit": "Mrays/s", "cores": O.num_threads(), "kind": "port",
-            "ms_per_step": dt * 1e3,
-            "sample": "%d whole frame(s) of the same workload on the host cores (oracle port of the "
+            "ms_per_frame": dt * 1e3,
+            "sample": "%d whole frame(s)/view(s) of the same workload on the host cores (oracle port of the "
                       "reference's VTK-m/OpenMP algorithm; the reference itself is not buildable here)" % n}
 
 
@@ -344,11 +393,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=None, choices=[None, "c2", "c3"])
+    ap.add_argument("--workload", default=None, choices=[None, "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
     args = ap.parse_args()
     wname = args.workload or ("c2" if args.gpus == 1 else "c3")
-    wl = workload_c2() if wname == "c2" else workload_c3()
+    wl = {"c2": workload_c2, "c3": workload_c3, "c4": workload_c4, "c5": workload_c5}[wname]()
     if args.impl == "reference":
         if args.steps > 5:
             args.steps = 5
