@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("VR_LIB_NAME", "libvr_b200.so"))
 VR_OK = 0
 VR_F32, VR_F64 = 0, 1
 VR_POINT, VR_CELL = 0, 1
-VR_HOST, VR_DEVICE = 0, 1
+VR_HOST, VR_DEVICE, VR_HOST_MAPPED = 0, 1, 2
 IPC_HANDLE_BYTES = 64
 FRAME_WRITE_CANVAS, FRAME_NO_CLEAR = 1, 2
 
@@ -23,14 +23,14 @@ SYMBOLS = [
     "vr_create", "vr_destroy", "vr_last_error", "vr_set_stream", "vr_synchronize",
     "vr_kernel_launches", "vr_block_uniform", "vr_block_rectilinear", "vr_block_free",
     "vr_block_bounds", "vr_set_tf", "vr_canvas_clear", "vr_canvas_upload", "vr_canvas_download",
-    "vr_canvas_ptrs", "vr_trace_to_canvas", "vr_render_image", "vr_trace_to_image", "vr_partials_begin",
+    "vr_canvas_ptrs", "vr_canvas_blend_background", "vr_canvas_download_rgba8", "vr_trace_to_canvas", "vr_render_image", "vr_trace_to_image", "vr_partials_begin",
     "vr_trace_to_partials", "vr_partials_count", "vr_partials_download", "vr_render_partials",
-    "vr_free", "vr_layers_begin", "vr_trace_to_layer", "vr_layers_composite_to_canvas",
+    "vr_free", "vr_layers_begin", "vr_trace_to_layer", "vr_trace_blocks_to_layers", "vr_layers_composite_to_canvas",
     "vr_layers_to_partials", "vr_comm_layers_composite_to_canvas", "vr_image_from_canvas", "vr_image_download", "vr_fold_images_dev",
     "vr_composite_images", "vr_composite_zbuffer", "vr_zbuffer_composite_dev", "vr_image_to_canvas_dev",
     "vr_partials_composite", "vr_partials_composite_to_canvas", "vr_partials_to_canvas", "vr_composite_partials", "vr_comm_init",
     "vr_comm_connect", "vr_comm_composite_images", "vr_comm_composite_images_to_canvas",
-    "vr_image_result_download",
+    "vr_image_result_download", "vr_comm_composite_zbuffer", "vr_comm_sync_depths",
     "vr_image_result_to_canvas", "vr_comm_composite_partials", "vr_comm_composite_partials_to_canvas",
     "vr_image_ptrs",
     "vr_sample_distance", "vr_visibility_order", "vr_find_subset", "vr_synth_braid_dev",
@@ -87,6 +87,8 @@ def load():
                                       C.c_float, vp, vp]),
         "vr_trace_to_image": (C.c_int, [vp, C.c_int, cam, C.c_int, C.c_int, C.c_float, C.c_float,
                                         C.c_float, C.c_int]),
+        "vr_canvas_blend_background": (C.c_int, [vp, C.POINTER(C.c_float)]),
+        "vr_canvas_download_rgba8": (C.c_int, [vp, C.POINTER(C.c_float), C.c_int, vp]),
         "vr_partials_begin": (C.c_int, [vp, C.c_int, C.c_int]),
         "vr_trace_to_partials": (C.c_int, [vp, C.c_int, cam, C.c_float, C.c_float, C.c_float, C.c_int]),
         "vr_partials_count": (C.c_int, [vp, C.POINTER(sz)]),
@@ -96,6 +98,7 @@ def load():
         "vr_free": (None, [vp]),
         "vr_layers_begin": (C.c_int, [vp, C.c_int, C.c_int]),
         "vr_trace_to_layer": (C.c_int, [vp, C.c_int, cam, C.c_float, C.c_float, C.c_float, C.c_int]),
+        "vr_trace_blocks_to_layers": (C.c_int, [vp, C.c_int, ip, cam, C.c_float, C.c_float, C.c_float, C.c_int]),
         "vr_layers_composite_to_canvas": (C.c_int, [vp, cam, C.c_int]),
         "vr_layers_to_partials": (C.c_int, [vp]),
         "vr_comm_layers_composite_to_canvas": (C.c_int, [vp, cam]),
@@ -115,6 +118,8 @@ def load():
         "vr_comm_composite_images": (C.c_int, [vp, ip]),
         "vr_comm_composite_images_to_canvas": (C.c_int, [vp, ip]),
         "vr_image_result_download": (C.c_int, [vp, vp, vp]),
+        "vr_comm_composite_zbuffer": (C.c_int, [vp]),
+        "vr_comm_sync_depths": (C.c_int, [vp]),
         "vr_image_result_to_canvas": (C.c_int, [vp]),
         "vr_comm_composite_partials": (C.c_int, [vp]),
         "vr_comm_composite_partials_to_canvas": (C.c_int, [vp, cam]),
@@ -214,25 +219,29 @@ class Context:
 
     # -- blocks
     def block_uniform(self, block_id, dims, origin, spacing, field, assoc=VR_POINT, device_ptr=None,
-                      dtype=None):
+                      dtype=None, host_mapped=False):
+        """host_mapped: `field` is page-locked mapped host memory (e.g. a pinned torch tensor's
+        numpy view), sampled in place over PCIe (VR_HOST_MAPPED) instead of copied."""
         if device_ptr is not None:
             ptr, dt, where = C.c_void_p(device_ptr), dtype, VR_DEVICE
         else:
             field = np.ascontiguousarray(field)
             assert field.dtype in (np.float32, np.float64), "fields are f32 or f64"
-            ptr, dt, where = C.c_void_p(field.ctypes.data), (VR_F64 if field.dtype == np.float64 else VR_F32), VR_HOST
+            ptr, dt, where = C.c_void_p(field.ctypes.data), (VR_F64 if field.dtype == np.float64 else VR_F32), \
+                (VR_HOST_MAPPED if host_mapped else VR_HOST)
         self._ck(self.lib.vr_block_uniform(self.h, block_id, _i3(dims), _f3(origin), _f3(spacing), ptr,
                                            dt, assoc, where))
 
     def block_rectilinear(self, block_id, dims, axes, field, assoc=VR_POINT, device_ptr=None,
-                          dtype=None):
+                          dtype=None, host_mapped=False):
         ax = [np.ascontiguousarray(a, np.float64) for a in axes]
         if device_ptr is not None:
             ptr, dt, where = C.c_void_p(device_ptr), dtype, VR_DEVICE
         else:
             field = np.ascontiguousarray(field)
             assert field.dtype in (np.float32, np.float64), "fields are f32 or f64"
-            ptr, dt, where = C.c_void_p(field.ctypes.data), (VR_F64 if field.dtype == np.float64 else VR_F32), VR_HOST
+            ptr, dt, where = C.c_void_p(field.ctypes.data), (VR_F64 if field.dtype == np.float64 else VR_F32), \
+                (VR_HOST_MAPPED if host_mapped else VR_HOST)
         dpp = C.POINTER(C.c_double)
         self._ck(self.lib.vr_block_rectilinear(self.h, block_id, _i3(dims), ax[0].ctypes.data_as(dpp),
                                                ax[1].ctypes.data_as(dpp), ax[2].ctypes.data_as(dpp),
@@ -273,6 +282,16 @@ class Context:
         depth = np.empty(H * W, np.float32) if depth is None else depth
         self._ck(self.lib.vr_canvas_download(self.h, rgba.ctypes.data, depth.ctypes.data))
         return rgba, depth
+
+    def canvas_blend_background(self, bg):
+        b = (C.c_float * 4)(*[float(x) for x in bg])
+        self._ck(self.lib.vr_canvas_blend_background(self.h, b))
+
+    def canvas_download_rgba8(self, W, H, bg=None, flip=True, out=None):
+        out = np.empty((H, W, 4), np.uint8) if out is None else out
+        b = (C.c_float * 4)(*[float(x) for x in bg]) if bg is not None else None
+        self._ck(self.lib.vr_canvas_download_rgba8(self.h, b, int(flip), out.ctypes.data))
+        return out
 
     def canvas_ptrs(self):
         a, b = C.c_void_p(), C.c_void_p()
@@ -334,11 +353,23 @@ class Context:
         self._ck(self.lib.vr_trace_to_layer(self.h, block_id, C.byref(as_camera(cam)), sample_dist, rmin,
                                             rmax, int(use_canvas_depth)))
 
+    def trace_blocks_to_layers(self, block_ids, cam, sample_dist, rmin, rmax, use_canvas_depth=False):
+        ids = np.ascontiguousarray(block_ids, np.int32)
+        self._ck(self.lib.vr_trace_blocks_to_layers(self.h, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int)),
+                                                    C.byref(as_camera(cam)), sample_dist, rmin, rmax,
+                                                    int(use_canvas_depth)))
+
     def layers_composite_to_canvas(self, cam, canvas_is_clear=True):
         self._ck(self.lib.vr_layers_composite_to_canvas(self.h, C.byref(as_camera(cam)), int(canvas_is_clear)))
 
     def layers_to_partials(self):
         self._ck(self.lib.vr_layers_to_partials(self.h))
+
+    def comm_composite_zbuffer(self):
+        self._ck(self.lib.vr_comm_composite_zbuffer(self.h))
+
+    def comm_sync_depths(self):
+        self._ck(self.lib.vr_comm_sync_depths(self.h))
 
     def comm_layers_composite_to_canvas(self, cam):
         self._ck(self.lib.vr_comm_layers_composite_to_canvas(self.h, C.byref(as_camera(cam))))

@@ -54,6 +54,10 @@ struct Flags
   // geometry of this arena: every rank must have been initialised with the same values, because
   // a rank addresses its peers' arenas with its own layout (checked in vr_comm_connect)
   unsigned long long cfg_max_pixels, cfg_max_partials;
+  // depth broadcast (Scene::SynchDepths): rank 0's staging copy is complete for epoch s_ready;
+  // (rank 0 only) s_done[r] = last epoch rank r has finished pulling
+  unsigned int s_ready;
+  unsigned int s_done[kMaxRanks];
 };
 static_assert(sizeof(Flags) <= 4096, "flag block");
 
@@ -98,7 +102,13 @@ constexpr int kChunkGroups = 256; // 4-pixel groups per ownership chunk
 // TO_CANVAS: rank 0 also produces its float canvas (Renderer::ImageToCanvas, Renderer.cpp:265-283):
 // the groups no rank covers are written here, while the peers' pixels are still in flight; the
 // covered ones are converted by covered_to_canvas_kernel once they have landed.
-template <bool TO_CANVAS>
+// ZBUF: the opaque-surface mode of the same exchange (Compositor Z_BUFFER_SURFACE ->
+// RadixKCompositor::CompositeSurface, RadixKCompositor.cpp:35-180): the per-pixel operator is
+// ImageCompositor::ZBufferComposite (ImageCompositor.hpp:49-76) -- nearest fragment wins, fragments
+// with depth > 1 never replace -- folded over the ranks in rank order.  Select-nearest is associative
+// and commutative for distinct depths, so the radix-k tree and this direct-send fold give the same
+// image; fragments of different ranks at EXACTLY equal depth resolve to the higher rank here.
+template <bool TO_CANVAS, bool ZBUF>
 __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ FoldP2PParams P)
 {
   Flags* my_flags = reinterpret_cast<Flags*>(P.peers[P.rank] + P.off_flags);
@@ -195,6 +205,18 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
     for (int l = 1; l < kMaxRanks; ++l)
       if (l < P.size)
       {
+        if (ZBUF)
+        {
+          // outside its rectangle a layer is depth 1.001 (> 1): never selected
+          if (cover & (1u << l))
+          {
+            if (!(d[l].x > 1.f || fd.x < d[l].x)) { fd.x = d[l].x; f.x = c[l].x; }
+            if (!(d[l].y > 1.f || fd.y < d[l].y)) { fd.y = d[l].y; f.y = c[l].y; }
+            if (!(d[l].z > 1.f || fd.z < d[l].z)) { fd.z = d[l].z; f.z = c[l].z; }
+            if (!(d[l].w > 1.f || fd.w < d[l].w)) { fd.w = d[l].w; f.w = c[l].w; }
+          }
+          continue;
+        }
         if (cover & (1u << l))
         {
           f.x = blend_u8x4(f.x, c[l].x); f.y = blend_u8x4(f.y, c[l].y);
@@ -260,6 +282,45 @@ __global__ void wait_done_kernel(const unsigned int* done, int size, unsigned in
     while (ld_acquire_sys(done + threadIdx.x) < epoch) __nanosleep(64);
 }
 
+
+// ------------------------------------------------------------------ Scene::SynchDepths (Scene.cpp:249-264)
+// MPI_Bcast of rank 0's canvas depth: rank 0 stages its depth buffer in its arena and raises
+// s_ready; every other rank pulls it over NVLink into its own canvas and reports s_done, which
+// rank 0 waits on before it stages the next one.
+__global__ void sync_post_kernel(Flags* root_flags, unsigned int epoch)
+{
+  if (threadIdx.x == 0)
+  {
+    __threadfence_system();
+    root_flags->s_done[0] = epoch;
+    st_release_sys(&root_flags->s_ready, epoch);
+  }
+}
+__global__ void __launch_bounds__(256) sync_pull_kernel(Flags* root_flags, Flags* my_flags, const float* __restrict__ staged,
+                                                        float* __restrict__ depth, size_t n, int rank, unsigned int epoch)
+{
+  if (threadIdx.x == 0)
+    while (ld_acquire_sys(&root_flags->s_ready) < epoch) __nanosleep(128);
+  __syncthreads();
+  const size_t n4 = n / 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t i = t; i < n4; i += stride)
+    reinterpret_cast<float4*>(depth)[i] = reinterpret_cast<const float4*>(staged)[i];
+  for (size_t i = n4 * 4 + t; i < n; i += stride) depth[i] = staged[i];
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    __threadfence_system();
+    const unsigned prev = atomicAdd(&my_flags->cta_done, 1u);
+    if (prev == gridDim.x - 1)
+    {
+      my_flags->cta_done = 0;
+      __threadfence_system();
+      st_release_sys(&root_flags->s_done[rank], epoch);
+    }
+  }
+}
 
 // ------------------------------------------------------------------ partial path: pull + merge + fold
 struct MergeP2PParams
@@ -475,6 +536,7 @@ struct Layout
   size_t off_flags, off_img_rgba[2], off_img_depth[2], off_res_rgba[2], off_res_depth[2];
   size_t off_poff[2], off_psorted[2], off_pout, off_canvas_rgba, off_canvas_depth, total;
   size_t off_lflags, off_ltab[2], off_lpool_rgba[2], off_lpool_depth[2];
+  size_t off_sync_depth;
 };
 Layout make_layout(size_t max_pixels, size_t max_partials, bool is_root)
 {
@@ -502,6 +564,9 @@ Layout make_layout(size_t max_pixels, size_t max_partials, bool is_root)
   if (max_partials) o += align_up(max_pixels * sizeof(float4), 256);
   L.off_canvas_depth = o;
   if (max_partials) o += align_up(max_pixels * sizeof(float), 256);
+  // rank 0's staging copy of its canvas depth for the depth broadcast
+  L.off_sync_depth = o;
+  o += align_up(max_pixels * sizeof(float), 256);
   if (!is_root) o = common_end;
   L.total = align_up(o, 2 << 20);
   return L;
@@ -511,8 +576,9 @@ Layout make_layout(size_t max_pixels, size_t max_partials, bool is_root)
 
 cudaError_t launch_fold_p2p(const FoldP2PParams& p, int sm_count, cudaStream_t s)
 {
-  if (p.canvas_rgba) fold_p2p_kernel<true><<<sm_count * 2, 256, 0, s>>>(p);
-  else fold_p2p_kernel<false><<<sm_count * 2, 256, 0, s>>>(p);
+  if (p.zbuffer) fold_p2p_kernel<false, true><<<sm_count * 2, 256, 0, s>>>(p);
+  else if (p.canvas_rgba) fold_p2p_kernel<true, false><<<sm_count * 2, 256, 0, s>>>(p);
+  else fold_p2p_kernel<false, false><<<sm_count * 2, 256, 0, s>>>(p);
   return cudaGetLastError();
 }
 
@@ -675,7 +741,7 @@ extern "C" vr_status vr_comm_connect(vr_ctx* ctx, const void* all_handles)
   return VR_OK;
 }
 
-static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, bool to_canvas)
+static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, bool to_canvas, bool zbuffer = false)
 {
   Comm& c = ctx->comm;
   if (!c.on || !c.peer_dev) return cfail(ctx, VR_ERR_STATE, "vr_comm_composite_images: not connected", cudaSuccess);
@@ -709,7 +775,8 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
     idx[j + 1] = k;
   }
   for (int i = 0; i < c.size; ++i) p.order[i] = idx[i];
-  if (to_canvas && c.rank == 0 && ctx->W % 4 == 0)
+  p.zbuffer = zbuffer ? 1 : 0;
+  if (to_canvas && !zbuffer && c.rank == 0 && ctx->W % 4 == 0)
   {
     p.canvas_rgba = ctx->canvas_rgba;
     p.canvas_depth = ctx->canvas_depth;
@@ -895,6 +962,52 @@ extern "C" vr_status vr_comm_composite_images_to_canvas(vr_ctx* ctx, const int* 
 {
   if (!ctx) return VR_ERR_INVALID;
   return comm_composite_images_impl(ctx, vis_order, true);
+}
+
+extern "C" vr_status vr_comm_composite_zbuffer(vr_ctx* ctx)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  int order[kMaxRanks];
+  for (int i = 0; i < kMaxRanks; ++i) order[i] = i; // rank order
+  return comm_composite_images_impl(ctx, order, false, true);
+}
+
+extern "C" vr_status vr_comm_sync_depths(vr_ctx* ctx)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  Comm& c = ctx->comm;
+  if (!c.on || !c.peer_dev) return cfail(ctx, VR_ERR_STATE, "vr_comm_sync_depths: not connected", cudaSuccess);
+  if (ctx->W <= 0 || !ctx->canvas_depth) return cfail(ctx, VR_ERR_STATE, "vr_comm_sync_depths: no canvas", cudaSuccess);
+  const size_t n = (size_t)ctx->W * ctx->H;
+  if (n > c.max_pixels) return cfail(ctx, VR_ERR_INVALID, "vr_comm_sync_depths: canvas larger than max_pixels", cudaSuccess);
+  cudaSetDevice(ctx->device);
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
+  c.sepoch += 1;
+  Flags* root_flags = reinterpret_cast<Flags*>(c.peer[0] + L.off_flags);
+  float* staged = reinterpret_cast<float*>(c.peer[0] + L.off_sync_depth);
+  if (c.rank == 0)
+  {
+    // every rank has finished pulling the previous broadcast before the staging copy is replaced
+    if (c.sepoch > 1)
+    {
+      wait_done_kernel<<<1, 32, 0, ctx->stream>>>(root_flags->s_done, c.size, c.sepoch - 1);
+      ctx->launches++;
+    }
+    cudaError_t e = cudaMemcpyAsync(staged, ctx->canvas_depth, n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "vr_comm_sync_depths: stage", e);
+    sync_post_kernel<<<1, 32, 0, ctx->stream>>>(root_flags, c.sepoch);
+    ctx->launches++;
+  }
+  else
+  {
+    Flags* my_flags = reinterpret_cast<Flags*>(c.arena + L.off_flags);
+    sync_pull_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(root_flags, my_flags, staged, ctx->canvas_depth, n,
+                                                                 c.rank, c.sepoch);
+    ctx->launches++;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "vr_comm_sync_depths launch", e);
+  return VR_OK;
 }
 
 extern "C" vr_status vr_comm_layers_composite_to_canvas(vr_ctx* ctx, const vr_camera* cam)

@@ -146,9 +146,52 @@ __global__ void zbuffer_kernel(unsigned* __restrict__ front, float* __restrict__
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
   {
     const float d = depth[i];
-    if (fdepth[i] < d) continue; // ImageCompositor.hpp:63-66
+    if (d > 1.f || fdepth[i] < d) continue; // ImageCompositor.hpp:63-66 (depth is >= 0 after Image::Init)
     fdepth[i] = d;
     front[i] = img[i];
+  }
+}
+
+// ---------------------------------------------------------------- frame epilogue
+// Render::RenderBackground -> Canvas::BlendBackground (Render.cpp:277-286), in place on the canvas
+__global__ void blend_background_kernel(float4* __restrict__ canvas, size_t n, float4 bg)
+{
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    float4 c = canvas[i];
+    if (c.w >= 1.f) continue;
+    const float alpha = bg.w * (1.f - c.w);
+    c.x = c.x + bg.x * alpha;
+    c.y = c.y + bg.y * alpha;
+    c.z = c.z + bg.z * alpha;
+    c.w = alpha + c.w;
+    canvas[i] = c;
+  }
+}
+// PNGEncoder::Encode's conversion (ascent_png_encoder.cpp:257-281): (unsigned char)(c * 255.f), rows
+// flipped; BLEND fuses the background blend in front of it without touching the canvas
+template <bool BLEND>
+__global__ void encode_rgba8_kernel(const float4* __restrict__ canvas, int W, int H, int flip, float4 bg,
+                                    uchar4* __restrict__ out)
+{
+  const size_t n = (size_t)W * H;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    float4 c = canvas[i];
+    if (BLEND && !(c.w >= 1.f))
+    {
+      const float alpha = bg.w * (1.f - c.w);
+      c.x = c.x + bg.x * alpha;
+      c.y = c.y + bg.y * alpha;
+      c.z = c.z + bg.z * alpha;
+      c.w = alpha + c.w;
+    }
+    const int y = (int)(i / (size_t)W), x = (int)(i % (size_t)W);
+    const size_t o = (size_t)(flip ? H - y - 1 : y) * W + x;
+    out[o] = make_uchar4((unsigned char)(__float2ll_rz(c.x * 255.f) & 0xff), (unsigned char)(__float2ll_rz(c.y * 255.f) & 0xff),
+                         (unsigned char)(__float2ll_rz(c.z * 255.f) & 0xff), (unsigned char)(__float2ll_rz(c.w * 255.f) & 0xff));
   }
 }
 
@@ -576,6 +619,23 @@ cudaError_t launch_zbuffer(uchar4* front, float* fdepth, const uchar4* img, cons
 {
   zbuffer_kernel<<<grid_for(n, kT), kT, 0, s>>>(reinterpret_cast<unsigned*>(front), fdepth,
                                                  reinterpret_cast<const unsigned*>(img), depth, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_blend_background(float4* canvas, size_t n, const float bg[4], cudaStream_t s)
+{
+  blend_background_kernel<<<grid_for(n, kT), kT, 0, s>>>(canvas, n, make_float4(bg[0], bg[1], bg[2], bg[3]));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_encode_rgba8(const float4* canvas, int W, int H, int flip, const float* bg, uchar4* out,
+                                cudaStream_t s)
+{
+  const size_t n = (size_t)W * H;
+  if (bg)
+    encode_rgba8_kernel<true><<<grid_for(n, kT), kT, 0, s>>>(canvas, W, H, flip, make_float4(bg[0], bg[1], bg[2], bg[3]), out);
+  else
+    encode_rgba8_kernel<false><<<grid_for(n, kT), kT, 0, s>>>(canvas, W, H, flip, make_float4(0.f, 0.f, 0.f, 0.f), out);
   return cudaGetLastError();
 }
 

@@ -510,7 +510,8 @@ cudaError_t launch_dtype(const TraceParams& p, int mode, int grid, cudaStream_t 
 
 } // namespace
 
-cudaError_t launch_trace(const TraceParams& p, int mode_partials, int sm_count, cudaStream_t s)
+cudaError_t launch_trace(const TraceParams& p, int mode_partials, int sm_count, cudaStream_t s,
+                         bool zero_counter)
 {
   const long long n_tiles = (long long)p.tiles_x * p.tiles_y + (mode_partials == 2 ? p.n_clear_chunks : 0);
   if (n_tiles <= 0) return cudaSuccess;
@@ -519,8 +520,11 @@ cudaError_t launch_trace(const TraceParams& p, int mode_partials, int sm_count, 
   long long grid = (long long)sm_count * ctas_per_sm;
   const long long need = (n_tiles + 3) / 4;
   if (grid > need) grid = need;
-  cudaError_t e = cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned int), s);
-  if (e != cudaSuccess) return e;
+  if (zero_counter)
+  {
+    cudaError_t e = cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned int), s);
+    if (e != cudaSuccess) return e;
+  }
   return p.blk.kind == 0 ? launch_dtype<0>(p, mode_partials, (int)grid, s)
                          : launch_dtype<1>(p, mode_partials, (int)grid, s);
 }

@@ -77,7 +77,13 @@ extern "C" vr_status vr_create(int device, vr_ctx** out)
   ctx->stream = ctx->own_stream;
   if (const char* e = std::getenv("VR_CTAS_PER_SM")) ctx->ctas_per_sm = std::atoi(e); // tuning knob
   if (const char* e = std::getenv("VR_COUNT_SAMPLES")) ctx->count_samples = std::atoi(e) != 0;
-  cudaMalloc(&ctx->tile_counter, sizeof(unsigned int));
+  cudaMalloc(&ctx->tile_counter, (size_t)(1 + vr::kMaxLayers) * sizeof(unsigned int)); // [0]: single launches
+  for (int k = 0; k < vr::kAuxStreams; ++k)
+  {
+    cudaStreamCreateWithFlags(&ctx->aux[k], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming);
+  }
+  cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   cudaMalloc(&ctx->sample_counter, sizeof(unsigned long long));
   cudaMalloc(&ctx->partial_count, sizeof(unsigned long long));
   cudaMalloc(&ctx->partial_count_tmp, sizeof(unsigned long long));
@@ -140,8 +146,15 @@ extern "C" void vr_destroy(vr_ctx* ctx)
   cudaFree(ctx->sidx);
   cudaFree(ctx->rec);
   cudaFree(ctx->scan_blocks);
+  cudaFree(ctx->enc_rgba);
   cudaFree(ctx->tile_counter);
   cudaFree(ctx->sample_counter);
+  for (int k = 0; k < vr::kAuxStreams; ++k)
+  {
+    if (ctx->aux[k]) cudaStreamDestroy(ctx->aux[k]);
+    if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -184,7 +197,8 @@ static vr_status upload_field(vr_ctx* ctx, Block& b, const void* field, int dtyp
   REQUIRE(field != nullptr, "block: field is NULL");
   REQUIRE(dtype == VR_F32 || dtype == VR_F64, "block: dtype must be VR_F32 or VR_F64");
   REQUIRE(assoc == VR_POINT || assoc == VR_CELL, "block: assoc must be VR_POINT or VR_CELL");
-  REQUIRE(where == VR_HOST || where == VR_DEVICE, "block: where must be VR_HOST or VR_DEVICE");
+  REQUIRE(where == VR_HOST || where == VR_DEVICE || where == VR_HOST_MAPPED,
+          "block: where must be VR_HOST, VR_DEVICE or VR_HOST_MAPPED");
   const int* d = b.dev.dims;
   REQUIRE(d[0] >= 2 && d[1] >= 2 && d[2] >= 2, "block: point dims must be >= 2 (got %d %d %d)", d[0],
           d[1], d[2]);
@@ -195,6 +209,20 @@ static vr_status upload_field(vr_ctx* ctx, Block& b, const void* field, int dtyp
   b.dev.assoc = assoc;
   if (where == VR_DEVICE)
     b.dev.field = field;
+  else if (where == VR_HOST_MAPPED)
+  {
+    // page-locked host memory sampled in place over PCIe: the sparse default sampling touches about
+    // a quarter of the field's 32-byte sectors, so pulling just those beats copying the whole block
+    void* dptr = nullptr;
+    cudaError_t e = cudaHostGetDevicePointer(&dptr, const_cast<void*>(field), 0);
+    if (e != cudaSuccess)
+    {
+      cudaGetLastError();
+      return fail(ctx, VR_ERR_INVALID, "block: VR_HOST_MAPPED field is not page-locked mapped host memory "
+                  "(cudaHostAlloc / cudaHostRegister): %s", cudaGetErrorString(e));
+    }
+    b.dev.field = dptr;
+  }
   else
   {
     if (old && old->owned_field && field_bytes(old->dev) == bytes)
@@ -401,6 +429,40 @@ extern "C" vr_status vr_canvas_download(vr_ctx* ctx, float* rgba, float* depth)
   const size_t n = (size_t)ctx->W * ctx->H;
   if (rgba) CK(cudaMemcpyAsync(rgba, ctx->canvas_rgba, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
   if (depth) CK(cudaMemcpyAsync(depth, ctx->canvas_depth, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VR_OK;
+}
+
+extern "C" vr_status vr_canvas_blend_background(vr_ctx* ctx, const float bg_rgba[4])
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(ctx->W > 0, "vr_canvas_blend_background: no canvas yet");
+  REQUIRE(bg_rgba, "vr_canvas_blend_background: NULL colour");
+  CK(cudaSetDevice(ctx->device));
+  CK(launch_blend_background(ctx->canvas_rgba, (size_t)ctx->W * ctx->H, bg_rgba, ctx->stream));
+  ctx->launches++;
+  return VR_OK;
+}
+
+extern "C" vr_status vr_canvas_download_rgba8(vr_ctx* ctx, const float* bg_rgba, int flip_rows, uint8_t* out_rgba8)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(ctx->W > 0, "vr_canvas_download_rgba8: no canvas yet");
+  REQUIRE(out_rgba8, "vr_canvas_download_rgba8: NULL output");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)ctx->W * ctx->H;
+  if (n > ctx->enc_cap)
+  {
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->enc_rgba);
+    ctx->enc_rgba = nullptr;
+    ctx->enc_cap = 0;
+    CK(cudaMalloc(&ctx->enc_rgba, n * sizeof(uchar4)));
+    ctx->enc_cap = n;
+  }
+  CK(launch_encode_rgba8(ctx->canvas_rgba, ctx->W, ctx->H, flip_rows ? 1 : 0, bg_rgba, ctx->enc_rgba, ctx->stream));
+  ctx->launches++;
+  CK(cudaMemcpyAsync(out_rgba8, ctx->enc_rgba, n * sizeof(uchar4), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return VR_OK;
 }
@@ -738,6 +800,67 @@ extern "C" vr_status vr_trace_to_layer(vr_ctx* ctx, int block_id, const vr_camer
   d.x0 = p.sx; d.y0 = p.sy; d.w = p.sw; d.h = p.sh;
   d.base = base;
   ctx->lpool_used = base + area;
+  return VR_OK;
+}
+
+// Every local block of the frame in one call (the loop of RenderMultipleDomainsPerRank,
+// VolumeRenderer.cpp:557-578).  The launches are spread over a few side streams: each sampler launch
+// is a persistent grid that fills the GPU, so the next block's CTAs move in as the previous block's
+// long rays drain -- no idle tail between blocks -- and the host pays one counter memset per frame.
+extern "C" vr_status vr_trace_blocks_to_layers(vr_ctx* ctx, int n_blocks, const int* block_ids,
+                                               const vr_camera* cam, float sample_dist, float range_min,
+                                               float range_max, int use_canvas_depth)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  REQUIRE(ctx->lW > 0, "vr_trace_blocks_to_layers: call vr_layers_begin first");
+  REQUIRE(n_blocks >= 0 && (n_blocks == 0 || block_ids), "vr_trace_blocks_to_layers: NULL block list");
+  REQUIRE(!use_canvas_depth || (ctx->W == ctx->lW && ctx->H == ctx->lH),
+          "vr_trace_blocks_to_layers: canvas depth requested but canvas size differs");
+  CK(cudaSetDevice(ctx->device));
+  LayerTable& T = *ctx->ltab_host;
+  std::vector<TraceParams> ps;
+  ps.reserve(n_blocks);
+  size_t used = ctx->lpool_used;
+  for (int k = 0; k < n_blocks; ++k)
+  {
+    TraceParams p;
+    vr_status st = fill_trace_params(ctx, block_ids[k], cam, sample_dist, range_min, range_max, use_canvas_depth,
+                                     ctx->lW, ctx->lH, p);
+    if (st != VR_OK) return st;
+    if (p.sw <= 0 || p.sh <= 0) continue; // block off screen: no rays, no layer
+    const size_t base = (used + 3) & ~(size_t)3;
+    p.layer_base = base;
+    used = base + (size_t)p.sw * p.sh;
+    ps.push_back(p);
+  }
+  REQUIRE(T.n + (int)ps.size() <= kMaxLayers, "vr_trace_blocks_to_layers: more than %d layers in one frame",
+          kMaxLayers);
+  if (ps.empty()) return VR_OK;
+  vr_status st = ensure_layer_pool(ctx, used);
+  if (st != VR_OK) return st;
+  const int n = (int)ps.size();
+  const int n_streams = std::min(n, kAuxStreams);
+  CK(cudaMemsetAsync(ctx->tile_counter + 1, 0, (size_t)n * sizeof(unsigned int), ctx->stream));
+  CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  for (int k = 0; k < n_streams; ++k) CK(cudaStreamWaitEvent(ctx->aux[k], ctx->ev_fork, 0));
+  for (int k = 0; k < n; ++k)
+  {
+    TraceParams& p = ps[k];
+    p.layer_rgba = ctx->lpool_rgba;
+    p.layer_depth = ctx->lpool_depth;
+    p.tile_counter = ctx->tile_counter + 1 + k;
+    CK(launch_trace(p, 3, ctx->sm_count, ctx->aux[k % n_streams], false));
+    ctx->launches++;
+    LayerDesc& d = T.d[T.n++];
+    d.x0 = p.sx; d.y0 = p.sy; d.w = p.sw; d.h = p.sh;
+    d.base = p.layer_base;
+  }
+  for (int k = 0; k < n_streams; ++k)
+  {
+    CK(cudaEventRecord(ctx->ev_join[k], ctx->aux[k]));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0));
+  }
+  ctx->lpool_used = used;
   return VR_OK;
 }
 

@@ -11,6 +11,7 @@
 
 namespace vr
 {
+constexpr int kAuxStreams = 4;
 
 // ---------------------------------------------------------------- device-side descriptors
 struct BlockDev
@@ -89,6 +90,7 @@ struct Comm
   unsigned int epoch = 0;                       // image path frames composited so far
   unsigned int pepoch = 0;                      // partial path frames
   unsigned int lepoch = 0;                      // layer path frames
+  unsigned int sepoch = 0;                      // depth broadcasts
   int* minmax_dev = nullptr;                    // {min,max} pixel id of the current list
 };
 
@@ -153,8 +155,14 @@ struct vr_ctx
   bool layers_in_arena = false;
   int lW = 0, lH = 0;
 
-  unsigned int* tile_counter = nullptr;
+  uchar4* enc_rgba = nullptr;  // encoded final image (vr_canvas_download_rgba8)
+  size_t enc_cap = 0;
+
+  unsigned int* tile_counter = nullptr;   // [0] single launches, [1 + k] launch k of a batched call
   unsigned long long* sample_counter = nullptr;
+  // side streams of the batched block loop (vr_trace_blocks_to_layers)
+  cudaStream_t aux[4] = { nullptr, nullptr, nullptr, nullptr };
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = { nullptr, nullptr, nullptr, nullptr };
 
   vr::Comm comm;
 };
@@ -162,7 +170,8 @@ struct vr_ctx
 namespace vr
 {
 // sampler.cu
-cudaError_t launch_trace(const TraceParams& p, int mode_partials, int sm_count, cudaStream_t s);
+cudaError_t launch_trace(const TraceParams& p, int mode_partials, int sm_count, cudaStream_t s,
+                         bool zero_counter = true);
 
 // composite.cu
 cudaError_t launch_canvas_clear(float4* rgba, float* depth, size_t n, cudaStream_t s);
@@ -174,6 +183,9 @@ cudaError_t launch_fold_images(const uchar4* rgba, const float* depth, size_t la
                                cudaStream_t s);
 cudaError_t launch_zbuffer(uchar4* front, float* fdepth, const uchar4* img, const float* depth,
                            size_t n, cudaStream_t s);
+cudaError_t launch_blend_background(float4* canvas, size_t n, const float bg[4], cudaStream_t s);
+cudaError_t launch_encode_rgba8(const float4* canvas, int W, int H, int flip, const float* bg /* null: none */,
+                                uchar4* out, cudaStream_t s);
 cudaError_t launch_image_to_canvas(const uchar4* rgba, const float* depth, size_t n, float4* canvas,
                                    float* cdepth, cudaStream_t s);
 cudaError_t launch_synth_braid(void* field, int dtype, const int n[3], const int start[3],
@@ -298,6 +310,7 @@ struct FoldP2PParams
   int order[16]; // rank index per fold step (front to back)
   float4* canvas_rgba; // rank 0, fused ImageToCanvas (null: off)
   float* canvas_depth;
+  int zbuffer;         // 1: select-nearest (opaque surfaces) instead of the ordered blend
 };
 cudaError_t launch_fold_p2p(const FoldP2PParams& p, int sm_count, cudaStream_t s);
 } // namespace vr

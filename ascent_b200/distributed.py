@@ -161,8 +161,7 @@ def run_bench(args, wl, bench):
             ctx.trace_to_image(mine[0], cam, W, H, sp["sample_dist"], rmin, rmax, no_clear=True)
         else:
             ctx.layers_begin(W, H)
-            for i in mine:
-                ctx.trace_to_layer(i, cam, sp["sample_dist"], rmin, rmax, False)
+            ctx.trace_blocks_to_layers(mine, cam, sp["sample_dist"], rmin, rmax, False)
 
     def composite():
         if path_a:

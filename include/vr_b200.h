@@ -44,7 +44,9 @@ typedef enum
 
 enum { VR_F32 = 0, VR_F64 = 1 };     /* field scalar type (ascent_vtkh_data_adapter.cpp:1843-1887) */
 enum { VR_POINT = 0, VR_CELL = 1 };  /* field association */
-enum { VR_HOST = 0, VR_DEVICE = 1 }; /* where a caller-supplied pointer lives */
+/* where a caller-supplied field lives: pageable/pinned host memory to copy, device memory to adopt, or
+ * page-locked MAPPED host memory (cudaHostAlloc / cudaHostRegister) to sample in place over PCIe */
+enum { VR_HOST = 0, VR_DEVICE = 1, VR_HOST_MAPPED = 2 };
 
 /* vtkm::rendering::Camera as parse_camera fills it
  * (ascent_runtime_conduit_to_vtkm_parsing.cpp:97-173); f32 like VTK-m's. */
@@ -85,7 +87,12 @@ VR_API uint64_t vr_kernel_launches(const vr_ctx* ctx);
  * and reused by every render of the batch.
  *   where == VR_HOST   : `field` is host memory, copied to the device.
  *   where == VR_DEVICE : `field` is device memory on this GPU and is used in place (zero copy;
- *                        must outlive the block).                                            */
+ *                        must outlive the block).
+ *   where == VR_HOST_MAPPED : `field` is page-locked, device-mapped host memory (the simulation's
+ *                        own array after cudaHostRegister, cf. the zero-copy Blueprint path of
+ *                        ascent_vtkh_data_adapter.cpp:1351-1355); no copy is made, the sampler
+ *                        pulls only the sectors its rays touch across PCIe.  Worth it for a field
+ *                        rendered once or a few times per publish; must outlive the block.   */
 VR_API vr_status vr_block_uniform(vr_ctx* ctx, int block_id, const int dims[3],
                                   const float origin[3], const float spacing[3], const void* field,
                                   int dtype, int assoc, int where);
@@ -109,6 +116,18 @@ VR_API vr_status vr_canvas_upload(vr_ctx* ctx, int width, int height, const floa
                                   const float* depth);
 VR_API vr_status vr_canvas_download(vr_ctx* ctx, float* rgba, float* depth); /* syncs */
 VR_API vr_status vr_canvas_ptrs(vr_ctx* ctx, void** rgba_dev, void** depth_dev);
+/* Frame epilogue on the device (what Scene::Render does with each finished canvas on rank 0,
+ * Scene.cpp:236-243, when annotations are off):
+ * vr_canvas_blend_background = Render::RenderBackground -> vtkm Canvas::BlendBackground
+ * (Render.cpp:277-286), in place on the device canvas.
+ * vr_canvas_download_rgba8   = the float -> uint8 conversion PNGEncoder::Encode applies to the colour
+ * buffer in Render::Save (Render.cpp:299-312, ascent_png_encoder.cpp:257-281): (unsigned char)(c*255.f),
+ * rows flipped when flip_rows != 0; with bg_rgba != NULL the background blend is applied on the fly
+ * (the canvas itself is left untouched).  Moves 4 B/pixel to the host instead of the 20 B/pixel float
+ * canvas.  Syncs.                                                                               */
+VR_API vr_status vr_canvas_blend_background(vr_ctx* ctx, const float bg_rgba[4]);
+VR_API vr_status vr_canvas_download_rgba8(vr_ctx* ctx, const float* bg_rgba, int flip_rows,
+                                          uint8_t* out_rgba8);
 
 /* ------------------------------------------------------------------ (1) path A render
  * MapperVolume::RenderCells for one block and one camera: ray generation over the block's
@@ -169,6 +188,12 @@ VR_API void vr_free(void* p);
 VR_API vr_status vr_layers_begin(vr_ctx* ctx, int width, int height);
 VR_API vr_status vr_trace_to_layer(vr_ctx* ctx, int block_id, const vr_camera* cam, float sample_dist,
                                    float range_min, float range_max, int use_canvas_depth);
+/* The whole per-domain loop of RenderMultipleDomainsPerRank (VolumeRenderer.cpp:557-578) in one call:
+ * same layers as n_blocks calls of vr_trace_to_layer in block_ids order, launched so that consecutive
+ * blocks overlap on the GPU.                                                                    */
+VR_API vr_status vr_trace_blocks_to_layers(vr_ctx* ctx, int n_blocks, const int* block_ids,
+                                           const vr_camera* cam, float sample_dist, float range_min,
+                                           float range_max, int use_canvas_depth);
 /* One rank: PartialCompositor::composite + partials_to_canvas (VolumeRenderer.cpp:580-595).
  * canvas_is_clear as for vr_partials_composite_to_canvas.                                       */
 VR_API vr_status vr_layers_composite_to_canvas(vr_ctx* ctx, const vr_camera* cam, int canvas_is_clear);
@@ -248,6 +273,16 @@ VR_API vr_status vr_comm_composite_images(vr_ctx* ctx, const int* vis_order);
 /* The same plus Renderer::ImageToCanvas on rank 0 (vr_image_result_to_canvas) folded into the
  * exchange: rank 0 converts the pixels no rank covers while the others are still in flight.    */
 VR_API vr_status vr_comm_composite_images_to_canvas(vr_ctx* ctx, const int* vis_order);
+/* Opaque surfaces, all ranks collectively (Compositor Z_BUFFER_SURFACE -> RadixKCompositor::
+ * CompositeSurface, RadixKCompositor.cpp:35-180): the same fused exchange with
+ * ImageCompositor::ZBufferComposite (ImageCompositor.hpp:49-76) as the per-pixel operator, folded in
+ * rank order; the nearest fragment's RGBA8 + depth land on rank 0 (vr_image_result_*).  Identical to
+ * the reference's radix-k tree except for fragments of DIFFERENT ranks at exactly equal depth (here:
+ * the higher rank wins).                                                                         */
+VR_API vr_status vr_comm_composite_zbuffer(vr_ctx* ctx);
+/* Scene::SynchDepths (Scene.cpp:249-264), all ranks collectively: rank 0's canvas depth replaces every
+ * other rank's canvas depth (NVLink pull), so the volume pass stops at the composited surfaces.   */
+VR_API vr_status vr_comm_sync_depths(vr_ctx* ctx);
 VR_API vr_status vr_image_result_download(vr_ctx* ctx, uint8_t* rgba, float* depth); /* syncs */
 VR_API vr_status vr_image_result_to_canvas(vr_ctx* ctx);
 /* Path B, collective: redistribute partials by pixel-range owner, sort+fold on the owner,

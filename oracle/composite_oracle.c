@@ -99,8 +99,11 @@ ORC_API void orc_ordered_composite(const uint8_t* layers_rgba, const float* laye
   free(idx);
 }
 
-/* ---- C4: ImageCompositor::ZBufferComposite, ImageCompositor.hpp:49-76 (vtk-h, no gl_depth
- * switch) / apcomp internal/ImageCompositor.hpp (gl_depth: skip depth > 1) */
+/* ---- C4: ImageCompositor::ZBufferComposite.  vtk-h (src/libs/vtkh/compositing/ImageCompositor.hpp:
+ * 49-76) has one form: a fragment with depth > 1 never replaces -- call with gl_depth = 1 (its
+ * abs(depth) is the identity: Image::Init has already made depths non-negative).  apcomp
+ * (src/libs/apcomp/internal/ImageCompositor.hpp:67-122) switches on m_gl_depth: 1 = the same rule,
+ * 0 = plain nearest-wins. */
 ORC_API void orc_zbuffer_composite(uint8_t* front_rgba, float* front_depth,
                                    const uint8_t* img_rgba, const float* img_depth, int n_pixels,
                                    int gl_depth)
@@ -123,6 +126,38 @@ ORC_API void orc_image_to_canvas(const uint8_t* rgba, const float* depth, int n_
   float one_over_255 = 1.f / 255.f;
   for (int i = 0; i < n_pixels * 4; ++i) canvas_rgba[i] = (float)rgba[i] * one_over_255;
   if (canvas_depth) memcpy(canvas_depth, depth, sizeof(float) * (size_t)n_pixels);
+}
+
+/* ---- Render::RenderBackground (src/libs/vtkh/rendering/Render.cpp:277-286) -> vtkm::rendering::
+ * Canvas::BlendBackground [VTK-m 2.1.0, recalled: vtkm/rendering/Canvas.cxx BlendBackground worklet]:
+ * per pixel, if alpha >= 1 keep; else a = bg.a * (1 - alpha); rgb += bg.rgb * a; alpha = a + alpha.
+ * Pinned end to end by the reference's render goldens (tests/test_oracle_golden.py). */
+ORC_API void orc_blend_background(float* canvas_rgba, int n_pixels, const float* bg)
+{
+  for (int i = 0; i < n_pixels; ++i)
+  {
+    float* c = canvas_rgba + 4 * (size_t)i;
+    if (c[3] >= 1.f) continue;
+    const float alpha = bg[3] * (1.f - c[3]);
+    c[0] = c[0] + bg[0] * alpha;
+    c[1] = c[1] + bg[1] * alpha;
+    c[2] = c[2] + bg[2] * alpha;
+    c[3] = alpha + c[3];
+  }
+}
+
+/* ---- PNGEncoder::Encode(const float*,...), src/libs/png_utils/ascent_png_encoder.cpp:257-281 (called by
+ * Render::Save, Render.cpp:299-312): (unsigned char)(c * 255.f) per channel, rows flipped vertically. */
+ORC_API void orc_encode_rgba8(const float* canvas_rgba, int width, int height, int flip, uint8_t* out)
+{
+  for (int y = 0; y < height; ++y)
+    for (int x = 0; x < width; ++x)
+    {
+      const size_t in = ((size_t)y * width + x) * 4;
+      const size_t o = ((size_t)(flip ? height - y - 1 : y) * width + x) * 4;
+      for (int k = 0; k < 4; ++k)
+        out[o + k] = (uint8_t)(long long)(canvas_rgba[in + k] * 255.f); /* x86: cvttss2si, low byte */
+    }
 }
 
 /* ---- P1: VolumePartial::blend, src/libs/vtkh/compositing/VolumePartial.hpp:86-95 */

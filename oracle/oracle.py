@@ -278,6 +278,21 @@ def image_to_canvas(rgba_u8, depth):
     return out, od
 
 
+def blend_background(canvas_rgba, bg):
+    """Canvas::BlendBackground in place (Render::RenderBackground)."""
+    assert canvas_rgba.dtype == np.float32 and canvas_rgba.flags.c_contiguous
+    b = np.ascontiguousarray(bg, np.float32)
+    lib.orc_blend_background(_ptr(canvas_rgba, C.c_float), canvas_rgba.size // 4, _ptr(b, C.c_float))
+
+
+def encode_rgba8(canvas_rgba, W, H, flip=True):
+    """PNGEncoder::Encode's float -> uint8 conversion (rows flipped like the PNG on disk)."""
+    c = np.ascontiguousarray(canvas_rgba, np.float32)
+    out = np.zeros((H, W, 4), np.uint8)
+    lib.orc_encode_rgba8(_ptr(c, C.c_float), W, H, int(flip), _ptr(out, C.c_uint8))
+    return out
+
+
 def composite_partials(partial_lists):
     """PartialCompositor::composite for a list of per-domain partial arrays (single rank)."""
     allp = (np.concatenate(partial_lists) if len(partial_lists) else np.zeros(0, PARTIAL_DTYPE))

@@ -92,8 +92,11 @@ def gpu_checks(rank, world):
             fused = rep == 1 or layers  # pixels stored straight into rank 0's canvas, no list
             if layers:
                 ctx.layers_begin(W, H)
-                for i in mine:
-                    ctx.trace_to_layer(i, cam, sc["sample_dist"], rmin, rmax, False)
+                if rep == 4:   # the whole block loop in one call, launches overlapped
+                    ctx.trace_blocks_to_layers(mine, cam, sc["sample_dist"], rmin, rmax, False)
+                else:
+                    for i in mine:
+                        ctx.trace_to_layer(i, cam, sc["sample_dist"], rmin, rmax, False)
                 ctx.comm_layers_composite_to_canvas(cam)
             else:
                 ctx.partials_begin(W, H)
@@ -179,6 +182,71 @@ def gpu_checks(rank, world):
                 assert np.array_equal(can, o_can) and np.array_equal(cd, o_cd, equal_nan=True), "path A canvas (rep %d)" % rep
                 cov = ref[:, 3] > 0
                 assert cov.sum() > 1000
+            else:
+                ctx.synchronize()
+            dist.barrier()
+
+        # ---------------- opaque surfaces + volume (Scene::Render passes 1 and 2, Scene.cpp:160-214):
+        # every rank holds an opaque canvas (here: synthetic fragments, incl. cross-rank depth ties and
+        # far fragments) -> z-buffer composite to rank 0 -> ImageToCanvas -> SynchDepths -> volume pass
+        # clamped at the synchronised depth, blended over each rank's canvas -> vis-order composite
+        cam = O.camera_reset_to_bounds(gb)
+        O.camera_azimuth(cam, 20.0)
+        vis_all, _ = D.global_visibility_order([bounds[rank]], cam, dist)
+        vo = np.ascontiguousarray(vis_all[:, 0], np.int32)
+        for rep in range(3):
+            def opaque(r):
+                g = np.random.default_rng(100 * rep + r)
+                col = np.zeros((H, W, 4), np.float32)
+                dep = np.full((H, W), 1.001, np.float32)
+                for _ in range(6):
+                    x0, y0 = int(g.integers(0, W - 40)), int(g.integers(0, H - 30))
+                    w, h = int(g.integers(20, 160)), int(g.integers(20, 120))
+                    col[y0:y0 + h, x0:x0 + w] = [g.random(), g.random(), g.random(), 1.0]
+                    # a small set of depth values so that fragments of different ranks tie exactly
+                    dep[y0:y0 + h, x0:x0 + w] = np.float32(g.choice([0.80, 0.90, 0.95, 0.97, 0.99]))
+                dep[:8, :] = np.float32(1.5)  # beyond the far plane: never replaces
+                col[:8, :] = [0.3, 0.3, 0.3, 1.0]
+                return col.reshape(-1, 4), dep.reshape(-1)
+            my_col, my_dep = opaque(rank)
+            ctx.canvas_upload(W, H, my_col, my_dep)
+            ctx.image_from_canvas()
+            ctx.comm_composite_zbuffer()
+            if rank == 0:
+                ctx.image_result_to_canvas()
+                zu8, zd = ctx.image_result_download(W, H)
+            ctx.comm_sync_depths()
+            ctx.trace_to_canvas(0, cam, sd, rmin, rmax, True)
+            sync_can, sync_depth = ctx.canvas_download(W, H)
+            ctx.image_from_canvas()
+            ctx.comm_composite_images(vo)
+            # ---- oracle, every rank computes the whole thing (small) and checks its own part
+            cols, deps = zip(*[opaque(r) for r in range(world)])
+            front, fd = O.image_init(cols[0], deps[0], 0)
+            for r in range(1, world):
+                q, dq = O.image_init(cols[r], deps[r], 0)
+                O.zbuffer_composite(front, fd, q, dq, gl_depth=True)
+            root_can, root_depth = O.image_to_canvas(front, fd)
+            layers, depths = [], []
+            for r in range(world):
+                c_r = (root_can if r == 0 else cols[r]).copy()
+                d_r = root_depth.copy()   # SynchDepths: rank 0's depth everywhere
+                O.render_to_canvas(scenes.oracle_block(doms[r]), cam, W, H, sc["lut"], sd, rmin, rmax, c_r, d_r,
+                                   use_depth=True)
+                if r == rank:
+                    assert np.array_equal(sync_can, c_r), "opaque+volume: canvas after the volume pass (rep %d)" % rep
+                    assert np.array_equal(sync_depth, d_r, equal_nan=True), "opaque+volume: depth (rep %d)" % rep
+                q = O.image_init(c_r, d_r, 0)
+                layers.append(q[0])
+                depths.append(q[1])
+            if rank == 0:
+                assert np.array_equal(zu8, front) and np.array_equal(zd, fd), "z-buffer composite differs (rep %d)" % rep
+                assert (front[:, 3] == 255).sum() > 1000
+                order, _ = O.visibility_order(np.array(bounds), cam)
+                ref, rd = O.ordered_composite(np.stack(layers), np.stack(depths), order)
+                u8, d = ctx.image_result_download(W, H)
+                assert np.array_equal(u8, ref) and np.array_equal(d, rd, equal_nan=True), \
+                    "opaque+volume: final composite differs (rep %d)" % rep
             else:
                 ctx.synchronize()
             dist.barrier()

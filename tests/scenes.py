@@ -34,10 +34,9 @@ def field_range(doms):
 def png_bytes(canvas_rgba, W, H, bg=(0., 0., 0., 1.)):
     """Render::RenderBackground (BlendBackground: c + bg*(1-a)) then PNGEncoder
     ((uchar)(c*255.f), ascent_png_encoder.cpp:274-281); rows left un-flipped."""
-    bgc = np.array(bg, np.float32)
-    a = canvas_rgba[:, 3:4]
-    c = canvas_rgba + bgc[None, :] * (np.float32(1) - a)
-    return (c * np.float32(255.0)).astype(np.uint8).reshape(H, W, 4)
+    c = np.ascontiguousarray(canvas_rgba, np.float32).copy()
+    O.blend_background(c, bg)
+    return O.encode_rgba8(c, W, H, flip=False)
 
 
 def multi_render_scene(which):

@@ -407,6 +407,98 @@ def test_layers_equal_list_pipeline(ctx, n_block, per_axis, az, res):
         ctx.block_free(i)
 
 
+@pytest.mark.parametrize("n_block,per_axis,az,res", [(12, 2, 0.0, (240, 200)), (7, 4, 61.0, (320, 180))])
+def test_batched_block_loop_equals_per_block_calls(ctx, n_block, per_axis, az, res):
+    """vr_trace_blocks_to_layers (whole RenderMultipleDomainsPerRank loop, launches overlapped on side
+    streams) leaves the same layers and the same canvas as one vr_trace_to_layer per block."""
+    doms = datasets.braid_uniform_blocks(n_block, per_axis, dtype=np.float32)
+    gb = datasets.union_bounds([datasets.domain_bounds(d) for d in doms])
+    W, H = res
+    cam = O.camera_reset_to_bounds(gb)
+    O.camera_azimuth(cam, az)
+    lut = color_table.parse_color_table(scenes.RAMP_TF).corrected_opacity(100).lut()
+    sd = O.sample_distance(gb, 100)
+    rmin, rmax = scenes.field_range(doms)
+    ctx.set_tf(lut)
+    for i, d in enumerate(doms):
+        ctx.block_from_domain(i, d)
+    layer_frame(ctx, doms, cam, W, H, sd, rmin, rmax)
+    ctx.layers_composite_to_canvas(cam, canvas_is_clear=True)
+    c_a, d_a = ctx.canvas_download(W, H)
+    ctx.layers_to_partials()
+    p_a = np.sort(ctx.partials_download(), order=["pixel_id", "depth"])
+    for _ in range(2):  # twice: the per-launch counters are re-armed every call
+        ctx.layers_begin(W, H)
+        ctx.trace_blocks_to_layers(list(range(len(doms))), cam, sd, rmin, rmax, False)
+        ctx.layers_composite_to_canvas(cam, canvas_is_clear=True)
+        c_b, d_b = ctx.canvas_download(W, H)
+        assert np.array_equal(c_a, c_b) and np.array_equal(d_a, d_b)
+    ctx.layers_to_partials()
+    p_b = np.sort(ctx.partials_download(), order=["pixel_id", "depth"])
+    assert p_a.size == p_b.size > 1000
+    assert np.array_equal(np.sort(p_a.view(np.uint8).reshape(-1, 24), axis=0),
+                          np.sort(p_b.view(np.uint8).reshape(-1, 24), axis=0))
+    # split over two calls in one frame == one call
+    ctx.layers_begin(W, H)
+    half = len(doms) // 2
+    ctx.trace_blocks_to_layers(list(range(half)), cam, sd, rmin, rmax, False)
+    ctx.trace_blocks_to_layers(list(range(half, len(doms))), cam, sd, rmin, rmax, False)
+    ctx.layers_composite_to_canvas(cam, canvas_is_clear=True)
+    c_c, d_c = ctx.canvas_download(W, H)
+    assert np.array_equal(c_a, c_c) and np.array_equal(d_a, d_c)
+    with pytest.raises(_lib.VRError):
+        ctx.trace_blocks_to_layers([0, 9999], cam, sd, rmin, rmax, False)
+    for i in range(len(doms)):
+        ctx.block_free(i)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "rectilinear"])
+def test_host_mapped_field_is_sampled_in_place(ctx, kind):
+    """VR_HOST_MAPPED: a page-locked host field sampled over PCIe gives the same frame, bit for bit,
+    as the copied field; the library sees later writes to the host array (no copy was made); plain
+    pageable memory is refused."""
+    import torch
+    n = 40
+    dom = datasets.braid_uniform(n, dtype=np.float32) if kind == "uniform" else \
+        datasets.braid_rectilinear(n, power=1.5, dtype=np.float32)
+    b = datasets.domain_bounds(dom)
+    W, H = 320, 200
+    cam = O.camera_reset_to_bounds(b)
+    O.camera_azimuth(cam, 25.0)
+    lut = color_table.parse_color_table(scenes.RAMP_TF).corrected_opacity(100).lut()
+    sd = O.sample_distance(b, 100)
+    rmin, rmax = scenes.field_range([dom])
+    ctx.set_tf(lut)
+
+    def publish(field, mapped):
+        if kind == "uniform":
+            ctx.block_uniform(0, dom["dims"], dom["origin"], dom["spacing"], field, host_mapped=mapped)
+        else:
+            ctx.block_rectilinear(0, dom["dims"], dom["axes"], field, host_mapped=mapped)
+
+    def frame():
+        ctx.trace_to_image(0, cam, W, H, sd, rmin, rmax, write_canvas=True)
+        return ctx.canvas_download(W, H)
+
+    publish(dom["field"], False)
+    c_copy, d_copy = frame()
+    pinned = torch.empty(dom["field"].size, dtype=torch.float32, pin_memory=True)
+    host = pinned.numpy()
+    host[:] = dom["field"].reshape(-1)
+    publish(host, True)
+    c_map, d_map = frame()
+    assert np.array_equal(c_copy, c_map) and np.array_equal(d_copy, d_map)
+    assert (c_map[:, 3] > 0).sum() > 1000
+    # in place: a change of the host array shows up in the next frame without re-publishing
+    ctx.synchronize()
+    host[:] = np.float32(rmax)
+    c_new, _ = frame()
+    assert not np.array_equal(c_new, c_map)
+    with pytest.raises(_lib.VRError):
+        publish(dom["field"].copy(), True)
+    ctx.block_free(0)
+
+
 @pytest.mark.parametrize("n_slabs", [40, 200])
 def test_layers_deep_pixels(ctx, n_slabs):
     """more entries per pixel than the in-register ordering holds (32) and more layers over one
@@ -522,6 +614,79 @@ def test_partial_composite_random_with_ties(ctx, seed):
     assert ctx.composite_partials(p[:0], W, H).size == 0
     one = ctx.composite_partials(p[:1], W, H)
     assert one.tobytes() == p[:1].tobytes()
+
+
+@pytest.mark.parametrize("bg", [(0., 0., 0., 1.), (1., 1., 1., 1.), (0.2, 0.4, 0.6, 0.5)])
+def test_frame_epilogue_background_and_rgba8(ctx, bg):
+    """Render::RenderBackground + the PNGEncoder conversion of Render::Save on the device: bit-exact
+    vs the oracle (which the reference's render goldens pin), fused and unfused, flipped and not."""
+    sc = scenes.multi_render_scene(0)
+    W, H = sc["W"], sc["H"]
+    rgba, _ = gpu_path_a_canvas(ctx, sc["doms"][0], sc)
+    ref = rgba.copy()
+    O.blend_background(ref, bg)
+    fused = ctx.canvas_download_rgba8(W, H, bg=bg, flip=True)
+    assert np.array_equal(fused, O.encode_rgba8(ref, W, H, flip=True))
+    again, _ = ctx.canvas_download(W, H)
+    assert np.array_equal(again, rgba)          # the fused form leaves the canvas alone
+    ctx.canvas_blend_background(bg)
+    blended, _ = ctx.canvas_download(W, H)
+    assert np.array_equal(blended, ref)
+    assert np.array_equal(ctx.canvas_download_rgba8(W, H, flip=False), O.encode_rgba8(ref, W, H, flip=False))
+    # values outside [0,1] and NaN convert like the x86 cast (low byte of the truncated integer)
+    rng = np.random.default_rng(5)
+    odd = (rng.random((H * W, 4), dtype=np.float32) * 3 - 1).astype(np.float32)
+    odd[::97, 0] = np.nan
+    ctx.canvas_upload(W, H, odd, np.zeros(H * W, np.float32))
+    assert np.array_equal(ctx.canvas_download_rgba8(W, H, flip=True), O.encode_rgba8(odd, W, H, flip=True))
+
+
+def _zbuffer_oracle(rgba, depth):
+    """vtk-h Compositor in Z_BUFFER_SURFACE mode on one rank (Compositor.cpp:146-160): Image::Init of
+    every image, z-selected into the first one in the order they were added."""
+    front, fd = O.image_init(rgba[0], depth[0], 0)
+    for i in range(1, len(rgba)):
+        q, d = O.image_init(rgba[i], depth[i], 0)
+        O.zbuffer_composite(front, fd, q, d, gl_depth=True)
+    return front, fd
+
+
+def test_zbuffer_apcomp_scene_through_abi(ctx, golden_dir):
+    """t_apcomp_zbuffer.cpp:26-68 (four overlapping opaque squares, depth 0.05*i over a 1.01
+    background) through vr_composite_zbuffer: bit-exact vs the oracle and the reference's golden."""
+    import os
+    W = H = 1024
+    rgba, depth = [], []
+    for i in range(4):
+        c = np.float32(0.1) + np.float32(i) * np.float32(0.1)
+        px = np.zeros((H, W, 4), np.float32)
+        dp = np.full((H, W), 1.01, np.float32)
+        px[400:700, 200 + 100 * i:500 + 100 * i] = [c, c, c, 1.0]
+        dp[400:700, 200 + 100 * i:500 + 100 * i] = np.float32(i) * np.float32(0.05)
+        rgba.append(px.reshape(-1, 4))
+        depth.append(dp.reshape(-1))
+    out, od = ctx.composite_zbuffer(np.stack(rgba), np.stack(depth), W, H)
+    ref, rd = _zbuffer_oracle(rgba, depth)
+    assert np.array_equal(out, ref) and np.array_equal(od, rd)
+    g = np.load(os.path.join(golden_dir, "apcomp_goldens.npz"))["apcomp_zbuffer"]
+    assert np.array_equal(out.reshape(H, W, 4), g)
+    assert tuple(out.reshape(H, W, 4)[600, 450]) == (25, 25, 25, 255)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_zbuffer_random_with_ties_and_far_fragments(ctx, seed):
+    """ImageCompositor::ZBufferComposite (ImageCompositor.hpp:49-76) edge cases: equal depths (the
+    later image wins), fragments beyond depth 1 (never replace, also not a farther one), negative
+    depths (Image::Init makes them positive first)."""
+    rng = np.random.default_rng(seed)
+    W, H, n = 203, 77, 5
+    rgba = rng.random((n, H * W, 4), dtype=np.float32)
+    depth = rng.choice(np.array([0.0, 0.25, 0.25, 0.5, 0.75, 1.0, 1.001, 1.01, 1.5, -0.3], np.float32),
+                       size=(n, H * W))
+    depth[:, ::7] = rng.random((n, depth[:, ::7].shape[1]), dtype=np.float32)
+    out, od = ctx.composite_zbuffer(rgba, depth, W, H)
+    ref, rd = _zbuffer_oracle(list(rgba), list(depth))
+    assert np.array_equal(out, ref) and np.array_equal(od, rd)
 
 
 def test_path_a_single_rank_roundtrip(ctx):
