@@ -108,7 +108,8 @@ constexpr int kChunkGroups = 256; // 4-pixel groups per ownership chunk
 // with depth > 1 never replace -- folded over the ranks in rank order.  Select-nearest is associative
 // and commutative for distinct depths, so the radix-k tree and this direct-send fold give the same
 // image; fragments of different ranks at EXACTLY equal depth resolve to the higher rank here.
-template <bool TO_CANVAS, bool ZBUF>
+// NR: number of ranks rounded up to a power of two (the per-layer registers are fully unrolled).
+template <int NR, bool TO_CANVAS, bool ZBUF>
 __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ FoldP2PParams P)
 {
   Flags* my_flags = reinterpret_cast<Flags*>(P.peers[P.rank] + P.off_flags);
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
   }
   // ---- wait until every rank's image is complete
   if (threadIdx.x < P.size)
-    while (ld_acquire_sys(&my_flags->ready[threadIdx.x]) < P.epoch) __nanosleep(64);
+    while (ld_acquire_sys(&my_flags->ready[threadIdx.x]) < P.epoch) __nanosleep(32);
   __syncthreads();
 
   __shared__ int s_rect[kMaxRanks][4]; // in fold order
@@ -135,10 +136,10 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
   }
   __syncthreads();
 
-  const uint4* layer_rgba[kMaxRanks];
-  const float4* layer_depth[kMaxRanks];
+  const uint4* layer_rgba[NR];
+  const float4* layer_depth[NR];
 #pragma unroll
-  for (int l = 0; l < kMaxRanks; ++l)
+  for (int l = 0; l < NR; ++l)
     if (l < P.size)
     {
       layer_rgba[l] = reinterpret_cast<const uint4*>(P.peers[P.order[l]] + P.off_img_rgba);
@@ -151,41 +152,46 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
   const size_t n4 = (P.n_pixels + 3) / 4;
   const int w4 = P.W >= 4 ? P.W / 4 : 1;
   const size_t n_chunks = (n4 + kChunkGroups - 1) / kChunkGroups;
-  // my chunks: rank, rank + size, ...; rank 0 also walks the others' chunks for uncovered groups
-  for (size_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x)
-  {
-    const bool mine = (int)(chunk % (size_t)P.size) == P.rank;
-    if (!mine && P.rank != 0) continue;
-    const size_t i = chunk * kChunkGroups + threadIdx.x;
-    if (i >= n4) continue;
+
+  auto coverage = [&](size_t i) -> unsigned {
     const int y = (int)(i / (size_t)w4), x = (int)(i % (size_t)w4) * 4;
     unsigned cover = 0;
 #pragma unroll
-    for (int l = 0; l < kMaxRanks; ++l)
+    for (int l = 0; l < NR; ++l)
       if (l < P.size && y >= s_rect[l][1] && y < s_rect[l][3] && x >= s_rect[l][0] && x < s_rect[l][2])
         cover |= 1u << l;
+    return cover;
+  };
+  auto write_empty = [&](size_t i) {
+    out_rgba[i] = make_uint4(0u, 0u, 0u, 0u);
+    // N >= 2 all-clear layers fold to min(min(1.001,1.001), ...) = 1.001; one layer is copied
+    out_depth[i] = make_float4(1.001f, 1.001f, 1.001f, 1.001f);
+    if (TO_CANVAS)
+    {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) P.canvas_rgba[4 * i + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      reinterpret_cast<float4*>(P.canvas_depth)[i] = make_float4(1.001f, 1.001f, 1.001f, 1.001f);
+    }
+  };
+
+  // ---- my chunks: rank, rank + size, rank + 2 size, ... dealt to the CTAs one after the other
+  const size_t n_mine = n_chunks > (size_t)P.rank ? (n_chunks - 1 - (size_t)P.rank) / (size_t)P.size + 1 : 0;
+  for (size_t k = blockIdx.x; k < n_mine; k += gridDim.x)
+  {
+    const size_t chunk = k * (size_t)P.size + (size_t)P.rank;
+    const size_t i = chunk * kChunkGroups + threadIdx.x;
+    if (i >= n4) continue;
+    const unsigned cover = coverage(i);
     if (cover == 0)
     {
-      if (P.rank == 0)
-      {
-        out_rgba[i] = make_uint4(0u, 0u, 0u, 0u);
-        // N >= 2 all-clear layers fold to min(min(1.001,1.001), ...) = 1.001; one layer is copied
-        out_depth[i] = make_float4(1.001f, 1.001f, 1.001f, 1.001f);
-        if (TO_CANVAS)
-        {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) P.canvas_rgba[4 * i + k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          reinterpret_cast<float4*>(P.canvas_depth)[i] = make_float4(1.001f, 1.001f, 1.001f, 1.001f);
-        }
-      }
+      if (P.rank == 0) write_empty(i);
       continue;
     }
-    if (!mine) continue;
     // issue all covering layer loads first (independent 16-byte NVLink reads)
-    uint4 c[kMaxRanks];
-    float4 d[kMaxRanks];
+    uint4 c[NR];
+    float4 d[NR];
 #pragma unroll
-    for (int l = 0; l < kMaxRanks; ++l)
+    for (int l = 0; l < NR; ++l)
       if (l < P.size)
       {
         if (cover & (1u << l))
@@ -202,7 +208,7 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
     uint4 f = c[0];
     float4 fd = d[0];
 #pragma unroll
-    for (int l = 1; l < kMaxRanks; ++l)
+    for (int l = 1; l < NR; ++l)
       if (l < P.size)
       {
         if (ZBUF)
@@ -228,6 +234,15 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
     out_rgba[i] = f;
     out_depth[i] = fd;
   }
+  // ---- rank 0 also writes the groups NO rank covers inside the other ranks' chunks (their owners skip
+  // them); streaming stores into local HBM while the peers' folded pixels are still in flight
+  if (P.rank == 0 && P.size > 1)
+    for (size_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x)
+    {
+      if (chunk % (size_t)P.size == 0) continue;
+      const size_t i = chunk * kChunkGroups + threadIdx.x;
+      if (i < n4 && coverage(i) == 0) write_empty(i);
+    }
 
   // ---- last CTA out tells rank 0 that my range has landed
   __syncthreads();
@@ -250,6 +265,11 @@ __global__ void __launch_bounds__(256) covered_to_canvas_kernel(const __grid_con
 {
   const Flags* my_flags = reinterpret_cast<const Flags*>(P.peers[0] + P.off_flags);
   const int par = P.epoch & 1;
+  // every rank's folded range has landed in my result image (what wait_done_kernel does, without
+  // the extra launch)
+  if (threadIdx.x < P.size)
+    while (ld_acquire_sys(&my_flags->done[threadIdx.x]) < P.epoch) __nanosleep(32);
+  __syncthreads();
   __shared__ int s_rect[kMaxRanks][4];
   if (threadIdx.x < P.size * 4) s_rect[threadIdx.x >> 2][threadIdx.x & 3] = my_flags->img_rect[par][threadIdx.x >> 2][threadIdx.x & 3];
   __syncthreads();
@@ -574,12 +594,33 @@ Layout make_layout(size_t max_pixels, size_t max_partials, bool is_root)
 
 } // namespace
 
+template <int NR>
+static cudaError_t launch_fold_p2p_nr(const FoldP2PParams& p, int sm_count, cudaStream_t s)
+{
+  auto go = [&](auto kernel) {
+    // persistent grid = the CTAs resident at once (register-limited), capped by this rank's chunks
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0);
+    if (per_sm < 1) per_sm = 1;
+    const size_t n4 = (p.n_pixels + 3) / 4;
+    const size_t n_chunks = (n4 + kChunkGroups - 1) / kChunkGroups;
+    size_t grid = (size_t)sm_count * per_sm;
+    const size_t want = p.rank == 0 ? n_chunks : (n_chunks + p.size - 1) / p.size;
+    if (grid > want) grid = want ? want : 1;
+    kernel<<<(unsigned)grid, 256, 0, s>>>(p);
+  };
+  if (p.zbuffer) go(fold_p2p_kernel<NR, false, true>);
+  else if (p.canvas_rgba) go(fold_p2p_kernel<NR, true, false>);
+  else go(fold_p2p_kernel<NR, false, false>);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_fold_p2p(const FoldP2PParams& p, int sm_count, cudaStream_t s)
 {
-  if (p.zbuffer) fold_p2p_kernel<false, true><<<sm_count * 2, 256, 0, s>>>(p);
-  else if (p.canvas_rgba) fold_p2p_kernel<true, false><<<sm_count * 2, 256, 0, s>>>(p);
-  else fold_p2p_kernel<false, false><<<sm_count * 2, 256, 0, s>>>(p);
-  return cudaGetLastError();
+  if (p.size <= 2) return launch_fold_p2p_nr<2>(p, sm_count, s);
+  if (p.size <= 4) return launch_fold_p2p_nr<4>(p, sm_count, s);
+  if (p.size <= 8) return launch_fold_p2p_nr<8>(p, sm_count, s);
+  return launch_fold_p2p_nr<16>(p, sm_count, s);
 }
 
 void comm_destroy(vr_ctx* ctx)
@@ -787,20 +828,24 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
   if (c.rank == 0)
   {
     const Flags* f = reinterpret_cast<const Flags*>(c.arena + L.off_flags);
-    wait_done_kernel<<<1, 32, 0, ctx->stream>>>(f->done, c.size, c.epoch);
-    ctx->launches++;
     // result of this epoch (res_* currently points at parity b)
     ctx->res_rgba = reinterpret_cast<uchar4*>(c.arena + L.off_res_rgba[b]);
     ctx->res_depth = reinterpret_cast<float*>(c.arena + L.off_res_depth[b]);
     if (p.canvas_rgba)
     {
+      // waits for every rank's "done" itself, then converts the covered groups
       covered_to_canvas_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(p);
       ctx->launches++;
     }
-    else if (to_canvas)
+    else
     {
-      vr_status st = vr_image_result_to_canvas(ctx);
-      if (st != VR_OK) return st;
+      wait_done_kernel<<<1, 32, 0, ctx->stream>>>(f->done, c.size, c.epoch);
+      ctx->launches++;
+      if (to_canvas)
+      {
+        vr_status st = vr_image_result_to_canvas(ctx);
+        if (st != VR_OK) return st;
+      }
     }
   }
   // next frame quantises into the other parity

@@ -634,12 +634,15 @@ void VolumeRenderer::RenderMultipleDomainsPerRank()
     // wrapper->render(camera, canvas, partials) per domain (VolumeRenderer.cpp:561-577): the rays of
     // each structured block stay in a dense layer on the device
     m_ctx->Check(vr_layers_begin(m_ctx->h, W, H));
+    std::vector<int> ids;
     for (int i = 0; i < m_input->GetNumberOfDomains(); ++i)
     {
       const DataSet::Domain& d = m_input->GetDomain(i);
-      if (!d.Find(m_field_name)) continue;
-      m_ctx->Check(vr_trace_to_layer(m_ctx->h, d.id, &cam, m_sample_dist, rmin, rmax, r.IsCleared() ? 0 : 1));
+      if (d.Find(m_field_name)) ids.push_back(d.id);
     }
+    // the whole per-domain loop in one call: consecutive blocks overlap on the GPU
+    m_ctx->Check(vr_trace_blocks_to_layers(m_ctx->h, (int)ids.size(), ids.data(), &cam, m_sample_dist, rmin, rmax,
+                                           r.IsCleared() ? 0 : 1));
     // PartialCompositor::composite + partials_to_canvas (VolumeRenderer.cpp:580-595), one kernel
     m_ctx->Check(vr_layers_composite_to_canvas(m_ctx->h, &cam, r.IsCleared() ? 1 : 0));
     m_ctx->Check(vr_canvas_download(m_ctx->h, r.GetColorBuffer().data(), r.GetDepthBuffer().data()));

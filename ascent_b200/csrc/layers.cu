@@ -35,6 +35,7 @@ namespace
 constexpr int kTileW = 32, kTileH = 8;           // 256 threads
 constexpr int kMaxTileLayers = 192;              // layers overlapping one tile (smem list)
 constexpr int kMaxSeg = 32;                      // entries per pixel ordered in local memory
+constexpr int kBatch = 8;                        // layer entries requested together per pixel
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v)
 {
@@ -169,42 +170,60 @@ __global__ void __launch_bounds__(kTileW* kTileH) layers_fold_kernel(const __gri
     const int x = tx0 + lx, y = ty0 + ly;
     if (x < P.W && y < P.H)
     {
-      // ---- gather this pixel's entries, insertion-sorted by (exit distance, rank, block)
+      // ---- gather this pixel's entries, insertion-sorted by (exit distance, rank, block).  The
+      // entries of up to kBatch overlapping layers are requested together (independent loads, remote
+      // ones cross NVLink): one round trip per batch instead of two per layer, and the colour is
+      // kept so the fold below does not ask again.
       float kd[kMaxSeg];
       int ko[kMaxSeg];
-      unsigned short kl[kMaxSeg];
+      float4 kq[kMaxSeg];
       int c = 0;
       bool deep = false;
-      for (int l = 0; l < nt; ++l)
+      for (int l0 = 0; l0 < nt && !deep; l0 += kBatch)
       {
-        const TileLayer L = fetch(l);
-        if (x < L.x0 || x >= L.x1 || y < L.y0 || y >= L.y1) continue;
-        const size_t e = (size_t)(y - L.y0) * L.w + (x - L.x0);
-        const float alpha = L.rgba[e].w;
-        if (alpha < 0.001f) continue; // the reference's `if(alpha < 0.001f) continue;` (:270-272)
-        if (c == kMaxSeg) { deep = true; break; }
-        const float d = L.depth[e];
-        int b = c - 1;
-        while (b >= 0 && (kd[b] > d || (kd[b] == d && ko[b] > L.order)))
+        float4 q[kBatch];
+        float d[kBatch];
+        int ord[kBatch];
+        bool in[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u)
         {
-          kd[b + 1] = kd[b]; ko[b + 1] = ko[b]; kl[b + 1] = kl[b];
-          --b;
+          in[u] = false;
+          if (l0 + u < nt)
+          {
+            const TileLayer L = fetch(l0 + u);
+            if (!(x < L.x0 || x >= L.x1 || y < L.y0 || y >= L.y1))
+            {
+              const size_t e = (size_t)(y - L.y0) * L.w + (x - L.x0);
+              q[u] = L.rgba[e];
+              d[u] = L.depth[e];
+              ord[u] = L.order;
+              in[u] = true;
+            }
+          }
         }
-        kd[b + 1] = d; ko[b + 1] = L.order; kl[b + 1] = (unsigned short)l;
-        ++c;
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u)
+        {
+          if (!in[u] || q[u].w < 0.001f) continue; // the reference's `if(alpha < 0.001f) continue;` (:270-272)
+          if (c == kMaxSeg) { deep = true; break; }
+          int b = c - 1;
+          while (b >= 0 && (kd[b] > d[u] || (kd[b] == d[u] && ko[b] > ord[u])))
+          {
+            kd[b + 1] = kd[b]; ko[b + 1] = ko[b]; kq[b + 1] = kq[b];
+            --b;
+          }
+          kd[b + 1] = d[u]; ko[b + 1] = ord[u]; kq[b + 1] = q[u];
+          ++c;
+        }
       }
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       float first_depth = 0.f;
       bool any = false;
       if (!deep)
       {
-        for (int a = 0; a < c; ++a)
-        {
-          const TileLayer L = fetch(kl[a]);
-          const float4 q = L.rgba[(size_t)(y - L.y0) * L.w + (x - L.x0)];
-          if (a == 0) { acc = q; first_depth = kd[0]; any = true; }
-          else blend(acc, q);
-        }
+        if (c > 0) { acc = kq[0]; first_depth = kd[0]; any = true; }
+        for (int a = 1; a < c; ++a) blend(acc, kq[a]);
       }
       else
       {
@@ -341,7 +360,12 @@ cudaError_t launch_layers_fold(const LayerFoldParams& p, bool comm, int sm_count
     attr_set = true;
   }
   const long long tiles = (long long)((p.W + kTileW - 1) / kTileW) * ((p.H + kTileH - 1) / kTileH);
-  long long grid = (long long)sm_count * 4;
+  // persistent grid: exactly the CTAs that are resident at once (registers and the table's smem decide)
+  int per_sm = 0;
+  if (comm) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layers_fold_kernel<true>, kTileW * kTileH, smem);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layers_fold_kernel<false>, kTileW * kTileH, smem);
+  if (per_sm < 1) per_sm = 1;
+  long long grid = (long long)sm_count * per_sm;
   const long long mine = (tiles + p.size - 1) / p.size;
   if (grid > mine) grid = mine > 0 ? mine : 1;
   if (comm) layers_fold_kernel<true><<<(int)grid, kTileW * kTileH, smem, s>>>(p);

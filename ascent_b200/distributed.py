@@ -223,6 +223,9 @@ def run_bench(args, wl, bench):
 
     t = torch.tensor([total_ms, render_ms, tail_ms, comp_ms, float(launches), float(n_partials)],
                      dtype=torch.float64, device="cuda")
+    per_rank = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(per_rank, t)
+    per_rank = [[round(float(x), 4) for x in pr[:4]] for pr in per_rank]
     tmax = t.clone()
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     tsum = t.clone()
@@ -269,6 +272,8 @@ def run_bench(args, wl, bench):
                 "frames_per_s": 1e3 / ms, "render_ms_per_frame": render_ms,
                 "composite_ms_per_frame": comp_ms, "composite_in_step_ms": tail_ms,
                 "partials_total": int(tsum[5]),
+                "per_rank_ms": {"columns": ["total", "render_per_frame", "composite_in_step", "composite_aligned"],
+                                "rows": per_rank},
                 "nvlink": {"bytes_into_rank0_per_frame": nv_bytes, "pulled": pulled, "pushed_into_rank0": pushed,
                            "achieved_gbs": nv_bytes / (comp_ms * 1e-3) / 1e9, "peak_gbs": 770.0,
                            "peak_source": "measured peer copy per direction (B200_PROFILING.md)"},

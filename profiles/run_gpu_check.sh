@@ -12,6 +12,7 @@ timeout 600 python bench.py --steps 50 --warmup 5 > $O/${TAG}_bench_c2.json 2> $
 timeout 300 python bench.py --workload c3 --steps 20 --no-cpu > $O/${TAG}_bench_c3_n1.json 2> $O/${TAG}_bench_c3.err; cat $O/${TAG}_bench_c3_n1.json
 timeout 300 python bench.py --workload c4 --steps 3 --no-cpu > $O/${TAG}_bench_c4.json 2> $O/${TAG}_bench_c4.err; cat $O/${TAG}_bench_c4.json
 timeout 300 python bench.py --workload c5 --steps 10 --no-cpu > $O/${TAG}_bench_c5.json 2> $O/${TAG}_bench_c5.err; cat $O/${TAG}_bench_c5.json
+timeout 300 python bench.py --samples 887 --steps 20 --no-cpu > $O/${TAG}_bench_c2_p1.json 2> $O/${TAG}_bench_c2_p1.err; cat $O/${TAG}_bench_c2_p1.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_ref.json 2> $O/${TAG}_bench_ref.err; cat $O/${TAG}_bench_ref.json
 # launch list of the same bench command (cold-cache, serialised: shares only)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches_c2.csv \
