@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("VR_LIB_NAME", "libvr_b200.so"))
 VR_OK = 0
 VR_F32, VR_F64 = 0, 1
 VR_POINT, VR_CELL = 0, 1
-VR_HOST, VR_DEVICE, VR_HOST_MAPPED = 0, 1, 2
+VR_HOST, VR_DEVICE, VR_HOST_MAPPED, VR_HOST_STAGED = 0, 1, 2, 3
 IPC_HANDLE_BYTES = 64
 FRAME_WRITE_CANVAS, FRAME_NO_CLEAR = 1, 2
 
@@ -22,7 +22,7 @@ FRAME_WRITE_CANVAS, FRAME_NO_CLEAR = 1, 2
 SYMBOLS = [
     "vr_create", "vr_destroy", "vr_last_error", "vr_set_stream", "vr_synchronize",
     "vr_kernel_launches", "vr_block_uniform", "vr_block_rectilinear", "vr_block_free",
-    "vr_block_bounds", "vr_set_tf", "vr_canvas_clear", "vr_canvas_upload", "vr_canvas_download",
+    "vr_block_bounds", "vr_block_staged_bytes", "vr_set_tf", "vr_canvas_clear", "vr_canvas_upload", "vr_canvas_download",
     "vr_canvas_ptrs", "vr_canvas_blend_background", "vr_canvas_download_rgba8", "vr_trace_to_canvas", "vr_render_image", "vr_trace_to_image", "vr_partials_begin",
     "vr_trace_to_partials", "vr_partials_count", "vr_partials_download", "vr_render_partials",
     "vr_free", "vr_layers_begin", "vr_trace_to_layer", "vr_trace_blocks_to_layers", "vr_layers_composite_to_canvas",
@@ -89,6 +89,7 @@ def load():
                                         C.c_float, C.c_int]),
         "vr_canvas_blend_background": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "vr_canvas_download_rgba8": (C.c_int, [vp, C.POINTER(C.c_float), C.c_int, vp]),
+        "vr_block_staged_bytes": (C.c_int, [vp, C.c_int, C.POINTER(sz)]),
         "vr_partials_begin": (C.c_int, [vp, C.c_int, C.c_int]),
         "vr_trace_to_partials": (C.c_int, [vp, C.c_int, cam, C.c_float, C.c_float, C.c_float, C.c_int]),
         "vr_partials_count": (C.c_int, [vp, C.POINTER(sz)]),
@@ -219,21 +220,22 @@ class Context:
 
     # -- blocks
     def block_uniform(self, block_id, dims, origin, spacing, field, assoc=VR_POINT, device_ptr=None,
-                      dtype=None, host_mapped=False):
-        """host_mapped: `field` is page-locked mapped host memory (e.g. a pinned torch tensor's
-        numpy view), sampled in place over PCIe (VR_HOST_MAPPED) instead of copied."""
+                      dtype=None, host_mapped=False, staged=False):
+        """host_mapped / staged: `field` is page-locked mapped host memory (e.g. a pinned torch
+        tensor's numpy view), sampled in place over PCIe (VR_HOST_MAPPED) or staged on demand, only
+        the 128-byte lines the rays touch (VR_HOST_STAGED), instead of copied."""
         if device_ptr is not None:
             ptr, dt, where = C.c_void_p(device_ptr), dtype, VR_DEVICE
         else:
             field = np.ascontiguousarray(field)
             assert field.dtype in (np.float32, np.float64), "fields are f32 or f64"
             ptr, dt, where = C.c_void_p(field.ctypes.data), (VR_F64 if field.dtype == np.float64 else VR_F32), \
-                (VR_HOST_MAPPED if host_mapped else VR_HOST)
+                (VR_HOST_STAGED if staged else VR_HOST_MAPPED if host_mapped else VR_HOST)
         self._ck(self.lib.vr_block_uniform(self.h, block_id, _i3(dims), _f3(origin), _f3(spacing), ptr,
                                            dt, assoc, where))
 
     def block_rectilinear(self, block_id, dims, axes, field, assoc=VR_POINT, device_ptr=None,
-                          dtype=None, host_mapped=False):
+                          dtype=None, host_mapped=False, staged=False):
         ax = [np.ascontiguousarray(a, np.float64) for a in axes]
         if device_ptr is not None:
             ptr, dt, where = C.c_void_p(device_ptr), dtype, VR_DEVICE
@@ -241,11 +243,16 @@ class Context:
             field = np.ascontiguousarray(field)
             assert field.dtype in (np.float32, np.float64), "fields are f32 or f64"
             ptr, dt, where = C.c_void_p(field.ctypes.data), (VR_F64 if field.dtype == np.float64 else VR_F32), \
-                (VR_HOST_MAPPED if host_mapped else VR_HOST)
+                (VR_HOST_STAGED if staged else VR_HOST_MAPPED if host_mapped else VR_HOST)
         dpp = C.POINTER(C.c_double)
         self._ck(self.lib.vr_block_rectilinear(self.h, block_id, _i3(dims), ax[0].ctypes.data_as(dpp),
                                                ax[1].ctypes.data_as(dpp), ax[2].ctypes.data_as(dpp),
                                                ptr, dt, assoc, where))
+
+    def block_staged_bytes(self, block_id):
+        n = C.c_size_t(0)
+        self._ck(self.lib.vr_block_staged_bytes(self.h, block_id, C.byref(n)))
+        return int(n.value)
 
     def block_from_domain(self, block_id, dom):
         assoc = VR_CELL if dom.get("assoc") == "cell" else VR_POINT

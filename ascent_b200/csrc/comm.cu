@@ -30,6 +30,7 @@
 
 namespace vr
 {
+vr_status ensure_frame_pub(vr_ctx* ctx, int W, int H); // vr_api.cu
 
 namespace
 {
@@ -1081,8 +1082,9 @@ extern "C" vr_status vr_comm_layers_composite_to_canvas(vr_ctx* ctx, const vr_ca
   if (st != VR_OK) return st;
   if (c.rank == 0)
   {
-    // Canvas::Clear of the frame on rank 0's arena canvas, before this rank announces "ready"
-    st = vr_canvas_clear(ctx, ctx->lW, ctx->lH);
+    // rank 0's arena canvas takes the frame; Canvas::Clear happens inside the fold kernel (outside the
+    // layers' bounding box by rank 0 itself, inside it by the owner of each tile)
+    st = ensure_frame_pub(ctx, ctx->lW, ctx->lH);
     if (st != VR_OK) return st;
   }
   LayerFoldParams p;

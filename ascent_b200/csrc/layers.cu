@@ -69,8 +69,9 @@ struct TileLayer
   const float* depth;
 };
 
-// COMM: flags/peers are live, only covered pixels are written (rank 0 cleared its canvas before
-// announcing); !COMM: one rank, every pixel of the frame is written (cleared or blended over).
+// COMM: flags/peers are live, the frame starts from a cleared canvas: the owner of a tile writes all
+// of its pixels into rank 0's canvas, rank 0 clears what lies outside the layers' bounding box;
+// !COMM: one rank, every pixel of the frame is written (cleared or blended over).
 template <bool COMM>
 __global__ void __launch_bounds__(kTileW* kTileH) layers_fold_kernel(const __grid_constant__ LayerFoldParams P)
 {
@@ -118,17 +119,60 @@ __global__ void __launch_bounds__(kTileW* kTileH) layers_fold_kernel(const __gri
   }
   __syncthreads();
 
-  const int tiles_x = (P.W + kTileW - 1) / kTileW, tiles_y = (P.H + kTileH - 1) / kTileH;
-  const long long n_tiles = (long long)tiles_x * tiles_y;
   const int lx = threadIdx.x % kTileW, ly = threadIdx.x / kTileW;
   float4* canvas = P.canvas_rgba;
   float* cdepth = P.canvas_depth;
 
-  // tiles are dealt round-robin to the ranks, then to the CTAs of a rank
+  // ---- the tile-aligned bounding box of every layer of the frame: only tiles inside it can hold
+  // a partial; everything outside is Canvas::Clear territory
+  __shared__ int s_box[4];
+  if (threadIdx.x < 32)
+  {
+    int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = 0, y1 = 0;
+    for (int k = threadIdx.x; k < s_total; k += 32)
+    {
+      const LayerDesc d = s_desc[k];
+      x0 = min(x0, d.x0); y0 = min(y0, d.y0); x1 = max(x1, d.x0 + d.w); y1 = max(y1, d.y0 + d.h);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+      x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    if (threadIdx.x == 0)
+    {
+      if (x1 <= x0 || y1 <= y0) x0 = y0 = x1 = y1 = 0;
+      s_box[0] = x0 / kTileW; s_box[1] = y0 / kTileH;
+      s_box[2] = (min(x1, P.W) + kTileW - 1) / kTileW; s_box[3] = (min(y1, P.H) + kTileH - 1) / kTileH;
+    }
+  }
+  __syncthreads();
+  const int btx0 = s_box[0], bty0 = s_box[1];
+  const int btw = s_box[2] - s_box[0], bth = s_box[3] - s_box[1];
+  const long long n_tiles = (long long)btw * bth;
+
+  // ---- Canvas::Clear outside the box: streaming stores, no table look-ups.  One rank: only when the
+  // frame starts from a cleared canvas; N ranks: rank 0 clears its own canvas (the others' pixels land
+  // inside the box only), while the peers' entries are still crossing NVLink.
+  if (COMM ? (P.rank == 0) : (P.clear != 0))
+  {
+    const int px0 = btx0 * kTileW, px1 = (btx0 + btw) * kTileW, py0 = bty0 * kTileH, py1 = (bty0 + bth) * kTileH;
+    const size_t n_px = (size_t)P.W * P.H;
+    for (size_t px = (size_t)blockIdx.x * blockDim.x + threadIdx.x; px < n_px; px += (size_t)gridDim.x * blockDim.x)
+    {
+      const int y = (int)(px / (size_t)P.W), x = (int)(px % (size_t)P.W);
+      if (y >= py0 && y < py1 && x >= px0 && x < px1) continue;
+      canvas[px] = make_float4(0.f, 0.f, 0.f, 0.f);
+      cdepth[px] = 1.001f;
+    }
+  }
+
+  // tiles of the box are dealt round-robin to the ranks, then to the CTAs of a rank
   for (long long t = (long long)P.rank + (long long)blockIdx.x * P.size; t < n_tiles;
        t += (long long)gridDim.x * P.size)
   {
-    const int tx0 = (int)(t % tiles_x) * kTileW, ty0 = (int)(t / tiles_x) * kTileH;
+    const int tx0 = (btx0 + (int)(t % btw)) * kTileW, ty0 = (bty0 + (int)(t / btw)) * kTileH;
     if (threadIdx.x == 0) s_ntile = 0;
     __syncthreads();
     // ---- layers overlapping this tile
@@ -268,8 +312,9 @@ __global__ void __launch_bounds__(kTileW* kTileH) layers_fold_kernel(const __gri
         canvas[px] = o;
         cdepth[px] = dimg;
       }
-      else if (!COMM && P.clear)
+      else if (COMM || P.clear)
       {
+        // inside the box but no partial on this pixel: the cleared canvas value
         canvas[px] = make_float4(0.f, 0.f, 0.f, 0.f);
         cdepth[px] = 1.001f;
       }
@@ -359,6 +404,7 @@ cudaError_t launch_layers_fold(const LayerFoldParams& p, bool comm, int sm_count
     cudaFuncSetAttribute(layers_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr_set = true;
   }
+  // (the kernel restricts itself to the layers' bounding box; the full frame bounds the grid)
   const long long tiles = (long long)((p.W + kTileW - 1) / kTileW) * ((p.H + kTileH - 1) / kTileH);
   // persistent grid: exactly the CTAs that are resident at once (registers and the table's smem decide)
   int per_sm = 0;

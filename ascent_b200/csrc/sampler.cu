@@ -140,9 +140,11 @@ struct Cell
   int cx, cy, cz;
 };
 
-template <int KIND, typename FT, int ASSOC, typename IDX>
+// MARK: the demand-staging pre-pass (MODE 4): instead of gathering the corner scalars, flag the
+// 128-byte lines of the field they live in (TraceParams::mark, one byte per line).
+template <int KIND, typename FT, int ASSOC, typename IDX, bool MARK = false>
 __device__ __forceinline__ void locate_and_load(const BlockDev& B, float px, float py, float pz,
-                                                Cell& c)
+                                                Cell& c, unsigned char* __restrict__ mark = nullptr)
 {
   if (KIND == 0)
   {
@@ -176,6 +178,20 @@ __device__ __forceinline__ void locate_and_load(const BlockDev& B, float px, flo
     const IDX Nx = (IDX)B.dims[0], NxNy = (IDX)B.dims[0] * (IDX)B.dims[1];
     const IDX i0 = ((IDX)c.cz * (IDX)B.dims[1] + (IDX)c.cy) * Nx + (IDX)c.cx;
     const IDX i3 = i0 + Nx, i4 = i0 + NxNy, i7 = i4 + Nx;
+    if (MARK)
+    {
+      constexpr int SH = sizeof(FT) == 4 ? 5 : 4; // elements per 128-byte line = 1 << SH
+      const IDX rows[4] = { i0, i3, i4, i7 };
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+      {
+        const IDX l0 = rows[r] >> SH, l1 = (rows[r] + 1) >> SH;
+        mark[l0] = 1;
+        if (l1 != l0) mark[l1] = 1;
+      }
+      c.s0 = c.s3 = c.s4 = c.s7 = c.s6m7 = c.s5m4 = c.s1m0 = c.s2m3 = 0.f;
+      return;
+    }
     const float s0 = load_scalar<FT>(B.field, i0);
     const float s1 = load_scalar<FT>(B.field, i0 + 1);
     const float s3 = load_scalar<FT>(B.field, i3);
@@ -190,6 +206,13 @@ __device__ __forceinline__ void locate_and_load(const BlockDev& B, float px, flo
   else
   {
     const IDX ci = ((IDX)c.cz * (IDX)(B.dims[1] - 1) + (IDX)c.cy) * (IDX)(B.dims[0] - 1) + (IDX)c.cx;
+    if (MARK)
+    {
+      constexpr int SH = sizeof(FT) == 4 ? 5 : 4;
+      mark[ci >> SH] = 1;
+      c.s0 = 0.f;
+      return;
+    }
     c.s0 = load_scalar<FT>(B.field, ci);
   }
 }
@@ -199,8 +222,11 @@ __global__ void __launch_bounds__(kThreads, VR_MIN_BLOCKS)
 trace_kernel(const __grid_constant__ TraceParams P)
 {
   __shared__ float4 s_lut[1024];
-  for (int i = threadIdx.x; i < P.lut_size; i += kThreads) s_lut[i] = __ldg(P.lut + i);
-  __syncthreads();
+  if (MODE != 4) // the staging pre-pass never classifies
+  {
+    for (int i = threadIdx.x; i < P.lut_size; i += kThreads) s_lut[i] = __ldg(P.lut + i);
+    __syncthreads();
+  }
 
   const BlockDev& B = P.blk;
   const int lane = threadIdx.x & 31;
@@ -308,7 +334,7 @@ trace_kernel(const __grid_constant__ TraceParams P)
           Cell cur;
           cur.cx = cur.cy = cur.cz = 0;
           cur.isx = cur.isy = cur.isz = 0.f;
-          locate_and_load<KIND, FT, ASSOC, IDX>(B, px, py, pz, cur);
+          locate_and_load<KIND, FT, ASSOC, IDX, MODE == 4>(B, px, py, pz, cur, P.mark);
           float tx = (px - cur.blx) * cur.isx, ty = (py - cur.bly) * cur.isy, tz = (pz - cur.blz) * cur.isz;
           for (;;)
           {
@@ -325,11 +351,22 @@ trace_kernel(const __grid_constant__ TraceParams P)
               const float maxt = fmaxf(ntx, fmaxf(nty, ntz));
               if (maxt > 1.f || mint < 0.f)
               {
-                locate_and_load<KIND, FT, ASSOC, IDX>(B, npx, npy, npz, nxt);
+                locate_and_load<KIND, FT, ASSOC, IDX, MODE == 4>(B, npx, npy, npz, nxt, P.mark);
                 ntx = (npx - nxt.blx) * nxt.isx;
                 nty = (npy - nxt.bly) * nxt.isy;
                 ntz = (npz - nxt.blz) * nxt.isz;
               }
+            }
+            if (MODE == 4)
+            {
+              // pre-pass: every sample up to the exit is visited (no opacity, so no early exit): a
+              // superset of what the real trace will touch
+              if (!next_ok) break;
+              cur = nxt;
+              px = npx; py = npy; pz = npz;
+              distance = ndist;
+              tx = ntx; ty = nty; tz = ntz;
+              continue;
             }
             // ---- sample k: interpolate, classify, blend
             float v;
@@ -483,6 +520,7 @@ cudaError_t launch_mode(const TraceParams& p, int mode, int grid, cudaStream_t s
   if (mode == 0)      trace_kernel<KIND, FT, ASSOC, 0, IDX><<<grid, kThreads, 0, s>>>(p);
   else if (mode == 1) trace_kernel<KIND, FT, ASSOC, 1, IDX><<<grid, kThreads, 0, s>>>(p);
   else if (mode == 2) trace_kernel<KIND, FT, ASSOC, 2, IDX><<<grid, kThreads, 0, s>>>(p);
+  else if (mode == 4) trace_kernel<KIND, FT, ASSOC, 4, IDX><<<grid, kThreads, 0, s>>>(p);
   else                trace_kernel<KIND, FT, ASSOC, 3, IDX><<<grid, kThreads, 0, s>>>(p);
   return cudaGetLastError();
 }

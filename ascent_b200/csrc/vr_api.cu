@@ -104,8 +104,17 @@ static void free_block(Block& b)
 {
   if (b.owned_field) cudaFree(b.owned_field);
   if (b.owned_axes) cudaFree(b.owned_axes);
+  if (b.line_want) cudaFree(b.line_want);
+  if (b.line_have) cudaFree(b.line_have);
+  if (b.n_have_dev) cudaFree(b.n_have_dev);
+  if (b.n_have_host) cudaFreeHost(b.n_have_host);
+  b.n_have_dev = b.n_have_host = nullptr;
+  b.all_resident = false;
   b.owned_field = nullptr;
   b.owned_axes = nullptr;
+  b.line_want = b.line_have = nullptr;
+  b.staged_src = nullptr;
+  b.n_lines = 0;
 }
 
 namespace vr { void comm_destroy(vr_ctx* ctx); }
@@ -147,6 +156,7 @@ extern "C" void vr_destroy(vr_ctx* ctx)
   cudaFree(ctx->rec);
   cudaFree(ctx->scan_blocks);
   cudaFree(ctx->enc_rgba);
+  cudaFree(ctx->scratch_u64);
   cudaFree(ctx->tile_counter);
   cudaFree(ctx->sample_counter);
   for (int k = 0; k < vr::kAuxStreams; ++k)
@@ -197,8 +207,8 @@ static vr_status upload_field(vr_ctx* ctx, Block& b, const void* field, int dtyp
   REQUIRE(field != nullptr, "block: field is NULL");
   REQUIRE(dtype == VR_F32 || dtype == VR_F64, "block: dtype must be VR_F32 or VR_F64");
   REQUIRE(assoc == VR_POINT || assoc == VR_CELL, "block: assoc must be VR_POINT or VR_CELL");
-  REQUIRE(where == VR_HOST || where == VR_DEVICE || where == VR_HOST_MAPPED,
-          "block: where must be VR_HOST, VR_DEVICE or VR_HOST_MAPPED");
+  REQUIRE(where == VR_HOST || where == VR_DEVICE || where == VR_HOST_MAPPED || where == VR_HOST_STAGED,
+          "block: where must be VR_HOST, VR_DEVICE, VR_HOST_MAPPED or VR_HOST_STAGED");
   const int* d = b.dev.dims;
   REQUIRE(d[0] >= 2 && d[1] >= 2 && d[2] >= 2, "block: point dims must be >= 2 (got %d %d %d)", d[0],
           d[1], d[2]);
@@ -209,6 +219,47 @@ static vr_status upload_field(vr_ctx* ctx, Block& b, const void* field, int dtyp
   b.dev.assoc = assoc;
   if (where == VR_DEVICE)
     b.dev.field = field;
+  else if (where == VR_HOST_STAGED)
+  {
+    // demand staging (stage.cu): nothing moves now; every trace first pulls the 128-byte lines its
+    // rays will touch and that are not on the device yet
+    void* dptr = nullptr;
+    cudaError_t e = cudaHostGetDevicePointer(&dptr, const_cast<void*>(field), 0);
+    if (e != cudaSuccess)
+    {
+      cudaGetLastError();
+      return fail(ctx, VR_ERR_INVALID, "block: VR_HOST_STAGED field is not page-locked mapped host memory "
+                  "(cudaHostAlloc / cudaHostRegister): %s", cudaGetErrorString(e));
+    }
+    const size_t n_lines = (bytes + 127) / 128;
+    if (old && old->owned_field && old->line_have && field_bytes(old->dev) == bytes && old->n_lines == n_lines)
+    {
+      // re-publish of a same-sized field (one per simulation cycle): keep the buffers, forget the lines
+      b.owned_field = old->owned_field; old->owned_field = nullptr;
+      b.line_want = old->line_want; old->line_want = nullptr;
+      b.line_have = old->line_have; old->line_have = nullptr;
+      b.n_have_dev = old->n_have_dev; old->n_have_dev = nullptr;
+      b.n_have_host = old->n_have_host; old->n_have_host = nullptr;
+      // the pinned mirror may still be the target of an async copy of the previous publish
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+    else
+    {
+      CK(cudaMalloc(&b.owned_field, n_lines * 128));
+      CK(cudaMalloc(&b.line_want, n_lines));
+      CK(cudaMalloc(&b.line_have, n_lines));
+      CK(cudaMalloc(&b.n_have_dev, sizeof(unsigned long long)));
+      CK(cudaHostAlloc(&b.n_have_host, sizeof(unsigned long long), cudaHostAllocDefault));
+      CK(cudaMemsetAsync(b.line_want, 0, n_lines, ctx->stream));
+    }
+    CK(cudaMemsetAsync(b.line_have, 0, n_lines, ctx->stream));
+    CK(cudaMemsetAsync(b.n_have_dev, 0, sizeof(unsigned long long), ctx->stream));
+    *b.n_have_host = 0;
+    b.all_resident = false;
+    b.n_lines = n_lines;
+    b.staged_src = dptr;
+    b.dev.field = b.owned_field;
+  }
   else if (where == VR_HOST_MAPPED)
   {
     // page-locked host memory sampled in place over PCIe: the sparse default sampling touches about
@@ -266,7 +317,7 @@ extern "C" vr_status vr_block_uniform(vr_ctx* ctx, int block_id, const int dims[
   Block* old = it != ctx->blocks.end() ? &it->second : nullptr;
   vr_status st = upload_field(ctx, b, field, dtype, assoc, where, old);
   if (st != VR_OK) { free_block(b); return st; }
-  if (old && (old->owned_field || old->owned_axes))
+  if (old && (old->owned_field || old->owned_axes || old->line_want || old->line_have))
   {
     cudaStreamSynchronize(ctx->stream);
     free_block(*old);
@@ -314,7 +365,7 @@ extern "C" vr_status vr_block_rectilinear(vr_ctx* ctx, int block_id, const int d
   Block* old = it != ctx->blocks.end() ? &it->second : nullptr;
   vr_status st = upload_field(ctx, b, field, dtype, assoc, where, old);
   if (st != VR_OK) { free_block(b); return st; }
-  if (old && (old->owned_field || old->owned_axes))
+  if (old && (old->owned_field || old->owned_axes || old->line_want || old->line_have))
   {
     cudaStreamSynchronize(ctx->stream);
     free_block(*old);
@@ -331,6 +382,24 @@ extern "C" vr_status vr_block_free(vr_ctx* ctx, int block_id)
   CK(cudaStreamSynchronize(ctx->stream));
   free_block(it->second);
   ctx->blocks.erase(it);
+  return VR_OK;
+}
+
+extern "C" vr_status vr_block_staged_bytes(vr_ctx* ctx, int block_id, size_t* bytes)
+{
+  if (!ctx) return VR_ERR_INVALID;
+  auto it = ctx->blocks.find(block_id);
+  REQUIRE(it != ctx->blocks.end() && bytes, "vr_block_staged_bytes: unknown block %d", block_id);
+  const Block& b = it->second;
+  *bytes = 0;
+  if (!b.staged_src) return VR_OK;
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->scratch_u64) CK(cudaMalloc(&ctx->scratch_u64, sizeof(unsigned long long)));
+  CK(launch_count_lines(b.line_have, b.n_lines, ctx->scratch_u64, ctx->stream));
+  unsigned long long n = 0;
+  CK(cudaMemcpyAsync(&n, ctx->scratch_u64, sizeof(n), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *bytes = (size_t)n * 128;
   return VR_OK;
 }
 
@@ -455,6 +524,7 @@ extern "C" vr_status vr_canvas_download_rgba8(vr_ctx* ctx, const float* bg_rgba,
   {
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->enc_rgba);
+  cudaFree(ctx->scratch_u64);
     ctx->enc_rgba = nullptr;
     ctx->enc_cap = 0;
     CK(cudaMalloc(&ctx->enc_rgba, n * sizeof(uchar4)));
@@ -477,6 +547,41 @@ extern "C" vr_status vr_canvas_ptrs(vr_ctx* ctx, void** rgba_dev, void** depth_d
 }
 
 // ================================================================= tracing
+// VR_HOST_STAGED blocks: run the sampler's pre-pass for exactly this trace (same params, mode 4) and
+// fetch the flagged lines that are still missing, on stream `s`, before the real launch.
+static vr_status stage_for_trace(vr_ctx* ctx, int block_id, const TraceParams& p, cudaStream_t s,
+                                 unsigned int* counter, bool zero_counter)
+{
+  auto it = ctx->blocks.find(block_id);
+  if (it == ctx->blocks.end() || !it->second.staged_src) return VR_OK;
+  Block& b = it->second;
+  if (p.sw <= 0 || p.sh <= 0 || b.all_resident) return VR_OK;
+  // most of the block is on the device already (many views per publish): pull the rest in one sweep
+  // and stop paying for pre-passes.  The mirror may lag by one trace; it only steers this heuristic.
+  if (*(volatile unsigned long long*)b.n_have_host * 4 >= b.n_lines * 3)
+  {
+    CK(launch_fetch_lines(b.line_want, b.line_have, b.staged_src, b.owned_field, b.n_lines, field_bytes(b.dev),
+                          true, b.n_have_dev, ctx->sm_count, s));
+    ctx->launches++;
+    b.all_resident = true;
+    return VR_OK;
+  }
+  TraceParams m = p;
+  m.mark = b.line_want;
+  m.tile_counter = counter;
+  m.sample_counter = nullptr;
+  m.n_clear_chunks = 0;
+  m.tiles_x = (m.sw + 7) / 8; // the plain ray rectangle (mode 2 widens it for its clears)
+  m.tx0 = m.sx;
+  m.tx1 = m.sx + m.sw;
+  CK(launch_trace(m, 4, ctx->sm_count, s, zero_counter));
+  CK(launch_fetch_lines(b.line_want, b.line_have, b.staged_src, b.owned_field, b.n_lines, field_bytes(b.dev),
+                        false, b.n_have_dev, ctx->sm_count, s));
+  CK(cudaMemcpyAsync(b.n_have_host, b.n_have_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  ctx->launches += 2;
+  return VR_OK;
+}
+
 static vr_status fill_trace_params(vr_ctx* ctx, int block_id, const vr_camera* cam, float sample_dist,
                                    float range_min, float range_max, int use_depth, int W, int H,
                                    TraceParams& p)
@@ -545,6 +650,8 @@ extern "C" vr_status vr_trace_to_canvas(vr_ctx* ctx, int block_id, const vr_came
   vr_status st = fill_trace_params(ctx, block_id, cam, sample_dist, range_min, range_max,
                                    use_canvas_depth, ctx->W, ctx->H, p);
   if (st != VR_OK) return st;
+  st = stage_for_trace(ctx, block_id, p, ctx->stream, ctx->tile_counter, true);
+  if (st != VR_OK) return st;
   CK(launch_trace(p, 0, ctx->sm_count, ctx->stream));
   ctx->launches++;
   return VR_OK;
@@ -585,6 +692,8 @@ extern "C" vr_status vr_trace_to_image(vr_ctx* ctx, int block_id, const vr_camer
   p.img_depth = ctx->img_depth;
   p.write_canvas = (flags & VR_FRAME_WRITE_CANVAS) ? 1 : 0;
   p.n_clear_chunks = (flags & VR_FRAME_NO_CLEAR) ? 0 : (int)(((size_t)width * height + 511) / 512);
+  st = stage_for_trace(ctx, block_id, p, ctx->stream, ctx->tile_counter, true);
+  if (st != VR_OK) return st;
   CK(launch_trace(p, 2, ctx->sm_count, ctx->stream));
   ctx->launches++;
   // what the multi-GPU fold needs to know: outside this rectangle my image is empty
@@ -651,6 +760,8 @@ extern "C" vr_status vr_trace_to_partials(vr_ctx* ctx, int block_id, const vr_ca
   p.partials = ctx->partials;
   p.partial_count = ctx->partial_count;
   p.partial_capacity = ctx->partial_cap;
+  st = stage_for_trace(ctx, block_id, p, ctx->stream, ctx->tile_counter, true);
+  if (st != VR_OK) return st;
   CK(launch_trace(p, 1, ctx->sm_count, ctx->stream));
   ctx->launches++;
   return VR_OK;
@@ -794,6 +905,8 @@ extern "C" vr_status vr_trace_to_layer(vr_ctx* ctx, int block_id, const vr_camer
   p.layer_rgba = ctx->lpool_rgba;
   p.layer_depth = ctx->lpool_depth;
   p.layer_base = base;
+  st = stage_for_trace(ctx, block_id, p, ctx->stream, ctx->tile_counter, true);
+  if (st != VR_OK) return st;
   CK(launch_trace(p, 3, ctx->sm_count, ctx->stream));
   ctx->launches++;
   LayerDesc& d = T.d[T.n++];
@@ -819,6 +932,7 @@ extern "C" vr_status vr_trace_blocks_to_layers(vr_ctx* ctx, int n_blocks, const 
   CK(cudaSetDevice(ctx->device));
   LayerTable& T = *ctx->ltab_host;
   std::vector<TraceParams> ps;
+  std::vector<int> block_of;
   ps.reserve(n_blocks);
   size_t used = ctx->lpool_used;
   for (int k = 0; k < n_blocks; ++k)
@@ -832,6 +946,7 @@ extern "C" vr_status vr_trace_blocks_to_layers(vr_ctx* ctx, int n_blocks, const 
     p.layer_base = base;
     used = base + (size_t)p.sw * p.sh;
     ps.push_back(p);
+    block_of.push_back(block_ids[k]);
   }
   REQUIRE(T.n + (int)ps.size() <= kMaxLayers, "vr_trace_blocks_to_layers: more than %d layers in one frame",
           kMaxLayers);
@@ -849,7 +964,13 @@ extern "C" vr_status vr_trace_blocks_to_layers(vr_ctx* ctx, int n_blocks, const 
     p.layer_rgba = ctx->lpool_rgba;
     p.layer_depth = ctx->lpool_depth;
     p.tile_counter = ctx->tile_counter + 1 + k;
-    CK(launch_trace(p, 3, ctx->sm_count, ctx->aux[k % n_streams], false));
+    const bool staged = ctx->blocks[block_of[k]].staged_src != nullptr;
+    if (staged)
+    {
+      st = stage_for_trace(ctx, block_of[k], p, ctx->aux[k % n_streams], p.tile_counter, true);
+      if (st != VR_OK) return st;
+    }
+    CK(launch_trace(p, 3, ctx->sm_count, ctx->aux[k % n_streams], staged));
     ctx->launches++;
     LayerDesc& d = T.d[T.n++];
     d.x0 = p.sx; d.y0 = p.sy; d.w = p.sw; d.h = p.sh;
@@ -872,6 +993,7 @@ static vr_status upload_layer_table(vr_ctx* ctx)
   return VR_OK;
 }
 namespace vr { vr_status upload_layer_table_pub(vr_ctx* ctx) { return upload_layer_table(ctx); } }
+namespace vr { vr_status ensure_frame_pub(vr_ctx* ctx, int W, int H) { return ensure_frame(ctx, W, H); } }
 
 extern "C" vr_status vr_layers_composite_to_canvas(vr_ctx* ctx, const vr_camera* cam, int canvas_is_clear)
 {

@@ -61,6 +61,8 @@ struct TraceParams
   vr_partial* partials;
   unsigned long long* partial_count;
   unsigned long long partial_capacity;
+  // demand staging pre-pass (mode 4): one byte per 128-byte line of the field
+  unsigned char* mark;
   // dynamic tile scheduler + sample counter
   unsigned int* tile_counter;
   unsigned long long* sample_counter; // may be null
@@ -74,6 +76,15 @@ struct Block
   void* owned_field = nullptr; // device copy we own (null when adopted)
   float* owned_axes = nullptr;
   double bounds[6];
+  // VR_HOST_STAGED: the field stays in mapped host memory; owned_field is a device buffer of the
+  // same size that holds only the 128-byte lines some ray has needed since the publish
+  const void* staged_src = nullptr;   // device-visible alias of the host array
+  unsigned char* line_want = nullptr; // lines the next trace will touch (pre-pass output)
+  unsigned char* line_have = nullptr; // lines already fetched since the publish
+  size_t n_lines = 0;
+  unsigned long long* n_have_dev = nullptr;  // lines resident (device counter)
+  unsigned long long* n_have_host = nullptr; // pinned mirror, refreshed asynchronously after every fetch
+  bool all_resident = false;                 // every line is on the device: no more pre-passes
 };
 
 struct LayerTable; // layers.cu section below
@@ -155,6 +166,7 @@ struct vr_ctx
   bool layers_in_arena = false;
   int lW = 0, lH = 0;
 
+  unsigned long long* scratch_u64 = nullptr;
   uchar4* enc_rgba = nullptr;  // encoded final image (vr_canvas_download_rgba8)
   size_t enc_cap = 0;
 
@@ -172,6 +184,13 @@ namespace vr
 // sampler.cu
 cudaError_t launch_trace(const TraceParams& p, int mode_partials, int sm_count, cudaStream_t s,
                          bool zero_counter = true);
+
+// stage.cu
+cudaError_t launch_fetch_lines(unsigned char* want, unsigned char* have, const void* src, void* dst,
+                               size_t n_lines, size_t n_bytes, bool all, unsigned long long* n_have,
+                               int sm_count, cudaStream_t s);
+
+cudaError_t launch_count_lines(const unsigned char* have, size_t n_lines, unsigned long long* out, cudaStream_t s);
 
 // composite.cu
 cudaError_t launch_canvas_clear(float4* rgba, float* depth, size_t n, cudaStream_t s);

@@ -287,19 +287,22 @@ def run_single(args, wl):
 
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
-        def e2e_frame(mapped):
-            # publish: the simulation's field (pinned host memory), every step.  "copy": the whole
-            # block goes host -> device (cudaMemcpyAsync) before the trace.  "mapped": the block is
-            # registered in place (VR_HOST_MAPPED) and the sampler pulls the 32-byte sectors its rays
-            # touch across PCIe -- about a quarter of the field at samples=100.  L2 is flushed first so
-            # that no sector of the previous step's (identical) field is served from cache.
-            if mapped:
+        def e2e_frame(mode):
+            # publish: the simulation's field (pinned host memory), every step.
+            #  "copy"   : the whole block goes host -> device (cudaMemcpyAsync) before the trace;
+            #  "mapped" : the block is registered in place (VR_HOST_MAPPED), the sampler reads it over PCIe;
+            #  "staged" : VR_HOST_STAGED -- a pre-pass of the sampler flags the 128-byte lines the rays of
+            #             this view touch, a gather kernel pulls exactly those over PCIe, then the trace.
+            # For the in-place modes L2 is flushed first so that no line of the previous step's
+            # (identical) field can be served from cache.
+            if mode != "copy":
                 with torch.cuda.stream(stream):
                     flush.zero_()
+            kw = dict(host_mapped=(mode == "mapped"), staged=(mode == "staged"))
             if wl.get("rectilinear"):
-                ctx.block_rectilinear(100, b["dims"], axes, hf, host_mapped=mapped)
+                ctx.block_rectilinear(100, b["dims"], axes, hf, **kw)
             else:
-                ctx.block_uniform(100, b["dims"], b["origin"], b["spacing"], hf, host_mapped=mapped)
+                ctx.block_uniform(100, b["dims"], b["origin"], b["spacing"], hf, **kw)
             # the volume-only scene of the config: the frame starts from a cleared canvas, so the
             # whole per-rank body is one launch; the result comes back as the float canvas
             for v in views:
@@ -307,16 +310,18 @@ def run_single(args, wl):
                 ctx.canvas_download(W, H, hr, hd)
 
         n_e2e = max(3, min(args.steps, 10))
-        modes = {}
-        for name, mapped in (("copy", False), ("mapped", True)):
-            if mapped and len(views) > 8:
-                continue  # many views per publish: the copy is amortised, in-place sampling is not
+        modes, moved = {}, {}
+        for name in ("copy", "mapped", "staged"):
+            if name == "mapped" and len(views) > 8:
+                continue  # many views per publish: in-place sampling re-reads the block for every view
             for _ in range(2):
-                e2e_frame(mapped)
+                e2e_frame(name)
             t0 = time.perf_counter()
             for _ in range(n_e2e):
-                e2e_frame(mapped)
+                e2e_frame(name)
             modes[name] = (time.perf_counter() - t0) / n_e2e
+            if name == "staged":
+                moved[name] = ctx.block_staged_bytes(100)
         best = min(modes, key=modes.get)
         dt = modes[best]
         # the same frame through the canvas-in/canvas-out form vtk-h's RenderCells seam needs when
@@ -333,16 +338,21 @@ def run_single(args, wl):
         tpj = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpj):
             touched = (json.load(open(tpj)).get(wl["key"]) or {}).get("dram_read_bytes")
+        h2d = {"copy": nvox * 4, "mapped": touched or nvox * 4, "staged": moved.get("staged", nvox * 4)}
         e2e = {"value": W * H * len(views) / dt / 1e6, "unit": "Mrays/s", "ms_per_step": dt * 1e3,
                "mode": best,
-               "h2d_bytes_per_step": nvox * 4 if best == "copy" else (touched or nvox * 4),
+               "h2d_bytes_per_step": h2d[best],
                "d2h_bytes_per_step": W * H * 20 * len(views),
                "modes_ms_per_step": {k: v * 1e3 for k, v in modes.items()},
-               "what": "per step: publish the pinned host field (copy: vr_block_uniform VR_HOST = cudaMemcpyAsync of "
-                       "the whole block; mapped: VR_HOST_MAPPED, the sampler reads the sectors it touches over "
-                       "PCIe, h2d bytes = the kernel's DRAM read bytes from the ncu capture, L2 flushed every "
-                       "step) + vr_trace_to_image + vr_canvas_download(host canvas) per view; the faster mode "
-                       "is reported",
+               "modes_h2d_bytes": {k: h2d[k] for k in modes},
+               "field_bytes": nvox * 4,
+               "what": "per step: publish the pinned host field + vr_trace_to_image + vr_canvas_download(host "
+                       "canvas) per view, all through the C ABI with host buffers.  copy: VR_HOST, cudaMemcpyAsync "
+                       "of the whole block; staged: VR_HOST_STAGED, sampler pre-pass flags the 128-byte lines the "
+                       "view's rays touch and a gather kernel pulls exactly those across PCIe (h2d bytes counted "
+                       "by the library, L2 flushed every step); mapped: VR_HOST_MAPPED, sampled in place (h2d = "
+                       "DRAM-read bytes of the ncu capture).  The fastest mode is the headline; images are "
+                       "bit-identical in all three (tests/test_gpu_parity.py)",
                "render_image_canvas_inout_ms": dt_inout * 1e3}
         ctx.block_free(100)
 

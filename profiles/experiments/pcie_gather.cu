@@ -84,6 +84,47 @@ __global__ void fetch_lines_v4(const unsigned char* __restrict__ want, const flo
   }
 }
 
+// 64-byte granules: flag per granule, half a warp (16 lanes x 4 B) per granule, UNROLL pairs in flight
+template <int UNROLL>
+__global__ void fetch_half_lines(const unsigned char* __restrict__ want, const float* __restrict__ host,
+                                 float* __restrict__ dev, size_t n_gran)
+{
+  const int lane = threadIdx.x & 31;
+  const int half = lane >> 4, sub = lane & 15;
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t base = warp * 64; base < n_gran; base += n_warps * 64)
+  {
+    // half h of the warp owns granules base + 32 h .. base + 32 h + 31; lane flags: 2 per lane
+    const bool w0 = (base + lane < n_gran) && want[base + lane];
+    const bool w1 = (base + 32 + lane < n_gran) && want[base + 32 + lane];
+    const unsigned m0 = __ballot_sync(0xffffffffu, w0), m1 = __ballot_sync(0xffffffffu, w1);
+    unsigned m = half ? m1 : m0;
+    const size_t hb = base + 32 * half;
+    // both halves iterate max(popc) times (warp-synchronous loads are not required here)
+    while (__any_sync(0xffffffffu, m != 0))
+    {
+      float v[UNROLL];
+      size_t at[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+      {
+        at[u] = ~(size_t)0;
+        if (m)
+        {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          at[u] = (hb + b) * 16 + sub;
+          v[u] = __ldcs(host + at[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        if (at[u] != ~(size_t)0) dev[at[u]] = v[u];
+    }
+  }
+}
+
 int main()
 {
   const size_t n = (size_t)512 * 512 * 512;
@@ -146,6 +187,32 @@ int main()
                d, cnt, cnt * 128 / 1e6, variant, best, cnt * 128 / best / 1e6);
       }
     }
+  // 64-byte granules at the same densities (random pattern)
+  {
+    const size_t n_gran = n / 16;
+    unsigned char* want64 = nullptr;
+    CK(cudaMalloc(&want64, n_gran));
+    std::vector<unsigned char> hw64(n_gran);
+    for (double d : dens)
+    {
+      size_t cnt = 0;
+      srand(2);
+      for (size_t i = 0; i < n_gran; ++i) { hw64[i] = (rand() / (double)RAND_MAX) < d; cnt += hw64[i]; }
+      CK(cudaMemcpy(want64, hw64.data(), n_gran, cudaMemcpyHostToDevice));
+      float best = 1e9f;
+      for (int r = 0; r < 3; ++r)
+      {
+        cudaEventRecord(a);
+        fetch_half_lines<4><<<148 * 8, 256>>>(want64, hdev, dev, n_gran);
+        cudaEventRecord(b);
+        CK(cudaEventSynchronize(b));
+        cudaEventElapsedTime(&ms, a, b);
+        best = ms < best ? ms : best;
+      }
+      printf("64-byte granules random density %.2f (%zu granules, %.1f MB): %.3f ms  %.1f GB/s\n", d, cnt, cnt * 64 / 1e6,
+             best, cnt * 64 / best / 1e6);
+    }
+  }
   CK(cudaGetLastError());
   return 0;
 }

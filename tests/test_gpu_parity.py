@@ -499,6 +499,139 @@ def test_host_mapped_field_is_sampled_in_place(ctx, kind):
     ctx.block_free(0)
 
 
+def _pinned(arr):
+    import torch
+    t = torch.empty(arr.size, dtype=torch.float32 if arr.dtype == np.float32 else torch.float64, pin_memory=True)
+    h = t.numpy()
+    h[:] = arr.reshape(-1)
+    return t, h
+
+
+@pytest.mark.parametrize("kind,dtype,assoc", [("uniform", np.float32, "point"), ("uniform", np.float64, "point"),
+                                              ("rectilinear", np.float32, "point"), ("uniform", np.float32, "cell"),
+                                              ("rectilinear", np.float64, "cell")])
+def test_demand_staged_field_matches_copied_field(ctx, kind, dtype, assoc):
+    """VR_HOST_STAGED: the publish copies nothing; every trace pulls the 128-byte lines its rays touch.
+    Frames must be bit-identical to the copied field -- for several views per publish (lines accumulate),
+    through every render entry point, and after a re-publish (stale lines must not survive: the first
+    publish stages a poisoned field from other view points)."""
+    n = 48
+    dom = datasets.braid_uniform(n, dtype=dtype) if kind == "uniform" else \
+        datasets.braid_rectilinear(n, power=1.5, dtype=dtype)
+    if assoc == "cell":
+        dom["assoc"] = "cell"
+        dom["field"] = np.ascontiguousarray(dom["field"].reshape(n, n, n)[:n - 1, :n - 1, :n - 1]).reshape(-1)
+    b = datasets.domain_bounds(dom)
+    W, H = 333, 210
+    lut = color_table.parse_color_table(scenes.RAMP_TF).corrected_opacity(100).lut()
+    sd = O.sample_distance(b, 100)
+    rmin, rmax = scenes.field_range([dom])
+    ctx.set_tf(lut)
+    A = _lib.VR_CELL if assoc == "cell" else _lib.VR_POINT
+
+    def publish(field, staged):
+        if kind == "uniform":
+            ctx.block_uniform(0, dom["dims"], dom["origin"], dom["spacing"], field, assoc=A, staged=staged)
+        else:
+            ctx.block_rectilinear(0, dom["dims"], dom["axes"], field, assoc=A, staged=staged)
+
+    def cams():
+        out = []
+        for az, el, zoom in [(0., 0., 0.), (35., 20., 0.), (-120., -40., 0.5), (35., 20., 0.)]:
+            c = O.camera_reset_to_bounds(b)
+            O.camera_azimuth(c, az)
+            O.camera_elevation(c, el)
+            O.camera_zoom(c, zoom)
+            out.append(c)
+        return out
+
+    def frames():
+        res = []
+        for c in cams():
+            ctx.trace_to_image(0, c, W, H, sd, rmin, rmax, write_canvas=True)
+            res.append(ctx.canvas_download(W, H))
+        # canvas-in/out with a depth clamp, the list path and the layer paths
+        c = cams()[1]
+        rgba0 = np.full((H * W, 4), 0.25, np.float32)
+        depth0 = np.full(H * W, 0.97, np.float32)
+        ctx.canvas_upload(W, H, rgba0, depth0)
+        ctx.trace_to_canvas(0, c, sd, rmin, rmax, True)
+        res.append(ctx.canvas_download(W, H))
+        ctx.partials_begin(W, H)
+        ctx.trace_to_partials(0, c, sd, rmin, rmax, False)
+        res.append((np.sort(ctx.partials_download(), order=["pixel_id", "depth"]).view(np.uint8), np.zeros(1)))
+        for batched in (False, True):
+            ctx.layers_begin(W, H)
+            if batched:
+                ctx.trace_blocks_to_layers([0], c, sd, rmin, rmax, False)
+            else:
+                ctx.trace_to_layer(0, c, sd, rmin, rmax, False)
+            ctx.layers_composite_to_canvas(c, canvas_is_clear=True)
+            res.append(ctx.canvas_download(W, H))
+        return res
+
+    publish(dom["field"], False)
+    ref = frames()
+    assert (ref[0][0][:, 3] > 0).sum() > 1000
+    keep, host = _pinned(dom["field"])
+    # first publish: poison, looked at from a few view points, so that plenty of lines are resident
+    host[:] = np.nan
+    publish(host, True)
+    ctx.trace_to_image(0, cams()[0], W, H, sd, rmin, rmax, write_canvas=True)
+    ctx.trace_to_image(0, cams()[2], W, H, sd, rmin, rmax, write_canvas=True)
+    ctx.synchronize()
+    # second publish of the same array with the real values
+    host[:] = dom["field"].reshape(-1)
+    publish(host, True)
+    got = frames()
+    for k, ((ra, rd), (ga, gd)) in enumerate(zip(ref, got)):
+        assert np.array_equal(ra, ga, equal_nan=True) and np.array_equal(rd, gd, equal_nan=True), "frame %d differs" % k
+    with pytest.raises(_lib.VRError):
+        publish(dom["field"].copy(), True)   # pageable memory cannot be staged
+    ctx.block_free(0)
+    del keep
+
+
+def test_demand_staging_fetches_a_fraction_of_a_sparse_sampled_block(ctx):
+    """the point of staging: at the default sampling a frame needs only part of the block.  Count the
+    resident lines through the library's own statistic."""
+    n = 160
+    dom = datasets.braid_uniform(n, dtype=np.float32)
+    b = datasets.domain_bounds(dom)
+    W, H = 480, 270
+    cam = O.camera_reset_to_bounds(b)
+    ctx.set_tf(color_table.parse_color_table(scenes.RAMP_TF).corrected_opacity(100).lut())
+    sd = O.sample_distance(b, 18)    # a step of ~15 voxels: the regime of a 512^3+ block at samples = 100
+    rmin, rmax = scenes.field_range([dom])
+    keep, host = _pinned(dom["field"])
+    ctx.block_uniform(0, dom["dims"], dom["origin"], dom["spacing"], host, staged=True)
+    assert ctx.block_staged_bytes(0) == 0
+    ctx.trace_to_image(0, cam, W, H, sd, rmin, rmax, write_canvas=True)
+    first = ctx.block_staged_bytes(0)
+    assert 0 < first < 0.6 * dom["field"].nbytes
+    ctx.trace_to_image(0, cam, W, H, sd, rmin, rmax, write_canvas=True)
+    assert ctx.block_staged_bytes(0) == first          # same view: nothing new to fetch
+    O.camera_azimuth(cam, 90.0)
+    ctx.trace_to_image(0, cam, W, H, sd, rmin, rmax, write_canvas=True)
+    assert first < ctx.block_staged_bytes(0) <= dom["field"].nbytes + 128
+    # many views per publish: once most lines are resident the rest is pulled in one sweep
+    ref = None
+    for k in range(12):
+        O.camera_azimuth(cam, 30.0)
+        O.camera_elevation(cam, 7.0)
+        ctx.trace_to_image(0, cam, W, H, sd, rmin, rmax, write_canvas=True)
+        ctx.synchronize()
+    assert ctx.block_staged_bytes(0) >= dom["field"].nbytes
+    got = ctx.canvas_download(W, H)
+    ctx.block_uniform(1, dom["dims"], dom["origin"], dom["spacing"], dom["field"])
+    ctx.trace_to_image(1, cam, W, H, sd, rmin, rmax, write_canvas=True)
+    ref = ctx.canvas_download(W, H)
+    assert np.array_equal(ref[0], got[0]) and np.array_equal(ref[1], got[1])
+    ctx.block_free(0)
+    ctx.block_free(1)
+    del keep
+
+
 @pytest.mark.parametrize("n_slabs", [40, 200])
 def test_layers_deep_pixels(ctx, n_slabs):
     """more entries per pixel than the in-register ordering holds (32) and more layers over one
