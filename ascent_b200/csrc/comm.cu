@@ -36,6 +36,11 @@ namespace
 {
 constexpr size_t kFlagBytes = 4096;
 constexpr int kMaxRanks = 16;
+// A rank's quantised image of frame e lives in ring slot e % 3.  Two slots would do for strictly
+// alternating render/exchange; the third lets a rank trace frame e+1 BEFORE it joins the exchange of
+// frame e (VR_FRAME_AHEAD): when it later traces frame e+2 into the slot of frame e-1, its own
+// exchange of frame e has passed the all-ranks barrier, so every peer has finished reading e-1.
+constexpr int kImgRing = 3;
 
 struct Flags
 {
@@ -554,7 +559,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct Layout
 {
-  size_t off_flags, off_img_rgba[2], off_img_depth[2], off_res_rgba[2], off_res_depth[2];
+  size_t off_flags, off_img_rgba[kImgRing], off_img_depth[kImgRing], off_res_rgba[2], off_res_depth[2];
   size_t off_poff[2], off_psorted[2], off_pout, off_canvas_rgba, off_canvas_depth, total;
   size_t off_lflags, off_ltab[2], off_lpool_rgba[2], off_lpool_depth[2];
   size_t off_sync_depth;
@@ -565,8 +570,8 @@ Layout make_layout(size_t max_pixels, size_t max_partials, bool is_root)
   const size_t px = align_up(max_pixels, 64);
   size_t o = 0;
   L.off_flags = o; o += kFlagBytes;
-  for (int b = 0; b < 2; ++b) { L.off_img_rgba[b] = o; o += px * 4; }
-  for (int b = 0; b < 2; ++b) { L.off_img_depth[b] = o; o += px * 4; }
+  for (int b = 0; b < kImgRing; ++b) { L.off_img_rgba[b] = o; o += px * 4; }
+  for (int b = 0; b < kImgRing; ++b) { L.off_img_depth[b] = o; o += px * 4; }
   for (int b = 0; b < 2; ++b) { L.off_res_rgba[b] = o; o += px * 4; }
   for (int b = 0; b < 2; ++b) { L.off_res_depth[b] = o; o += px * 4; }
   for (int b = 0; b < 2; ++b) { L.off_poff[b] = o; o += max_partials ? align_up(partial_scan_padded(max_pixels) * 4, 256) : 0; }
@@ -647,8 +652,9 @@ vr_status comm_bind_frame(vr_ctx* ctx, size_t n_pixels)
   }
   const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
   const int b = (c.epoch + 1) & 1;
-  ctx->img_rgba = reinterpret_cast<uchar4*>(c.arena + L.off_img_rgba[b]);
-  ctx->img_depth = reinterpret_cast<float*>(c.arena + L.off_img_depth[b]);
+  const int slot = (int)((c.epoch + 1) % kImgRing);
+  ctx->img_rgba = reinterpret_cast<uchar4*>(c.arena + L.off_img_rgba[slot]);
+  ctx->img_depth = reinterpret_cast<float*>(c.arena + L.off_img_depth[slot]);
   ctx->res_rgba = reinterpret_cast<uchar4*>(c.arena + L.off_res_rgba[b]);
   ctx->res_depth = reinterpret_cast<float*>(c.arena + L.off_res_depth[b]);
   if (c.rank == 0 && c.max_partials)
@@ -665,6 +671,22 @@ vr_status comm_bind_frame(vr_ctx* ctx, size_t n_pixels)
     ctx->canvas_depth = reinterpret_cast<float*>(c.arena + L.off_canvas_depth);
     if (ctx->cap_pixels < c.max_pixels) ctx->cap_pixels = c.max_pixels;
   }
+  return VR_OK;
+}
+
+// where an image traced one frame AHEAD of the pending exchange goes (VR_FRAME_AHEAD)
+vr_status comm_ahead_image(vr_ctx* ctx, uchar4** rgba, float** depth)
+{
+  Comm& c = ctx->comm;
+  if (!c.on)
+  {
+    ctx->err = "VR_FRAME_AHEAD needs the exchange arena (vr_comm_init)";
+    return VR_ERR_STATE;
+  }
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
+  const int slot = (int)((c.epoch + 2) % kImgRing);
+  *rgba = reinterpret_cast<uchar4*>(c.arena + L.off_img_rgba[slot]);
+  *depth = reinterpret_cast<float*>(c.arena + L.off_img_depth[slot]);
   return VR_OK;
 }
 
@@ -802,8 +824,8 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
   p.W = ctx->W;
   for (int k = 0; k < 4; ++k) p.rect[k] = ctx->img_rect[k];
   if (ctx->W % 4 != 0) { p.rect[0] = p.rect[1] = 0; p.rect[2] = p.rect[3] = 0x7fffffff; }
-  p.off_img_rgba = L.off_img_rgba[b];
-  p.off_img_depth = L.off_img_depth[b];
+  p.off_img_rgba = L.off_img_rgba[c.epoch % kImgRing];
+  p.off_img_depth = L.off_img_depth[c.epoch % kImgRing];
   p.off_res_rgba = L.off_res_rgba[b];
   p.off_res_depth = L.off_res_depth[b];
   p.off_flags = L.off_flags;
@@ -849,10 +871,15 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
       }
     }
   }
-  // next frame quantises into the other parity
-  const int nb = (c.epoch + 1) & 1;
-  ctx->img_rgba = reinterpret_cast<uchar4*>(c.arena + L.off_img_rgba[nb]);
-  ctx->img_depth = reinterpret_cast<float*>(c.arena + L.off_img_depth[nb]);
+  // the next frame's image: the following ring slot -- where a frame traced ahead already sits
+  const int ns = (int)((c.epoch + 1) % kImgRing);
+  ctx->img_rgba = reinterpret_cast<uchar4*>(c.arena + L.off_img_rgba[ns]);
+  ctx->img_depth = reinterpret_cast<float*>(c.arena + L.off_img_depth[ns]);
+  if (ctx->img_ahead)
+  {
+    for (int k = 0; k < 4; ++k) ctx->img_rect[k] = ctx->img_rect_ahead[k];
+    ctx->img_ahead = false;
+  }
   return VR_OK;
 }
 

@@ -44,6 +44,7 @@ static vr_status fail(vr_ctx* c, vr_status st, const char* fmt, ...)
   } while (0)
 
 static vr_status ensure_frame(vr_ctx* ctx, int W, int H);
+namespace vr { vr_status comm_ahead_image(vr_ctx* ctx, uchar4** rgba, float** depth); } // comm.cu
 static void fill_to_canvas_params(const vr_camera* cam, int W, int H, ToCanvasParams& tp);
 
 // ================================================================= context
@@ -690,6 +691,16 @@ extern "C" vr_status vr_trace_to_image(vr_ctx* ctx, int block_id, const vr_camer
   }
   p.img_rgba = ctx->img_rgba;
   p.img_depth = ctx->img_depth;
+  const bool ahead = (flags & VR_FRAME_AHEAD) != 0;
+  if (ahead)
+  {
+    // the frame AFTER the one whose exchange is still to be issued: next slot of the image ring
+    REQUIRE(!(flags & VR_FRAME_WRITE_CANVAS), "vr_trace_to_image: VR_FRAME_AHEAD cannot write the canvas "
+            "(it belongs to the frame being exchanged)");
+    REQUIRE(!ctx->img_ahead, "vr_trace_to_image: one frame is already traced ahead; exchange a frame first");
+    st = comm_ahead_image(ctx, &p.img_rgba, &p.img_depth);
+    if (st != VR_OK) return st;
+  }
   p.write_canvas = (flags & VR_FRAME_WRITE_CANVAS) ? 1 : 0;
   p.n_clear_chunks = (flags & VR_FRAME_NO_CLEAR) ? 0 : (int)(((size_t)width * height + 511) / 512);
   st = stage_for_trace(ctx, block_id, p, ctx->stream, ctx->tile_counter, true);
@@ -697,9 +708,11 @@ extern "C" vr_status vr_trace_to_image(vr_ctx* ctx, int block_id, const vr_camer
   CK(launch_trace(p, 2, ctx->sm_count, ctx->stream));
   ctx->launches++;
   // what the multi-GPU fold needs to know: outside this rectangle my image is empty
-  ctx->img_rect[0] = p.tx0; ctx->img_rect[1] = p.sy;
-  ctx->img_rect[2] = p.tx1; ctx->img_rect[3] = p.sy + p.sh;
-  if (p.sw <= 0 || p.sh <= 0) ctx->img_rect[0] = ctx->img_rect[1] = ctx->img_rect[2] = ctx->img_rect[3] = 0;
+  int* rect = ahead ? ctx->img_rect_ahead : ctx->img_rect;
+  rect[0] = p.tx0; rect[1] = p.sy;
+  rect[2] = p.tx1; rect[3] = p.sy + p.sh;
+  if (p.sw <= 0 || p.sh <= 0) rect[0] = rect[1] = rect[2] = rect[3] = 0;
+  if (ahead) ctx->img_ahead = true;
   return VR_OK;
 }
 

@@ -134,6 +134,9 @@ struct vr_ctx
   bool img_in_arena = false;
   bool canvas_in_arena = false;
   int img_rect[4] = { 0, 0, 0x7fffffff, 0x7fffffff }; // where the quantised image may be non-empty
+  // an image traced one frame ahead of the pending exchange (VR_FRAME_AHEAD) and its rectangle
+  bool img_ahead = false;
+  int img_rect_ahead[4] = { 0, 0, 0x7fffffff, 0x7fffffff };
 
   // partial list
   vr_partial* partials = nullptr;

@@ -126,6 +126,11 @@ def run_bench(args, wl, bench):
 
     blocks = bench.block_layout(wl)
     mine = assign_blocks(len(blocks), world)[rank]
+    if getattr(args, "one_block_per_rank", False):
+        # diagnostics: the front blocks of c3, one per rank -> the image path (A) at any N
+        blocks = blocks[len(blocks) - world:]
+        mine = [rank]
+        wl = dict(wl, name=wl["name"] + " [diagnostic: %d front blocks only]" % world)
     W, H = wl["W"], wl["H"]
     nvox = int(np.prod(blocks[0]["dims"]))
     fields = {}
@@ -157,10 +162,11 @@ def run_bench(args, wl, bench):
     vis_all, _ = global_visibility_order([sp["bounds"][i] for i in mine], cam, dist)
     vis_rank = np.ascontiguousarray(vis_all[:, 0], np.int32)  # path A: one domain per rank
 
-    def render():
+    def render(ahead=False):
         if path_a:
             # Canvas::Clear + RenderCells + Image::Init in one launch, straight into the exchange arena
-            ctx.trace_to_image(mine[0], cam, W, H, sp["sample_dist"], rmin, rmax, no_clear=True)
+            # (ahead: into the next slot of the image ring, see VR_FRAME_AHEAD)
+            ctx.trace_to_image(mine[0], cam, W, H, sp["sample_dist"], rmin, rmax, no_clear=True, ahead=ahead)
         else:
             ctx.layers_begin(W, H)
             ctx.trace_blocks_to_layers(mine, cam, sp["sample_dist"], rmin, rmax, False)
@@ -188,25 +194,44 @@ def run_bench(args, wl, bench):
         clocks = bench.ClockSampler(local) if rank == 0 else None
         if clocks:
             clocks.start()
-        marks = [(ev(), ev(), ev()) for _ in range(args.steps)]
-        t0, t1 = ev(), ev()
-        torch.cuda.synchronize()
-        dist.barrier()
-        t0.record(stream)
-        for k in range(args.steps):
-            marks[k][0].record(stream)
-            render()
-            marks[k][1].record(stream)
-            composite()
-            marks[k][2].record(stream)
-        t1.record(stream)
-        torch.cuda.synchronize()
-        dist.barrier()
-        clk = clocks.stop() if clocks else None
+        def timed(pipelined):
+            """K steps, each one trace + one exchange.  serial: trace(k), exchange(k).  pipelined (path A,
+            the renders of a batch are independent, Scene.cpp:133-149): trace(k+1) is issued BEFORE
+            exchange(k) -- the first trace is the prologue outside the timed region, the last traced
+            image is left over -- so a rank that finishes early traces on instead of idling in the
+            exchange.  Same kernels and the same number of them per step either way."""
+            marks = [(ev(), ev(), ev()) for _ in range(args.steps)]
+            t0, t1 = ev(), ev()
+            if pipelined:
+                render()
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0.record(stream)
+            for k in range(args.steps):
+                marks[k][0].record(stream)
+                render(ahead=pipelined)
+                marks[k][1].record(stream)
+                composite()
+                marks[k][2].record(stream)
+            t1.record(stream)
+            torch.cuda.synchronize()
+            dist.barrier()
+            return (t0.elapsed_time(t1), float(np.mean([a.elapsed_time(b) for a, b, _ in marks])),
+                    float(np.mean([b.elapsed_time(c) for _, b, c in marks])))
+
+        serial = timed(False)
         launches = ctx.kernel_launches() - l0
-        total_ms = t0.elapsed_time(t1)
-        render_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in marks]))
-        tail_ms = float(np.mean([b.elapsed_time(c) for _, b, c in marks]))
+        piped = timed(True) if path_a else None
+        clk = clocks.stop() if clocks else None
+        # the pipelined order is the product path for batches of renders; report it when it wins on
+        # EVERY rank's clock (max over ranks is taken below), the serial order otherwise
+        use_piped = False
+        if piped is not None:
+            tp = torch.tensor([piped[0], serial[0]], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            use_piped = bool(tp[0] < tp[1])
+            serial_total_max = float(tp[1])
+        total_ms, render_ms, tail_ms = piped if use_piped else serial
 
         # composite alone: all local images/partials resident, ranks aligned by a barrier
         comp = []
@@ -269,9 +294,12 @@ def run_bench(args, wl, bench):
                            "path": "A (uint8 image, P2P direct-send fold)" if path_a else
                                    "B (float partials as dense ray layers, P2P gather+fold)",
                            "blocks_per_gpu": len(mine),
+                           "order": ("pipelined: trace(k+1) issued before exchange(k) (VR_FRAME_AHEAD)" if use_piped
+                                     else "serial: trace(k), exchange(k)"),
                            "l2": "inputs (%.0f MB of field per GPU) larger than the 126 MB L2" % (
                                nvox * 4 * len(mine) / 1e6)},
                 "frames_per_s": 1e3 / ms, "render_ms_per_frame": render_ms,
+                "ms_per_step_serial_order": (serial_total_max / args.steps) if piped is not None else ms,
                 "composite_ms_per_frame": comp_ms, "composite_in_step_ms": tail_ms,
                 "partials_total": int(tsum[5]),
                 "per_rank_ms": {"columns": ["total", "render_per_frame", "composite_in_step", "composite_aligned"],

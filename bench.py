@@ -433,6 +433,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
+    ap.add_argument("--one-block-per-rank", action="store_true",
+                    help="N > 1 diagnostics: rank r renders only block r of c3 (path A at any N); not a bench line")
     ap.add_argument("--samples", type=int, default=None,
                     help="samples option of the volume plot (default 100; 887 = one sample per voxel on c2)")
     args = ap.parse_args()

@@ -166,8 +166,13 @@ VR_API vr_status vr_render_image(vr_ctx* ctx, int block_id, const vr_camera* cam
  * k/255 float canvas.  Results are bit-identical to vr_canvas_clear + vr_trace_to_canvas(.., 0) +
  * vr_image_from_canvas [+ vr_image_to_canvas_dev].
  * VR_FRAME_NO_CLEAR: do not write the pixels outside the block's screen rectangle (they are left
- * undefined); only for images handed to vr_comm_composite_images, which never reads them.       */
-enum { VR_FRAME_WRITE_CANVAS = 1, VR_FRAME_NO_CLEAR = 2 };
+ * undefined); only for images handed to vr_comm_composite_images, which never reads them.
+ * VR_FRAME_AHEAD (multi-GPU, after vr_comm_init): this is the image of the frame AFTER the one whose
+ * vr_comm_composite_images call is still to come -- it goes to the next slot of the rank's image ring
+ * and becomes the pending image once that exchange has been issued.  Lets the renders of a batch
+ * (Scene.cpp:133-149) be software-pipelined: trace(k+1), exchange(k), trace(k+2), exchange(k+1), ... so
+ * that no rank idles in an exchange while it could be tracing.  At most one frame may be ahead.    */
+enum { VR_FRAME_WRITE_CANVAS = 1, VR_FRAME_NO_CLEAR = 2, VR_FRAME_AHEAD = 4 };
 VR_API vr_status vr_trace_to_image(vr_ctx* ctx, int block_id, const vr_camera* cam, int width,
                                    int height, float sample_dist, float range_min, float range_max,
                                    int flags);

@@ -186,6 +186,50 @@ def gpu_checks(rank, world):
                 ctx.synchronize()
             dist.barrier()
 
+        # ---------------- path A, renders of a batch software-pipelined (VR_FRAME_AHEAD): trace(k+1) is
+        # issued before exchange(k); every exchanged frame must still be the oracle's frame k
+        def cam_of(k):
+            c = O.camera_reset_to_bounds(gb)
+            O.camera_azimuth(c, 15.0 + 40.0 * k)
+            O.camera_elevation(c, 5.0 * k)
+            return c
+
+        def oracle_frame(c):
+            layers, depths = [], []
+            for dom in doms:
+                r, dd = O.new_canvas(W, H)
+                O.render_to_canvas(scenes.oracle_block(dom), c, W, H, sc["lut"], sd, rmin, rmax, r, dd)
+                q = O.image_init(r, dd, 0)
+                layers.append(q[0])
+                depths.append(q[1])
+            order, _ = O.visibility_order(np.array(bounds), c)
+            return O.ordered_composite(np.stack(layers), np.stack(depths), order)
+
+        n_frames = 5
+        ctx.trace_to_image(0, cam_of(0), W, H, sd, rmin, rmax, no_clear=True)
+        for k in range(n_frames):
+            if k + 1 < n_frames:
+                ctx.trace_to_image(0, cam_of(k + 1), W, H, sd, rmin, rmax, no_clear=True, ahead=True)
+                if k == 0:
+                    try:   # only one frame may be ahead
+                        ctx.trace_to_image(0, cam_of(k + 2), W, H, sd, rmin, rmax, no_clear=True, ahead=True)
+                        raise AssertionError("a second frame ahead must be refused")
+                    except _lib.VRError:
+                        pass
+            vis_all, _ = D.global_visibility_order([bounds[rank]], cam_of(k), dist)
+            ctx.comm_composite_images_to_canvas(np.ascontiguousarray(vis_all[:, 0], np.int32))
+            if rank == 0:
+                u8, d = ctx.image_result_download(W, H)
+                ref, rd = oracle_frame(cam_of(k))
+                assert np.array_equal(u8, ref), "pipelined path A: frame %d differs" % k
+                assert np.array_equal(d, rd, equal_nan=True), "pipelined path A: depth of frame %d differs" % k
+                can, cd = ctx.canvas_download(W, H)
+                o_can, o_cd = O.image_to_canvas(ref, rd)
+                assert np.array_equal(can, o_can) and np.array_equal(cd, o_cd, equal_nan=True)
+            else:
+                ctx.synchronize()
+            dist.barrier()
+
         # ---------------- opaque surfaces + volume (Scene::Render passes 1 and 2, Scene.cpp:160-214):
         # every rank holds an opaque canvas (here: synthetic fragments, incl. cross-rank depth ties and
         # far fragments) -> z-buffer composite to rank 0 -> ImageToCanvas -> SynchDepths -> volume pass
