@@ -64,6 +64,10 @@ struct Flags
   // (rank 0 only) s_done[r] = last epoch rank r has finished pulling
   unsigned int s_ready;
   unsigned int s_done[kMaxRanks];
+  // (rank 0 only) outside these rectangles {x0,y0,x1,y1} the result image of each parity / the canvas
+  // hold the cleared value, as left by the last exchange kernel (host decides whether that still holds)
+  int clean_res[2][4];
+  int clean_canvas[4];
 };
 static_assert(sizeof(Flags) <= 4096, "flag block");
 
@@ -168,11 +172,38 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
         cover |= 1u << l;
     return cover;
   };
+  // ---- rank 0: what may be dirty.  The previous exchange left the result image of this parity (and the
+  // canvas) cleared outside the rectangles in the flags; if the host vouches that nobody wrote them
+  // since, only groups inside those rectangles that no rank covers now need the cleared value again.
+  __shared__ int s_dirty[2][4]; // [0] result image, [1] canvas
+  __shared__ int s_union[4];    // bounding box of this frame's rectangles
+  if (P.rank == 0 && threadIdx.x == 0)
+  {
+    int u[4] = { 0x7fffffff, 0x7fffffff, 0, 0 };
+    for (int l = 0; l < P.size; ++l)
+      if (s_rect[l][2] > s_rect[l][0] && s_rect[l][3] > s_rect[l][1])
+      {
+        u[0] = min(u[0], s_rect[l][0]); u[1] = min(u[1], s_rect[l][1]);
+        u[2] = max(u[2], s_rect[l][2]); u[3] = max(u[3], s_rect[l][3]);
+      }
+    if (u[2] <= u[0]) u[0] = u[1] = u[2] = u[3] = 0;
+    for (int k = 0; k < 4; ++k)
+    {
+      s_union[k] = u[k];
+      s_dirty[0][k] = P.track_res ? ((volatile int*)my_flags->clean_res[par])[k] : (k < 2 ? 0 : 0x7fffffff);
+      s_dirty[1][k] = P.track_canvas ? ((volatile int*)my_flags->clean_canvas)[k] : (k < 2 ? 0 : 0x7fffffff);
+    }
+  }
+  __syncthreads();
   auto write_empty = [&](size_t i) {
-    out_rgba[i] = make_uint4(0u, 0u, 0u, 0u);
-    // N >= 2 all-clear layers fold to min(min(1.001,1.001), ...) = 1.001; one layer is copied
-    out_depth[i] = make_float4(1.001f, 1.001f, 1.001f, 1.001f);
-    if (TO_CANVAS)
+    const int y = (int)(i / (size_t)w4), x = (int)(i % (size_t)w4) * 4;
+    if (y >= s_dirty[0][1] && y < s_dirty[0][3] && x >= s_dirty[0][0] && x < s_dirty[0][2])
+    {
+      out_rgba[i] = make_uint4(0u, 0u, 0u, 0u);
+      // N >= 2 all-clear layers fold to min(min(1.001,1.001), ...) = 1.001; one layer is copied
+      out_depth[i] = make_float4(1.001f, 1.001f, 1.001f, 1.001f);
+    }
+    if (TO_CANVAS && y >= s_dirty[1][1] && y < s_dirty[1][3] && x >= s_dirty[1][0] && x < s_dirty[1][2])
     {
 #pragma unroll
       for (int k = 0; k < 4; ++k) P.canvas_rgba[4 * i + k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -243,12 +274,20 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
   // ---- rank 0 also writes the groups NO rank covers inside the other ranks' chunks (their owners skip
   // them); streaming stores into local HBM while the peers' folded pixels are still in flight
   if (P.rank == 0 && P.size > 1)
-    for (size_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x)
+  {
+    // only the rows the dirty rectangles span
+    const int y_lo = min(s_dirty[0][1], TO_CANVAS ? s_dirty[1][1] : 0x7fffffff);
+    const int y_hi = max(s_dirty[0][3], TO_CANVAS ? s_dirty[1][3] : 0);
+    const size_t c_lo = y_lo <= 0 ? 0 : ((size_t)y_lo * (size_t)w4) / kChunkGroups;
+    const size_t c_end = y_hi >= (int)(n4 / (size_t)w4) ? n_chunks
+                                                          : min(n_chunks, ((size_t)y_hi * (size_t)w4) / kChunkGroups + 1);
+    for (size_t chunk = c_lo + blockIdx.x; chunk < c_end; chunk += gridDim.x)
     {
       if (chunk % (size_t)P.size == 0) continue;
       const size_t i = chunk * kChunkGroups + threadIdx.x;
       if (i < n4 && coverage(i) == 0) write_empty(i);
     }
+  }
 
   // ---- last CTA out tells rank 0 that my range has landed
   __syncthreads();
@@ -259,6 +298,15 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
     if (prev == gridDim.x - 1)
     {
       my_flags->cta_done = 0;
+      if (P.rank == 0)
+      {
+        // every CTA has read the old rectangles: what this frame leaves cleared
+        for (int k = 0; k < 4; ++k)
+        {
+          my_flags->clean_res[par][k] = s_union[k];
+          if (TO_CANVAS) my_flags->clean_canvas[k] = s_union[k];
+        }
+      }
       Flags* root = reinterpret_cast<Flags*>(P.peers[0] + P.off_flags);
       __threadfence_system();
       st_release_sys(&root->done[P.rank], P.epoch);
@@ -726,7 +774,7 @@ static vr_status cfail(vr_ctx* ctx, vr_status st, const char* what, cudaError_t 
 extern "C" vr_status vr_comm_init(vr_ctx* ctx, int rank, int n_ranks, size_t max_pixels,
                                   size_t max_partials, void* handle_out)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   if (ctx->comm.on) return cfail(ctx, VR_ERR_STATE, "vr_comm_init: already initialised", cudaSuccess);
   if (rank < 0 || n_ranks < 1 || rank >= n_ranks || n_ranks > kMaxRanks || !handle_out || max_pixels == 0)
     return cfail(ctx, VR_ERR_INVALID, "vr_comm_init: bad rank/size (max 16 ranks) or NULL handle", cudaSuccess);
@@ -770,7 +818,7 @@ extern "C" vr_status vr_comm_init(vr_ctx* ctx, int rank, int n_ranks, size_t max
 
 extern "C" vr_status vr_comm_connect(vr_ctx* ctx, const void* all_handles)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   Comm& c = ctx->comm;
   if (!c.on || !all_handles) return cfail(ctx, VR_ERR_STATE, "vr_comm_connect: call vr_comm_init first", cudaSuccess);
   cudaSetDevice(ctx->device);
@@ -845,6 +893,15 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
     p.canvas_rgba = ctx->canvas_rgba;
     p.canvas_depth = ctx->canvas_depth;
   }
+  if (c.rank == 0)
+  {
+    // may the kernel trust the "cleared outside" rectangles its predecessor left in the flags?
+    auto still = [&](const Comm::Clean& k) {
+      return k.valid && k.serial == ctx->api_serial && k.W == ctx->W && k.H == ctx->H;
+    };
+    p.track_res = still(c.clean_res[b]) ? 1 : 0;
+    p.track_canvas = (p.canvas_rgba && still(c.clean_canvas)) ? 1 : 0;
+  }
   cudaError_t e = launch_fold_p2p(p, ctx->sm_count, ctx->stream);
   if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "fold_p2p launch", e);
   ctx->launches++;
@@ -871,6 +928,16 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
       }
     }
   }
+  if (c.rank == 0)
+  {
+    // (a canvas not written by this call keeps whatever state it had: its serial no longer matches
+    // only if some other entry point has been called since)
+    c.clean_res[b].valid = true; c.clean_res[b].serial = ctx->api_serial; c.clean_res[b].W = ctx->W; c.clean_res[b].H = ctx->H;
+    if (p.canvas_rgba)
+    {
+      c.clean_canvas.valid = true; c.clean_canvas.serial = ctx->api_serial; c.clean_canvas.W = ctx->W; c.clean_canvas.H = ctx->H;
+    }
+  }
   // the next frame's image: the following ring slot -- where a frame traced ahead already sits
   const int ns = (int)((c.epoch + 1) % kImgRing);
   ctx->img_rgba = reinterpret_cast<uchar4*>(c.arena + L.off_img_rgba[ns]);
@@ -885,7 +952,7 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
 
 extern "C" vr_status vr_image_result_download(vr_ctx* ctx, uint8_t* rgba, float* depth)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER_RO(ctx);
   if (ctx->W <= 0 || !ctx->res_rgba) return cfail(ctx, VR_ERR_STATE, "vr_image_result_download: no result", cudaSuccess);
   const size_t n = (size_t)ctx->W * ctx->H;
   cudaError_t e = cudaSuccess;
@@ -898,7 +965,7 @@ extern "C" vr_status vr_image_result_download(vr_ctx* ctx, uint8_t* rgba, float*
 
 extern "C" vr_status vr_image_result_to_canvas(vr_ctx* ctx)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   if (ctx->W <= 0 || !ctx->res_rgba) return cfail(ctx, VR_ERR_STATE, "vr_image_result_to_canvas: no result", cudaSuccess);
   return vr_image_to_canvas_dev(ctx, reinterpret_cast<const uint8_t*>(ctx->res_rgba), ctx->res_depth);
 }
@@ -1014,32 +1081,32 @@ static vr_status comm_composite_partials_impl(vr_ctx* ctx, const vr_camera* cam)
 
 extern "C" vr_status vr_comm_composite_partials(vr_ctx* ctx)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   return comm_composite_partials_impl(ctx, nullptr);
 }
 
 extern "C" vr_status vr_comm_composite_partials_to_canvas(vr_ctx* ctx, const vr_camera* cam)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   if (!cam) return cfail(ctx, VR_ERR_INVALID, "vr_comm_composite_partials_to_canvas: camera is NULL", cudaSuccess);
   return comm_composite_partials_impl(ctx, cam);
 }
 
 extern "C" vr_status vr_comm_composite_images(vr_ctx* ctx, const int* vis_order)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER_RO(ctx);
   return comm_composite_images_impl(ctx, vis_order, false);
 }
 
 extern "C" vr_status vr_comm_composite_images_to_canvas(vr_ctx* ctx, const int* vis_order)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER_RO(ctx);
   return comm_composite_images_impl(ctx, vis_order, true);
 }
 
 extern "C" vr_status vr_comm_composite_zbuffer(vr_ctx* ctx)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER_RO(ctx);
   int order[kMaxRanks];
   for (int i = 0; i < kMaxRanks; ++i) order[i] = i; // rank order
   return comm_composite_images_impl(ctx, order, false, true);
@@ -1047,7 +1114,7 @@ extern "C" vr_status vr_comm_composite_zbuffer(vr_ctx* ctx)
 
 extern "C" vr_status vr_comm_sync_depths(vr_ctx* ctx)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   Comm& c = ctx->comm;
   if (!c.on || !c.peer_dev) return cfail(ctx, VR_ERR_STATE, "vr_comm_sync_depths: not connected", cudaSuccess);
   if (ctx->W <= 0 || !ctx->canvas_depth) return cfail(ctx, VR_ERR_STATE, "vr_comm_sync_depths: no canvas", cudaSuccess);
@@ -1085,7 +1152,7 @@ extern "C" vr_status vr_comm_sync_depths(vr_ctx* ctx)
 
 extern "C" vr_status vr_comm_layers_composite_to_canvas(vr_ctx* ctx, const vr_camera* cam)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   Comm& c = ctx->comm;
   if (!c.on || !c.peer_dev) return cfail(ctx, VR_ERR_STATE, "vr_comm_layers_composite_to_canvas: not connected", cudaSuccess);
   if (!cam) return cfail(ctx, VR_ERR_INVALID, "vr_comm_layers_composite_to_canvas: camera is NULL", cudaSuccess);

@@ -177,7 +177,7 @@ extern "C" const char* vr_last_error(const vr_ctx* ctx)
 
 extern "C" vr_status vr_set_stream(vr_ctx* ctx, void* cuda_stream)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER_RO(ctx);
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   return VR_OK;
@@ -185,7 +185,7 @@ extern "C" vr_status vr_set_stream(vr_ctx* ctx, void* cuda_stream)
 
 extern "C" vr_status vr_synchronize(vr_ctx* ctx)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER_RO(ctx);
   CK(cudaStreamSynchronize(ctx->stream));
   return VR_OK;
 }
@@ -294,7 +294,7 @@ extern "C" vr_status vr_block_uniform(vr_ctx* ctx, int block_id, const int dims[
                                       const float origin[3], const float spacing[3],
                                       const void* field, int dtype, int assoc, int where)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER_RO(ctx);
   REQUIRE(dims && origin && spacing, "vr_block_uniform: NULL argument");
   CK(cudaSetDevice(ctx->device));
   Block b;
@@ -331,7 +331,7 @@ extern "C" vr_status vr_block_rectilinear(vr_ctx* ctx, int block_id, const int d
                                           const double* x, const double* y, const double* z,
                                           const void* field, int dtype, int assoc, int where)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER_RO(ctx);
   REQUIRE(dims && x && y && z, "vr_block_rectilinear: NULL argument");
   CK(cudaSetDevice(ctx->device));
   Block b;
@@ -377,7 +377,7 @@ extern "C" vr_status vr_block_rectilinear(vr_ctx* ctx, int block_id, const int d
 
 extern "C" vr_status vr_block_free(vr_ctx* ctx, int block_id)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER_RO(ctx);
   auto it = ctx->blocks.find(block_id);
   REQUIRE(it != ctx->blocks.end(), "vr_block_free: unknown block %d", block_id);
   CK(cudaStreamSynchronize(ctx->stream));
@@ -388,7 +388,7 @@ extern "C" vr_status vr_block_free(vr_ctx* ctx, int block_id)
 
 extern "C" vr_status vr_block_staged_bytes(vr_ctx* ctx, int block_id, size_t* bytes)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER_RO(ctx);
   auto it = ctx->blocks.find(block_id);
   REQUIRE(it != ctx->blocks.end() && bytes, "vr_block_staged_bytes: unknown block %d", block_id);
   const Block& b = it->second;
@@ -406,7 +406,7 @@ extern "C" vr_status vr_block_staged_bytes(vr_ctx* ctx, int block_id, size_t* by
 
 extern "C" vr_status vr_block_bounds(vr_ctx* ctx, int block_id, double out[6])
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER_RO(ctx);
   auto it = ctx->blocks.find(block_id);
   REQUIRE(it != ctx->blocks.end() && out, "vr_block_bounds: unknown block %d", block_id);
   std::memcpy(out, it->second.bounds, sizeof(double) * 6);
@@ -416,7 +416,7 @@ extern "C" vr_status vr_block_bounds(vr_ctx* ctx, int block_id, double out[6])
 // ================================================================= transfer function
 extern "C" vr_status vr_set_tf(vr_ctx* ctx, const float* rgba, int n_entries)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER_RO(ctx);
   REQUIRE(rgba && n_entries >= 2 && n_entries <= 1024, "vr_set_tf: need 2..1024 entries (got %d)",
           n_entries);
   CK(cudaSetDevice(ctx->device));
@@ -469,7 +469,7 @@ static vr_status ensure_frame(vr_ctx* ctx, int W, int H)
 
 extern "C" vr_status vr_canvas_clear(vr_ctx* ctx, int width, int height)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   CK(cudaSetDevice(ctx->device));
   vr_status st = ensure_frame(ctx, width, height);
   if (st != VR_OK) return st;
@@ -481,7 +481,7 @@ extern "C" vr_status vr_canvas_clear(vr_ctx* ctx, int width, int height)
 extern "C" vr_status vr_canvas_upload(vr_ctx* ctx, int width, int height, const float* rgba,
                                       const float* depth)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(rgba && depth, "vr_canvas_upload: NULL buffer");
   CK(cudaSetDevice(ctx->device));
   vr_status st = ensure_frame(ctx, width, height);
@@ -494,7 +494,7 @@ extern "C" vr_status vr_canvas_upload(vr_ctx* ctx, int width, int height, const 
 
 extern "C" vr_status vr_canvas_download(vr_ctx* ctx, float* rgba, float* depth)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER_RO(ctx);
   REQUIRE(ctx->W > 0, "vr_canvas_download: no canvas yet");
   const size_t n = (size_t)ctx->W * ctx->H;
   if (rgba) CK(cudaMemcpyAsync(rgba, ctx->canvas_rgba, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
@@ -505,7 +505,7 @@ extern "C" vr_status vr_canvas_download(vr_ctx* ctx, float* rgba, float* depth)
 
 extern "C" vr_status vr_canvas_blend_background(vr_ctx* ctx, const float bg_rgba[4])
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(ctx->W > 0, "vr_canvas_blend_background: no canvas yet");
   REQUIRE(bg_rgba, "vr_canvas_blend_background: NULL colour");
   CK(cudaSetDevice(ctx->device));
@@ -516,7 +516,7 @@ extern "C" vr_status vr_canvas_blend_background(vr_ctx* ctx, const float bg_rgba
 
 extern "C" vr_status vr_canvas_download_rgba8(vr_ctx* ctx, const float* bg_rgba, int flip_rows, uint8_t* out_rgba8)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER_RO(ctx);
   REQUIRE(ctx->W > 0, "vr_canvas_download_rgba8: no canvas yet");
   REQUIRE(out_rgba8, "vr_canvas_download_rgba8: NULL output");
   CK(cudaSetDevice(ctx->device));
@@ -540,7 +540,7 @@ extern "C" vr_status vr_canvas_download_rgba8(vr_ctx* ctx, const float* bg_rgba,
 
 extern "C" vr_status vr_canvas_ptrs(vr_ctx* ctx, void** rgba_dev, void** depth_dev)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(ctx->W > 0, "vr_canvas_ptrs: no canvas yet");
   if (rgba_dev) *rgba_dev = ctx->canvas_rgba;
   if (depth_dev) *depth_dev = ctx->canvas_depth;
@@ -644,7 +644,7 @@ extern "C" vr_status vr_trace_to_canvas(vr_ctx* ctx, int block_id, const vr_came
                                         float sample_dist, float range_min, float range_max,
                                         int use_canvas_depth)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(ctx->W > 0, "vr_trace_to_canvas: call vr_canvas_clear/upload first");
   CK(cudaSetDevice(ctx->device));
   TraceParams p;
@@ -662,7 +662,7 @@ extern "C" vr_status vr_render_image(vr_ctx* ctx, int block_id, const vr_camera*
                                      int height, float sample_dist, float range_min,
                                      float range_max, float* rgba_inout, float* depth_inout)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(rgba_inout && depth_inout, "vr_render_image: NULL canvas");
   vr_status st = vr_canvas_upload(ctx, width, height, rgba_inout, depth_inout);
   if (st != VR_OK) return st;
@@ -675,7 +675,8 @@ extern "C" vr_status vr_trace_to_image(vr_ctx* ctx, int block_id, const vr_camer
                                        int height, float sample_dist, float range_min,
                                        float range_max, int flags)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER_RO(ctx);
+  if (flags & VR_FRAME_WRITE_CANVAS) ++ctx->api_serial; // writes the canvas
   CK(cudaSetDevice(ctx->device));
   vr_status st = ensure_frame(ctx, width, height);
   if (st != VR_OK) return st;
@@ -740,7 +741,7 @@ static vr_status ensure_partials(vr_ctx* ctx, size_t need)
 
 extern "C" vr_status vr_partials_begin(vr_ctx* ctx, int width, int height)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(width > 0 && height > 0 && (long long)width * height < (1ll << 31), "bad image size");
   CK(cudaSetDevice(ctx->device));
   ctx->pW = width;
@@ -755,7 +756,7 @@ extern "C" vr_status vr_trace_to_partials(vr_ctx* ctx, int block_id, const vr_ca
                                           float sample_dist, float range_min, float range_max,
                                           int use_canvas_depth)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(ctx->pW > 0, "vr_trace_to_partials: call vr_partials_begin first");
   REQUIRE(!use_canvas_depth || (ctx->W == ctx->pW && ctx->H == ctx->pH),
           "vr_trace_to_partials: canvas depth requested but canvas size differs");
@@ -782,7 +783,7 @@ extern "C" vr_status vr_trace_to_partials(vr_ctx* ctx, int block_id, const vr_ca
 
 extern "C" vr_status vr_partials_count(vr_ctx* ctx, size_t* n)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER_RO(ctx);
   REQUIRE(n, "vr_partials_count: NULL");
   unsigned long long c = 0;
   const unsigned long long* src = ctx->plist ? ctx->plist_count : ctx->partial_count;
@@ -795,7 +796,7 @@ extern "C" vr_status vr_partials_count(vr_ctx* ctx, size_t* n)
 
 extern "C" vr_status vr_partials_download(vr_ctx* ctx, vr_partial* out, size_t capacity, size_t* n)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER_RO(ctx);
   size_t c = 0;
   vr_status st = vr_partials_count(ctx, &c);
   if (st != VR_OK) return st;
@@ -815,7 +816,7 @@ extern "C" vr_status vr_render_partials(vr_ctx* ctx, int block_id, const vr_came
                                         float range_max, const float* depth_in, vr_partial** out,
                                         size_t* n)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(out && n, "vr_render_partials: NULL output");
   *out = nullptr;
   *n = 0;
@@ -877,7 +878,7 @@ static vr_status ensure_layer_pool(vr_ctx* ctx, size_t need)
 
 extern "C" vr_status vr_layers_begin(vr_ctx* ctx, int width, int height)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(width > 0 && height > 0 && (long long)width * height < (1ll << 31), "bad image size");
   CK(cudaSetDevice(ctx->device));
   if (!ctx->ltab_host) ctx->ltab_host = new LayerTable(); // pageable on purpose: async copies stage it
@@ -898,7 +899,7 @@ extern "C" vr_status vr_layers_begin(vr_ctx* ctx, int width, int height)
 extern "C" vr_status vr_trace_to_layer(vr_ctx* ctx, int block_id, const vr_camera* cam, float sample_dist,
                                        float range_min, float range_max, int use_canvas_depth)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(ctx->lW > 0, "vr_trace_to_layer: call vr_layers_begin first");
   REQUIRE(!use_canvas_depth || (ctx->W == ctx->lW && ctx->H == ctx->lH),
           "vr_trace_to_layer: canvas depth requested but canvas size differs");
@@ -937,7 +938,7 @@ extern "C" vr_status vr_trace_blocks_to_layers(vr_ctx* ctx, int n_blocks, const 
                                                const vr_camera* cam, float sample_dist, float range_min,
                                                float range_max, int use_canvas_depth)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(ctx->lW > 0, "vr_trace_blocks_to_layers: call vr_layers_begin first");
   REQUIRE(n_blocks >= 0 && (n_blocks == 0 || block_ids), "vr_trace_blocks_to_layers: NULL block list");
   REQUIRE(!use_canvas_depth || (ctx->W == ctx->lW && ctx->H == ctx->lH),
@@ -1010,7 +1011,7 @@ namespace vr { vr_status ensure_frame_pub(vr_ctx* ctx, int W, int H) { return en
 
 extern "C" vr_status vr_layers_composite_to_canvas(vr_ctx* ctx, const vr_camera* cam, int canvas_is_clear)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(cam, "vr_layers_composite_to_canvas: camera is NULL");
   REQUIRE(ctx->lW > 0, "vr_layers_composite_to_canvas: call vr_layers_begin first");
   CK(cudaSetDevice(ctx->device));
@@ -1045,7 +1046,7 @@ extern "C" vr_status vr_layers_composite_to_canvas(vr_ctx* ctx, const vr_camera*
 
 extern "C" vr_status vr_layers_to_partials(vr_ctx* ctx)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(ctx->lW > 0, "vr_layers_to_partials: call vr_layers_begin first");
   vr_status st = vr_partials_begin(ctx, ctx->lW, ctx->lH);
   if (st != VR_OK) return st;
@@ -1063,7 +1064,7 @@ extern "C" vr_status vr_layers_to_partials(vr_ctx* ctx)
 // ================================================================= image compositing
 extern "C" vr_status vr_image_from_canvas(vr_ctx* ctx)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(ctx->W > 0, "vr_image_from_canvas: no canvas yet");
   CK(cudaSetDevice(ctx->device));
   CK(launch_quantize(ctx->canvas_rgba, ctx->canvas_depth, (size_t)ctx->W * ctx->H, ctx->img_rgba,
@@ -1076,7 +1077,7 @@ extern "C" vr_status vr_image_from_canvas(vr_ctx* ctx)
 
 extern "C" vr_status vr_image_download(vr_ctx* ctx, uint8_t* rgba, float* depth)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER_RO(ctx);
   REQUIRE(ctx->W > 0, "vr_image_download: no image yet");
   const size_t n = (size_t)ctx->W * ctx->H;
   if (rgba) CK(cudaMemcpyAsync(rgba, ctx->img_rgba, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1087,7 +1088,7 @@ extern "C" vr_status vr_image_download(vr_ctx* ctx, uint8_t* rgba, float* depth)
 
 extern "C" vr_status vr_image_ptrs(vr_ctx* ctx, void** rgba8_dev, void** depth_dev)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(ctx->W > 0, "vr_image_ptrs: no image yet");
   if (rgba8_dev) *rgba8_dev = ctx->img_rgba;
   if (depth_dev) *depth_dev = ctx->img_depth;
@@ -1106,7 +1107,7 @@ extern "C" vr_status vr_fold_images_dev(vr_ctx* ctx, const uint8_t* rgba, const 
                                         int n_layers, size_t n_pixels, uint8_t* out_rgba,
                                         float* out_depth)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(rgba && depth && vis_order_host && out_rgba && out_depth, "vr_fold_images_dev: NULL argument");
   REQUIRE(n_layers >= 1 && n_layers <= 64, "vr_fold_images_dev: 1..64 layers supported (got %d)", n_layers);
   CK(cudaSetDevice(ctx->device));
@@ -1122,7 +1123,7 @@ extern "C" vr_status vr_composite_images(vr_ctx* ctx, const float* rgba, const f
                                          const int* vis_order, int n_images, int width, int height,
                                          uint8_t* out_rgba, float* out_depth)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(rgba && depth && vis_order && out_rgba && out_depth, "vr_composite_images: NULL argument");
   REQUIRE(n_images >= 1 && n_images <= 64, "vr_composite_images: 1..64 images supported");
   CK(cudaSetDevice(ctx->device));
@@ -1166,7 +1167,7 @@ extern "C" vr_status vr_composite_images(vr_ctx* ctx, const float* rgba, const f
 extern "C" vr_status vr_composite_zbuffer(vr_ctx* ctx, const float* rgba, const float* depth, int n_images,
                                           int width, int height, uint8_t* out_rgba, float* out_depth)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(rgba && depth && out_rgba && out_depth, "vr_composite_zbuffer: NULL argument");
   REQUIRE(n_images >= 1, "vr_composite_zbuffer: no images");
   CK(cudaSetDevice(ctx->device));
@@ -1199,7 +1200,7 @@ extern "C" vr_status vr_zbuffer_composite_dev(vr_ctx* ctx, uint8_t* front_rgba, 
                                               const uint8_t* rgba, const float* depth,
                                               size_t n_pixels)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(front_rgba && front_depth && rgba && depth, "vr_zbuffer_composite_dev: NULL argument");
   CK(cudaSetDevice(ctx->device));
   CK(launch_zbuffer((uchar4*)front_rgba, front_depth, (const uchar4*)rgba, depth, n_pixels, ctx->stream));
@@ -1209,7 +1210,7 @@ extern "C" vr_status vr_zbuffer_composite_dev(vr_ctx* ctx, uint8_t* front_rgba, 
 
 extern "C" vr_status vr_image_to_canvas_dev(vr_ctx* ctx, const uint8_t* rgba, const float* depth)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(ctx->W > 0 && rgba && depth, "vr_image_to_canvas_dev: no canvas or NULL argument");
   CK(cudaSetDevice(ctx->device));
   CK(launch_image_to_canvas((const uchar4*)rgba, depth, (size_t)ctx->W * ctx->H, ctx->canvas_rgba,
@@ -1321,20 +1322,20 @@ static vr_status partials_composite_impl(vr_ctx* ctx, const vr_camera* cam, int 
 
 extern "C" vr_status vr_partials_composite(vr_ctx* ctx)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   return partials_composite_impl(ctx, nullptr, 0);
 }
 
 extern "C" vr_status vr_partials_composite_to_canvas(vr_ctx* ctx, const vr_camera* cam, int canvas_is_clear)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(cam, "vr_partials_composite_to_canvas: camera is NULL");
   return partials_composite_impl(ctx, cam, canvas_is_clear ? 1 : 0);
 }
 
 extern "C" vr_status vr_partials_to_canvas(vr_ctx* ctx, const vr_camera* cam)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(cam, "vr_partials_to_canvas: camera is NULL");
   REQUIRE(ctx->W == ctx->pW && ctx->H == ctx->pH && ctx->W > 0,
           "vr_partials_to_canvas: canvas (%dx%d) and partial frame (%dx%d) differ", ctx->W, ctx->H,
@@ -1355,7 +1356,7 @@ extern "C" vr_status vr_partials_to_canvas(vr_ctx* ctx, const vr_camera* cam)
 extern "C" vr_status vr_composite_partials(vr_ctx* ctx, const vr_partial* in, size_t n_in, int width,
                                            int height, vr_partial* out, size_t* n_out)
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER(ctx);
   REQUIRE(out && n_out && (in || n_in == 0), "vr_composite_partials: NULL argument");
   vr_status st = vr_partials_begin(ctx, width, height);
   if (st != VR_OK) return st;
@@ -1416,7 +1417,7 @@ extern "C" void vr_find_subset(const vr_camera* cam, int width, int height, cons
 extern "C" vr_status vr_synth_braid_dev(vr_ctx* ctx, void* field_dev, int dtype, const int n[3],
                                         const int start[3], const int global[3])
 {
-  if (!ctx) return VR_ERR_INVALID;
+  VR_ENTER_RO(ctx);
   REQUIRE(field_dev && n && start && global, "vr_synth_braid_dev: NULL argument");
   REQUIRE(dtype == VR_F32 || dtype == VR_F64, "vr_synth_braid_dev: bad dtype");
   CK(cudaSetDevice(ctx->device));

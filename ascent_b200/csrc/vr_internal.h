@@ -102,14 +102,26 @@ struct Comm
   unsigned int pepoch = 0;                      // partial path frames
   unsigned int lepoch = 0;                      // layer path frames
   unsigned int sepoch = 0;                      // depth broadcasts
+  // rank 0: "this buffer holds the cleared value outside the rectangle kept in the arena flags",
+  // valid while api_serial has not moved and the frame size is the same
+  struct Clean { bool valid = false; uint64_t serial = 0; int W = 0, H = 0; };
+  Clean clean_res[2], clean_canvas;
   int* minmax_dev = nullptr;                    // {min,max} pixel id of the current list
 };
 
 } // namespace vr
 
+// Entry-point prologues.  VR_ENTER counts the call in ctx->api_serial: rank 0's exchange kernels skip
+// re-clearing the parts of the result image / canvas they left cleared last time, which is only sound
+// if nothing else may have written those buffers since -- any entry point that is not explicitly
+// marked read-only (VR_ENTER_RO: never writes the canvas or the composited image) invalidates that.
+#define VR_ENTER(ctx) do { if (!(ctx)) return VR_ERR_INVALID; ++(ctx)->api_serial; } while (0)
+#define VR_ENTER_RO(ctx) do { if (!(ctx)) return VR_ERR_INVALID; } while (0)
+
 struct vr_ctx
 {
   int device = 0;
+  uint64_t api_serial = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   std::string err;
@@ -333,6 +345,9 @@ struct FoldP2PParams
   float4* canvas_rgba; // rank 0, fused ImageToCanvas (null: off)
   float* canvas_depth;
   int zbuffer;         // 1: select-nearest (opaque surfaces) instead of the ordered blend
+  // rank 0: the result image of this parity / the canvas are known to be cleared outside the
+  // rectangle the previous exchange left in the flags -> only that rectangle needs clearing again
+  int track_res, track_canvas;
 };
 cudaError_t launch_fold_p2p(const FoldP2PParams& p, int sm_count, cudaStream_t s);
 } // namespace vr

@@ -16,11 +16,16 @@ from . import _lib
 
 
 # ----------------------------------------------------------------------------- pure host logic
-def assign_blocks(n_blocks, world_size):
-    """Contiguous block sets, one per rank (ContiguousAssigner-style): rank r owns
-    [r*n/world, (r+1)*n/world)."""
-    return [list(range(r * n_blocks // world_size, (r + 1) * n_blocks // world_size))
-            for r in range(world_size)]
+def assign_blocks(n_blocks, world_size, mode="round_robin"):
+    """Which blocks a rank renders.  Sort-last rendering does not care (Ascent renders whatever
+    domains the simulation left on each rank), load balance does: with blocks numbered x-fastest,
+    "round_robin" (rank r owns r, r + world, ...) gives every rank the same number of blocks near
+    the camera and far from it for any axis-aligned view, where "contiguous" (rank r owns
+    [r*n/world, (r+1)*n/world), DIY's ContiguousAssigner) hands one rank all the front blocks."""
+    if mode == "contiguous":
+        return [list(range(r * n_blocks // world_size, (r + 1) * n_blocks // world_size))
+                for r in range(world_size)]
+    return [list(range(r, n_blocks, world_size)) for r in range(world_size)]
 
 
 def one_domain_per_rank(n_local, dist=None):
@@ -231,6 +236,7 @@ def run_bench(args, wl, bench):
             dist.all_reduce(tp, op=dist.ReduceOp.MAX)
             use_piped = bool(tp[0] < tp[1])
             serial_total_max = float(tp[1])
+            piped_total_max = float(tp[0])
         total_ms, render_ms, tail_ms = piped if use_piped else serial
 
         # composite alone: all local images/partials resident, ranks aligned by a barrier
@@ -300,6 +306,7 @@ def run_bench(args, wl, bench):
                                nvox * 4 * len(mine) / 1e6)},
                 "frames_per_s": 1e3 / ms, "render_ms_per_frame": render_ms,
                 "ms_per_step_serial_order": (serial_total_max / args.steps) if piped is not None else ms,
+                "ms_per_step_pipelined_order": (piped_total_max / args.steps) if piped is not None else None,
                 "composite_ms_per_frame": comp_ms, "composite_in_step_ms": tail_ms,
                 "partials_total": int(tsum[5]),
                 "per_rank_ms": {"columns": ["total", "render_per_frame", "composite_in_step", "composite_aligned"],

@@ -39,6 +39,9 @@ def host_checks(rank, world):
     sc = scene(world)
     owners = D.assign_blocks(len(sc["doms"]), world)
     assert sorted(sum(owners, [])) == list(range(len(sc["doms"])))
+    for mode in ("contiguous", "round_robin"):
+        o = D.assign_blocks(13, world, mode)
+        assert sorted(sum(o, [])) == list(range(13)) and max(map(len, o)) - min(map(len, o)) <= 1
     mine = owners[rank]
     # global scalar range / bounds == the serial values
     lmin = min(float(sc["doms"][i]["field"].min()) for i in mine)
