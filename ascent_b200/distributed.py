@@ -266,6 +266,12 @@ def run_bench(args, wl, bench):
     total_ms, render_ms, tail_ms, comp_ms = [float(x) for x in tmax[:4]]
     ms = total_ms / args.steps
 
+    nccl_base = None
+    if path_a and getattr(args, "nccl_baseline", False):
+        def render_full():
+            ctx.trace_to_image(mine[0], cam, W, H, sp["sample_dist"], rmin, rmax)
+        nccl_base = nccl_image_composite_baseline(ctx, dist, stream, W, H, vis_rank, render_full)
+
     # ---- e2e: every rank publishes its blocks from pinned host memory, root reads the canvas back
     e2e = _e2e(ctx, dist, stream, blocks, mine, fields, sp, cam, W, H, rmin, rmax, render, composite,
                rank, max(3, min(args.steps, 5)))
@@ -314,6 +320,7 @@ def run_bench(args, wl, bench):
                 "nvlink": {"bytes_into_rank0_per_frame": nv_bytes, "pulled": pulled, "pushed_into_rank0": pushed,
                            "achieved_gbs": nv_bytes / (comp_ms * 1e-3) / 1e9, "peak_gbs": 770.0,
                            "peak_source": "measured peer copy per direction (B200_PROFILING.md)"},
+                "nccl_baseline": nccl_base,
                 "e2e": e2e, "gpu_launches": int(tsum[4]), "clocks": clk,
                 "roofline": {"bound": "hbm", "kernel": "trace_kernel (sampler.cu)",
                              "achieved": alg / (render_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
@@ -326,6 +333,80 @@ def run_bench(args, wl, bench):
     dist.barrier()
     ctx.close()
     dist.destroy_process_group()
+
+
+class _DevBuf:
+    """A raw device pointer as something torch.as_tensor can adopt (zero copy)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def nccl_image_composite_baseline(ctx, dist, stream, W, H, vis_rank, render_full, n_iter=10):
+    """What the reference's DirectSendCompositor does (DirectSendCompositor.cpp:121-181), with NCCL as the
+    transport instead of DIY/MPI: every rank cuts its full RGBA8 + depth image into `world` bands and
+    all-to-alls them (ncclSend/ncclRecv groups), folds the `world` bands it received in visibility
+    order -- with the SAME fold kernel the one-GPU path uses (vr_fold_images_dev) -- then the folded
+    bands are gathered on rank 0 and converted to the float canvas (vr_image_to_canvas_dev).  This is
+    the baseline the fused peer-memory kernel (fold_p2p_kernel) is measured against; not a product
+    path.  Returns {"composite_ms": median, "matches_fused": bool | None}."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n = W * H
+    assert n % (4 * world) == 0, "baseline needs W*H divisible by 4*world"
+    band = n // world
+    times = []
+    with torch.cuda.stream(stream):
+        recv_c = torch.empty(n, dtype=torch.int32, device="cuda")
+        recv_d = torch.empty(n, dtype=torch.float32, device="cuda")
+        out_c = torch.empty(band, dtype=torch.int32, device="cuda")
+        out_d = torch.empty(band, dtype=torch.float32, device="cuda")
+        if rank == 0:
+            gath_c = [torch.empty(band, dtype=torch.int32, device="cuda") for _ in range(world)]
+            gath_d = [torch.empty(band, dtype=torch.float32, device="cuda") for _ in range(world)]
+            res_c = torch.empty(n, dtype=torch.int32, device="cuda")
+            res_d = torch.empty(n, dtype=torch.float32, device="cuda")
+        for it in range(n_iter + 2):
+            render_full()                       # Canvas::Clear + trace + Image::Init: a FULL image
+            rgba_ptr, depth_ptr = ctx.image_ptrs()
+            img_c = torch.as_tensor(_DevBuf(rgba_ptr, n, "<i4"), device="cuda")
+            img_d = torch.as_tensor(_DevBuf(depth_ptr, n, "<f4"), device="cuda")
+            torch.cuda.synchronize()
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            dist.all_to_all_single(recv_c, img_c)
+            dist.all_to_all_single(recv_d, img_d)
+            ctx.fold_images_dev(recv_c.data_ptr(), recv_d.data_ptr(), band, vis_rank, band, out_c.data_ptr(),
+                                out_d.data_ptr())
+            dist.gather(out_c, gath_c if rank == 0 else None, dst=0)
+            dist.gather(out_d, gath_d if rank == 0 else None, dst=0)
+            if rank == 0:
+                torch.cat(gath_c, out=res_c)
+                torch.cat(gath_d, out=res_d)
+                ctx.image_to_canvas_dev(res_c.data_ptr(), res_d.data_ptr())
+            b.record(stream)
+            torch.cuda.synchronize()
+            if it >= 2:
+                times.append(a.elapsed_time(b))
+        matches = None
+        if rank == 0:
+            base_rgba, base_depth = ctx.canvas_download(W, H)
+        # the same frame through the fused peer-memory exchange
+        render_full()
+        ctx.comm_composite_images_to_canvas(vis_rank)
+        if rank == 0:
+            fused_rgba, fused_depth = ctx.canvas_download(W, H)
+            matches = bool(np.array_equal(base_rgba, fused_rgba) and np.array_equal(base_depth, fused_depth))
+        else:
+            ctx.synchronize()
+        dist.barrier()
+    t = torch.tensor([float(np.median(times))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"composite_ms": float(t.item()), "matches_fused": matches,
+            "what": "NCCL all_to_all of image bands + local ordered fold (vr_fold_images_dev) + NCCL gather to "
+                    "rank 0 + ImageToCanvas; full images, ranks aligned by a barrier (compare composite_ms_per_frame)"}
 
 
 def _count_local_partials(ctx, render):

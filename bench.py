@@ -435,6 +435,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
     ap.add_argument("--one-block-per-rank", action="store_true",
                     help="N > 1 diagnostics: rank r renders only block r of c3 (path A at any N); not a bench line")
+    ap.add_argument("--nccl-baseline", action="store_true",
+                    help="N > 1, image path: also time the NCCL all_to_all + fold + gather form of the exchange")
     ap.add_argument("--samples", type=int, default=None,
                     help="samples option of the volume plot (default 100; 887 = one sample per voxel on c2)")
     args = ap.parse_args()
