@@ -93,3 +93,21 @@ def test_python_camera_mirror_tracks_oracle_camera():
     mc = cams[1 * 8 + 1].to_struct()
     assert np.allclose(list(mc.position), list(oc.position), rtol=1e-5, atol=1e-4)
     assert np.allclose(list(mc.up), list(oc.up), rtol=1e-5, atol=1e-5)
+
+
+def test_header_is_plain_c_and_library_exports_only_the_abi(tmp_path):
+    """The boundary is a C ABI: include/vr_b200.h must compile as C99 (no C++ or torch types in the
+    signatures) and libvr_b200.so must export nothing but the vr_* entry points it declares."""
+    import subprocess
+    src = tmp_path / "abi_check.c"
+    src.write_text('#include "vr_b200.h"\n'
+                   "int main(void) { vr_camera c; vr_partial p; (void)c; (void)p;\n"
+                   "  return (int)sizeof(vr_partial) == 24 && VR_IPC_HANDLE_BYTES == 64 ? 0 : 1; }\n")
+    exe = tmp_path / "abi_check"
+    r = subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)]).returncode == 0
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l)
+    assert exported == header_symbols(), sorted(set(exported) ^ set(header_symbols()))
