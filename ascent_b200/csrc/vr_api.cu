@@ -703,7 +703,9 @@ extern "C" vr_status vr_trace_to_image(vr_ctx* ctx, int block_id, const vr_camer
     if (st != VR_OK) return st;
   }
   p.write_canvas = (flags & VR_FRAME_WRITE_CANVAS) ? 1 : 0;
-  p.n_clear_chunks = (flags & VR_FRAME_NO_CLEAR) ? 0 : (int)(((size_t)width * height + 511) / 512);
+  // (a width that is not a multiple of 4 has no announced rectangle -- the exchange reads the whole
+  // image -- so such frames are always cleared)
+  p.n_clear_chunks = ((flags & VR_FRAME_NO_CLEAR) && p.vec_ok) ? 0 : (int)(((size_t)width * height + 511) / 512);
   st = stage_for_trace(ctx, block_id, p, ctx->stream, ctx->tile_counter, true);
   if (st != VR_OK) return st;
   CK(launch_trace(p, 2, ctx->sm_count, ctx->stream));
