@@ -900,7 +900,7 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
       return k.valid && k.serial == ctx->api_serial && k.W == ctx->W && k.H == ctx->H;
     };
     p.track_res = still(c.clean_res[b]) ? 1 : 0;
-    p.track_canvas = (p.canvas_rgba && still(c.clean_canvas)) ? 1 : 0;
+    p.track_canvas = (p.canvas_rgba && !ctx->canvas_exposed && still(c.clean_canvas)) ? 1 : 0;
   }
   cudaError_t e = launch_fold_p2p(p, ctx->sm_count, ctx->stream);
   if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "fold_p2p launch", e);

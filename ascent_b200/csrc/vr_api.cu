@@ -542,6 +542,7 @@ extern "C" vr_status vr_canvas_ptrs(vr_ctx* ctx, void** rgba_dev, void** depth_d
 {
   VR_ENTER(ctx);
   REQUIRE(ctx->W > 0, "vr_canvas_ptrs: no canvas yet");
+  ctx->canvas_exposed = true; // the caller may write through these at any time: no more clean-rectangle shortcuts
   if (rgba_dev) *rgba_dev = ctx->canvas_rgba;
   if (depth_dev) *depth_dev = ctx->canvas_depth;
   return VR_OK;

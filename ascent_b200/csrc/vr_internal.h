@@ -122,6 +122,7 @@ struct vr_ctx
 {
   int device = 0;
   uint64_t api_serial = 0;
+  bool canvas_exposed = false; // vr_canvas_ptrs handed the canvas out: its contents are never assumed
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   std::string err;
