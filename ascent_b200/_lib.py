@@ -34,6 +34,8 @@ SYMBOLS = [
     "vr_image_result_to_canvas", "vr_comm_composite_partials", "vr_comm_composite_partials_to_canvas",
     "vr_image_ptrs",
     "vr_sample_distance", "vr_visibility_order", "vr_find_subset", "vr_synth_braid_dev",
+    "vr_camera_default", "vr_camera_reset_to_bounds", "vr_camera_azimuth", "vr_camera_elevation",
+    "vr_camera_zoom", "vr_camera_cinema", "vr_color_table_sample", "vr_correct_opacity",
 ]
 
 
@@ -129,6 +131,14 @@ def load():
         "vr_visibility_order": (None, [dp, C.c_int, cam, ip]),
         "vr_find_subset": (None, [cam, C.c_int, C.c_int, dp, ip]),
         "vr_synth_braid_dev": (C.c_int, [vp, vp, C.c_int, ip, ip, ip]),
+        "vr_camera_default": (None, [cam]),
+        "vr_camera_reset_to_bounds": (None, [cam, dp]),
+        "vr_camera_azimuth": (None, [cam, C.c_float]),
+        "vr_camera_elevation": (None, [cam, C.c_float]),
+        "vr_camera_zoom": (None, [cam, C.c_float]),
+        "vr_camera_cinema": (None, [cam, dp, C.c_float, C.c_float]),
+        "vr_color_table_sample": (C.c_int, [C.c_int, C.c_int, dp, fp, C.c_int, dp, fp, C.c_int, vp, fp]),
+        "vr_correct_opacity": (C.c_float, [C.c_float, C.c_float]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

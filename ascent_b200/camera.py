@@ -3,6 +3,7 @@
 src/libs/vtkh/rendering/Render.cpp:314-347, cinema orbit
 ascent_runtime_rendering_filters.cpp:906-960).  All state is float32 like VTK-m's.  The tracer
 consumes the plain ``vr_camera`` struct (``to_struct``)."""
+import ctypes as C
 import math
 
 import numpy as np
@@ -10,7 +11,6 @@ import numpy as np
 from . import _lib
 
 F = np.float32
-_PI_180 = F(0.01745329251994329547437168059786927)
 
 
 def _v(x):
@@ -22,85 +22,62 @@ def _normalize(v):
     return (v * r).astype(np.float32)
 
 
-def _cross(a, b):
-    a64, b64 = a.astype(np.float64), b.astype(np.float64)
-    return np.cross(a64, b64).astype(np.float32)
-
-
-def _rotate(deg, axis):
-    a = _PI_180 * F(deg)
-    n = _normalize(_v(axis))
-    s, c = F(math.sin(a)), F(math.cos(a))
-    m = np.eye(4, dtype=np.float32)
-    for i in range(3):
-        for j in range(3):
-            m[i, j] = n[i] * n[j] * (F(1) - c)
-    m[0, 0] += c; m[1, 1] += c; m[2, 2] += c
-    m[0, 1] -= n[2] * s; m[0, 2] += n[1] * s
-    m[1, 0] += n[2] * s; m[1, 2] -= n[0] * s
-    m[2, 0] -= n[1] * s; m[2, 1] += n[0] * s
-    return m
-
-
-def _translate(t):
-    m = np.eye(4, dtype=np.float32)
-    m[:3, 3] = t
-    return m
-
-
 class Camera:
+    """State = one ``vr_camera`` struct; every operation is the library's host helper
+    (csrc/vr_host_math.hpp), so Python and C++ callers get the same bits."""
+
     def __init__(self):
-        self.look_at = _v([0, 0, 0])
-        self.position = _v([0, 0, 1])
-        self.up = _v([0, 1, 0])
-        self.fov = F(60)
-        self.zoom = F(1)
-        self.xpan = F(0)
-        self.ypan = F(0)
-        self.near_plane = F(0.01)
-        self.far_plane = F(1000)
+        self.c = _lib.CameraStruct()
+        _lib.load().vr_camera_default(C.byref(self.c))
+
+    # -- vector-valued fields as float32 numpy views of the struct
+    def _get(self, name):
+        return np.array(list(getattr(self.c, name)), np.float32)
+
+    def _set(self, name, v):
+        getattr(self.c, name)[:] = [float(F(x)) for x in v]
+
+    look_at = property(lambda self: self._get("look_at"), lambda self, v: self._set("look_at", v))
+    position = property(lambda self: self._get("position"), lambda self, v: self._set("position", v))
+    up = property(lambda self: self._get("up"), lambda self, v: self._set("up", v))
+
+    def _scalar(name):
+        return property(lambda self: F(getattr(self.c, name)), lambda self, v: setattr(self.c, name, float(F(v))))
+
+    fov = _scalar("fov")
+    zoom = _scalar("zoom")
+    xpan = _scalar("xpan")
+    ypan = _scalar("ypan")
+    near_plane = _scalar("near_plane")
+    far_plane = _scalar("far_plane")
+    del _scalar
 
     # -- setters named after the vtkm methods parse_camera calls
-    def set_look_at(self, v): self.look_at = _v(v)
-    def set_position(self, v): self.position = _v(v)
-    def set_view_up(self, v): self.up = _v(v)
-    def set_field_of_view(self, deg): self.fov = F(deg)
+    def set_look_at(self, v): self.look_at = v
+    def set_position(self, v): self.position = v
+    def set_view_up(self, v): self.up = v
+    def set_field_of_view(self, deg): self.fov = deg
 
     def set_clipping_range(self, near, far):
-        self.near_plane, self.far_plane = F(near), F(far)
+        self.near_plane, self.far_plane = near, far
 
     def reset_to_bounds(self, bounds):
         """``Camera::ResetToBounds(bounds)``: look at the centre from |extent| away along the
         current view direction, fov 60, clip [0.1, 10] x diagonal, pan 0, zoom 1."""
-        b = np.asarray(bounds, np.float64)
-        d = _normalize(self.position - self.look_at)
-        center = _v([(b[0] + b[1]) / 2, (b[2] + b[3]) / 2, (b[4] + b[5]) / 2])
-        ext = _v([b[1] - b[0], b[3] - b[2], b[5] - b[4]])
-        diag = F(np.sqrt(F(ext[0] * ext[0] + ext[1] * ext[1] + ext[2] * ext[2])))
-        self.look_at = center
-        self.position = (center + d * diag * F(1.0)).astype(np.float32)
-        self.fov = F(60)
-        self.near_plane, self.far_plane = F(0.1) * diag, diag * F(10)
-        self.xpan = self.ypan = F(0)
-        self.zoom = F(1)
+        _lib.load().vr_camera_reset_to_bounds(C.byref(self.c), _lib._d6(bounds))
         return self
 
-    def _rotate_about_look_at(self, deg, axis):
-        m = _translate(self.look_at) @ _rotate(deg, axis) @ _translate(-self.look_at)
-        p = m @ np.append(self.position, F(1)).astype(np.float32)
-        self.position = p[:3].astype(np.float32)
-
     def azimuth(self, deg):
-        self._rotate_about_look_at(deg, self.up)
+        _lib.load().vr_camera_azimuth(C.byref(self.c), C.c_float(deg))
         return self
 
     def elevation(self, deg):
-        self._rotate_about_look_at(deg, _cross(self.position - self.look_at, self.up))
+        _lib.load().vr_camera_elevation(C.byref(self.c), C.c_float(deg))
         return self
 
     def zoom_by(self, z):
         """``Camera::Zoom(z)``: zoom *= 4^z."""
-        self.zoom = F(self.zoom * F(math.pow(4.0, z)))
+        _lib.load().vr_camera_zoom(C.byref(self.c), C.c_float(z))
         return self
 
     def apply_ascent_zoom(self, user_zoom):
@@ -112,13 +89,9 @@ class Camera:
         return self
 
     def to_struct(self):
-        c = _lib.CameraStruct()
-        c.position[:] = [float(x) for x in self.position]
-        c.look_at[:] = [float(x) for x in self.look_at]
-        c.up[:] = [float(x) for x in self.up]
-        c.fov, c.zoom, c.xpan, c.ypan = float(self.fov), float(self.zoom), float(self.xpan), float(self.ypan)
-        c.near_plane, c.far_plane = float(self.near_plane), float(self.far_plane)
-        return c
+        out = _lib.CameraStruct()
+        C.memmove(C.byref(out), C.byref(self.c), C.sizeof(_lib.CameraStruct))
+        return out
 
 
 def parse_camera(node, camera):
@@ -143,20 +116,11 @@ def parse_camera(node, camera):
 def cinema_cameras(bounds, phi_values, theta_values):
     """``CinemaManager::create_cinema_cameras`` (rendering_filters.cpp:906-960) for the
     phi x theta grid of ``create_cinema_angles`` (:882-893)."""
-    b = np.asarray(bounds, np.float64)
-    center = _v([(b[0] + b[1]) / 2, (b[2] + b[3]) / 2, (b[4] + b[5]) / 2])
-    ext = _v([b[1] - b[0], b[3] - b[2], b[5] - b[4]])
-    radius = F(F(np.sqrt(F(ext[0] * ext[0] + ext[1] * ext[1] + ext[2] * ext[2]))) * 2.5 / 2.0)
     cams = []
     for phi in phi_values:
         for theta in theta_values:
-            cam = Camera().reset_to_bounds(b)
-            rot = _rotate(F(phi), [0, 0, 1]) @ _rotate(F(theta), [1, 0, 0])
-            up = _normalize((rot[:3, :3] @ _v([0, 1, 0])).astype(np.float32))
-            pos = (rot @ _v([0, 0, 1, 1]))[:3]
-            cam.up = up
-            cam.look_at = center
-            cam.position = (pos * radius + center).astype(np.float32)
+            cam = Camera()
+            _lib.load().vr_camera_cinema(C.byref(cam.c), _lib._d6(bounds), C.c_float(phi), C.c_float(theta))
             cams.append(cam)
     return cams
 

@@ -43,156 +43,34 @@ private:
 };
 
 // ------------------------------------------------------------------------------------------ camera
-namespace
-{
-const float kPi180 = (float)0.01745329251994329547437168059786927;
-
-void normalize3(float v[3])
-{
-  const float r = 1.0f / std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-  v[0] *= r; v[1] *= r; v[2] *= r;
-}
-// Rodrigues rotation matrix (3x3, row major) about a unit axis
-void rotation(float deg, const float axis_in[3], float m[9])
-{
-  float n[3] = { axis_in[0], axis_in[1], axis_in[2] };
-  normalize3(n);
-  const float a = kPi180 * deg;
-  const float s = std::sin(a), c = std::cos(a), t = 1.0f - c;
-  m[0] = n[0] * n[0] * t + c;        m[1] = n[0] * n[1] * t - n[2] * s; m[2] = n[0] * n[2] * t + n[1] * s;
-  m[3] = n[1] * n[0] * t + n[2] * s; m[4] = n[1] * n[1] * t + c;        m[5] = n[1] * n[2] * t - n[0] * s;
-  m[6] = n[2] * n[0] * t - n[1] * s; m[7] = n[2] * n[1] * t + n[0] * s; m[8] = n[2] * n[2] * t + c;
-}
-} // namespace
-
-Camera::Camera()
-{
-  // vtkm::rendering::Camera defaults: look_at 0, position (0,0,1), up +y, fov 60
-  std::memset(&m_c, 0, sizeof(m_c));
-  m_c.position[2] = 1.f;
-  m_c.up[1] = 1.f;
-  m_c.fov = 60.f;
-  m_c.zoom = 1.f;
-  m_c.near_plane = 0.01f;
-  m_c.far_plane = 1000.f;
-}
+// State is the plain vr_camera; the arithmetic is the library's (vr_camera_*: the same Float32
+// operation order as vtkm::rendering::Camera, shared with the Python harness).
+Camera::Camera() { vr_camera_default(&m_c); }
 void Camera::SetLookAt(const float v[3]) { std::memcpy(m_c.look_at, v, 12); }
 void Camera::SetPosition(const float v[3]) { std::memcpy(m_c.position, v, 12); }
 void Camera::SetViewUp(const float v[3]) { std::memcpy(m_c.up, v, 12); }
-
 void Camera::ResetToBounds(const Bounds& b)
 {
-  // look at the centre from one diagonal away along the current view direction
-  float d[3] = { m_c.position[0] - m_c.look_at[0], m_c.position[1] - m_c.look_at[1], m_c.position[2] - m_c.look_at[2] };
-  normalize3(d);
-  const float center[3] = { (float)b.X.Center(), (float)b.Y.Center(), (float)b.Z.Center() };
-  const float ext[3] = { (float)b.X.Length(), (float)b.Y.Length(), (float)b.Z.Length() };
-  const float diag = std::sqrt(ext[0] * ext[0] + ext[1] * ext[1] + ext[2] * ext[2]);
-  for (int k = 0; k < 3; ++k)
-  {
-    m_c.look_at[k] = center[k];
-    m_c.position[k] = center[k] + d[k] * diag;
-  }
-  m_c.fov = 60.f;
-  m_c.near_plane = 0.1f * diag;
-  m_c.far_plane = diag * 10.f;
-  m_c.xpan = m_c.ypan = 0.f;
-  m_c.zoom = 1.f;
+  double a[6];
+  b.ToArray(a);
+  vr_camera_reset_to_bounds(&m_c, a);
 }
-void Camera::RotateAboutLookAt(float deg, const float axis[3])
-{
-  float m[9];
-  rotation(deg, axis, m);
-  const float p[3] = { m_c.position[0] - m_c.look_at[0], m_c.position[1] - m_c.look_at[1], m_c.position[2] - m_c.look_at[2] };
-  for (int r = 0; r < 3; ++r)
-    m_c.position[r] = m[3 * r] * p[0] + m[3 * r + 1] * p[1] + m[3 * r + 2] * p[2] + m_c.look_at[r];
-}
-void Camera::Azimuth(float deg) { RotateAboutLookAt(deg, m_c.up); }
-void Camera::Elevation(float deg)
-{
-  const double p[3] = { (double)m_c.position[0] - m_c.look_at[0], (double)m_c.position[1] - m_c.look_at[1],
-                        (double)m_c.position[2] - m_c.look_at[2] };
-  const double u[3] = { m_c.up[0], m_c.up[1], m_c.up[2] };
-  const float axis[3] = { (float)(p[1] * u[2] - p[2] * u[1]), (float)(p[2] * u[0] - p[0] * u[2]),
-                          (float)(p[0] * u[1] - p[1] * u[0]) };
-  RotateAboutLookAt(deg, axis);
-}
-void Camera::Zoom(float z) { m_c.zoom = m_c.zoom * (float)std::pow(4.0, (double)z); }
+void Camera::Azimuth(float deg) { vr_camera_azimuth(&m_c, deg); }
+void Camera::Elevation(float deg) { vr_camera_elevation(&m_c, deg); }
+void Camera::Zoom(float z) { vr_camera_zoom(&m_c, z); }
 void Camera::Pan(float dx, float dy) { m_c.xpan += dx; m_c.ypan += dy; }
+Camera Camera::Cinema(const Bounds& b, float phi, float theta)
+{
+  Camera c;
+  double a[6];
+  b.ToArray(a);
+  vr_camera_cinema(&c.m_c, a, phi, theta);
+  return c;
+}
 
 // ------------------------------------------------------------------------------------------ colour table
 namespace
 {
-const double kRefX = 0.9505, kRefY = 1.000, kRefZ = 1.089, kPi = 3.14159265358979323846;
-
-void rgb_to_lab(const double rgb[3], double lab[3])
-{
-  double c[3];
-  for (int k = 0; k < 3; ++k) c[k] = rgb[k] > 0.04045 ? std::pow((rgb[k] + 0.055) / 1.055, 2.4) : rgb[k] / 12.92;
-  const double x = c[0] * 0.4124 + c[1] * 0.3576 + c[2] * 0.1805;
-  const double y = c[0] * 0.2126 + c[1] * 0.7152 + c[2] * 0.0722;
-  const double z = c[0] * 0.0193 + c[1] * 0.1192 + c[2] * 0.9505;
-  auto f = [](double t) { return t > 0.008856 ? std::cbrt(t) : 7.787 * t + 16.0 / 116.0; };
-  const double fx = f(x / kRefX), fy = f(y / kRefY), fz = f(z / kRefZ);
-  lab[0] = 116.0 * fy - 16.0; lab[1] = 500.0 * (fx - fy); lab[2] = 200.0 * (fy - fz);
-}
-void lab_to_rgb(const double lab[3], double rgb[3])
-{
-  const double vy = (lab[0] + 16.0) / 116.0, vx = lab[1] / 500.0 + vy, vz = vy - lab[2] / 200.0;
-  auto finv = [](double v) { const double v3 = v * v * v; return v3 > 0.008856 ? v3 : (v - 16.0 / 116.0) / 7.787; };
-  const double x = kRefX * finv(vx), y = kRefY * finv(vy), z = kRefZ * finv(vz);
-  double c[3] = { x * 3.2406 + y * -1.5372 + z * -0.4986, x * -0.9689 + y * 1.8758 + z * 0.0415,
-                  x * 0.0557 + y * -0.2040 + z * 1.0570 };
-  double m = 0.0;
-  for (int k = 0; k < 3; ++k)
-  {
-    c[k] = c[k] > 0.0031308 ? 1.055 * std::pow(c[k], 1.0 / 2.4) - 0.055 : 12.92 * c[k];
-    m = std::max(m, c[k]);
-  }
-  for (int k = 0; k < 3; ++k) rgb[k] = std::max((m > 1.0 ? c[k] / m : c[k]), 0.0);
-}
-void lab_to_msh(const double lab[3], double msh[3])
-{
-  msh[0] = std::sqrt(lab[0] * lab[0] + lab[1] * lab[1] + lab[2] * lab[2]);
-  msh[1] = msh[0] > 0.001 ? std::acos(lab[0] / msh[0]) : 0.0;
-  msh[2] = msh[1] > 0.001 ? std::atan2(lab[2], lab[1]) : 0.0;
-}
-void msh_to_lab(const double msh[3], double lab[3])
-{
-  lab[0] = msh[0] * std::cos(msh[1]);
-  lab[1] = msh[0] * std::sin(msh[1]) * std::cos(msh[2]);
-  lab[2] = msh[0] * std::sin(msh[1]) * std::sin(msh[2]);
-}
-double angle_diff(double a1, double a2)
-{
-  double d = std::fabs(a1 - a2);
-  while (d >= 2.0 * kPi) d -= 2.0 * kPi;
-  return d > kPi ? 2.0 * kPi - d : d;
-}
-double adjust_hue(const double msh[3], double unsat_m)
-{
-  if (msh[0] >= unsat_m - 0.1) return msh[2];
-  const double spin = msh[1] * std::sqrt(unsat_m * unsat_m - msh[0] * msh[0]) / (msh[0] * std::sin(msh[1]));
-  return msh[2] > -0.3 * kPi ? msh[2] + spin : msh[2] - spin;
-}
-void interp_diverging(const double rgb1[3], const double rgb2[3], double w, double out[3])
-{
-  double lab[3], msh1[3], msh2[3];
-  rgb_to_lab(rgb1, lab); lab_to_msh(lab, msh1);
-  rgb_to_lab(rgb2, lab); lab_to_msh(lab, msh2);
-  if (msh1[1] > 0.05 && msh2[1] > 0.05 && angle_diff(msh1[2], msh2[2]) > 0.33 * kPi)
-  {
-    const double mmid = std::max(88.0, std::max(msh1[0], msh2[0]));
-    if (w < 0.5) { msh2[0] = mmid; msh2[1] = 0.0; msh2[2] = 0.0; w = 2.0 * w; }
-    else { msh1[0] = mmid; msh1[1] = 0.0; msh1[2] = 0.0; w = 2.0 * w - 1.0; }
-  }
-  if (msh1[1] < 0.05 && msh2[1] > 0.05) msh1[2] = adjust_hue(msh2, msh1[0]);
-  else if (msh2[1] < 0.05 && msh1[1] > 0.05) msh2[2] = adjust_hue(msh1, msh2[0]);
-  double tmp[3];
-  for (int k = 0; k < 3; ++k) tmp[k] = (1.0 - w) * msh1[k] + w * msh2[k];
-  msh_to_lab(tmp, lab);
-  lab_to_rgb(lab, out);
-}
 std::string lower(std::string s)
 {
   for (char& c : s) c = (char)std::tolower((unsigned char)c);
@@ -203,17 +81,26 @@ std::string lower(std::string s)
 ColorTable::ColorTable(const std::string& name)
 {
   const std::string key = lower(name);
-  m_alpha = { { 0.0, { 1.0, 0, 0 } }, { 1.0, { 1.0, 0, 0 } } };
+  m_alpha = { { 0.0, { 1.0f, 0, 0 } }, { 1.0, { 1.0f, 0, 0 } } };
+  auto f = [](double v) { return (float)v; };
   if (key == "cool to warm")
   {
     m_space = 2;
-    m_rgb = { { 0.0, { 0.23137254902, 0.298039215686, 0.752941176471 } }, { 0.5, { 0.865, 0.865, 0.865 } },
-              { 1.0, { 0.705882352941, 0.0156862745098, 0.149019607843 } } };
+    m_rgb = { { 0.0, { f(0.23137254902), f(0.298039215686), f(0.752941176471) } }, { 0.5, { f(0.865), f(0.865), f(0.865) } },
+              { 1.0, { f(0.705882352941), f(0.0156862745098), f(0.149019607843) } } };
+  }
+  else if (key == "rainbow desaturated")
+  {
+    m_space = 0;
+    m_rgb = { { 0.0, { f(0.278431372549), f(0.278431372549), f(0.858823529412) } }, { 0.143, { 0, 0, f(0.360784313725) } },
+              { 0.285, { 0, 1, 1 } }, { 0.429, { 0, f(0.501960784314), 0 } }, { 0.571, { 1, 1, 0 } },
+              { 0.714, { 1, f(0.380392156863), 0 } }, { 0.857, { f(0.419607843137), 0, 0 } },
+              { 1.0, { f(0.878431372549), f(0.301960784314), f(0.301960784314) } } };
   }
   else if (key == "black-body radiation")
   {
     m_space = 0;
-    m_rgb = { { 0.0, { 0, 0, 0 } }, { 0.4, { 0.9, 0, 0 } }, { 0.8, { 0.9, 0.9, 0 } }, { 1.0, { 1, 1, 1 } } };
+    m_rgb = { { 0.0, { 0, 0, 0 } }, { 0.4, { f(0.9), 0, 0 } }, { 0.8, { f(0.9), f(0.9), 0 } }, { 1.0, { 1, 1, 1 } } };
   }
   else if (key == "grayscale")
   {
@@ -233,72 +120,28 @@ void ColorTable::Insert(std::vector<Node>& pts, const Node& n)
 void ColorTable::AddPoint(double x, const float rgb[3])
 {
   Node n{ x, { 0, 0, 0 } };
-  for (int k = 0; k < 3; ++k) n.v[k] = std::min(1.0, std::max(0.0, (double)rgb[k]));
+  for (int k = 0; k < 3; ++k) n.v[k] = std::min(1.0f, std::max(0.0f, rgb[k]));
   Insert(m_rgb, n);
 }
 void ColorTable::AddPointAlpha(double x, float alpha)
 {
-  Insert(m_alpha, Node{ x, { std::min(1.0, std::max(0.0, (double)alpha)), 0, 0 } });
+  Insert(m_alpha, Node{ x, { std::min(1.0f, std::max(0.0f, alpha)), 0, 0 } });
 }
 void ColorTable::ReverseColors()
 {
   for (Node& n : m_rgb) n.x = 1.0 - n.x;
   std::stable_sort(m_rgb.begin(), m_rgb.end(), [](const Node& a, const Node& b) { return a.x < b.x; });
 }
-void ColorTable::ColorAt(double x, double out[3]) const
-{
-  out[0] = out[1] = out[2] = 0.0;
-  if (m_rgb.empty()) return;
-  const Node* hit = nullptr;
-  if (x <= m_rgb.front().x) hit = &m_rgb.front();
-  else if (x >= m_rgb.back().x) hit = &m_rgb.back();
-  if (hit) { std::memcpy(out, hit->v, sizeof(hit->v)); return; }
-  for (size_t i = 0; i + 1 < m_rgb.size(); ++i)
-  {
-    const Node &a = m_rgb[i], &b = m_rgb[i + 1];
-    if (x < a.x || x > b.x) continue;
-    if (x == a.x) { std::memcpy(out, a.v, sizeof(a.v)); return; }
-    if (x == b.x) { std::memcpy(out, b.v, sizeof(b.v)); return; }
-    const double w = (double)(float)((x - a.x) / (b.x - a.x));
-    if (m_space == 2) interp_diverging(a.v, b.v, w, out);
-    else if (m_space == 1)
-    {
-      double l1[3], l2[3], l[3];
-      rgb_to_lab(a.v, l1); rgb_to_lab(b.v, l2);
-      for (int k = 0; k < 3; ++k) l[k] = (1.0 - w) * l1[k] + w * l2[k];
-      lab_to_rgb(l, out);
-    }
-    else
-      for (int k = 0; k < 3; ++k) out[k] = (1.0 - w) * a.v[k] + w * b.v[k];
-    return;
-  }
-}
-double ColorTable::AlphaAt(double x) const
-{
-  if (m_alpha.empty()) return 1.0;
-  if (x <= m_alpha.front().x) return m_alpha.front().v[0];
-  if (x >= m_alpha.back().x) return m_alpha.back().v[0];
-  for (size_t i = 0; i + 1 < m_alpha.size(); ++i)
-  {
-    const Node &a = m_alpha[i], &b = m_alpha[i + 1];
-    if (x < a.x || x > b.x) continue;
-    const double w = (x - a.x) / (b.x - a.x);
-    return (1.0 - w) * a.v[0] + w * b.v[0];
-  }
-  return m_alpha.back().v[0];
-}
 void ColorTable::Sample(int n, std::vector<uint8_t>& rgba8) const
 {
+  std::vector<double> cx, ax;
+  std::vector<float> cc, av;
+  for (const Node& p : m_rgb) { cx.push_back(p.x); cc.insert(cc.end(), p.v, p.v + 3); }
+  for (const Node& p : m_alpha) { ax.push_back(p.x); av.push_back(p.v[0]); }
   rgba8.assign((size_t)n * 4, 0);
-  const float delta = 1.0f / (float)(n - 1);
-  for (int i = 0; i < n; ++i)
-  {
-    const double x = (i == n - 1) ? 1.0 : (double)(0.0f + delta * (float)i);
-    double c[4];
-    ColorAt(x, c);
-    c[3] = AlphaAt(x);
-    for (int k = 0; k < 4; ++k) rgba8[(size_t)i * 4 + k] = (uint8_t)(int)((float)c[k] * 255.0f + 0.5f);
-  }
+  if (vr_color_table_sample(m_space, (int)cx.size(), cx.data(), cc.data(), (int)ax.size(), ax.data(), av.data(), n,
+                            rgba8.data(), nullptr) != VR_OK)
+    throw Error("ColorTable::Sample: invalid table");
 }
 
 // ------------------------------------------------------------------------------------------ data set
@@ -498,14 +341,13 @@ void VolumeRenderer::SetInput(DataSet* input)
 void VolumeRenderer::CorrectOpacity()
 {
   // alpha' = 1 - (1 - alpha)^(10/samples) on every alpha control point (VolumeRenderer.cpp:448-466)
-  const float correction_scalar = 10.f;
-  const float ratio = correction_scalar / (float)m_num_samples;
+  const float samples = (float)m_num_samples;
   m_corrected_color_table = m_color_table;
   for (int i = 0; i < m_corrected_color_table.GetNumberOfPointsAlpha(); ++i)
   {
     double x, a;
     m_corrected_color_table.GetPointAlpha(i, x, a);
-    m_corrected_color_table.UpdatePointAlpha(i, x, 1.0 - std::pow(1.0 - a, (double)ratio));
+    m_corrected_color_table.UpdatePointAlpha(i, x, vr_correct_opacity((float)a, samples));
   }
 }
 void VolumeRenderer::UploadInput()

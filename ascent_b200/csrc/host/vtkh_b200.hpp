@@ -80,8 +80,9 @@ public:
   void Zoom(float z);           // zoom *= 4^z
   void Pan(float dx, float dy);
   const vr_camera& ToVR() const { return m_c; }
+  // one camera of the cinema orbit (CinemaManager::create_cinema_cameras, rendering_filters.cpp:906-960)
+  static Camera Cinema(const Bounds& b, float phi_degrees, float theta_degrees);
 private:
-  void RotateAboutLookAt(float deg, const float axis[3]);
   vr_camera m_c;
 };
 
@@ -97,13 +98,11 @@ public:
   void ReverseColors();
   int GetNumberOfPointsAlpha() const { return (int)m_alpha.size(); }
   void GetPointAlpha(int i, double& x, double& a) const { x = m_alpha[i].x; a = m_alpha[i].v[0]; }
-  void UpdatePointAlpha(int i, double x, double a) { m_alpha[i].x = x; m_alpha[i].v[0] = a; }
+  void UpdatePointAlpha(int i, double x, double a) { m_alpha[i].x = x; m_alpha[i].v[0] = (float)a; }
   void Sample(int n, std::vector<uint8_t>& rgba8) const; // ColorTable::Sample(n, Vec4ui_8)
 private:
-  struct Node { double x; double v[3]; };
+  struct Node { double x; float v[3]; }; // positions Float64, values Float32 (as VTK-m stores them)
   static void Insert(std::vector<Node>& pts, const Node& n);
-  void ColorAt(double x, double out[3]) const;
-  double AlphaAt(double x) const;
   int m_space; // 0 rgb, 1 lab, 2 diverging
   std::vector<Node> m_rgb, m_alpha;
 };

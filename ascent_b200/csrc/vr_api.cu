@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "vr_color_table.hpp"
 #include "vr_host_math.hpp"
 #include "vr_internal.h"
 
@@ -1415,6 +1416,56 @@ extern "C" void vr_find_subset(const vr_camera* cam, int width, int height, cons
                                int out[4])
 {
   hm::find_subset(*cam, width, height, bounds, out);
+}
+
+extern "C" void vr_camera_default(vr_camera* cam) { if (cam) hm::camera_default(*cam); }
+extern "C" void vr_camera_reset_to_bounds(vr_camera* cam, const double bounds[6])
+{
+  if (cam && bounds) hm::camera_reset_to_bounds(*cam, bounds);
+}
+extern "C" void vr_camera_azimuth(vr_camera* cam, float degrees) { if (cam) hm::camera_azimuth(*cam, degrees); }
+extern "C" void vr_camera_elevation(vr_camera* cam, float degrees) { if (cam) hm::camera_elevation(*cam, degrees); }
+extern "C" void vr_camera_zoom(vr_camera* cam, float zoom) { if (cam) hm::camera_zoom(*cam, zoom); }
+extern "C" void vr_camera_cinema(vr_camera* cam, const double bounds[6], float phi_degrees, float theta_degrees)
+{
+  if (cam && bounds) hm::camera_cinema(*cam, bounds, phi_degrees, theta_degrees);
+}
+
+extern "C" vr_status vr_color_table_sample(int color_space, int n_color, const double* color_x,
+                                           const float* color_rgb, int n_alpha, const double* alpha_x,
+                                           const float* alpha, int n_samples, uint8_t* rgba8_out, float* rgba_out)
+{
+  if (color_space < 0 || color_space > 2 || n_samples < 2 || n_color < 0 || n_alpha < 0) return VR_ERR_INVALID;
+  if ((n_color && (!color_x || !color_rgb)) || (n_alpha && (!alpha_x || !alpha))) return VR_ERR_INVALID;
+  ct::Table t;
+  t.space = color_space;
+  for (int i = 0; i < n_color; ++i)
+  {
+    if (i && !(color_x[i] > color_x[i - 1])) return VR_ERR_INVALID;
+    t.color_x.push_back(color_x[i]);
+    t.color.push_back(ct::Rgb{ { color_rgb[3 * i], color_rgb[3 * i + 1], color_rgb[3 * i + 2] } });
+  }
+  for (int i = 0; i < n_alpha; ++i)
+  {
+    if (i && !(alpha_x[i] > alpha_x[i - 1])) return VR_ERR_INVALID;
+    t.alpha_x.push_back(alpha_x[i]);
+    t.alpha.push_back(alpha[i]);
+  }
+  std::vector<uint8_t> u8((size_t)n_samples * 4);
+  ct::sample_u8(t, n_samples, u8.data());
+  if (rgba8_out) std::memcpy(rgba8_out, u8.data(), u8.size());
+  if (rgba_out)
+  {
+    const float k = 1.0f / 255.0f; // convert_table's conversionToFloatSpace
+    for (size_t i = 0; i < u8.size(); ++i) rgba_out[i] = (float)u8[i] * k;
+  }
+  return VR_OK;
+}
+
+extern "C" float vr_correct_opacity(float alpha, float samples)
+{
+  const float ratio = 10.f / samples; // VTKH_OPACITY_CORRECTION / samples (VolumeRenderer.cpp:25,453)
+  return (float)(1. - std::pow(1. - (double)alpha, (double)ratio));
 }
 
 extern "C" vr_status vr_synth_braid_dev(vr_ctx* ctx, void* field_dev, int dtype, const int n[3],

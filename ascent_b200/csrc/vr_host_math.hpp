@@ -157,6 +157,86 @@ inline Mat4 projview(const vr_camera& c, int w, int h)
   return mul(projection_matrix(c, w, h), view_matrix(c));
 }
 
+// ---------------------------------------------------------------------------------------------
+// vtkm::rendering::Camera (3-D mode) as Ascent's render parsing drives it
+// (ascent_runtime_conduit_to_vtkm_parsing.cpp:97-173, Render.cpp:314-347): ResetToBounds, Azimuth,
+// Elevation, Zoom, and the cinema orbit of ascent_runtime_rendering_filters.cpp:906-960.
+inline Mat4 translation(float x, float y, float z)
+{
+  Mat4 m = identity();
+  m(0, 3) = x; m(1, 3) = y; m(2, 3) = z;
+  return m;
+}
+// Transform3DRotate(angleDegrees, axis): Rodrigues matrix about the normalised axis
+inline Mat4 rotation(float deg, const Vec3& axis)
+{
+  const float ang = kPi180 * deg;
+  const Vec3 n = normal(axis);
+  const float s = std::sin(ang), c = std::cos(ang), ic = 1 - c;
+  Mat4 m = identity();
+  m(0, 0) = n[0] * n[0] * ic + c;        m(0, 1) = n[0] * n[1] * ic - n[2] * s; m(0, 2) = n[0] * n[2] * ic + n[1] * s;
+  m(1, 0) = n[1] * n[0] * ic + n[2] * s; m(1, 1) = n[1] * n[1] * ic + c;        m(1, 2) = n[1] * n[2] * ic - n[0] * s;
+  m(2, 0) = n[2] * n[0] * ic - n[1] * s; m(2, 1) = n[2] * n[1] * ic + n[0] * s; m(2, 2) = n[2] * n[2] * ic + c;
+  return m;
+}
+inline void camera_default(vr_camera& c)
+{
+  const vr_camera d = { { 0.f, 0.f, 1.f }, { 0.f, 0.f, 0.f }, { 0.f, 1.f, 0.f }, 60.f, 1.f, 0.f, 0.f, 0.01f, 1000.f };
+  c = d;
+}
+inline void camera_reset_to_bounds(vr_camera& c, const double b[6])
+{
+  const Vec3 dir = normal(sub(make3(c.position), make3(c.look_at)));
+  const Vec3 centre = { { (float)((b[0] + b[1]) / 2.0), (float)((b[2] + b[3]) / 2.0), (float)((b[4] + b[5]) / 2.0) } };
+  const Vec3 extent = { { (float)(b[1] - b[0]), (float)(b[3] - b[2]), (float)(b[5] - b[4]) } };
+  const float diag = magnitude(extent);
+  for (int k = 0; k < 3; ++k)
+  {
+    c.look_at[k] = centre[k];
+    c.position[k] = centre[k] + dir[k] * diag * 1.0f;
+  }
+  c.fov = 60.f;
+  c.near_plane = 0.1f * diag;
+  c.far_plane = diag * 10.0f;
+  c.xpan = c.ypan = 0.f;
+  c.zoom = 1.f;
+}
+// the camera position turned about the look-at point: T(look_at) * R * T(-look_at), applied as a point
+inline void camera_turn(vr_camera& c, float deg, const Vec3& axis)
+{
+  const Mat4 m = mul(mul(translation(c.look_at[0], c.look_at[1], c.look_at[2]), rotation(deg, axis)),
+                     translation(-c.look_at[0], -c.look_at[1], -c.look_at[2]));
+  const float p[4] = { c.position[0], c.position[1], c.position[2], 1.f };
+  float q[4];
+  mulv(m, p, q);
+  c.position[0] = q[0]; c.position[1] = q[1]; c.position[2] = q[2];
+}
+inline void camera_azimuth(vr_camera& c, float deg) { camera_turn(c, deg, make3(c.up)); }
+inline void camera_elevation(vr_camera& c, float deg)
+{
+  camera_turn(c, deg, cross(sub(make3(c.position), make3(c.look_at)), make3(c.up)));
+}
+inline void camera_zoom(vr_camera& c, float z) { c.zoom *= std::pow(4.0f, z); }
+inline void camera_cinema(vr_camera& c, const double b[6], float phi, float theta)
+{
+  camera_default(c);
+  camera_reset_to_bounds(c, b);
+  const Vec3 extent = { { (float)(b[1] - b[0]), (float)(b[3] - b[2]), (float)(b[5] - b[4]) } };
+  const float radius = (float)((double)magnitude(extent) * 2.5 / 2.0);
+  const Mat4 rot = mul(rotation(phi, Vec3{ { 0.f, 0.f, 1.f } }), rotation(theta, Vec3{ { 1.f, 0.f, 0.f } }));
+  const float up_h[4] = { 0.f, 1.f, 0.f, 0.f }, pos_h[4] = { 0.f, 0.f, 1.f, 1.f };
+  float u[4], q[4];
+  mulv(rot, up_h, u);
+  mulv(rot, pos_h, q);
+  const Vec3 un = normal(Vec3{ { u[0], u[1], u[2] } });
+  for (int k = 0; k < 3; ++k)
+  {
+    c.up[k] = un[k];
+    c.look_at[k] = (float)((b[2 * k] + b[2 * k + 1]) / 2.0);
+    c.position[k] = q[k] * radius + c.look_at[k];
+  }
+}
+
 struct RayGen
 {
   float nlook[3], delta_x[3], delta_y[3];

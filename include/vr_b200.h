@@ -327,6 +327,25 @@ VR_API void vr_visibility_order(const double* domain_bounds /* n x 6 */, int n_d
                                 const vr_camera* cam, int* order_out);
 VR_API void vr_find_subset(const vr_camera* cam, int width, int height, const double bounds[6],
                            int out_minx_miny_w_h[4]);
+/* vtkm::rendering::Camera, 3-D mode, as Ascent drives it -- parse_camera
+ * (ascent_runtime_conduit_to_vtkm_parsing.cpp:97-173), Render.cpp:314-347 (ResetToBounds on the scene
+ * bounds), and one camera of the cinema orbit (ascent_runtime_rendering_filters.cpp:906-960).  K0.   */
+VR_API void vr_camera_default(vr_camera* cam);
+VR_API void vr_camera_reset_to_bounds(vr_camera* cam, const double bounds[6]);
+VR_API void vr_camera_azimuth(vr_camera* cam, float degrees);
+VR_API void vr_camera_elevation(vr_camera* cam, float degrees);
+VR_API void vr_camera_zoom(vr_camera* cam, float zoom); /* zoom factor *= 4^zoom */
+VR_API void vr_camera_cinema(vr_camera* cam, const double bounds[6], float phi_degrees, float theta_degrees);
+/* vtkm::cont::ColorTable::Sample(n_samples, Vec4ui_8) for a table given by its nodes (positions
+ * ascending in [0,1]; colour space 0 RGB, 1 CIELAB, 2 diverging/Msh), and convert_table's uint8 -> float4
+ * (VolumeRenderer.cpp:64-91).  K8: what vr_set_tf expects.  Either output may be NULL.  Returns
+ * VR_ERR_INVALID for unsorted nodes, n_samples < 2 or an unknown colour space.                      */
+VR_API vr_status vr_color_table_sample(int color_space, int n_color, const double* color_x,
+                                       const float* color_rgb /* n_color x 3 */, int n_alpha,
+                                       const double* alpha_x, const float* alpha, int n_samples,
+                                       uint8_t* rgba8_out, float* rgba_out);
+/* VolumeRenderer::CorrectOpacity for one alpha node (VolumeRenderer.cpp:448-466).  V3.           */
+VR_API float vr_correct_opacity(float alpha, float samples);
 /* Synthetic braid field (Conduit blueprint::mesh::examples::braid) written straight into device
  * memory: window (i0,j0,k0)+(nx,ny,nz) of a (gx,gy,gz) global grid.  Bench input generator.    */
 VR_API vr_status vr_synth_braid_dev(vr_ctx* ctx, void* field_dev, int dtype, const int n[3],

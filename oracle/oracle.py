@@ -43,11 +43,14 @@ assert PARTIAL_DTYPE.itemsize == 24
 
 
 def build(force=False):
-    """Compile liboracle.so (and _ref/ when /root/reference is present)."""
-    if force or not os.path.exists(os.path.join(_HERE, "liboracle.so")) or (
-            os.path.isdir("/root/reference")
-            and not os.path.exists(os.path.join(_HERE, "_ref", "libapcomp_ref.so"))):
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    """Compile liboracle.so (and _ref/ when /root/reference is present); make only rebuilds what is
+    older than its sources."""
+    have = os.path.exists(os.path.join(_HERE, "liboracle.so"))
+    try:
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    except (OSError, subprocess.CalledProcessError):
+        if not have:
+            raise
 
 
 def _ptr(a, t):
@@ -68,12 +71,24 @@ lib.orc_composite_partials.restype = C.c_int64
 lib.orc_composite_partials.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
 lib.orc_partial_owner.restype = C.c_int
 lib.orc_num_threads.restype = C.c_int
+lib.orc_set_num_threads.argtypes = [C.c_int]
 if ref is not None:
     ref.ref_composite_partials.restype = C.c_longlong
 
 
 def num_threads():
     return int(lib.orc_num_threads())
+
+
+def use_all_cores():
+    """OpenMP threads = the cores this process may run on, whatever OMP_NUM_THREADS says (torchrun
+    exports OMP_NUM_THREADS=1 to its workers)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib.orc_set_num_threads(int(n))
+    return num_threads()
 
 
 # ----------------------------------------------------------------------------- camera (K0)
@@ -110,6 +125,22 @@ def camera_elevation(c, deg):
 
 def camera_zoom(c, z):
     lib.orc_camera_zoom(C.byref(c), C.c_float(z))
+
+
+def camera_cinema(bounds, phi, theta):
+    """One camera of the cinema orbit (CinemaManager::create_cinema_cameras)."""
+    c = Camera()
+    b = (C.c_double * 6)(*[float(v) for v in bounds])
+    lib.orc_camera_cinema(C.byref(c), b, C.c_float(phi), C.c_float(theta))
+    return c
+
+
+def cinema_angles(phi, theta):
+    """CinemaManager::create_cinema_angles (rendering_filters.cpp:882-893 with the phi/theta ranges
+    of :568-574,613-619): phi in [-180, 180), theta in [0, 180), both as float."""
+    ph = [float(np.float32(-180.0 + (360.0 / float(phi)) * a)) for a in range(phi)]
+    th = [float(np.float32(0.0 + (180.0 / float(theta)) * a)) for a in range(theta)]
+    return ph, th
 
 
 def projview(c, w, h):
@@ -339,3 +370,97 @@ def ref_composite_partials(partial_lists):
     n = ref.ref_composite_partials(allp.ctypes.data_as(C.c_void_p), _ptr(counts, C.c_longlong),
                                    int(counts.size), out.ctypes.data_as(C.c_void_p))
     return out[:n].copy()
+
+
+# ----------------------------------------------------------------------------- colour table (K8)
+class _CTable(C.Structure):
+    _fields_ = [("space", C.c_int), ("n_color", C.c_int), ("color_x", C.c_double * 64),
+                ("color_rgb", (C.c_float * 3) * 64), ("n_alpha", C.c_int), ("alpha_x", C.c_double * 64),
+                ("alpha_v", C.c_float * 64)]
+
+
+lib.orc_colortable_add_point.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
+lib.orc_colortable_add_point_alpha.argtypes = [C.c_void_p, C.c_double, C.c_double]
+lib.orc_colortable_correct_opacity.argtypes = [C.c_void_p, C.c_float]
+
+PRESETS = {"cool to warm": 0, "rainbow desaturated": 1, "black-body radiation": 2, "grayscale": 3}
+
+
+class ColorTable:
+    """vtkm::cont::ColorTable as the volume plot uses it (oracle/colortable_oracle.c)."""
+
+    def __init__(self, name="cool to warm"):
+        self.t = _CTable()
+        if lib.orc_colortable_preset(C.byref(self.t), PRESETS[name.lower()]) != 0:
+            raise ValueError(name)
+
+    def add_point(self, x, rgb):
+        lib.orc_colortable_add_point(C.byref(self.t), float(x), float(rgb[0]), float(rgb[1]), float(rgb[2]))
+        return self
+
+    def add_point_alpha(self, x, a):
+        lib.orc_colortable_add_point_alpha(C.byref(self.t), float(x), float(a))
+        return self
+
+    def clear_colors(self):
+        lib.orc_colortable_clear_colors(C.byref(self.t))
+        return self
+
+    def correct_opacity(self, samples):
+        """VolumeRenderer::CorrectOpacity (in place)."""
+        lib.orc_colortable_correct_opacity(C.byref(self.t), C.c_float(samples))
+        return self
+
+    def sample_u8(self, n=1024):
+        out = np.zeros((n, 4), np.uint8)
+        lib.orc_colortable_sample_u8(C.byref(self.t), int(n), _ptr(out, C.c_uint8))
+        return out
+
+    def lut(self, n=1024):
+        out = np.zeros((n, 4), np.float32)
+        lib.orc_colortable_lut(C.byref(self.t), int(n), _ptr(out, C.c_float))
+        return out
+
+
+def parse_color_table(node):
+    """parse_color_table (ascent_runtime_conduit_to_vtkm_parsing.cpp:199-305) for the subset the volume
+    tests use: a preset name, alpha / rgb control points appended in order."""
+    name = str(node.get("name", "cool to warm")).lower()
+    t = ColorTable(name if name in PRESETS else "cool to warm")
+    cps = node.get("control_points", [])
+    if any(p["type"] == "rgb" for p in cps) and "name" not in node:
+        t.clear_colors()
+    for p in cps:
+        if p["type"] == "rgb":
+            t.add_point(p["position"], p["color"])
+        elif p["type"] == "alpha":
+            t.add_point_alpha(p["position"], p["alpha"])
+    return t
+
+
+def default_volume_table():
+    """VolumeRenderer ctor, VolumeRenderer.cpp:395-408 (both alpha points at x = 0)."""
+    return ColorTable("cool to warm").add_point_alpha(0.0, 0.02).add_point_alpha(0.0, 0.5)
+
+
+# ----------------------------------------------------------------------------- braid (input generator)
+def braid_values(nx, ny, nz, i0=0, j0=0, k0=0, gx=None, gy=None, gz=None, dtype=np.float64):
+    """Conduit blueprint::mesh::examples::braid vertex field [Conduit, recalled; corroborated by
+    src/examples/tutorial/ascent_intro/cpp/blueprint_example3.cpp:61-86], evaluated point by point:
+    window (i0,j0,k0)+(nx,ny,nz) of a (gx,gy,gz) grid, x fastest."""
+    gx, gy, gz = gx or nx, gy or ny, gz or nz
+    pi = 3.14159265359
+    dx = float(np.float32(4.0 * pi)) / float(gx - 1)
+    dy = float(np.float32(2.0 * pi)) / float(gy - 1)
+    dz = float(np.float32(3.0 * pi)) / float(gz - 1)
+    out = np.empty((nz, ny, nx), dtype)
+    i = np.arange(i0, i0 + nx, dtype=np.float64)[None, :]
+    j = np.arange(j0, j0 + ny, dtype=np.float64)[:, None]
+    cx = i * dx + 2.0 * pi
+    cy = j * dy - pi
+    for k in range(nz):
+        cz = (k0 + k) * dz - 1.5 * pi
+        v = np.sin(cx) + np.sin(cy) + 2 * np.cos(np.sqrt((cx * cx) / 2.0 + cy * cy) / .75) + 4 * np.cos(cx * cy / 4.0)
+        v = v + np.sin(cz) + 1.5 * np.cos(np.sqrt(cx * cx + cy * cy + cz * cz) / .75)
+        out[k] = v
+    return out.reshape(-1)

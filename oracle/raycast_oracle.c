@@ -252,6 +252,37 @@ ORC_API void orc_camera_zoom(orc_camera* c, float z)
   c->zoom *= factor;
 }
 
+/* CinemaManager::create_cinema_cameras, src/libs/ascent/runtimes/flow_filters/
+ * ascent_runtime_rendering_filters.cpp:906-960, for one (phi, theta) pair: ResetToBounds, then
+ * position = center + radius * (RotateZ(phi) * RotateX(theta)) (0,0,1), up = the same rotation of
+ * (0,1,0), radius = |extent| * 2.5 / 2.0 (double arithmetic, narrowed).  [VTK-m] Transform3DRotateX/Z
+ * are Transform3DRotate about the unit axes (general formula, so the diagonal entry of the fixed
+ * axis is (1 - cos) + cos, not a literal 1). */
+ORC_API void orc_camera_cinema(orc_camera* c, const double b[6], float phi, float theta)
+{
+  orc_camera_default(c);
+  orc_camera_reset_to_bounds(c, b);
+  float center[3] = { (float)((b[0] + b[1]) / 2.0), (float)((b[2] + b[3]) / 2.0),
+                      (float)((b[4] + b[5]) / 2.0) };
+  float ext[3] = { (float)(b[1] - b[0]), (float)(b[3] - b[2]), (float)(b[5] - b[4]) };
+  float radius = (float)((double)v_mag(ext) * 2.5 / 2.0);
+  const float zaxis[3] = { 0.f, 0.f, 1.f }, xaxis[3] = { 1.f, 0.f, 0.f };
+  float Rz[16], Rx[16], R[16];
+  m_rotate(phi, zaxis, Rz);
+  m_rotate(theta, xaxis, Rx);
+  m_mul(Rz, Rx, R);
+  float up4[4] = { 0.f, 1.f, 0.f, 0.f }, pos4[4] = { 0.f, 0.f, 1.f, 1.f }, u[4], q[4];
+  m_mulv(R, up4, u);   /* Transform3DVector */
+  v_normalize(u);
+  m_mulv(R, pos4, q);  /* Transform3DPoint: no perspective divide */
+  for (int i = 0; i < 3; ++i)
+  {
+    c->up[i] = u[i];
+    c->look_at[i] = center[i];
+    c->position[i] = q[i] * radius + center[i];
+  }
+}
+
 /* [VTK-m] Camera3DStruct::CreateViewMatrix */
 ORC_API void orc_view_matrix(const orc_camera* c, float m[16])
 {
@@ -936,6 +967,16 @@ ORC_API void orc_visibility_order(const double* domain_bounds, int n, const orc_
   for (int i = 0; i < n; ++i) out_order[idx[i]] = i;
   if (out_depths) memcpy(out_depths, depth, sizeof(float) * (size_t)n);
   free(depth); free(idx);
+}
+
+/* bench.py --impl reference: use every host core even when the launcher exported OMP_NUM_THREADS=1 */
+ORC_API void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
 }
 
 ORC_API int orc_num_threads(void)

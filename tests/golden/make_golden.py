@@ -8,6 +8,14 @@ Sources (all under /root/reference/src/tests/_baseline_images/):
                                                               zbuffer}{,_mpi}.cpp
   render_0100.png, render_1100.png   <- t_ascent_render_3d.cpp:1643-1780 (test_render_3d_multi_render)
   tout_render_mpi_3d_diy_volume100.png <- t_ascent_mpi_render_3d.cpp:284-388
+  tout_render_3d_multi_default_runtime100.png <- t_ascent_render_3d.cpp:1017-1122 (colour bars only: the
+      scene itself needs the contour filter and the surface ray tracer, which are outside the volume path)
+
+Colour bars: VTK-m's ColorBarAnnotation draws ColorTable::Sample(bar height) of the plot's table into
+the image (one table sample per pixel row), so one pixel column of a bar is a golden vector for K8:
+  colorbars.npz: cool_to_warm_179 (mpi volume golden), cool_to_warm_359 and rainbow_desaturated_359
+  (multi_default_runtime golden: the pseudocolor plot's default table and the volume plot's
+  "rainbow desaturated"), each n x 3 uint8, index 0 = table position 0.
 
 PNG rows are flipped vertically on save (ascent_png_encoder.cpp:95-96): stored arrays are
 un-flipped, i.e. row j of the array is image row y=j in canvas/test coordinates.
@@ -45,6 +53,13 @@ def main():
     np.savez_compressed(os.path.join(HERE, "tout_render_mpi_3d_diy_volume100.npz"),
                         rgb=load("tout_render_mpi_3d_diy_volume100.png")[..., :3],
                         rects=flip_rects([(200, 350, 100, 250), (170, 350, 262, 420)], 512))
+    vol = load("tout_render_mpi_3d_diy_volume100.png")
+    multi = load("tout_render_3d_multi_default_runtime100.png")
+    # (arrays are un-flipped: row index grows upwards, like the table position along a vertical bar)
+    np.savez_compressed(os.path.join(HERE, "colorbars.npz"),
+                        cool_to_warm_179=vol[512 - 230:512 - 51, 481, :3],
+                        cool_to_warm_359=multi[1024 - 461:1024 - 102, 975, :3],
+                        rainbow_desaturated_359=multi[1024 - 922:1024 - 563, 975, :3])
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

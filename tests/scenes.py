@@ -146,25 +146,6 @@ def partials_to_image(partials, width, height):
 
 
 def cinema_camera(bounds, phi, theta):
-    """CinemaManager::create_cinema_cameras (ascent_runtime_rendering_filters.cpp:906-960):
-    radius = |extent| * 2.5 / 2, RotateZ(phi) * RotateX(theta) applied to (0,0,1) and up (0,1,0)."""
-    b = np.asarray(bounds, np.float64)
-    cam = O.camera_reset_to_bounds(b)
-    center = np.array([(b[0] + b[1]) / 2, (b[2] + b[3]) / 2, (b[4] + b[5]) / 2], np.float32)
-    ext = np.array([b[1] - b[0], b[3] - b[2], b[5] - b[4]], np.float32)
-    radius = np.float32(np.float32(np.sqrt((ext * ext).sum(dtype=np.float32))) * 2.5 / 2.0)
-
-    def rot(deg, axis):
-        a = np.float32(0.01745329251994329547437168059786927) * np.float32(deg)
-        s, c = np.float32(np.sin(a)), np.float32(np.cos(a))
-        if axis == "z":
-            return np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]], np.float32)
-        return np.array([[1, 0, 0], [0, c, -s], [0, s, c]], np.float32)
-    R = rot(phi, "z") @ rot(theta, "x")
-    up = R @ np.array([0, 1, 0], np.float32)
-    up = up / np.float32(np.sqrt((up * up).sum(dtype=np.float32)))
-    pos = (R @ np.array([0, 0, 1], np.float32)) * radius + center
-    cam.up[:] = [float(v) for v in up]
-    cam.look_at[:] = [float(v) for v in center]
-    cam.position[:] = [float(v) for v in pos]
-    return cam
+    """CinemaManager::create_cinema_cameras (ascent_runtime_rendering_filters.cpp:906-960), one angle
+    pair: the oracle's restatement."""
+    return O.camera_cinema(bounds, phi, theta)

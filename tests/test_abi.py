@@ -70,8 +70,8 @@ def test_host_helpers_match_oracle():
         assert list(_lib.visibility_order(doms, cam)) == list(O.visibility_order(doms, cam)[0])
 
 
-def test_python_camera_mirror_tracks_oracle_camera():
-    """ascent_b200.camera (host mirror of vtkm::rendering::Camera) vs the oracle's K0."""
+def test_python_camera_mirror_equals_oracle_camera():
+    """ascent_b200.camera (host mirror of vtkm::rendering::Camera) vs the oracle's K0: same bits."""
     from ascent_b200 import camera
     b = [-10, 10.5, -3, 7, 0, 31]
     c = camera.Camera().reset_to_bounds(b)
@@ -82,17 +82,10 @@ def test_python_camera_mirror_tracks_oracle_camera():
         O.camera_elevation(o, deg_e)
     c.zoom_by(0.5)
     O.camera_zoom(o, 0.5)
-    s = c.to_struct()
-    for name in ("position", "look_at", "up"):
-        assert np.allclose(list(getattr(s, name)), list(getattr(o, name)), rtol=1e-5, atol=1e-5)
-    for name in ("fov", "zoom", "near_plane", "far_plane"):
-        assert abs(getattr(s, name) - getattr(o, name)) <= 1e-5 * abs(getattr(o, name))
+    assert bytes(c.to_struct()) == bytes(o)
     cams = camera.cinema_cameras(b, *camera.cinema_angles(8, 8))
     assert len(cams) == 64
-    oc = scenes.cinema_camera(b, -135.0, 22.5)
-    mc = cams[1 * 8 + 1].to_struct()
-    assert np.allclose(list(mc.position), list(oc.position), rtol=1e-5, atol=1e-4)
-    assert np.allclose(list(mc.up), list(oc.up), rtol=1e-5, atol=1e-5)
+    assert bytes(cams[1 * 8 + 1].to_struct()) == bytes(O.camera_cinema(b, -135.0, 22.5))
 
 
 def test_header_is_plain_c_and_library_exports_only_the_abi(tmp_path):
