@@ -149,7 +149,9 @@ def run_bench(args, wl, bench):
         lmin = min(float(t.min()) for t in fields.values())
         lmax = max(float(t.max()) for t in fields.values())
     rmin, rmax = global_range(lmin, lmax, dist)
-    sp = bench.scene_params(wl, blocks, (rmin, rmax))
+    sp = bench.scene_params(wl, (rmin, rmax))
+    if getattr(args, "one_block_per_rank", False):
+        sp["bounds"] = sp["bounds"][len(sp["bounds"]) - world:]
     ctx.set_tf(sp["lut"])
     for i in mine:
         b = blocks[i]
@@ -276,9 +278,45 @@ def run_bench(args, wl, bench):
     e2e = _e2e(ctx, dist, stream, blocks, mine, fields, sp, cam, W, H, rmin, rmax, render, composite,
                rank, max(3, min(args.steps, 5)))
 
+    # ---- rank 0, outside every timed region: the oracle on the same inputs (parity of the frame that was
+    # timed, CPU baseline on the host cores) and T(1) of the same workload on this rank's GPU alone
+    parity = cpu = t1 = None
+    diag = getattr(args, "one_block_per_rank", False)
+    if rank == 0 and not args.no_cpu and not diag:
+        with torch.cuda.stream(stream):
+            render()
+            composite()
+            g_rgba, g_depth = ctx.canvas_download(W, H)
+    else:
+        with torch.cuda.stream(stream):
+            if not args.no_cpu and not diag:
+                render()
+                composite()
+            ctx.synchronize()
+    if rank == 0 and not args.no_cpu and not diag:
+        from oracle import oracle as O
+        cores = O.use_all_cores()
+        host_fields = []
+        tmp = torch.empty(nvox, dtype=torch.float32, device="cuda")
+        for b in blocks:
+            ctx.synth_braid_dev(tmp.data_ptr(), _lib.VR_F32, b["dims"], b["start"], b["glob"])
+            ctx.synchronize()
+            host_fields.append(tmp.cpu().numpy())
+        del tmp
+        sc = bench.OracleScene(wl, host_fields, world, rng=(rmin, rmax))
+        o_rgba, o_depth = sc.frame(0)
+        parity = bench.compare_canvas(g_rgba, g_depth, o_rgba, o_depth)
+        dt_cpu, n_cpu = sc.time_frames(5, 10.0)
+        cpu = bench.cpu_entry(dt_cpu, n_cpu, cores, wl, "bounded to ~10 s, rank 0's host cores")
+        del sc, host_fields
+        l1 = bench.measure_single(args, dict(wl), full=False)
+        t1 = {"ms_per_step": l1["ms_per_step"], "value": l1["value"], "unit": "Mrays/s",
+              "render_ms_per_frame": l1["render_ms_per_frame"], "composite_ms_per_frame": l1["composite_ms_per_frame"],
+              "what": "the same workload (all %d blocks, path B) on rank 0's GPU alone, measured in this run while "
+                      "the other ranks wait: T(1) of the strong-scaling curve" % len(blocks)}
+
     if rank == 0:
-        pk, pk_src = bench.peaks()
-        alg = nvox * 4 * len(blocks) / world + W * H * 20  # per GPU per frame
+        alg = nvox * 4 + W * H * 20  # SURVEY 8(d), one launch = one block, one view
         # NVLink bytes that reach the busiest GPU (rank 0) per frame: what it pulls for the pixels it
         # owns plus what the other owners store into its result
         rects = []
@@ -295,21 +333,26 @@ def run_bench(args, wl, bench):
             pulled = layer_px / world * (world - 1) / world * 8.0   # RGBA8 + depth of the covering layers
             pushed = covered * (world - 1) / world * 8.0            # folded pixels stored into rank 0
         else:
+            alg = nvox * 4 + layer_px / len(rects) * 20  # a layer launch writes its rectangle, not the frame
             pulled = layer_px / world * (world - 1) / world * 20.0  # layer entries (rgba + depth)
             pushed = covered * (world - 1) / world * 20.0           # finished canvas pixels into rank 0
         nv_bytes = pulled + pushed
+        roof = bench.roofline_of(alg, render_ms / len(mine), len(mine),
+                                 ("c3_a" if path_a else "c3") if bench.SAMPLES == 100 else "none",
+                                 "trace_kernel (sampler.cu)")
+        roof["note"] = ("per GPU; kernel_ms_per_launch = the slowest rank's render span / its launches; at samples = 100 "
+                        "the rays touch a fraction of the block, so `frac` (SURVEY 8(d) accounting) may exceed 1 -- "
+                        "`frac_measured` is the DRAM-traffic statement")
+        cfg = bench.config_of(wl, world)
         line = {"metric": "volume_render_mrays_per_s", "value": W * H / (ms * 1e-3) / 1e6, "unit": "Mrays/s",
                 "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": wl["name"], "image": [W, H], "samples": bench.SAMPLES,
-                           "path": "A (uint8 image, P2P direct-send fold)" if path_a else
-                                   "B (float partials as dense ray layers, P2P gather+fold)",
-                           "blocks_per_gpu": len(mine),
-                           "order": ("pipelined: trace(k+1) issued before exchange(k) (VR_FRAME_AHEAD)" if use_piped
-                                     else "serial: trace(k), exchange(k)"),
-                           "l2": "inputs (%.0f MB of field per GPU) larger than the 126 MB L2" % (
-                               nvox * 4 * len(mine) / 1e6)},
+                "data": "synthetic", "config": cfg,
+                "details": {"exchange": "P2P direct-send fold (uint8 images)" if path_a else
+                                        "P2P gather + fold of dense ray layers (float partials)",
+                            "blocks_per_gpu": len(mine),
+                            "order": ("pipelined: trace(k+1) issued before exchange(k) (VR_FRAME_AHEAD)" if use_piped
+                                      else "serial: trace(k), exchange(k)")},
                 "frames_per_s": 1e3 / ms, "render_ms_per_frame": render_ms,
                 "ms_per_step_serial_order": (serial_total_max / args.steps) if piped is not None else ms,
                 "ms_per_step_pipelined_order": (piped_total_max / args.steps) if piped is not None else None,
@@ -319,16 +362,12 @@ def run_bench(args, wl, bench):
                                 "rows": per_rank},
                 "nvlink": {"bytes_into_rank0_per_frame": nv_bytes, "pulled": pulled, "pushed_into_rank0": pushed,
                            "achieved_gbs": nv_bytes / (comp_ms * 1e-3) / 1e9, "peak_gbs": 770.0,
-                           "peak_source": "measured peer copy per direction (B200_PROFILING.md)"},
+                           "peak_source": "measured peer copy per direction (B200_PROFILING.md)",
+                           "how": "bytes from the frame's geometry (screen rectangles), time = composite_ms_per_frame"},
                 "nccl_baseline": nccl_base,
+                "t1_same_run": t1,
                 "e2e": e2e, "gpu_launches": int(tsum[4]), "clocks": clk,
-                "roofline": {"bound": "hbm", "kernel": "trace_kernel (sampler.cu)",
-                             "achieved": alg / (render_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
-                             "peak_source": pk_src, "unit": "GB/s",
-                             "frac": alg / (render_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
-                             "algorithmic_bytes_per_gpu_per_frame": alg,
-                             "kernel_ms_per_frame": render_ms, "launches_per_frame": len(mine)},
-                "cpu_baseline": None}
+                "roofline": roof, "parity": parity, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     dist.barrier()
     ctx.close()

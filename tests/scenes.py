@@ -4,7 +4,7 @@ Each builder returns plain data (domains, camera parameters, LUT, range, sample 
 same inputs can be handed to the oracle and to the C-ABI."""
 import numpy as np
 
-from ascent_b200 import color_table, datasets
+from ascent_b200 import datasets
 from oracle import oracle as O
 
 MULTI_RENDER_TF = {"name": "blue", "control_points": [
@@ -57,7 +57,7 @@ def multi_render_scene(which):
         cam.near_plane, cam.far_plane = 0.1, 100.1
         O.camera_azimuth(cam, 10.0)
         O.camera_elevation(cam, -10.0)
-    lut = color_table.parse_color_table(MULTI_RENDER_TF).corrected_opacity(100).lut()
+    lut = O.parse_color_table(MULTI_RENDER_TF).correct_opacity(100).lut()
     rmin, rmax = field_range([dom])
     return dict(doms=[dom], cam=cam, W=W, H=H, lut=lut, rmin=rmin, rmax=rmax,
                 sample_dist=O.sample_distance(bounds, 100), bounds=bounds)
@@ -70,11 +70,11 @@ def mpi_volume_scene():
     gb = datasets.union_bounds(bl)
     cam = O.camera_reset_to_bounds(gb)
     O.camera_azimuth(cam, 45.0)
-    tf = color_table.parse_color_table({"control_points": [
+    tf = O.parse_color_table({"control_points": [
         {"type": "alpha", "position": 0., "alpha": 0.8},
         {"type": "alpha", "position": 1.0, "alpha": 0.0}]})
     rmin, rmax = field_range(doms)
-    return dict(doms=doms, cam=cam, W=512, H=512, lut=tf.corrected_opacity(100).lut(), rmin=rmin,
+    return dict(doms=doms, cam=cam, W=512, H=512, lut=tf.correct_opacity(100).lut(), rmin=rmin,
                 rmax=rmax, sample_dist=O.sample_distance(gb, 100), bounds=gb, dom_bounds=bl)
 
 
