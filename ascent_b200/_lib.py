@@ -16,7 +16,7 @@ VR_F32, VR_F64 = 0, 1
 VR_POINT, VR_CELL = 0, 1
 VR_HOST, VR_DEVICE, VR_HOST_MAPPED, VR_HOST_STAGED = 0, 1, 2, 3
 IPC_HANDLE_BYTES = 64
-FRAME_WRITE_CANVAS, FRAME_NO_CLEAR, FRAME_AHEAD = 1, 2, 4
+FRAME_WRITE_CANVAS, FRAME_NO_CLEAR, FRAME_AHEAD, FRAME_PUSH = 1, 2, 4, 8
 
 # every symbol include/vr_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -326,9 +326,9 @@ class Context:
                                           rmin, rmax, rgba.ctypes.data, depth.ctypes.data))
 
     def trace_to_image(self, block_id, cam, W, H, sample_dist, rmin, rmax, write_canvas=False,
-                       no_clear=False, ahead=False):
+                       no_clear=False, ahead=False, push=False):
         flags = (FRAME_WRITE_CANVAS if write_canvas else 0) | (FRAME_NO_CLEAR if no_clear else 0) | \
-            (FRAME_AHEAD if ahead else 0)
+            (FRAME_AHEAD if ahead else 0) | (FRAME_PUSH if push else 0)
         self._ck(self.lib.vr_trace_to_image(self.h, block_id, C.byref(as_camera(cam)), W, H, sample_dist,
                                             rmin, rmax, flags))
 

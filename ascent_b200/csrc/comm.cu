@@ -24,6 +24,7 @@
 // slower peer still reads frame e.
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "vr_internal.h"
@@ -68,19 +69,20 @@ struct Flags
   // hold the cleared value, as left by the last exchange kernel (host decides whether that still holds)
   int clean_res[2][4];
   int clean_canvas[4];
+  // image path: rank r PUSHED its image of that epoch parity into the owners' receive slots (sampler
+  // mode 5) instead of leaving it in its own arena
+  int img_pushed[2][kMaxRanks];
+  // a rank that hit a rank-local error publishes "I abort exchange <epoch>" here (per path: image,
+  // partial list, layers) together with its ready flag, so that nobody waits for data that never comes
+  unsigned int aborted[3][kMaxRanks];
+  // (local) first exchange of this rank that did not complete normally: epoch, path, reason
+  // (1 = a wait ran into the time limit, 2 = a peer aborted), for the host to report
+  unsigned int err_epoch, err_path, err_reason, err_peer;
 };
 static_assert(sizeof(Flags) <= 4096, "flag block");
+enum { kPathImage = 0, kPathPartials = 1, kPathLayers = 2 };
 
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v)
-{
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p)
-{
-  unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
+__device__ __forceinline__ ExchangeError* err_of(Flags* f) { return reinterpret_cast<ExchangeError*>(&f->err_epoch); }
 
 __device__ __forceinline__ unsigned blend_u8x4(unsigned front, unsigned back)
 {
@@ -124,36 +126,50 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
 {
   Flags* my_flags = reinterpret_cast<Flags*>(P.peers[P.rank] + P.off_flags);
   const int par = P.epoch & 1;
-  // ---- announce: my image for this epoch is complete (previous kernel on this stream wrote it)
+  // ---- announce: my image for this epoch is complete (previous kernel on this stream wrote it -- into
+  // my own arena, or, pushed, into the owners' receive slots)
   if (blockIdx.x == 0 && threadIdx.x < P.size)
   {
     Flags* f = reinterpret_cast<Flags*>(P.peers[threadIdx.x] + P.off_flags);
 #pragma unroll
     for (int k = 0; k < 4; ++k) ((volatile int*)f->img_rect[par][P.rank])[k] = P.rect[k];
+    ((volatile int*)f->img_pushed[par])[P.rank] = P.pushed;
     __threadfence_system();
     st_release_sys(&f->ready[P.rank], P.epoch);
   }
-  // ---- wait until every rank's image is complete
-  if (threadIdx.x < P.size)
-    while (ld_acquire_sys(&my_flags->ready[threadIdx.x]) < P.epoch) __nanosleep(32);
-  __syncthreads();
+  // ---- wait until every rank's image is complete (bounded: a peer that bailed out must not hang us)
+  const bool go = wait_all_ready(err_of(my_flags), my_flags->ready, my_flags->aborted[kPathImage], kPathImage, P.size,
+                                 P.epoch, P.timeout_ns);
 
   __shared__ int s_rect[kMaxRanks][4]; // in fold order
   if (threadIdx.x < P.size * 4)
   {
     const int l = threadIdx.x >> 2, k = threadIdx.x & 3;
-    s_rect[l][k] = ((volatile int*)my_flags->img_rect[par][P.order[l]])[k];
+    s_rect[l][k] = go ? ((volatile int*)my_flags->img_rect[par][P.order[l]])[k] : 0; // aborted: nothing to fold
   }
   __syncthreads();
 
+  // a layer that was PUSHED sits in my own arena, in the receive slot of its source rank, indexed by
+  // my local chunk number; one that was not is pulled out of its owner's arena at the global index
   const uint4* layer_rgba[NR];
   const float4* layer_depth[NR];
+  unsigned local_mask = 0;
 #pragma unroll
   for (int l = 0; l < NR; ++l)
     if (l < P.size)
     {
-      layer_rgba[l] = reinterpret_cast<const uint4*>(P.peers[P.order[l]] + P.off_img_rgba);
-      layer_depth[l] = reinterpret_cast<const float4*>(P.peers[P.order[l]] + P.off_img_depth);
+      const int src = P.order[l];
+      if (((volatile int*)my_flags->img_pushed[par])[src])
+      {
+        local_mask |= 1u << l;
+        layer_rgba[l] = reinterpret_cast<const uint4*>(P.peers[P.rank] + P.off_recv_rgba) + (size_t)src * P.share_groups;
+        layer_depth[l] = reinterpret_cast<const float4*>(P.peers[P.rank] + P.off_recv_depth) + (size_t)src * P.share_groups;
+      }
+      else
+      {
+        layer_rgba[l] = reinterpret_cast<const uint4*>(P.peers[src] + P.off_img_rgba);
+        layer_depth[l] = reinterpret_cast<const float4*>(P.peers[src] + P.off_img_depth);
+      }
     }
   uint4* out_rgba = reinterpret_cast<uint4*>(P.peers[0] + P.off_res_rgba);
   float4* out_depth = reinterpret_cast<float4*>(P.peers[0] + P.off_res_depth);
@@ -233,8 +249,9 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
       {
         if (cover & (1u << l))
         {
-          c[l] = layer_rgba[l][i];
-          d[l] = layer_depth[l][i];
+          const size_t at = (local_mask & (1u << l)) ? k * kChunkGroups + threadIdx.x : i;
+          c[l] = layer_rgba[l][at];
+          d[l] = layer_depth[l][at];
         }
         else
         {
@@ -321,8 +338,8 @@ __global__ void __launch_bounds__(256) covered_to_canvas_kernel(const __grid_con
   const int par = P.epoch & 1;
   // every rank's folded range has landed in my result image (what wait_done_kernel does, without
   // the extra launch)
-  if (threadIdx.x < P.size)
-    while (ld_acquire_sys(&my_flags->done[threadIdx.x]) < P.epoch) __nanosleep(32);
+  if (threadIdx.x < P.size && !wait_epoch(&my_flags->done[threadIdx.x], P.epoch, P.timeout_ns))
+    report_error(err_of(const_cast<Flags*>(my_flags)), P.epoch, kPathImage, 1u, threadIdx.x);
   __syncthreads();
   __shared__ int s_rect[kMaxRanks][4];
   if (threadIdx.x < P.size * 4) s_rect[threadIdx.x >> 2][threadIdx.x & 3] = my_flags->img_rect[par][threadIdx.x >> 2][threadIdx.x & 3];
@@ -350,10 +367,35 @@ __global__ void __launch_bounds__(256) covered_to_canvas_kernel(const __grid_con
   }
 }
 
-__global__ void wait_done_kernel(const unsigned int* done, int size, unsigned int epoch)
+__global__ void wait_done_kernel(Flags* mine, const unsigned int* done, int size, unsigned int epoch, unsigned path,
+                                 unsigned long long timeout_ns)
 {
-  if (threadIdx.x < size)
-    while (ld_acquire_sys(done + threadIdx.x) < epoch) __nanosleep(64);
+  if (threadIdx.x < size && !wait_epoch(done + threadIdx.x, epoch, timeout_ns, 64))
+    report_error(err_of(mine), epoch, path, 1u, threadIdx.x);
+}
+
+// A rank that cannot take part in exchange <epoch> (rank-local error: list too long for the arena, too
+// many layers, ...) still has to release its peers: it raises its ready flag for the epoch together
+// with an abort mark, and reports "done" to rank 0.  The peers' kernels see the mark, skip the work and
+// leave an error for their hosts (vr_status of the next synchronising call).
+__global__ void abort_announce_kernel(unsigned char* const* peers, int rank, int size, size_t off_flags, unsigned path,
+                                      unsigned int epoch)
+{
+  const int t = threadIdx.x;
+  if (t < size)
+  {
+    Flags* f = reinterpret_cast<Flags*>(peers[t] + off_flags);
+    ((volatile unsigned int*)f->aborted[path])[rank] = epoch;
+    __threadfence_system();
+    st_release_sys(path == kPathImage ? &f->ready[rank] : &f->p_ready[rank], epoch);
+  }
+  if (t == 0)
+  {
+    Flags* root = reinterpret_cast<Flags*>(peers[0] + off_flags);
+    __threadfence_system();
+    st_release_sys(path == kPathImage ? &root->done[rank] : &root->p_done[rank], epoch);
+    report_error(err_of(reinterpret_cast<Flags*>(peers[rank] + off_flags)), epoch, path, 2u, rank);
+  }
 }
 
 
@@ -370,18 +412,21 @@ __global__ void sync_post_kernel(Flags* root_flags, unsigned int epoch)
     st_release_sys(&root_flags->s_ready, epoch);
   }
 }
-__global__ void __launch_bounds__(256) sync_pull_kernel(Flags* root_flags, Flags* my_flags, const float* __restrict__ staged,
-                                                        float* __restrict__ depth, size_t n, int rank, unsigned int epoch)
+// (`staged` is rank 0's peer memory, rewritten by rank 0 for every broadcast: no const/__restrict__,
+// so that the loads cannot be turned into non-coherent ones)
+__global__ void __launch_bounds__(256) sync_pull_kernel(Flags* root_flags, Flags* my_flags, float* staged,
+                                                        float* depth, size_t n, int rank, unsigned int epoch,
+                                                        unsigned long long timeout_ns)
 {
-  if (threadIdx.x == 0)
-    while (ld_acquire_sys(&root_flags->s_ready) < epoch) __nanosleep(128);
+  if (threadIdx.x == 0 && !wait_epoch(&root_flags->s_ready, epoch, timeout_ns, 128))
+    report_error(err_of(my_flags), epoch, kPathImage, 1u, 0u);
   __syncthreads();
   const size_t n4 = n / 4;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (size_t i = t; i < n4; i += stride)
-    reinterpret_cast<float4*>(depth)[i] = reinterpret_cast<const float4*>(staged)[i];
-  for (size_t i = n4 * 4 + t; i < n; i += stride) depth[i] = staged[i];
+    reinterpret_cast<float4*>(depth)[i] = __ldcv(reinterpret_cast<const float4*>(staged) + i);
+  for (size_t i = n4 * 4 + t; i < n; i += stride) depth[i] = __ldcv(staged + i);
   __syncthreads();
   if (threadIdx.x == 0)
   {
@@ -405,6 +450,7 @@ struct MergeP2PParams
   size_t n_pixels;
   size_t off_flags, off_poff, off_psorted, off_pout;
   size_t sorted_cap, out_cap;
+  unsigned long long timeout_ns;
   // fused partials_to_canvas (frame starts from a cleared canvas): owners write rank 0's canvas
   size_t off_canvas_rgba, off_canvas_depth;
   ToCanvasParams tp;
@@ -448,14 +494,13 @@ __global__ void __launch_bounds__(256) merge_fold_p2p_kernel(const __grid_consta
     __threadfence_system();
     st_release_sys(&f->p_ready[P.rank], P.epoch);
   }
-  if (threadIdx.x < P.size)
-    while (ld_acquire_sys(&my_flags->p_ready[threadIdx.x]) < P.epoch) __nanosleep(64);
-  __syncthreads();
+  const bool go = wait_all_ready(err_of(my_flags), my_flags->p_ready, my_flags->aborted[kPathPartials], kPathPartials,
+                                 P.size, P.epoch, P.timeout_ns, 64);
 
   // ---- global pixel bounds and my range: RegularDecomposer<DiscreteBounds>, 1-D
   // (vtkh_diy_partial_redistribute.hpp:133-150, decomposition.hpp:37-46,648-666)
   int gmin = 0x7fffffff, gmax = -1;
-  for (int r = 0; r < P.size; ++r)
+  for (int r = 0; r < P.size && go; ++r) // (an aborted exchange folds nothing, but still reports "done")
   {
     const int lo = ((volatile int*)my_flags->p_minmax[par][r])[0];
     const int hi = ((volatile int*)my_flags->p_minmax[par][r])[1];
@@ -611,6 +656,9 @@ struct Layout
   size_t off_poff[2], off_psorted[2], off_pout, off_canvas_rgba, off_canvas_depth, total;
   size_t off_lflags, off_ltab[2], off_lpool_rgba[2], off_lpool_depth[2];
   size_t off_sync_depth;
+  // receive ring of pushed frames: slot e % 3 holds, for every source rank, the pixels of frame e that
+  // THIS rank owns (round-robin 1024-pixel chunks), written by the sources' samplers over NVLink
+  size_t off_recv_rgba[kImgRing], off_recv_depth[kImgRing];
 };
 Layout make_layout(size_t max_pixels, size_t max_partials, bool is_root)
 {
@@ -622,6 +670,10 @@ Layout make_layout(size_t max_pixels, size_t max_partials, bool is_root)
   for (int b = 0; b < kImgRing; ++b) { L.off_img_depth[b] = o; o += px * 4; }
   for (int b = 0; b < 2; ++b) { L.off_res_rgba[b] = o; o += px * 4; }
   for (int b = 0; b < 2; ++b) { L.off_res_depth[b] = o; o += px * 4; }
+  // `ranks` receive slots of ceil(chunks / ranks) whole chunks each: up to one extra chunk per rank
+  const size_t px_recv = px + (size_t)kMaxRanks * 1024;
+  for (int b = 0; b < kImgRing; ++b) { L.off_recv_rgba[b] = o; o += px_recv * 4; }
+  for (int b = 0; b < kImgRing; ++b) { L.off_recv_depth[b] = o; o += px_recv * 4; }
   for (int b = 0; b < 2; ++b) { L.off_poff[b] = o; o += max_partials ? align_up(partial_scan_padded(max_pixels) * 4, 256) : 0; }
   for (int b = 0; b < 2; ++b) { L.off_psorted[b] = o; o += align_up(max_partials * sizeof(vr_partial), 256); }
   // dense ray layers (layers.cu): flags, layer tables and pools, double-buffered
@@ -738,6 +790,57 @@ vr_status comm_ahead_image(vr_ctx* ctx, uchar4** rgba, float** depth)
   return VR_OK;
 }
 
+// receive-slot geometry of a pushed frame (sampler mode 5)
+vr_status comm_push_target(vr_ctx* ctx, bool ahead, int width, int height, TraceParams& p)
+{
+  Comm& c = ctx->comm;
+  if (!c.on || !c.peer_dev)
+  {
+    ctx->err = "VR_FRAME_PUSH needs a connected exchange (vr_comm_init + vr_comm_connect)";
+    return VR_ERR_STATE;
+  }
+  if ((size_t)width * height > c.max_pixels)
+  {
+    ctx->err = "image larger than the max_pixels given to vr_comm_init";
+    return VR_ERR_INVALID;
+  }
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
+  const int slot = (int)((c.epoch + (ahead ? 2 : 1)) % kImgRing);
+  const size_t n4 = ((size_t)width * height + 3) / 4;
+  const size_t n_chunks = (n4 + kChunkGroups - 1) / kChunkGroups;
+  p.push_peers = c.peer_dev;
+  p.push_off_rgba = L.off_recv_rgba[slot];
+  p.push_off_depth = L.off_recv_depth[slot];
+  p.push_share_px = (unsigned int)(((n_chunks + c.size - 1) / c.size) * 1024);
+  p.push_rank = c.rank;
+  p.push_size = c.size;
+  return VR_OK;
+}
+
+// what the exchange kernels left for the host (a wait that hit the time limit, a peer that aborted):
+// reported once, by the next synchronising entry point
+vr_status comm_check_errors(vr_ctx* ctx)
+{
+  Comm& c = ctx->comm;
+  if (!c.on) return VR_OK;
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
+  unsigned int e[4] = { 0, 0, 0, 0 }, le[4] = { 0, 0, 0, 0 };
+  if (cudaMemcpy(e, c.arena + L.off_flags + offsetof(Flags, err_epoch), sizeof(e), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return VR_OK;
+  if (c.max_partials)
+    cudaMemcpy(le, c.arena + L.off_lflags + offsetof(LayerFlags, err), sizeof(le), cudaMemcpyDeviceToHost);
+  const unsigned int* w = e[0] ? e : (le[0] ? le : nullptr);
+  if (!w) return VR_OK;
+  static const char* path[3] = { "image", "partial-list", "ray-layer" };
+  char buf[240];
+  snprintf(buf, sizeof(buf), "%s exchange %u did not complete on rank %d: %s (rank %u)", path[w[1] < 3 ? w[1] : 0], w[0],
+           c.rank, w[2] == 2 ? "aborted by a rank-local error" : "timed out waiting for a peer", w[3]);
+  ctx->err = buf;
+  cudaMemset(c.arena + L.off_flags + offsetof(Flags, err_epoch), 0, sizeof(e));
+  if (c.max_partials) cudaMemset(c.arena + L.off_lflags + offsetof(LayerFlags, err), 0, sizeof(le));
+  return VR_ERR_STATE;
+}
+
 // point the context's layer table/pools at the arena halves of the NEXT layer frame's parity
 vr_status comm_bind_layers(vr_ctx* ctx)
 {
@@ -784,6 +887,12 @@ extern "C" vr_status vr_comm_init(vr_ctx* ctx, int rank, int n_ranks, size_t max
   c.size = n_ranks;
   c.max_pixels = max_pixels;
   c.max_partials = max_partials;
+  {
+    // every cross-rank wait inside the kernels is bounded (default 20 s; VR_COMM_TIMEOUT_MS=0: unbounded)
+    const char* t = std::getenv("VR_COMM_TIMEOUT_MS");
+    const long long ms = t ? std::atoll(t) : 20000;
+    c.timeout_ns = ms > 0 ? (unsigned long long)ms * 1000000ull : 0ull;
+  }
   const Layout L = make_layout(max_pixels, max_partials, rank == 0);
   c.arena_bytes = L.total;
   cudaError_t e = cudaMalloc(&c.arena, c.arena_bytes);
@@ -888,6 +997,15 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
   }
   for (int i = 0; i < c.size; ++i) p.order[i] = idx[i];
   p.zbuffer = zbuffer ? 1 : 0;
+  p.timeout_ns = c.timeout_ns;
+  p.pushed = ctx->img_pushed ? 1 : 0;
+  {
+    const size_t n4 = (p.n_pixels + 3) / 4;
+    const size_t n_chunks = (n4 + kChunkGroups - 1) / kChunkGroups;
+    p.share_groups = ((n_chunks + c.size - 1) / c.size) * kChunkGroups;
+    p.off_recv_rgba = L.off_recv_rgba[c.epoch % kImgRing];
+    p.off_recv_depth = L.off_recv_depth[c.epoch % kImgRing];
+  }
   if (to_canvas && !zbuffer && c.rank == 0 && ctx->W % 4 == 0)
   {
     p.canvas_rgba = ctx->canvas_rgba;
@@ -919,7 +1037,7 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
     }
     else
     {
-      wait_done_kernel<<<1, 32, 0, ctx->stream>>>(f->done, c.size, c.epoch);
+      wait_done_kernel<<<1, 32, 0, ctx->stream>>>(const_cast<Flags*>(f), f->done, c.size, c.epoch, kPathImage, c.timeout_ns);
       ctx->launches++;
       if (to_canvas)
       {
@@ -942,10 +1060,13 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
   const int ns = (int)((c.epoch + 1) % kImgRing);
   ctx->img_rgba = reinterpret_cast<uchar4*>(c.arena + L.off_img_rgba[ns]);
   ctx->img_depth = reinterpret_cast<float*>(c.arena + L.off_img_depth[ns]);
+  ctx->img_pushed = false;
   if (ctx->img_ahead)
   {
     for (int k = 0; k < 4; ++k) ctx->img_rect[k] = ctx->img_rect_ahead[k];
+    ctx->img_pushed = ctx->img_pushed_ahead;
     ctx->img_ahead = false;
+    ctx->img_pushed_ahead = false;
   }
   return VR_OK;
 }
@@ -984,15 +1105,21 @@ static vr_status comm_composite_partials_impl(vr_ctx* ctx, const vr_camera* cam)
   const size_t n_pixels = (size_t)ctx->pW * ctx->pH;
   if (c.max_partials == 0 || n_pixels > c.max_pixels)
     return cfail(ctx, VR_ERR_INVALID, "vr_comm_composite_partials: frame larger than the max_pixels/max_partials given to vr_comm_init", cudaSuccess);
+  cudaSetDevice(ctx->device);
   if (ctx->n_partials_host > c.max_partials)
   {
+    // rank-local: the peers are (or will be) inside this exchange already -- release them
+    const Layout La = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
+    c.pepoch += 1;
+    abort_announce_kernel<<<1, 32, 0, ctx->stream>>>(c.peer_dev, c.rank, c.size, La.off_flags, kPathPartials, c.pepoch);
+    ctx->launches++;
     char buf[200];
-    snprintf(buf, sizeof(buf), "vr_comm_composite_partials: up to %zu partials this frame but max_partials = %zu",
-             ctx->n_partials_host, c.max_partials);
+    snprintf(buf, sizeof(buf), "vr_comm_composite_partials: up to %zu partials this frame but max_partials = %zu "
+             "(exchange %u aborted on all ranks)", ctx->n_partials_host, c.max_partials, c.pepoch);
     ctx->err = buf;
+    ctx->n_partials_host = 0;
     return VR_ERR_NOMEM;
   }
-  cudaSetDevice(ctx->device);
   vr_status st = ensure_partial_scratch_pub(ctx, n_pixels, ctx->partial_cap ? ctx->partial_cap : 1);
   if (st != VR_OK) return st;
   const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
@@ -1030,6 +1157,7 @@ static vr_status comm_composite_partials_impl(vr_ctx* ctx, const vr_camera* cam)
   p.off_pout = L.off_pout;
   p.sorted_cap = c.max_partials;
   p.out_cap = c.max_pixels;
+  p.timeout_ns = c.timeout_ns;
   p.off_canvas_rgba = L.off_canvas_rgba;
   p.off_canvas_depth = L.off_canvas_depth;
   const int grid = ctx->sm_count * 4;
@@ -1060,7 +1188,7 @@ static vr_status comm_composite_partials_impl(vr_ctx* ctx, const vr_camera* cam)
   Flags* f = reinterpret_cast<Flags*>(c.arena + L.off_flags);
   if (c.rank == 0)
   {
-    wait_done_kernel<<<1, 32, 0, ctx->stream>>>(f->p_done, c.size, c.pepoch);
+    wait_done_kernel<<<1, 32, 0, ctx->stream>>>(f, f->p_done, c.size, c.pepoch, kPathPartials, c.timeout_ns);
     ctx->launches++;
     // root-only result (PartialCompositor.cpp:580-595): the read side now sees the composited list
     // (fused canvas mode: the pixels went straight to the canvas, the list is empty)
@@ -1130,7 +1258,7 @@ extern "C" vr_status vr_comm_sync_depths(vr_ctx* ctx)
     // every rank has finished pulling the previous broadcast before the staging copy is replaced
     if (c.sepoch > 1)
     {
-      wait_done_kernel<<<1, 32, 0, ctx->stream>>>(root_flags->s_done, c.size, c.sepoch - 1);
+      wait_done_kernel<<<1, 32, 0, ctx->stream>>>(root_flags, root_flags->s_done, c.size, c.sepoch - 1, kPathImage, c.timeout_ns);
       ctx->launches++;
     }
     cudaError_t e = cudaMemcpyAsync(staged, ctx->canvas_depth, n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream);
@@ -1142,7 +1270,7 @@ extern "C" vr_status vr_comm_sync_depths(vr_ctx* ctx)
   {
     Flags* my_flags = reinterpret_cast<Flags*>(c.arena + L.off_flags);
     sync_pull_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(root_flags, my_flags, staged, ctx->canvas_depth, n,
-                                                                 c.rank, c.sepoch);
+                                                                 c.rank, c.sepoch, c.timeout_ns);
     ctx->launches++;
   }
   cudaError_t e = cudaGetLastError();
@@ -1160,14 +1288,7 @@ extern "C" vr_status vr_comm_layers_composite_to_canvas(vr_ctx* ctx, const vr_ca
     return cfail(ctx, VR_ERR_STATE, "vr_comm_layers_composite_to_canvas: call vr_layers_begin (after vr_comm_connect) first", cudaSuccess);
   if ((size_t)ctx->lW * ctx->lH > c.max_pixels)
     return cfail(ctx, VR_ERR_INVALID, "vr_comm_layers_composite_to_canvas: frame larger than max_pixels", cudaSuccess);
-  if (ctx->ltab_host->n > kMaxSmemLayers / c.size)
-  {
-    char buf[160];
-    snprintf(buf, sizeof(buf), "vr_comm_layers_composite_to_canvas: %d layers on this rank, at most %d with %d ranks",
-             ctx->ltab_host->n, kMaxSmemLayers / c.size, c.size);
-    ctx->err = buf;
-    return VR_ERR_INVALID;
-  }
+  const bool too_many = ctx->ltab_host->n > kMaxSmemLayers / c.size;
   cudaSetDevice(ctx->device);
   const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
   c.lepoch += 1;
@@ -1190,6 +1311,7 @@ extern "C" vr_status vr_comm_layers_composite_to_canvas(vr_ctx* ctx, const vr_ca
   p.H = ctx->lH;
   p.clear = 1;
   p.smem_layers = kMaxSmemLayers;
+  p.timeout_ns = c.timeout_ns;
   for (int r = 0; r < c.size; ++r)
   {
     p.table[r] = reinterpret_cast<const LayerTable*>(c.peer[r] + L.off_ltab[par]);
@@ -1200,13 +1322,30 @@ extern "C" vr_status vr_comm_layers_composite_to_canvas(vr_ctx* ctx, const vr_ca
   p.canvas_rgba = reinterpret_cast<float4*>(c.peer[0] + L.off_canvas_rgba);
   p.canvas_depth = reinterpret_cast<float*>(c.peer[0] + L.off_canvas_depth);
   fill_to_canvas_params_pub(cam, ctx->lW, ctx->lH, p.tp);
+  if (too_many || c.frame_poisoned)
+  {
+    // rank-local error (too many layers here, or a layer of this frame did not fit the arena pool): the
+    // peers are inside this exchange already -- release them instead of leaving them to the time limit
+    launch_layers_abort(p, ctx->stream);
+    ctx->launches++;
+    char buf[200];
+    if (too_many)
+      snprintf(buf, sizeof(buf), "vr_comm_layers_composite_to_canvas: %d layers on this rank, at most %d with %d ranks "
+               "(exchange %u aborted on all ranks)", ctx->ltab_host->n, kMaxSmemLayers / c.size, c.size, c.lepoch);
+    else
+      snprintf(buf, sizeof(buf), "vr_comm_layers_composite_to_canvas: a layer of this frame did not fit max_partials "
+               "(exchange %u aborted on all ranks)", c.lepoch);
+    ctx->err = buf;
+    c.frame_poisoned = false;
+    ctx->lW = ctx->lH = 0;
+    return VR_ERR_INVALID;
+  }
   cudaError_t e = launch_layers_fold(p, true, ctx->sm_count, ctx->stream);
   if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "layers_fold launch", e);
   ctx->launches++;
   if (c.rank == 0)
   {
-    const LayerFlags* f = reinterpret_cast<const LayerFlags*>(c.arena + L.off_lflags);
-    e = launch_layers_wait_done(f->done, c.size, c.lepoch, ctx->stream);
+    e = launch_layers_wait_done(c.arena + L.off_lflags, c.size, c.lepoch, c.timeout_ns, ctx->stream);
     if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "layers wait launch", e);
     ctx->launches++;
   }

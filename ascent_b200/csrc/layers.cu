@@ -37,17 +37,6 @@ constexpr int kMaxTileLayers = 192;              // layers overlapping one tile 
 constexpr int kMaxSeg = 32;                      // entries per pixel ordered in local memory
 constexpr int kBatch = 8;                        // layer entries requested together per pixel
 
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v)
-{
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p)
-{
-  unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
 __device__ __forceinline__ void blend(float4& a, const float4 o)
 {
   // VolumePartial::blend, VolumePartial.hpp:86-95 (rgb in xyz, alpha in w)
@@ -82,6 +71,7 @@ __global__ void __launch_bounds__(kTileW* kTileH) layers_fold_kernel(const __gri
   __shared__ int s_ntile;
   __shared__ int s_total;
 
+  bool go = true; // false: a peer aborted this exchange (or never showed up): fold nothing, still report "done"
   if (COMM)
   {
     LayerFlags* my_flags = reinterpret_cast<LayerFlags*>(P.flags[P.rank]);
@@ -91,9 +81,8 @@ __global__ void __launch_bounds__(kTileW* kTileH) layers_fold_kernel(const __gri
       __threadfence_system();
       st_release_sys(&f->ready[P.rank], P.epoch);
     }
-    if (threadIdx.x < P.size)
-      while (ld_acquire_sys(&my_flags->ready[threadIdx.x]) < P.epoch) __nanosleep(64);
-    __syncthreads();
+    go = wait_all_ready(reinterpret_cast<ExchangeError*>(my_flags->err), my_flags->ready, my_flags->aborted, 2u, P.size,
+                        P.epoch, P.timeout_ns, 64);
   }
 
   // ---- every rank's layer table into shared memory (once per CTA)
@@ -103,7 +92,7 @@ __global__ void __launch_bounds__(kTileW* kTileH) layers_fold_kernel(const __gri
     for (int r = 0; r < P.size; ++r)
     {
       s_first[r] = total;
-      int n = P.table[r]->n;
+      int n = go ? P.table[r]->n : 0;
       if (n > kMaxLayers) n = kMaxLayers;
       if (total + n > P.smem_layers) n = P.smem_layers - total; // flagged on the host side
       total += n;
@@ -342,10 +331,31 @@ __global__ void __launch_bounds__(kTileW* kTileH) layers_fold_kernel(const __gri
   }
 }
 
-__global__ void layers_wait_done_kernel(const unsigned int* done, int size, unsigned int epoch)
+__global__ void layers_wait_done_kernel(LayerFlags* f, int size, unsigned int epoch, unsigned long long timeout_ns)
 {
-  if (threadIdx.x < size)
-    while (ld_acquire_sys(done + threadIdx.x) < epoch) __nanosleep(64);
+  if (threadIdx.x < size && !wait_epoch(f->done + threadIdx.x, epoch, timeout_ns, 64))
+    report_error(reinterpret_cast<ExchangeError*>(f->err), epoch, 2u, 1u, threadIdx.x);
+}
+
+// layer-path form of comm.cu's abort_announce_kernel
+__global__ void layers_abort_kernel(LayerFoldParams P)
+{
+  const int t = threadIdx.x;
+  if (t < P.size)
+  {
+    LayerFlags* f = reinterpret_cast<LayerFlags*>(P.flags[t]);
+    ((volatile unsigned int*)f->aborted)[P.rank] = P.epoch;
+    __threadfence_system();
+    st_release_sys(&f->ready[P.rank], P.epoch);
+  }
+  if (t == 0)
+  {
+    LayerFlags* root = reinterpret_cast<LayerFlags*>(P.flags[0]);
+    __threadfence_system();
+    st_release_sys(&root->done[P.rank], P.epoch);
+    report_error(reinterpret_cast<ExchangeError*>(reinterpret_cast<LayerFlags*>(P.flags[P.rank])->err), P.epoch, 2u, 2u,
+                 P.rank);
+  }
 }
 
 // layers -> the reference's compact list (StructuredWrapper::render :260-283), for callers that
@@ -397,13 +407,9 @@ __global__ void layers_to_partials_kernel(const LayerTable* __restrict__ table,
 cudaError_t launch_layers_fold(const LayerFoldParams& p, bool comm, int sm_count, cudaStream_t s)
 {
   const size_t smem = (size_t)p.smem_layers * sizeof(LayerDesc);
-  static bool attr_set = false;
-  if (!attr_set)
-  {
-    cudaFuncSetAttribute(layers_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(layers_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_set = true;
-  }
+  // per device, not per process (a process may hold contexts on several GPUs): cheap enough to set per launch
+  if (comm) cudaFuncSetAttribute(layers_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  else cudaFuncSetAttribute(layers_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   // (the kernel restricts itself to the layers' bounding box; the full frame bounds the grid)
   const long long tiles = (long long)((p.W + kTileW - 1) / kTileW) * ((p.H + kTileH - 1) / kTileH);
   // persistent grid: exactly the CTAs that are resident at once (registers and the table's smem decide)
@@ -419,9 +425,16 @@ cudaError_t launch_layers_fold(const LayerFoldParams& p, bool comm, int sm_count
   return cudaGetLastError();
 }
 
-cudaError_t launch_layers_wait_done(const unsigned int* done, int size, unsigned int epoch, cudaStream_t s)
+cudaError_t launch_layers_wait_done(unsigned char* flags, int size, unsigned int epoch, unsigned long long timeout_ns,
+                                    cudaStream_t s)
 {
-  layers_wait_done_kernel<<<1, 32, 0, s>>>(done, size, epoch);
+  layers_wait_done_kernel<<<1, 32, 0, s>>>(reinterpret_cast<LayerFlags*>(flags), size, epoch, timeout_ns);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_layers_abort(const LayerFoldParams& p, cudaStream_t s)
+{
+  layers_abort_kernel<<<1, 32, 0, s>>>(p);
   return cudaGetLastError();
 }
 

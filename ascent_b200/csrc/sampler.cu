@@ -130,6 +130,22 @@ __device__ __forceinline__ void clear_chunk(const TraceParams& P, unsigned chunk
   }
 }
 
+// MODE 5 (pushed frame): the quantised pixel does not stay on this GPU -- it is stored straight into
+// the receive slot [owner of the pixel's 1024-pixel chunk][this rank] of the exchange (comm.cu), a
+// posted NVLink store (a local one for the chunks this rank owns itself), so that the fold kernel
+// later reads local memory only.
+__device__ __forceinline__ void push_pixel(const TraceParams& P, long long pixel, uchar4 q, float depth)
+{
+  const unsigned px = (unsigned)pixel;
+  const unsigned chunk = px >> 10;
+  const unsigned turn = chunk / (unsigned)P.push_size;
+  const unsigned owner = chunk - turn * (unsigned)P.push_size;
+  const size_t at = (size_t)P.push_rank * P.push_share_px + (size_t)turn * 1024u + (px & 1023u);
+  unsigned char* base = P.push_peers[owner];
+  reinterpret_cast<uchar4*>(base + P.push_off_rgba)[at] = q;
+  reinterpret_cast<float*>(base + P.push_off_depth)[at] = depth;
+}
+
 // the state of "the cell the ray is in": corner scalars in the pre-differenced form the
 // reference keeps them in, the cell's lower-left point and inverse spacing
 struct Cell
@@ -428,7 +444,7 @@ trace_kernel(const __grid_constant__ TraceParams P)
         P.canvas_depth[pixel] = depth;
         P.canvas_rgba[pixel] = out;
       }
-      if (MODE == 2)
+      if (MODE == 2 || MODE == 5)
       {
         // ---------------- K7 over a cleared canvas (in = 0), fused with Image::Init
         // (Image.hpp:80-113: truncating uint8, depth < 0 -> |d|) and, for a single rank,
@@ -446,16 +462,23 @@ trace_kernel(const __grid_constant__ TraceParams P)
         out.w = fminf(1.f, fmaxf(0.f * a + c3, 0.f));
         const uchar4 q = make_uchar4(quant_u8(out.x), quant_u8(out.y), quant_u8(out.z), quant_u8(out.w));
         depth = depth < 0.f ? fabsf(depth) : depth;
-        P.img_rgba[pixel] = q;
-        P.img_depth[pixel] = depth;
-        if (P.write_canvas)
+        if (MODE == 5)
+          push_pixel(P, pixel, q, depth);
+        else
         {
-          const float k = 1.f / 255.f;
-          P.canvas_rgba[pixel] = make_float4((float)q.x * k, (float)q.y * k, (float)q.z * k, (float)q.w * k);
-          P.canvas_depth[pixel] = depth;
+          P.img_rgba[pixel] = q;
+          P.img_depth[pixel] = depth;
+          if (P.write_canvas)
+          {
+            const float k = 1.f / 255.f;
+            P.canvas_rgba[pixel] = make_float4((float)q.x * k, (float)q.y * k, (float)q.z * k, (float)q.w * k);
+            P.canvas_depth[pixel] = depth;
+          }
         }
       }
     } // in_subset
+    else if (MODE == 5 && in_rect)
+      push_pixel(P, pixel, make_uchar4(0, 0, 0, 0), 1.001f); // the widened rectangle's padding columns
     else if (MODE == 2 && in_rect)
     {
       P.img_rgba[pixel] = make_uchar4(0, 0, 0, 0);
@@ -521,6 +544,7 @@ cudaError_t launch_mode(const TraceParams& p, int mode, int grid, cudaStream_t s
   else if (mode == 1) trace_kernel<KIND, FT, ASSOC, 1, IDX><<<grid, kThreads, 0, s>>>(p);
   else if (mode == 2) trace_kernel<KIND, FT, ASSOC, 2, IDX><<<grid, kThreads, 0, s>>>(p);
   else if (mode == 4) trace_kernel<KIND, FT, ASSOC, 4, IDX><<<grid, kThreads, 0, s>>>(p);
+  else if (mode == 5) trace_kernel<KIND, FT, ASSOC, 5, IDX><<<grid, kThreads, 0, s>>>(p);
   else                trace_kernel<KIND, FT, ASSOC, 3, IDX><<<grid, kThreads, 0, s>>>(p);
   return cudaGetLastError();
 }

@@ -46,6 +46,8 @@ static vr_status fail(vr_ctx* c, vr_status st, const char* fmt, ...)
 
 static vr_status ensure_frame(vr_ctx* ctx, int W, int H);
 namespace vr { vr_status comm_ahead_image(vr_ctx* ctx, uchar4** rgba, float** depth); } // comm.cu
+namespace vr { vr_status comm_push_target(vr_ctx* ctx, bool ahead, int width, int height, vr::TraceParams& p); }
+namespace vr { vr_status comm_check_errors(vr_ctx* ctx); }
 static void fill_to_canvas_params(const vr_camera* cam, int W, int H, ToCanvasParams& tp);
 
 // ================================================================= context
@@ -188,7 +190,7 @@ extern "C" vr_status vr_synchronize(vr_ctx* ctx)
 {
   VR_ENTER_RO(ctx);
   CK(cudaStreamSynchronize(ctx->stream));
-  return VR_OK;
+  return comm_check_errors(ctx); // an exchange that timed out / was aborted by a peer is reported here
 }
 
 extern "C" uint64_t vr_kernel_launches(const vr_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -457,11 +459,23 @@ static vr_status ensure_frame(vr_ctx* ctx, int W, int H)
       CK(cudaMalloc(&ctx->res_depth, n * sizeof(float)));
     }
     ctx->cap_pixels = n;
+    // fresh, uninitialised buffers: nothing about their contents may be assumed any more
+    ctx->comm.clean_canvas.valid = false;
+    ctx->comm.clean_res[0].valid = ctx->comm.clean_res[1].valid = false;
   }
   if (ctx->comm.on)
   {
     vr_status st = comm_bind_frame(ctx, n);
     if (st != VR_OK) return st;
+  }
+  if (W != ctx->W || H != ctx->H)
+  {
+    // a frame traced ahead belongs to the pending exchange's size: changing it now would hand that
+    // exchange the wrong pixel count
+    REQUIRE(!ctx->img_ahead, "frame size changed (%dx%d -> %dx%d) while a frame traced ahead is pending", ctx->W,
+            ctx->H, W, H);
+    ctx->comm.clean_canvas.valid = false;
+    ctx->comm.clean_res[0].valid = ctx->comm.clean_res[1].valid = false;
   }
   ctx->W = W;
   ctx->H = H;
@@ -501,7 +515,7 @@ extern "C" vr_status vr_canvas_download(vr_ctx* ctx, float* rgba, float* depth)
   if (rgba) CK(cudaMemcpyAsync(rgba, ctx->canvas_rgba, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
   if (depth) CK(cudaMemcpyAsync(depth, ctx->canvas_depth, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  return VR_OK;
+  return comm_check_errors(ctx);
 }
 
 extern "C" vr_status vr_canvas_blend_background(vr_ctx* ctx, const float bg_rgba[4])
@@ -704,20 +718,30 @@ extern "C" vr_status vr_trace_to_image(vr_ctx* ctx, int block_id, const vr_camer
     st = comm_ahead_image(ctx, &p.img_rgba, &p.img_depth);
     if (st != VR_OK) return st;
   }
+  const bool push = (flags & VR_FRAME_PUSH) != 0;
+  if (push)
+  {
+    // the image is scattered to the exchange's owners as it is produced (sampler mode 5)
+    REQUIRE(!(flags & VR_FRAME_WRITE_CANVAS), "vr_trace_to_image: VR_FRAME_PUSH cannot write the canvas");
+    REQUIRE(p.vec_ok, "vr_trace_to_image: VR_FRAME_PUSH needs a width that is a multiple of 4");
+    st = comm_push_target(ctx, ahead, width, height, p);
+    if (st != VR_OK) return st;
+  }
   p.write_canvas = (flags & VR_FRAME_WRITE_CANVAS) ? 1 : 0;
   // (a width that is not a multiple of 4 has no announced rectangle -- the exchange reads the whole
   // image -- so such frames are always cleared)
-  p.n_clear_chunks = ((flags & VR_FRAME_NO_CLEAR) && p.vec_ok) ? 0 : (int)(((size_t)width * height + 511) / 512);
+  p.n_clear_chunks = (((flags & VR_FRAME_NO_CLEAR) && p.vec_ok) || push) ? 0 : (int)(((size_t)width * height + 511) / 512);
   st = stage_for_trace(ctx, block_id, p, ctx->stream, ctx->tile_counter, true);
   if (st != VR_OK) return st;
-  CK(launch_trace(p, 2, ctx->sm_count, ctx->stream));
+  CK(launch_trace(p, push ? 5 : 2, ctx->sm_count, ctx->stream));
   ctx->launches++;
   // what the multi-GPU fold needs to know: outside this rectangle my image is empty
   int* rect = ahead ? ctx->img_rect_ahead : ctx->img_rect;
   rect[0] = p.tx0; rect[1] = p.sy;
   rect[2] = p.tx1; rect[3] = p.sy + p.sh;
   if (p.sw <= 0 || p.sh <= 0) rect[0] = rect[1] = rect[2] = rect[3] = 0;
-  if (ahead) ctx->img_ahead = true;
+  if (ahead) { ctx->img_ahead = true; ctx->img_pushed_ahead = push; }
+  else ctx->img_pushed = push;
   return VR_OK;
 }
 
@@ -858,8 +882,14 @@ namespace vr { vr_status comm_bind_layers(vr_ctx* ctx); }
 static vr_status ensure_layer_pool(vr_ctx* ctx, size_t need)
 {
   if (need <= ctx->lpool_cap) return VR_OK;
-  REQUIRE(!ctx->layers_in_arena, "ray layers need %zu entries this frame but max_partials = %zu (vr_comm_init)",
-          need, ctx->lpool_cap);
+  if (ctx->layers_in_arena)
+  {
+    // rank-local failure inside a collective frame: remember it, so that this rank's call of the layer
+    // exchange releases its peers (abort) instead of leaving them waiting
+    ctx->comm.frame_poisoned = true;
+    return fail(ctx, VR_ERR_INVALID, "ray layers need %zu entries this frame but max_partials = %zu (vr_comm_init)", need,
+                ctx->lpool_cap);
+  }
   const size_t cap = std::max(need, ctx->lpool_cap * 2);
   float4* nr = nullptr;
   float* nd = nullptr;
@@ -1083,6 +1113,7 @@ extern "C" vr_status vr_image_download(vr_ctx* ctx, uint8_t* rgba, float* depth)
 {
   VR_ENTER_RO(ctx);
   REQUIRE(ctx->W > 0, "vr_image_download: no image yet");
+  REQUIRE(!ctx->img_pushed, "vr_image_download: the pending image was pushed to the exchange (VR_FRAME_PUSH)");
   const size_t n = (size_t)ctx->W * ctx->H;
   if (rgba) CK(cudaMemcpyAsync(rgba, ctx->img_rgba, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   if (depth) CK(cudaMemcpyAsync(depth, ctx->img_depth, n * 4, cudaMemcpyDeviceToHost, ctx->stream));

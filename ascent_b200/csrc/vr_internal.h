@@ -61,6 +61,13 @@ struct TraceParams
   vr_partial* partials;
   unsigned long long* partial_count;
   unsigned long long partial_capacity;
+  // pushed frame (mode 5): the exchange's receive slots on every rank (comm.cu).  Pixel p of this
+  // rank's image goes to rank (p / 1024) % push_size, slot entry
+  // push_rank * push_share_px + (p / 1024 / push_size) * 1024 + p % 1024
+  unsigned char* const* push_peers; // device table of arena base pointers
+  unsigned long long push_off_rgba, push_off_depth; // byte offsets of the receive ring slot inside an arena
+  unsigned int push_share_px;       // pixels per (owner, source) slot
+  int push_rank, push_size;
   // demand staging pre-pass (mode 4): one byte per 128-byte line of the field
   unsigned char* mark;
   // dynamic tile scheduler + sample counter
@@ -102,6 +109,8 @@ struct Comm
   unsigned int pepoch = 0;                      // partial path frames
   unsigned int lepoch = 0;                      // layer path frames
   unsigned int sepoch = 0;                      // depth broadcasts
+  unsigned long long timeout_ns = 0;            // bound of every cross-rank wait inside the kernels
+  bool frame_poisoned = false;                  // a rank-local error hit this frame: the next collective aborts
   // rank 0: "this buffer holds the cleared value outside the rectangle kept in the arena flags",
   // valid while api_serial has not moved and the frame size is the same
   struct Clean { bool valid = false; uint64_t serial = 0; int W = 0, H = 0; };
@@ -147,6 +156,8 @@ struct vr_ctx
   bool img_in_arena = false;
   bool canvas_in_arena = false;
   int img_rect[4] = { 0, 0, 0x7fffffff, 0x7fffffff }; // where the quantised image may be non-empty
+  // the pending / ahead image was pushed into the owners' receive slots (VR_FRAME_PUSH, sampler mode 5)
+  bool img_pushed = false, img_pushed_ahead = false;
   // an image traced one frame ahead of the pending exchange (VR_FRAME_AHEAD) and its rectangle
   bool img_ahead = false;
   int img_rect_ahead[4] = { 0, 0, 0x7fffffff, 0x7fffffff };
@@ -242,6 +253,79 @@ struct ToCanvasParams
   int W, H;
 };
 #ifdef __CUDACC__
+// ---- cross-GPU flag protocol of the exchange kernels (comm.cu, layers.cu): system-scope release /
+// acquire on epoch counters in the peers' arenas, every wait bounded in time
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v)
+{
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p)
+{
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until *flag >= epoch; gives up after timeout_ns (0 = never) so that a peer that died or bailed
+// out with a rank-local error cannot hang this GPU
+__device__ __forceinline__ bool wait_epoch(const unsigned int* flag, unsigned int epoch, unsigned long long timeout_ns,
+                                           unsigned sleep_ns = 32)
+{
+  if (ld_acquire_sys(flag) >= epoch) return true;
+  const unsigned long long t0 = global_ns();
+  for (;;)
+  {
+    __nanosleep(sleep_ns);
+    if (ld_acquire_sys(flag) >= epoch) return true;
+    if (timeout_ns && global_ns() - t0 > timeout_ns) return false;
+  }
+}
+// what an exchange kernel leaves for the host when it could not complete: the first failing epoch,
+// the reason (1 = a wait ran into the time limit, 2 = a peer aborted the exchange) and the peer
+struct ExchangeError
+{
+  unsigned int epoch, path, reason, peer;
+};
+__device__ __forceinline__ void report_error(ExchangeError* e, unsigned epoch, unsigned path, unsigned reason, unsigned peer)
+{
+  if (atomicCAS(&e->epoch, 0u, epoch) == 0u)
+  {
+    e->path = path;
+    e->reason = reason;
+    e->peer = peer;
+  }
+}
+// the wait of an exchange kernel's prologue: thread r < size waits for rank r's ready flag of `epoch`
+// and checks that r did not abort it; returns (block-wide) whether the exchange can go ahead
+__device__ __forceinline__ bool wait_all_ready(ExchangeError* err, const unsigned int* ready, const unsigned int* aborted,
+                                               unsigned path, int size, unsigned epoch, unsigned long long timeout_ns,
+                                               unsigned sleep_ns = 32)
+{
+  __shared__ int s_bad;
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+  if ((int)threadIdx.x < size)
+  {
+    if (!wait_epoch(ready + threadIdx.x, epoch, timeout_ns, sleep_ns))
+    {
+      s_bad = 1;
+      report_error(err, epoch, path, 1u, threadIdx.x);
+    }
+    else if (((volatile const unsigned int*)aborted)[threadIdx.x] == epoch)
+    {
+      s_bad = 1;
+      report_error(err, epoch, path, 2u, threadIdx.x);
+    }
+  }
+  __syncthreads();
+  return s_bad == 0;
+}
+
 // one pixel of partials_to_canvas (VolumeRenderer.cpp:287-391): recompute the ray like K1 (with the
 // reference's delta_y-from-ru quirk baked into T by the host), project origin + depth*dir, blend
 // the partial over the canvas value `in`
@@ -310,6 +394,8 @@ struct LayerFlags
   unsigned int ready[kMaxCommRanks];
   unsigned int done[kMaxCommRanks];
   unsigned int cta_done;
+  unsigned int aborted[kMaxCommRanks]; // rank r aborted layer exchange <epoch> (rank-local error)
+  unsigned int err[4];                 // ExchangeError of this rank's layer exchanges
 };
 struct LayerFoldParams
 {
@@ -325,9 +411,12 @@ struct LayerFoldParams
   float4* canvas_rgba; // where finished pixels go (rank 0's canvas)
   float* canvas_depth;
   ToCanvasParams tp;
+  unsigned long long timeout_ns; // bound of every cross-rank wait (0 = none)
 };
 cudaError_t launch_layers_fold(const LayerFoldParams& p, bool comm, int sm_count, cudaStream_t s);
-cudaError_t launch_layers_wait_done(const unsigned int* done, int size, unsigned int epoch, cudaStream_t s);
+cudaError_t launch_layers_wait_done(unsigned char* flags, int size, unsigned int epoch, unsigned long long timeout_ns,
+                                    cudaStream_t s);
+cudaError_t launch_layers_abort(const LayerFoldParams& p, cudaStream_t s);
 cudaError_t launch_layers_to_partials(const LayerTable* table, int n_layers, const float4* pool_rgba,
                                       const float* pool_depth, int W, vr_partial* out,
                                       unsigned long long* count, size_t cap, cudaStream_t s);
@@ -349,6 +438,12 @@ struct FoldP2PParams
   // rank 0: the result image of this parity / the canvas are known to be cleared outside the
   // rectangle the previous exchange left in the flags -> only that rectangle needs clearing again
   int track_res, track_canvas;
+  // my image of this epoch was pushed into the owners' receive slots (sampler mode 5); a receive slot
+  // holds share_groups 4-pixel groups per source rank, at off_recv_* of the owner's arena
+  int pushed;
+  size_t share_groups;
+  size_t off_recv_rgba, off_recv_depth;
+  unsigned long long timeout_ns; // bound of every cross-rank wait (0 = none)
 };
 cudaError_t launch_fold_p2p(const FoldP2PParams& p, int sm_count, cudaStream_t s);
 } // namespace vr

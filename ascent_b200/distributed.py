@@ -169,11 +169,16 @@ def run_bench(args, wl, bench):
     vis_all, _ = global_visibility_order([sp["bounds"][i] for i in mine], cam, dist)
     vis_rank = np.ascontiguousarray(vis_all[:, 0], np.int32)  # path A: one domain per rank
 
+    # path A: the sampler's epilogue stores every finished pixel straight into its owner's receive slot
+    # (VR_FRAME_PUSH), so the exchange folds from local memory; VR_PUSH=0 keeps the image local (pull)
+    use_push = os.environ.get("VR_PUSH", "1") == "1" and W % 4 == 0
+
     def render(ahead=False):
         if path_a:
             # Canvas::Clear + RenderCells + Image::Init in one launch, straight into the exchange arena
             # (ahead: into the next slot of the image ring, see VR_FRAME_AHEAD)
-            ctx.trace_to_image(mine[0], cam, W, H, sp["sample_dist"], rmin, rmax, no_clear=True, ahead=ahead)
+            ctx.trace_to_image(mine[0], cam, W, H, sp["sample_dist"], rmin, rmax, no_clear=True, ahead=ahead,
+                               push=use_push)
         else:
             ctx.layers_begin(W, H)
             ctx.trace_blocks_to_layers(mine, cam, sp["sample_dist"], rmin, rmax, False)
@@ -348,7 +353,9 @@ def run_bench(args, wl, bench):
                 "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": cfg,
-                "details": {"exchange": "P2P direct-send fold (uint8 images)" if path_a else
+                "details": {"exchange": ("P2P direct-send fold (uint8 images, %s)" % (
+                                             "pushed by the sampler into the owners' receive slots" if use_push
+                                             else "pulled from the peers' arenas")) if path_a else
                                         "P2P gather + fold of dense ray layers (float partials)",
                             "blocks_per_gpu": len(mine),
                             "order": ("pipelined: trace(k+1) issued before exchange(k) (VR_FRAME_AHEAD)" if use_piped

@@ -86,7 +86,10 @@ VR_API uint64_t vr_kernel_launches(const vr_ctx* ctx);
  * SetInput :868-907).  dims are POINT dims, x fastest: index (k*ny + j)*nx + i.  A cell field
  * has (nx-1)(ny-1)(nz-1) values.  The field is copied (or adopted, see below) once per publish
  * and reused by every render of the batch.
- *   where == VR_HOST   : `field` is host memory, copied to the device.
+ *   where == VR_HOST   : `field` is host memory, copied to the device (cudaMemcpyAsync on the
+ *                        context's stream: a page-locked array must stay valid and unchanged until the
+ *                        next synchronising call -- vr_synchronize or any entry point that fills host
+ *                        memory; pageable memory is staged by the runtime before the call returns).
  *   where == VR_DEVICE : `field` is device memory on this GPU and is used in place (zero copy;
  *                        must outlive the block).
  *   where == VR_HOST_MAPPED : `field` is page-locked, device-mapped host memory (the simulation's
@@ -171,8 +174,14 @@ VR_API vr_status vr_render_image(vr_ctx* ctx, int block_id, const vr_camera* cam
  * vr_comm_composite_images call is still to come -- it goes to the next slot of the rank's image ring
  * and becomes the pending image once that exchange has been issued.  Lets the renders of a batch
  * (Scene.cpp:133-149) be software-pipelined: trace(k+1), exchange(k), trace(k+2), exchange(k+1), ... so
- * that no rank idles in an exchange while it could be tracing.  At most one frame may be ahead.    */
-enum { VR_FRAME_WRITE_CANVAS = 1, VR_FRAME_NO_CLEAR = 2, VR_FRAME_AHEAD = 4 };
+ * that no rank idles in an exchange while it could be tracing.  At most one frame may be ahead.
+ * VR_FRAME_PUSH (multi-GPU, after vr_comm_connect; implies NO_CLEAR; width % 4 == 0): every finished
+ * pixel is stored straight into the exchange's receive slot on the GPU that owns the pixel (posted
+ * NVLink stores from the sampler's epilogue, 8 bytes per pixel of the block's screen rectangle)
+ * instead of into this rank's own image, so that vr_comm_composite_images folds from local memory
+ * only -- no NVLink load round trips in the exchange.  The rank's own image is then not available to
+ * vr_image_download.  Ranks may mix pushed and unpushed images within one exchange.            */
+enum { VR_FRAME_WRITE_CANVAS = 1, VR_FRAME_NO_CLEAR = 2, VR_FRAME_AHEAD = 4, VR_FRAME_PUSH = 8 };
 VR_API vr_status vr_trace_to_image(vr_ctx* ctx, int block_id, const vr_camera* cam, int width,
                                    int height, float sample_dist, float range_min, float range_max,
                                    int flags);
@@ -277,7 +286,12 @@ VR_API vr_status vr_composite_partials(vr_ctx* ctx, const vr_partial* in, size_t
  * max_pixels / max_partials size the arena (largest frame; longest per-rank partial list, resp.
  * the sum over a rank's blocks of (screen-rectangle area + 4) when ray layers are used; 0
  * partials = image path only) and MUST be identical on every rank: a rank addresses its peers'
- * arenas with its own layout (vr_comm_connect checks and fails otherwise).                     */
+ * arenas with its own layout (vr_comm_connect checks and fails otherwise).
+ * Failure behaviour of the collectives: every cross-GPU wait inside the exchange kernels is bounded
+ * (20 s; VR_COMM_TIMEOUT_MS overrides, 0 = unbounded), and a rank that hits a rank-local error in a
+ * collective call (its partial list or layers do not fit the arena, ...) returns that error AND
+ * releases its peers: their kernels skip the frame and their next synchronising call
+ * (vr_synchronize, vr_canvas_download) returns VR_ERR_STATE naming the exchange and the rank.      */
 #define VR_IPC_HANDLE_BYTES 64
 VR_API vr_status vr_comm_init(vr_ctx* ctx, int rank, int n_ranks, size_t max_pixels,
                               size_t max_partials, void* handle_out /* VR_IPC_HANDLE_BYTES */);

@@ -10,6 +10,7 @@ _ref/libapcomp_ref.so = the reference's own apcomp sources (src/libs/apcomp/*.cp
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -47,7 +48,8 @@ def build(force=False):
     older than its sources."""
     have = os.path.exists(os.path.join(_HERE, "liboracle.so"))
     try:
-        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+        # (make's chatter goes to stderr: bench.py's stdout is one JSON line)
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []), stdout=sys.stderr)
     except (OSError, subprocess.CalledProcessError):
         if not have:
             raise

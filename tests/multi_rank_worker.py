@@ -1,9 +1,15 @@
 """Worker run under ``python -m torch.distributed.run`` by test_multi_rank.py.
 
 mode "host" (gloo, CPU): the host-side plumbing of ascent_b200.distributed against the oracle.
-mode "gpu"  (nccl, one GPU per rank): sort-last path A (uint8 images, P2P fold) and path B (float
-partials, P2P pull+merge+fold) against the oracle at the same rank/block layout (SURVEY 8(d):
-"parity is always vs the oracle at the same layout").  Exit code 0 = all checks passed."""
+mode "gpu"  (nccl, one GPU per rank): sort-last path A (uint8 images, P2P fold, pulled and pushed) and
+path B (float partials, P2P pull+merge+fold; ray layers) against the oracle at the same rank/block
+layout ("parity is always vs the oracle at the same layout"), the opaque + volume scene,
+and the failure behaviour of the collectives (a rank-local error releases the peers).
+mode "gpu-shared" (gloo for the O(ranks) scalars, EVERY rank on cuda:0): the same checks with the
+ranks' processes time-sharing one GPU -- the exchange arenas are mapped through CUDA IPC exactly as
+across GPUs, so the cross-rank kernels run for real on a one-GPU box.
+With VR_FULL_SIZE=1 (or 8 ranks) BASELINE configs 3 and 5 are also checked at their named sizes.
+Exit code 0 = all checks passed."""
 import os
 import sys
 
@@ -137,6 +143,50 @@ def gpu_checks(rank, world):
             elif not layers:
                 assert ctx.partials_count() == 0  # root-only result
             dist.barrier()
+        # ---------------- a rank-local error inside a collective must not hang the peers: the
+        # last rank overflows max_partials -> it gets the error, everybody else is released, is told so by
+        # its next synchronising call, and the following frame composites normally again
+        if world > 1:
+            cam = sc["cam"]
+            ctx.partials_begin(W, H)
+            reps = 1
+            if rank == world - 1:
+                area = sum(max(1, _lib.find_subset(cam, W, H, sc["bounds"][i])[2] *
+                               _lib.find_subset(cam, W, H, sc["bounds"][i])[3]) for i in mine)
+                reps = (W * H * max(len(o) for o in owners)) // area + 2  # connect() sized the arena for the largest rank
+            for _ in range(reps):
+                for i in mine:
+                    ctx.trace_to_partials(i, cam, sc["sample_dist"], rmin, rmax, False)
+            try:
+                ctx.comm_composite_partials()
+                failed_here = False
+            except _lib.VRError as e:
+                failed_here = True
+                assert "max_partials" in str(e) and "aborted" in str(e), str(e)
+            assert failed_here == (rank == world - 1)
+            try:
+                ctx.synchronize()
+                told = False
+            except _lib.VRError as e:
+                told = True
+                assert "aborted" in str(e) and "rank %d" % (world - 1) in str(e), str(e)
+            assert told, "rank %d was not told that exchange was aborted" % rank
+            dist.barrier()
+            ctx.partials_begin(W, H)
+            for i in mine:
+                ctx.trace_to_partials(i, cam, sc["sample_dist"], rmin, rmax, False)
+            ctx.comm_composite_partials_to_canvas(cam)
+            if rank == 0:
+                rgba, depth = ctx.canvas_download(W, H)
+                o_rgba, o_depth = O.new_canvas(W, H)
+                pl = [O.render_partials(scenes.oracle_block(sc["doms"][i]), cam, W, H, sc["lut"],
+                                        sc["sample_dist"], rmin, rmax, o_depth)
+                      for r in range(world) for i in owners[r]]
+                O.partials_to_canvas(O.composite_partials(pl), cam, W, H, o_rgba, o_depth)
+                assert np.array_equal(rgba, o_rgba), "path B canvas differs after an aborted exchange"
+            else:
+                ctx.synchronize()
+            dist.barrier()
         for i in mine:
             ctx.block_free(i)
 
@@ -208,11 +258,17 @@ def gpu_checks(rank, world):
             order, _ = O.visibility_order(np.array(bounds), c)
             return O.ordered_composite(np.stack(layers), np.stack(depths), order)
 
-        n_frames = 5
+        # frames 3.. are PUSHED (VR_FRAME_PUSH): the sampler stores every pixel into its owner's receive
+        # slot, the fold reads local memory; frame 5 mixes pushed (even ranks) and pulled (odd ranks) images
+        def pushed(k):
+            return k in (3, 4, 6, 7, 8) or (k == 5 and rank % 2 == 0)
+
+        n_frames = 9
         ctx.trace_to_image(0, cam_of(0), W, H, sd, rmin, rmax, no_clear=True)
         for k in range(n_frames):
             if k + 1 < n_frames:
-                ctx.trace_to_image(0, cam_of(k + 1), W, H, sd, rmin, rmax, no_clear=True, ahead=True)
+                ctx.trace_to_image(0, cam_of(k + 1), W, H, sd, rmin, rmax, no_clear=True, ahead=True,
+                                   push=pushed(k + 1))
                 if k == 0:
                     try:   # only one frame may be ahead
                         ctx.trace_to_image(0, cam_of(k + 2), W, H, sd, rmin, rmax, no_clear=True, ahead=True)
@@ -308,6 +364,10 @@ def main():
     if mode == "host":
         dist.init_process_group("gloo")
         host_checks(rank, world)
+    elif mode == "gpu-shared":
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo")
+        gpu_checks(rank, world)
     else:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
         dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))

@@ -26,7 +26,7 @@ def _run(mode, world, timeout):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(HERE, "multi_rank_worker.py"), mode]
-    env = dict(os.environ, OMP_NUM_THREADS="2")
+    env = dict(os.environ, OMP_NUM_THREADS="2", VR_COMM_TIMEOUT_MS=os.environ.get("VR_COMM_TIMEOUT_MS", "8000"))
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "checks OK" in r.stdout
@@ -38,6 +38,15 @@ def test_host_logic_world2_gloo():
 
 def test_host_logic_world4_gloo():
     _run("host", 4, 300)
+
+
+@pytest.mark.gpu
+def test_sort_last_p2p_ranks_sharing_one_gpu():
+    """2 and 3 rank processes time-sharing cuda:0, arenas mapped through CUDA IPC: every cross-rank kernel
+    (pull and push image folds, partial merge, layer fold, z-buffer, depth broadcast, abort protocol) runs
+    against the oracle even on a one-GPU box."""
+    _run("gpu-shared", 2, 900)
+    _run("gpu-shared", 3, 900)
 
 
 @pytest.mark.gpu
