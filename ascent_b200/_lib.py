@@ -35,7 +35,8 @@ SYMBOLS = [
     "vr_image_ptrs",
     "vr_sample_distance", "vr_visibility_order", "vr_find_subset", "vr_synth_braid_dev",
     "vr_camera_default", "vr_camera_reset_to_bounds", "vr_camera_azimuth", "vr_camera_elevation",
-    "vr_camera_zoom", "vr_camera_cinema", "vr_color_table_sample", "vr_correct_opacity",
+    "vr_camera_zoom", "vr_camera_cinema", "vr_color_table_sample", "vr_correct_opacity", "vr_comm_timeline",
+    "vr_comm_join",
 ]
 
 
@@ -139,6 +140,8 @@ def load():
         "vr_camera_cinema": (None, [cam, dp, C.c_float, C.c_float]),
         "vr_color_table_sample": (C.c_int, [C.c_int, C.c_int, dp, fp, C.c_int, dp, fp, C.c_int, vp, fp]),
         "vr_correct_opacity": (C.c_float, [C.c_float, C.c_float]),
+        "vr_comm_timeline": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
+        "vr_comm_join": (C.c_int, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -469,6 +472,14 @@ class Context:
     def comm_connect(self, all_handles):
         buf = (C.c_ubyte * len(all_handles)).from_buffer_copy(all_handles)
         self._ck(self.lib.vr_comm_connect(self.h, buf))
+
+    def comm_join(self):
+        self._ck(self.lib.vr_comm_join(self.h))
+
+    def comm_timeline(self):
+        out = (C.c_uint64 * 16)()
+        self._ck(self.lib.vr_comm_timeline(self.h, out))
+        return [int(x) for x in out]
 
     def comm_composite_images(self, vis_order):
         vo = np.ascontiguousarray(vis_order, np.int32)

@@ -37,11 +37,13 @@ namespace
 {
 constexpr size_t kFlagBytes = 4096;
 constexpr int kMaxRanks = 16;
-// A rank's quantised image of frame e lives in ring slot e % 3.  Two slots would do for strictly
-// alternating render/exchange; the third lets a rank trace frame e+1 BEFORE it joins the exchange of
-// frame e (VR_FRAME_AHEAD): when it later traces frame e+2 into the slot of frame e-1, its own
-// exchange of frame e has passed the all-ranks barrier, so every peer has finished reading e-1.
-constexpr int kImgRing = 3;
+// A rank's quantised image of frame e lives in ring slot e % 4 (its own arena when pulled, the owners'
+// receive slots when pushed).  Two slots would do for strictly alternating render/exchange; the third
+// lets a rank trace frame e+1 BEFORE it issues the exchange of frame e (VR_FRAME_AHEAD); the fourth lets
+// that trace start while the rank's own exchange of frame e-1 is still RUNNING on the exchange stream:
+// frame e+1 reuses the slot of frame e-3, and every peer has finished reading e-3 once this rank's
+// exchange of e-2 -- the one before the latest, which vr_trace_to_image waits for -- has completed.
+constexpr int kImgRing = 4;
 
 struct Flags
 {
@@ -78,6 +80,11 @@ struct Flags
   // (local) first exchange of this rank that did not complete normally: epoch, path, reason
   // (1 = a wait ran into the time limit, 2 = a peer aborted), for the host to report
   unsigned int err_epoch, err_path, err_reason, err_peer;
+  // (diagnostics, VR_TIMELINE=1) globaltimer stamps of the last image exchange on this GPU:
+  // [0] fold kernel entered  [1] all ranks ready  [2] last fold CTA out ("done" released)
+  // [3] to-canvas kernel entered (rank 0)  [4] all ranks done  [5] its CTA 0 finished  [6] end of the last trace
+  // CTA 0 of the fold kernel: [8] prologue done  [9] own chunks folded  [10] rank 0's clears done  [11] fenced + counted
+  unsigned long long timeline[16];
 };
 static_assert(sizeof(Flags) <= 4096, "flag block");
 enum { kPathImage = 0, kPathPartials = 1, kPathLayers = 2 };
@@ -137,15 +144,28 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
     __threadfence_system();
     st_release_sys(&f->ready[P.rank], P.epoch);
   }
+  if (P.timeline && blockIdx.x == 0 && threadIdx.x == 0) my_flags->timeline[0] = global_ns();
   // ---- wait until every rank's image is complete (bounded: a peer that bailed out must not hang us)
   const bool go = wait_all_ready(err_of(my_flags), my_flags->ready, my_flags->aborted[kPathImage], kPathImage, P.size,
                                  P.epoch, P.timeout_ns);
 
+  if (P.timeline && blockIdx.x == 0 && threadIdx.x == 0) my_flags->timeline[1] = global_ns();
+  // ---- everything this CTA needs from the flag block, fetched by different threads at once (these are
+  // system-coherent loads of ~1 us each: one after the other they used to cost more than the fold)
   __shared__ int s_rect[kMaxRanks][4]; // in fold order
+  __shared__ int s_pushed[kMaxRanks];  // in fold order
+  __shared__ int s_clean[2][4];        // rank 0: [0] result image of this parity, [1] canvas
   if (threadIdx.x < P.size * 4)
   {
     const int l = threadIdx.x >> 2, k = threadIdx.x & 3;
     s_rect[l][k] = go ? ((volatile int*)my_flags->img_rect[par][P.order[l]])[k] : 0; // aborted: nothing to fold
+  }
+  else if (threadIdx.x >= 64 && threadIdx.x < 64 + P.size)
+    s_pushed[threadIdx.x - 64] = ((volatile int*)my_flags->img_pushed[par])[P.order[threadIdx.x - 64]];
+  else if (threadIdx.x >= 96 && threadIdx.x < 104 && P.rank == 0)
+  {
+    const int k = threadIdx.x - 96;
+    s_clean[k >> 2][k & 3] = k < 4 ? ((volatile int*)my_flags->clean_res[par])[k] : ((volatile int*)my_flags->clean_canvas)[k - 4];
   }
   __syncthreads();
 
@@ -159,7 +179,7 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
     if (l < P.size)
     {
       const int src = P.order[l];
-      if (((volatile int*)my_flags->img_pushed[par])[src])
+      if (s_pushed[l])
       {
         local_mask |= 1u << l;
         layer_rgba[l] = reinterpret_cast<const uint4*>(P.peers[P.rank] + P.off_recv_rgba) + (size_t)src * P.share_groups;
@@ -179,12 +199,14 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
   const int w4 = P.W >= 4 ? P.W / 4 : 1;
   const size_t n_chunks = (n4 + kChunkGroups - 1) / kChunkGroups;
 
-  auto coverage = [&](size_t i) -> unsigned {
-    const int y = (int)(i / (size_t)w4), x = (int)(i % (size_t)w4) * 4;
+  // group index -> (row, first column); 32-bit arithmetic (n_pixels < 2^31): a 64-bit divide per group
+  // used to cost more than the fold itself
+  const unsigned w4u = (unsigned)w4;
+  auto coverage = [&](unsigned y, unsigned x) -> unsigned {
     unsigned cover = 0;
 #pragma unroll
     for (int l = 0; l < NR; ++l)
-      if (l < P.size && y >= s_rect[l][1] && y < s_rect[l][3] && x >= s_rect[l][0] && x < s_rect[l][2])
+      if (l < P.size && (int)y >= s_rect[l][1] && (int)y < s_rect[l][3] && (int)x >= s_rect[l][0] && (int)x < s_rect[l][2])
         cover |= 1u << l;
     return cover;
   };
@@ -206,13 +228,13 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
     for (int k = 0; k < 4; ++k)
     {
       s_union[k] = u[k];
-      s_dirty[0][k] = P.track_res ? ((volatile int*)my_flags->clean_res[par])[k] : (k < 2 ? 0 : 0x7fffffff);
-      s_dirty[1][k] = P.track_canvas ? ((volatile int*)my_flags->clean_canvas)[k] : (k < 2 ? 0 : 0x7fffffff);
+      s_dirty[0][k] = P.track_res ? s_clean[0][k] : (k < 2 ? 0 : 0x7fffffff);
+      s_dirty[1][k] = P.track_canvas ? s_clean[1][k] : (k < 2 ? 0 : 0x7fffffff);
     }
   }
   __syncthreads();
-  auto write_empty = [&](size_t i) {
-    const int y = (int)(i / (size_t)w4), x = (int)(i % (size_t)w4) * 4;
+  auto write_empty = [&](size_t i, unsigned uy, unsigned ux) {
+    const int y = (int)uy, x = (int)ux;
     if (y >= s_dirty[0][1] && y < s_dirty[0][3] && x >= s_dirty[0][0] && x < s_dirty[0][2])
     {
       out_rgba[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -227,6 +249,7 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
     }
   };
 
+  if (P.timeline && blockIdx.x == 0 && threadIdx.x == 0) my_flags->timeline[8] = global_ns();
   // ---- my chunks: rank, rank + size, rank + 2 size, ... dealt to the CTAs one after the other
   const size_t n_mine = n_chunks > (size_t)P.rank ? (n_chunks - 1 - (size_t)P.rank) / (size_t)P.size + 1 : 0;
   for (size_t k = blockIdx.x; k < n_mine; k += gridDim.x)
@@ -234,10 +257,11 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
     const size_t chunk = k * (size_t)P.size + (size_t)P.rank;
     const size_t i = chunk * kChunkGroups + threadIdx.x;
     if (i >= n4) continue;
-    const unsigned cover = coverage(i);
+    const unsigned gy = (unsigned)i / w4u, gx = ((unsigned)i - gy * w4u) * 4u;
+    const unsigned cover = coverage(gy, gx);
     if (cover == 0)
     {
-      if (P.rank == 0) write_empty(i);
+      if (P.rank == 0) write_empty(i, gy, gx);
       continue;
     }
     // issue all covering layer loads first (independent 16-byte NVLink reads)
@@ -288,6 +312,7 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
     out_rgba[i] = f;
     out_depth[i] = fd;
   }
+  if (P.timeline && blockIdx.x == 0 && threadIdx.x == 0) my_flags->timeline[9] = global_ns();
   // ---- rank 0 also writes the groups NO rank covers inside the other ranks' chunks (their owners skip
   // them); streaming stores into local HBM while the peers' folded pixels are still in flight
   if (P.rank == 0 && P.size > 1)
@@ -302,7 +327,9 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
     {
       if (chunk % (size_t)P.size == 0) continue;
       const size_t i = chunk * kChunkGroups + threadIdx.x;
-      if (i < n4 && coverage(i) == 0) write_empty(i);
+      if (i >= n4) continue;
+      const unsigned gy = (unsigned)i / w4u, gx = ((unsigned)i - gy * w4u) * 4u;
+      if (coverage(gy, gx) == 0) write_empty(i, gy, gx);
     }
   }
 
@@ -310,8 +337,10 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
   __syncthreads();
   if (threadIdx.x == 0)
   {
+    if (P.timeline && blockIdx.x == 0) my_flags->timeline[10] = global_ns();
     __threadfence_system();
     const unsigned prev = atomicAdd(&my_flags->cta_done, 1u);
+    if (P.timeline && blockIdx.x == 0) my_flags->timeline[11] = global_ns();
     if (prev == gridDim.x - 1)
     {
       my_flags->cta_done = 0;
@@ -327,6 +356,7 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
       Flags* root = reinterpret_cast<Flags*>(P.peers[0] + P.off_flags);
       __threadfence_system();
       st_release_sys(&root->done[P.rank], P.epoch);
+      if (P.timeline) my_flags->timeline[2] = global_ns();
     }
   }
 }
@@ -336,11 +366,13 @@ __global__ void __launch_bounds__(256) covered_to_canvas_kernel(const __grid_con
 {
   const Flags* my_flags = reinterpret_cast<const Flags*>(P.peers[0] + P.off_flags);
   const int par = P.epoch & 1;
+  if (P.timeline && blockIdx.x == 0 && threadIdx.x == 0) const_cast<Flags*>(my_flags)->timeline[3] = global_ns();
   // every rank's folded range has landed in my result image (what wait_done_kernel does, without
   // the extra launch)
   if (threadIdx.x < P.size && !wait_epoch(&my_flags->done[threadIdx.x], P.epoch, P.timeout_ns))
     report_error(err_of(const_cast<Flags*>(my_flags)), P.epoch, kPathImage, 1u, threadIdx.x);
   __syncthreads();
+  if (P.timeline && blockIdx.x == 0 && threadIdx.x == 0) const_cast<Flags*>(my_flags)->timeline[4] = global_ns();
   __shared__ int s_rect[kMaxRanks][4];
   if (threadIdx.x < P.size * 4) s_rect[threadIdx.x >> 2][threadIdx.x & 3] = my_flags->img_rect[par][threadIdx.x >> 2][threadIdx.x & 3];
   __syncthreads();
@@ -352,7 +384,8 @@ __global__ void __launch_bounds__(256) covered_to_canvas_kernel(const __grid_con
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
   {
-    const int y = (int)(i / (size_t)w4), x = (int)(i % (size_t)w4) * 4;
+    const unsigned uy = (unsigned)i / (unsigned)w4;
+    const int y = (int)uy, x = (int)(((unsigned)i - uy * (unsigned)w4) * 4u);
     bool cover = false;
     for (int l = 0; l < P.size; ++l)
       cover = cover || (y >= s_rect[l][1] && y < s_rect[l][3] && x >= s_rect[l][0] && x < s_rect[l][2]);
@@ -365,6 +398,7 @@ __global__ void __launch_bounds__(256) covered_to_canvas_kernel(const __grid_con
                                              (float)((w[q] >> 16) & 0xffu) * k, (float)(w[q] >> 24) * k);
     reinterpret_cast<float4*>(P.canvas_depth)[i] = res_depth[i];
   }
+  if (P.timeline && blockIdx.x == 0 && threadIdx.x == 0) const_cast<Flags*>(my_flags)->timeline[5] = global_ns();
 }
 
 __global__ void wait_done_kernel(Flags* mine, const unsigned int* done, int size, unsigned int epoch, unsigned path,
@@ -738,6 +772,10 @@ void comm_destroy(vr_ctx* ctx)
   cudaFree(c.peer_dev);
   cudaFree(c.minmax_dev);
   cudaFree(c.arena);
+  if (c.xstream) { cudaStreamSynchronize(c.xstream); cudaStreamDestroy(c.xstream); }
+  if (c.ev_trace) cudaEventDestroy(c.ev_trace);
+  if (c.ev_x[0]) cudaEventDestroy(c.ev_x[0]);
+  if (c.ev_x[1]) cudaEventDestroy(c.ev_x[1]);
   c.on = false;
 }
 
@@ -790,6 +828,15 @@ vr_status comm_ahead_image(vr_ctx* ctx, uchar4** rgba, float** depth)
   return VR_OK;
 }
 
+// vr_trace_to_image without VR_FRAME_WRITE_CANVAS touches only this frame's ring slot: it may start
+// while the latest exchange is still running, but not before the one before it has completed
+void comm_join_for_image_trace(vr_ctx* ctx)
+{
+  Comm& c = ctx->comm;
+  if (!c.on || !c.xstream || c.epoch < 2) return;
+  cudaStreamWaitEvent(ctx->stream, c.ev_x[(c.epoch - 1) & 1], 0);
+}
+
 // receive-slot geometry of a pushed frame (sampler mode 5)
 vr_status comm_push_target(vr_ctx* ctx, bool ahead, int width, int height, TraceParams& p)
 {
@@ -815,6 +862,16 @@ vr_status comm_push_target(vr_ctx* ctx, bool ahead, int width, int height, Trace
   p.push_rank = c.rank;
   p.push_size = c.size;
   return VR_OK;
+}
+
+// diagnostics: the globaltimer stamps of the last image exchange (VR_TIMELINE=1) and where the sampler
+// should leave its end-of-kernel stamp
+unsigned long long* comm_timeline_slot(vr_ctx* ctx, int k)
+{
+  Comm& c = ctx->comm;
+  if (!c.on || !c.timeline) return nullptr;
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
+  return reinterpret_cast<unsigned long long*>(c.arena + L.off_flags + offsetof(Flags, timeline)) + k;
 }
 
 // what the exchange kernels left for the host (a wait that hit the time limit, a peer that aborted):
@@ -892,6 +949,13 @@ extern "C" vr_status vr_comm_init(vr_ctx* ctx, int rank, int n_ranks, size_t max
     const char* t = std::getenv("VR_COMM_TIMEOUT_MS");
     const long long ms = t ? std::atoll(t) : 20000;
     c.timeout_ns = ms > 0 ? (unsigned long long)ms * 1000000ull : 0ull;
+    if (const char* e = std::getenv("VR_TIMELINE")) c.timeline = std::atoi(e) != 0;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaStreamCreateWithPriority(&c.xstream, cudaStreamNonBlocking, hi); // its CTAs go first when SM slots free up
+    cudaEventCreateWithFlags(&c.ev_trace, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c.ev_x[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c.ev_x[1], cudaEventDisableTiming);
   }
   const Layout L = make_layout(max_pixels, max_partials, rank == 0);
   c.arena_bytes = L.total;
@@ -998,6 +1062,7 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
   for (int i = 0; i < c.size; ++i) p.order[i] = idx[i];
   p.zbuffer = zbuffer ? 1 : 0;
   p.timeout_ns = c.timeout_ns;
+  p.timeline = c.timeline ? 1 : 0;
   p.pushed = ctx->img_pushed ? 1 : 0;
   {
     const size_t n4 = (p.n_pixels + 3) / 4;
@@ -1020,7 +1085,17 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
     p.track_res = still(c.clean_res[b]) ? 1 : 0;
     p.track_canvas = (p.canvas_rgba && !ctx->canvas_exposed && still(c.clean_canvas)) ? 1 : 0;
   }
-  cudaError_t e = launch_fold_p2p(p, ctx->sm_count, ctx->stream);
+  // the exchange stream: ordered after the trace that produced this image (everything queued on the
+  // context's stream so far), not before anything the caller queues next
+  cudaStream_t xs = c.xstream ? c.xstream : ctx->stream;
+  const bool fused_tail = c.rank != 0 || p.canvas_rgba != nullptr || (!to_canvas);
+  if (!fused_tail) xs = ctx->stream; // (rank 0's unfused ImageToCanvas below runs on the context's stream)
+  if (xs != ctx->stream)
+  {
+    cudaEventRecord(c.ev_trace, ctx->stream);
+    cudaStreamWaitEvent(xs, c.ev_trace, 0);
+  }
+  cudaError_t e = launch_fold_p2p(p, ctx->sm_count, xs);
   if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "fold_p2p launch", e);
   ctx->launches++;
   if (c.rank == 0)
@@ -1032,12 +1107,12 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
     if (p.canvas_rgba)
     {
       // waits for every rank's "done" itself, then converts the covered groups
-      covered_to_canvas_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(p);
+      covered_to_canvas_kernel<<<ctx->sm_count * 4, 256, 0, xs>>>(p);
       ctx->launches++;
     }
     else
     {
-      wait_done_kernel<<<1, 32, 0, ctx->stream>>>(const_cast<Flags*>(f), f->done, c.size, c.epoch, kPathImage, c.timeout_ns);
+      wait_done_kernel<<<1, 32, 0, xs>>>(const_cast<Flags*>(f), f->done, c.size, c.epoch, kPathImage, c.timeout_ns);
       ctx->launches++;
       if (to_canvas)
       {
@@ -1055,6 +1130,11 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
     {
       c.clean_canvas.valid = true; c.clean_canvas.serial = ctx->api_serial; c.clean_canvas.W = ctx->W; c.clean_canvas.H = ctx->H;
     }
+  }
+  if (xs != ctx->stream)
+  {
+    cudaEventRecord(c.ev_x[c.epoch & 1], xs);
+    c.x_pending = true;
   }
   // the next frame's image: the following ring slot -- where a frame traced ahead already sits
   const int ns = (int)((c.epoch + 1) % kImgRing);

@@ -34,8 +34,12 @@ namespace
 
 constexpr int kTileW = 32, kTileH = 8;           // 256 threads
 constexpr int kMaxTileLayers = 192;              // layers overlapping one tile (smem list)
-constexpr int kMaxSeg = 32;                      // entries per pixel ordered in local memory
+constexpr int kMaxSeg = 20;                      // entries per pixel ordered in shared memory (deeper: selection)
 constexpr int kBatch = 8;                        // layer entries requested together per pixel
+constexpr int kThreadsFold = kTileW * kTileH;
+// per-thread sort keys live in shared memory, [slot][thread] so that a warp's accesses never conflict:
+// exit distance and (tie-break order << 12 | index into the tile's layer list)
+constexpr size_t kKeyBytes = (size_t)kMaxSeg * kThreadsFold * 8;
 
 __device__ __forceinline__ void blend(float4& a, const float4 o)
 {
@@ -65,7 +69,9 @@ template <bool COMM>
 __global__ void __launch_bounds__(kTileW* kTileH) layers_fold_kernel(const __grid_constant__ LayerFoldParams P)
 {
   extern __shared__ unsigned char smem_raw[];
-  LayerDesc* s_desc = reinterpret_cast<LayerDesc*>(smem_raw);          // all ranks' tables
+  float* s_kd = reinterpret_cast<float*>(smem_raw);                               // sort keys: exit distance
+  int* s_ko = reinterpret_cast<int*>(smem_raw + kKeyBytes / 2);                   // sort keys: order | list index
+  LayerDesc* s_desc = reinterpret_cast<LayerDesc*>(smem_raw + kKeyBytes);         // all ranks' tables
   __shared__ int s_first[kMaxCommRanks + 1];                          // table offsets per rank
   __shared__ TileLayer s_tile[kMaxTileLayers];
   __shared__ int s_ntile;
@@ -150,7 +156,8 @@ __global__ void __launch_bounds__(kTileW* kTileH) layers_fold_kernel(const __gri
     const size_t n_px = (size_t)P.W * P.H;
     for (size_t px = (size_t)blockIdx.x * blockDim.x + threadIdx.x; px < n_px; px += (size_t)gridDim.x * blockDim.x)
     {
-      const int y = (int)(px / (size_t)P.W), x = (int)(px % (size_t)P.W);
+      const unsigned uy = (unsigned)px / (unsigned)P.W; // 32-bit: W * H < 2^31
+      const int y = (int)uy, x = (int)((unsigned)px - uy * (unsigned)P.W);
       if (y >= py0 && y < py1 && x >= px0 && x < px1) continue;
       canvas[px] = make_float4(0.f, 0.f, 0.f, 0.f);
       cdepth[px] = 1.001f;
@@ -203,20 +210,17 @@ __global__ void __launch_bounds__(kTileW* kTileH) layers_fold_kernel(const __gri
     const int x = tx0 + lx, y = ty0 + ly;
     if (x < P.W && y < P.H)
     {
-      // ---- gather this pixel's entries, insertion-sorted by (exit distance, rank, block).  The
-      // entries of up to kBatch overlapping layers are requested together (independent loads, remote
-      // ones cross NVLink): one round trip per batch instead of two per layer, and the colour is
-      // kept so the fold below does not ask again.
-      float kd[kMaxSeg];
-      int ko[kMaxSeg];
-      float4 kq[kMaxSeg];
+      // ---- pass 1: this pixel's entries, insertion-sorted by (exit distance, rank, block).  Only the
+      // sort key is kept -- exit distance and the entry's place in the tile's layer list, in SHARED memory
+      // ([slot][thread]: conflict-free), not in per-thread local arrays -- so the kernel stays at ~50
+      // registers and several CTAs per SM.  The key fields of up to kBatch overlapping layers (exit
+      // distance, alpha) are requested together: independent loads, remote ones cross NVLink once per batch.
       int c = 0;
       bool deep = false;
       for (int l0 = 0; l0 < nt && !deep; l0 += kBatch)
       {
-        float4 q[kBatch];
-        float d[kBatch];
-        int ord[kBatch];
+        float w[kBatch], d[kBatch];
+        int key[kBatch];
         bool in[kBatch];
 #pragma unroll
         for (int u = 0; u < kBatch; ++u)
@@ -228,9 +232,9 @@ __global__ void __launch_bounds__(kTileW* kTileH) layers_fold_kernel(const __gri
             if (!(x < L.x0 || x >= L.x1 || y < L.y0 || y >= L.y1))
             {
               const size_t e = (size_t)(y - L.y0) * L.w + (x - L.x0);
-              q[u] = L.rgba[e];
+              w[u] = reinterpret_cast<const float*>(L.rgba + e)[3];
               d[u] = L.depth[e];
-              ord[u] = L.order;
+              key[u] = (L.order << 12) | (l0 + u); // order < 2^14 (16 ranks x 1024 layers), list index < 2^12
               in[u] = true;
             }
           }
@@ -238,15 +242,18 @@ __global__ void __launch_bounds__(kTileW* kTileH) layers_fold_kernel(const __gri
 #pragma unroll
         for (int u = 0; u < kBatch; ++u)
         {
-          if (!in[u] || q[u].w < 0.001f) continue; // the reference's `if(alpha < 0.001f) continue;` (:270-272)
+          if (!in[u] || w[u] < 0.001f) continue; // the reference's `if(alpha < 0.001f) continue;` (:270-272)
           if (c == kMaxSeg) { deep = true; break; }
           int b = c - 1;
-          while (b >= 0 && (kd[b] > d[u] || (kd[b] == d[u] && ko[b] > ord[u])))
+          while (b >= 0 && (s_kd[b * kThreadsFold + threadIdx.x] > d[u] ||
+                            (s_kd[b * kThreadsFold + threadIdx.x] == d[u] && s_ko[b * kThreadsFold + threadIdx.x] > key[u])))
           {
-            kd[b + 1] = kd[b]; ko[b + 1] = ko[b]; kq[b + 1] = kq[b];
+            s_kd[(b + 1) * kThreadsFold + threadIdx.x] = s_kd[b * kThreadsFold + threadIdx.x];
+            s_ko[(b + 1) * kThreadsFold + threadIdx.x] = s_ko[b * kThreadsFold + threadIdx.x];
             --b;
           }
-          kd[b + 1] = d[u]; ko[b + 1] = ord[u]; kq[b + 1] = q[u];
+          s_kd[(b + 1) * kThreadsFold + threadIdx.x] = d[u];
+          s_ko[(b + 1) * kThreadsFold + threadIdx.x] = key[u];
           ++c;
         }
       }
@@ -255,8 +262,14 @@ __global__ void __launch_bounds__(kTileW* kTileH) layers_fold_kernel(const __gri
       bool any = false;
       if (!deep)
       {
-        if (c > 0) { acc = kq[0]; first_depth = kd[0]; any = true; }
-        for (int a = 1; a < c; ++a) blend(acc, kq[a]);
+        // ---- pass 2: the colours, in order (the same 32-byte sectors pass 1 touched: cache hits)
+        for (int a = 0; a < c; ++a)
+        {
+          const TileLayer L = fetch(s_ko[a * kThreadsFold + threadIdx.x] & 0xfff);
+          const float4 q = L.rgba[(size_t)(y - L.y0) * L.w + (x - L.x0)];
+          if (a == 0) { acc = q; first_depth = s_kd[threadIdx.x]; any = true; }
+          else blend(acc, q);
+        }
       }
       else
       {
@@ -406,10 +419,10 @@ __global__ void layers_to_partials_kernel(const LayerTable* __restrict__ table,
 
 cudaError_t launch_layers_fold(const LayerFoldParams& p, bool comm, int sm_count, cudaStream_t s)
 {
-  const size_t smem = (size_t)p.smem_layers * sizeof(LayerDesc);
+  const size_t smem = kKeyBytes + (size_t)p.smem_layers * sizeof(LayerDesc);
   // per device, not per process (a process may hold contexts on several GPUs): cheap enough to set per launch
-  if (comm) cudaFuncSetAttribute(layers_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-  else cudaFuncSetAttribute(layers_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  if (comm) cudaFuncSetAttribute(layers_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+  else cudaFuncSetAttribute(layers_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
   // (the kernel restricts itself to the layers' bounding box; the full frame bounds the grid)
   const long long tiles = (long long)((p.W + kTileW - 1) / kTileW) * ((p.H + kTileH - 1) / kTileH);
   // persistent grid: exactly the CTAs that are resident at once (registers and the table's smem decide)

@@ -233,11 +233,339 @@ __device__ __forceinline__ void locate_and_load(const BlockDev& B, float px, flo
   }
 }
 
-template <int KIND, typename FT, int ASSOC, int MODE, typename IDX>
-__global__ void __launch_bounds__(kThreads, VR_MIN_BLOCKS)
+// ---------------------------------------------------------------------------------------------
+// Sparse march (uniform blocks, point fields, step >= 2.6 voxels -- the reference's default samples =
+// 100 on every BASELINE config): the host has established (TraceParams::sparse) that every step of
+// every ray leaves its cell, so each sample locates its cell from scratch -- exactly what the
+// reference's "new cell" branch does -- and nothing is carried from one sample to the next except the
+// position and the accumulated colour.  That makes a sample's eight gathers independent of all
+// earlier samples: THREE samples are kept in flight per ray (slots A, B, C, rotated by unrolling, no
+// register copies), against one in the general march.  float -> int of the non-negative cell
+// coordinate is a round-toward-zero add of 2^23 (mantissa = integer part; exact below 2^22) on the
+// FMA pipe instead of F2I/I2F on the quarter-rate conversion pipe.
+__shared__ float4 s_lut[1024]; // the transfer function, one copy per CTA (every kernel of this file)
+
+struct SparseSlot
+{
+  float s0, s1, s2, s3, s4, s5, s6, s7; // the eight corner scalars, raw
+  float tx, ty, tz;                     // position inside the cell
+};
+
+// a gather that is skipped (result 0) when `on` is false: one predicated LDG, no branch
+__device__ __forceinline__ float ldg_if(const float* p, bool on)
+{
+  float v;
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
+      : "=f"(v) : "l"(p), "r"((int)on));
+  return v;
+}
+__device__ __forceinline__ float ldg_if(const double* p, bool on)
+{
+  double v;
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@q ld.global.nc.f64 %0, [%1];\n\t}"
+      : "=d"(v) : "l"(p), "r"((int)on));
+  return (float)v;
+}
+
+// cell lookup + the eight gathers of one sample.  Branch-free: for a sample past the end of the ray
+// (`on` false) the arithmetic runs on whatever the position is and only the loads are predicated off.
+template <typename FT, typename IDX>
+__device__ __forceinline__ void sparse_issue(const TraceParams& P, float px, float py, float pz, bool on, SparseSlot& s)
+{
+  const BlockDev& B = P.blk;
+  // UniformLocator::LocateCell
+  float t0 = (px - B.min_point[0]) * B.inv_spacing[0];
+  float t1 = (py - B.min_point[1]) * B.inv_spacing[1];
+  float t2 = (pz - B.min_point[2]) * B.inv_spacing[2];
+  if (t0 == P.dims_m1[0]) t0 = P.dims_m2[0];
+  if (t1 == P.dims_m1[1]) t1 = P.dims_m2[1];
+  if (t2 == P.dims_m1[2]) t2 = P.dims_m2[2];
+  const float kMagic = 8388608.f; // 2^23
+  const float r0 = __fadd_rz(t0, kMagic), r1 = __fadd_rz(t1, kMagic), r2 = __fadd_rz(t2, kMagic);
+  const int cx = __float_as_int(r0) - 0x4B000000, cy = __float_as_int(r1) - 0x4B000000,
+            cz = __float_as_int(r2) - 0x4B000000;
+  const float fcx = r0 - kMagic, fcy = r1 - kMagic, fcz = r2 - kMagic; // exact
+  // GetPoint(cell): origin + spacing * ijk (see locate_and_load)
+  const float blx = __fmaf_rn(B.spacing[0], fcx, B.origin[0]);
+  const float bly = __fmaf_rn(B.spacing[1], fcy, B.origin[1]);
+  const float blz = __fmaf_rn(B.spacing[2], fcz, B.origin[2]);
+  s.tx = (px - blx) * B.inv_spacing[0];
+  s.ty = (py - bly) * B.inv_spacing[1];
+  s.tz = (pz - blz) * B.inv_spacing[2];
+  // four row pointers, each one widening multiply-add away from the previous
+  const IDX i0 = ((IDX)cz * (IDX)B.dims[1] + (IDX)cy) * (IDX)B.dims[0] + (IDX)cx;
+  const FT* f0 = reinterpret_cast<const FT*>(B.field) + i0;
+  const FT* f3 = f0 + B.dims[0];
+  const FT* f4 = f0 + P.slice_elems;
+  const FT* f7 = f4 + B.dims[0];
+  s.s0 = ldg_if(f0, on);
+  s.s1 = ldg_if(f0 + 1, on);
+  s.s3 = ldg_if(f3, on);
+  s.s2 = ldg_if(f3 + 1, on);
+  s.s4 = ldg_if(f4, on);
+  s.s5 = ldg_if(f4 + 1, on);
+  s.s7 = ldg_if(f7, on);
+  s.s6 = ldg_if(f7 + 1, on);
+}
+
+// interpolate + classify + blend one sample; returns true when the ray is saturated (alpha >= 1)
+__device__ __forceinline__ bool sparse_shade(const TraceParams& P, const SparseSlot& s, float& c0, float& c1, float& c2,
+                                             float& c3)
+{
+  const float cms_f = P.cms_f;
+  const float s6m7 = s.s6 - s.s7, s5m4 = s.s5 - s.s4, s1m0 = s.s1 - s.s0, s2m3 = s.s2 - s.s3;
+  const float l76 = s.s7 + s.tx * s6m7;
+  const float l45 = s.s4 + s.tx * s5m4;
+  const float ltop = l45 + s.ty * (l76 - l45);
+  const float l01 = s.s0 + s.tx * s1m0;
+  const float l32 = s.s3 + s.tx * s2m3;
+  const float lbot = l01 + s.ty * (l32 - l01);
+  float v = lbot + s.tz * (ltop - lbot);
+  v = (v - P.range_min) * P.inv_delta_scalar;
+  const float raw = v * cms_f;
+  float fidx = fminf(fmaxf(raw, 0.f), cms_f); // (see the general march for the NaN / overflow cases)
+  if (raw >= 9.2233720e18f) fidx = 0.f;
+  const int idx = __float_as_int(__fadd_rz(fidx, 8388608.f)) - 0x4B000000;
+  const float4 sc = s_lut[idx];
+  const float alpha = sc.w * (1.f - c3);
+  c0 = c0 + sc.x * alpha;
+  c1 = c1 + sc.y * alpha;
+  c2 = c2 + sc.z * alpha;
+  c3 = alpha + c3;
+  return c3 >= 1.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Brick march (uniform blocks, f32 point fields, step <= 2 voxels -- dense sampling, e.g. samples = 887 on
+// the 512^3 block): consecutive samples of a ray, and the rays of a warp's 8x4 pixel packet, walk through
+// neighbouring cells, so the warp stages the sub-volume its next kBrickSteps samples will touch in shared
+// memory with ONE TMA tensor copy (cp.async.bulk.tensor.3d, a 16x10x10 box of the field addressed through a
+// CUtensorMap the host encodes per block; completion on an mbarrier; out-of-range parts of the box are
+// zero-filled by the hardware and never read) and fetches the eight corners of every sample with LDS at
+// constant offsets from one address.  Two bricks per warp are in flight: while the lanes sample brick w,
+// the copy engine fills brick w+1.  A packet ends when a warp ballot finds no lane with a live ray (early
+// termination, exit, miss).  The brick is anchored at the low corner of the axis-aligned box around the
+// cells of the window's first and last sample of every live lane, padded by a cell (rounding, "keep the
+// cell while 0 <= t <= 1"); the window is halved until that box (plus the upper corners) fits.  A sample
+// whose cell is not in the brick gathers from global memory like the general march.  The arithmetic per
+// sample is the general march's, so the pixels are the same bits.
+// brick = kBrickX x kBrickY x kBrickZ points.  TMA wants the box to start on a 16-byte boundary of the
+// innermost (x) dimension -- measured: any other x coordinate raises "illegal instruction", y and z are
+// free, negative coordinates included (profiles/experiments/tma_probe.cu) -- so x is anchored at a multiple
+// of 4 points and the box is 4 points wider there than the 12 the window needs.
+constexpr int kBrickX = 16, kBrickY = 10, kBrickZ = 10;
+constexpr int kBrickFloats = kBrickX * kBrickY * kBrickZ; // 6400 bytes = 50 * 128
+constexpr int kBrickSteps = 8;                           // samples per window (halved until the brick fits)
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes)
+{
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity)
+{
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tma_load_box(unsigned dst, const void* tmap, int x, int y, int z, unsigned bar)
+{
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+struct Brick
+{
+  int x0, y0, z0; // first point staged
+  int on;         // a brick was requested for this window
+};
+
+// the brick of the window [a, a + k) steps ahead of the lanes' current positions (warp-uniform result)
+__device__ __forceinline__ Brick brick_of_window(const TraceParams& P, bool live, float px, float py, float pz, float sx,
+                                                 float sy, float sz, float a, int& k)
+{
+  const BlockDev& B = P.blk;
+  Brick b;
+  b.on = 0;
+  b.x0 = b.y0 = b.z0 = 0;
+  if (!__any_sync(0xffffffffu, live)) return b;
+  for (;; k >>= 1)
+  {
+    const float e = a + (float)(k - 1);
+    int lo[3], hi[3];
+    const float q0[3] = { px + a * sx, py + a * sy, pz + a * sz }, q1[3] = { px + e * sx, py + e * sy, pz + e * sz };
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+    {
+      const int c0 = __float2int_rd((q0[d] - B.min_point[d]) * B.inv_spacing[d]);
+      const int c1 = __float2int_rd((q1[d] - B.min_point[d]) * B.inv_spacing[d]);
+      lo[d] = __reduce_min_sync(0xffffffffu, live ? min(c0, c1) - 1 : 0x7fffffff);
+      hi[d] = __reduce_max_sync(0xffffffffu, live ? max(c0, c1) + 2 : -0x7fffffff); // + upper corner + a cell
+    }
+    const int x0 = lo[0] & ~3; // (two's complement: rounds towards -inf, also below zero)
+    if (hi[0] - x0 < kBrickX && hi[1] - lo[1] < kBrickY && hi[2] - lo[2] < kBrickZ)
+    {
+      b.x0 = x0; b.y0 = lo[1]; b.z0 = lo[2];
+      b.on = 1;
+      return b;
+    }
+    if (k == 1) return b; // does not fit even for one step: these samples gather from global memory
+  }
+}
+
+// `live`: this lane has a ray whose current position (px,py,pz at `distance`) is its first valid sample
+template <typename IDX>
+__device__ __forceinline__ void brick_march(const TraceParams& P, bool live, float px, float py, float pz, float sx,
+                                            float sy, float sz, float distance, float max_distance, float& c0, float& c1,
+                                            float& c2, float& c3, unsigned& my_samples, unsigned wbuf, unsigned wbar,
+                                            unsigned& parity)
+{
+  const BlockDev& B = P.blk;
+  const int lane = threadIdx.x & 31;
+  if (!__any_sync(0xffffffffu, live)) return;
+  const float minx = B.min_point[0], miny = B.min_point[1], minz = B.min_point[2];
+  const float maxx = B.max_point[0], maxy = B.max_point[1], maxz = B.max_point[2];
+  const float sd = P.sample_dist;
+  const void* tmap = B.tmap;
+  // the cell the ray is in (general march semantics: kept while 0 <= t <= 1)
+  bool fresh = true;
+  int cx = 0, cy = 0, cz = 0;
+  float blx = 0.f, bly = 0.f, blz = 0.f;
+
+  int k_cur = kBrickSteps;
+  Brick cur = brick_of_window(P, live, px, py, pz, sx, sy, sz, 0.f, k_cur);
+  unsigned slot = 0; // buffer / barrier of the current window: wbuf + slot * kBrickFloats * 4, wbar + slot * 8
+  if (cur.on && lane == 0)
+  {
+    mbar_arrive_expect_tx(wbar, kBrickFloats * 4u);
+    tma_load_box(wbuf, tmap, cur.x0, cur.y0, cur.z0, wbar);
+  }
+  for (;;)
+  {
+    // ---- the copy engine starts on the next window while this one is sampled
+    int k_next = kBrickSteps;
+    const bool live_next = live && (distance + (float)k_cur * sd < max_distance);
+    const Brick nxt = brick_of_window(P, live_next, px, py, pz, sx, sy, sz, (float)k_cur, k_next);
+    if (nxt.on && lane == 0)
+    {
+      const unsigned nb = wbar + (slot ^ 1u) * 8u;
+      mbar_arrive_expect_tx(nb, kBrickFloats * 4u);
+      tma_load_box(wbuf + (slot ^ 1u) * (kBrickFloats * 4u), tmap, nxt.x0, nxt.y0, nxt.z0, nb);
+    }
+    if (cur.on)
+    {
+      while (!mbar_try_wait(wbar + slot * 8u, (parity >> slot) & 1u)) {}
+      parity ^= 1u << slot;
+    }
+    const unsigned bk = wbuf + slot * (kBrickFloats * 4u);
+    for (int j = 0; j < k_cur; ++j)
+    {
+      if (live)
+      {
+        float tx = (px - blx) * B.inv_spacing[0], ty = (py - bly) * B.inv_spacing[1], tz = (pz - blz) * B.inv_spacing[2];
+        if (fresh || fmaxf(tx, fmaxf(ty, tz)) > 1.f || fminf(tx, fminf(ty, tz)) < 0.f)
+        {
+          // UniformLocator::LocateCell (same arithmetic as locate_and_load)
+          float t0 = (px - minx) * B.inv_spacing[0], t1 = (py - miny) * B.inv_spacing[1], t2 = (pz - minz) * B.inv_spacing[2];
+          if (t0 == P.dims_m1[0]) t0 = P.dims_m2[0];
+          if (t1 == P.dims_m1[1]) t1 = P.dims_m2[1];
+          if (t2 == P.dims_m1[2]) t2 = P.dims_m2[2];
+          cx = (int)t0; cy = (int)t1; cz = (int)t2;
+          blx = __fmaf_rn(B.spacing[0], (float)cx, B.origin[0]);
+          bly = __fmaf_rn(B.spacing[1], (float)cy, B.origin[1]);
+          blz = __fmaf_rn(B.spacing[2], (float)cz, B.origin[2]);
+          tx = (px - blx) * B.inv_spacing[0]; ty = (py - bly) * B.inv_spacing[1]; tz = (pz - blz) * B.inv_spacing[2];
+          fresh = false;
+        }
+        float s0, s1, s2, s3, s4, s5, s6, s7;
+        const int ux = cx - cur.x0, uy = cy - cur.y0, uz = cz - cur.z0;
+        if (cur.on && (unsigned)ux < (unsigned)(kBrickX - 1) && (unsigned)uy < (unsigned)(kBrickY - 1) &&
+            (unsigned)uz < (unsigned)(kBrickZ - 1))
+        {
+          // row pitch 16 floats = 64 bytes, slab pitch 160 floats = 640 bytes: all eight corners at constant
+          // offsets from one address
+          static_assert(kBrickX == 16 && kBrickY == 10, "the LDS offsets below assume a 16 x 10 x n brick");
+          const unsigned q = bk + (unsigned)((uz * kBrickY + uy) * kBrickX + ux) * 4u;
+          asm volatile("ld.shared.f32 %0, [%8];\n\tld.shared.f32 %1, [%8+4];\n\t"
+                       "ld.shared.f32 %3, [%8+64];\n\tld.shared.f32 %2, [%8+68];\n\t"
+                       "ld.shared.f32 %4, [%8+640];\n\tld.shared.f32 %5, [%8+644];\n\t"
+                       "ld.shared.f32 %7, [%8+704];\n\tld.shared.f32 %6, [%8+708];"
+                       : "=f"(s0), "=f"(s1), "=f"(s2), "=f"(s3), "=f"(s4), "=f"(s5), "=f"(s6), "=f"(s7)
+                       : "r"(q) : "memory");
+        }
+        else
+        {
+          const IDX Nx = (IDX)B.dims[0], NxNy = (IDX)B.dims[0] * (IDX)B.dims[1];
+          const float* f = reinterpret_cast<const float*>(B.field) + (((IDX)cz * (IDX)B.dims[1] + (IDX)cy) * Nx + (IDX)cx);
+          s0 = __ldg(f); s1 = __ldg(f + 1); s3 = __ldg(f + Nx); s2 = __ldg(f + Nx + 1);
+          s4 = __ldg(f + NxNy); s5 = __ldg(f + NxNy + 1); s7 = __ldg(f + NxNy + Nx); s6 = __ldg(f + NxNy + Nx + 1);
+        }
+        const float s6m7 = s6 - s7, s5m4 = s5 - s4, s1m0 = s1 - s0, s2m3 = s2 - s3;
+        const float l76 = s7 + tx * s6m7;
+        const float l45 = s4 + tx * s5m4;
+        const float ltop = l45 + ty * (l76 - l45);
+        const float l01 = s0 + tx * s1m0;
+        const float l32 = s3 + tx * s2m3;
+        const float lbot = l01 + ty * (l32 - l01);
+        float v = lbot + tz * (ltop - lbot);
+        v = (v - P.range_min) * P.inv_delta_scalar;
+        const float raw = v * P.cms_f;
+        float fidx = fminf(fmaxf(raw, 0.f), P.cms_f);
+        if (raw >= 9.2233720e18f) fidx = 0.f;
+        const float4 sc = s_lut[(int)fidx];
+        const float alpha = sc.w * (1.f - c3);
+        c0 = c0 + sc.x * alpha;
+        c1 = c1 + sc.y * alpha;
+        c2 = c2 + sc.z * alpha;
+        c3 = alpha + c3;
+        ++my_samples;
+        // next sample of this ray, or the end of it (saturated / left the block / reached the depth limit)
+        px = px + sx; py = py + sy; pz = pz + sz;
+        distance = distance + sd;
+        live = !(c3 >= 1.f) && !(px < minx || px > maxx) && !(py < miny || py > maxy) && !(pz < minz || pz > maxz) &&
+               distance < max_distance;
+      }
+    }
+    __syncwarp(); // every lane is done reading this window's brick before its buffer is filled again
+    // ---- ray-packet termination: one ballot for the whole warp
+    const bool more = __any_sync(0xffffffffu, live);
+    if (!more)
+    {
+      if (nxt.on)
+      {
+        // a brick is still in flight: let it land so that barrier and buffer are free for the next packet
+        while (!mbar_try_wait(wbar + (slot ^ 1u) * 8u, (parity >> (slot ^ 1u)) & 1u)) {}
+        parity ^= 1u << (slot ^ 1u);
+      }
+      return;
+    }
+    cur = nxt;
+    k_cur = k_next;
+    slot ^= 1u;
+  }
+}
+
+// MARCH: 0 = general march (any block, any step), 1 = sparse march, 2 = brick march (see above); each is
+// its own kernel so that each gets the register budget it needs: 56 / 72 / 96 registers per thread
+// (9 / 7 / 3 resident CTAs per SM; the brick march is bounded by its shared-memory bricks anyway).
+template <int KIND, typename FT, int ASSOC, int MODE, typename IDX, int MARCH>
+__global__ void __launch_bounds__(kThreads, MARCH == 0 ? VR_MIN_BLOCKS : (MARCH == 1 ? 7 : 3))
 trace_kernel(const __grid_constant__ TraceParams P)
 {
-  __shared__ float4 s_lut[1024];
+  extern __shared__ __align__(128) unsigned char s_dyn[]; // brick march: per-warp brick buffers + mbarriers
+  unsigned brick_parity = 0;
+  if (MARCH == 2)
+  {
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_dyn + (size_t)(kThreads / 32) * 2 * kBrickFloats * 4);
+    if (threadIdx.x < (kThreads / 32) * 2) mbar_init(smem_addr(bars + threadIdx.x), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+  }
   if (MODE != 4) // the staging pre-pass never classifies
   {
     for (int i = threadIdx.x; i < P.lut_size; i += kThreads) s_lut[i] = __ldg(P.lut + i);
@@ -249,7 +577,7 @@ trace_kernel(const __grid_constant__ TraceParams P)
   const int lx = lane & (kTileW - 1), ly = lane >> 3;
   const unsigned n_tiles = (unsigned)(P.tiles_x * P.tiles_y);
   const unsigned n_work = n_tiles + (MODE == 2 ? (unsigned)P.n_clear_chunks : 0u);
-  const float cms_f = (float)(P.lut_size - 1);
+  const float cms_f = P.cms_f;
   const float minx = B.min_point[0], miny = B.min_point[1], minz = B.min_point[2];
   const float maxx = B.max_point[0], maxy = B.max_point[1], maxz = B.max_point[2];
   const float sd = P.sample_dist;
@@ -281,10 +609,14 @@ trace_kernel(const __grid_constant__ TraceParams P)
     const long long pixel = (long long)j * P.W + i;
     float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
     float max_distance = __int_as_float(0x7f800000);
+    // (brick march: the march itself runs after the divergent ray set-up, with the whole warp present)
+    bool b_live = false;
+    float b_px = 0.f, b_py = 0.f, b_pz = 0.f, b_sx = 0.f, b_sy = 0.f, b_sz = 0.f, b_dist = 0.f;
+    // K7 needs these after the march
+    float dx = 0.f, dy = 0.f, dz = 0.f, distance0 = 0.f;
     if (in_subset)
     {
       // ---------------- K1: PerspectiveRayGen
-      float dx, dy, dz;
       {
         const float fx = (2.f * (float)i - (float)P.W) / 2.0f;
         const float fy = (2.f * (float)j - (float)P.H) / 2.0f;
@@ -299,7 +631,7 @@ trace_kernel(const __grid_constant__ TraceParams P)
         dx = dx / sq; dy = dy / sq; dz = dz / sq;
       }
       const float ox = P.origin[0], oy = P.origin[1], oz = P.origin[2];
-      float min_distance = 0.f, distance0 = 0.f;
+      float min_distance = 0.f;
 
       // ---------------- K2: RayMapCanvas
       if (P.use_depth)
@@ -343,7 +675,42 @@ trace_kernel(const __grid_constant__ TraceParams P)
           distance += sd;
           px = ox + distance * dx; py = oy + distance * dy; pz = oz + distance * dz;
         }
-        if (VR_INSIDE(px, py, pz) && distance < max_distance)
+        if (MARCH == 2)
+        {
+          // ---- brick march: only note where the ray starts; the warp marches together below
+          b_live = VR_INSIDE(px, py, pz) && distance < max_distance;
+          b_px = px; b_py = py; b_pz = pz; b_dist = distance;
+          b_sx = sd * dx; b_sy = sd * dy; b_sz = sd * dz;
+        }
+        else if (MARCH == 1 && VR_INSIDE(px, py, pz) && distance < max_distance)
+        {
+          // ---- sparse march: three samples in flight (slots A, B, C)
+          const float stepx = sd * dx, stepy = sd * dy, stepz = sd * dz;
+          SparseSlot A, B_, C;
+          bool vB, vC, vA;
+          sparse_issue<FT, IDX>(P, px, py, pz, true, A);
+#define VR_ADVANCE(valid_prev, valid_out, slot)                                              \
+          px = px + stepx; py = py + stepy; pz = pz + stepz;                                 \
+          distance = distance + sd;                                                          \
+          valid_out = (valid_prev) && VR_INSIDE(px, py, pz) && distance < max_distance;      \
+          sparse_issue<FT, IDX>(P, px, py, pz, valid_out, slot);
+          VR_ADVANCE(true, vB, B_)
+          VR_ADVANCE(vB, vC, C)
+          for (;;)
+          {
+            ++my_samples;
+            if (sparse_shade(P, A, c0, c1, c2, c3) || !vB) break;
+            VR_ADVANCE(vC, vA, A)
+            ++my_samples;
+            if (sparse_shade(P, B_, c0, c1, c2, c3) || !vC) break;
+            VR_ADVANCE(vA, vB, B_)
+            ++my_samples;
+            if (sparse_shade(P, C, c0, c1, c2, c3) || !vA) break;
+            VR_ADVANCE(vB, vC, C)
+          }
+#undef VR_ADVANCE
+        }
+        else if (MARCH == 0 && VR_INSIDE(px, py, pz) && distance < max_distance)
         {
           const float stepx = sd * dx, stepy = sd * dy, stepz = sd * dz;
           // first sample: the reference enters its loop with newCell = true
@@ -419,9 +786,22 @@ trace_kernel(const __grid_constant__ TraceParams P)
             tx = ntx; ty = nty; tz = ntz;
           }
         }
-        c0 = fminf(c0, 1.f); c1 = fminf(c1, 1.f); c2 = fminf(c2, 1.f); c3 = fminf(c3, 1.f);
+        if (MARCH != 2) { c0 = fminf(c0, 1.f); c1 = fminf(c1, 1.f); c2 = fminf(c2, 1.f); c3 = fminf(c3, 1.f); }
       }
-
+    }
+    if (MARCH == 2)
+    {
+      // this warp's two brick buffers (128-byte aligned: 6912 = 54 * 128) and its two mbarriers
+      const unsigned wbuf = smem_addr(s_dyn) + (threadIdx.x >> 5) * (2u * kBrickFloats * 4u);
+      const unsigned wbar = smem_addr(s_dyn) + (kThreads / 32) * (2u * kBrickFloats * 4u) + (threadIdx.x >> 5) * 16u;
+      const bool had_ray = b_live; // (a ray that never reaches a valid sample keeps colour 0, as in the other marches)
+      brick_march<IDX>(P, b_live, b_px, b_py, b_pz, b_sx, b_sy, b_sz, b_dist, max_distance, c0, c1, c2, c3, my_samples,
+                       wbuf, wbar, brick_parity);
+      if (had_ray) { c0 = fminf(c0, 1.f); c1 = fminf(c1, 1.f); c2 = fminf(c2, 1.f); c3 = fminf(c3, 1.f); }
+    }
+    if (in_subset)
+    {
+      const float ox = P.origin[0], oy = P.origin[1], oz = P.origin[2];
       if (MODE == 0)
       {
         // ---------------- K7: SurfaceConverter (blend over canvas, projected entry depth)
@@ -527,6 +907,7 @@ trace_kernel(const __grid_constant__ TraceParams P)
     }
   }
 #undef VR_INSIDE
+  if (P.end_stamp && threadIdx.x == 0) atomicMax(P.end_stamp, global_ns());
   if (P.sample_counter)
   {
     // one atomic per warp
@@ -537,16 +918,41 @@ trace_kernel(const __grid_constant__ TraceParams P)
   }
 }
 
+constexpr size_t kBrickSmem = (size_t)(kThreads / 32) * 2 * kBrickFloats * 4 + (size_t)(kThreads / 32) * 2 * 8;
+
+template <int KIND, typename FT, int ASSOC, typename IDX, int MARCH>
+cudaError_t launch_march(const TraceParams& p, int mode, int grid, cudaStream_t s)
+{
+  const size_t smem = MARCH == 2 ? kBrickSmem : 0;
+  auto go = [&](auto kernel) {
+    // static (16 KiB table) + dynamic (bricks) shared memory exceed the 48 KiB a kernel gets by default;
+    // the opt-in is per device, so it is (cheaply) repeated per launch
+    if (MARCH == 2) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBrickSmem);
+    kernel<<<grid, kThreads, smem, s>>>(p);
+  };
+  if (mode == 0)      go(trace_kernel<KIND, FT, ASSOC, 0, IDX, MARCH>);
+  else if (mode == 1) go(trace_kernel<KIND, FT, ASSOC, 1, IDX, MARCH>);
+  else if (mode == 2) go(trace_kernel<KIND, FT, ASSOC, 2, IDX, MARCH>);
+  else if (mode == 5) go(trace_kernel<KIND, FT, ASSOC, 5, IDX, MARCH>);
+  else                go(trace_kernel<KIND, FT, ASSOC, 3, IDX, MARCH>);
+  return cudaGetLastError();
+}
+
+// which march a launch runs (the host decided what the block and the step allow: TraceParams::march)
 template <int KIND, typename FT, int ASSOC, typename IDX>
 cudaError_t launch_mode(const TraceParams& p, int mode, int grid, cudaStream_t s)
 {
-  if (mode == 0)      trace_kernel<KIND, FT, ASSOC, 0, IDX><<<grid, kThreads, 0, s>>>(p);
-  else if (mode == 1) trace_kernel<KIND, FT, ASSOC, 1, IDX><<<grid, kThreads, 0, s>>>(p);
-  else if (mode == 2) trace_kernel<KIND, FT, ASSOC, 2, IDX><<<grid, kThreads, 0, s>>>(p);
-  else if (mode == 4) trace_kernel<KIND, FT, ASSOC, 4, IDX><<<grid, kThreads, 0, s>>>(p);
-  else if (mode == 5) trace_kernel<KIND, FT, ASSOC, 5, IDX><<<grid, kThreads, 0, s>>>(p);
-  else                trace_kernel<KIND, FT, ASSOC, 3, IDX><<<grid, kThreads, 0, s>>>(p);
-  return cudaGetLastError();
+  if (mode == 4) // the demand-staging pre-pass visits cells only: general march
+  {
+    trace_kernel<KIND, FT, ASSOC, 4, IDX, 0><<<grid, kThreads, 0, s>>>(p);
+    return cudaGetLastError();
+  }
+  if (KIND == 0 && ASSOC == VR_POINT)
+  {
+    if (p.march == 1) return launch_march<0, FT, VR_POINT, IDX, 1>(p, mode, grid, s);
+    if (p.march == 2 && sizeof(FT) == 4) return launch_march<0, float, VR_POINT, IDX, 2>(p, mode, grid, s);
+  }
+  return launch_march<KIND, FT, ASSOC, IDX, 0>(p, mode, grid, s);
 }
 template <int KIND, typename FT, int ASSOC>
 cudaError_t launch_idx(const TraceParams& p, int mode, int grid, cudaStream_t s)
@@ -578,7 +984,8 @@ cudaError_t launch_trace(const TraceParams& p, int mode_partials, int sm_count, 
   const long long n_tiles = (long long)p.tiles_x * p.tiles_y + (mode_partials == 2 ? p.n_clear_chunks : 0);
   if (n_tiles <= 0) return cudaSuccess;
   // persistent grid: SMs x resident CTAs (4 warps each), capped by the work available
-  const int ctas_per_sm = p.ctas_per_sm > 0 ? p.ctas_per_sm : VR_MIN_BLOCKS;
+  const bool std_march = mode_partials == 4 || p.march == 0;
+  const int ctas_per_sm = p.ctas_per_sm > 0 && std_march ? p.ctas_per_sm : (std_march ? VR_MIN_BLOCKS : (p.march == 1 ? 7 : 3));
   long long grid = (long long)sm_count * ctas_per_sm;
   const long long need = (n_tiles + 3) / 4;
   if (grid > need) grid = need;

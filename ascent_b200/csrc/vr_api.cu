@@ -9,6 +9,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cuda.h> // CUtensorMap types only: the encoder is looked up through the runtime, libcuda is not linked
+
 #include "vr_color_table.hpp"
 #include "vr_host_math.hpp"
 #include "vr_internal.h"
@@ -48,6 +50,8 @@ static vr_status ensure_frame(vr_ctx* ctx, int W, int H);
 namespace vr { vr_status comm_ahead_image(vr_ctx* ctx, uchar4** rgba, float** depth); } // comm.cu
 namespace vr { vr_status comm_push_target(vr_ctx* ctx, bool ahead, int width, int height, vr::TraceParams& p); }
 namespace vr { vr_status comm_check_errors(vr_ctx* ctx); }
+namespace vr { void comm_join_for_image_trace(vr_ctx* ctx); }
+namespace vr { unsigned long long* comm_timeline_slot(vr_ctx* ctx, int k); }
 static void fill_to_canvas_params(const vr_camera* cam, int W, int H, ToCanvasParams& tp);
 
 // ================================================================= context
@@ -70,6 +74,7 @@ extern "C" vr_status vr_create(int device, vr_ctx** out)
                 prop.major, prop.minor);
   if ((e = cudaSetDevice(device)) != cudaSuccess)
     return fail(nullptr, VR_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaGetLastError(); // a stale error of some earlier, unrelated runtime call must not fail this one
   ctx = new vr_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
@@ -81,6 +86,8 @@ extern "C" vr_status vr_create(int device, vr_ctx** out)
   ctx->stream = ctx->own_stream;
   if (const char* e = std::getenv("VR_CTAS_PER_SM")) ctx->ctas_per_sm = std::atoi(e); // tuning knob
   if (const char* e = std::getenv("VR_COUNT_SAMPLES")) ctx->count_samples = std::atoi(e) != 0;
+  if (const char* e = std::getenv("VR_NO_SPARSE")) ctx->no_sparse = std::atoi(e) != 0; // A/B knobs: general march only
+  if (const char* e = std::getenv("VR_NO_BRICK")) ctx->no_brick = std::atoi(e) != 0;
   cudaMalloc(&ctx->tile_counter, (size_t)(1 + vr::kMaxLayers) * sizeof(unsigned int)); // [0]: single launches
   for (int k = 0; k < vr::kAuxStreams; ++k)
   {
@@ -106,6 +113,9 @@ extern "C" vr_status vr_create(int device, vr_ctx** out)
 
 static void free_block(Block& b)
 {
+  if (b.tmap_dev) cudaFree(b.tmap_dev);
+  b.tmap_dev = nullptr;
+  b.dev.tmap = nullptr;
   if (b.owned_field) cudaFree(b.owned_field);
   if (b.owned_axes) cudaFree(b.owned_axes);
   if (b.line_want) cudaFree(b.line_want);
@@ -195,7 +205,26 @@ extern "C" vr_status vr_synchronize(vr_ctx* ctx)
 
 extern "C" uint64_t vr_kernel_launches(const vr_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" vr_status vr_comm_join(vr_ctx* ctx)
+{
+  VR_ENTER_RO(ctx); // (the prologue is the join)
+  return VR_OK;
+}
+
+extern "C" vr_status vr_comm_timeline(vr_ctx* ctx, uint64_t out_ns[16])
+{
+  VR_ENTER_RO(ctx);
+  REQUIRE(out_ns, "vr_comm_timeline: NULL output");
+  unsigned long long* src = comm_timeline_slot(ctx, 0);
+  REQUIRE(src != nullptr, "vr_comm_timeline: no exchange arena, or VR_TIMELINE was not set at vr_comm_init");
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(out_ns, src, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return VR_OK;
+}
+
 // ================================================================= blocks
+static bool encode_brick_tensor_map(const BlockDev& b, unsigned char out[128]);
+
 static size_t field_bytes(const BlockDev& d)
 {
   const size_t n = d.assoc == VR_POINT ? (size_t)d.dims[0] * d.dims[1] * d.dims[2]
@@ -321,7 +350,20 @@ extern "C" vr_status vr_block_uniform(vr_ctx* ctx, int block_id, const int dims[
   Block* old = it != ctx->blocks.end() ? &it->second : nullptr;
   vr_status st = upload_field(ctx, b, field, dtype, assoc, where, old);
   if (st != VR_OK) { free_block(b); return st; }
-  if (old && (old->owned_field || old->owned_axes || old->line_want || old->line_have))
+  // dense-sampling candidates get the brick march's tensor map now (f32 point field, x-rows on 16-byte
+  // boundaries, resident in device memory); 128 bytes, copied synchronously
+  if (dtype == VR_F32 && assoc == VR_POINT && dims[0] % 4 == 0 && where != VR_HOST_STAGED && where != VR_HOST_MAPPED &&
+      (reinterpret_cast<uintptr_t>(b.dev.field) & 15) == 0 && !ctx->no_brick)
+  {
+    alignas(64) unsigned char m[128];
+    if (encode_brick_tensor_map(b.dev, m) && cudaMalloc(&b.tmap_dev, 128) == cudaSuccess)
+    {
+      if (cudaMemcpy(b.tmap_dev, m, 128, cudaMemcpyHostToDevice) == cudaSuccess) b.dev.tmap = b.tmap_dev;
+    }
+    else
+      cudaGetLastError();
+  }
+  if (old && (old->owned_field || old->owned_axes || old->line_want || old->line_have || old->tmap_dev))
   {
     cudaStreamSynchronize(ctx->stream);
     free_block(*old);
@@ -540,7 +582,6 @@ extern "C" vr_status vr_canvas_download_rgba8(vr_ctx* ctx, const float* bg_rgba,
   {
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->enc_rgba);
-  cudaFree(ctx->scratch_u64);
     ctx->enc_rgba = nullptr;
     ctx->enc_cap = 0;
     CK(cudaMalloc(&ctx->enc_rgba, n * sizeof(uchar4)));
@@ -599,6 +640,42 @@ static vr_status stage_for_trace(vr_ctx* ctx, int block_id, const TraceParams& p
   return VR_OK;
 }
 
+// The 3-D tensor map of a block's f32 point field with the brick march's box (sampler.cu: kBrickX/Y/Z):
+// cuTensorMapEncodeTiled through cudaGetDriverEntryPoint.  Returns false when the driver cannot encode it.
+static const int kBrickBox[3] = { 16, 10, 10 };
+static bool encode_brick_tensor_map(const BlockDev& b, unsigned char out[128])
+{
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn fn = nullptr;
+  static bool looked_up = false;
+  if (!looked_up)
+  {
+    looked_up = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<encode_fn>(sym);
+    else
+      cudaGetLastError();
+  }
+  if (!fn) return false;
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+  alignas(64) CUtensorMap m;
+  const cuuint64_t dims[3] = { (cuuint64_t)b.dims[0], (cuuint64_t)b.dims[1], (cuuint64_t)b.dims[2] };
+  const cuuint64_t strides[2] = { (cuuint64_t)b.dims[0] * 4, (cuuint64_t)b.dims[0] * (cuuint64_t)b.dims[1] * 4 };
+  const cuuint32_t box[3] = { (cuuint32_t)kBrickBox[0], (cuuint32_t)kBrickBox[1], (cuuint32_t)kBrickBox[2] };
+  const cuuint32_t estr[3] = { 1, 1, 1 };
+  const CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(b.field), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  std::memcpy(out, &m, 128);
+  return true;
+}
+
 static vr_status fill_trace_params(vr_ctx* ctx, int block_id, const vr_camera* cam, float sample_dist,
                                    float range_min, float range_max, int use_depth, int W, int H,
                                    TraceParams& p)
@@ -646,8 +723,44 @@ static vr_status fill_trace_params(vr_ctx* ctx, int block_id, const vr_camera* c
   p.sample_dist = sample_dist > 0.f ? sample_dist : mag / 200.f;
   p.range_min = range_min;
   p.inv_delta_scalar = (range_max - range_min) != 0.f ? 1.f / (range_max - range_min) : range_min;
+  p.march = 0;
+  if (b.dev.kind == 0)
+  {
+    float min_inv = b.dev.inv_spacing[0], min_sp = b.dev.spacing[0], big = 0.f;
+    for (int k = 0; k < 3; ++k)
+    {
+      p.dims_m1[k] = (float)(b.dev.dims[k] - 1);
+      p.dims_m2[k] = (float)(b.dev.dims[k] - 2);
+      min_inv = std::min(min_inv, b.dev.inv_spacing[k]);
+      min_sp = std::min(min_sp, b.dev.spacing[k]);
+      big = std::max(big, std::max(std::fabs(b.dev.min_point[k]), std::fabs(b.dev.max_point[k])));
+    }
+    // Along its dominant axis a unit direction has |d_k| >= 1/sqrt(3), so a step of >= 2.6 of the LARGEST
+    // voxel edge moves every ray by >= 1.5 cells on some axis.  With the previous sample inside its cell
+    // (0 <= t <= 1) the next one then lies outside [0,1] on that axis by half a cell, while the f32
+    // rounding of p += step is below ulp(|p|) <= 1.2e-7 * |block coordinates| -- less than 1 % of a cell
+    // when the smallest edge is >= 1e-4 of the coordinates' magnitude.  The reference therefore takes its
+    // "new cell" branch on every sample, which is all the sparse march does.
+    const bool well_conditioned = min_sp >= big * 1e-4f && b.dev.dims[0] < (1 << 22) && b.dev.dims[1] < (1 << 22) &&
+                                  b.dev.dims[2] < (1 << 22);
+    const long long slice = (long long)b.dev.dims[0] * b.dev.dims[1];
+    p.slice_elems = slice < (1ll << 31) ? (int)slice : 0;
+    if (b.dev.assoc == VR_POINT && well_conditioned && p.slice_elems > 0 && p.sample_dist * min_inv >= 2.6f &&
+        !ctx->no_sparse)
+      p.march = 1;
+    // Dense steps: stage bricks of the field in shared memory with TMA bulk copies.  Needs f32 scalars whose
+    // x-rows start on 16-byte boundaries (row length a multiple of 4, 16-byte aligned base) and, to pay off,
+    // a step of at most two of the SMALLEST voxel edges (neighbouring samples then share cells / rows).
+    float max_inv = b.dev.inv_spacing[0];
+    for (int k = 1; k < 3; ++k) max_inv = std::max(max_inv, b.dev.inv_spacing[k]);
+    if (p.march == 0 && b.dev.assoc == VR_POINT && b.dev.dtype == VR_F32 && b.dev.dims[0] % 4 == 0 &&
+        (reinterpret_cast<uintptr_t>(b.dev.field) & 15) == 0 && p.sample_dist * max_inv <= 2.0f && !ctx->no_brick &&
+        !b.staged_src && b.dev.tmap)
+      p.march = 2;
+  }
   p.lut = ctx->lut;
   p.lut_size = ctx->lut_size;
+  p.cms_f = (float)(ctx->lut_size - 1);
   p.canvas_rgba = ctx->canvas_rgba;
   p.canvas_depth = ctx->canvas_depth;
   p.tile_counter = ctx->tile_counter;
@@ -691,8 +804,14 @@ extern "C" vr_status vr_trace_to_image(vr_ctx* ctx, int block_id, const vr_camer
                                        int height, float sample_dist, float range_min,
                                        float range_max, int flags)
 {
-  VR_ENTER_RO(ctx);
-  if (flags & VR_FRAME_WRITE_CANVAS) ++ctx->api_serial; // writes the canvas
+  VR_ENTER_NOJOIN(ctx);
+  if (flags & VR_FRAME_WRITE_CANVAS)
+  {
+    ++ctx->api_serial; // writes the canvas: after everything the latest exchange does to it
+    VR_JOIN(ctx);
+  }
+  else
+    comm_join_for_image_trace(ctx); // image only: may overlap the latest exchange (see vr_internal.h)
   CK(cudaSetDevice(ctx->device));
   vr_status st = ensure_frame(ctx, width, height);
   if (st != VR_OK) return st;
@@ -731,6 +850,8 @@ extern "C" vr_status vr_trace_to_image(vr_ctx* ctx, int block_id, const vr_camer
   // (a width that is not a multiple of 4 has no announced rectangle -- the exchange reads the whole
   // image -- so such frames are always cleared)
   p.n_clear_chunks = (((flags & VR_FRAME_NO_CLEAR) && p.vec_ok) || push) ? 0 : (int)(((size_t)width * height + 511) / 512);
+  p.end_stamp = comm_timeline_slot(ctx, 6);
+  if (p.end_stamp) CK(cudaMemsetAsync(p.end_stamp, 0, sizeof(unsigned long long), ctx->stream));
   st = stage_for_trace(ctx, block_id, p, ctx->stream, ctx->tile_counter, true);
   if (st != VR_OK) return st;
   CK(launch_trace(p, push ? 5 : 2, ctx->sm_count, ctx->stream));

@@ -24,6 +24,9 @@ struct BlockDev
   float min_point[3], max_point[3], inv_spacing[3];
   const float* axis[3];        // rectilinear: axes narrowed to f32 once on upload
   const void* field;
+  // brick march: the CUtensorMap (128 bytes in device memory, 64-byte aligned) of the field as a 3-D f32
+  // tensor with a kBrick^3 box, encoded when the block is published; null when the block does not qualify
+  const void* tmap;
 };
 
 // Everything one trace launch needs; passed by value as a __grid_constant__.
@@ -47,6 +50,14 @@ struct TraceParams
   float bmin[3], bmax[3];
   // K4
   float mesh_eps, sample_dist, range_min, inv_delta_scalar;
+  // uniform blocks: (float)(dims - 1), (float)(dims - 2) for the locator's upper-face fix-up, and which
+  // march the sampler runs.  Sparse: EVERY step of EVERY ray is guaranteed to leave its cell (step >= 2.6
+  // voxels on a well-conditioned grid), so no sample ever tests for a cell change.  Brick: dense steps
+  // (<= 2 voxels) through an f32 point field whose x-rows can be bulk-copied (16-byte aligned).
+  float dims_m1[3], dims_m2[3];
+  int march;        // 0 general, 1 sparse, 2 brick (TMA-staged): chosen by the host per launch
+  int slice_elems;  // dims[0] * dims[1] when that fits 31 bits (sparse march: one z-slice of the field, in elements)
+  float cms_f;      // (float)(lut_size - 1)
   int lut_size;
   const float4* lut;
   // K7
@@ -73,6 +84,7 @@ struct TraceParams
   // dynamic tile scheduler + sample counter
   unsigned int* tile_counter;
   unsigned long long* sample_counter; // may be null
+  unsigned long long* end_stamp;      // diagnostics: atomicMax of globaltimer at CTA exit (may be null)
   int ctas_per_sm;                    // 0 = default
 };
 
@@ -81,6 +93,7 @@ struct Block
 {
   BlockDev dev;
   void* owned_field = nullptr; // device copy we own (null when adopted)
+  void* tmap_dev = nullptr;    // the brick march's tensor map (owned)
   float* owned_axes = nullptr;
   double bounds[6];
   // VR_HOST_STAGED: the field stays in mapped host memory; owned_field is a device buffer of the
@@ -110,6 +123,15 @@ struct Comm
   unsigned int lepoch = 0;                      // layer path frames
   unsigned int sepoch = 0;                      // depth broadcasts
   unsigned long long timeout_ns = 0;            // bound of every cross-rank wait inside the kernels
+  // The image exchange runs on its own stream so that it overlaps the NEXT frame's trace (the folded
+  // pixels drain into rank 0 over NVLink while the sampler is already busy): ev_trace orders it after the
+  // trace that produced the image, ev_x[e & 1] marks exchange e done.  Every entry point first makes the
+  // context's stream wait for the latest exchange (x_pending), except an image-only vr_trace_to_image,
+  // which only needs the one before (its ring slot is then free on every rank).
+  cudaStream_t xstream = nullptr;
+  cudaEvent_t ev_trace = nullptr, ev_x[2] = { nullptr, nullptr };
+  bool x_pending = false;                       // exchange `epoch` may still be running on xstream
+  bool timeline = false;                        // VR_TIMELINE=1: kernels leave globaltimer stamps in the flags
   bool frame_poisoned = false;                  // a rank-local error hit this frame: the next collective aborts
   // rank 0: "this buffer holds the cleared value outside the rectangle kept in the arena flags",
   // valid while api_serial has not moved and the frame size is the same
@@ -124,8 +146,19 @@ struct Comm
 // re-clearing the parts of the result image / canvas they left cleared last time, which is only sound
 // if nothing else may have written those buffers since -- any entry point that is not explicitly
 // marked read-only (VR_ENTER_RO: never writes the canvas or the composited image) invalidates that.
-#define VR_ENTER(ctx) do { if (!(ctx)) return VR_ERR_INVALID; ++(ctx)->api_serial; } while (0)
-#define VR_ENTER_RO(ctx) do { if (!(ctx)) return VR_ERR_INVALID; } while (0)
+#define VR_JOIN(ctx)                                                                               \
+  do                                                                                               \
+  {                                                                                                \
+    if ((ctx)->comm.x_pending)                                                                     \
+    {                                                                                              \
+      cudaStreamWaitEvent((ctx)->stream, (ctx)->comm.ev_x[(ctx)->comm.epoch & 1], 0);              \
+      (ctx)->comm.x_pending = false;                                                               \
+    }                                                                                              \
+  } while (0)
+#define VR_ENTER(ctx) do { if (!(ctx)) return VR_ERR_INVALID; ++(ctx)->api_serial; VR_JOIN(ctx); } while (0)
+#define VR_ENTER_RO(ctx) do { if (!(ctx)) return VR_ERR_INVALID; VR_JOIN(ctx); } while (0)
+// (vr_trace_to_image: joins selectively, see there)
+#define VR_ENTER_NOJOIN(ctx) do { if (!(ctx)) return VR_ERR_INVALID; } while (0)
 
 struct vr_ctx
 {
@@ -139,6 +172,8 @@ struct vr_ctx
   int sm_count = 148;
   int ctas_per_sm = 0;        // trace kernel residency (0 = built-in default)
   bool count_samples = false; // accumulate the number of samples taken (debug/bench)
+  bool no_sparse = false;     // never select the sampler's sparse march (A/B runs)
+  bool no_brick = false;      // never select the brick march (A/B runs)
 
   std::map<int, vr::Block> blocks;
   float4* lut = nullptr;
@@ -444,6 +479,7 @@ struct FoldP2PParams
   size_t share_groups;
   size_t off_recv_rgba, off_recv_depth;
   unsigned long long timeout_ns; // bound of every cross-rank wait (0 = none)
+  int timeline;                  // diagnostics: leave globaltimer stamps in the flags
 };
 cudaError_t launch_fold_p2p(const FoldP2PParams& p, int sm_count, cudaStream_t s);
 } // namespace vr

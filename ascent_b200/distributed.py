@@ -225,6 +225,7 @@ def run_bench(args, wl, bench):
                 marks[k][1].record(stream)
                 composite()
                 marks[k][2].record(stream)
+            ctx.comm_join()  # the last exchange runs on the library's exchange stream: inside the timed region
             t1.record(stream)
             torch.cuda.synchronize()
             dist.barrier()
@@ -255,6 +256,7 @@ def run_bench(args, wl, bench):
             a, b = ev(), ev()
             a.record(stream)
             composite()
+            ctx.comm_join()
             b.record(stream)
             torch.cuda.synchronize()
             comp.append(a.elapsed_time(b))
@@ -272,6 +274,31 @@ def run_bench(args, wl, bench):
     dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
     total_ms, render_ms, tail_ms, comp_ms = [float(x) for x in tmax[:4]]
     ms = total_ms / args.steps
+
+    # ---- diagnostics (VR_TIMELINE=1): where the time of one exchange goes on every rank, from the
+    # globaltimer stamps the kernels leave in the arena flags (per GPU; differences only)
+    timeline = None
+    if path_a and os.environ.get("VR_TIMELINE") == "1":
+        rows = []
+        with torch.cuda.stream(stream):
+            for _ in range(8):
+                torch.cuda.synchronize()
+                dist.barrier()
+                render()
+                composite()
+                tl = ctx.comm_timeline()
+                rows.append([(tl[0] - tl[6]) * 1e-3, (tl[1] - tl[0]) * 1e-3, (tl[2] - tl[1]) * 1e-3,
+                             (tl[3] - tl[2]) * 1e-3 if rank == 0 else 0.0, (tl[4] - tl[3]) * 1e-3 if rank == 0 else 0.0,
+                             (tl[5] - tl[4]) * 1e-3 if rank == 0 else 0.0,
+                             (tl[8] - tl[1]) * 1e-3, (tl[9] - tl[8]) * 1e-3, (tl[10] - tl[9]) * 1e-3,
+                             (tl[11] - tl[10]) * 1e-3, (tl[2] - tl[11]) * 1e-3])
+        tt = torch.tensor(np.median(np.array(rows[2:]), axis=0), dtype=torch.float64, device="cuda")
+        allt = [torch.empty_like(tt) for _ in range(world)]
+        dist.all_gather(allt, tt)
+        timeline = {"columns": ["trace_end_to_fold_start", "wait_all_ready", "fold", "fold_end_to_canvas_start(rank0)",
+                                "wait_all_done(rank0)", "to_canvas(rank0)", "cta0:prologue", "cta0:own_chunks",
+                                "cta0:rank0_clears", "cta0:fence+count", "cta0_end_to_last_cta_out"],
+                    "rows_us": [[round(float(x), 2) for x in r] for r in allt]}
 
     nccl_base = None
     if path_a and getattr(args, "nccl_baseline", False):
@@ -371,7 +398,7 @@ def run_bench(args, wl, bench):
                            "achieved_gbs": nv_bytes / (comp_ms * 1e-3) / 1e9, "peak_gbs": 770.0,
                            "peak_source": "measured peer copy per direction (B200_PROFILING.md)",
                            "how": "bytes from the frame's geometry (screen rectangles), time = composite_ms_per_frame"},
-                "nccl_baseline": nccl_base,
+                "nccl_baseline": nccl_base, "exchange_timeline": timeline,
                 "t1_same_run": t1,
                 "e2e": e2e, "gpu_launches": int(tsum[4]), "clocks": clk,
                 "roofline": roof, "parity": parity, "cpu_baseline": cpu}

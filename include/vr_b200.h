@@ -300,8 +300,15 @@ VR_API vr_status vr_comm_connect(vr_ctx* ctx, const void* all_handles /* n_ranks
  * images + visibility-ordered fold + gather to rank 0, fused in one kernel per rank (peer
  * loads of the owned tile from every rank, peer store of the folded tile into rank 0).
  * vis_order[r] = composite order of rank r's image (VolumeRenderer.cpp:833-867).
- * On rank 0 the composited image is left in the context (vr_image_result_*).                   */
+ * On rank 0 the composited image is left in the context (vr_image_result_*).
+ * The exchange is queued on an internal stream, after everything queued on the context so far; the
+ * next image-only vr_trace_to_image (no VR_FRAME_WRITE_CANVAS) may overlap it -- the folded pixels drain
+ * into rank 0 while the sampler is already on the next frame -- and every other entry point first waits
+ * for it on the context's stream, so callers see plain in-order semantics.                        */
 VR_API vr_status vr_comm_composite_images(vr_ctx* ctx, const int* vis_order);
+/* Make the context's stream wait for the exchange queued last (no host synchronisation): for callers
+ * that time or order their own work on that stream against the exchange.                         */
+VR_API vr_status vr_comm_join(vr_ctx* ctx);
 /* The same plus Renderer::ImageToCanvas on rank 0 (vr_image_result_to_canvas) folded into the
  * exchange: rank 0 converts the pixels no rank covers while the others are still in flight.    */
 VR_API vr_status vr_comm_composite_images_to_canvas(vr_ctx* ctx, const int* vis_order);
@@ -329,6 +336,13 @@ VR_API vr_status vr_comm_composite_partials_to_canvas(vr_ctx* ctx, const vr_came
  * NVLink, folds and stores finished pixels into rank 0's canvas.  vr_layers_begin must have been
  * called after vr_comm_connect (the layers then live in the exchange arena).                     */
 VR_API vr_status vr_comm_layers_composite_to_canvas(vr_ctx* ctx, const vr_camera* cam);
+/* Diagnostics (VR_TIMELINE=1 in the environment at vr_comm_init): %globaltimer stamps, in ns, that the
+ * kernels of the last image exchange left on this GPU -- [0] fold kernel entered, [1] every rank's image
+ * ready, [2] last fold CTA out, [3] rank 0's to-canvas kernel entered, [4] every rank's pixels landed,
+ * [5] to-canvas done, [6] end of the last vr_trace_to_image kernel, [7] unused; CTA 0 of the fold
+ * kernel: [8] prologue done, [9] own chunks folded, [10] rank 0's clears done, [11] fenced and counted;
+ * [12..15] unused.  Syncs.                                                                       */
+VR_API vr_status vr_comm_timeline(vr_ctx* ctx, uint64_t out_ns[16]);
 /* Device pointers into this rank's arena for transports that move the bytes themselves
  * (NCCL send/recv baseline in the harness).                                                    */
 VR_API vr_status vr_image_ptrs(vr_ctx* ctx, void** rgba8_dev, void** depth_dev);
