@@ -44,6 +44,7 @@ constexpr int kMaxRanks = 16;
 // frame e+1 reuses the slot of frame e-3, and every peer has finished reading e-3 once this rank's
 // exchange of e-2 -- the one before the latest, which vr_trace_to_image waits for -- has completed.
 constexpr int kImgRing = 4;
+constexpr int kLayerRing = 3; // ray layers of frame e live in buffer e % 3 (same argument, no frame is traced ahead)
 
 struct Flags
 {
@@ -688,7 +689,7 @@ struct Layout
 {
   size_t off_flags, off_img_rgba[kImgRing], off_img_depth[kImgRing], off_res_rgba[2], off_res_depth[2];
   size_t off_poff[2], off_psorted[2], off_pout, off_canvas_rgba, off_canvas_depth, total;
-  size_t off_lflags, off_ltab[2], off_lpool_rgba[2], off_lpool_depth[2];
+  size_t off_lflags, off_ltab[kLayerRing], off_lpool_rgba[kLayerRing], off_lpool_depth[kLayerRing];
   size_t off_sync_depth;
   // receive ring of pushed frames: slot e % 3 holds, for every source rank, the pixels of frame e that
   // THIS rank owns (round-robin 1024-pixel chunks), written by the sources' samplers over NVLink
@@ -712,9 +713,9 @@ Layout make_layout(size_t max_pixels, size_t max_partials, bool is_root)
   for (int b = 0; b < 2; ++b) { L.off_psorted[b] = o; o += align_up(max_partials * sizeof(vr_partial), 256); }
   // dense ray layers (layers.cu): flags, layer tables and pools, double-buffered
   L.off_lflags = o; o += max_partials ? kFlagBytes : 0;
-  for (int b = 0; b < 2; ++b) { L.off_ltab[b] = o; o += max_partials ? align_up(sizeof(LayerTable), 256) : 0; }
-  for (int b = 0; b < 2; ++b) { L.off_lpool_rgba[b] = o; o += align_up(max_partials * sizeof(float4), 256); }
-  for (int b = 0; b < 2; ++b) { L.off_lpool_depth[b] = o; o += align_up(max_partials * sizeof(float), 256); }
+  for (int b = 0; b < kLayerRing; ++b) { L.off_ltab[b] = o; o += max_partials ? align_up(sizeof(LayerTable), 256) : 0; }
+  for (int b = 0; b < kLayerRing; ++b) { L.off_lpool_rgba[b] = o; o += align_up(max_partials * sizeof(float4), 256); }
+  for (int b = 0; b < kLayerRing; ++b) { L.off_lpool_depth[b] = o; o += align_up(max_partials * sizeof(float), 256); }
   // regions only rank 0 allocates; their OFFSETS are the same on every rank (peers address them)
   const size_t common_end = o;
   L.off_pout = o;
@@ -738,13 +739,12 @@ template <int NR>
 static cudaError_t launch_fold_p2p_nr(const FoldP2PParams& p, int sm_count, cudaStream_t s)
 {
   auto go = [&](auto kernel) {
-    // persistent grid = the CTAs resident at once (register-limited), capped by this rank's chunks
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0);
-    if (per_sm < 1) per_sm = 1;
+    // One CTA per SM: the exchange overlaps the next frame's trace (exchange stream), so what counts is how
+    // few SM resources it holds while its stores drain over NVLink -- and every CTA ends with one
+    // system-scope fence, which is the expensive part -- not how fast it would run alone.
     const size_t n4 = (p.n_pixels + 3) / 4;
     const size_t n_chunks = (n4 + kChunkGroups - 1) / kChunkGroups;
-    size_t grid = (size_t)sm_count * per_sm;
+    size_t grid = (size_t)sm_count;
     const size_t want = p.rank == 0 ? n_chunks : (n_chunks + p.size - 1) / p.size;
     if (grid > want) grid = want ? want : 1;
     kernel<<<(unsigned)grid, 256, 0, s>>>(p);
@@ -828,13 +828,14 @@ vr_status comm_ahead_image(vr_ctx* ctx, uchar4** rgba, float** depth)
   return VR_OK;
 }
 
-// vr_trace_to_image without VR_FRAME_WRITE_CANVAS touches only this frame's ring slot: it may start
-// while the latest exchange is still running, but not before the one before it has completed
-void comm_join_for_image_trace(vr_ctx* ctx)
+// vr_trace_to_image without VR_FRAME_WRITE_CANVAS, and the layer tracing calls without a canvas-depth
+// clamp, touch only the new frame's ring slot / layer buffer: they may start while the latest exchange is
+// still running, but not before the one before it has completed
+void comm_join_previous_exchange(vr_ctx* ctx)
 {
   Comm& c = ctx->comm;
-  if (!c.on || !c.xstream || c.epoch < 2) return;
-  cudaStreamWaitEvent(ctx->stream, c.ev_x[(c.epoch - 1) & 1], 0);
+  if (!c.on || !c.xstream || c.xserial < 2) return;
+  cudaStreamWaitEvent(ctx->stream, c.ev_x[(c.xserial - 1) & 1], 0);
 }
 
 // receive-slot geometry of a pushed frame (sampler mode 5)
@@ -903,7 +904,7 @@ vr_status comm_bind_layers(vr_ctx* ctx)
 {
   Comm& c = ctx->comm;
   const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
-  const int b = (c.lepoch + 1) & 1;
+  const int b = (int)((c.lepoch + 1) % kLayerRing);
   if (!ctx->layers_in_arena)
   {
     cudaStreamSynchronize(ctx->stream);
@@ -1107,7 +1108,7 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
     if (p.canvas_rgba)
     {
       // waits for every rank's "done" itself, then converts the covered groups
-      covered_to_canvas_kernel<<<ctx->sm_count * 4, 256, 0, xs>>>(p);
+      covered_to_canvas_kernel<<<ctx->sm_count * 2, 256, 0, xs>>>(p);
       ctx->launches++;
     }
     else
@@ -1133,7 +1134,8 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
   }
   if (xs != ctx->stream)
   {
-    cudaEventRecord(c.ev_x[c.epoch & 1], xs);
+    c.xserial += 1;
+    cudaEventRecord(c.ev_x[c.xserial & 1], xs);
     c.x_pending = true;
   }
   // the next frame's image: the following ring slot -- where a frame traced ahead already sits
@@ -1372,7 +1374,7 @@ extern "C" vr_status vr_comm_layers_composite_to_canvas(vr_ctx* ctx, const vr_ca
   cudaSetDevice(ctx->device);
   const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
   c.lepoch += 1;
-  const int par = c.lepoch & 1;
+  const int par = (int)(c.lepoch % kLayerRing);
   vr_status st = upload_layer_table_pub(ctx); // into the arena table of this parity (bound at vr_layers_begin)
   if (st != VR_OK) return st;
   if (c.rank == 0)
@@ -1420,14 +1422,28 @@ extern "C" vr_status vr_comm_layers_composite_to_canvas(vr_ctx* ctx, const vr_ca
     ctx->lW = ctx->lH = 0;
     return VR_ERR_INVALID;
   }
-  cudaError_t e = launch_layers_fold(p, true, ctx->sm_count, ctx->stream);
+  // on the exchange stream: after everything queued on the context so far (the traces that filled the layers,
+  // the table upload), overlapping whatever the caller traces next
+  cudaStream_t xs = c.xstream ? c.xstream : ctx->stream;
+  if (xs != ctx->stream)
+  {
+    cudaEventRecord(c.ev_trace, ctx->stream);
+    cudaStreamWaitEvent(xs, c.ev_trace, 0);
+  }
+  cudaError_t e = launch_layers_fold(p, true, ctx->sm_count, xs);
   if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "layers_fold launch", e);
   ctx->launches++;
   if (c.rank == 0)
   {
-    e = launch_layers_wait_done(c.arena + L.off_lflags, c.size, c.lepoch, c.timeout_ns, ctx->stream);
+    e = launch_layers_wait_done(c.arena + L.off_lflags, c.size, c.lepoch, c.timeout_ns, xs);
     if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "layers wait launch", e);
     ctx->launches++;
+  }
+  if (xs != ctx->stream)
+  {
+    c.xserial += 1;
+    cudaEventRecord(c.ev_x[c.xserial & 1], xs);
+    c.x_pending = true;
   }
   ctx->lW = ctx->lH = 0; // the frame is consumed: vr_layers_begin starts the next one
   return VR_OK;

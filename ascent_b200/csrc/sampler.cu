@@ -81,6 +81,13 @@ __device__ __forceinline__ void locate_axis_rect(const float* __restrict__ ax, i
   inv_sp = 1.f / (maxVal - minVal);
 }
 
+// k-th element of 0..n-1 visited from the middle outwards: m, m+1, m-1, m+2, ... with m = (n-1)/2
+__device__ __forceinline__ int centre_out(int k, int n)
+{
+  const int m = (n - 1) >> 1;
+  return (k & 1) ? m + ((k + 1) >> 1) : m - (k >> 1);
+}
+
 __device__ __forceinline__ unsigned char quant_u8(float c)
 {
   // static_cast<unsigned char>(c * 255.f) on x86: cvttss2si then low byte
@@ -599,7 +606,11 @@ trace_kernel(const __grid_constant__ TraceParams P)
       clear_chunk(P, tile - n_tiles, lane);
       continue;
     }
-    const int ti = (int)(tile % (unsigned)P.tiles_x), tj = (int)(tile / (unsigned)P.tiles_x);
+    // tiles are handed out centre rows first, and centre-out within a row: rays through the middle of the
+    // block's screen rectangle are the long ones, so the kernel's tail -- a warp resident at a time draws
+    // only a handful of tiles -- is made of the short edge rays
+    const int rj = (int)(tile / (unsigned)P.tiles_x), ri = (int)(tile % (unsigned)P.tiles_x);
+    const int tj = centre_out(rj, P.tiles_y), ti = centre_out(ri, P.tiles_x);
     const int i = P.tx0 + ti * kTileW + lx;
     const int j = P.sy + tj * kTileH + ly;
     // tx0 <= sx: in MODE 2 the traced rectangle is widened to 4-pixel boundaries so that its

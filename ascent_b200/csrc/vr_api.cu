@@ -50,7 +50,7 @@ static vr_status ensure_frame(vr_ctx* ctx, int W, int H);
 namespace vr { vr_status comm_ahead_image(vr_ctx* ctx, uchar4** rgba, float** depth); } // comm.cu
 namespace vr { vr_status comm_push_target(vr_ctx* ctx, bool ahead, int width, int height, vr::TraceParams& p); }
 namespace vr { vr_status comm_check_errors(vr_ctx* ctx); }
-namespace vr { void comm_join_for_image_trace(vr_ctx* ctx); }
+namespace vr { void comm_join_previous_exchange(vr_ctx* ctx); }
 namespace vr { unsigned long long* comm_timeline_slot(vr_ctx* ctx, int k); }
 static void fill_to_canvas_params(const vr_camera* cam, int W, int H, ToCanvasParams& tp);
 
@@ -87,7 +87,11 @@ extern "C" vr_status vr_create(int device, vr_ctx** out)
   if (const char* e = std::getenv("VR_CTAS_PER_SM")) ctx->ctas_per_sm = std::atoi(e); // tuning knob
   if (const char* e = std::getenv("VR_COUNT_SAMPLES")) ctx->count_samples = std::atoi(e) != 0;
   if (const char* e = std::getenv("VR_NO_SPARSE")) ctx->no_sparse = std::atoi(e) != 0; // A/B knobs: general march only
-  if (const char* e = std::getenv("VR_NO_BRICK")) ctx->no_brick = std::atoi(e) != 0;
+  // The brick march (TMA-staged bricks) is bit-identical to the general march but measured SLOWER on B200 at
+  // the dense operating point (0.75 vs 0.54 ms on c2 at samples = 887: the per-sample arithmetic, not the
+  // gather latency, bounds that regime -- DESIGN.md section 4.1), so it is opt-in: VR_BRICK=1.
+  ctx->no_brick = true;
+  if (const char* e = std::getenv("VR_BRICK")) ctx->no_brick = std::atoi(e) == 0;
   cudaMalloc(&ctx->tile_counter, (size_t)(1 + vr::kMaxLayers) * sizeof(unsigned int)); // [0]: single launches
   for (int k = 0; k < vr::kAuxStreams; ++k)
   {
@@ -811,7 +815,7 @@ extern "C" vr_status vr_trace_to_image(vr_ctx* ctx, int block_id, const vr_camer
     VR_JOIN(ctx);
   }
   else
-    comm_join_for_image_trace(ctx); // image only: may overlap the latest exchange (see vr_internal.h)
+    comm_join_previous_exchange(ctx); // image only: may overlap the latest exchange (see vr_internal.h)
   CK(cudaSetDevice(ctx->device));
   vr_status st = ensure_frame(ctx, width, height);
   if (st != VR_OK) return st;
@@ -1033,7 +1037,9 @@ static vr_status ensure_layer_pool(vr_ctx* ctx, size_t need)
 
 extern "C" vr_status vr_layers_begin(vr_ctx* ctx, int width, int height)
 {
-  VR_ENTER(ctx);
+  VR_ENTER_NOJOIN(ctx); // (touches only the next frame's layer buffer: may overlap the latest exchange)
+  ++ctx->api_serial;
+  vr::comm_join_previous_exchange(ctx);
   REQUIRE(width > 0 && height > 0 && (long long)width * height < (1ll << 31), "bad image size");
   CK(cudaSetDevice(ctx->device));
   if (!ctx->ltab_host) ctx->ltab_host = new LayerTable(); // pageable on purpose: async copies stage it
@@ -1054,7 +1060,10 @@ extern "C" vr_status vr_layers_begin(vr_ctx* ctx, int width, int height)
 extern "C" vr_status vr_trace_to_layer(vr_ctx* ctx, int block_id, const vr_camera* cam, float sample_dist,
                                        float range_min, float range_max, int use_canvas_depth)
 {
-  VR_ENTER(ctx);
+  VR_ENTER_NOJOIN(ctx);
+  ++ctx->api_serial;
+  if (use_canvas_depth) VR_JOIN(ctx); // reads the canvas the latest exchange may still be writing
+  else vr::comm_join_previous_exchange(ctx);
   REQUIRE(ctx->lW > 0, "vr_trace_to_layer: call vr_layers_begin first");
   REQUIRE(!use_canvas_depth || (ctx->W == ctx->lW && ctx->H == ctx->lH),
           "vr_trace_to_layer: canvas depth requested but canvas size differs");
@@ -1093,7 +1102,10 @@ extern "C" vr_status vr_trace_blocks_to_layers(vr_ctx* ctx, int n_blocks, const 
                                                const vr_camera* cam, float sample_dist, float range_min,
                                                float range_max, int use_canvas_depth)
 {
-  VR_ENTER(ctx);
+  VR_ENTER_NOJOIN(ctx);
+  ++ctx->api_serial;
+  if (use_canvas_depth) VR_JOIN(ctx);
+  else vr::comm_join_previous_exchange(ctx);
   REQUIRE(ctx->lW > 0, "vr_trace_blocks_to_layers: call vr_layers_begin first");
   REQUIRE(n_blocks >= 0 && (n_blocks == 0 || block_ids), "vr_trace_blocks_to_layers: NULL block list");
   REQUIRE(!use_canvas_depth || (ctx->W == ctx->lW && ctx->H == ctx->lH),

@@ -125,12 +125,13 @@ struct Comm
   unsigned long long timeout_ns = 0;            // bound of every cross-rank wait inside the kernels
   // The image exchange runs on its own stream so that it overlaps the NEXT frame's trace (the folded
   // pixels drain into rank 0 over NVLink while the sampler is already busy): ev_trace orders it after the
-  // trace that produced the image, ev_x[e & 1] marks exchange e done.  Every entry point first makes the
+  // trace that produced the image, ev_x[n & 1] marks the n-th exchange done.  Every entry point first makes the
   // context's stream wait for the latest exchange (x_pending), except an image-only vr_trace_to_image,
   // which only needs the one before (its ring slot is then free on every rank).
   cudaStream_t xstream = nullptr;
   cudaEvent_t ev_trace = nullptr, ev_x[2] = { nullptr, nullptr };
-  bool x_pending = false;                       // exchange `epoch` may still be running on xstream
+  unsigned int xserial = 0;                     // exchanges queued on xstream so far (images and layers)
+  bool x_pending = false;                       // exchange `xserial` may still be running on xstream
   bool timeline = false;                        // VR_TIMELINE=1: kernels leave globaltimer stamps in the flags
   bool frame_poisoned = false;                  // a rank-local error hit this frame: the next collective aborts
   // rank 0: "this buffer holds the cleared value outside the rectangle kept in the arena flags",
@@ -151,7 +152,7 @@ struct Comm
   {                                                                                                \
     if ((ctx)->comm.x_pending)                                                                     \
     {                                                                                              \
-      cudaStreamWaitEvent((ctx)->stream, (ctx)->comm.ev_x[(ctx)->comm.epoch & 1], 0);              \
+      cudaStreamWaitEvent((ctx)->stream, (ctx)->comm.ev_x[(ctx)->comm.xserial & 1], 0);            \
       (ctx)->comm.x_pending = false;                                                               \
     }                                                                                              \
   } while (0)

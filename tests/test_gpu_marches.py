@@ -1,6 +1,7 @@
 """The sampler's three marches (general / sparse / brick, sampler.cu) must produce the same bits: every
-scene is rendered by two contexts, one restricted to the general march (VR_NO_SPARSE / VR_NO_BRICK are read
-at vr_create), one free to pick, and the float canvases are compared bit for bit -- plus the oracle."""
+scene is rendered by two contexts, one restricted to the general march, one free to pick any of the three
+(VR_NO_SPARSE / VR_BRICK are read at vr_create), and the float canvases are compared bit for bit -- plus the
+oracle."""
 import os
 
 import numpy as np
@@ -16,11 +17,12 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def ctxs():
     os.environ["VR_NO_SPARSE"] = "1"
-    os.environ["VR_NO_BRICK"] = "1"
+    os.environ["VR_BRICK"] = "0"
     g = _lib.Context(0)
     os.environ["VR_NO_SPARSE"] = "0"
-    os.environ["VR_NO_BRICK"] = "0"
+    os.environ["VR_BRICK"] = "1"   # the brick march is opt-in (slower than the general march on B200)
     p = _lib.Context(0)
+    del os.environ["VR_BRICK"], os.environ["VR_NO_SPARSE"]
     yield g, p
     g.close()
     p.close()
