@@ -362,8 +362,240 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
   }
 }
 
+// The same exchange with CTAs of 128 threads and <= 72 registers: exactly the footprint of ONE sampler CTA.
+// The exchange of frame k runs (exchange stream, highest priority) while the sampler -- a persistent grid that
+// holds every register of every SM until its tile counter runs dry -- is busy with frame k+1.  A 256-thread x
+// 128-register CTA (fold_p2p_kernel<8>) needs the slots of four sampler CTAs of one SM to be free at once,
+// which only happens at the very end of a trace; this one is placed as soon as ANY sampler CTA of any launch
+// retires.  The layers are folded in batches of four (8 + 8 registers each in flight) instead of all at once.
+// Same ownership, same fold order and operator as fold_p2p_kernel: the same bits.
+constexpr int kLightThreads = 128;
+template <bool TO_CANVAS, bool ZBUF>
+__global__ void __launch_bounds__(kLightThreads, 7) fold_p2p_light_kernel(const __grid_constant__ FoldP2PParams P)
+{
+  Flags* my_flags = reinterpret_cast<Flags*>(P.peers[P.rank] + P.off_flags);
+  const int par = P.epoch & 1;
+  if (blockIdx.x == 0 && threadIdx.x < P.size)
+  {
+    Flags* f = reinterpret_cast<Flags*>(P.peers[threadIdx.x] + P.off_flags);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ((volatile int*)f->img_rect[par][P.rank])[k] = P.rect[k];
+    ((volatile int*)f->img_pushed[par])[P.rank] = P.pushed;
+    __threadfence_system();
+    st_release_sys(&f->ready[P.rank], P.epoch);
+  }
+  if (P.timeline && blockIdx.x == 0 && threadIdx.x == 0) my_flags->timeline[0] = global_ns();
+  const bool go = wait_all_ready(err_of(my_flags), my_flags->ready, my_flags->aborted[kPathImage], kPathImage, P.size,
+                                 P.epoch, P.timeout_ns);
+  if (P.timeline && blockIdx.x == 0 && threadIdx.x == 0) my_flags->timeline[1] = global_ns();
+
+  __shared__ int s_rect[kMaxRanks][4]; // in fold order
+  __shared__ int s_pushed[kMaxRanks];  // in fold order
+  __shared__ int s_clean[2][4];        // rank 0: [0] result image of this parity, [1] canvas
+  __shared__ const uint4* s_lrgba[kMaxRanks];
+  __shared__ const float4* s_ldepth[kMaxRanks];
+  if (threadIdx.x < P.size * 4)
+  {
+    const int l = threadIdx.x >> 2, k = threadIdx.x & 3;
+    s_rect[l][k] = go ? ((volatile int*)my_flags->img_rect[par][P.order[l]])[k] : 0;
+  }
+  else if (threadIdx.x >= 64 && threadIdx.x < 64 + P.size)
+    s_pushed[threadIdx.x - 64] = ((volatile int*)my_flags->img_pushed[par])[P.order[threadIdx.x - 64]];
+  else if (threadIdx.x >= 96 && threadIdx.x < 104 && P.rank == 0)
+  {
+    const int k = threadIdx.x - 96;
+    s_clean[k >> 2][k & 3] = k < 4 ? ((volatile int*)my_flags->clean_res[par])[k] : ((volatile int*)my_flags->clean_canvas)[k - 4];
+  }
+  __syncthreads();
+  if (threadIdx.x < P.size)
+  {
+    const int l = threadIdx.x, src = P.order[l];
+    if (s_pushed[l])
+    {
+      s_lrgba[l] = reinterpret_cast<const uint4*>(P.peers[P.rank] + P.off_recv_rgba) + (size_t)src * P.share_groups;
+      s_ldepth[l] = reinterpret_cast<const float4*>(P.peers[P.rank] + P.off_recv_depth) + (size_t)src * P.share_groups;
+    }
+    else
+    {
+      s_lrgba[l] = reinterpret_cast<const uint4*>(P.peers[src] + P.off_img_rgba);
+      s_ldepth[l] = reinterpret_cast<const float4*>(P.peers[src] + P.off_img_depth);
+    }
+  }
+  uint4* out_rgba = reinterpret_cast<uint4*>(P.peers[0] + P.off_res_rgba);
+  float4* out_depth = reinterpret_cast<float4*>(P.peers[0] + P.off_res_depth);
+
+  const size_t n4 = (P.n_pixels + 3) / 4;
+  const int w4 = P.W >= 4 ? P.W / 4 : 1;
+  const size_t n_chunks = (n4 + kChunkGroups - 1) / kChunkGroups;
+  const unsigned w4u = (unsigned)w4;
+  const int size = P.size;
+  auto coverage = [&](unsigned y, unsigned x) -> unsigned {
+    unsigned cover = 0;
+    for (int l = 0; l < size; ++l)
+      if ((int)y >= s_rect[l][1] && (int)y < s_rect[l][3] && (int)x >= s_rect[l][0] && (int)x < s_rect[l][2])
+        cover |= 1u << l;
+    return cover;
+  };
+  __shared__ int s_dirty[2][4]; // [0] result image, [1] canvas
+  __shared__ int s_union[4];    // bounding box of this frame's rectangles
+  if (P.rank == 0 && threadIdx.x == 0)
+  {
+    int u[4] = { 0x7fffffff, 0x7fffffff, 0, 0 };
+    for (int l = 0; l < P.size; ++l)
+      if (s_rect[l][2] > s_rect[l][0] && s_rect[l][3] > s_rect[l][1])
+      {
+        u[0] = min(u[0], s_rect[l][0]); u[1] = min(u[1], s_rect[l][1]);
+        u[2] = max(u[2], s_rect[l][2]); u[3] = max(u[3], s_rect[l][3]);
+      }
+    if (u[2] <= u[0]) u[0] = u[1] = u[2] = u[3] = 0;
+    for (int k = 0; k < 4; ++k)
+    {
+      s_union[k] = u[k];
+      s_dirty[0][k] = P.track_res ? s_clean[0][k] : (k < 2 ? 0 : 0x7fffffff);
+      s_dirty[1][k] = P.track_canvas ? s_clean[1][k] : (k < 2 ? 0 : 0x7fffffff);
+    }
+  }
+  __syncthreads();
+  auto write_empty = [&](size_t i, unsigned uy, unsigned ux) {
+    const int y = (int)uy, x = (int)ux;
+    if (y >= s_dirty[0][1] && y < s_dirty[0][3] && x >= s_dirty[0][0] && x < s_dirty[0][2])
+    {
+      out_rgba[i] = make_uint4(0u, 0u, 0u, 0u);
+      out_depth[i] = make_float4(1.001f, 1.001f, 1.001f, 1.001f);
+    }
+    if (TO_CANVAS && y >= s_dirty[1][1] && y < s_dirty[1][3] && x >= s_dirty[1][0] && x < s_dirty[1][2])
+    {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) P.canvas_rgba[4 * i + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      reinterpret_cast<float4*>(P.canvas_depth)[i] = make_float4(1.001f, 1.001f, 1.001f, 1.001f);
+    }
+  };
+
+  if (P.timeline && blockIdx.x == 0 && threadIdx.x == 0) my_flags->timeline[8] = global_ns();
+  // ---- my chunks (rank, rank + size, ...), dealt to the CTAs one after the other; a thread folds two of
+  // the chunk's 256 four-pixel groups
+  const size_t n_mine = n_chunks > (size_t)P.rank ? (n_chunks - 1 - (size_t)P.rank) / (size_t)P.size + 1 : 0;
+  for (size_t k = blockIdx.x; k < n_mine; k += gridDim.x)
+  {
+    const size_t chunk = k * (size_t)P.size + (size_t)P.rank;
+#pragma unroll 1
+    for (int h = 0; h < kChunkGroups / kLightThreads; ++h)
+    {
+      const unsigned g = threadIdx.x + h * kLightThreads;
+      const size_t i = chunk * kChunkGroups + g;
+      if (i >= n4) continue;
+      const unsigned gy = (unsigned)i / w4u, gx = ((unsigned)i - gy * w4u) * 4u;
+      const unsigned cover = coverage(gy, gx);
+      if (cover == 0)
+      {
+        if (P.rank == 0) write_empty(i, gy, gx);
+        continue;
+      }
+      const size_t at_local = k * kChunkGroups + g;
+      uint4 f = make_uint4(0u, 0u, 0u, 0u);
+      float4 fd = make_float4(1.001f, 1.001f, 1.001f, 1.001f);
+      for (int l0 = 0; l0 < size; l0 += 4)
+      {
+        uint4 c[4];
+        float4 d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+          const int l = l0 + u;
+          if (l < size && (cover & (1u << l)))
+          {
+            const size_t at = s_pushed[l] ? at_local : i;
+            c[u] = s_lrgba[l][at];
+            d[u] = s_ldepth[l][at];
+          }
+          else
+          {
+            c[u] = make_uint4(0u, 0u, 0u, 0u);
+            d[u] = make_float4(1.001f, 1.001f, 1.001f, 1.001f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+          const int l = l0 + u;
+          if (l >= size) break;
+          if (l == 0) { f = c[0]; fd = d[0]; continue; }
+          if (ZBUF)
+          {
+            if (cover & (1u << l))
+            {
+              if (!(d[u].x > 1.f || fd.x < d[u].x)) { fd.x = d[u].x; f.x = c[u].x; }
+              if (!(d[u].y > 1.f || fd.y < d[u].y)) { fd.y = d[u].y; f.y = c[u].y; }
+              if (!(d[u].z > 1.f || fd.z < d[u].z)) { fd.z = d[u].z; f.z = c[u].z; }
+              if (!(d[u].w > 1.f || fd.w < d[u].w)) { fd.w = d[u].w; f.w = c[u].w; }
+            }
+            continue;
+          }
+          if (cover & (1u << l))
+          {
+            f.x = blend_u8x4(f.x, c[u].x); f.y = blend_u8x4(f.y, c[u].y);
+            f.z = blend_u8x4(f.z, c[u].z); f.w = blend_u8x4(f.w, c[u].w);
+          }
+          fd.x = blend_depth(fd.x, d[u].x); fd.y = blend_depth(fd.y, d[u].y);
+          fd.z = blend_depth(fd.z, d[u].z); fd.w = blend_depth(fd.w, d[u].w);
+        }
+      }
+      out_rgba[i] = f;
+      out_depth[i] = fd;
+    }
+  }
+  if (P.timeline && blockIdx.x == 0 && threadIdx.x == 0) my_flags->timeline[9] = global_ns();
+  // ---- rank 0: the groups NO rank covers inside the other ranks' chunks, where they may be dirty
+  if (P.rank == 0 && P.size > 1)
+  {
+    const int y_lo = min(s_dirty[0][1], TO_CANVAS ? s_dirty[1][1] : 0x7fffffff);
+    const int y_hi = max(s_dirty[0][3], TO_CANVAS ? s_dirty[1][3] : 0);
+    const size_t c_lo = y_lo <= 0 ? 0 : ((size_t)y_lo * (size_t)w4) / kChunkGroups;
+    const size_t c_end = y_hi >= (int)(n4 / (size_t)w4) ? n_chunks
+                                                          : min(n_chunks, ((size_t)y_hi * (size_t)w4) / kChunkGroups + 1);
+    for (size_t chunk = c_lo + blockIdx.x; chunk < c_end; chunk += gridDim.x)
+    {
+      if (chunk % (size_t)P.size == 0) continue;
+      for (int h = 0; h < kChunkGroups / kLightThreads; ++h)
+      {
+        const size_t i = chunk * kChunkGroups + threadIdx.x + h * kLightThreads;
+        if (i >= n4) continue;
+        const unsigned gy = (unsigned)i / w4u, gx = ((unsigned)i - gy * w4u) * 4u;
+        if (coverage(gy, gx) == 0) write_empty(i, gy, gx);
+      }
+    }
+  }
+
+  // ---- last CTA out tells rank 0 that my range has landed
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    if (P.timeline && blockIdx.x == 0) my_flags->timeline[10] = global_ns();
+    __threadfence_system();
+    const unsigned prev = atomicAdd(&my_flags->cta_done, 1u);
+    if (P.timeline && blockIdx.x == 0) my_flags->timeline[11] = global_ns();
+    if (prev == gridDim.x - 1)
+    {
+      my_flags->cta_done = 0;
+      if (P.rank == 0)
+      {
+        for (int k = 0; k < 4; ++k)
+        {
+          my_flags->clean_res[par][k] = s_union[k];
+          if (TO_CANVAS) my_flags->clean_canvas[k] = s_union[k];
+        }
+      }
+      Flags* root = reinterpret_cast<Flags*>(P.peers[0] + P.off_flags);
+      __threadfence_system();
+      st_release_sys(&root->done[P.rank], P.epoch);
+      if (P.timeline) my_flags->timeline[2] = global_ns();
+    }
+  }
+}
+
 // rank 0, after every rank's range has landed: ImageToCanvas for the groups some rank covers
-__global__ void __launch_bounds__(256) covered_to_canvas_kernel(const __grid_constant__ FoldP2PParams P)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) covered_to_canvas_kernel(const __grid_constant__ FoldP2PParams P)
 {
   const Flags* my_flags = reinterpret_cast<const Flags*>(P.peers[0] + P.off_flags);
   const int par = P.epoch & 1;
@@ -375,18 +607,40 @@ __global__ void __launch_bounds__(256) covered_to_canvas_kernel(const __grid_con
   __syncthreads();
   if (P.timeline && blockIdx.x == 0 && threadIdx.x == 0) const_cast<Flags*>(my_flags)->timeline[4] = global_ns();
   __shared__ int s_rect[kMaxRanks][4];
+  __shared__ int s_box[4];
   if (threadIdx.x < P.size * 4) s_rect[threadIdx.x >> 2][threadIdx.x & 3] = my_flags->img_rect[par][threadIdx.x >> 2][threadIdx.x & 3];
+  __syncthreads();
+  const int w4 = P.W >= 4 ? P.W / 4 : 1;
+  const size_t n4 = (P.n_pixels + 3) / 4;
+  const int h_img = (int)(n4 / (size_t)w4) + ((n4 % (size_t)w4) ? 1 : 0);
+  if (threadIdx.x == 0)
+  {
+    // bounding box of the rectangles, in groups of 4 pixels: nothing outside of it is covered
+    int u[4] = { 0x7fffffff, 0x7fffffff, 0, 0 };
+    for (int l = 0; l < P.size; ++l)
+      if (s_rect[l][2] > s_rect[l][0] && s_rect[l][3] > s_rect[l][1])
+      {
+        u[0] = min(u[0], s_rect[l][0]); u[1] = min(u[1], s_rect[l][1]);
+        u[2] = max(u[2], s_rect[l][2]); u[3] = max(u[3], s_rect[l][3]);
+      }
+    if (u[2] <= u[0]) u[0] = u[1] = u[2] = u[3] = 0;
+    s_box[0] = max(u[0], 0) / 4; s_box[1] = max(u[1], 0);
+    s_box[2] = min((min(u[2], P.W) + 3) / 4, w4); s_box[3] = min(u[3], h_img);
+    if (P.W % 4 != 0) { s_box[0] = 0; s_box[1] = 0; s_box[2] = w4; s_box[3] = h_img; } // (unbounded rectangles)
+  }
   __syncthreads();
   const uint4* res_rgba = reinterpret_cast<const uint4*>(P.peers[0] + P.off_res_rgba);
   const float4* res_depth = reinterpret_cast<const float4*>(P.peers[0] + P.off_res_depth);
-  const size_t n4 = (P.n_pixels + 3) / 4;
-  const int w4 = P.W >= 4 ? P.W / 4 : 1;
   const float k = 1.f / 255.f;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
+  const int bw = s_box[2] - s_box[0], bh = s_box[3] - s_box[1];
+  const unsigned n_box = bw > 0 && bh > 0 ? (unsigned)bw * (unsigned)bh : 0u;
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n_box; t += stride)
   {
-    const unsigned uy = (unsigned)i / (unsigned)w4;
-    const int y = (int)uy, x = (int)(((unsigned)i - uy * (unsigned)w4) * 4u);
+    const unsigned by = t / (unsigned)bw;
+    const int y = s_box[1] + (int)by, x4 = s_box[0] + (int)(t - by * (unsigned)bw), x = x4 * 4;
+    const size_t i = (size_t)y * (size_t)w4 + (size_t)x4;
+    if (i >= n4) continue;
     bool cover = false;
     for (int l = 0; l < P.size; ++l)
       cover = cover || (y >= s_rect[l][1] && y < s_rect[l][3] && x >= s_rect[l][0] && x < s_rect[l][2]);
@@ -757,6 +1011,18 @@ static cudaError_t launch_fold_p2p_nr(const FoldP2PParams& p, int sm_count, cuda
 
 cudaError_t launch_fold_p2p(const FoldP2PParams& p, int sm_count, cudaStream_t s)
 {
+  if (p.light)
+  {
+    const size_t n4 = (p.n_pixels + 3) / 4;
+    const size_t n_chunks = (n4 + kChunkGroups - 1) / kChunkGroups;
+    size_t grid = (size_t)sm_count;
+    const size_t want = p.rank == 0 ? n_chunks : (n_chunks + p.size - 1) / p.size;
+    if (grid > want) grid = want ? want : 1;
+    if (p.zbuffer) fold_p2p_light_kernel<false, true><<<(unsigned)grid, kLightThreads, 0, s>>>(p);
+    else if (p.canvas_rgba) fold_p2p_light_kernel<true, false><<<(unsigned)grid, kLightThreads, 0, s>>>(p);
+    else fold_p2p_light_kernel<false, false><<<(unsigned)grid, kLightThreads, 0, s>>>(p);
+    return cudaGetLastError();
+  }
   if (p.size <= 2) return launch_fold_p2p_nr<2>(p, sm_count, s);
   if (p.size <= 4) return launch_fold_p2p_nr<4>(p, sm_count, s);
   if (p.size <= 8) return launch_fold_p2p_nr<8>(p, sm_count, s);
@@ -766,16 +1032,23 @@ cudaError_t launch_fold_p2p(const FoldP2PParams& p, int sm_count, cudaStream_t s
 void comm_destroy(vr_ctx* ctx)
 {
   Comm& c = ctx->comm;
+  // (the streams belong to the context, not to the arena: created in vr_create)
+  if (c.xstream) { cudaStreamSynchronize(c.xstream); cudaStreamDestroy(c.xstream); c.xstream = nullptr; }
+  for (int k = 0; k < 2; ++k)
+  {
+    if (c.tstream[k]) { cudaStreamSynchronize(c.tstream[k]); cudaStreamDestroy(c.tstream[k]); c.tstream[k] = nullptr; }
+    if (c.ev_t[k]) cudaEventDestroy(c.ev_t[k]);
+  }
+  if (c.ev_trace) cudaEventDestroy(c.ev_trace);
+  if (c.ev_main) cudaEventDestroy(c.ev_main);
+  for (int k = 0; k < 8; ++k)
+    if (c.ev_x[k]) cudaEventDestroy(c.ev_x[k]);
   if (!c.on) return;
   for (int r = 0; r < (int)c.peer.size(); ++r)
     if (r != c.rank && c.peer[r]) cudaIpcCloseMemHandle(c.peer[r]);
   cudaFree(c.peer_dev);
   cudaFree(c.minmax_dev);
   cudaFree(c.arena);
-  if (c.xstream) { cudaStreamSynchronize(c.xstream); cudaStreamDestroy(c.xstream); }
-  if (c.ev_trace) cudaEventDestroy(c.ev_trace);
-  if (c.ev_x[0]) cudaEventDestroy(c.ev_x[0]);
-  if (c.ev_x[1]) cudaEventDestroy(c.ev_x[1]);
   c.on = false;
 }
 
@@ -834,8 +1107,28 @@ vr_status comm_ahead_image(vr_ctx* ctx, uchar4** rgba, float** depth)
 void comm_join_previous_exchange(vr_ctx* ctx)
 {
   Comm& c = ctx->comm;
-  if (!c.on || !c.xstream || c.xserial < 2) return;
-  cudaStreamWaitEvent(ctx->stream, c.ev_x[(c.xserial - 1) & 1], 0);
+  if (!c.xstream || c.xserial < 2) return;
+  cudaStreamWaitEvent(ctx->stream, c.ev_x[(c.xserial - 1) & 7], 0);
+}
+
+// An image-only trace of image frame e (= epoch + 1, or + 2 when traced ahead) writes ring slot e % 4 -- in
+// this rank's arena, or, pushed, in every owner's receive ring -- which frame e - 4 used.  Every rank has
+// finished reading frame e - 4 once THIS rank's exchange of frame e - 3 has completed: that exchange passed
+// the all-ranks-ready barrier of e - 3, which a rank only joins after its own exchange of e - 4 (same
+// stream).  So the trace waits for exchange e - 3 -- issued two or three calls ago, i.e. normally long
+// done -- and the exchanges of e - 2 and e - 1 may still be running while it goes.
+void comm_join_for_image_trace(vr_ctx* ctx, bool ahead, cudaStream_t s)
+{
+  Comm& c = ctx->comm;
+  if (!c.on || !c.xstream) return;
+  const unsigned int e = c.epoch + (ahead ? 2u : 1u);
+  if (e < 4) return;
+  const unsigned int xs = c.x_of_img_epoch[(e - 3) & 7];
+  if (xs == 0) return; // that exchange ran on the context's stream: ordered already
+  // (an event slot is reused every 8 exchanges: if image and layer exchanges were mixed in between, fall
+  // back to the latest exchange)
+  const unsigned int w = (c.xserial - xs >= 8) ? c.xserial : xs;
+  cudaStreamWaitEvent(s, c.ev_x[w & 7], 0);
 }
 
 // receive-slot geometry of a pushed frame (sampler mode 5)
@@ -908,7 +1201,12 @@ vr_status comm_bind_layers(vr_ctx* ctx)
   if (!ctx->layers_in_arena)
   {
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->ltab); cudaFree(ctx->lpool_rgba); cudaFree(ctx->lpool_depth);
+    for (int k = 0; k < vr_ctx::kOwnLayerRing; ++k)
+    {
+      cudaFree(ctx->own_ltab[k]); cudaFree(ctx->own_lpool_rgba[k]); cudaFree(ctx->own_lpool_depth[k]);
+      ctx->own_ltab[k] = nullptr; ctx->own_lpool_rgba[k] = nullptr; ctx->own_lpool_depth[k] = nullptr;
+      ctx->own_lpool_cap[k] = 0;
+    }
     ctx->layers_in_arena = true;
   }
   ctx->ltab = reinterpret_cast<LayerTable*>(c.arena + L.off_ltab[b]);
@@ -951,12 +1249,6 @@ extern "C" vr_status vr_comm_init(vr_ctx* ctx, int rank, int n_ranks, size_t max
     const long long ms = t ? std::atoll(t) : 20000;
     c.timeout_ns = ms > 0 ? (unsigned long long)ms * 1000000ull : 0ull;
     if (const char* e = std::getenv("VR_TIMELINE")) c.timeline = std::atoi(e) != 0;
-    int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    cudaStreamCreateWithPriority(&c.xstream, cudaStreamNonBlocking, hi); // its CTAs go first when SM slots free up
-    cudaEventCreateWithFlags(&c.ev_trace, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&c.ev_x[0], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&c.ev_x[1], cudaEventDisableTiming);
   }
   const Layout L = make_layout(max_pixels, max_partials, rank == 0);
   c.arena_bytes = L.total;
@@ -1095,7 +1387,17 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
   {
     cudaEventRecord(c.ev_trace, ctx->stream);
     cudaStreamWaitEvent(xs, c.ev_trace, 0);
+    // this frame's image was traced on side stream (epoch & 1): the exchange is what waits for it, and whoever
+    // joins the exchange has thereby joined the trace (a frame traced AHEAD sits on the other stream)
+    if (c.t_pending[c.epoch & 1])
+    {
+      cudaStreamWaitEvent(xs, c.ev_t[c.epoch & 1], 0);
+      c.t_pending[c.epoch & 1] = false;
+    }
   }
+  else
+    VR_JOIN(ctx);
+  p.light = (c.fold_light && c.size <= 16) ? 1 : 0;
   cudaError_t e = launch_fold_p2p(p, ctx->sm_count, xs);
   if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "fold_p2p launch", e);
   ctx->launches++;
@@ -1108,7 +1410,8 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
     if (p.canvas_rgba)
     {
       // waits for every rank's "done" itself, then converts the covered groups
-      covered_to_canvas_kernel<<<ctx->sm_count * 2, 256, 0, xs>>>(p);
+      if (p.light) covered_to_canvas_kernel<128><<<ctx->sm_count * 2, 128, 0, xs>>>(p);
+      else covered_to_canvas_kernel<256><<<ctx->sm_count * 2, 256, 0, xs>>>(p);
       ctx->launches++;
     }
     else
@@ -1132,11 +1435,13 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
       c.clean_canvas.valid = true; c.clean_canvas.serial = ctx->api_serial; c.clean_canvas.W = ctx->W; c.clean_canvas.H = ctx->H;
     }
   }
+  c.x_of_img_epoch[c.epoch & 7] = 0;
   if (xs != ctx->stream)
   {
     c.xserial += 1;
-    cudaEventRecord(c.ev_x[c.xserial & 1], xs);
+    cudaEventRecord(c.ev_x[c.xserial & 7], xs);
     c.x_pending = true;
+    c.x_of_img_epoch[c.epoch & 7] = c.xserial;
   }
   // the next frame's image: the following ring slot -- where a frame traced ahead already sits
   const int ns = (int)((c.epoch + 1) % kImgRing);
@@ -1304,19 +1609,19 @@ extern "C" vr_status vr_comm_composite_partials_to_canvas(vr_ctx* ctx, const vr_
 
 extern "C" vr_status vr_comm_composite_images(vr_ctx* ctx, const int* vis_order)
 {
-  VR_ENTER_RO(ctx);
+  VR_ENTER_NOJOIN(ctx); // (the exchange stream orders itself after the trace and the previous exchange)
   return comm_composite_images_impl(ctx, vis_order, false);
 }
 
 extern "C" vr_status vr_comm_composite_images_to_canvas(vr_ctx* ctx, const int* vis_order)
 {
-  VR_ENTER_RO(ctx);
+  VR_ENTER_NOJOIN(ctx); // (the exchange stream orders itself after the trace and the previous exchange)
   return comm_composite_images_impl(ctx, vis_order, true);
 }
 
 extern "C" vr_status vr_comm_composite_zbuffer(vr_ctx* ctx)
 {
-  VR_ENTER_RO(ctx);
+  VR_ENTER_NOJOIN(ctx); // (the exchange stream orders itself after the trace and the previous exchange)
   int order[kMaxRanks];
   for (int i = 0; i < kMaxRanks; ++i) order[i] = i; // rank order
   return comm_composite_images_impl(ctx, order, false, true);
@@ -1393,6 +1698,7 @@ extern "C" vr_status vr_comm_layers_composite_to_canvas(vr_ctx* ctx, const vr_ca
   p.H = ctx->lH;
   p.clear = 1;
   p.smem_layers = kMaxSmemLayers;
+  p.light = c.fold_light ? 1 : 0;
   p.timeout_ns = c.timeout_ns;
   for (int r = 0; r < c.size; ++r)
   {
@@ -1442,7 +1748,7 @@ extern "C" vr_status vr_comm_layers_composite_to_canvas(vr_ctx* ctx, const vr_ca
   if (xs != ctx->stream)
   {
     c.xserial += 1;
-    cudaEventRecord(c.ev_x[c.xserial & 1], xs);
+    cudaEventRecord(c.ev_x[c.xserial & 7], xs);
     c.x_pending = true;
   }
   ctx->lW = ctx->lH = 0; // the frame is consumed: vr_layers_begin starts the next one

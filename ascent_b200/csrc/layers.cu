@@ -32,14 +32,17 @@ namespace vr
 namespace
 {
 
-constexpr int kTileW = 32, kTileH = 8;           // 256 threads
+// A CTA owns a 32 x TH pixel tile.  TH = 8 (256 threads) when the fold has the GPU to itself; TH = 4 (128
+// threads, <= 72 registers) is the footprint of ONE sampler CTA: the fold of frame k runs on the exchange
+// stream while the sampler's persistent grids are busy with frame k+1, and such a CTA is placed as soon as any
+// sampler CTA retires instead of waiting for two slots of one SM to fall free together.
+constexpr int kTileW = 32;
 constexpr int kMaxTileLayers = 192;              // layers overlapping one tile (smem list)
 constexpr int kMaxSeg = 20;                      // entries per pixel ordered in shared memory (deeper: selection)
 constexpr int kBatch = 8;                        // layer entries requested together per pixel
-constexpr int kThreadsFold = kTileW * kTileH;
 // per-thread sort keys live in shared memory, [slot][thread] so that a warp's accesses never conflict:
 // exit distance and (tie-break order << 12 | index into the tile's layer list)
-constexpr size_t kKeyBytes = (size_t)kMaxSeg * kThreadsFold * 8;
+constexpr size_t key_bytes(int th) { return (size_t)kMaxSeg * kTileW * th * 8; }
 
 __device__ __forceinline__ void blend(float4& a, const float4 o)
 {
@@ -65,9 +68,11 @@ struct TileLayer
 // COMM: flags/peers are live, the frame starts from a cleared canvas: the owner of a tile writes all
 // of its pixels into rank 0's canvas, rank 0 clears what lies outside the layers' bounding box;
 // !COMM: one rank, every pixel of the frame is written (cleared or blended over).
-template <bool COMM>
-__global__ void __launch_bounds__(kTileW* kTileH) layers_fold_kernel(const __grid_constant__ LayerFoldParams P)
+template <bool COMM, int kTileH>
+__global__ void __launch_bounds__(kTileW* kTileH, kTileH == 4 ? 7 : 4) layers_fold_kernel(const __grid_constant__ LayerFoldParams P)
 {
+  constexpr int kThreadsFold = kTileW * kTileH;
+  constexpr size_t kKeyBytes = (size_t)kMaxSeg * kTileW * kTileH * 8;
   extern __shared__ unsigned char smem_raw[];
   float* s_kd = reinterpret_cast<float*>(smem_raw);                               // sort keys: exit distance
   int* s_ko = reinterpret_cast<int*>(smem_raw + kKeyBytes / 2);                   // sort keys: order | list index
@@ -417,25 +422,29 @@ __global__ void layers_to_partials_kernel(const LayerTable* __restrict__ table,
 
 } // namespace
 
-cudaError_t launch_layers_fold(const LayerFoldParams& p, bool comm, int sm_count, cudaStream_t s)
+template <bool COMM, int TH>
+static cudaError_t launch_layers_fold_t(const LayerFoldParams& p, int sm_count, cudaStream_t s)
 {
-  const size_t smem = kKeyBytes + (size_t)p.smem_layers * sizeof(LayerDesc);
+  const size_t smem = key_bytes(TH) + (size_t)p.smem_layers * sizeof(LayerDesc);
   // per device, not per process (a process may hold contexts on several GPUs): cheap enough to set per launch
-  if (comm) cudaFuncSetAttribute(layers_fold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-  else cudaFuncSetAttribute(layers_fold_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+  cudaFuncSetAttribute(layers_fold_kernel<COMM, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
   // (the kernel restricts itself to the layers' bounding box; the full frame bounds the grid)
-  const long long tiles = (long long)((p.W + kTileW - 1) / kTileW) * ((p.H + kTileH - 1) / kTileH);
+  const long long tiles = (long long)((p.W + kTileW - 1) / kTileW) * ((p.H + TH - 1) / TH);
   // persistent grid: exactly the CTAs that are resident at once (registers and the table's smem decide)
   int per_sm = 0;
-  if (comm) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layers_fold_kernel<true>, kTileW * kTileH, smem);
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layers_fold_kernel<false>, kTileW * kTileH, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layers_fold_kernel<COMM, TH>, kTileW * TH, smem);
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)sm_count * per_sm;
   const long long mine = (tiles + p.size - 1) / p.size;
   if (grid > mine) grid = mine > 0 ? mine : 1;
-  if (comm) layers_fold_kernel<true><<<(int)grid, kTileW * kTileH, smem, s>>>(p);
-  else layers_fold_kernel<false><<<(int)grid, kTileW * kTileH, smem, s>>>(p);
+  layers_fold_kernel<COMM, TH><<<(int)grid, kTileW * TH, smem, s>>>(p);
   return cudaGetLastError();
+}
+
+cudaError_t launch_layers_fold(const LayerFoldParams& p, bool comm, int sm_count, cudaStream_t s)
+{
+  if (p.light) return comm ? launch_layers_fold_t<true, 4>(p, sm_count, s) : launch_layers_fold_t<false, 4>(p, sm_count, s);
+  return comm ? launch_layers_fold_t<true, 8>(p, sm_count, s) : launch_layers_fold_t<false, 8>(p, sm_count, s);
 }
 
 cudaError_t launch_layers_wait_done(unsigned char* flags, int size, unsigned int epoch, unsigned long long timeout_ns,

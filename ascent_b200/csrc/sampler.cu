@@ -996,7 +996,8 @@ cudaError_t launch_trace(const TraceParams& p, int mode_partials, int sm_count, 
   if (n_tiles <= 0) return cudaSuccess;
   // persistent grid: SMs x resident CTAs (4 warps each), capped by the work available
   const bool std_march = mode_partials == 4 || p.march == 0;
-  const int ctas_per_sm = p.ctas_per_sm > 0 && std_march ? p.ctas_per_sm : (std_march ? VR_MIN_BLOCKS : (p.march == 1 ? 7 : 3));
+  const int full = std_march ? VR_MIN_BLOCKS : (p.march == 1 ? 7 : 3); // what the registers allow
+  const int ctas_per_sm = p.ctas_per_sm > 0 && p.ctas_per_sm < full ? p.ctas_per_sm : full; // (VR_CTAS_PER_SM: A/B runs)
   long long grid = (long long)sm_count * ctas_per_sm;
   const long long need = (n_tiles + 3) / 4;
   if (grid > need) grid = need;

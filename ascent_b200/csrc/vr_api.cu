@@ -51,6 +51,7 @@ namespace vr { vr_status comm_ahead_image(vr_ctx* ctx, uchar4** rgba, float** de
 namespace vr { vr_status comm_push_target(vr_ctx* ctx, bool ahead, int width, int height, vr::TraceParams& p); }
 namespace vr { vr_status comm_check_errors(vr_ctx* ctx); }
 namespace vr { void comm_join_previous_exchange(vr_ctx* ctx); }
+namespace vr { void comm_join_for_image_trace(vr_ctx* ctx, bool ahead, cudaStream_t s); }
 namespace vr { unsigned long long* comm_timeline_slot(vr_ctx* ctx, int k); }
 static void fill_to_canvas_params(const vr_camera* cam, int W, int H, ToCanvasParams& tp);
 
@@ -92,7 +93,26 @@ extern "C" vr_status vr_create(int device, vr_ctx** out)
   // gather latency, bounds that regime -- DESIGN.md section 4.1), so it is opt-in: VR_BRICK=1.
   ctx->no_brick = true;
   if (const char* e = std::getenv("VR_BRICK")) ctx->no_brick = std::atoi(e) == 0;
-  cudaMalloc(&ctx->tile_counter, (size_t)(1 + vr::kMaxLayers) * sizeof(unsigned int)); // [0]: single launches
+  // [0]: single launches, [1 + k]: launch k of a batched call, [1 + kMaxLayers + s]: image trace on side stream s
+  cudaMalloc(&ctx->tile_counter, (size_t)(3 + vr::kMaxLayers) * sizeof(unsigned int));
+  {
+    // the exchange stream (fold of frame k overlaps the trace of frame k+1; its CTAs go first when SM slots
+    // free up) and the two side streams of image-only traces -- see vr_internal.h
+    vr::Comm& c = ctx->comm;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaStreamCreateWithPriority(&c.xstream, cudaStreamNonBlocking, hi);
+    cudaEventCreateWithFlags(&c.ev_trace, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c.ev_main, cudaEventDisableTiming);
+    for (int k = 0; k < 8; ++k) cudaEventCreateWithFlags(&c.ev_x[k], cudaEventDisableTiming);
+    for (int k = 0; k < 2; ++k)
+    {
+      cudaStreamCreateWithFlags(&c.tstream[k], cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&c.ev_t[k], cudaEventDisableTiming);
+    }
+    if (const char* e = std::getenv("VR_TRACE_STREAMS")) c.trace_side = std::atoi(e) != 0;
+    if (const char* e = std::getenv("VR_FOLD_LIGHT")) c.fold_light = std::atoi(e) != 0;
+  }
   for (int k = 0; k < vr::kAuxStreams; ++k)
   {
     cudaStreamCreateWithFlags(&ctx->aux[k], cudaStreamNonBlocking);
@@ -157,11 +177,11 @@ extern "C" void vr_destroy(vr_ctx* ctx)
     cudaFree(ctx->res_rgba);
     cudaFree(ctx->res_depth);
   }
-  if (!ctx->layers_in_arena)
+  for (int k = 0; k < vr_ctx::kOwnLayerRing; ++k)
   {
-    cudaFree(ctx->ltab);
-    cudaFree(ctx->lpool_rgba);
-    cudaFree(ctx->lpool_depth);
+    cudaFree(ctx->own_ltab[k]);
+    cudaFree(ctx->own_lpool_rgba[k]);
+    cudaFree(ctx->own_lpool_depth[k]);
   }
   delete ctx->ltab_host;
   cudaFree(ctx->partials);
@@ -809,19 +829,38 @@ extern "C" vr_status vr_trace_to_image(vr_ctx* ctx, int block_id, const vr_camer
                                        float range_max, int flags)
 {
   VR_ENTER_NOJOIN(ctx);
+  const bool ahead = (flags & VR_FRAME_AHEAD) != 0;
+  CK(cudaSetDevice(ctx->device));
+  // Where the launch goes.  A frame that also writes the canvas runs on the context's stream, after
+  // everything the latest exchange does to the canvas.  An image-only frame of a connected context runs on
+  // one of two side streams (by frame parity): it neither waits for the previous frame's trace nor for the
+  // exchanges still in flight, only for the exchange that frees its ring slot (comm_join_for_image_trace).
+  cudaStream_t ts = ctx->stream;
+  int side = -1;
   if (flags & VR_FRAME_WRITE_CANVAS)
   {
-    ++ctx->api_serial; // writes the canvas: after everything the latest exchange does to it
+    ++ctx->api_serial;
     VR_JOIN(ctx);
   }
-  else
-    comm_join_previous_exchange(ctx); // image only: may overlap the latest exchange (see vr_internal.h)
-  CK(cudaSetDevice(ctx->device));
+  else if (ctx->comm.on && ctx->comm.trace_side && ctx->comm.tstream[0])
+  {
+    auto it = ctx->blocks.find(block_id);
+    const bool staging = it != ctx->blocks.end() && it->second.staged_src && !it->second.all_resident;
+    if (!staging) // (demand staging keeps per-block state on the device: one trace of the block at a time)
+    {
+      side = (int)((ctx->comm.epoch + (ahead ? 2u : 1u)) & 1u);
+      ts = ctx->comm.tstream[side];
+      CK(cudaEventRecord(ctx->comm.ev_main, ctx->stream)); // after what the caller queued so far (publishes, ...)
+      CK(cudaStreamWaitEvent(ts, ctx->comm.ev_main, 0));
+    }
+  }
+  if (!(flags & VR_FRAME_WRITE_CANVAS)) comm_join_for_image_trace(ctx, ahead, ts);
   vr_status st = ensure_frame(ctx, width, height);
   if (st != VR_OK) return st;
   TraceParams p;
   st = fill_trace_params(ctx, block_id, cam, sample_dist, range_min, range_max, 0, width, height, p);
   if (st != VR_OK) return st;
+  if (side >= 0) p.tile_counter = ctx->tile_counter + 1 + vr::kMaxLayers + side;
   p.vec_ok = (width % 4 == 0) ? 1 : 0;
   if (p.vec_ok && p.sw > 0)
   {
@@ -831,7 +870,6 @@ extern "C" vr_status vr_trace_to_image(vr_ctx* ctx, int block_id, const vr_camer
   }
   p.img_rgba = ctx->img_rgba;
   p.img_depth = ctx->img_depth;
-  const bool ahead = (flags & VR_FRAME_AHEAD) != 0;
   if (ahead)
   {
     // the frame AFTER the one whose exchange is still to be issued: next slot of the image ring
@@ -855,11 +893,16 @@ extern "C" vr_status vr_trace_to_image(vr_ctx* ctx, int block_id, const vr_camer
   // image -- so such frames are always cleared)
   p.n_clear_chunks = (((flags & VR_FRAME_NO_CLEAR) && p.vec_ok) || push) ? 0 : (int)(((size_t)width * height + 511) / 512);
   p.end_stamp = comm_timeline_slot(ctx, 6);
-  if (p.end_stamp) CK(cudaMemsetAsync(p.end_stamp, 0, sizeof(unsigned long long), ctx->stream));
-  st = stage_for_trace(ctx, block_id, p, ctx->stream, ctx->tile_counter, true);
+  if (p.end_stamp) CK(cudaMemsetAsync(p.end_stamp, 0, sizeof(unsigned long long), ts));
+  st = stage_for_trace(ctx, block_id, p, ts, p.tile_counter, true);
   if (st != VR_OK) return st;
-  CK(launch_trace(p, push ? 5 : 2, ctx->sm_count, ctx->stream));
+  CK(launch_trace(p, push ? 5 : 2, ctx->sm_count, ts));
   ctx->launches++;
+  if (side >= 0)
+  {
+    CK(cudaEventRecord(ctx->comm.ev_t[side], ts));
+    ctx->comm.t_pending[side] = true;
+  }
   // what the multi-GPU fold needs to know: outside this rectangle my image is empty
   int* rect = ahead ? ctx->img_rect_ahead : ctx->img_rect;
   rect[0] = p.tx0; rect[1] = p.sy;
@@ -1029,9 +1072,9 @@ static vr_status ensure_layer_pool(vr_ctx* ctx, size_t need)
   CK(cudaStreamSynchronize(ctx->stream));
   cudaFree(ctx->lpool_rgba);
   cudaFree(ctx->lpool_depth);
-  ctx->lpool_rgba = nr;
-  ctx->lpool_depth = nd;
-  ctx->lpool_cap = cap;
+  ctx->lpool_rgba = ctx->own_lpool_rgba[ctx->own_lslot] = nr;
+  ctx->lpool_depth = ctx->own_lpool_depth[ctx->own_lslot] = nd;
+  ctx->lpool_cap = ctx->own_lpool_cap[ctx->own_lslot] = cap;
   return VR_OK;
 }
 
@@ -1048,8 +1091,17 @@ extern "C" vr_status vr_layers_begin(vr_ctx* ctx, int width, int height)
     vr_status st = comm_bind_layers(ctx);
     if (st != VR_OK) return st;
   }
-  else if (!ctx->ltab)
-    CK(cudaMalloc(&ctx->ltab, sizeof(LayerTable)));
+  else
+  {
+    // the next buffer of the context's own ring (its last reader, the fold of three frames ago, is done:
+    // comm_join_previous_exchange above)
+    const int k = ctx->own_lslot = (ctx->own_lslot + 1) % vr_ctx::kOwnLayerRing;
+    if (!ctx->own_ltab[k]) CK(cudaMalloc(&ctx->own_ltab[k], sizeof(LayerTable)));
+    ctx->ltab = ctx->own_ltab[k];
+    ctx->lpool_rgba = ctx->own_lpool_rgba[k];
+    ctx->lpool_depth = ctx->own_lpool_depth[k];
+    ctx->lpool_cap = ctx->own_lpool_cap[k];
+  }
   ctx->ltab_host->n = 0;
   ctx->lpool_used = 0;
   ctx->lW = width;
@@ -1178,7 +1230,17 @@ namespace vr { vr_status ensure_frame_pub(vr_ctx* ctx, int W, int H) { return en
 
 extern "C" vr_status vr_layers_composite_to_canvas(vr_ctx* ctx, const vr_camera* cam, int canvas_is_clear)
 {
-  VR_ENTER(ctx);
+  // A fold over a cleared canvas only WRITES the canvas: it goes to the exchange stream (after this frame's
+  // traces, after the previous fold) and overlaps whatever is traced next -- every entry point that touches
+  // the canvas joins it first.  One that blends over the existing canvas stays on the context's stream.
+  VR_ENTER_NOJOIN(ctx);
+  ++ctx->api_serial;
+  // (measured on B200, c3 on one GPU: 0.539 ms per frame overlapped against 0.495 ms one after the other --
+  // with every block resident the sampler's launches already keep the SMs' issue slots busy, and the fold's
+  // streaming traffic costs them L2 hits -- so the overlap is opt-in: VR_FOLD_OVERLAP=1)
+  static const bool overlap = [] { const char* e = std::getenv("VR_FOLD_OVERLAP"); return e && std::atoi(e) != 0; }();
+  const bool on_x = overlap && canvas_is_clear && ctx->comm.xstream;
+  if (!on_x) VR_JOIN(ctx);
   REQUIRE(cam, "vr_layers_composite_to_canvas: camera is NULL");
   REQUIRE(ctx->lW > 0, "vr_layers_composite_to_canvas: call vr_layers_begin first");
   CK(cudaSetDevice(ctx->device));
@@ -1206,8 +1268,21 @@ extern "C" vr_status vr_layers_composite_to_canvas(vr_ctx* ctx, const vr_camera*
   p.canvas_rgba = ctx->canvas_rgba;
   p.canvas_depth = ctx->canvas_depth;
   fill_to_canvas_params(cam, ctx->lW, ctx->lH, p.tp);
-  CK(launch_layers_fold(p, false, ctx->sm_count, ctx->stream));
+  p.light = on_x ? 1 : 0; // alone on the GPU the 32x8 tiles are faster
+  cudaStream_t xs = on_x ? ctx->comm.xstream : ctx->stream;
+  if (on_x)
+  {
+    CK(cudaEventRecord(ctx->comm.ev_trace, ctx->stream));
+    CK(cudaStreamWaitEvent(xs, ctx->comm.ev_trace, 0));
+  }
+  CK(launch_layers_fold(p, false, ctx->sm_count, xs));
   ctx->launches++;
+  if (on_x)
+  {
+    ctx->comm.xserial += 1;
+    CK(cudaEventRecord(ctx->comm.ev_x[ctx->comm.xserial & 7], xs));
+    ctx->comm.x_pending = true;
+  }
   return VR_OK;
 }
 

@@ -125,13 +125,24 @@ struct Comm
   unsigned long long timeout_ns = 0;            // bound of every cross-rank wait inside the kernels
   // The image exchange runs on its own stream so that it overlaps the NEXT frame's trace (the folded
   // pixels drain into rank 0 over NVLink while the sampler is already busy): ev_trace orders it after the
-  // trace that produced the image, ev_x[n & 1] marks the n-th exchange done.  Every entry point first makes the
+  // trace that produced the image, ev_x[n & 7] marks the n-th exchange done.  Every entry point first makes the
   // context's stream wait for the latest exchange (x_pending), except an image-only vr_trace_to_image,
   // which only needs the one before (its ring slot is then free on every rank).
   cudaStream_t xstream = nullptr;
-  cudaEvent_t ev_trace = nullptr, ev_x[2] = { nullptr, nullptr };
+  cudaEvent_t ev_trace = nullptr, ev_x[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
   unsigned int xserial = 0;                     // exchanges queued on xstream so far (images and layers)
   bool x_pending = false;                       // exchange `xserial` may still be running on xstream
+  unsigned int x_of_img_epoch[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; // xserial of image exchange e, at [e & 7] (0: not on xstream)
+  // Image-only traces (vr_trace_to_image without VR_FRAME_WRITE_CANVAS) of consecutive frames alternate
+  // between two side streams, so that the next frame's CTAs move in while this frame's long rays drain
+  // (the sampler is a persistent grid: alone, its tail leaves the GPU half empty for ~a tile's duration).
+  // ev_t[k] marks the latest trace on tstream[k]; the frame's exchange waits for it, and so does every
+  // entry point that joins (t_pending).
+  cudaStream_t tstream[2] = { nullptr, nullptr };
+  cudaEvent_t ev_t[2] = { nullptr, nullptr }, ev_main = nullptr;
+  bool t_pending[2] = { false, false };
+  bool trace_side = true;                       // VR_TRACE_STREAMS=0: image-only traces stay on the context's stream
+  bool fold_light = true;                       // VR_FOLD_LIGHT=0: the 256-thread exchange kernels (A/B runs)
   bool timeline = false;                        // VR_TIMELINE=1: kernels leave globaltimer stamps in the flags
   bool frame_poisoned = false;                  // a rank-local error hit this frame: the next collective aborts
   // rank 0: "this buffer holds the cleared value outside the rectangle kept in the arena flags",
@@ -152,9 +163,15 @@ struct Comm
   {                                                                                                \
     if ((ctx)->comm.x_pending)                                                                     \
     {                                                                                              \
-      cudaStreamWaitEvent((ctx)->stream, (ctx)->comm.ev_x[(ctx)->comm.xserial & 1], 0);            \
+      cudaStreamWaitEvent((ctx)->stream, (ctx)->comm.ev_x[(ctx)->comm.xserial & 7], 0);            \
       (ctx)->comm.x_pending = false;                                                               \
     }                                                                                              \
+    for (int k_ = 0; k_ < 2; ++k_)                                                                 \
+      if ((ctx)->comm.t_pending[k_])                                                               \
+      {                                                                                            \
+        cudaStreamWaitEvent((ctx)->stream, (ctx)->comm.ev_t[k_], 0);                               \
+        (ctx)->comm.t_pending[k_] = false;                                                         \
+      }                                                                                            \
   } while (0)
 #define VR_ENTER(ctx) do { if (!(ctx)) return VR_ERR_INVALID; ++(ctx)->api_serial; VR_JOIN(ctx); } while (0)
 #define VR_ENTER_RO(ctx) do { if (!(ctx)) return VR_ERR_INVALID; VR_JOIN(ctx); } while (0)
@@ -227,6 +244,14 @@ struct vr_ctx
   float* lpool_depth = nullptr;
   size_t lpool_cap = 0, lpool_used = 0;
   bool layers_in_arena = false;
+  // without an exchange arena the context owns a ring of three layer buffers (table + pools), like the
+  // arena's: the fold of frame k runs on the exchange stream while frame k+1 is traced into the next one
+  static constexpr int kOwnLayerRing = 3;
+  vr::LayerTable* own_ltab[kOwnLayerRing] = { nullptr, nullptr, nullptr };
+  float4* own_lpool_rgba[kOwnLayerRing] = { nullptr, nullptr, nullptr };
+  float* own_lpool_depth[kOwnLayerRing] = { nullptr, nullptr, nullptr };
+  size_t own_lpool_cap[kOwnLayerRing] = { 0, 0, 0 };
+  int own_lslot = 0;
   int lW = 0, lH = 0;
 
   unsigned long long* scratch_u64 = nullptr;
@@ -448,6 +473,7 @@ struct LayerFoldParams
   float* canvas_depth;
   ToCanvasParams tp;
   unsigned long long timeout_ns; // bound of every cross-rank wait (0 = none)
+  int light;        // 32x4 tiles / 128-thread CTAs (fit the slot of one sampler CTA) instead of 32x8 / 256
 };
 cudaError_t launch_layers_fold(const LayerFoldParams& p, bool comm, int sm_count, cudaStream_t s);
 cudaError_t launch_layers_wait_done(unsigned char* flags, int size, unsigned int epoch, unsigned long long timeout_ns,
@@ -481,6 +507,7 @@ struct FoldP2PParams
   size_t off_recv_rgba, off_recv_depth;
   unsigned long long timeout_ns; // bound of every cross-rank wait (0 = none)
   int timeline;                  // diagnostics: leave globaltimer stamps in the flags
+  int light;                     // 128-thread CTAs that fit the slot of one sampler CTA (see fold_p2p_light_kernel)
 };
 cudaError_t launch_fold_p2p(const FoldP2PParams& p, int sm_count, cudaStream_t s);
 } // namespace vr

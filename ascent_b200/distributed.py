@@ -247,11 +247,19 @@ def run_bench(args, wl, bench):
             piped_total_max = float(tp[0])
         total_ms, render_ms, tail_ms = piped if use_piped else serial
 
-        # composite alone: all local images/partials resident, ranks aligned by a barrier
-        comp = []
+        # trace alone and composite alone: ranks aligned by a barrier, nothing else in flight (the library
+        # runs image-only traces and the exchange on its own streams: comm_join brings them back)
+        comp, rend = [], []
         for _ in range(min(args.steps, 10)):
-            render()
             torch.cuda.synchronize()
+            dist.barrier()
+            a, b = ev(), ev()
+            a.record(stream)
+            render()
+            ctx.comm_join()
+            b.record(stream)
+            torch.cuda.synchronize()
+            rend.append(a.elapsed_time(b))
             dist.barrier()
             a, b = ev(), ev()
             a.record(stream)
@@ -261,6 +269,7 @@ def run_bench(args, wl, bench):
             torch.cuda.synchronize()
             comp.append(a.elapsed_time(b))
         comp_ms = float(np.median(comp))
+        render_ms = float(np.median(rend))
         n_partials = 0 if path_a else _count_local_partials(ctx, render)
 
     t = torch.tensor([total_ms, render_ms, tail_ms, comp_ms, float(launches), float(n_partials)],
@@ -307,8 +316,10 @@ def run_bench(args, wl, bench):
         nccl_base = nccl_image_composite_baseline(ctx, dist, stream, W, H, vis_rank, render_full)
 
     # ---- e2e: every rank publishes its blocks from pinned host memory, root reads the canvas back
-    e2e = _e2e(ctx, dist, stream, blocks, mine, fields, sp, cam, W, H, rmin, rmax, render, composite,
-               rank, max(3, min(args.steps, 5)))
+    e2e = None
+    if not getattr(args, "no_e2e", False):
+        e2e = _e2e(ctx, dist, stream, blocks, mine, fields, sp, cam, W, H, rmin, rmax, render, composite,
+                   rank, max(3, min(args.steps, 5)))
 
     # ---- rank 0, outside every timed region: the oracle on the same inputs (parity of the frame that was
     # timed, CPU baseline on the host cores) and T(1) of the same workload on this rank's GPU alone
@@ -392,7 +403,7 @@ def run_bench(args, wl, bench):
                 "ms_per_step_pipelined_order": (piped_total_max / args.steps) if piped is not None else None,
                 "composite_ms_per_frame": comp_ms, "composite_in_step_ms": tail_ms,
                 "partials_total": int(tsum[5]),
-                "per_rank_ms": {"columns": ["total", "render_per_frame", "composite_in_step", "composite_aligned"],
+                "per_rank_ms": {"columns": ["total", "render_alone", "composite_in_step", "composite_aligned"],
                                 "rows": per_rank},
                 "nvlink": {"bytes_into_rank0_per_frame": nv_bytes, "pulled": pulled, "pushed_into_rank0": pushed,
                            "achieved_gbs": nv_bytes / (comp_ms * 1e-3) / 1e9, "peak_gbs": 770.0,

@@ -435,6 +435,7 @@ def measure_single(args, wl, full=True):
         t_begin.record(stream)
         for k in range(args.steps):
             frame(evs[k])
+        ctx.comm_join()  # the last frame's fold runs on the library's exchange stream: inside the timed region
         t_end.record(stream)
         torch.cuda.synchronize()
         clk = clocks.stop()
@@ -620,6 +621,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=[None, "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample and the parity check")
     ap.add_argument("--no-c3", action="store_true", help="plain N=1 run: skip the extra c3_n1 measurement")
+    ap.add_argument("--no-e2e", action="store_true", help="diagnostic runs: skip the end-to-end (host buffer) measurement")
     ap.add_argument("--one-block-per-rank", action="store_true",
                     help="N > 1 diagnostics: rank r renders only block r of c3 (path A at any N); not a bench line")
     ap.add_argument("--nccl-baseline", action="store_true",
