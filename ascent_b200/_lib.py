@@ -36,7 +36,7 @@ SYMBOLS = [
     "vr_sample_distance", "vr_visibility_order", "vr_find_subset", "vr_synth_braid_dev",
     "vr_camera_default", "vr_camera_reset_to_bounds", "vr_camera_azimuth", "vr_camera_elevation",
     "vr_camera_zoom", "vr_camera_cinema", "vr_color_table_sample", "vr_correct_opacity", "vr_comm_timeline",
-    "vr_comm_join",
+    "vr_comm_join", "vr_comm_render_frames",
 ]
 
 
@@ -142,6 +142,8 @@ def load():
         "vr_correct_opacity": (C.c_float, [C.c_float, C.c_float]),
         "vr_comm_timeline": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
         "vr_comm_join": (C.c_int, [vp]),
+        "vr_comm_render_frames": (C.c_int, [vp, C.c_int, C.POINTER(CameraStruct), C.c_int, C.c_int, C.c_int, C.c_float,
+                                            C.c_float, C.c_float, C.POINTER(C.c_int), fp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -475,6 +477,22 @@ class Context:
 
     def comm_join(self):
         self._ck(self.lib.vr_comm_join(self.h))
+
+    def comm_render_frames(self, block_id, cams, W, H, sample_dist, rmin, rmax, vis_orders, bg=None, out_rgba8=None):
+        """vr_comm_render_frames: the frames of a batch in one ABI call.  cams: sequence of cameras (or a prepared
+        ctypes array), vis_orders: (n_frames, n_ranks) int32, out_rgba8: host uint8 array (n_frames, H, W, 4) or None"""
+        if isinstance(cams, C.Array):
+            arr = cams
+        else:
+            arr = (CameraStruct * len(cams))(*[as_camera(c) for c in cams])
+        vo = np.ascontiguousarray(vis_orders, np.int32)
+        bgp = None
+        if bg is not None:
+            bga = np.ascontiguousarray(bg, np.float32)
+            bgp = bga.ctypes.data_as(C.POINTER(C.c_float))
+        self._ck(self.lib.vr_comm_render_frames(self.h, block_id, arr, len(arr), W, H, sample_dist, rmin, rmax,
+                                                vo.ctypes.data_as(C.POINTER(C.c_int)), bgp,
+                                                out_rgba8.ctypes.data if out_rgba8 is not None else None))
 
     def comm_timeline(self):
         out = (C.c_uint64 * 16)()

@@ -37,13 +37,13 @@ namespace
 {
 constexpr size_t kFlagBytes = 4096;
 constexpr int kMaxRanks = 16;
-// A rank's quantised image of frame e lives in ring slot e % 4 (its own arena when pulled, the owners'
+// A rank's quantised image of frame e lives in ring slot e % kImgRing (its own arena when pulled, the owners'
 // receive slots when pushed).  Two slots would do for strictly alternating render/exchange; the third
 // lets a rank trace frame e+1 BEFORE it issues the exchange of frame e (VR_FRAME_AHEAD); the fourth lets
 // that trace start while the rank's own exchange of frame e-1 is still RUNNING on the exchange stream:
 // frame e+1 reuses the slot of frame e-3, and every peer has finished reading e-3 once this rank's
 // exchange of e-2 -- the one before the latest, which vr_trace_to_image waits for -- has completed.
-constexpr int kImgRing = 4;
+constexpr int kImgRing = 6;
 constexpr int kLayerRing = 3; // ray layers of frame e live in buffer e % 3 (same argument, no frame is traced ahead)
 
 struct Flags
@@ -369,9 +369,8 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
 // which only happens at the very end of a trace; this one is placed as soon as ANY sampler CTA of any launch
 // retires.  The layers are folded in batches of four (8 + 8 registers each in flight) instead of all at once.
 // Same ownership, same fold order and operator as fold_p2p_kernel: the same bits.
-constexpr int kLightThreads = 128;
-template <bool TO_CANVAS, bool ZBUF>
-__global__ void __launch_bounds__(kLightThreads, 7) fold_p2p_light_kernel(const __grid_constant__ FoldP2PParams P)
+template <int kLightThreads, bool TO_CANVAS, bool ZBUF>
+__global__ void __launch_bounds__(kLightThreads, kLightThreads == 128 ? 7 : 3) fold_p2p_light_kernel(const __grid_constant__ FoldP2PParams P)
 {
   Flags* my_flags = reinterpret_cast<Flags*>(P.peers[P.rank] + P.off_flags);
   const int par = P.epoch & 1;
@@ -998,7 +997,7 @@ static cudaError_t launch_fold_p2p_nr(const FoldP2PParams& p, int sm_count, cuda
     // system-scope fence, which is the expensive part -- not how fast it would run alone.
     const size_t n4 = (p.n_pixels + 3) / 4;
     const size_t n_chunks = (n4 + kChunkGroups - 1) / kChunkGroups;
-    size_t grid = (size_t)sm_count;
+    size_t grid = (size_t)sm_count * (size_t)(p.grid_per_sm > 0 ? p.grid_per_sm : 1);
     const size_t want = p.rank == 0 ? n_chunks : (n_chunks + p.size - 1) / p.size;
     if (grid > want) grid = want ? want : 1;
     kernel<<<(unsigned)grid, 256, 0, s>>>(p);
@@ -1015,14 +1014,19 @@ cudaError_t launch_fold_p2p(const FoldP2PParams& p, int sm_count, cudaStream_t s
   {
     const size_t n4 = (p.n_pixels + 3) / 4;
     const size_t n_chunks = (n4 + kChunkGroups - 1) / kChunkGroups;
-    size_t grid = (size_t)sm_count;
+    size_t grid = (size_t)sm_count * (size_t)(p.grid_per_sm > 0 ? p.grid_per_sm : 1);
     const size_t want = p.rank == 0 ? n_chunks : (n_chunks + p.size - 1) / p.size;
     if (grid > want) grid = want ? want : 1;
-    if (p.zbuffer) fold_p2p_light_kernel<false, true><<<(unsigned)grid, kLightThreads, 0, s>>>(p);
-    else if (p.canvas_rgba) fold_p2p_light_kernel<true, false><<<(unsigned)grid, kLightThreads, 0, s>>>(p);
-    else fold_p2p_light_kernel<false, false><<<(unsigned)grid, kLightThreads, 0, s>>>(p);
+    auto go = [&](auto k128, auto k256) {
+      if (p.light == 1) k128<<<(unsigned)grid, 128, 0, s>>>(p);
+      else k256<<<(unsigned)grid, 256, 0, s>>>(p);
+    };
+    if (p.zbuffer) go(fold_p2p_light_kernel<128, false, true>, fold_p2p_light_kernel<256, false, true>);
+    else if (p.canvas_rgba) go(fold_p2p_light_kernel<128, true, false>, fold_p2p_light_kernel<256, true, false>);
+    else go(fold_p2p_light_kernel<128, false, false>, fold_p2p_light_kernel<256, false, false>);
     return cudaGetLastError();
   }
+  if (p.force_nr8 && p.size <= 8) return launch_fold_p2p_nr<8>(p, sm_count, s);
   if (p.size <= 2) return launch_fold_p2p_nr<2>(p, sm_count, s);
   if (p.size <= 4) return launch_fold_p2p_nr<4>(p, sm_count, s);
   if (p.size <= 8) return launch_fold_p2p_nr<8>(p, sm_count, s);
@@ -1034,7 +1038,7 @@ void comm_destroy(vr_ctx* ctx)
   Comm& c = ctx->comm;
   // (the streams belong to the context, not to the arena: created in vr_create)
   if (c.xstream) { cudaStreamSynchronize(c.xstream); cudaStreamDestroy(c.xstream); c.xstream = nullptr; }
-  for (int k = 0; k < 2; ++k)
+  for (int k = 0; k < Comm::kMaxTraceStreams; ++k)
   {
     if (c.tstream[k]) { cudaStreamSynchronize(c.tstream[k]); cudaStreamDestroy(c.tstream[k]); c.tstream[k] = nullptr; }
     if (c.ev_t[k]) cudaEventDestroy(c.ev_t[k]);
@@ -1111,19 +1115,19 @@ void comm_join_previous_exchange(vr_ctx* ctx)
   cudaStreamWaitEvent(ctx->stream, c.ev_x[(c.xserial - 1) & 7], 0);
 }
 
-// An image-only trace of image frame e (= epoch + 1, or + 2 when traced ahead) writes ring slot e % 4 -- in
-// this rank's arena, or, pushed, in every owner's receive ring -- which frame e - 4 used.  Every rank has
-// finished reading frame e - 4 once THIS rank's exchange of frame e - 3 has completed: that exchange passed
-// the all-ranks-ready barrier of e - 3, which a rank only joins after its own exchange of e - 4 (same
-// stream).  So the trace waits for exchange e - 3 -- issued two or three calls ago, i.e. normally long
-// done -- and the exchanges of e - 2 and e - 1 may still be running while it goes.
+// An image-only trace of image frame e (= epoch + 1, or + 2 when traced ahead) writes ring slot e % R
+// (R = kImgRing) -- in this rank's arena, or, pushed, in every owner's receive ring -- which frame e - R
+// used.  Every rank has finished reading frame e - R once THIS rank's exchange of frame e - R + 1 has
+// completed: that exchange passed the all-ranks-ready barrier of e - R + 1, which a rank only joins after
+// its own exchange of e - R (same stream).  So the trace waits for exchange e - R + 1 -- issued several
+// calls ago, i.e. normally long done -- and the exchanges after it may still be running while it goes.
 void comm_join_for_image_trace(vr_ctx* ctx, bool ahead, cudaStream_t s)
 {
   Comm& c = ctx->comm;
   if (!c.on || !c.xstream) return;
   const unsigned int e = c.epoch + (ahead ? 2u : 1u);
-  if (e < 4) return;
-  const unsigned int xs = c.x_of_img_epoch[(e - 3) & 7];
+  if (e < (unsigned)kImgRing) return;
+  const unsigned int xs = c.x_of_img_epoch[(e - (kImgRing - 1)) & 7];
   if (xs == 0) return; // that exchange ran on the context's stream: ordered already
   // (an event slot is reused every 8 exchanges: if image and layer exchanges were mixed in between, fall
   // back to the latest exchange)
@@ -1387,17 +1391,20 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
   {
     cudaEventRecord(c.ev_trace, ctx->stream);
     cudaStreamWaitEvent(xs, c.ev_trace, 0);
-    // this frame's image was traced on side stream (epoch & 1): the exchange is what waits for it, and whoever
+    // this frame's image was traced on side stream (epoch % streams): the exchange is what waits for it, and whoever
     // joins the exchange has thereby joined the trace (a frame traced AHEAD sits on the other stream)
-    if (c.t_pending[c.epoch & 1])
+    const int side = c.trace_streams > 0 ? (int)(c.epoch % (unsigned)c.trace_streams) : 0;
+    if (c.t_pending[side])
     {
-      cudaStreamWaitEvent(xs, c.ev_t[c.epoch & 1], 0);
-      c.t_pending[c.epoch & 1] = false;
+      cudaStreamWaitEvent(xs, c.ev_t[side], 0);
+      c.t_pending[side] = false;
     }
   }
   else
     VR_JOIN(ctx);
-  p.light = (c.fold_light && c.size <= 16) ? 1 : 0;
+  p.light = c.fold_light;
+  p.grid_per_sm = c.fold_grid;
+  p.force_nr8 = c.fold_nr8 ? 1 : 0;
   cudaError_t e = launch_fold_p2p(p, ctx->sm_count, xs);
   if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "fold_p2p launch", e);
   ctx->launches++;
@@ -1410,7 +1417,7 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
     if (p.canvas_rgba)
     {
       // waits for every rank's "done" itself, then converts the covered groups
-      if (p.light) covered_to_canvas_kernel<128><<<ctx->sm_count * 2, 128, 0, xs>>>(p);
+      if (p.light == 1) covered_to_canvas_kernel<128><<<ctx->sm_count * 2, 128, 0, xs>>>(p);
       else covered_to_canvas_kernel<256><<<ctx->sm_count * 2, 256, 0, xs>>>(p);
       ctx->launches++;
     }
@@ -1619,6 +1626,53 @@ extern "C" vr_status vr_comm_composite_images_to_canvas(vr_ctx* ctx, const int* 
   return comm_composite_images_impl(ctx, vis_order, true);
 }
 
+// The renders of a batch (Scene::Render renders its m_renders in batches and loops over them, Scene.cpp:133-149;
+// a Cinema database is 64+ cameras per cycle) are independent frames of the same blocks: one call issues all
+// of them back to back -- trace (pushed into the exchange) + visibility-ordered exchange per frame -- so that
+// the host's per-call overhead (one ABI crossing, one parameter set-up per frame instead of two) stays off
+// the GPU's critical path and consecutive frames overlap on the side streams.  frames_rgba8_host (rank 0 only,
+// may be NULL): frame k's final image, background-blended and quantised like Render::Save's input
+// (vr_canvas_download_rgba8), is copied to frames_rgba8_host + k * W * H * 4 as soon as its exchange is done.
+extern "C" vr_status vr_comm_render_frames(vr_ctx* ctx, int block_id, const vr_camera* cams, int n_frames, int width,
+                                           int height, float sample_dist, float range_min, float range_max,
+                                           const int* vis_orders, const float* bg_rgba, uint8_t* frames_rgba8_host)
+{
+  VR_ENTER_NOJOIN(ctx);
+  Comm& c = ctx->comm;
+  if (!c.on || !c.peer_dev) return cfail(ctx, VR_ERR_STATE, "vr_comm_render_frames: not connected", cudaSuccess);
+  if (!cams || !vis_orders || n_frames < 0) return cfail(ctx, VR_ERR_INVALID, "vr_comm_render_frames: NULL argument", cudaSuccess);
+  const int flags = (width % 4 == 0) ? (VR_FRAME_NO_CLEAR | VR_FRAME_PUSH) : 0;
+  const size_t n = (size_t)width * height;
+  for (int k = 0; k < n_frames; ++k)
+  {
+    vr_status st = vr_trace_to_image(ctx, block_id, cams + k, width, height, sample_dist, range_min, range_max, flags);
+    if (st != VR_OK) return st;
+    st = comm_composite_images_impl(ctx, vis_orders + (size_t)k * c.size, true);
+    if (st != VR_OK) return st;
+    if (c.rank == 0 && frames_rgba8_host)
+    {
+      // on the stream the exchange ran on, right behind it: encode + copy out while the next frames trace
+      cudaStream_t xs = c.x_pending ? c.xstream : ctx->stream;
+      if (n > ctx->enc_cap)
+      {
+        cudaStreamSynchronize(xs);
+        cudaFree(ctx->enc_rgba);
+        ctx->enc_rgba = nullptr;
+        ctx->enc_cap = 0;
+        if (cudaMalloc(&ctx->enc_rgba, n * sizeof(uchar4)) != cudaSuccess) return cfail(ctx, VR_ERR_NOMEM, "vr_comm_render_frames", cudaErrorMemoryAllocation);
+        ctx->enc_cap = n;
+      }
+      cudaError_t e = launch_encode_rgba8(ctx->canvas_rgba, width, height, 1, bg_rgba, ctx->enc_rgba, xs);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(frames_rgba8_host + (size_t)k * n * 4, ctx->enc_rgba, n * sizeof(uchar4), cudaMemcpyDeviceToHost, xs);
+      if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "vr_comm_render_frames: encode/copy", e);
+      ctx->launches++;
+      if (xs == c.xstream) cudaEventRecord(c.ev_x[c.xserial & 7], xs); // joining the exchange now joins the copy too
+    }
+  }
+  return VR_OK;
+}
+
 extern "C" vr_status vr_comm_composite_zbuffer(vr_ctx* ctx)
 {
   VR_ENTER_NOJOIN(ctx); // (the exchange stream orders itself after the trace and the previous exchange)
@@ -1698,7 +1752,7 @@ extern "C" vr_status vr_comm_layers_composite_to_canvas(vr_ctx* ctx, const vr_ca
   p.H = ctx->lH;
   p.clear = 1;
   p.smem_layers = kMaxSmemLayers;
-  p.light = c.fold_light ? 1 : 0;
+  p.light = c.fold_light == 1 ? 1 : 0;
   p.timeout_ns = c.timeout_ns;
   for (int r = 0; r < c.size; ++r)
   {

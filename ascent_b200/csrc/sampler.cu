@@ -610,7 +610,7 @@ trace_kernel(const __grid_constant__ TraceParams P)
     // block's screen rectangle are the long ones, so the kernel's tail -- a warp resident at a time draws
     // only a handful of tiles -- is made of the short edge rays
     const int rj = (int)(tile / (unsigned)P.tiles_x), ri = (int)(tile % (unsigned)P.tiles_x);
-    const int tj = centre_out(rj, P.tiles_y), ti = centre_out(ri, P.tiles_x);
+    const int tj = P.tile_order ? rj : centre_out(rj, P.tiles_y), ti = P.tile_order ? ri : centre_out(ri, P.tiles_x);
     const int i = P.tx0 + ti * kTileW + lx;
     const int j = P.sy + tj * kTileH + ly;
     // tx0 <= sx: in MODE 2 the traced rectangle is widened to 4-pixel boundaries so that its

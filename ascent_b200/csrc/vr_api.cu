@@ -86,6 +86,7 @@ extern "C" vr_status vr_create(int device, vr_ctx** out)
   }
   ctx->stream = ctx->own_stream;
   if (const char* e = std::getenv("VR_CTAS_PER_SM")) ctx->ctas_per_sm = std::atoi(e); // tuning knob
+  if (const char* e = std::getenv("VR_TILE_ORDER")) ctx->tile_order = std::atoi(e);
   if (const char* e = std::getenv("VR_COUNT_SAMPLES")) ctx->count_samples = std::atoi(e) != 0;
   if (const char* e = std::getenv("VR_NO_SPARSE")) ctx->no_sparse = std::atoi(e) != 0; // A/B knobs: general march only
   // The brick march (TMA-staged bricks) is bit-identical to the general march but measured SLOWER on B200 at
@@ -94,7 +95,7 @@ extern "C" vr_status vr_create(int device, vr_ctx** out)
   ctx->no_brick = true;
   if (const char* e = std::getenv("VR_BRICK")) ctx->no_brick = std::atoi(e) == 0;
   // [0]: single launches, [1 + k]: launch k of a batched call, [1 + kMaxLayers + s]: image trace on side stream s
-  cudaMalloc(&ctx->tile_counter, (size_t)(3 + vr::kMaxLayers) * sizeof(unsigned int));
+  cudaMalloc(&ctx->tile_counter, (size_t)(1 + vr::kMaxLayers + vr::Comm::kMaxTraceStreams) * sizeof(unsigned int));
   {
     // the exchange stream (fold of frame k overlaps the trace of frame k+1; its CTAs go first when SM slots
     // free up) and the two side streams of image-only traces -- see vr_internal.h
@@ -105,13 +106,15 @@ extern "C" vr_status vr_create(int device, vr_ctx** out)
     cudaEventCreateWithFlags(&c.ev_trace, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c.ev_main, cudaEventDisableTiming);
     for (int k = 0; k < 8; ++k) cudaEventCreateWithFlags(&c.ev_x[k], cudaEventDisableTiming);
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < vr::Comm::kMaxTraceStreams; ++k)
     {
       cudaStreamCreateWithFlags(&c.tstream[k], cudaStreamNonBlocking);
       cudaEventCreateWithFlags(&c.ev_t[k], cudaEventDisableTiming);
     }
-    if (const char* e = std::getenv("VR_TRACE_STREAMS")) c.trace_side = std::atoi(e) != 0;
-    if (const char* e = std::getenv("VR_FOLD_LIGHT")) c.fold_light = std::atoi(e) != 0;
+    if (const char* e = std::getenv("VR_TRACE_STREAMS")) c.trace_streams = std::max(0, std::min(std::atoi(e), (int)vr::Comm::kMaxTraceStreams));
+    if (const char* e = std::getenv("VR_FOLD_LIGHT")) c.fold_light = std::atoi(e);
+    if (const char* e = std::getenv("VR_FOLD_GRID")) c.fold_grid = std::atoi(e);
+    if (const char* e = std::getenv("VR_FOLD_NR8")) c.fold_nr8 = std::atoi(e) != 0;
   }
   for (int k = 0; k < vr::kAuxStreams; ++k)
   {
@@ -790,6 +793,7 @@ static vr_status fill_trace_params(vr_ctx* ctx, int block_id, const vr_camera* c
   p.tile_counter = ctx->tile_counter;
   p.sample_counter = ctx->count_samples ? ctx->sample_counter : nullptr;
   p.ctas_per_sm = ctx->ctas_per_sm;
+  p.tile_order = ctx->tile_order;
   return VR_OK;
 }
 
@@ -833,7 +837,7 @@ extern "C" vr_status vr_trace_to_image(vr_ctx* ctx, int block_id, const vr_camer
   CK(cudaSetDevice(ctx->device));
   // Where the launch goes.  A frame that also writes the canvas runs on the context's stream, after
   // everything the latest exchange does to the canvas.  An image-only frame of a connected context runs on
-  // one of two side streams (by frame parity): it neither waits for the previous frame's trace nor for the
+  // one of a few side streams (round-robin by frame): it neither waits for the previous frame's trace nor for the
   // exchanges still in flight, only for the exchange that frees its ring slot (comm_join_for_image_trace).
   cudaStream_t ts = ctx->stream;
   int side = -1;
@@ -842,13 +846,13 @@ extern "C" vr_status vr_trace_to_image(vr_ctx* ctx, int block_id, const vr_camer
     ++ctx->api_serial;
     VR_JOIN(ctx);
   }
-  else if (ctx->comm.on && ctx->comm.trace_side && ctx->comm.tstream[0])
+  else if (ctx->comm.on && ctx->comm.trace_streams > 0 && ctx->comm.tstream[0])
   {
     auto it = ctx->blocks.find(block_id);
     const bool staging = it != ctx->blocks.end() && it->second.staged_src && !it->second.all_resident;
     if (!staging) // (demand staging keeps per-block state on the device: one trace of the block at a time)
     {
-      side = (int)((ctx->comm.epoch + (ahead ? 2u : 1u)) & 1u);
+      side = (int)((ctx->comm.epoch + (ahead ? 2u : 1u)) % (unsigned)ctx->comm.trace_streams);
       ts = ctx->comm.tstream[side];
       CK(cudaEventRecord(ctx->comm.ev_main, ctx->stream)); // after what the caller queued so far (publishes, ...)
       CK(cudaStreamWaitEvent(ts, ctx->comm.ev_main, 0));

@@ -86,6 +86,7 @@ struct TraceParams
   unsigned long long* sample_counter; // may be null
   unsigned long long* end_stamp;      // diagnostics: atomicMax of globaltimer at CTA exit (may be null)
   int ctas_per_sm;                    // 0 = default
+  int tile_order;                     // 0 = centre-out (default), 1 = row-major (VR_TILE_ORDER, A/B runs)
 };
 
 // ---------------------------------------------------------------- host-side state
@@ -133,16 +134,20 @@ struct Comm
   unsigned int xserial = 0;                     // exchanges queued on xstream so far (images and layers)
   bool x_pending = false;                       // exchange `xserial` may still be running on xstream
   unsigned int x_of_img_epoch[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; // xserial of image exchange e, at [e & 7] (0: not on xstream)
-  // Image-only traces (vr_trace_to_image without VR_FRAME_WRITE_CANVAS) of consecutive frames alternate
-  // between two side streams, so that the next frame's CTAs move in while this frame's long rays drain
+  // Image-only traces (vr_trace_to_image without VR_FRAME_WRITE_CANVAS) of consecutive frames rotate
+  // over a few side streams, so that the next frames' CTAs move in while this frame's long rays drain
   // (the sampler is a persistent grid: alone, its tail leaves the GPU half empty for ~a tile's duration).
   // ev_t[k] marks the latest trace on tstream[k]; the frame's exchange waits for it, and so does every
   // entry point that joins (t_pending).
-  cudaStream_t tstream[2] = { nullptr, nullptr };
-  cudaEvent_t ev_t[2] = { nullptr, nullptr }, ev_main = nullptr;
-  bool t_pending[2] = { false, false };
-  bool trace_side = true;                       // VR_TRACE_STREAMS=0: image-only traces stay on the context's stream
-  bool fold_light = true;                       // VR_FOLD_LIGHT=0: the 256-thread exchange kernels (A/B runs)
+  static constexpr int kMaxTraceStreams = 4;
+  cudaStream_t tstream[kMaxTraceStreams] = { nullptr, nullptr, nullptr, nullptr };
+  cudaEvent_t ev_t[kMaxTraceStreams] = { nullptr, nullptr, nullptr, nullptr }, ev_main = nullptr;
+  bool t_pending[kMaxTraceStreams] = { false, false, false, false };
+  int trace_streams = 3;                        // VR_TRACE_STREAMS=0..4: 0 keeps image-only traces on the context's stream
+  // exchange kernel shape (A/B runs): 0 = all layers in registers, 256 threads (default); 1 / 2 = layers in
+  // batches of four, <= 72 registers, 128 / 256 threads; fold_grid = CTAs per SM (0: 1)
+  int fold_light = 0, fold_grid = 0;
+  bool fold_nr8 = false;                        // VR_FOLD_NR8=1: instantiate the fold for 8 ranks even with fewer
   bool timeline = false;                        // VR_TIMELINE=1: kernels leave globaltimer stamps in the flags
   bool frame_poisoned = false;                  // a rank-local error hit this frame: the next collective aborts
   // rank 0: "this buffer holds the cleared value outside the rectangle kept in the arena flags",
@@ -166,7 +171,7 @@ struct Comm
       cudaStreamWaitEvent((ctx)->stream, (ctx)->comm.ev_x[(ctx)->comm.xserial & 7], 0);            \
       (ctx)->comm.x_pending = false;                                                               \
     }                                                                                              \
-    for (int k_ = 0; k_ < 2; ++k_)                                                                 \
+    for (int k_ = 0; k_ < vr::Comm::kMaxTraceStreams; ++k_)                                        \
       if ((ctx)->comm.t_pending[k_])                                                               \
       {                                                                                            \
         cudaStreamWaitEvent((ctx)->stream, (ctx)->comm.ev_t[k_], 0);                               \
@@ -189,6 +194,7 @@ struct vr_ctx
   uint64_t launches = 0;
   int sm_count = 148;
   int ctas_per_sm = 0;        // trace kernel residency (0 = built-in default)
+  int tile_order = 0;         // VR_TILE_ORDER=1: tiles in row-major order instead of centre-out
   bool count_samples = false; // accumulate the number of samples taken (debug/bench)
   bool no_sparse = false;     // never select the sampler's sparse march (A/B runs)
   bool no_brick = false;      // never select the brick march (A/B runs)
@@ -507,7 +513,9 @@ struct FoldP2PParams
   size_t off_recv_rgba, off_recv_depth;
   unsigned long long timeout_ns; // bound of every cross-rank wait (0 = none)
   int timeline;                  // diagnostics: leave globaltimer stamps in the flags
-  int light;                     // 128-thread CTAs that fit the slot of one sampler CTA (see fold_p2p_light_kernel)
+  int light;                     // 0: fold_p2p_kernel; 1 / 2: fold_p2p_light_kernel with 128 / 256 threads
+  int grid_per_sm;               // CTAs per SM of the fold (0: one)
+  int force_nr8;                 // diagnostics: the 8-rank instantiation whatever the size
 };
 cudaError_t launch_fold_p2p(const FoldP2PParams& p, int sm_count, cudaStream_t s);
 } // namespace vr

@@ -312,6 +312,18 @@ VR_API vr_status vr_comm_join(vr_ctx* ctx);
 /* The same plus Renderer::ImageToCanvas on rank 0 (vr_image_result_to_canvas) folded into the
  * exchange: rank 0 converts the pixels no rank covers while the others are still in flight.    */
 VR_API vr_status vr_comm_composite_images_to_canvas(vr_ctx* ctx, const int* vis_order);
+/* A batch of renders on path A, all ranks collectively (the loop over the renders of a batch in
+ * vtkh::Scene::Render, Scene.cpp:133-149, around RenderOneDomainPerRank + Composite,
+ * VolumeRenderer.cpp:482-536, 652-688): for k in [0, n_frames): vr_trace_to_image(block_id, cams[k]) pushed into
+ * the exchange, then vr_comm_composite_images_to_canvas(vis_orders + k * n_ranks).  One ABI crossing for the
+ * whole batch; consecutive frames overlap (trace of k+1 and k+2 while k is exchanged).  Rank 0's canvas holds
+ * the last frame afterwards; frames_rgba8_host (rank 0, may be NULL; pinned memory makes the copies
+ * asynchronous) receives EVERY frame as RGBA8, rows flipped, blended over bg_rgba (NULL: no background) -- the
+ * input of Render::Save's PNG encoder (Render.cpp:299-312) -- frame k at offset k * width * height * 4.
+ * Call vr_synchronize before reading the host frames.                                             */
+VR_API vr_status vr_comm_render_frames(vr_ctx* ctx, int block_id, const vr_camera* cams, int n_frames, int width,
+                                       int height, float sample_dist, float range_min, float range_max,
+                                       const int* vis_orders, const float* bg_rgba, uint8_t* frames_rgba8_host);
 /* Opaque surfaces, all ranks collectively (Compositor Z_BUFFER_SURFACE -> RadixKCompositor::
  * CompositeSurface, RadixKCompositor.cpp:35-180): the same fused exchange with
  * ImageCompositor::ZBufferComposite (ImageCompositor.hpp:49-76) as the per-pixel operator, folded in
