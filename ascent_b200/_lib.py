@@ -36,7 +36,7 @@ SYMBOLS = [
     "vr_sample_distance", "vr_visibility_order", "vr_find_subset", "vr_synth_braid_dev",
     "vr_camera_default", "vr_camera_reset_to_bounds", "vr_camera_azimuth", "vr_camera_elevation",
     "vr_camera_zoom", "vr_camera_cinema", "vr_color_table_sample", "vr_correct_opacity", "vr_comm_timeline",
-    "vr_comm_join", "vr_comm_render_frames",
+    "vr_comm_join", "vr_comm_render_frames", "vr_comm_connect_local",
 ]
 
 
@@ -142,6 +142,7 @@ def load():
         "vr_correct_opacity": (C.c_float, [C.c_float, C.c_float]),
         "vr_comm_timeline": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
         "vr_comm_join": (C.c_int, [vp]),
+        "vr_comm_connect_local": (C.c_int, [C.POINTER(vp), C.c_int]),
         "vr_comm_render_frames": (C.c_int, [vp, C.c_int, C.POINTER(CameraStruct), C.c_int, C.c_int, C.c_int, C.c_float,
                                             C.c_float, C.c_float, C.POINTER(C.c_int), fp, vp]),
     }
@@ -163,6 +164,15 @@ def _f3(v):
 
 def _d6(v):
     return (C.c_double * 6)(*[float(x) for x in v])
+
+
+def comm_connect_local(ctxs):
+    """vr_comm_connect_local: the contexts of ONE process (one per GPU), each already comm_init'ed as rank r"""
+    arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    st = load().vr_comm_connect_local(arr, len(ctxs))
+    if st != 0:
+        raise VRError("vr_comm_connect_local failed (%d): %s" % (
+            st, "; ".join(c.lib.vr_last_error(c.h).decode() for c in ctxs)))
 
 
 def as_camera(cam):

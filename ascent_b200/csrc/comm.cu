@@ -22,6 +22,7 @@
 //   [partial offsets x2][sorted partials x2][composited partials (rank 0)]
 // Buffers are double-buffered by epoch parity so a rank may start producing frame e+1 while a
 // slower peer still reads frame e.
+#include <algorithm>
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
@@ -947,8 +948,11 @@ struct Layout
   // receive ring of pushed frames: slot e % 3 holds, for every source rank, the pixels of frame e that
   // THIS rank owns (round-robin 1024-pixel chunks), written by the sources' samplers over NVLink
   size_t off_recv_rgba[kImgRing], off_recv_depth[kImgRing];
+  // receive pools of pushed ray layers: buffer e % 3 holds, per source rank, max_partials entries at the
+  // source's own pool indices -- only those whose screen tile this rank folds are ever written
+  size_t off_lrecv_rgba[kLayerRing], off_lrecv_depth[kLayerRing];
 };
-Layout make_layout(size_t max_pixels, size_t max_partials, bool is_root)
+Layout make_layout(size_t max_pixels, size_t max_partials, bool is_root, int n_ranks)
 {
   Layout L;
   const size_t px = align_up(max_pixels, 64);
@@ -969,6 +973,9 @@ Layout make_layout(size_t max_pixels, size_t max_partials, bool is_root)
   for (int b = 0; b < kLayerRing; ++b) { L.off_ltab[b] = o; o += max_partials ? align_up(sizeof(LayerTable), 256) : 0; }
   for (int b = 0; b < kLayerRing; ++b) { L.off_lpool_rgba[b] = o; o += align_up(max_partials * sizeof(float4), 256); }
   for (int b = 0; b < kLayerRing; ++b) { L.off_lpool_depth[b] = o; o += align_up(max_partials * sizeof(float), 256); }
+  const size_t recv_entries = n_ranks > 1 ? max_partials * (size_t)n_ranks : 0;
+  for (int b = 0; b < kLayerRing; ++b) { L.off_lrecv_rgba[b] = o; o += align_up(recv_entries * sizeof(float4), 256); }
+  for (int b = 0; b < kLayerRing; ++b) { L.off_lrecv_depth[b] = o; o += align_up(recv_entries * sizeof(float), 256); }
   // regions only rank 0 allocates; their OFFSETS are the same on every rank (peers address them)
   const size_t common_end = o;
   L.off_pout = o;
@@ -1000,6 +1007,7 @@ static cudaError_t launch_fold_p2p_nr(const FoldP2PParams& p, int sm_count, cuda
     size_t grid = (size_t)sm_count * (size_t)(p.grid_per_sm > 0 ? p.grid_per_sm : 1);
     const size_t want = p.rank == 0 ? n_chunks : (n_chunks + p.size - 1) / p.size;
     if (grid > want) grid = want ? want : 1;
+    if (p.max_ctas > 0 && grid > (size_t)p.max_ctas) grid = (size_t)p.max_ctas;
     kernel<<<(unsigned)grid, 256, 0, s>>>(p);
   };
   if (p.zbuffer) go(fold_p2p_kernel<NR, false, true>);
@@ -1017,6 +1025,7 @@ cudaError_t launch_fold_p2p(const FoldP2PParams& p, int sm_count, cudaStream_t s
     size_t grid = (size_t)sm_count * (size_t)(p.grid_per_sm > 0 ? p.grid_per_sm : 1);
     const size_t want = p.rank == 0 ? n_chunks : (n_chunks + p.size - 1) / p.size;
     if (grid > want) grid = want ? want : 1;
+    if (p.max_ctas > 0 && grid > (size_t)p.max_ctas) grid = (size_t)p.max_ctas;
     auto go = [&](auto k128, auto k256) {
       if (p.light == 1) k128<<<(unsigned)grid, 128, 0, s>>>(p);
       else k256<<<(unsigned)grid, 256, 0, s>>>(p);
@@ -1049,7 +1058,7 @@ void comm_destroy(vr_ctx* ctx)
     if (c.ev_x[k]) cudaEventDestroy(c.ev_x[k]);
   if (!c.on) return;
   for (int r = 0; r < (int)c.peer.size(); ++r)
-    if (r != c.rank && c.peer[r]) cudaIpcCloseMemHandle(c.peer[r]);
+    if (r != c.rank && c.peer[r] && !c.local_peers) cudaIpcCloseMemHandle(c.peer[r]);
   cudaFree(c.peer_dev);
   cudaFree(c.minmax_dev);
   cudaFree(c.arena);
@@ -1065,7 +1074,7 @@ vr_status comm_bind_frame(vr_ctx* ctx, size_t n_pixels)
     ctx->err = "image larger than the max_pixels given to vr_comm_init";
     return VR_ERR_INVALID;
   }
-  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0, c.size);
   const int b = (c.epoch + 1) & 1;
   const int slot = (int)((c.epoch + 1) % kImgRing);
   ctx->img_rgba = reinterpret_cast<uchar4*>(c.arena + L.off_img_rgba[slot]);
@@ -1098,7 +1107,7 @@ vr_status comm_ahead_image(vr_ctx* ctx, uchar4** rgba, float** depth)
     ctx->err = "VR_FRAME_AHEAD needs the exchange arena (vr_comm_init)";
     return VR_ERR_STATE;
   }
-  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0, c.size);
   const int slot = (int)((c.epoch + 2) % kImgRing);
   *rgba = reinterpret_cast<uchar4*>(c.arena + L.off_img_rgba[slot]);
   *depth = reinterpret_cast<float*>(c.arena + L.off_img_depth[slot]);
@@ -1149,7 +1158,7 @@ vr_status comm_push_target(vr_ctx* ctx, bool ahead, int width, int height, Trace
     ctx->err = "image larger than the max_pixels given to vr_comm_init";
     return VR_ERR_INVALID;
   }
-  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0, c.size);
   const int slot = (int)((c.epoch + (ahead ? 2 : 1)) % kImgRing);
   const size_t n4 = ((size_t)width * height + 3) / 4;
   const size_t n_chunks = (n4 + kChunkGroups - 1) / kChunkGroups;
@@ -1168,7 +1177,7 @@ unsigned long long* comm_timeline_slot(vr_ctx* ctx, int k)
 {
   Comm& c = ctx->comm;
   if (!c.on || !c.timeline) return nullptr;
-  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0, c.size);
   return reinterpret_cast<unsigned long long*>(c.arena + L.off_flags + offsetof(Flags, timeline)) + k;
 }
 
@@ -1178,7 +1187,7 @@ vr_status comm_check_errors(vr_ctx* ctx)
 {
   Comm& c = ctx->comm;
   if (!c.on) return VR_OK;
-  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0, c.size);
   unsigned int e[4] = { 0, 0, 0, 0 }, le[4] = { 0, 0, 0, 0 };
   if (cudaMemcpy(e, c.arena + L.off_flags + offsetof(Flags, err_epoch), sizeof(e), cudaMemcpyDeviceToHost) != cudaSuccess)
     return VR_OK;
@@ -1200,7 +1209,7 @@ vr_status comm_check_errors(vr_ctx* ctx)
 vr_status comm_bind_layers(vr_ctx* ctx)
 {
   Comm& c = ctx->comm;
-  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0, c.size);
   const int b = (int)((c.lepoch + 1) % kLayerRing);
   if (!ctx->layers_in_arena)
   {
@@ -1217,7 +1226,25 @@ vr_status comm_bind_layers(vr_ctx* ctx)
   ctx->lpool_rgba = reinterpret_cast<float4*>(c.arena + L.off_lpool_rgba[b]);
   ctx->lpool_depth = reinterpret_cast<float*>(c.arena + L.off_lpool_depth[b]);
   ctx->lpool_cap = c.max_partials;
+  ctx->layers_pushed = c.layer_push && c.peer_dev && c.size > 1;
   return VR_OK;
+}
+
+// where the sampler pushes the entries of the layer frame being traced (see TraceParams::lpush_*)
+void comm_layer_push_target(vr_ctx* ctx, TraceParams& p)
+{
+  Comm& c = ctx->comm;
+  p.lpush_peers = nullptr;
+  if (!ctx->layers_pushed || !c.on || !c.peer_dev || c.size < 2) return;
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0, c.size);
+  const int b = (int)((c.lepoch + 1) % kLayerRing);
+  p.lpush_peers = c.peer_dev;
+  p.lpush_off_rgba = L.off_lrecv_rgba[b];
+  p.lpush_off_depth = L.off_lrecv_depth[b];
+  p.lpush_stride = c.max_partials;
+  p.lpush_rank = c.rank;
+  p.lpush_size = c.size;
+  p.lpush_tpr = (p.W + 31) / 32;
 }
 
 vr_status upload_layer_table_pub(vr_ctx* ctx);
@@ -1254,7 +1281,7 @@ extern "C" vr_status vr_comm_init(vr_ctx* ctx, int rank, int n_ranks, size_t max
     c.timeout_ns = ms > 0 ? (unsigned long long)ms * 1000000ull : 0ull;
     if (const char* e = std::getenv("VR_TIMELINE")) c.timeline = std::atoi(e) != 0;
   }
-  const Layout L = make_layout(max_pixels, max_partials, rank == 0);
+  const Layout L = make_layout(max_pixels, max_partials, rank == 0, n_ranks);
   c.arena_bytes = L.total;
   cudaError_t e = cudaMalloc(&c.arena, c.arena_bytes);
   if (e != cudaSuccess) return cfail(ctx, VR_ERR_NOMEM, "vr_comm_init: arena", e);
@@ -1323,13 +1350,61 @@ extern "C" vr_status vr_comm_connect(vr_ctx* ctx, const void* all_handles)
   return VR_OK;
 }
 
+// Deployment shape (i) of SURVEY 8(b): ONE process drives every GPU of the node, one context per GPU.  No IPC:
+// the arenas are this process's own allocations; a context on another device reaches them through plain
+// peer access (cudaDeviceEnablePeerAccess over NVLink).  Everything else -- kernels, flags, rings -- is the
+// one-process-per-GPU path.  Collective entry points must then be ISSUED on every context before any of
+// them is synchronised (the kernels of one context wait for the others' flags).
+extern "C" vr_status vr_comm_connect_local(vr_ctx* const* ctxs, int n_ranks)
+{
+  if (!ctxs || n_ranks < 1 || n_ranks > kMaxRanks) return VR_ERR_INVALID;
+  for (int r = 0; r < n_ranks; ++r)
+  {
+    vr_ctx* ctx = ctxs[r];
+    if (!ctx) return VR_ERR_INVALID;
+    Comm& c = ctx->comm;
+    if (!c.on || c.rank != r || c.size != n_ranks)
+      return cfail(ctx, VR_ERR_STATE, "vr_comm_connect_local: context r must have been vr_comm_init'ed as rank r of n_ranks", cudaSuccess);
+    if (c.peer_dev) return cfail(ctx, VR_ERR_STATE, "vr_comm_connect_local: already connected", cudaSuccess);
+    if (c.max_pixels != ctxs[0]->comm.max_pixels || c.max_partials != ctxs[0]->comm.max_partials)
+      return cfail(ctx, VR_ERR_INVALID, "vr_comm_connect_local: max_pixels/max_partials must be identical on all ranks", cudaSuccess);
+  }
+  for (int r = 0; r < n_ranks; ++r)
+  {
+    vr_ctx* ctx = ctxs[r];
+    Comm& c = ctx->comm;
+    cudaSetDevice(ctx->device);
+    for (int q = 0; q < n_ranks; ++q)
+    {
+      if (ctxs[q]->device != ctx->device)
+      {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, ctx->device, ctxs[q]->device);
+        if (!can) return cfail(ctx, VR_ERR_CUDA, "vr_comm_connect_local: no peer access between two of the devices", cudaSuccess);
+        cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "cudaDeviceEnablePeerAccess", e);
+      }
+      c.peer[q] = ctxs[q]->comm.arena;
+    }
+    cudaError_t e = cudaMalloc(&c.peer_dev, sizeof(unsigned char*) * kMaxRanks);
+    if (e != cudaSuccess) return cfail(ctx, VR_ERR_NOMEM, "vr_comm_connect_local", e);
+    unsigned char* table[kMaxRanks] = { nullptr };
+    for (int q = 0; q < n_ranks; ++q) table[q] = c.peer[q];
+    e = cudaMemcpy(c.peer_dev, table, sizeof(table), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "vr_comm_connect_local", e);
+    c.local_peers = true;
+  }
+  return VR_OK;
+}
+
 static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, bool to_canvas, bool zbuffer = false)
 {
   Comm& c = ctx->comm;
   if (!c.on || !c.peer_dev) return cfail(ctx, VR_ERR_STATE, "vr_comm_composite_images: not connected", cudaSuccess);
   if (!vis_order || ctx->W <= 0) return cfail(ctx, VR_ERR_INVALID, "vr_comm_composite_images: no image / NULL order", cudaSuccess);
   cudaSetDevice(ctx->device);
-  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0, c.size);
   c.epoch += 1; // the image was quantised into parity (epoch+1)&1 by vr_image_from_canvas
   const int b = c.epoch & 1;
   FoldP2PParams p;
@@ -1405,6 +1480,7 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
   p.light = c.fold_light;
   p.grid_per_sm = c.fold_grid;
   p.force_nr8 = c.fold_nr8 ? 1 : 0;
+  p.max_ctas = c.exchange_max_ctas;
   cudaError_t e = launch_fold_p2p(p, ctx->sm_count, xs);
   if (e != cudaSuccess) return cfail(ctx, VR_ERR_CUDA, "fold_p2p launch", e);
   ctx->launches++;
@@ -1417,8 +1493,9 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
     if (p.canvas_rgba)
     {
       // waits for every rank's "done" itself, then converts the covered groups
-      if (p.light == 1) covered_to_canvas_kernel<128><<<ctx->sm_count * 2, 128, 0, xs>>>(p);
-      else covered_to_canvas_kernel<256><<<ctx->sm_count * 2, 256, 0, xs>>>(p);
+      const int cgrid = c.exchange_max_ctas > 0 ? std::min(ctx->sm_count * 2, c.exchange_max_ctas) : ctx->sm_count * 2;
+      if (p.light == 1) covered_to_canvas_kernel<128><<<cgrid, 128, 0, xs>>>(p);
+      else covered_to_canvas_kernel<256><<<cgrid, 256, 0, xs>>>(p);
       ctx->launches++;
     }
     else
@@ -1503,7 +1580,7 @@ static vr_status comm_composite_partials_impl(vr_ctx* ctx, const vr_camera* cam)
   if (ctx->n_partials_host > c.max_partials)
   {
     // rank-local: the peers are (or will be) inside this exchange already -- release them
-    const Layout La = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
+    const Layout La = make_layout(c.max_pixels, c.max_partials, c.rank == 0, c.size);
     c.pepoch += 1;
     abort_announce_kernel<<<1, 32, 0, ctx->stream>>>(c.peer_dev, c.rank, c.size, La.off_flags, kPathPartials, c.pepoch);
     ctx->launches++;
@@ -1516,7 +1593,7 @@ static vr_status comm_composite_partials_impl(vr_ctx* ctx, const vr_camera* cam)
   }
   vr_status st = ensure_partial_scratch_pub(ctx, n_pixels, ctx->partial_cap ? ctx->partial_cap : 1);
   if (st != VR_OK) return st;
-  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0, c.size);
   c.pepoch += 1;
   const int par = c.pepoch & 1;
   PartialScratch sc{ ctx->px_count, ctx->px_end, ctx->sidx, ctx->rec, ctx->scan_blocks };
@@ -1643,6 +1720,17 @@ extern "C" vr_status vr_comm_render_frames(vr_ctx* ctx, int block_id, const vr_c
   if (!cams || !vis_orders || n_frames < 0) return cfail(ctx, VR_ERR_INVALID, "vr_comm_render_frames: NULL argument", cudaSuccess);
   const int flags = (width % 4 == 0) ? (VR_FRAME_NO_CLEAR | VR_FRAME_PUSH) : 0;
   const size_t n = (size_t)width * height;
+  if (c.rank == 0 && frames_rgba8_host && n > ctx->enc_cap)
+  {
+    // (before anything of this batch is queued: nothing here may block on a peer that has not been issued yet)
+    VR_JOIN(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->enc_rgba);
+    ctx->enc_rgba = nullptr;
+    ctx->enc_cap = 0;
+    if (cudaMalloc(&ctx->enc_rgba, n * sizeof(uchar4)) != cudaSuccess) return cfail(ctx, VR_ERR_NOMEM, "vr_comm_render_frames", cudaErrorMemoryAllocation);
+    ctx->enc_cap = n;
+  }
   for (int k = 0; k < n_frames; ++k)
   {
     vr_status st = vr_trace_to_image(ctx, block_id, cams + k, width, height, sample_dist, range_min, range_max, flags);
@@ -1653,15 +1741,6 @@ extern "C" vr_status vr_comm_render_frames(vr_ctx* ctx, int block_id, const vr_c
     {
       // on the stream the exchange ran on, right behind it: encode + copy out while the next frames trace
       cudaStream_t xs = c.x_pending ? c.xstream : ctx->stream;
-      if (n > ctx->enc_cap)
-      {
-        cudaStreamSynchronize(xs);
-        cudaFree(ctx->enc_rgba);
-        ctx->enc_rgba = nullptr;
-        ctx->enc_cap = 0;
-        if (cudaMalloc(&ctx->enc_rgba, n * sizeof(uchar4)) != cudaSuccess) return cfail(ctx, VR_ERR_NOMEM, "vr_comm_render_frames", cudaErrorMemoryAllocation);
-        ctx->enc_cap = n;
-      }
       cudaError_t e = launch_encode_rgba8(ctx->canvas_rgba, width, height, 1, bg_rgba, ctx->enc_rgba, xs);
       if (e == cudaSuccess)
         e = cudaMemcpyAsync(frames_rgba8_host + (size_t)k * n * 4, ctx->enc_rgba, n * sizeof(uchar4), cudaMemcpyDeviceToHost, xs);
@@ -1690,7 +1769,7 @@ extern "C" vr_status vr_comm_sync_depths(vr_ctx* ctx)
   const size_t n = (size_t)ctx->W * ctx->H;
   if (n > c.max_pixels) return cfail(ctx, VR_ERR_INVALID, "vr_comm_sync_depths: canvas larger than max_pixels", cudaSuccess);
   cudaSetDevice(ctx->device);
-  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0, c.size);
   c.sepoch += 1;
   Flags* root_flags = reinterpret_cast<Flags*>(c.peer[0] + L.off_flags);
   float* staged = reinterpret_cast<float*>(c.peer[0] + L.off_sync_depth);
@@ -1731,7 +1810,7 @@ extern "C" vr_status vr_comm_layers_composite_to_canvas(vr_ctx* ctx, const vr_ca
     return cfail(ctx, VR_ERR_INVALID, "vr_comm_layers_composite_to_canvas: frame larger than max_pixels", cudaSuccess);
   const bool too_many = ctx->ltab_host->n > kMaxSmemLayers / c.size;
   cudaSetDevice(ctx->device);
-  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0);
+  const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0, c.size);
   c.lepoch += 1;
   const int par = (int)(c.lepoch % kLayerRing);
   vr_status st = upload_layer_table_pub(ctx); // into the arena table of this parity (bound at vr_layers_begin)
@@ -1754,11 +1833,23 @@ extern "C" vr_status vr_comm_layers_composite_to_canvas(vr_ctx* ctx, const vr_ca
   p.smem_layers = kMaxSmemLayers;
   p.light = c.fold_light == 1 ? 1 : 0;
   p.timeout_ns = c.timeout_ns;
+  p.max_ctas = c.exchange_max_ctas;
+  p.pushed = ctx->layers_pushed ? 1 : 0;
+  if (p.pushed) p.light = 0; // (the samplers addressed the owners by 32x8 tiles)
   for (int r = 0; r < c.size; ++r)
   {
     p.table[r] = reinterpret_cast<const LayerTable*>(c.peer[r] + L.off_ltab[par]);
-    p.pool_rgba[r] = reinterpret_cast<const float4*>(c.peer[r] + L.off_lpool_rgba[par]);
-    p.pool_depth[r] = reinterpret_cast<const float*>(c.peer[r] + L.off_lpool_depth[par]);
+    if (p.pushed)
+    {
+      // every rank's entries of MY tiles sit in my own arena, pushed there by the samplers
+      p.pool_rgba[r] = reinterpret_cast<const float4*>(c.arena + L.off_lrecv_rgba[par]) + (size_t)r * c.max_partials;
+      p.pool_depth[r] = reinterpret_cast<const float*>(c.arena + L.off_lrecv_depth[par]) + (size_t)r * c.max_partials;
+    }
+    else
+    {
+      p.pool_rgba[r] = reinterpret_cast<const float4*>(c.peer[r] + L.off_lpool_rgba[par]);
+      p.pool_depth[r] = reinterpret_cast<const float*>(c.peer[r] + L.off_lpool_depth[par]);
+    }
     p.flags[r] = c.peer[r] + L.off_lflags;
   }
   p.canvas_rgba = reinterpret_cast<float4*>(c.peer[0] + L.off_canvas_rgba);

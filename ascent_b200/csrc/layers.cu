@@ -169,11 +169,24 @@ __global__ void __launch_bounds__(kTileW* kTileH, kTileH == 4 ? 7 : 4) layers_fo
     }
   }
 
-  // tiles of the box are dealt round-robin to the ranks, then to the CTAs of a rank
-  for (long long t = (long long)P.rank + (long long)blockIdx.x * P.size; t < n_tiles;
-       t += (long long)gridDim.x * P.size)
+  // tiles of the box are dealt round-robin to the ranks, then to the CTAs of a rank.  Pushed layers: by the
+  // tile's ABSOLUTE index in the frame (what the samplers used to address the owners), walking the box's tile
+  // rows and skipping the columns outside the box
+  const int tpr = (P.W + kTileW - 1) / kTileW;
+  const long long t_first = P.pushed ? (long long)bty0 * tpr : 0;
+  const long long t_end = P.pushed ? (long long)(bty0 + bth) * tpr : n_tiles;
+  long long t_begin = t_first + (long long)P.rank;
+  if (P.pushed) t_begin = t_first + (((long long)P.rank - t_first) % P.size + P.size) % P.size;
+  for (long long t = t_begin + (long long)blockIdx.x * P.size; t < t_end; t += (long long)gridDim.x * P.size)
   {
-    const int tx0 = (btx0 + (int)(t % btw)) * kTileW, ty0 = (bty0 + (int)(t / btw)) * kTileH;
+    int tile_x, tile_y;
+    if (P.pushed)
+    {
+      tile_x = (int)(t % tpr); tile_y = (int)(t / tpr);
+      if (tile_x < btx0 || tile_x >= btx0 + btw) continue; // (uniform for the CTA: no barrier is skipped by a part of it)
+    }
+    else { tile_x = btx0 + (int)(t % btw); tile_y = bty0 + (int)(t / btw); }
+    const int tx0 = tile_x * kTileW, ty0 = tile_y * kTileH;
     if (threadIdx.x == 0) s_ntile = 0;
     __syncthreads();
     // ---- layers overlapping this tile
@@ -437,6 +450,7 @@ static cudaError_t launch_layers_fold_t(const LayerFoldParams& p, int sm_count, 
   long long grid = (long long)sm_count * per_sm;
   const long long mine = (tiles + p.size - 1) / p.size;
   if (grid > mine) grid = mine > 0 ? mine : 1;
+  if (p.max_ctas > 0 && grid > p.max_ctas) grid = p.max_ctas;
   layers_fold_kernel<COMM, TH><<<(int)grid, kTileW * TH, smem, s>>>(p);
   return cudaGetLastError();
 }

@@ -889,8 +889,19 @@ trace_kernel(const __grid_constant__ TraceParams P)
       {
         const size_t e = P.layer_base + (size_t)(j - P.sy) * P.sw + (size_t)(i - P.sx);
         const bool keep = !(c3 < 0.001f);
-        P.layer_rgba[e] = keep ? make_float4(c0, c1, c2, c3) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 entry = keep ? make_float4(c0, c1, c2, c3) : make_float4(0.f, 0.f, 0.f, 0.f);
+        P.layer_rgba[e] = entry;
         P.layer_depth[e] = max_distance; // rays.MaxDistance: the exit distance (:262-263)
+        if (P.lpush_peers)
+        {
+          // N ranks: the entry also goes straight to the rank that folds this pixel's tile (posted NVLink
+          // stores, overlapped with the rest of the trace), same index, receive pool of source lpush_rank
+          const int owner = (int)(((unsigned)(j >> 3) * (unsigned)P.lpush_tpr + (unsigned)(i >> 5)) % (unsigned)P.lpush_size);
+          unsigned char* base = P.lpush_peers[owner];
+          const size_t at = (size_t)P.lpush_rank * P.lpush_stride + e;
+          reinterpret_cast<float4*>(base + P.lpush_off_rgba)[at] = entry;
+          reinterpret_cast<float*>(base + P.lpush_off_depth)[at] = max_distance;
+        }
       }
     }
     if (MODE == 1)

@@ -115,6 +115,8 @@ extern "C" vr_status vr_create(int device, vr_ctx** out)
     if (const char* e = std::getenv("VR_FOLD_LIGHT")) c.fold_light = std::atoi(e);
     if (const char* e = std::getenv("VR_FOLD_GRID")) c.fold_grid = std::atoi(e);
     if (const char* e = std::getenv("VR_FOLD_NR8")) c.fold_nr8 = std::atoi(e) != 0;
+    if (const char* e = std::getenv("VR_LAYER_PUSH")) c.layer_push = std::atoi(e) != 0;
+    if (const char* e = std::getenv("VR_EXCHANGE_MAX_CTAS")) c.exchange_max_ctas = std::max(0, std::atoi(e));
   }
   for (int k = 0; k < vr::kAuxStreams; ++k)
   {
@@ -1050,6 +1052,7 @@ extern "C" void vr_free(void* p) { std::free(p); }
 
 // ================================================================= ray layers (path B without lists)
 namespace vr { vr_status comm_bind_layers(vr_ctx* ctx); }
+namespace vr { void comm_layer_push_target(vr_ctx* ctx, vr::TraceParams& p); }
 
 static vr_status ensure_layer_pool(vr_ctx* ctx, size_t need)
 {
@@ -1099,6 +1102,7 @@ extern "C" vr_status vr_layers_begin(vr_ctx* ctx, int width, int height)
   {
     // the next buffer of the context's own ring (its last reader, the fold of three frames ago, is done:
     // comm_join_previous_exchange above)
+    ctx->layers_pushed = false;
     const int k = ctx->own_lslot = (ctx->own_lslot + 1) % vr_ctx::kOwnLayerRing;
     if (!ctx->own_ltab[k]) CK(cudaMalloc(&ctx->own_ltab[k], sizeof(LayerTable)));
     ctx->ltab = ctx->own_ltab[k];
@@ -1139,6 +1143,7 @@ extern "C" vr_status vr_trace_to_layer(vr_ctx* ctx, int block_id, const vr_camer
   p.layer_rgba = ctx->lpool_rgba;
   p.layer_depth = ctx->lpool_depth;
   p.layer_base = base;
+  comm_layer_push_target(ctx, p);
   st = stage_for_trace(ctx, block_id, p, ctx->stream, ctx->tile_counter, true);
   if (st != VR_OK) return st;
   CK(launch_trace(p, 3, ctx->sm_count, ctx->stream));
@@ -1200,6 +1205,7 @@ extern "C" vr_status vr_trace_blocks_to_layers(vr_ctx* ctx, int n_blocks, const 
     TraceParams& p = ps[k];
     p.layer_rgba = ctx->lpool_rgba;
     p.layer_depth = ctx->lpool_depth;
+    comm_layer_push_target(ctx, p);
     p.tile_counter = ctx->tile_counter + 1 + k;
     const bool staged = ctx->blocks[block_of[k]].staged_src != nullptr;
     if (staged)

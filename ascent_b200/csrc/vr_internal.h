@@ -68,6 +68,13 @@ struct TraceParams
   float4* layer_rgba;
   float* layer_depth;
   unsigned long long layer_base;
+  // pushed layers (N ranks): entry e of this rank's layer pool is ALSO stored into the receive pool
+  // [source = lpush_rank] of the rank that will fold the entry's pixel -- the owner of its 32x8 screen tile,
+  // (tile_y * lpush_tpr + tile_x) % lpush_size -- so that the fold reads local memory only (comm.cu, layers.cu)
+  unsigned char* const* lpush_peers; // device table of arena base pointers (null: no push)
+  unsigned long long lpush_off_rgba, lpush_off_depth; // byte offsets of this frame's receive pools inside an arena
+  unsigned long long lpush_stride;   // entries per source in a receive pool (= max_partials)
+  int lpush_rank, lpush_size, lpush_tpr;
   // partial emission (path B)
   vr_partial* partials;
   unsigned long long* partial_count;
@@ -119,6 +126,7 @@ struct Comm
   unsigned char* arena = nullptr;               // own arena (cudaMalloc, IPC-exported)
   std::vector<unsigned char*> peer;             // mapped arenas, peer[rank] == arena
   unsigned char** peer_dev = nullptr;           // device copy of the pointer table
+  bool local_peers = false;                     // the peers are contexts of this process (vr_comm_connect_local): no IPC mappings
   unsigned int epoch = 0;                       // image path frames composited so far
   unsigned int pepoch = 0;                      // partial path frames
   unsigned int lepoch = 0;                      // layer path frames
@@ -146,8 +154,12 @@ struct Comm
   int trace_streams = 3;                        // VR_TRACE_STREAMS=0..4: 0 keeps image-only traces on the context's stream
   // exchange kernel shape (A/B runs): 0 = all layers in registers, 256 threads (default); 1 / 2 = layers in
   // batches of four, <= 72 registers, 128 / 256 threads; fold_grid = CTAs per SM (0: 1)
-  int fold_light = 0, fold_grid = 0;
+  int fold_light = 0, fold_grid = 2;
   bool fold_nr8 = false;                        // VR_FOLD_NR8=1: instantiate the fold for 8 ranks even with fewer
+  int exchange_max_ctas = 0;                    // VR_EXCHANGE_MAX_CTAS: cap of the exchange kernels' grids (0: none).  Their
+                                                // CTAs spin on the peers' flags: several ranks sharing ONE device inside ONE
+                                                // process (tests) must all fit on it at once
+  bool layer_push = true;                       // VR_LAYER_PUSH=0: ray layers stay in their rank's arena, the fold pulls them
   bool timeline = false;                        // VR_TIMELINE=1: kernels leave globaltimer stamps in the flags
   bool frame_poisoned = false;                  // a rank-local error hit this frame: the next collective aborts
   // rank 0: "this buffer holds the cleared value outside the rectangle kept in the arena flags",
@@ -250,6 +262,7 @@ struct vr_ctx
   float* lpool_depth = nullptr;
   size_t lpool_cap = 0, lpool_used = 0;
   bool layers_in_arena = false;
+  bool layers_pushed = false;            // this frame's entries also go to the tile owners' receive pools
   // without an exchange arena the context owns a ring of three layer buffers (table + pools), like the
   // arena's: the fold of frame k runs on the exchange stream while frame k+1 is traced into the next one
   static constexpr int kOwnLayerRing = 3;
@@ -480,6 +493,9 @@ struct LayerFoldParams
   ToCanvasParams tp;
   unsigned long long timeout_ns; // bound of every cross-rank wait (0 = none)
   int light;        // 32x4 tiles / 128-thread CTAs (fit the slot of one sampler CTA) instead of 32x8 / 256
+  int max_ctas;     // cap of the grid (0: none)
+  int pushed;       // the pools are this rank's RECEIVE pools (the samplers pushed every entry to the owner of its
+                    // tile): tiles are owned by absolute index, (tile_y * tiles_per_row + tile_x) % size
 };
 cudaError_t launch_layers_fold(const LayerFoldParams& p, bool comm, int sm_count, cudaStream_t s);
 cudaError_t launch_layers_wait_done(unsigned char* flags, int size, unsigned int epoch, unsigned long long timeout_ns,
@@ -515,6 +531,7 @@ struct FoldP2PParams
   int timeline;                  // diagnostics: leave globaltimer stamps in the flags
   int light;                     // 0: fold_p2p_kernel; 1 / 2: fold_p2p_light_kernel with 128 / 256 threads
   int grid_per_sm;               // CTAs per SM of the fold (0: one)
+  int max_ctas;                  // cap of the grid (0: none)
   int force_nr8;                 // diagnostics: the 8-rank instantiation whatever the size
 };
 cudaError_t launch_fold_p2p(const FoldP2PParams& p, int sm_count, cudaStream_t s);

@@ -296,6 +296,11 @@ VR_API vr_status vr_composite_partials(vr_ctx* ctx, const vr_partial* in, size_t
 VR_API vr_status vr_comm_init(vr_ctx* ctx, int rank, int n_ranks, size_t max_pixels,
                               size_t max_partials, void* handle_out /* VR_IPC_HANDLE_BYTES */);
 VR_API vr_status vr_comm_connect(vr_ctx* ctx, const void* all_handles /* n_ranks * 64 B */);
+/* The single-process form of vr_comm_connect (SURVEY 8(b) deployment shape (i): one process, one context per
+ * GPU of the node): ctxs[r] must have been vr_comm_init'ed as rank r of n_ranks with identical sizes.  No IPC
+ * handles travel; contexts on different devices reach each other's arenas through peer access.  Afterwards
+ * every collective entry point must be issued on ALL contexts before any of them is synchronised.        */
+VR_API vr_status vr_comm_connect_local(vr_ctx* const* ctxs, int n_ranks);
 /* Path A, all ranks call collectively once per image: direct-send exchange of the quantised
  * images + visibility-ordered fold + gather to rank 0, fused in one kernel per rank (peer
  * loads of the owned tile from every rank, peer store of the folded tile into rank 0).
