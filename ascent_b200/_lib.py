@@ -36,7 +36,7 @@ SYMBOLS = [
     "vr_sample_distance", "vr_visibility_order", "vr_find_subset", "vr_synth_braid_dev",
     "vr_camera_default", "vr_camera_reset_to_bounds", "vr_camera_azimuth", "vr_camera_elevation",
     "vr_camera_zoom", "vr_camera_cinema", "vr_color_table_sample", "vr_correct_opacity", "vr_comm_timeline",
-    "vr_comm_join", "vr_comm_render_frames", "vr_comm_connect_local",
+    "vr_comm_join", "vr_comm_render_frames", "vr_comm_connect_local", "vr_field_gather_strided", "vr_field_free",
 ]
 
 
@@ -143,6 +143,8 @@ def load():
         "vr_comm_timeline": (C.c_int, [vp, C.POINTER(C.c_uint64)]),
         "vr_comm_join": (C.c_int, [vp]),
         "vr_comm_connect_local": (C.c_int, [C.POINTER(vp), C.c_int]),
+        "vr_field_gather_strided": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(vp)]),
+        "vr_field_free": (C.c_int, [vp, vp]),
         "vr_comm_render_frames": (C.c_int, [vp, C.c_int, C.POINTER(CameraStruct), C.c_int, C.c_int, C.c_int, C.c_float,
                                             C.c_float, C.c_float, C.POINTER(C.c_int), fp, vp]),
     }
@@ -244,6 +246,23 @@ class Context:
         return int(self.lib.vr_kernel_launches(self.h))
 
     # -- blocks
+    def field_gather_strided(self, src, n_values, element_stride, element_offset=0, device_ptr=None, dtype=None):
+        """vr_field_gather_strided: src = host numpy array (the whole strided buffer) or device_ptr; returns the
+        dense device pointer (int) to publish with where=VR_DEVICE and to release with field_free"""
+        out = C.c_void_p()
+        if device_ptr is not None:
+            self._ck(self.lib.vr_field_gather_strided(self.h, C.c_void_p(device_ptr), VR_DEVICE, dtype, n_values,
+                                                      element_stride, element_offset, C.byref(out)))
+        else:
+            a = np.ascontiguousarray(src)
+            dt = VR_F32 if a.dtype == np.float32 else VR_F64
+            self._ck(self.lib.vr_field_gather_strided(self.h, a.ctypes.data, VR_HOST, dt, n_values, element_stride,
+                                                      element_offset, C.byref(out)))
+        return out.value
+
+    def field_free(self, dense_ptr):
+        self._ck(self.lib.vr_field_free(self.h, C.c_void_p(dense_ptr)))
+
     def block_uniform(self, block_id, dims, origin, spacing, field, assoc=VR_POINT, device_ptr=None,
                       dtype=None, host_mapped=False, staged=False):
         """host_mapped / staged: `field` is page-locked mapped host memory (e.g. a pinned torch

@@ -85,7 +85,31 @@ __global__ void count_lines_kernel(const unsigned char* __restrict__ have, size_
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
+// dense[i] = strided[offset + i * stride]: one component of an interleaved Blueprint mcarray, or a padded array
+// (what ascent_vtkh_data_adapter.cpp:1836-1887 wraps in a vtkm::cont::ArrayHandleStride)
+template <typename T>
+__global__ void gather_strided_kernel(const T* __restrict__ src, size_t stride, size_t n, T* __restrict__ dst)
+{
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i * stride];
+}
 } // namespace
+
+cudaError_t launch_gather_strided(const void* src, int elem_bytes, size_t stride, size_t n, void* dst, int sm_count,
+                                  cudaStream_t s)
+{
+  if (n == 0) return cudaSuccess;
+  size_t grid = (size_t)sm_count * 8;
+  const size_t need = (n + 255) / 256;
+  if (grid > need) grid = need;
+  if (elem_bytes == 4)
+    gather_strided_kernel<unsigned int><<<(unsigned)grid, 256, 0, s>>>(static_cast<const unsigned int*>(src), stride, n,
+                                                                      static_cast<unsigned int*>(dst));
+  else
+    gather_strided_kernel<unsigned long long><<<(unsigned)grid, 256, 0, s>>>(static_cast<const unsigned long long*>(src),
+                                                                            stride, n, static_cast<unsigned long long*>(dst));
+  return cudaGetLastError();
+}
 
 cudaError_t launch_count_lines(const unsigned char* have, size_t n_lines, unsigned long long* out, cudaStream_t s)
 {

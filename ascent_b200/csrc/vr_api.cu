@@ -351,6 +351,56 @@ static vr_status upload_field(vr_ctx* ctx, Block& b, const void* field, int dtyp
   return VR_OK;
 }
 
+// Strided Blueprint values (ascent_vtkh_data_adapter.cpp:1836-1887: a byte stride that is a multiple of the
+// element size, handed to VTK-m as an ArrayHandleStride -- one component of an interleaved mcarray, a padded
+// array): gathered ONCE per publish into a dense device array that the block entry points adopt with
+// VR_DEVICE, so the sampler keeps its unit-stride, coalescible gathers.
+extern "C" vr_status vr_field_gather_strided(vr_ctx* ctx, const void* src, int where, int dtype, size_t n_values,
+                                             size_t element_stride, size_t element_offset, void** dense_dev_out)
+{
+  VR_ENTER_RO(ctx);
+  REQUIRE(src && dense_dev_out, "vr_field_gather_strided: NULL argument");
+  REQUIRE(dtype == VR_F32 || dtype == VR_F64, "vr_field_gather_strided: dtype must be VR_F32 or VR_F64");
+  REQUIRE(where == VR_HOST || where == VR_DEVICE, "vr_field_gather_strided: where must be VR_HOST or VR_DEVICE");
+  REQUIRE(element_stride >= 1 && n_values >= 1, "vr_field_gather_strided: stride and count must be positive");
+  CK(cudaSetDevice(ctx->device));
+  *dense_dev_out = nullptr;
+  const size_t eb = dtype == VR_F32 ? 4 : 8;
+  void* dense = nullptr;
+  CK(cudaMalloc(&dense, n_values * eb));
+  const unsigned char* from = static_cast<const unsigned char*>(src) + element_offset * eb;
+  void* span_dev = nullptr;
+  cudaError_t e = cudaSuccess;
+  if (where == VR_HOST)
+  {
+    // the whole strided span crosses PCIe once (the DMA engine has no 4-byte gather worth using)
+    const size_t span = ((n_values - 1) * element_stride + 1) * eb;
+    e = cudaMalloc(&span_dev, span);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(span_dev, from, span, cudaMemcpyHostToDevice, ctx->stream);
+    from = static_cast<const unsigned char*>(span_dev);
+  }
+  if (e == cudaSuccess) e = launch_gather_strided(from, (int)eb, element_stride, n_values, dense, ctx->sm_count, ctx->stream);
+  ctx->launches++;
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); // (the caller may reuse its array; the span is freed)
+  cudaFree(span_dev);
+  if (e != cudaSuccess)
+  {
+    cudaFree(dense);
+    return fail(ctx, VR_ERR_CUDA, "vr_field_gather_strided: %s", cudaGetErrorString(e));
+  }
+  *dense_dev_out = dense;
+  return VR_OK;
+}
+
+extern "C" vr_status vr_field_free(vr_ctx* ctx, void* dense_dev)
+{
+  VR_ENTER_RO(ctx);
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(dense_dev);
+  return VR_OK;
+}
+
 extern "C" vr_status vr_block_uniform(vr_ctx* ctx, int block_id, const int dims[3],
                                       const float origin[3], const float spacing[3],
                                       const void* field, int dtype, int assoc, int where)

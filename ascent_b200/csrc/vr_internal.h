@@ -297,6 +297,8 @@ cudaError_t launch_fetch_lines(unsigned char* want, unsigned char* have, const v
                                size_t n_lines, size_t n_bytes, bool all, unsigned long long* n_have,
                                int sm_count, cudaStream_t s);
 
+cudaError_t launch_gather_strided(const void* src, int elem_bytes, size_t stride, size_t n, void* dst, int sm_count,
+                                  cudaStream_t s);
 cudaError_t launch_count_lines(const unsigned char* have, size_t n_lines, unsigned long long* out, cudaStream_t s);
 
 // composite.cu

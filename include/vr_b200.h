@@ -114,6 +114,15 @@ VR_API vr_status vr_block_rectilinear(vr_ctx* ctx, int block_id, const int dims[
                                       const double* y, const double* z, const void* field,
                                       int dtype, int assoc, int where);
 VR_API vr_status vr_block_free(vr_ctx* ctx, int block_id);
+/* Strided values (ascent_vtkh_data_adapter.cpp:1836-1887: Blueprint arrays whose byte stride is a multiple of the
+ * element size -- one component of an interleaved mcarray, a padded array -- which the reference hands to VTK-m
+ * as an ArrayHandleStride).  dense[i] = src[element_offset + i * element_stride] is gathered once into a new
+ * dense device array (where = VR_HOST: the strided span is copied across PCIe first; VR_DEVICE: gathered in
+ * place at HBM speed), to be published with vr_block_*(..., dense, dtype, assoc, VR_DEVICE) and released with
+ * vr_field_free after the block has been freed or re-published.  The call synchronises: src may be reused.  */
+VR_API vr_status vr_field_gather_strided(vr_ctx* ctx, const void* src, int where, int dtype, size_t n_values,
+                                         size_t element_stride, size_t element_offset, void** dense_dev_out);
+VR_API vr_status vr_field_free(vr_ctx* ctx, void* dense_dev);
 /* Bytes of a VR_HOST_STAGED block fetched to the device since its last publish (0 for other kinds). Syncs. */
 VR_API vr_status vr_block_staged_bytes(vr_ctx* ctx, int block_id, size_t* bytes);
 /* coords.GetBounds(): xmin,xmax,ymin,ymax,zmin,zmax */
