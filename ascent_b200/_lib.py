@@ -36,7 +36,7 @@ SYMBOLS = [
     "vr_sample_distance", "vr_visibility_order", "vr_find_subset", "vr_synth_braid_dev",
     "vr_camera_default", "vr_camera_reset_to_bounds", "vr_camera_azimuth", "vr_camera_elevation",
     "vr_camera_zoom", "vr_camera_cinema", "vr_color_table_sample", "vr_correct_opacity", "vr_comm_timeline",
-    "vr_comm_join", "vr_comm_render_frames", "vr_comm_connect_local", "vr_field_gather_strided", "vr_field_free",
+    "vr_comm_join", "vr_comm_render_frames", "vr_comm_connect_local", "vr_field_gather_strided", "vr_field_free", "vr_radixk_schedule",
 ]
 
 
@@ -145,6 +145,8 @@ def load():
         "vr_comm_connect_local": (C.c_int, [C.POINTER(vp), C.c_int]),
         "vr_field_gather_strided": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(vp)]),
         "vr_field_free": (C.c_int, [vp, vp]),
+        "vr_radixk_schedule": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                         C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "vr_comm_render_frames": (C.c_int, [vp, C.c_int, C.POINTER(CameraStruct), C.c_int, C.c_int, C.c_int, C.c_float,
                                             C.c_float, C.c_float, C.POINTER(C.c_int), fp, vp]),
     }
@@ -199,6 +201,19 @@ def visibility_order(domain_bounds, cam):
     load().vr_visibility_order(db.ctypes.data_as(C.POINTER(C.c_double)), db.shape[0],
                                C.byref(as_camera(cam)), out.ctypes.data_as(C.POINTER(C.c_int)))
     return out
+
+
+def radixk_schedule(n_ranks, W, H):
+    """vr_radixk_schedule: {"divisions", "lo" [x starts, y starts], "seq" per block} or None where the
+    reference cannot decompose the frame."""
+    div = (C.c_int * 2)()
+    lo_x = (C.c_int * n_ranks)()
+    lo_y = (C.c_int * n_ranks)()
+    seq = (C.c_int * (n_ranks * n_ranks))()
+    if load().vr_radixk_schedule(n_ranks, W, H, div, lo_x, lo_y, seq) != 0:
+        return None
+    return {"divisions": list(div), "lo": [list(lo_x)[:div[0]], list(lo_y)[:div[1]]],
+            "seq": [list(seq[g * n_ranks:(g + 1) * n_ranks]) for g in range(n_ranks)]}
 
 
 def find_subset(cam, W, H, bounds):

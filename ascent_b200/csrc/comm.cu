@@ -27,8 +27,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "vr_internal.h"
+#include "vr_radixk.hpp"
 
 namespace vr
 {
@@ -126,10 +128,66 @@ constexpr int kChunkGroups = 256; // 4-pixel groups per ownership chunk
 // ZBUF: the opaque-surface mode of the same exchange (Compositor Z_BUFFER_SURFACE ->
 // RadixKCompositor::CompositeSurface, RadixKCompositor.cpp:35-180): the per-pixel operator is
 // ImageCompositor::ZBufferComposite (ImageCompositor.hpp:49-76) -- nearest fragment wins, fragments
-// with depth > 1 never replace -- folded over the ranks in rank order.  Select-nearest is associative
-// and commutative for distinct depths, so the radix-k tree and this direct-send fold give the same
-// image; fragments of different ranks at EXACTLY equal depth resolve to the higher rank here.
+// with depth > 1 never replace, an incoming fragment at EQUAL depth does.  Select-nearest is associative,
+// so the reference's multi-round tree (k = 8) and one round of k = N give the same image provided equal-depth
+// fragments are visited in the tree's order: zselect_group takes that order, piece by piece, from the
+// closed-form schedule of vr_radixk.hpp (pinned against the reference's own reduce_images + DIY,
+// tests/test_oracle_radixk.py).  One round is the right radix on NVSwitch: every peer at full bandwidth.
 // NR: number of ranks rounded up to a power of two (the per-layer registers are fully unrolled).
+// Four pixels (one 16-byte group, linear index 4 i .. 4 i + 3) of the radix-k z-select: the nearest fragment
+// with depth <= 1 wins; among equal depths the one the reference's tree composites LAST into the piece that
+// ends up owning the pixel (ImageCompositor.hpp:65: `front.depth < depth` keeps, so <= replaces); if no
+// fragment is <= 1 the piece owner's own pixel stays (the first of the sequence is always the owner).
+template <int NR>
+__device__ __forceinline__ void zselect_group(const FoldP2PParams& P, const uint4 (&c)[NR], const float4 (&d)[NR],
+                                              unsigned cover, size_t i, uint4& f, float4& fd)
+{
+  unsigned oc[4];
+  float od[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+  {
+    const unsigned idx = (unsigned)i * 4u + (unsigned)q;
+    const unsigned y = idx / (unsigned)P.W, x = idx - y * (unsigned)P.W;
+    int cx = 0, cy = 0;
+#pragma unroll
+    for (int s = 1; s < 16; ++s) // (unused entries are INT_MAX; equal starts = empty pieces: the last one wins)
+    {
+      if ((int)x >= P.zs.lo_x[s]) cx = s;
+      if ((int)y >= P.zs.lo_y[s]) cy = s;
+    }
+    const int g = cx + P.zs.div_x * cy;
+    int best = -1, bp = -1;
+    float bd = 0.f;
+    unsigned bc = 0u;
+#pragma unroll
+    for (int l = 0; l < NR; ++l)
+      if (l < P.size && ((cover >> l) & 1u))
+      {
+        const float dl = (&d[l].x)[q];
+        if (!(dl > 1.f))
+        {
+          const int p = P.zs.pos[g][l];
+          if (best < 0 || dl < bd || (dl == bd && p > bp))
+          {
+            best = l; bd = dl; bp = p; bc = (&c[l].x)[q];
+          }
+        }
+      }
+    if (best < 0)
+    {
+      bc = 0u; bd = 1.001f; // (outside its rectangle a layer is colour 0, depth 1.001)
+#pragma unroll
+      for (int l = 0; l < NR; ++l)
+        if (l == g && ((cover >> l) & 1u)) { bc = (&c[l].x)[q]; bd = (&d[l].x)[q]; }
+    }
+    oc[q] = bc;
+    od[q] = bd;
+  }
+  f = make_uint4(oc[0], oc[1], oc[2], oc[3]);
+  fd = make_float4(od[0], od[1], od[2], od[3]);
+}
+
 template <int NR, bool TO_CANVAS, bool ZBUF>
 __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ FoldP2PParams P)
 {
@@ -287,22 +345,11 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
       }
     uint4 f = c[0];
     float4 fd = d[0];
+    if (ZBUF) zselect_group<NR>(P, c, d, cover, i, f, fd);
 #pragma unroll
     for (int l = 1; l < NR; ++l)
-      if (l < P.size)
+      if (!ZBUF && l < P.size)
       {
-        if (ZBUF)
-        {
-          // outside its rectangle a layer is depth 1.001 (> 1): never selected
-          if (cover & (1u << l))
-          {
-            if (!(d[l].x > 1.f || fd.x < d[l].x)) { fd.x = d[l].x; f.x = c[l].x; }
-            if (!(d[l].y > 1.f || fd.y < d[l].y)) { fd.y = d[l].y; f.y = c[l].y; }
-            if (!(d[l].z > 1.f || fd.z < d[l].z)) { fd.z = d[l].z; f.z = c[l].z; }
-            if (!(d[l].w > 1.f || fd.w < d[l].w)) { fd.w = d[l].w; f.w = c[l].w; }
-          }
-          continue;
-        }
         if (cover & (1u << l))
         {
           f.x = blend_u8x4(f.x, c[l].x); f.y = blend_u8x4(f.y, c[l].y);
@@ -370,7 +417,7 @@ __global__ void __launch_bounds__(256) fold_p2p_kernel(const __grid_constant__ F
 // which only happens at the very end of a trace; this one is placed as soon as ANY sampler CTA of any launch
 // retires.  The layers are folded in batches of four (8 + 8 registers each in flight) instead of all at once.
 // Same ownership, same fold order and operator as fold_p2p_kernel: the same bits.
-template <int kLightThreads, bool TO_CANVAS, bool ZBUF>
+template <int kLightThreads, bool TO_CANVAS>
 __global__ void __launch_bounds__(kLightThreads, kLightThreads == 128 ? 7 : 3) fold_p2p_light_kernel(const __grid_constant__ FoldP2PParams P)
 {
   Flags* my_flags = reinterpret_cast<Flags*>(P.peers[P.rank] + P.off_flags);
@@ -520,17 +567,6 @@ __global__ void __launch_bounds__(kLightThreads, kLightThreads == 128 ? 7 : 3) f
           const int l = l0 + u;
           if (l >= size) break;
           if (l == 0) { f = c[0]; fd = d[0]; continue; }
-          if (ZBUF)
-          {
-            if (cover & (1u << l))
-            {
-              if (!(d[u].x > 1.f || fd.x < d[u].x)) { fd.x = d[u].x; f.x = c[u].x; }
-              if (!(d[u].y > 1.f || fd.y < d[u].y)) { fd.y = d[u].y; f.y = c[u].y; }
-              if (!(d[u].z > 1.f || fd.z < d[u].z)) { fd.z = d[u].z; f.z = c[u].z; }
-              if (!(d[u].w > 1.f || fd.w < d[u].w)) { fd.w = d[u].w; f.w = c[u].w; }
-            }
-            continue;
-          }
           if (cover & (1u << l))
           {
             f.x = blend_u8x4(f.x, c[u].x); f.y = blend_u8x4(f.y, c[u].y);
@@ -1018,7 +1054,7 @@ static cudaError_t launch_fold_p2p_nr(const FoldP2PParams& p, int sm_count, cuda
 
 cudaError_t launch_fold_p2p(const FoldP2PParams& p, int sm_count, cudaStream_t s)
 {
-  if (p.light)
+  if (p.light && !p.zbuffer) // (the z-select lives in fold_p2p_kernel only)
   {
     const size_t n4 = (p.n_pixels + 3) / 4;
     const size_t n_chunks = (n4 + kChunkGroups - 1) / kChunkGroups;
@@ -1030,9 +1066,8 @@ cudaError_t launch_fold_p2p(const FoldP2PParams& p, int sm_count, cudaStream_t s
       if (p.light == 1) k128<<<(unsigned)grid, 128, 0, s>>>(p);
       else k256<<<(unsigned)grid, 256, 0, s>>>(p);
     };
-    if (p.zbuffer) go(fold_p2p_light_kernel<128, false, true>, fold_p2p_light_kernel<256, false, true>);
-    else if (p.canvas_rgba) go(fold_p2p_light_kernel<128, true, false>, fold_p2p_light_kernel<256, true, false>);
-    else go(fold_p2p_light_kernel<128, false, false>, fold_p2p_light_kernel<256, false, false>);
+    if (p.canvas_rgba) go(fold_p2p_light_kernel<128, true>, fold_p2p_light_kernel<256, true>);
+    else go(fold_p2p_light_kernel<128, false>, fold_p2p_light_kernel<256, false>);
     return cudaGetLastError();
   }
   if (p.force_nr8 && p.size <= 8) return launch_fold_p2p_nr<8>(p, sm_count, s);
@@ -1040,6 +1075,35 @@ cudaError_t launch_fold_p2p(const FoldP2PParams& p, int sm_count, cudaStream_t s
   if (p.size <= 4) return launch_fold_p2p_nr<4>(p, sm_count, s);
   if (p.size <= 8) return launch_fold_p2p_nr<8>(p, sm_count, s);
   return launch_fold_p2p_nr<16>(p, sm_count, s);
+}
+
+void preload_comm_kernels()
+{
+  auto folds = [](auto nr) {
+    constexpr int NR = decltype(nr)::value;
+    preload_kernel(fold_p2p_kernel<NR, false, false>);
+    preload_kernel(fold_p2p_kernel<NR, true, false>);
+    preload_kernel(fold_p2p_kernel<NR, false, true>);
+    preload_kernel(merge_fold_p2p_kernel<NR, true>);
+    preload_kernel(merge_fold_p2p_kernel<NR, false>);
+  };
+  folds(std::integral_constant<int, 2>());
+  folds(std::integral_constant<int, 4>());
+  folds(std::integral_constant<int, 8>());
+  folds(std::integral_constant<int, 16>());
+  preload_kernel(merge_fold_p2p_kernel<1, true>);
+  preload_kernel(merge_fold_p2p_kernel<1, false>);
+  preload_kernel(fold_p2p_light_kernel<128, true>);
+  preload_kernel(fold_p2p_light_kernel<128, false>);
+  preload_kernel(fold_p2p_light_kernel<256, true>);
+  preload_kernel(fold_p2p_light_kernel<256, false>);
+  preload_kernel(covered_to_canvas_kernel<128>);
+  preload_kernel(covered_to_canvas_kernel<256>);
+  preload_kernel(wait_done_kernel);
+  preload_kernel(abort_announce_kernel);
+  preload_kernel(sync_post_kernel);
+  preload_kernel(sync_pull_kernel);
+  preload_kernel(publish_minmax_kernel);
 }
 
 void comm_destroy(vr_ctx* ctx)
@@ -1403,6 +1467,11 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
   Comm& c = ctx->comm;
   if (!c.on || !c.peer_dev) return cfail(ctx, VR_ERR_STATE, "vr_comm_composite_images: not connected", cudaSuccess);
   if (!vis_order || ctx->W <= 0) return cfail(ctx, VR_ERR_INVALID, "vr_comm_composite_images: no image / NULL order", cudaSuccess);
+  radixk::Schedule zsched;
+  if (zbuffer && !radixk::make_schedule(c.size, ctx->W, ctx->H, zsched))
+    // (every rank computes the same schedule from the same n, W, H: all fail alike, nobody waits.  The
+    // reference throws "Unable to decompose domain into N blocks" from RegularDecomposer::fill_divisions.)
+    return cfail(ctx, VR_ERR_INVALID, "vr_comm_composite_zbuffer: unable to decompose the frame into one block per rank", cudaSuccess);
   cudaSetDevice(ctx->device);
   const Layout L = make_layout(c.max_pixels, c.max_partials, c.rank == 0, c.size);
   c.epoch += 1; // the image was quantised into parity (epoch+1)&1 by vr_image_from_canvas
@@ -1433,6 +1502,12 @@ static vr_status comm_composite_images_impl(vr_ctx* ctx, const int* vis_order, b
   }
   for (int i = 0; i < c.size; ++i) p.order[i] = idx[i];
   p.zbuffer = zbuffer ? 1 : 0;
+  if (zbuffer)
+  {
+    for (int k = 0; k < 16; ++k) { p.zs.lo_x[k] = zsched.lo[0][k]; p.zs.lo_y[k] = zsched.lo[1][k]; }
+    p.zs.div_x = zsched.divisions[0];
+    std::memcpy(p.zs.pos, zsched.pos, sizeof(p.zs.pos));
+  }
   p.timeout_ns = c.timeout_ns;
   p.timeline = c.timeline ? 1 : 0;
   p.pushed = ctx->img_pushed ? 1 : 0;

@@ -580,6 +580,28 @@ __global__ void partials_to_canvas_kernel(const vr_partial* __restrict__ p,
 } // namespace
 
 // ================================================================= launchers
+void preload_composite_kernels()
+{
+  preload_kernel(canvas_clear_kernel);
+  preload_kernel(quantize_kernel);
+  preload_kernel(fold_images_kernel);
+  preload_kernel(fold_images_scalar_kernel);
+  preload_kernel(zbuffer_kernel);
+  preload_kernel(blend_background_kernel);
+  preload_kernel(encode_rgba8_kernel<true>);
+  preload_kernel(encode_rgba8_kernel<false>);
+  preload_kernel(image_to_canvas_kernel);
+  preload_kernel(partial_init_kernel);
+  preload_kernel(px_count_kernel);
+  preload_kernel(scan_reduce_kernel);
+  preload_kernel(scan_blocks_kernel);
+  preload_kernel(scan_apply_kernel);
+  preload_kernel(px_scatter_kernel);
+  preload_kernel(px_fold_kernel);
+  preload_kernel(px_sort_emit_kernel);
+  preload_kernel(partials_to_canvas_kernel);
+}
+
 cudaError_t launch_canvas_clear(float4* rgba, float* depth, size_t n, cudaStream_t s)
 {
   canvas_clear_kernel<<<grid_for(n, kT), kT, 0, s>>>(rgba, depth, n);

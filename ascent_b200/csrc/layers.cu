@@ -455,6 +455,17 @@ static cudaError_t launch_layers_fold_t(const LayerFoldParams& p, int sm_count, 
   return cudaGetLastError();
 }
 
+void preload_layers_kernels()
+{
+  preload_kernel(layers_fold_kernel<true, 4>);
+  preload_kernel(layers_fold_kernel<false, 4>);
+  preload_kernel(layers_fold_kernel<true, 8>);
+  preload_kernel(layers_fold_kernel<false, 8>);
+  preload_kernel(layers_wait_done_kernel);
+  preload_kernel(layers_abort_kernel);
+  preload_kernel(layers_to_partials_kernel);
+}
+
 cudaError_t launch_layers_fold(const LayerFoldParams& p, bool comm, int sm_count, cudaStream_t s)
 {
   if (p.light) return comm ? launch_layers_fold_t<true, 4>(p, sm_count, s) : launch_layers_fold_t<false, 4>(p, sm_count, s);

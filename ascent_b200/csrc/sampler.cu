@@ -27,6 +27,8 @@
 //    default sampling touches ~1/4 of the block: DRAM runs at <10 % of peak), so doubling the loads
 //    in flight per warp is what shortens a ray;
 //  * the 16 KiB transfer function sits in shared memory (one LDS.128 per sample).
+#include <cstring>
+
 #include "vr_internal.h"
 
 namespace vr
@@ -942,11 +944,13 @@ trace_kernel(const __grid_constant__ TraceParams P)
 
 constexpr size_t kBrickSmem = (size_t)(kThreads / 32) * 2 * kBrickFloats * 4 + (size_t)(kThreads / 32) * 2 * 8;
 
+// grid < 0: load the kernel this dispatch would launch, launch nothing (preload_trace_kernels)
 template <int KIND, typename FT, int ASSOC, typename IDX, int MARCH>
 cudaError_t launch_march(const TraceParams& p, int mode, int grid, cudaStream_t s)
 {
   const size_t smem = MARCH == 2 ? kBrickSmem : 0;
   auto go = [&](auto kernel) {
+    if (grid < 0) { preload_kernel(kernel); return; }
     // static (16 KiB table) + dynamic (bricks) shared memory exceed the 48 KiB a kernel gets by default;
     // the opt-in is per device, so it is (cheaply) repeated per launch
     if (MARCH == 2) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBrickSmem);
@@ -966,7 +970,8 @@ cudaError_t launch_mode(const TraceParams& p, int mode, int grid, cudaStream_t s
 {
   if (mode == 4) // the demand-staging pre-pass visits cells only: general march
   {
-    trace_kernel<KIND, FT, ASSOC, 4, IDX, 0><<<grid, kThreads, 0, s>>>(p);
+    if (grid < 0) preload_kernel(trace_kernel<KIND, FT, ASSOC, 4, IDX, 0>);
+    else trace_kernel<KIND, FT, ASSOC, 4, IDX, 0><<<grid, kThreads, 0, s>>>(p);
     return cudaGetLastError();
   }
   if (KIND == 0 && ASSOC == VR_POINT)
@@ -999,6 +1004,21 @@ cudaError_t launch_dtype(const TraceParams& p, int mode, int grid, cudaStream_t 
 }
 
 } // namespace
+
+void preload_trace_kernels(const BlockDev& blk)
+{
+  TraceParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.blk = blk;
+  for (int march = 0; march < 3; ++march)
+    for (int mode = 0; mode <= 5; ++mode)
+    {
+      p.march = march;
+      if (blk.kind == 0) launch_dtype<0>(p, mode, -1, nullptr);
+      else launch_dtype<1>(p, mode, -1, nullptr);
+    }
+  cudaGetLastError();
+}
 
 cudaError_t launch_trace(const TraceParams& p, int mode_partials, int sm_count, cudaStream_t s,
                          bool zero_counter)

@@ -95,6 +95,15 @@ __global__ void gather_strided_kernel(const T* __restrict__ src, size_t stride, 
 }
 } // namespace
 
+void preload_stage_kernels()
+{
+  preload_kernel(fetch_lines_kernel<true>);
+  preload_kernel(fetch_lines_kernel<false>);
+  preload_kernel(count_lines_kernel);
+  preload_kernel(gather_strided_kernel<unsigned int>);
+  preload_kernel(gather_strided_kernel<unsigned long long>);
+}
+
 cudaError_t launch_gather_strided(const void* src, int elem_bytes, size_t stride, size_t n, void* dst, int sm_count,
                                   cudaStream_t s)
 {

@@ -14,6 +14,7 @@
 #include "vr_color_table.hpp"
 #include "vr_host_math.hpp"
 #include "vr_internal.h"
+#include "vr_radixk.hpp"
 
 using namespace vr;
 
@@ -85,6 +86,11 @@ extern "C" vr_status vr_create(int device, vr_ctx** out)
     return fail(nullptr, VR_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
   }
   ctx->stream = ctx->own_stream;
+  preload_comm_kernels();
+  preload_layers_kernels();
+  preload_composite_kernels();
+  preload_stage_kernels();
+  cudaGetLastError();
   if (const char* e = std::getenv("VR_CTAS_PER_SM")) ctx->ctas_per_sm = std::atoi(e); // tuning knob
   if (const char* e = std::getenv("VR_TILE_ORDER")) ctx->tile_order = std::atoi(e);
   if (const char* e = std::getenv("VR_COUNT_SAMPLES")) ctx->count_samples = std::atoi(e) != 0;
@@ -401,6 +407,17 @@ extern "C" vr_status vr_field_free(vr_ctx* ctx, void* dense_dev)
   return VR_OK;
 }
 
+// first publish of a (grid kind, scalar type, association, index width) on this context: load the sampler
+// kernels such a block can run (vr_internal.h, "kernel preloading")
+static void preload_block_kernels(vr_ctx* ctx, const BlockDev& d)
+{
+  const long long n = (long long)d.dims[0] * d.dims[1] * d.dims[2];
+  const unsigned bit = 1u << ((d.kind & 1) | (d.dtype & 1) << 1 | (d.assoc & 1) << 2 | (n >= (1ll << 31) ? 8 : 0));
+  if (ctx->trace_preloaded & bit) return;
+  preload_trace_kernels(d);
+  ctx->trace_preloaded |= bit;
+}
+
 extern "C" vr_status vr_block_uniform(vr_ctx* ctx, int block_id, const int dims[3],
                                       const float origin[3], const float spacing[3],
                                       const void* field, int dtype, int assoc, int where)
@@ -448,6 +465,7 @@ extern "C" vr_status vr_block_uniform(vr_ctx* ctx, int block_id, const int dims[
     free_block(*old);
   }
   ctx->blocks[block_id] = b;
+  preload_block_kernels(ctx, b.dev);
   return VR_OK;
 }
 
@@ -496,6 +514,7 @@ extern "C" vr_status vr_block_rectilinear(vr_ctx* ctx, int block_id, const int d
     free_block(*old);
   }
   ctx->blocks[block_id] = b;
+  preload_block_kernels(ctx, b.dev);
   return VR_OK;
 }
 
@@ -1709,6 +1728,21 @@ extern "C" void vr_visibility_order(const double* domain_bounds, int n, const vr
   }
   std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return depth[a] < depth[b]; });
   for (int i = 0; i < n; ++i) order_out[idx[i]] = i;
+}
+
+extern "C" int vr_radixk_schedule(int n_ranks, int width, int height, int divisions[2], int* lo_x, int* lo_y, int* seq)
+{
+  radixk::Schedule s;
+  if (!radixk::make_schedule(n_ranks, width, height, s)) return -1;
+  if (divisions) { divisions[0] = s.divisions[0]; divisions[1] = s.divisions[1]; }
+  for (int i = 0; i < n_ranks; ++i)
+  {
+    if (lo_x) lo_x[i] = s.lo[0][i];
+    if (lo_y) lo_y[i] = s.lo[1][i];
+    if (seq)
+      for (int k = 0; k < n_ranks; ++k) seq[i * n_ranks + k] = s.seq[i][k];
+  }
+  return 0;
 }
 
 extern "C" void vr_find_subset(const vr_camera* cam, int width, int height, const double bounds[6],

@@ -204,6 +204,7 @@ struct vr_ctx
   cudaStream_t stream = nullptr;
   std::string err;
   uint64_t launches = 0;
+  unsigned trace_preloaded = 0; // bit (kind | dtype << 1 | assoc << 2 | 64-bit index << 3): sampler variants loaded
   int sm_count = 148;
   int ctas_per_sm = 0;        // trace kernel residency (0 = built-in default)
   int tile_order = 0;         // VR_TILE_ORDER=1: tiles in row-major order instead of centre-out
@@ -535,6 +536,33 @@ struct FoldP2PParams
   int grid_per_sm;               // CTAs per SM of the fold (0: one)
   int max_ctas;                  // cap of the grid (0: none)
   int force_nr8;                 // diagnostics: the 8-rank instantiation whatever the size
+  // zbuffer: the order in which the reference's radix-k tree visits the ranks' fragments, per piece of the
+  // frame (vr_radixk.hpp): piece column / row starts, pieces per row, and pos[g][rank] = position of the
+  // rank in the sequence of the piece gid g ends up owning (ties at equal depth go to the LAST position)
+  struct ZSelect
+  {
+    int lo_x[16], lo_y[16];
+    int div_x;
+    unsigned char pos[16][16];
+  } zs;
 };
 cudaError_t launch_fold_p2p(const FoldP2PParams& p, int sm_count, cudaStream_t s);
+
+// ---- kernel preloading.  CUDA loads a kernel lazily at its first launch, and that load may have to
+// synchronise the context -- which never returns while an exchange kernel of this context is resident and
+// spinning on a peer whose own kernel the SAME host thread has not launched yet (one thread driving several
+// contexts: vr_comm_connect_local; documented hazard of CUDA_MODULE_LOADING=LAZY).  vr_create therefore loads
+// every kernel of the exchange, fold, composite and staging units up front, and a block's publish loads the
+// sampler variants that block can run (cudaFuncGetAttributes forces the load; later calls are no-ops).
+template <typename K>
+inline void preload_kernel(K k)
+{
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(k));
+}
+void preload_comm_kernels();
+void preload_layers_kernels();
+void preload_composite_kernels();
+void preload_stage_kernels();
+void preload_trace_kernels(const BlockDev& blk);
 } // namespace vr

@@ -340,11 +340,21 @@ VR_API vr_status vr_comm_render_frames(vr_ctx* ctx, int block_id, const vr_camer
                                        const int* vis_orders, const float* bg_rgba, uint8_t* frames_rgba8_host);
 /* Opaque surfaces, all ranks collectively (Compositor Z_BUFFER_SURFACE -> RadixKCompositor::
  * CompositeSurface, RadixKCompositor.cpp:35-180): the same fused exchange with
- * ImageCompositor::ZBufferComposite (ImageCompositor.hpp:49-76) as the per-pixel operator, folded in
- * rank order; the nearest fragment's RGBA8 + depth land on rank 0 (vr_image_result_*).  Identical to
- * the reference's radix-k tree except for fragments of DIFFERENT ranks at exactly equal depth (here:
- * the higher rank wins).                                                                         */
+ * ImageCompositor::ZBufferComposite (ImageCompositor.hpp:49-76) as the per-pixel operator; the nearest
+ * fragment's RGBA8 + depth land on rank 0 (vr_image_result_*).  One round of radix k = N over NVLink
+ * instead of the reference's rounds of k <= 8, with equal-depth fragments of different ranks resolved
+ * exactly as the reference's tree resolves them (the piece-by-piece visiting order of vr_radixk_schedule):
+ * the same image for every input with depths >= 0.  Fails with VR_ERR_INVALID where the reference throws
+ * "Unable to decompose domain" (frame too small for one block per rank).                          */
 VR_API vr_status vr_comm_composite_zbuffer(vr_ctx* ctx);
+/* The schedule behind it, host only (no context, no GPU): DIY's RegularDecomposer + RegularSwapPartners(k = 8,
+ * distance halving) as RadixKCompositor::CompositeImpl (RadixKCompositor.cpp:138-180) configures them, and
+ * reduce_images' balanced splits (:66-92), in closed form.  divisions[2]: blocks along x, y;  lo_x[n], lo_y[n]:
+ * first 0-based pixel of each block column / row (INT_MAX beyond divisions[d]; the pixel a piece shares with its
+ * lower neighbour counts for the higher gid, which CollectImages pastes later);  seq[n*n]: seq[g*n + i] = the
+ * i-th rank whose fragment is z-composited for the pixels block g = cx + divisions[0] * cy ends up owning.
+ * Returns 0, or -1 if the frame cannot be decomposed into n_ranks blocks (n_ranks <= 16).             */
+VR_API int vr_radixk_schedule(int n_ranks, int width, int height, int divisions[2], int* lo_x, int* lo_y, int* seq);
 /* Scene::SynchDepths (Scene.cpp:249-264), all ranks collectively: rank 0's canvas depth replaces every
  * other rank's canvas depth (NVLink pull), so the volume pass stops at the composited surfaces.   */
 VR_API vr_status vr_comm_sync_depths(vr_ctx* ctx);

@@ -374,6 +374,273 @@ def ref_composite_partials(partial_lists):
     return out[:n].copy()
 
 
+# ----------------------------------------------------------------------------- radix-k surface compositing (C4)
+# Restatement of RadixKCompositor::CompositeImpl (src/libs/vtkh/compositing/RadixKCompositor.cpp:35-180; the
+# apcomp copy is textually the same) and of the vendored DIY pieces it drives
+# (src/libs/vtkh/compositing/internal/diy/include/diy: decomposition.hpp fill_divisions/factor,
+# partners/common.hpp factor/fill/fill_steps with contiguous = false, reduce.hpp, and CollectImages in
+# vtkh_diy_collect.hpp).  PINNED against the reference's own code run in one process
+# (oracle/_ref/libradixk_ref.so, tests/test_oracle_radixk.py).
+RADIXK_MAGIC_K = 8  # RadixKCompositor.cpp:144
+
+
+def _diy_factor_ascending(n):
+    """RegularDecomposer::factor (decomposition.hpp:596-611): prime factors, smallest first."""
+    f = []
+    while n != 1:
+        for i in range(2, n + 1):
+            if n % i == 0:
+                f.append(i)
+                n //= i
+                break
+    return f
+
+
+def radixk_divisions(n, W, H):
+    """RegularDecomposer<DiscreteBounds>(2, [1..W]x[1..H], n).fill_divisions (decomposition.hpp:514-594):
+    the largest remaining prime factor always splits the dimension whose blocks are currently largest
+    (ties: fewer blocks so far, then the lower dimension)."""
+    dmin, dmax = [1, 1], [W, H]
+    divs = [{"dim": d, "nb": 1, "b_size": dmax[d] - dmin[d]} for d in range(2)]
+    for f in reversed(_diy_factor_ascending(n)):
+        divs.sort(key=lambda v: (-v["b_size"], v["nb"], v["dim"]))
+        v = divs[0]
+        nn = v["nb"] * f
+        lo = dmin[v["dim"]]
+        hi = dmax[v["dim"]] if nn == 1 else lo + (dmax[v["dim"]] - lo + 1) // nn - 1
+        if hi < lo:
+            raise RuntimeError("Unable to decompose domain into %d blocks" % n)
+        v["nb"], v["b_size"] = nn, hi - lo
+    out = [0, 0]
+    for v in divs:
+        out[v["dim"]] = v["nb"]
+    return out
+
+
+def _diy_factor_k(k, tot):
+    """RegularPartners::factor(k, tot_b, kv) (partners/common.hpp:170-201)."""
+    kv, rem = [], tot
+    while rem > 1:
+        if rem % k == 0:
+            kv.append(k)
+            rem //= k
+        else:
+            for j in range(k - 1, 1, -1):
+                if rem % j == 0:
+                    kv.append(j)
+                    rem //= j
+                    break
+            else:
+                kv.append(rem)
+                rem = 1
+    return kv
+
+
+def radixk_rounds(divisions, k=RADIXK_MAGIC_K):
+    """[(dim, group size, step)] per round: per-dimension factorisations interleaved dimension by dimension
+    (partners/common.hpp:139-166), steps for contiguous = false, i.e. distance halving (:75-83)."""
+    per_dim = [_diy_factor_k(k, d) for d in divisions]
+    kvs, at = [], [0] * len(divisions)
+    while True:
+        changed = False
+        for d in range(len(divisions)):
+            if at[d] < len(per_dim[d]):
+                kvs.append((d, per_dim[d][at[d]]))
+                at[d] += 1
+                changed = True
+        if not changed:
+            break
+    cur = list(divisions)
+    rounds = []
+    for d, size in kvs:
+        cur[d] //= size
+        rounds.append((d, size, cur[d]))
+    return rounds
+
+
+def _gid_to_coords(gid, divisions):
+    c = []
+    for d in divisions:
+        c.append(gid % d)
+        gid //= d
+    return c
+
+
+def _coords_to_gid(c, divisions):
+    gid = 0
+    for i in range(len(c) - 1, -1, -1):
+        gid = gid * divisions[i] + c[i]
+    return gid
+
+
+def radixk_group(gid, rnd, divisions):
+    """RegularPartners::fill (partners/common.hpp:86-113): the gids of `gid`'s group in a round, by
+    ascending position; this is the out_link order of that round and the in_link order of the next."""
+    d, size, step = rnd
+    c = _gid_to_coords(gid, divisions)
+    pos = c[d] // step % size
+    first = c[d] - pos * step
+    out = []
+    for j in range(size):
+        cc = list(c)
+        cc[d] = first + j * step
+        out.append(_coords_to_gid(cc, divisions))
+    return out, pos
+
+
+def _radixk_split(lo, hi, size):
+    """reduce_images' balanced ranges (RadixKCompositor.cpp:66-92) of the INCLUSIVE pixel interval [lo, hi]:
+    range_length = hi - lo (not + 1), so neighbouring pieces share their boundary pixel."""
+    length = hi - lo
+    base, rem = length // size, length % size
+    out, m = [], lo
+    for i in range(size):
+        b = base + (1 if i < rem else 0)
+        out.append((m, m + b))
+        m += b
+    return out
+
+
+def radixk_simulate(rgba_u8, depth, W, H):
+    """The literal algorithm: every block's image is split, swapped and z-composited round by round
+    (reduce_images), then block 0 pastes every block's final piece into the full frame in gid order
+    (CollectImages: its own piece first, then gids 1..n-1; later pastes overwrite the shared boundary pixels).
+    rgba_u8 [n, H*W, 4] uint8, depth [n, H*W] f32 (row 0 = bounds y = 1).  Returns (rgba [H*W,4], depth [H*W])."""
+    n = rgba_u8.shape[0]
+    divisions = radixk_divisions(n, W, H)
+    rounds = radixk_rounds(divisions)
+    # a block's image: bounds (x0, y0, x1, y1) inclusive, 1-based + arrays over that rectangle
+    imgs = [{"b": (1, 1, W, H), "c": rgba_u8[g].reshape(H, W, 4).copy(), "d": depth[g].reshape(H, W).copy()}
+            for g in range(n)]
+
+    def subset(im, b):
+        x0, y0, x1, y1 = b
+        ox, oy = im["b"][0], im["b"][1]
+        return {"b": b, "c": im["c"][y0 - oy:y1 - oy + 1, x0 - ox:x1 - ox + 1].copy(),
+                "d": im["d"][y0 - oy:y1 - oy + 1, x0 - ox:x1 - ox + 1].copy()}
+
+    def zcomp(front, inc):  # ImageCompositor::ZBufferComposite (ImageCompositor.hpp:49-76)
+        assert front["b"] == inc["b"]
+        take = ~((inc["d"] > 1.0) | (front["d"] < inc["d"]))
+        front["d"][take] = np.abs(inc["d"][take])
+        front["c"][take] = inc["c"][take]
+
+    inbox = [dict() for _ in range(n)]
+    for r, rnd in enumerate(rounds + [None]):
+        if r > 0:
+            for g in range(n):
+                group, _ = radixk_group(g, rounds[r - 1], divisions)
+                for q in group:  # in_link order
+                    if q != g:
+                        zcomp(imgs[g], inbox[g][q])
+            inbox = [dict() for _ in range(n)]
+        if rnd is None:
+            break
+        d = rnd[0]
+        nxt = [None] * n
+        for g in range(n):
+            group, _ = radixk_group(g, rnd, divisions)
+            x0, y0, x1, y1 = imgs[g]["b"]
+            pieces = _radixk_split(x0 if d == 0 else y0, x1 if d == 0 else y1, len(group))
+            for i, q in enumerate(group):
+                b = (pieces[i][0], y0, pieces[i][1], y1) if d == 0 else (x0, pieces[i][0], x1, pieces[i][1])
+                piece = subset(imgs[g], b)
+                if q == g:
+                    nxt[g] = piece
+                else:
+                    inbox[q][g] = piece
+        imgs = nxt
+    out_c = np.zeros((H, W, 4), np.uint8)
+    out_d = np.zeros((H, W), np.float32)
+    for g in range(n):
+        x0, y0, x1, y1 = imgs[g]["b"]
+        out_c[y0 - 1:y1, x0 - 1:x1] = imgs[g]["c"]
+        out_d[y0 - 1:y1, x0 - 1:x1] = imgs[g]["d"]
+    return out_c.reshape(-1, 4), out_d.reshape(-1)
+
+
+def radixk_schedule(n, W, H):
+    """Closed form of the above, the shape the GPU kernel consumes.  Returns
+      divisions [dx, dy];
+      lo[d]  : for each coordinate c along dimension d, the first 0-based pixel of block column/row c's
+               EFFECTIVE span (a boundary pixel shared by two pieces ends up with the higher gid's value,
+               because CollectImages pastes in gid order);
+      seq[g] : the order in which the ranks' fragments are z-composited for the pixels gid g ends up owning:
+               Seq_0(b) = [b]; Seq_{r+1}(g) = Seq_r(g) ++ Seq_r(q) for q in group_r(g) by position, q != g.
+    The composited pixel is the LAST fragment of seq with the minimum depth among those with depth <= 1
+    (ImageCompositor.hpp:65: an incoming fragment replaces on <=), or seq[0]'s pixel if none is <= 1."""
+    divisions = radixk_divisions(n, W, H)
+    rounds = radixk_rounds(divisions)
+    seq = [[g] for g in range(n)]
+    for rnd in rounds:
+        nxt = []
+        for g in range(n):
+            group, _ = radixk_group(g, rnd, divisions)
+            s = list(seq[g])
+            for q in group:
+                if q != g:
+                    s += seq[q]
+            nxt.append(s)
+        seq = nxt
+    lo = []
+    for d in range(2):
+        spans = [(1, W if d == 0 else H)]
+        for rd, size, _ in rounds:
+            if rd == d:
+                spans = [p for s in spans for p in _radixk_split(s[0], s[1], size)]
+        # piece 0 starts at pixel 0; every other piece effectively starts AT the boundary pixel it shares with
+        # its lower neighbour (1-based s[0] -> 0-based s[0] - 1): the higher gid is pasted later
+        lo.append([0] + [s[0] - 1 for s in spans[1:]])
+    return {"divisions": divisions, "rounds": rounds, "lo": lo, "seq": seq}
+
+
+def radixk_zbuffer(rgba_u8, depth, W, H):
+    """Z-composite n full-frame images through radixk_schedule (per pixel; the form the kernel implements)."""
+    n = rgba_u8.shape[0]
+    s = radixk_schedule(n, W, H)
+    cx = np.searchsorted(np.asarray(s["lo"][0]), np.arange(W), side="right") - 1
+    cy = np.searchsorted(np.asarray(s["lo"][1]), np.arange(H), side="right") - 1
+    gid = (cx[None, :] + s["divisions"][0] * cy[:, None]).reshape(-1)
+    out_c = np.zeros((H * W, 4), np.uint8)
+    out_d = np.zeros(H * W, np.float32)
+    for g in range(n):
+        px = np.nonzero(gid == g)[0]
+        if px.size == 0:
+            continue
+        order = s["seq"][g]
+        fc = rgba_u8[order[0]][px].copy()
+        fd = depth[order[0]][px].copy()
+        for r in order[1:]:
+            d = depth[r][px]
+            take = ~((d > 1.0) | (fd < d))
+            fd[take] = np.abs(d[take])
+            fc[take] = rgba_u8[r][px][take]
+        out_c[px], out_d[px] = fc, fd
+    return out_c, out_d
+
+
+_radixk_ref_path = os.path.join(_HERE, "_ref", "libradixk_ref.so")
+radixk_ref = C.CDLL(_radixk_ref_path) if os.path.exists(_radixk_ref_path) else None
+
+
+def ref_radixk_zbuffer(rgba_u8, depth, W, H):
+    """The reference's own reduce_images + DIY, n blocks in one process (oracle/radixk_ref_harness.cpp)."""
+    assert radixk_ref is not None
+    c = np.ascontiguousarray(rgba_u8, np.uint8)
+    d = np.ascontiguousarray(depth, np.float32)
+    n = c.shape[0]
+    out = np.zeros((H * W, 4), np.uint8)
+    od = np.zeros(H * W, np.float32)
+    info = (C.c_int * 64)()
+    rc = radixk_ref.ref_radixk_zbuffer(c.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), n, W, H,
+                                       out.ctypes.data_as(C.c_void_p), od.ctypes.data_as(C.c_void_p), info)
+    if rc != 0:
+        raise RuntimeError("reference radix-k failed (rc %d)" % rc)
+    info = list(info)
+    k = info.index(-1)
+    return out, od, {"divisions": info[:2], "rounds": [(info[i], info[i + 1]) for i in range(2, k, 2)]}
+
+
 # ----------------------------------------------------------------------------- colour table (K8)
 class _CTable(C.Structure):
     _fields_ = [("space", C.c_int), ("n_color", C.c_int), ("color_x", C.c_double * 64),

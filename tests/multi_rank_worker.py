@@ -325,10 +325,9 @@ def gpu_checks(rank, world):
             ctx.comm_composite_images(vo)
             # ---- oracle, every rank computes the whole thing (small) and checks its own part
             cols, deps = zip(*[opaque(r) for r in range(world)])
-            front, fd = O.image_init(cols[0], deps[0], 0)
-            for r in range(1, world):
-                q, dq = O.image_init(cols[r], deps[r], 0)
-                O.zbuffer_composite(front, fd, q, dq, gl_depth=True)
+            # RadixKCompositor: equal-depth fragments of different ranks resolve in the tree's visiting order
+            qs = [O.image_init(cols[r], deps[r], 0) for r in range(world)]
+            front, fd = O.radixk_zbuffer(np.stack([q[0] for q in qs]), np.stack([q[1] for q in qs]), W, H)
             root_can, root_depth = O.image_to_canvas(front, fd)
             layers, depths = [], []
             for r in range(world):

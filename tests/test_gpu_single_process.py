@@ -168,3 +168,38 @@ def test_path_b_layers_two_contexts(push):
             _close(ctxs)
     finally:
         del os.environ["VR_LAYER_PUSH"]
+
+
+@pytest.mark.parametrize("n,W,H", [(2, 200, 120), (3, 203, 77), (4, 256, 144), (6, 200, 120), (8, 320, 200)])
+def test_zselect_resolves_ties_like_the_reference_radixk(n, W, H):
+    """vr_comm_composite_zbuffer against oracle.radixk_zbuffer (pinned to the reference's own reduce_images + DIY,
+    tests/test_oracle_radixk.py): depths drawn from a handful of values, so most pixels carry equal-depth fragments
+    of several ranks -- the case where the reference's answer depends on the radix-k tree's visiting order -- plus
+    fragments beyond the far plane (> 1), all-empty pixels, and a width that is not a multiple of 4."""
+    ctxs = _contexts(n, W * H)
+    try:
+        for rep in range(2):
+            g = np.random.default_rng(17 * n + rep)
+            cols = g.random((n, H * W, 4), dtype=np.float32)
+            deps = g.choice(np.array([0.2, 0.4, 0.4, 0.6, 0.8, 1.0, 1.001, 1.5], np.float32), (n, H * W))
+            deps[:, :W] = np.float32(1.25)  # a row where NO rank has a fragment in (.., 1]: the piece owner's pixel stays
+            for r, c in enumerate(ctxs):
+                c.canvas_upload(W, H, cols[r], deps[r])
+                c.image_from_canvas()
+            for c in ctxs:
+                c.comm_composite_zbuffer()
+            u8, d = ctxs[0].image_result_download(W, H)
+            for c in ctxs[1:]:
+                c.synchronize()
+            qs = [O.image_init(cols[r], deps[r], 0) for r in range(n)]
+            want, wd = O.radixk_zbuffer(np.stack([q[0] for q in qs]), np.stack([q[1] for q in qs]), W, H)
+            assert np.array_equal(d, wd), "depth (rep %d): %d pixels differ" % (rep, (d != wd).sum())
+            assert np.array_equal(u8, want), "colour (rep %d): %d pixels differ" % (rep, (u8 != want).any(axis=1).sum())
+            # and the rank-order fold the kernel used to do is a DIFFERENT image on this input
+            if n > 1:
+                front, fd = qs[0][0].copy(), qs[0][1].copy()
+                for r in range(1, n):
+                    O.zbuffer_composite(front, fd, qs[r][0], qs[r][1], gl_depth=True)
+                assert not np.array_equal(front, want)
+    finally:
+        _close(ctxs)
