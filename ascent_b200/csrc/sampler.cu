@@ -559,54 +559,32 @@ __device__ __forceinline__ void brick_march(const TraceParams& P, bool live, flo
   }
 }
 
-// MARCH: 0 = general march (any block, any step), 1 = sparse march, 2 = brick march (see above); each is
-// its own kernel so that each gets the register budget it needs: 56 / 72 / 96 registers per thread
-// (9 / 7 / 3 resident CTAs per SM; the brick march is bounded by its shared-memory bricks anyway).
+// One work item of a trace: tile `tile` of the launch P describes (an 8x4 pixel tile of the block's screen
+// rectangle or, in MODE 2, a chunk of the frame's complement to clear).  P is the kernel's __grid_constant__
+// for the one-block kernels and a per-warp copy in shared memory for trace_multi_kernel.
 template <int KIND, typename FT, int ASSOC, int MODE, typename IDX, int MARCH>
-__global__ void __launch_bounds__(kThreads, MARCH == 0 ? VR_MIN_BLOCKS : (MARCH == 1 ? 7 : 3))
-trace_kernel(const __grid_constant__ TraceParams P)
+__device__ __forceinline__ void trace_tile(const TraceParams& P, unsigned tile, unsigned& my_samples, unsigned& brick_parity,
+                                           unsigned char* s_dyn)
 {
-  extern __shared__ __align__(128) unsigned char s_dyn[]; // brick march: per-warp brick buffers + mbarriers
-  unsigned brick_parity = 0;
-  if (MARCH == 2)
-  {
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_dyn + (size_t)(kThreads / 32) * 2 * kBrickFloats * 4);
-    if (threadIdx.x < (kThreads / 32) * 2) mbar_init(smem_addr(bars + threadIdx.x), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
-  }
-  if (MODE != 4) // the staging pre-pass never classifies
-  {
-    for (int i = threadIdx.x; i < P.lut_size; i += kThreads) s_lut[i] = __ldg(P.lut + i);
-    __syncthreads();
-  }
-
   const BlockDev& B = P.blk;
   const int lane = threadIdx.x & 31;
   const int lx = lane & (kTileW - 1), ly = lane >> 3;
   const unsigned n_tiles = (unsigned)(P.tiles_x * P.tiles_y);
-  const unsigned n_work = n_tiles + (MODE == 2 ? (unsigned)P.n_clear_chunks : 0u);
   const float cms_f = P.cms_f;
   const float minx = B.min_point[0], miny = B.min_point[1], minz = B.min_point[2];
   const float maxx = B.max_point[0], maxy = B.max_point[1], maxz = B.max_point[2];
   const float sd = P.sample_dist;
-  unsigned my_samples = 0;
 
 #define VR_INSIDE(x, y, z) \
   (!((x) < minx || (x) > maxx) && !((y) < miny || (y) > maxy) && !((z) < minz || (z) > maxz))
 
-  for (;;)
   {
-    unsigned tile = 0;
-    if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
-    tile = __shfl_sync(0xffffffffu, tile, 0);
-    if (tile >= n_work) break;
     if (MODE == 2 && tile >= n_tiles)
     {
       // ---------------- Canvas::Clear for everything outside the traced rectangle, in the
       // frame's final formats (Image::Init of a cleared canvas: colour 0, depth 1.001)
       clear_chunk(P, tile - n_tiles, lane);
-      continue;
+      return;
     }
     // tiles are handed out centre rows first, and centre-out within a row: rays through the middle of the
     // block's screen rectangle are the long ones, so the kernel's tail -- a warp resident at a time draws
@@ -931,6 +909,40 @@ trace_kernel(const __grid_constant__ TraceParams P)
     }
   }
 #undef VR_INSIDE
+}
+
+// MARCH: 0 = general march (any block, any step), 1 = sparse march, 2 = brick march (see above); each is
+// its own kernel so that each gets the register budget it needs: 56 / 72 / 96 registers per thread
+// (9 / 7 / 3 resident CTAs per SM; the brick march is bounded by its shared-memory bricks anyway).
+template <int KIND, typename FT, int ASSOC, int MODE, typename IDX, int MARCH>
+__global__ void __launch_bounds__(kThreads, MARCH == 0 ? VR_MIN_BLOCKS : (MARCH == 1 ? 7 : 3))
+trace_kernel(const __grid_constant__ TraceParams P)
+{
+  extern __shared__ __align__(128) unsigned char s_dyn[]; // brick march: per-warp brick buffers + mbarriers
+  unsigned brick_parity = 0;
+  if (MARCH == 2)
+  {
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_dyn + (size_t)(kThreads / 32) * 2 * kBrickFloats * 4);
+    if (threadIdx.x < (kThreads / 32) * 2) mbar_init(smem_addr(bars + threadIdx.x), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+  }
+  if (MODE != 4) // the staging pre-pass never classifies
+  {
+    for (int i = threadIdx.x; i < P.lut_size; i += kThreads) s_lut[i] = __ldg(P.lut + i);
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const unsigned n_work = (unsigned)(P.tiles_x * P.tiles_y) + (MODE == 2 ? (unsigned)P.n_clear_chunks : 0u);
+  unsigned my_samples = 0;
+  for (;;)
+  {
+    unsigned tile = 0;
+    if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= n_work) break;
+    trace_tile<KIND, FT, ASSOC, MODE, IDX, MARCH>(P, tile, my_samples, brick_parity, s_dyn);
+  }
   if (P.end_stamp && threadIdx.x == 0) atomicMax(P.end_stamp, global_ns());
   if (P.sample_counter)
   {
@@ -939,6 +951,73 @@ trace_kernel(const __grid_constant__ TraceParams P)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0 && s) atomicAdd(P.sample_counter, s);
+  }
+}
+
+// Path B with MANY blocks per rank (c5: 512 blocks of 128^3 at 4096^2): one persistent launch over the
+// (block, tile) work items of ALL the rank's blocks instead of one launch per block -- 512 launches of ~4000
+// tiles each leave the GPU waiting for the host (5.6 us per launch) and every launch's CTAs reload the 16 KiB
+// table.  table[b] is block b's TraceParams (device memory), tile_end[b] the running sum of the blocks' tile
+// counts; a warp draws kMultiChunk consecutive work items per atomic, finds their block by bisection and keeps
+// that block's parameters in its own slot of shared memory (re-read only when the block changes).  Same
+// trace_tile, same arithmetic, same order of operations per ray as the one-block kernel: the same bits.
+constexpr unsigned kMultiChunk = 4;
+template <int KIND, typename FT, int ASSOC, typename IDX, int MARCH>
+__global__ void __launch_bounds__(kThreads, MARCH == 0 ? VR_MIN_BLOCKS - 1 : 6)
+trace_multi_kernel(const TraceParams* __restrict__ table, const unsigned* __restrict__ tile_end, int n_blocks,
+                   unsigned* __restrict__ counter)
+{
+  __shared__ __align__(16) TraceParams s_P[kThreads / 32];
+  static_assert(sizeof(TraceParams) % 16 == 0, "TraceParams is copied in 16-byte words");
+  {
+    const float4* lut = table[0].lut; // (one transfer function per context: the same table for every block)
+    const int lut_size = table[0].lut_size;
+    for (int i = threadIdx.x; i < lut_size; i += kThreads) s_lut[i] = __ldg(lut + i);
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned total = tile_end[n_blocks - 1];
+  unsigned my_samples = 0, brick_parity = 0;
+  int cur = -1;
+  unsigned cur_begin = 0, cur_end = 0;
+  for (;;)
+  {
+    unsigned w0 = 0;
+    if (lane == 0) w0 = atomicAdd(counter, kMultiChunk);
+    w0 = __shfl_sync(0xffffffffu, w0, 0);
+    if (w0 >= total) break;
+    const unsigned w1 = min(w0 + kMultiChunk, total);
+    for (unsigned w = w0; w < w1; ++w)
+    {
+      if (w >= cur_end || w < cur_begin)
+      {
+        // first block whose running tile count exceeds w (blocks without tiles have equal neighbours)
+        int lo = 0, hi = n_blocks - 1;
+        while (lo < hi)
+        {
+          const int mid = (lo + hi) >> 1;
+          if (__ldg(tile_end + mid) > w) hi = mid; else lo = mid + 1;
+        }
+        cur = lo;
+        cur_begin = lo > 0 ? __ldg(tile_end + lo - 1) : 0u;
+        cur_end = __ldg(tile_end + lo);
+        __syncwarp();
+        const uint4* src = reinterpret_cast<const uint4*>(table + cur);
+        uint4* dst = reinterpret_cast<uint4*>(&s_P[warp]);
+        for (int k = lane; k < (int)(sizeof(TraceParams) / 16); k += 32) dst[k] = __ldg(src + k);
+        __syncwarp();
+      }
+      trace_tile<KIND, FT, ASSOC, 3, IDX, MARCH>(s_P[warp], w - cur_begin, my_samples, brick_parity, nullptr);
+    }
+  }
+  const TraceParams& P0 = table[0];
+  if (P0.end_stamp && threadIdx.x == 0) atomicMax(P0.end_stamp, global_ns());
+  if (P0.sample_counter)
+  {
+    unsigned long long s = my_samples;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0 && s) atomicAdd(P0.sample_counter, s);
   }
 }
 
@@ -1005,6 +1084,53 @@ cudaError_t launch_dtype(const TraceParams& p, int mode, int grid, cudaStream_t 
 
 } // namespace
 
+namespace
+{
+template <int KIND, typename FT, int ASSOC, typename IDX>
+cudaError_t launch_multi_march(const TraceParams& first, const TraceParams* table, const unsigned* tile_end, int n,
+                               unsigned* counter, int grid, cudaStream_t s)
+{
+  auto go = [&](auto kernel) {
+    if (grid < 0) { preload_kernel(kernel); return; }
+    kernel<<<grid, kThreads, 0, s>>>(table, tile_end, n, counter);
+  };
+  if (KIND == 0 && ASSOC == VR_POINT && first.march == 1) go(trace_multi_kernel<0, FT, VR_POINT, IDX, 1>);
+  else go(trace_multi_kernel<KIND, FT, ASSOC, IDX, 0>);
+  return cudaGetLastError();
+}
+template <int KIND, typename FT>
+cudaError_t launch_multi_assoc(const TraceParams& first, const TraceParams* table, const unsigned* tile_end, int n,
+                               unsigned* counter, int grid, cudaStream_t s)
+{
+  // (blocks of 2^31 points or more go one launch each: vr_trace_blocks_to_layers batches 32-bit blocks only)
+  return first.blk.assoc == VR_POINT ? launch_multi_march<KIND, FT, VR_POINT, int>(first, table, tile_end, n, counter, grid, s)
+                                     : launch_multi_march<KIND, FT, VR_CELL, int>(first, table, tile_end, n, counter, grid, s);
+}
+cudaError_t launch_multi_dispatch(const TraceParams& first, const TraceParams* table, const unsigned* tile_end, int n,
+                                  unsigned* counter, int grid, cudaStream_t s)
+{
+  if (first.blk.kind == 0)
+    return first.blk.dtype == VR_F32 ? launch_multi_assoc<0, float>(first, table, tile_end, n, counter, grid, s)
+                                     : launch_multi_assoc<0, double>(first, table, tile_end, n, counter, grid, s);
+  return first.blk.dtype == VR_F32 ? launch_multi_assoc<1, float>(first, table, tile_end, n, counter, grid, s)
+                                   : launch_multi_assoc<1, double>(first, table, tile_end, n, counter, grid, s);
+}
+} // namespace
+
+// all n blocks share `first`'s kernel variant (grid kind, scalar type, association, 32-bit indices, march 0 or 1);
+// `counter` has been zeroed on `s`
+cudaError_t launch_trace_multi(const TraceParams& first, const TraceParams* table, const unsigned* tile_end, int n,
+                               unsigned long long total_tiles, unsigned* counter, int sm_count, cudaStream_t s)
+{
+  if (n <= 0 || total_tiles == 0) return cudaSuccess;
+  const int full = first.march == 1 ? 6 : VR_MIN_BLOCKS - 1;
+  const int ctas_per_sm = first.ctas_per_sm > 0 && first.ctas_per_sm < full ? first.ctas_per_sm : full;
+  long long grid = (long long)sm_count * ctas_per_sm;
+  const long long need = (long long)((total_tiles + 4ull * kMultiChunk - 1) / (4ull * kMultiChunk));
+  if (grid > need) grid = need;
+  return launch_multi_dispatch(first, table, tile_end, n, counter, (int)grid, s);
+}
+
 void preload_trace_kernels(const BlockDev& blk)
 {
   TraceParams p;
@@ -1017,6 +1143,11 @@ void preload_trace_kernels(const BlockDev& blk)
       if (blk.kind == 0) launch_dtype<0>(p, mode, -1, nullptr);
       else launch_dtype<1>(p, mode, -1, nullptr);
     }
+  for (int march = 0; march < 2; ++march)
+  {
+    p.march = march;
+    launch_multi_dispatch(p, nullptr, nullptr, 0, nullptr, -1, nullptr);
+  }
   cudaGetLastError();
 }
 

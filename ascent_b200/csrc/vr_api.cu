@@ -57,6 +57,8 @@ namespace vr { unsigned long long* comm_timeline_slot(vr_ctx* ctx, int k); }
 static void fill_to_canvas_params(const vr_camera* cam, int W, int H, ToCanvasParams& tp);
 
 // ================================================================= context
+static void free_multi(vr_ctx* ctx);
+
 extern "C" vr_status vr_create(int device, vr_ctx** out)
 {
   vr_ctx* ctx = nullptr;
@@ -207,6 +209,7 @@ extern "C" void vr_destroy(vr_ctx* ctx)
   cudaFree(ctx->enc_rgba);
   cudaFree(ctx->scratch_u64);
   cudaFree(ctx->tile_counter);
+  free_multi(ctx);
   cudaFree(ctx->sample_counter);
   for (int k = 0; k < vr::kAuxStreams; ++k)
   {
@@ -405,6 +408,19 @@ extern "C" vr_status vr_field_free(vr_ctx* ctx, void* dense_dev)
   CK(cudaStreamSynchronize(ctx->stream));
   cudaFree(dense_dev);
   return VR_OK;
+}
+
+static void free_multi(vr_ctx* ctx)
+{
+  cudaFree(ctx->multi_table);
+  cudaFree(ctx->multi_tile_end);
+  if (ctx->multi_host) cudaFreeHost(ctx->multi_host);
+  for (int k = 0; k < vr_ctx::kMultiSlots; ++k)
+    if (ctx->multi_ev[k]) { cudaEventDestroy(ctx->multi_ev[k]); ctx->multi_ev[k] = nullptr; }
+  ctx->multi_table = nullptr;
+  ctx->multi_tile_end = nullptr;
+  ctx->multi_host = nullptr;
+  ctx->multi_cap = 0;
 }
 
 // first publish of a (grid kind, scalar type, association, index width) on this context: load the sampler
@@ -1265,6 +1281,74 @@ extern "C" vr_status vr_trace_blocks_to_layers(vr_ctx* ctx, int n_blocks, const 
   vr_status st = ensure_layer_pool(ctx, used);
   if (st != VR_OK) return st;
   const int n = (int)ps.size();
+  // ---- many blocks: ONE persistent launch over the (block, tile) work items of all of them (sampler.cu,
+  // trace_multi_kernel) when they all run the same kernel variant; otherwise one launch per block, below
+  {
+    // (VR_MULTI_MIN: smallest batch that takes this route, 0 = never; read per call so that tests can switch it)
+    const char* mm = std::getenv("VR_MULTI_MIN");
+    const int multi_min = mm ? std::atoi(mm) : 16;
+    bool multi = multi_min > 0 && n >= multi_min;
+    for (int k = 0; k < n && multi; ++k)
+    {
+      const BlockDev& d = ps[k].blk;
+      const BlockDev& d0 = ps[0].blk;
+      const long long pts = (long long)d.dims[0] * d.dims[1] * d.dims[2];
+      multi = d.kind == d0.kind && d.dtype == d0.dtype && d.assoc == d0.assoc && pts < (1ll << 31) &&
+              ps[k].march == ps[0].march && ps[k].march <= 1 && !ctx->blocks[block_of[k]].staged_src;
+    }
+    if (multi)
+    {
+      std::vector<unsigned> tile_end(n);
+      unsigned long long total = 0;
+      for (int k = 0; k < n; ++k)
+      {
+        TraceParams& p = ps[k];
+        p.layer_rgba = ctx->lpool_rgba;
+        p.layer_depth = ctx->lpool_depth;
+        comm_layer_push_target(ctx, p);
+        p.tile_counter = nullptr;
+        total += (unsigned long long)p.tiles_x * p.tiles_y;
+        tile_end[k] = (unsigned)total;
+      }
+      if (total < (1ull << 32))
+      {
+        if (ctx->multi_cap < n)
+        {
+          CK(cudaStreamSynchronize(ctx->stream));
+          free_multi(ctx);
+          const int cap = std::max(n, 64);
+          CK(cudaMalloc(&ctx->multi_table, (size_t)cap * sizeof(TraceParams)));
+          CK(cudaMalloc(&ctx->multi_tile_end, (size_t)cap * sizeof(unsigned)));
+          // pinned staging, a ring of kMultiSlots frames: the copies below never make the host wait for the GPU
+          CK(cudaMallocHost(&ctx->multi_host, (size_t)vr_ctx::kMultiSlots * cap * (sizeof(TraceParams) + sizeof(unsigned))));
+          for (int k = 0; k < vr_ctx::kMultiSlots; ++k) CK(cudaEventCreateWithFlags(&ctx->multi_ev[k], cudaEventDisableTiming));
+          ctx->multi_cap = cap;
+          ctx->multi_slot = 0;
+        }
+        const int slot = ctx->multi_slot++ % vr_ctx::kMultiSlots;
+        CK(cudaEventSynchronize(ctx->multi_ev[slot])); // (the copy issued kMultiSlots batches ago: long done)
+        unsigned char* stage = ctx->multi_host + (size_t)slot * ctx->multi_cap * (sizeof(TraceParams) + sizeof(unsigned));
+        unsigned char* stage_ends = stage + (size_t)ctx->multi_cap * sizeof(TraceParams);
+        std::memcpy(stage, ps.data(), (size_t)n * sizeof(TraceParams));
+        std::memcpy(stage_ends, tile_end.data(), (size_t)n * sizeof(unsigned));
+        CK(cudaMemcpyAsync(ctx->multi_table, stage, (size_t)n * sizeof(TraceParams), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->multi_tile_end, stage_ends, (size_t)n * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->multi_ev[slot], ctx->stream));
+        CK(cudaMemsetAsync(ctx->tile_counter + 1, 0, sizeof(unsigned int), ctx->stream));
+        CK(launch_trace_multi(ps[0], ctx->multi_table, ctx->multi_tile_end, n, total, ctx->tile_counter + 1, ctx->sm_count,
+                              ctx->stream));
+        ctx->launches++;
+        for (int k = 0; k < n; ++k)
+        {
+          LayerDesc& d = T.d[T.n++];
+          d.x0 = ps[k].sx; d.y0 = ps[k].sy; d.w = ps[k].sw; d.h = ps[k].sh;
+          d.base = ps[k].layer_base;
+        }
+        ctx->lpool_used = used;
+        return VR_OK;
+      }
+    }
+  }
   const int n_streams = std::min(n, kAuxStreams);
   CK(cudaMemsetAsync(ctx->tile_counter + 1, 0, (size_t)n * sizeof(unsigned int), ctx->stream));
   CK(cudaEventRecord(ctx->ev_fork, ctx->stream));

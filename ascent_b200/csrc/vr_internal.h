@@ -29,8 +29,9 @@ struct BlockDev
   const void* tmap;
 };
 
-// Everything one trace launch needs; passed by value as a __grid_constant__.
-struct TraceParams
+// Everything one trace launch needs; passed by value as a __grid_constant__ (trace_multi_kernel reads a device
+// table of them in 16-byte words, hence the alignment).
+struct alignas(16) TraceParams
 {
   BlockDev blk;
   // K1
@@ -204,6 +205,13 @@ struct vr_ctx
   cudaStream_t stream = nullptr;
   std::string err;
   uint64_t launches = 0;
+  vr::TraceParams* multi_table = nullptr; // trace_multi_kernel: per-block parameters of the current batch
+  unsigned* multi_tile_end = nullptr; //                     running sum of the blocks' tile counts
+  int multi_cap = 0;
+  static constexpr int kMultiSlots = 4;
+  unsigned char* multi_host = nullptr; // pinned staging ring of the two arrays above
+  cudaEvent_t multi_ev[kMultiSlots] = { nullptr, nullptr, nullptr, nullptr };
+  int multi_slot = 0;
   unsigned trace_preloaded = 0; // bit (kind | dtype << 1 | assoc << 2 | 64-bit index << 3): sampler variants loaded
   int sm_count = 148;
   int ctas_per_sm = 0;        // trace kernel residency (0 = built-in default)
@@ -294,6 +302,8 @@ cudaError_t launch_trace(const TraceParams& p, int mode_partials, int sm_count, 
                          bool zero_counter = true);
 
 // stage.cu
+cudaError_t launch_trace_multi(const TraceParams& first, const TraceParams* table, const unsigned* tile_end, int n,
+                               unsigned long long total_tiles, unsigned* counter, int sm_count, cudaStream_t s);
 cudaError_t launch_fetch_lines(unsigned char* want, unsigned char* have, const void* src, void* dst,
                                size_t n_lines, size_t n_bytes, bool all, unsigned long long* n_have,
                                int sm_count, cudaStream_t s);

@@ -407,10 +407,14 @@ def test_layers_equal_list_pipeline(ctx, n_block, per_axis, az, res):
         ctx.block_free(i)
 
 
-@pytest.mark.parametrize("n_block,per_axis,az,res", [(12, 2, 0.0, (240, 200)), (7, 4, 61.0, (320, 180))])
-def test_batched_block_loop_equals_per_block_calls(ctx, n_block, per_axis, az, res):
-    """vr_trace_blocks_to_layers (whole RenderMultipleDomainsPerRank loop, launches overlapped on side
-    streams) leaves the same layers and the same canvas as one vr_trace_to_layer per block."""
+@pytest.mark.parametrize("n_block,per_axis,az,res,multi_min", [(12, 2, 0.0, (240, 200), None), (7, 4, 61.0, (320, 180), None),
+                                                              (12, 2, 33.0, (240, 200), "2"), (7, 4, 61.0, (320, 180), "0")])
+def test_batched_block_loop_equals_per_block_calls(ctx, n_block, per_axis, az, res, multi_min, monkeypatch):
+    """vr_trace_blocks_to_layers (whole RenderMultipleDomainsPerRank loop: one launch per block overlapped on side
+    streams, or -- from 16 blocks, VR_MULTI_MIN -- ONE persistent launch over the (block, tile) work items of all
+    blocks) leaves the same layers and the same canvas as one vr_trace_to_layer per block."""
+    if multi_min is not None:
+        monkeypatch.setenv("VR_MULTI_MIN", multi_min)
     doms = datasets.braid_uniform_blocks(n_block, per_axis, dtype=np.float32)
     gb = datasets.union_bounds([datasets.domain_bounds(d) for d in doms])
     W, H = res

@@ -129,11 +129,13 @@ def test_render_frames_batch_matches_per_frame(scene4):
         _close(ctxs)
 
 
-@pytest.mark.parametrize("push", ["1", "0"])
-def test_path_b_layers_two_contexts(push):
+@pytest.mark.parametrize("push,multi", [("1", "16"), ("0", "16"), ("1", "2"), ("0", "2")])
+def test_path_b_layers_two_contexts(push, multi):
     """four blocks per context (path B): ray layers pushed to / pulled by the tile owners, canvas bit-equal to
-    the single-rank oracle of the same eight domains"""
+    the single-rank oracle of the same eight domains; multi = 2: the four blocks of a context go through ONE
+    persistent launch over (block, tile) work items (trace_multi_kernel) instead of four launches"""
     os.environ["VR_LAYER_PUSH"] = push
+    os.environ["VR_MULTI_MIN"] = multi
     try:
         doms = datasets.braid_uniform_blocks(10, 2, dtype=np.float32)
         bl = [datasets.domain_bounds(d) for d in doms]
@@ -168,6 +170,7 @@ def test_path_b_layers_two_contexts(push):
             _close(ctxs)
     finally:
         del os.environ["VR_LAYER_PUSH"]
+        del os.environ["VR_MULTI_MIN"]
 
 
 @pytest.mark.parametrize("n,W,H", [(2, 200, 120), (3, 203, 77), (4, 256, 144), (6, 200, 120), (8, 320, 200)])
