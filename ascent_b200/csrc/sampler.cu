@@ -961,9 +961,15 @@ trace_kernel(const __grid_constant__ TraceParams P)
 // counts; a warp draws kMultiChunk consecutive work items per atomic, finds their block by bisection and keeps
 // that block's parameters in its own slot of shared memory (re-read only when the block changes).  Same
 // trace_tile, same arithmetic, same order of operations per ray as the one-block kernel: the same bits.
-constexpr unsigned kMultiChunk = 4;
+#ifndef VR_MULTI_SPARSE_CTAS
+#define VR_MULTI_SPARSE_CTAS 6 // resident CTAs per SM of the sparse-march variant (A/B: profiles/experiments)
+#endif
+#ifndef VR_MULTI_CHUNK
+#define VR_MULTI_CHUNK 8
+#endif
+constexpr unsigned kMultiChunk = VR_MULTI_CHUNK;
 template <int KIND, typename FT, int ASSOC, typename IDX, int MARCH>
-__global__ void __launch_bounds__(kThreads, MARCH == 0 ? VR_MIN_BLOCKS - 1 : 6)
+__global__ void __launch_bounds__(kThreads, MARCH == 0 ? VR_MIN_BLOCKS - 1 : VR_MULTI_SPARSE_CTAS)
 trace_multi_kernel(const TraceParams* __restrict__ table, const unsigned* __restrict__ tile_end, int n_blocks,
                    unsigned* __restrict__ counter)
 {
@@ -1123,7 +1129,7 @@ cudaError_t launch_trace_multi(const TraceParams& first, const TraceParams* tabl
                                unsigned long long total_tiles, unsigned* counter, int sm_count, cudaStream_t s)
 {
   if (n <= 0 || total_tiles == 0) return cudaSuccess;
-  const int full = first.march == 1 ? 6 : VR_MIN_BLOCKS - 1;
+  const int full = first.march == 1 ? VR_MULTI_SPARSE_CTAS : VR_MIN_BLOCKS - 1;
   const int ctas_per_sm = first.ctas_per_sm > 0 && first.ctas_per_sm < full ? first.ctas_per_sm : full;
   long long grid = (long long)sm_count * ctas_per_sm;
   const long long need = (long long)((total_tiles + 4ull * kMultiChunk - 1) / (4ull * kMultiChunk));

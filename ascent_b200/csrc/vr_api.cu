@@ -1288,6 +1288,17 @@ extern "C" vr_status vr_trace_blocks_to_layers(vr_ctx* ctx, int n_blocks, const 
     const char* mm = std::getenv("VR_MULTI_MIN");
     const int multi_min = mm ? std::atoi(mm) : 16;
     bool multi = multi_min > 0 && n >= multi_min;
+    if (multi)
+      for (int k = 0; k < n; ++k)
+      {
+        // short ray segments (a 128^3 block at the default sampling: ~14 samples per ray): the three-deep pipeline of
+        // the sparse march never fills, and its 80 registers cost residency -- the general march (64 registers, 8 CTAs
+        // per SM) is faster there (c5 on B200: render 2.09 vs 2.44 ms, profiles/r2_v20_c5_*.json).  Same bits either way
+        // (tests/test_gpu_marches.py).
+        TraceParams& q = ps[k];
+        const float ex = q.bmax[0] - q.bmin[0], ey = q.bmax[1] - q.bmin[1], ez = q.bmax[2] - q.bmin[2];
+        if (q.march == 1 && std::sqrt(ex * ex + ey * ey + ez * ez) < 32.f * q.sample_dist) q.march = 0;
+      }
     for (int k = 0; k < n && multi; ++k)
     {
       const BlockDev& d = ps[k].blk;

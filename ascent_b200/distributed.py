@@ -253,7 +253,14 @@ def run_bench(args, wl, bench):
             return t0.elapsed_time(t1)
 
         host_issue = [0.0, 0.0]
+        # NVLink payload bytes of this GPU from the NVML hardware counters, around the K timed frames
+        dev_index = torch.cuda.current_device()
+        nv0 = bench.nvlink_counters(dev_index)
         serial = timed(False)
+        nv1 = bench.nvlink_counters(dev_index)
+        nv_meas = [-1.0, -1.0]
+        if nv0 is not None and nv1 is not None:
+            nv_meas = [(nv1[0] - nv0[0]) / args.steps, (nv1[1] - nv0[1]) / args.steps]
         host_serial = host_issue[0]
         launches = ctx.kernel_launches() - l0
         piped = timed(True) if path_a else None
@@ -306,10 +313,11 @@ def run_bench(args, wl, bench):
         render_ms = float(np.median(rend))
         n_partials = 0 if path_a else _count_local_partials(ctx, render)
 
-    t = torch.tensor([total_ms, render_ms, tail_ms, comp_ms, float(launches), float(n_partials)],
+    t = torch.tensor([total_ms, render_ms, tail_ms, comp_ms, float(launches), float(n_partials), nv_meas[0], nv_meas[1]],
                      dtype=torch.float64, device="cuda")
     per_rank = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(per_rank, t)
+    nv_rows = [[float(pr[6]), float(pr[7])] for pr in per_rank]
     per_rank = [[round(float(x), 4) for x in pr[:4]] for pr in per_rank]
     tmax = t.clone()
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -446,7 +454,14 @@ def run_bench(args, wl, bench):
                 "nvlink": {"bytes_into_rank0_per_frame": nv_bytes, "pulled": pulled, "pushed_into_rank0": pushed,
                            "achieved_gbs": nv_bytes / (comp_ms * 1e-3) / 1e9, "peak_gbs": 770.0,
                            "peak_source": "measured peer copy per direction (B200_PROFILING.md)",
-                           "how": "bytes from the frame's geometry (screen rectangles), time = composite_ms_per_frame"},
+                           "how": "bytes from the frame's geometry (screen rectangles), time = composite_ms_per_frame",
+                           # hardware counters (NVML NVLINK_THROUGHPUT_DATA_RX/TX, payload, KiB granularity) read on
+                           # every rank around the K timed frames of the serial order: bytes per frame per GPU
+                           "measured": None if nv_rows[0][0] < 0 else {
+                               "rx_bytes_per_frame_by_rank": [round(r[0]) for r in nv_rows],
+                               "tx_bytes_per_frame_by_rank": [round(r[1]) for r in nv_rows],
+                               "rank0_rx_gbs": nv_rows[0][0] / (comp_ms * 1e-3) / 1e9,
+                               "source": "NVML field values 139/138 summed over links, delta over the timed frames"}},
                 "nccl_baseline": nccl_base, "exchange_timeline": timeline,
                 "t1_same_run": t1,
                 "e2e": e2e, "gpu_launches": int(tsum[4]), "clocks": clk,

@@ -92,6 +92,27 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def nvlink_counters(index):
+    """(rx_bytes, tx_bytes) of GPU `index` since boot, summed over its NVLinks, from the NVML hardware counters
+    (NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX/TX, payload bytes, reported in KiB) -- or None where NVML does not
+    expose them.  Read before and after a run of frames, the difference is what the exchange really moved."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(index))
+        all_links = 0xFFFFFFFF
+        v = pynvml.nvmlDeviceGetFieldValues(h, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, all_links),
+                                                (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, all_links)])
+        out = []
+        for x in v:
+            if x.nvmlReturn != 0:
+                return None
+            out.append(int(x.value.ullVal) * 1024)
+        return tuple(out)
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------- workloads
 def workload_c2():
     return dict(name="c2: braid uniform 512^3 f32, 1 domain, 1920x1080, default camera, samples=100",
