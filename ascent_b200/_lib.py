@@ -36,7 +36,7 @@ SYMBOLS = [
     "vr_sample_distance", "vr_visibility_order", "vr_find_subset", "vr_synth_braid_dev",
     "vr_camera_default", "vr_camera_reset_to_bounds", "vr_camera_azimuth", "vr_camera_elevation",
     "vr_camera_zoom", "vr_camera_cinema", "vr_color_table_sample", "vr_correct_opacity", "vr_comm_timeline",
-    "vr_comm_join", "vr_comm_render_frames", "vr_comm_connect_local", "vr_field_gather_strided", "vr_field_free", "vr_radixk_schedule",
+    "vr_comm_join", "vr_comm_render_frames", "vr_comm_connect_local", "vr_field_gather_strided", "vr_field_free", "vr_radixk_schedule", "vr_canvas_encode_png", "vr_png_bound",
 ]
 
 
@@ -145,6 +145,8 @@ def load():
         "vr_comm_connect_local": (C.c_int, [C.POINTER(vp), C.c_int]),
         "vr_field_gather_strided": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(vp)]),
         "vr_field_free": (C.c_int, [vp, vp]),
+        "vr_canvas_encode_png": (C.c_int, [vp, fp, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+        "vr_png_bound": (C.c_size_t, [C.c_int, C.c_int]),
         "vr_radixk_schedule": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                          C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "vr_comm_render_frames": (C.c_int, [vp, C.c_int, C.POINTER(CameraStruct), C.c_int, C.c_int, C.c_int, C.c_float,
@@ -337,6 +339,15 @@ class Context:
     # -- canvas
     def canvas_clear(self, W, H):
         self._ck(self.lib.vr_canvas_clear(self.h, W, H))
+
+    def canvas_encode_png(self, W, H, bg=None):
+        """vr_canvas_encode_png: the canvas as PNG file bytes (encoded on the device)"""
+        cap = int(self.lib.vr_png_bound(W, H))
+        buf = np.empty(cap, np.uint8)
+        n = C.c_size_t(0)
+        b = None if bg is None else np.ascontiguousarray(bg, np.float32).ctypes.data_as(C.POINTER(C.c_float))
+        self._ck(self.lib.vr_canvas_encode_png(self.h, b, buf.ctypes.data, cap, C.byref(n)))
+        return buf[:n.value].tobytes()
 
     def canvas_upload(self, W, H, rgba, depth):
         rgba = np.ascontiguousarray(rgba, np.float32)

@@ -92,6 +92,7 @@ extern "C" vr_status vr_create(int device, vr_ctx** out)
   preload_layers_kernels();
   preload_composite_kernels();
   preload_stage_kernels();
+  preload_png_kernels();
   cudaGetLastError();
   if (const char* e = std::getenv("VR_CTAS_PER_SM")) ctx->ctas_per_sm = std::atoi(e); // tuning knob
   if (const char* e = std::getenv("VR_TILE_ORDER")) ctx->tile_order = std::atoi(e);
@@ -210,6 +211,10 @@ extern "C" void vr_destroy(vr_ctx* ctx)
   cudaFree(ctx->scratch_u64);
   cudaFree(ctx->tile_counter);
   free_multi(ctx);
+  cudaFree(ctx->png_scratch);
+  cudaFree(ctx->png_out);
+  cudaFree(ctx->png_total);
+  if (ctx->png_total_host) cudaFreeHost(ctx->png_total_host);
   cudaFree(ctx->sample_counter);
   for (int k = 0; k < vr::kAuxStreams; ++k)
   {
@@ -707,6 +712,62 @@ extern "C" vr_status vr_canvas_download_rgba8(vr_ctx* ctx, const float* bg_rgba,
   CK(cudaStreamSynchronize(ctx->stream));
   return VR_OK;
 }
+
+extern "C" vr_status vr_canvas_encode_png(vr_ctx* ctx, const float* bg_rgba, uint8_t* png_host, size_t capacity,
+                                          size_t* png_bytes)
+{
+  VR_ENTER_RO(ctx);
+  REQUIRE(ctx->W > 0, "vr_canvas_encode_png: no canvas yet");
+  REQUIRE(png_bytes, "vr_canvas_encode_png: NULL size output");
+  REQUIRE(ctx->W <= 16384, "vr_canvas_encode_png: width above 16384");
+  CK(cudaSetDevice(ctx->device));
+  const int W = ctx->W, H = ctx->H;
+  const size_t n = (size_t)W * H;
+  if (n > ctx->enc_cap)
+  {
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->enc_rgba);
+    ctx->enc_rgba = nullptr;
+    ctx->enc_cap = 0;
+    CK(cudaMalloc(&ctx->enc_rgba, n * sizeof(uchar4)));
+    ctx->enc_cap = n;
+  }
+  const size_t need_scratch = png_scratch_bytes(W, H), need_out = png_capacity(W, H);
+  if (need_scratch > ctx->png_scratch_cap || need_out > ctx->png_out_cap)
+  {
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->png_scratch);
+    cudaFree(ctx->png_out);
+    ctx->png_scratch = ctx->png_out = nullptr;
+    ctx->png_scratch_cap = ctx->png_out_cap = 0;
+    CK(cudaMalloc(&ctx->png_scratch, need_scratch));
+    CK(cudaMalloc(&ctx->png_out, need_out));
+    ctx->png_scratch_cap = need_scratch;
+    ctx->png_out_cap = need_out;
+  }
+  if (!ctx->png_total)
+  {
+    CK(cudaMalloc(&ctx->png_total, sizeof(unsigned long long)));
+    CK(cudaMallocHost(&ctx->png_total_host, sizeof(unsigned long long)));
+  }
+  // PNGEncoder::Encode: (unsigned char)(c * 255.f), rows flipped (ascent_png_encoder.cpp:266-281)
+  CK(launch_encode_rgba8(ctx->canvas_rgba, W, H, 1, bg_rgba, ctx->enc_rgba, ctx->stream));
+  CK(launch_png_encode(ctx->enc_rgba, W, H, ctx->png_scratch, ctx->png_out, ctx->png_out_cap, ctx->png_total, ctx->sm_count,
+                       ctx->stream));
+  ctx->launches += 4;
+  CK(cudaMemcpyAsync(ctx->png_total_host, ctx->png_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const size_t total = (size_t)*ctx->png_total_host;
+  *png_bytes = total; // (also when it does not fit: the caller learns how much to provide)
+  REQUIRE(total <= ctx->png_out_cap, "vr_canvas_encode_png: internal bound of the file size exceeded");
+  if (!png_host) return VR_OK; // size query
+  REQUIRE(total <= capacity, "vr_canvas_encode_png: the file needs %zu bytes, the buffer holds %zu", total, capacity);
+  CK(cudaMemcpyAsync(png_host, ctx->png_out, total, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VR_OK;
+}
+
+extern "C" size_t vr_png_bound(int width, int height) { return png_capacity(width, height); }
 
 extern "C" vr_status vr_canvas_ptrs(vr_ctx* ctx, void** rgba_dev, void** depth_dev)
 {

@@ -208,6 +208,12 @@ struct vr_ctx
   vr::TraceParams* multi_table = nullptr; // trace_multi_kernel: per-block parameters of the current batch
   unsigned* multi_tile_end = nullptr; //                     running sum of the blocks' tile counts
   int multi_cap = 0;
+  // PNG encode on the device (png.cu): row slots + per-row checksums, the file, its size (device + pinned mirror)
+  unsigned char* png_scratch = nullptr;
+  unsigned char* png_out = nullptr;
+  unsigned long long* png_total = nullptr;
+  unsigned long long* png_total_host = nullptr;
+  size_t png_scratch_cap = 0, png_out_cap = 0;
   static constexpr int kMultiSlots = 4;
   unsigned char* multi_host = nullptr; // pinned staging ring of the two arrays above
   cudaEvent_t multi_ev[kMultiSlots] = { nullptr, nullptr, nullptr, nullptr };
@@ -575,4 +581,12 @@ void preload_layers_kernels();
 void preload_composite_kernels();
 void preload_stage_kernels();
 void preload_trace_kernels(const BlockDev& blk);
+void preload_png_kernels();
+
+// png.cu
+unsigned png_slot_stride(int W);
+size_t png_capacity(int W, int H);      // upper bound of the file size
+size_t png_scratch_bytes(int W, int H);
+cudaError_t launch_png_encode(const uchar4* rgba, int W, int H, unsigned char* scratch, unsigned char* out,
+                              unsigned long long capacity, unsigned long long* total_dev, int sm_count, cudaStream_t s);
 } // namespace vr

@@ -153,6 +153,17 @@ VR_API vr_status vr_canvas_ptrs(vr_ctx* ctx, void** rgba_dev, void** depth_dev);
 VR_API vr_status vr_canvas_blend_background(vr_ctx* ctx, const float bg_rgba[4]);
 VR_API vr_status vr_canvas_download_rgba8(vr_ctx* ctx, const float* bg_rgba, int flip_rows,
                                           uint8_t* out_rgba8);
+/* Render::Save's PNG encode on the device (Render.cpp:299-312 -> PNGEncoder::Encode + Save,
+ * ascent_png_encoder.cpp:258-303: float -> uint8, rows flipped, lodepng with Huffman-only deflate): the canvas
+ * (over bg_rgba when not NULL) becomes a complete PNG file -- RGBA, 8 bits, Sub-filtered scanlines, one
+ * fixed-Huffman deflate block per scanline with run-length matches, Adler-32 and CRC-32 combined from per-row
+ * partial sums -- and only the file crosses PCIe.  The decoded pixels equal vr_canvas_download_rgba8(ctx,
+ * bg_rgba, 1, ..); the byte stream is a different, equally lossless deflate encoding than lodepng's.
+ * *png_bytes receives the file size (always); png_host == NULL only queries it.  vr_png_bound(w, h) is an upper
+ * bound of the size for any content.  No annotations or tEXt comments (annotations off).  Syncs. */
+VR_API vr_status vr_canvas_encode_png(vr_ctx* ctx, const float* bg_rgba, uint8_t* png_host, size_t capacity,
+                                      size_t* png_bytes);
+VR_API size_t vr_png_bound(int width, int height);
 
 /* ------------------------------------------------------------------ (1) path A render
  * MapperVolume::RenderCells for one block and one camera: ray generation over the block's

@@ -994,3 +994,39 @@ def test_strided_blueprint_field_renders_like_the_dense_copy(ctx, dtype):
         ctx.field_free(dense)
         assert np.array_equal(rgba, want_rgba), src
         assert np.array_equal(depth, want_depth, equal_nan=True), src
+
+
+@pytest.mark.parametrize("W,H,bg", [(256, 192, None), (203, 77, (0.1, 0.2, 0.3, 1.0)), (1920, 1080, (1.0, 1.0, 1.0, 1.0))])
+def test_png_encoded_on_the_device(ctx, W, H, bg):
+    """vr_canvas_encode_png (Render::Save, Render.cpp:299-312 / ascent_png_encoder.cpp:258-303, on the GPU): the file
+    decodes (PIL) to exactly the pixels of vr_canvas_download_rgba8 -- the reference encoder's float -> uint8
+    conversion with flipped rows, oracle-checked in test_frame_epilogue_background_and_rgba8 -- and is byte for
+    byte the stream of the CPU model (tests/png_model.py): deflate blocks, Adler-32 and every chunk CRC."""
+    import io
+    from PIL import Image
+    import png_model
+    dom = datasets.braid_uniform(24, dtype=np.float32)
+    b = datasets.domain_bounds(dom)
+    cam = O.camera_reset_to_bounds(b)
+    O.camera_azimuth(cam, 35.0)
+    lut = color_table.parse_color_table(scenes.RAMP_TF).corrected_opacity(100).lut()
+    sd = O.sample_distance(b, 100)
+    rmin, rmax = scenes.field_range([dom])
+    ctx.set_tf(lut)
+    ctx.block_from_domain(0, dom)
+    ctx.canvas_clear(W, H)
+    ctx.trace_to_canvas(0, cam, sd, rmin, rmax, False)
+    bgv = None if bg is None else np.array(bg, np.float32)
+    want = np.asarray(ctx.canvas_download_rgba8(W, H, bgv, flip=True)).reshape(H, W, 4)
+    png = ctx.canvas_encode_png(W, H, bgv)
+    assert png[:8] == b"\x89PNG\r\n\x1a\n"
+    img = Image.open(io.BytesIO(png))
+    img.load()  # (verifies the chunk CRCs and the Adler-32)
+    assert img.mode == "RGBA" and img.size == (W, H)
+    assert np.array_equal(np.array(img), want)
+    if W * H <= 100000:  # (the model is a pure-Python loop over every byte)
+        model, _, _ = png_model.encode(want)
+        assert len(png) == len(model) and png == model
+    assert len(png) <= _lib.load().vr_png_bound(W, H)
+    assert len(png) < W * H * 4 // 2  # the background rows collapse
+    ctx.block_free(0)
