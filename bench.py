@@ -100,15 +100,27 @@ def nvlink_counters(index):
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(int(index))
-        all_links = 0xFFFFFFFF
-        v = pynvml.nvmlDeviceGetFieldValues(h, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, all_links),
-                                                (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, all_links)])
-        out = []
-        for x in v:
-            if x.nvmlReturn != 0:
+        ids = (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX)
+
+        def read(scope):
+            v = pynvml.nvmlDeviceGetFieldValues(h, [(ids[0], scope), (ids[1], scope)])
+            if any(x.nvmlReturn != 0 for x in v):
                 return None
-            out.append(int(x.value.ullVal) * 1024)
-        return tuple(out)
+            return [int(x.value.ullVal) * 1024 for x in v]
+
+        tot = read(0xFFFFFFFF)  # all links at once
+        if tot is None:        # ... or link by link
+            tot = [0, 0]
+            n_ok = 0
+            for link in range(18):
+                r = read(link)
+                if r is not None:
+                    tot[0] += r[0]
+                    tot[1] += r[1]
+                    n_ok += 1
+            if n_ok == 0:
+                return None
+        return tuple(tot)
     except Exception:
         return None
 
