@@ -340,14 +340,16 @@ class Context:
     def canvas_clear(self, W, H):
         self._ck(self.lib.vr_canvas_clear(self.h, W, H))
 
-    def canvas_encode_png(self, W, H, bg=None):
-        """vr_canvas_encode_png: the canvas as PNG file bytes (encoded on the device)"""
+    def canvas_encode_png(self, W, H, bg=None, out=None):
+        """vr_canvas_encode_png: the canvas as PNG file bytes (encoded on the device).  out: a uint8 host buffer of
+        at least vr_png_bound(W, H) bytes (e.g. pinned) -- then a view of it is returned instead of a copy."""
         cap = int(self.lib.vr_png_bound(W, H))
-        buf = np.empty(cap, np.uint8)
+        buf = np.empty(cap, np.uint8) if out is None else out
+        assert buf.dtype == np.uint8 and buf.size >= cap
         n = C.c_size_t(0)
         b = None if bg is None else np.ascontiguousarray(bg, np.float32).ctypes.data_as(C.POINTER(C.c_float))
-        self._ck(self.lib.vr_canvas_encode_png(self.h, b, buf.ctypes.data, cap, C.byref(n)))
-        return buf[:n.value].tobytes()
+        self._ck(self.lib.vr_canvas_encode_png(self.h, b, buf.ctypes.data, buf.size, C.byref(n)))
+        return buf[:n.value].tobytes() if out is None else buf[:n.value]
 
     def canvas_upload(self, W, H, rgba, depth):
         rgba = np.ascontiguousarray(rgba, np.float32)

@@ -115,3 +115,29 @@ def union_bounds(bounds_list):
     out[0::2] = bl[:, 0::2].min(axis=0)
     out[1::2] = bl[:, 1::2].max(axis=0)
     return out
+
+
+def structured_to_hexes(dims, origin, spacing, drop_cells=()):
+    """Explicit hexahedra (VTK vertex order) of a uniform grid: (points [n,3] f32, conn [n_cells,8] int32).
+    drop_cells: flat cell ids (x fastest) to leave out -- what vtk-h's ghost stripper does to a ragged ghost field."""
+    nx, ny, nz = [int(d) for d in dims]
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    pts = np.stack([np.float32(origin[0]) + np.float32(spacing[0]) * i.astype(np.float32),
+                    np.float32(origin[1]) + np.float32(spacing[1]) * j.astype(np.float32),
+                    np.float32(origin[2]) + np.float32(spacing[2]) * k.astype(np.float32)], -1).reshape(-1, 3)
+    ck, cj, ci = np.meshgrid(np.arange(nz - 1), np.arange(ny - 1), np.arange(nx - 1), indexing="ij")
+    i0 = ((ck * ny + cj) * nx + ci).reshape(-1)
+    conn = np.stack([i0, i0 + 1, i0 + 1 + nx, i0 + nx, i0 + nx * ny, i0 + nx * ny + 1, i0 + nx * ny + 1 + nx,
+                     i0 + nx * ny + nx], 1).astype(np.int32)
+    if len(drop_cells):
+        keep = np.ones(conn.shape[0], bool)
+        keep[np.asarray(drop_cells, int)] = False
+        conn = conn[keep]
+    return pts.astype(np.float32), conn
+
+
+def hexes_to_tets(conn):
+    """Six tetrahedra per hexahedron around the 0-6 diagonal (conforming across faces of a structured mesh)."""
+    c = np.asarray(conn)
+    order = [(0, 1, 2, 6), (0, 2, 3, 6), (0, 3, 7, 6), (0, 7, 4, 6), (0, 4, 5, 6), (0, 5, 1, 6)]
+    return np.concatenate([c[:, list(o)] for o in order], 0).astype(np.int32)

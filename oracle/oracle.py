@@ -228,6 +228,68 @@ def rays_free(rays):
     lib.orc_rays_free(C.byref(rays))
 
 
+class UMesh(C.Structure):
+    _fields_ = [("n_points", C.c_int), ("n_cells", C.c_int), ("shape", C.c_int), ("xyz", C.c_void_p),
+                ("conn", C.c_void_p), ("field", C.c_void_p), ("field_f64", C.c_int), ("cell_assoc", C.c_int),
+                ("bmin", C.c_float * 3), ("bmax", C.c_float * 3), ("ginv", C.c_float * 3), ("g", C.c_int * 3),
+                ("bin_start", C.c_void_p), ("bin_cells", C.c_void_p)]
+
+
+class OracleUMesh:
+    """N4: an explicit cell set (hexahedra or tetrahedra) with a point or cell field.  Keeps the arrays alive."""
+
+    def __init__(self, points, conn, field, cell_assoc=False):
+        self.points = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        self.conn = np.ascontiguousarray(conn, np.int32)
+        assert self.conn.ndim == 2 and self.conn.shape[1] in (4, 8)
+        self.field = np.ascontiguousarray(field)
+        assert self.field.dtype in (np.float32, np.float64)
+        assert self.field.size == (self.conn.shape[0] if cell_assoc else self.points.shape[0])
+        m = self.m = UMesh()
+        m.n_points, m.n_cells, m.shape = self.points.shape[0], self.conn.shape[0], self.conn.shape[1]
+        m.xyz, m.conn, m.field = self.points.ctypes.data, self.conn.ctypes.data, self.field.ctypes.data
+        m.field_f64 = int(self.field.dtype == np.float64)
+        m.cell_assoc = int(cell_assoc)
+        lib.orc_umesh_build(C.byref(m))
+
+    def __del__(self):
+        try:
+            lib.orc_umesh_free(C.byref(self.m))
+        except Exception:
+            pass
+
+    def bounds(self):
+        out = (C.c_double * 6)()
+        lib.orc_umesh_bounds(C.byref(self.m), out)
+        return np.array(out[:], np.float64)
+
+
+def trace_umesh(mesh, cam, W, H, lut, sample_dist, rmin, rmax, canvas_depth=None, keep=True, structured_phase=False):
+    lut = np.ascontiguousarray(lut, np.float32)
+    rays = Rays()
+    dptr = None if canvas_depth is None else _ptr(canvas_depth, C.c_float)
+    lib.orc_trace_umesh(C.byref(mesh.m), C.byref(cam), W, H, _ptr(lut, C.c_float), int(lut.shape[0]),
+                        C.c_float(sample_dist), C.c_float(rmin), C.c_float(rmax), dptr, int(structured_phase),
+                        C.byref(rays))
+    return rays, (TraceResult(rays) if keep else None)
+
+
+def render_umesh_partials(mesh, cam, W, H, lut, sample_dist, rmin, rmax, canvas_depth=None):
+    """UnstructuredWrapper::render + vtkm_to_partials (VolumeRenderer.cpp:141-221): one partial per ray that
+    gathered alpha >= 0.001, depth = the ray's exit distance."""
+    rays, _ = trace_umesh(mesh, cam, W, H, lut, sample_dist, rmin, rmax, canvas_depth, keep=False)
+    out = np.zeros(rays.n, PARTIAL_DTYPE)
+    n = lib.orc_extract_partials(C.byref(rays), out.ctypes.data_as(C.c_void_p))
+    rays_free(rays)
+    return out[:n].copy()
+
+
+def render_umesh_to_canvas(mesh, cam, W, H, lut, sample_dist, rmin, rmax, rgba, depth, use_depth=True):
+    rays, _ = trace_umesh(mesh, cam, W, H, lut, sample_dist, rmin, rmax, depth if use_depth else None, keep=False)
+    lib.orc_write_to_canvas(C.byref(rays), C.byref(cam), W, H, _ptr(rgba, C.c_float), _ptr(depth, C.c_float))
+    rays_free(rays)
+
+
 def new_canvas(W, H):
     """Canvas::Clear: colour 0, depth 1.001 (SURVEY B18)."""
     return np.zeros((H * W, 4), np.float32), np.full(H * W, 1.001, np.float32)

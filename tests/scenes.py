@@ -149,3 +149,38 @@ def cinema_camera(bounds, phi, theta):
     """CinemaManager::create_cinema_cameras (ascent_runtime_rendering_filters.cpp:906-960), one angle
     pair: the oracle's restatement."""
     return O.camera_cinema(bounds, phi, theta)
+
+
+GHOST_TF = {"name": "rainbow desaturated", "control_points": [
+    {"type": "alpha", "position": 0., "alpha": 0.2},
+    {"type": "alpha", "position": 1.0, "alpha": 0.5}]}
+
+
+def ghost_volume_scene():
+    """t_ascent_multi_topo.cpp:181-252 (single_ghost_vol_render): braid uniform 10^3 with a RAGGED ghost field (cells
+    0 and 1 flagged, t_utils.hpp:517-553) -- vtk-h's ghost stripper cannot cut a structured sub-box out of that, so it
+    thresholds the cells away and the volume renderer receives an explicit cell set: the unstructured path (N4).
+    Volume plot of the vertex field `braid`, fixed range [-0.5, 0.5], azimuth 170, elevation 11, 1024^2, no
+    annotations.  Returns the mesh as (points, hexahedra, point field)."""
+    dom = datasets.braid_uniform(10, dtype=np.float64)
+    bounds = datasets.domain_bounds(dom)
+    cam = O.camera_reset_to_bounds(bounds)
+    O.camera_azimuth(cam, 170.0)
+    O.camera_elevation(cam, 11.0)
+    pts, conn = datasets.structured_to_hexes(dom["dims"], dom["origin"], dom["spacing"], drop_cells=[0, 1])
+    lut = O.parse_color_table(GHOST_TF).correct_opacity(100).lut()
+    return dict(points=pts, conn=conn, field=dom["field"].reshape(-1), cam=cam, W=1024, H=1024, lut=lut, rmin=-0.5,
+                rmax=0.5, sample_dist=O.sample_distance(bounds, 100), bounds=bounds, dom=dom)
+
+
+def oracle_unstructured_path_b(scene, mesh=None):
+    """RenderMultipleDomainsPerRank with an unstructured domain (VolumeRenderer.cpp:539-597 + UnstructuredWrapper
+    :182-221): partials -> PartialCompositor -> partials_to_canvas.  Returns (partials, canvas rgba, canvas depth)."""
+    W, H = scene["W"], scene["H"]
+    um = mesh or O.OracleUMesh(scene["points"], scene["conn"], scene["field"], cell_assoc=scene.get("cell_assoc", False))
+    rgba, depth = O.new_canvas(W, H)
+    parts = O.render_umesh_partials(um, scene["cam"], W, H, scene["lut"], scene["sample_dist"], scene["rmin"],
+                                    scene["rmax"], depth)
+    res = O.composite_partials([parts])
+    O.partials_to_canvas(res, scene["cam"], W, H, rgba, depth)
+    return parts, rgba, depth
