@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("VR_LIB_NAME", "libvr_b200.so"))
 VR_OK = 0
 VR_F32, VR_F64 = 0, 1
 VR_POINT, VR_CELL = 0, 1
+VR_TETRA, VR_HEXAHEDRON = 10, 12
 VR_HOST, VR_DEVICE, VR_HOST_MAPPED, VR_HOST_STAGED = 0, 1, 2, 3
 IPC_HANDLE_BYTES = 64
 FRAME_WRITE_CANVAS, FRAME_NO_CLEAR, FRAME_AHEAD, FRAME_PUSH = 1, 2, 4, 8
@@ -36,7 +37,7 @@ SYMBOLS = [
     "vr_sample_distance", "vr_visibility_order", "vr_find_subset", "vr_synth_braid_dev",
     "vr_camera_default", "vr_camera_reset_to_bounds", "vr_camera_azimuth", "vr_camera_elevation",
     "vr_camera_zoom", "vr_camera_cinema", "vr_color_table_sample", "vr_correct_opacity", "vr_comm_timeline",
-    "vr_comm_join", "vr_comm_render_frames", "vr_comm_connect_local", "vr_field_gather_strided", "vr_field_free", "vr_radixk_schedule", "vr_canvas_encode_png", "vr_png_bound",
+    "vr_comm_join", "vr_comm_render_frames", "vr_comm_connect_local", "vr_field_gather_strided", "vr_field_free", "vr_radixk_schedule", "vr_canvas_encode_png", "vr_png_bound", "vr_block_unstructured",
 ]
 
 
@@ -147,6 +148,8 @@ def load():
         "vr_field_free": (C.c_int, [vp, vp]),
         "vr_canvas_encode_png": (C.c_int, [vp, fp, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
         "vr_png_bound": (C.c_size_t, [C.c_int, C.c_int]),
+        "vr_block_unstructured": (C.c_int, [vp, C.c_int, C.c_size_t, vp, C.c_int, C.c_size_t, C.c_int, vp, C.c_int, vp,
+                                            C.c_int, C.c_int, C.c_int]),
         "vr_radixk_schedule": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                          C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "vr_comm_render_frames": (C.c_int, [vp, C.c_int, C.POINTER(CameraStruct), C.c_int, C.c_int, C.c_int, C.c_float,
@@ -279,6 +282,19 @@ class Context:
 
     def field_free(self, dense_ptr):
         self._ck(self.lib.vr_field_free(self.h, C.c_void_p(dense_ptr)))
+
+    def block_unstructured(self, block_id, points, conn, field, assoc=VR_POINT):
+        """vr_block_unstructured from host arrays: points [n,3] f32/f64, conn [n_cells, 8|4] int32/int64, field f32/f64"""
+        pts = np.ascontiguousarray(points)
+        assert pts.dtype in (np.float32, np.float64) and pts.ndim == 2 and pts.shape[1] == 3
+        cn = np.ascontiguousarray(conn)
+        assert cn.dtype in (np.int32, np.int64) and cn.ndim == 2 and cn.shape[1] in (4, 8)
+        f = np.ascontiguousarray(field)
+        assert f.dtype in (np.float32, np.float64)
+        self._ck(self.lib.vr_block_unstructured(
+            self.h, block_id, pts.shape[0], pts.ctypes.data, VR_F32 if pts.dtype == np.float32 else VR_F64, cn.shape[0],
+            VR_HEXAHEDRON if cn.shape[1] == 8 else VR_TETRA, cn.ctypes.data, 32 if cn.dtype == np.int32 else 64,
+            f.ctypes.data, VR_F32 if f.dtype == np.float32 else VR_F64, assoc, VR_HOST))
 
     def block_uniform(self, block_id, dims, origin, spacing, field, assoc=VR_POINT, device_ptr=None,
                       dtype=None, host_mapped=False, staged=False):

@@ -93,6 +93,7 @@ extern "C" vr_status vr_create(int device, vr_ctx** out)
   preload_composite_kernels();
   preload_stage_kernels();
   preload_png_kernels();
+  preload_unstructured_kernels();
   cudaGetLastError();
   if (const char* e = std::getenv("VR_CTAS_PER_SM")) ctx->ctas_per_sm = std::atoi(e); // tuning knob
   if (const char* e = std::getenv("VR_TILE_ORDER")) ctx->tile_order = std::atoi(e);
@@ -156,6 +157,12 @@ static void free_block(Block& b)
   b.dev.tmap = nullptr;
   if (b.owned_field) cudaFree(b.owned_field);
   if (b.owned_axes) cudaFree(b.owned_axes);
+  if (b.owned_xyz) cudaFree(b.owned_xyz);
+  if (b.owned_conn) cudaFree(b.owned_conn);
+  if (b.owned_bin_start) cudaFree(b.owned_bin_start);
+  if (b.owned_bin_cells) cudaFree(b.owned_bin_cells);
+  b.owned_xyz = b.owned_conn = nullptr;
+  b.owned_bin_start = b.owned_bin_cells = nullptr;
   if (b.line_want) cudaFree(b.line_want);
   if (b.line_have) cudaFree(b.line_have);
   if (b.n_have_dev) cudaFree(b.n_have_dev);
@@ -539,6 +546,104 @@ extern "C" vr_status vr_block_rectilinear(vr_ctx* ctx, int block_id, const int d
   return VR_OK;
 }
 
+// N4: an explicit cell set.  Coordinates and connectivity are narrowed to f32 / int32 on the way in (VTK-m's
+// unstructured tracer works in f32 as well); the cell locator is built on the device.
+extern "C" vr_status vr_block_unstructured(vr_ctx* ctx, int block_id, size_t n_points, const void* xyz, int coord_dtype,
+                                           size_t n_cells, int cell_shape, const void* connectivity, int index_bits,
+                                           const void* field, int dtype, int assoc, int where)
+{
+  VR_ENTER_RO(ctx);
+  REQUIRE(xyz && connectivity && field, "vr_block_unstructured: NULL argument");
+  REQUIRE(cell_shape == VR_HEXAHEDRON || cell_shape == VR_TETRA,
+          "vr_block_unstructured: cell shape must be VR_HEXAHEDRON (12) or VR_TETRA (10)");
+  REQUIRE(coord_dtype == VR_F32 || coord_dtype == VR_F64, "vr_block_unstructured: coordinates must be VR_F32 or VR_F64");
+  REQUIRE(index_bits == 32 || index_bits == 64, "vr_block_unstructured: connectivity must be 32- or 64-bit integers");
+  REQUIRE(dtype == VR_F32 || dtype == VR_F64, "vr_block_unstructured: field must be VR_F32 or VR_F64");
+  REQUIRE(assoc == VR_POINT || assoc == VR_CELL, "vr_block_unstructured: bad association");
+  REQUIRE(where == VR_HOST || where == VR_DEVICE, "vr_block_unstructured: where must be VR_HOST or VR_DEVICE");
+  REQUIRE(n_points >= 4 && n_cells >= 1 && n_points < (1ull << 31) && n_cells < (1ull << 31) / 8,
+          "vr_block_unstructured: empty or too large mesh");
+  REQUIRE(where == VR_HOST || (coord_dtype == VR_F32 && index_bits == 32),
+          "vr_block_unstructured: device arrays are adopted in place and must be f32 coordinates / 32-bit connectivity");
+  CK(cudaSetDevice(ctx->device));
+  const int shape = cell_shape == VR_HEXAHEDRON ? 8 : 4;
+  Block b;
+  std::memset(&b.dev, 0, sizeof(b.dev));
+  std::memset(&b.um, 0, sizeof(b.um));
+  b.dev.kind = 2;
+  b.dev.dtype = dtype;
+  b.dev.assoc = assoc;
+  const size_t n_field = assoc == VR_POINT ? n_points : n_cells;
+  const size_t fb = n_field * (dtype == VR_F32 ? 4 : 8);
+  cudaError_t e = cudaSuccess;
+  if (where == VR_DEVICE)
+  {
+    b.um.xyz = static_cast<const float*>(xyz);
+    b.um.conn = static_cast<const int*>(connectivity);
+    b.um.field = field;
+  }
+  else
+  {
+    std::vector<float> hx(n_points * 3);
+    if (coord_dtype == VR_F32) std::memcpy(hx.data(), xyz, hx.size() * 4);
+    else
+      for (size_t i = 0; i < hx.size(); ++i) hx[i] = (float)static_cast<const double*>(xyz)[i];
+    std::vector<int> hc(n_cells * (size_t)shape);
+    for (size_t i = 0; i < hc.size(); ++i)
+    {
+      const long long v = index_bits == 32 ? (long long)static_cast<const int*>(connectivity)[i]
+                                           : static_cast<const long long*>(connectivity)[i];
+      if (v < 0 || (size_t)v >= n_points) return fail(ctx, VR_ERR_INVALID, "vr_block_unstructured: connectivity entry %zu out of range", i);
+      hc[i] = (int)v;
+    }
+    e = cudaMalloc(&b.owned_xyz, hx.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&b.owned_conn, hc.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&b.owned_field, fb);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b.owned_xyz, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b.owned_conn, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b.owned_field, field, fb, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); // (the staging vectors die with this scope)
+    if (e != cudaSuccess) { free_block(b); return fail(ctx, VR_ERR_CUDA, "vr_block_unstructured: %s", cudaGetErrorString(e)); }
+    b.um.xyz = static_cast<const float*>(b.owned_xyz);
+    b.um.conn = static_cast<const int*>(b.owned_conn);
+    b.um.field = b.owned_field;
+  }
+  b.um.dtype = dtype;
+  b.um.assoc = assoc;
+  b.um.shape = shape;
+  b.um.n_cells = (int)n_cells;
+  b.um.n_points = (int)n_points;
+  // point bounds (device reduction), bins per axis = ceil(cbrt(n_cells)) capped at 256
+  int* keys = nullptr;
+  e = cudaMalloc(&keys, 6 * sizeof(int));
+  if (e == cudaSuccess) e = umesh_bounds(b.um.xyz, n_points, keys, b.um.bmin, b.um.bmax, ctx->sm_count, ctx->stream);
+  cudaFree(keys);
+  if (e != cudaSuccess) { free_block(b); return fail(ctx, VR_ERR_CUDA, "vr_block_unstructured (bounds): %s", cudaGetErrorString(e)); }
+  int g = (int)std::ceil(std::cbrt((double)n_cells));
+  g = std::max(1, std::min(g, 256));
+  for (int a = 0; a < 3; ++a)
+  {
+    b.um.g[a] = g;
+    const float ext = b.um.bmax[a] - b.um.bmin[a];
+    b.um.ginv[a] = ext > 0.f ? (float)g / ext : 0.f;
+    b.bounds[2 * a] = (double)b.um.bmin[a];
+    b.bounds[2 * a + 1] = (double)b.um.bmax[a];
+    b.dev.min_point[a] = b.um.bmin[a];
+    b.dev.max_point[a] = b.um.bmax[a];
+  }
+  e = umesh_build_bins(b.um, &b.owned_bin_start, &b.owned_bin_cells, ctx->sm_count, ctx->stream);
+  ctx->launches += 4;
+  if (e != cudaSuccess) { free_block(b); return fail(ctx, VR_ERR_CUDA, "vr_block_unstructured (bins): %s", cudaGetErrorString(e)); }
+  auto it = ctx->blocks.find(block_id);
+  if (it != ctx->blocks.end())
+  {
+    cudaStreamSynchronize(ctx->stream);
+    free_block(it->second);
+  }
+  ctx->blocks[block_id] = b;
+  return VR_OK;
+}
+
 extern "C" vr_status vr_block_free(vr_ctx* ctx, int block_id)
 {
   VR_ENTER_RO(ctx);
@@ -853,13 +958,17 @@ static bool encode_brick_tensor_map(const BlockDev& b, unsigned char out[128])
 
 static vr_status fill_trace_params(vr_ctx* ctx, int block_id, const vr_camera* cam, float sample_dist,
                                    float range_min, float range_max, int use_depth, int W, int H,
-                                   TraceParams& p)
+                                   TraceParams& p, bool allow_unstructured = false)
 {
   REQUIRE(cam != nullptr, "trace: camera is NULL");
   auto it = ctx->blocks.find(block_id);
   REQUIRE(it != ctx->blocks.end(), "trace: unknown block %d", block_id);
   REQUIRE(ctx->lut_size >= 2, "trace: no transfer function set (vr_set_tf)");
   const Block& b = it->second;
+  // the reference renders unstructured domains as partials only (m_has_unstructured forces path B,
+  // VolumeRenderer.cpp:874-903)
+  REQUIRE(b.dev.kind != 2 || allow_unstructured,
+          "trace: block %d is unstructured: render it with vr_trace_to_partials (path B)", block_id);
   std::memset(&p, 0, sizeof(p));
   p.blk = b.dev;
   int sub[4];
@@ -1111,8 +1220,21 @@ extern "C" vr_status vr_trace_to_partials(vr_ctx* ctx, int block_id, const vr_ca
   CK(cudaSetDevice(ctx->device));
   TraceParams p;
   vr_status st = fill_trace_params(ctx, block_id, cam, sample_dist, range_min, range_max,
-                                   use_canvas_depth, ctx->pW, ctx->pH, p);
+                                   use_canvas_depth, ctx->pW, ctx->pH, p, true);
   if (st != VR_OK) return st;
+  if (p.blk.kind == 2)
+  {
+    // UnstructuredWrapper::render + vtkm_to_partials (VolumeRenderer.cpp:141-221)
+    ctx->n_partials_host += (size_t)p.sw * p.sh;
+    st = ensure_partials(ctx, ctx->n_partials_host);
+    if (st != VR_OK) return st;
+    p.partials = ctx->partials;
+    p.partial_count = ctx->partial_count;
+    p.partial_capacity = ctx->partial_cap;
+    CK(launch_utrace_partials(p, ctx->blocks[block_id].um, ctx->sm_count, ctx->stream));
+    ctx->launches++;
+    return VR_OK;
+  }
   // worst case every ray of the subset emits: reserve before launching (no overflow possible)
   // the list can only be bounded from the host by the sum of subset sizes so far
   static_assert(sizeof(vr_partial) == 24, "vr_partial must be 24 bytes");

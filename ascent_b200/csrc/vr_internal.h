@@ -29,6 +29,22 @@ struct BlockDev
   const void* tmap;
 };
 
+// An explicit cell set (unstructured.cu): hexahedra (VTK vertex order) or tetrahedra, with the uniform bins that
+// locate a sample's cell.  Passed by value as a __grid_constant__.
+struct UMeshDev
+{
+  const float* xyz;   // n_points x 3
+  const int* conn;    // n_cells x shape
+  const void* field;
+  int dtype, assoc;   // VR_F32 / VR_F64, VR_POINT / VR_CELL
+  int shape;          // 8 or 4
+  int n_cells, n_points;
+  float bmin[3], bmax[3], ginv[3];
+  int g[3];
+  const int* bin_start; // g0 g1 g2 + 1
+  const int* bin_cells;
+};
+
 // Everything one trace launch needs; passed by value as a __grid_constant__ (trace_multi_kernel reads a device
 // table of them in 16-byte words, hence the alignment).
 struct alignas(16) TraceParams
@@ -107,6 +123,12 @@ struct Block
   double bounds[6];
   // VR_HOST_STAGED: the field stays in mapped host memory; owned_field is a device buffer of the
   // same size that holds only the 128-byte lines some ray has needed since the publish
+  // kind 2 (vr_block_unstructured): the mesh; xyz / conn / bins owned unless adopted
+  UMeshDev um;
+  void* owned_xyz = nullptr;
+  void* owned_conn = nullptr;
+  int* owned_bin_start = nullptr;
+  int* owned_bin_cells = nullptr;
   const void* staged_src = nullptr;   // device-visible alias of the host array
   unsigned char* line_want = nullptr; // lines the next trace will touch (pre-pass output)
   unsigned char* line_have = nullptr; // lines already fetched since the publish
@@ -582,6 +604,13 @@ void preload_composite_kernels();
 void preload_stage_kernels();
 void preload_trace_kernels(const BlockDev& blk);
 void preload_png_kernels();
+void preload_unstructured_kernels();
+
+// unstructured.cu
+cudaError_t launch_utrace_partials(const TraceParams& p, const UMeshDev& u, int sm_count, cudaStream_t s);
+cudaError_t umesh_bounds(const float* xyz, size_t n_points, int* keys_dev, float bmin[3], float bmax[3], int sm_count,
+                         cudaStream_t s);
+cudaError_t umesh_build_bins(UMeshDev& u, int** bin_start_out, int** bin_cells_out, int sm_count, cudaStream_t s);
 
 // png.cu
 unsigned png_slot_stride(int W);

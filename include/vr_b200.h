@@ -113,6 +113,18 @@ VR_API vr_status vr_block_uniform(vr_ctx* ctx, int block_id, const int dims[3],
 VR_API vr_status vr_block_rectilinear(vr_ctx* ctx, int block_id, const int dims[3], const double* x,
                                       const double* y, const double* z, const void* field,
                                       int dtype, int assoc, int where);
+/* N4 -- a domain with an explicit cell set: hexahedra (VTK vertex order) or tetrahedra, point or cell field.
+ * The reference renders such a domain through UnstructuredWrapper::render (VolumeRenderer.cpp:182-221: VTK-m's
+ * ConnectivityProxy::PartialTrace + vtkm_to_partials :141-180) and then renders EVERY domain as partials
+ * (m_has_unstructured, :874-903): an unstructured block is accepted by vr_trace_to_partials / vr_render_partials
+ * only.  xyz: n_points x 3 interleaved; connectivity: n_cells x (8 | 4) point indices.  VR_HOST: copied (f64
+ * coordinates and 64-bit indices are narrowed to f32 / int32); VR_DEVICE: adopted in place (f32 coordinates and
+ * 32-bit connectivity only).  The cell locator (uniform bins over the point bounds) is built on the device by this
+ * call, which synchronises.  Algorithm and how it is pinned without VTK-m: DESIGN.md section 4.5.          */
+enum { VR_TETRA = 10, VR_HEXAHEDRON = 12 }; /* VTK / vtkm::CellShape ids */
+VR_API vr_status vr_block_unstructured(vr_ctx* ctx, int block_id, size_t n_points, const void* xyz, int coord_dtype,
+                                       size_t n_cells, int cell_shape, const void* connectivity, int index_bits,
+                                       const void* field, int dtype, int assoc, int where);
 VR_API vr_status vr_block_free(vr_ctx* ctx, int block_id);
 /* Strided values (ascent_vtkh_data_adapter.cpp:1836-1887: Blueprint arrays whose byte stride is a multiple of the
  * element size -- one component of an interleaved mcarray, a padded array -- which the reference hands to VTK-m
