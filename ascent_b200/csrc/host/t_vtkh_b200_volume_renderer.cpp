@@ -136,6 +136,69 @@ static int run_render(int num_blocks, int W, int H, const char* out)
   return 0;
 }
 
+// the same test body with the single domain handed over as an explicit cell set (hexahedra): the renderer must
+// classify it as unstructured and take path B although there is one domain per rank (VolumeRenderer.cpp:874-903, :470)
+static int run_render_unstructured(int W, int H, const char* out)
+{
+  TestDomain d = CreateTestData(0, 1, 16);
+  const int nx = d.dims[0], ny = d.dims[1], nz = d.dims[2];
+  std::vector<float> xyz((size_t)nx * ny * nz * 3);
+  for (int k = 0; k < nz; ++k)
+    for (int j = 0; j < ny; ++j)
+      for (int i = 0; i < nx; ++i)
+      {
+        const size_t p = ((size_t)k * ny + j) * nx + i;
+        xyz[3 * p + 0] = d.origin[0] + d.spacing[0] * (float)i;
+        xyz[3 * p + 1] = d.origin[1] + d.spacing[1] * (float)j;
+        xyz[3 * p + 2] = d.origin[2] + d.spacing[2] * (float)k;
+      }
+  std::vector<long long> conn;
+  for (int k = 0; k < nz - 1; ++k)
+    for (int j = 0; j < ny - 1; ++j)
+      for (int i = 0; i < nx - 1; ++i)
+      {
+        const long long i0 = ((long long)k * ny + j) * nx + i, up = (long long)nx * ny;
+        const long long c[8] = { i0, i0 + 1, i0 + 1 + nx, i0 + nx, i0 + up, i0 + up + 1, i0 + up + 1 + nx, i0 + up + nx };
+        conn.insert(conn.end(), c, c + 8);
+      }
+  DataSet data_set;
+  data_set.AddDomainUnstructured(0, xyz.size() / 3, xyz.data(), VR_F32, conn.size() / 8, VR_HEXAHEDRON, conn.data(), 64);
+  data_set.AddField(0, "point_data_Float64", d.point_data_Float64.data(), VR_F64, DataSet::Points);
+  Bounds bounds = data_set.GetGlobalBounds();
+  Camera camera;
+  camera.ResetToBounds(bounds);
+  camera.Azimuth(30.f);
+  camera.Elevation(20.f);
+  Render render = MakeRender(W, H, camera, data_set, "volume_unstructured");
+  ColorTable color_map("Cool to Warm");
+  color_map.AddPointAlpha(0.0, 0.01f);
+  color_map.AddPointAlpha(1.0, 0.6f);
+  VolumeRenderer tracer;
+  tracer.SetColorTable(color_map);
+  tracer.SetInput(&data_set);
+  tracer.SetField("point_data_Float64");
+  Scene scene;
+  scene.AddRender(render);
+  scene.AddRenderer(&tracer);
+  scene.Render();
+  const Render& done = scene.GetRenders()[0];
+  FILE* f = fopen(out, "wb");
+  if (!f) return 2;
+  const int hdr[4] = { W, H, 1, tracer.UsedImagePath() ? 1 : 0 };
+  put(f, hdr, sizeof(hdr));
+  put(f, &camera.ToVR(), sizeof(vr_camera));
+  const Range r = tracer.GetRange();
+  const double rr[2] = { r.Min, r.Max };
+  put(f, rr, sizeof(rr));
+  const unsigned long long launches = tracer.KernelLaunches();
+  put(f, &launches, sizeof(launches));
+  put(f, done.GetColorBuffer().data(), done.GetColorBuffer().size() * 4);
+  put(f, done.GetDepthBuffer().data(), done.GetDepthBuffer().size() * 4);
+  fclose(f);
+  std::cout << "render ok: unstructured, path " << (tracer.UsedImagePath() ? "A" : "B") << "\n";
+  return 0;
+}
+
 static int run_host(const char* out)
 {
   FILE* f = fopen(out, "wb");
@@ -232,6 +295,7 @@ int main(int argc, char** argv)
   {
     if (argc >= 3 && !strcmp(argv[1], "host")) return run_host(argv[2]);
     if (argc >= 6 && !strcmp(argv[1], "render")) return run_render(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argv[5]);
+    if (argc >= 5 && !strcmp(argv[1], "render_unstructured")) return run_render_unstructured(atoi(argv[2]), atoi(argv[3]), argv[4]);
     if (argc >= 2 && !strcmp(argv[1], "errors")) return run_errors();
   }
   catch (const std::exception& e)
@@ -239,6 +303,6 @@ int main(int argc, char** argv)
     std::cerr << "exception: " << e.what() << "\n";
     return 3;
   }
-  std::cerr << "usage: host <out> | render <blocks> <W> <H> <out> | errors\n";
+  std::cerr << "usage: host <out> | render <blocks> <W> <H> <out> | render_unstructured <W> <H> <out> | errors\n";
   return 1;
 }

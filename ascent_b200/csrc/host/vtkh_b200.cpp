@@ -167,6 +167,19 @@ void DataSet::AddDomainRectilinear(int domain_id, const int d[3], const double* 
   }
   m_domains.push_back(dom);
 }
+void DataSet::AddDomainUnstructured(int domain_id, size_t n_points, const void* xyz, int coord_dtype, size_t n_cells,
+                                    int cell_shape, const void* connectivity, int index_bits)
+{
+  if (!xyz || !connectivity || n_points == 0 || n_cells == 0) throw Error("DataSet::AddDomainUnstructured: empty mesh");
+  Domain dom;
+  dom.id = domain_id;
+  dom.kind = 2;
+  for (int k = 0; k < 3; ++k) { dom.dims[k] = 0; dom.origin[k] = 0.f; dom.spacing[k] = 0.f; }
+  dom.n_points = n_points; dom.n_cells = n_cells;
+  dom.xyz = xyz; dom.conn = connectivity;
+  dom.coord_dtype = coord_dtype; dom.cell_shape = cell_shape; dom.index_bits = index_bits;
+  m_domains.push_back(dom);
+}
 void DataSet::AddField(int i, const std::string& name, const void* data, int dtype, Assoc assoc, int where)
 {
   if (i < 0 || i >= (int)m_domains.size()) throw Error("DataSet::AddField: no such domain");
@@ -182,6 +195,18 @@ Bounds DataSet::GetDomainBounds(int i) const
 {
   const Domain& d = m_domains.at(i);
   double b[6];
+  if (d.kind == 2)
+  {
+    // coords.GetBounds() of explicit points (f32, as the tracer sees them)
+    float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    for (size_t i = 0; i < d.n_points * 3; ++i)
+    {
+      const float v = d.coord_dtype == VR_F32 ? static_cast<const float*>(d.xyz)[i] : (float)static_cast<const double*>(d.xyz)[i];
+      lo[i % 3] = std::min(lo[i % 3], v);
+      hi[i % 3] = std::max(hi[i % 3], v);
+    }
+    return Bounds(lo[0], hi[0], lo[1], hi[1], lo[2], hi[2]);
+  }
   for (int k = 0; k < 3; ++k)
   {
     if (d.kind == 0)
@@ -217,8 +242,9 @@ Range DataSet::GetGlobalRange(const std::string& field) const
     const Field* f = d.Find(field);
     if (!f) continue;
     if (f->where != VR_HOST) throw Error("GetGlobalRange: field '" + field + "' lives on the device; call SetRange");
-    const size_t n = f->assoc == Points ? (size_t)d.dims[0] * d.dims[1] * d.dims[2]
-                                        : (size_t)(d.dims[0] - 1) * (d.dims[1] - 1) * (d.dims[2] - 1);
+    const size_t n = d.kind == 2 ? (f->assoc == Points ? d.n_points : d.n_cells)
+                     : f->assoc == Points ? (size_t)d.dims[0] * d.dims[1] * d.dims[2]
+                                          : (size_t)(d.dims[0] - 1) * (d.dims[1] - 1) * (d.dims[2] - 1);
     if (f->dtype == VR_F64)
       for (size_t i = 0; i < n; ++i) r.Include(static_cast<const double*>(f->data)[i]);
     else
@@ -358,7 +384,13 @@ void VolumeRenderer::UploadInput()
     const DataSet::Domain& d = m_input->GetDomain(i);
     const DataSet::Field* f = d.Find(m_field_name);
     if (!f) continue;
-    if (d.kind == 0)
+    if (d.kind == 2)
+    {
+      m_has_unstructured = true;
+      m_ctx->Check(vr_block_unstructured(m_ctx->h, d.id, d.n_points, d.xyz, d.coord_dtype, d.n_cells, d.cell_shape, d.conn,
+                                         d.index_bits, f->data, f->dtype, f->assoc, VR_HOST));
+    }
+    else if (d.kind == 0)
       m_ctx->Check(vr_block_uniform(m_ctx->h, d.id, d.dims, d.origin, d.spacing, f->data, f->dtype, f->assoc, f->where));
     else
       m_ctx->Check(vr_block_rectilinear(m_ctx->h, d.id, d.dims, d.ax[0].data(), d.ax[1].data(), d.ax[2].data(), f->data,
@@ -422,7 +454,16 @@ void VolumeRenderer::DoExecute()
     m_comm.allgather(&one, all.data(), sizeof(int));
     for (int v : all) one = std::min(one, v);
   }
-  m_used_path_a = one != 0;
+  // ... and no rank holds an unstructured one (m_has_unstructured, :874-903 -> :470)
+  int unstructured = m_has_unstructured ? 1 : 0;
+  if (m_comm.size > 1)
+  {
+    std::vector<int> all((size_t)m_comm.size);
+    m_comm.allgather(&unstructured, all.data(), sizeof(int));
+    for (int v : all) unstructured = std::max(unstructured, v);
+  }
+  m_has_unstructured = unstructured != 0;
+  m_used_path_a = one != 0 && !m_has_unstructured;
   if (m_used_path_a) RenderOneDomainPerRank();
   else RenderMultipleDomainsPerRank();
 }
@@ -473,6 +514,22 @@ void VolumeRenderer::RenderMultipleDomainsPerRank()
     const vr_camera cam = r.GetCamera().ToVR();
     if (!r.IsCleared())
       m_ctx->Check(vr_canvas_upload(m_ctx->h, W, H, r.GetColorBuffer().data(), r.GetDepthBuffer().data()));
+    if (m_has_unstructured)
+    {
+      // a scene with an unstructured domain: every wrapper emits VolumePartials into ONE list
+      // (UnstructuredWrapper / StructuredWrapper::render, :182-284), PartialCompositor folds it (:580-595)
+      if (r.IsCleared()) m_ctx->Check(vr_canvas_clear(m_ctx->h, W, H));
+      m_ctx->Check(vr_partials_begin(m_ctx->h, W, H));
+      for (int i = 0; i < m_input->GetNumberOfDomains(); ++i)
+      {
+        const DataSet::Domain& d = m_input->GetDomain(i);
+        if (d.Find(m_field_name)) m_ctx->Check(vr_trace_to_partials(m_ctx->h, d.id, &cam, m_sample_dist, rmin, rmax, 1));
+      }
+      m_ctx->Check(vr_partials_composite_to_canvas(m_ctx->h, &cam, r.IsCleared() ? 1 : 0));
+      m_ctx->Check(vr_canvas_download(m_ctx->h, r.GetColorBuffer().data(), r.GetDepthBuffer().data()));
+      r.Touch();
+      continue;
+    }
     // wrapper->render(camera, canvas, partials) per domain (VolumeRenderer.cpp:561-577): the rays of
     // each structured block stay in a dense layer on the device
     m_ctx->Check(vr_layers_begin(m_ctx->h, W, H));

@@ -115,6 +115,10 @@ public:
   // AddDomain(vtkm::cont::DataSet, domain_id): the two coordinate kinds of the hot path
   void AddDomainUniform(int domain_id, const int point_dims[3], const float origin[3], const float spacing[3]);
   void AddDomainRectilinear(int domain_id, const int point_dims[3], const double* x, const double* y, const double* z);
+  // an explicit cell set (vtkm::cont::CellSetSingleType of hexahedra or tetrahedra): caller-owned host arrays,
+  // xyz interleaved; the volume renderer then takes the unstructured route for the whole scene (N4)
+  void AddDomainUnstructured(int domain_id, size_t n_points, const void* xyz, int coord_dtype, size_t n_cells,
+                             int cell_shape /* VR_HEXAHEDRON | VR_TETRA */, const void* connectivity, int index_bits);
   // data_set.AddField(...): caller-owned memory (zero copy on the host side; where = VR_HOST or VR_DEVICE)
   void AddField(int domain_index, const std::string& name, const void* data, int dtype, Assoc assoc, int where = VR_HOST);
   int GetNumberOfDomains() const { return (int)m_domains.size(); }
@@ -127,8 +131,11 @@ public:
   struct Field { std::string name; const void* data; int dtype; Assoc assoc; int where; };
   struct Domain
   {
-    int id; int kind; int dims[3]; float origin[3], spacing[3];
+    int id; int kind; int dims[3]; float origin[3], spacing[3]; // kind: 0 uniform, 1 rectilinear, 2 unstructured
     std::vector<double> ax[3];
+    size_t n_points = 0, n_cells = 0;                           // kind 2
+    const void* xyz = nullptr; const void* conn = nullptr;
+    int coord_dtype = VR_F32, cell_shape = VR_HEXAHEDRON, index_bits = 32;
     std::vector<Field> fields;
     const Field* Find(const std::string& n) const;
   };
@@ -252,6 +259,7 @@ protected:
   void RenderMultipleDomainsPerRank();
   void CorrectOpacity();
   void UploadInput();
+  bool m_has_unstructured = false; // SetInput's classification (VolumeRenderer.cpp:874-903)
   std::shared_ptr<Context> m_ctx;
   DataSet* m_input = nullptr;
   bool m_uploaded = false;

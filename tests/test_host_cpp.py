@@ -145,6 +145,30 @@ def test_reference_volume_test_body_against_oracle(exe, tmp_path, num_blocks):
 
 
 @pytest.mark.gpu
+def test_unstructured_domain_forces_path_b(exe, tmp_path):
+    """VolumeRenderer::SetInput's classification (VolumeRenderer.cpp:874-903): one domain per rank, but unstructured
+    -> m_has_unstructured -> RenderMultipleDomainsPerRank with the unstructured wrapper; against the N4 oracle"""
+    out = str(tmp_path / "u.bin")
+    r = subprocess.run([exe, "render_unstructured", "384", "320", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    W, H, nb, path_a, cam, rmin, rmax, launches, rgba, depth = read_render(out)
+    assert not path_a and launches > 0
+    dom = create_test_data(0, 1, 16)
+    pts, conn = datasets.structured_to_hexes(dom["dims"], dom["origin"], dom["spacing"])
+    gb = datasets.domain_bounds(dom)
+    t = color_table.ColorTable("cool to warm")
+    t.add_point_alpha(0.0, 0.01)
+    t.add_point_alpha(1.0, 0.6)
+    sc = dict(points=pts, conn=conn, field=dom["field"].reshape(-1), W=W, H=H, cam=cam,
+              lut=t.corrected_opacity(100).lut(), sample_dist=O.sample_distance(gb, 100), rmin=np.float32(rmin),
+              rmax=np.float32(rmax))
+    _, ref, _ = scenes.oracle_unstructured_path_b(sc)
+    d = np.abs(rgba - ref).max(axis=1)
+    assert (d <= 1 / 255).mean() >= 0.999 and d.max() <= 3 / 255
+    assert (ref[:, 3] > 0).sum() > 10000 and np.array_equal(rgba[:, 3] > 0, ref[:, 3] > 0)
+
+
+@pytest.mark.gpu
 def test_error_behaviour(exe):
     r = subprocess.run([exe, "errors"], capture_output=True, text=True)
     assert r.returncode == 0 and "errors ok" in r.stdout, r.stdout + r.stderr
