@@ -37,7 +37,7 @@ SYMBOLS = [
     "vr_sample_distance", "vr_visibility_order", "vr_find_subset", "vr_synth_braid_dev",
     "vr_camera_default", "vr_camera_reset_to_bounds", "vr_camera_azimuth", "vr_camera_elevation",
     "vr_camera_zoom", "vr_camera_cinema", "vr_color_table_sample", "vr_correct_opacity", "vr_comm_timeline",
-    "vr_comm_join", "vr_comm_render_frames", "vr_comm_connect_local", "vr_field_gather_strided", "vr_field_free", "vr_radixk_schedule", "vr_canvas_encode_png", "vr_png_bound", "vr_block_unstructured",
+    "vr_comm_join", "vr_comm_render_frames", "vr_comm_connect_local", "vr_field_gather_strided", "vr_field_free", "vr_radixk_schedule", "vr_canvas_encode_png", "vr_png_bound", "vr_block_unstructured", "vr_canvas_download_rect",
 ]
 
 
@@ -148,6 +148,7 @@ def load():
         "vr_field_free": (C.c_int, [vp, vp]),
         "vr_canvas_encode_png": (C.c_int, [vp, fp, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
         "vr_png_bound": (C.c_size_t, [C.c_int, C.c_int]),
+        "vr_canvas_download_rect": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
         "vr_block_unstructured": (C.c_int, [vp, C.c_int, C.c_size_t, vp, C.c_int, C.c_size_t, C.c_int, vp, C.c_int, vp,
                                             C.c_int, C.c_int, C.c_int]),
         "vr_radixk_schedule": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
@@ -377,6 +378,11 @@ class Context:
         depth = np.empty(H * W, np.float32) if depth is None else depth
         self._ck(self.lib.vr_canvas_download(self.h, rgba.ctypes.data, depth.ctypes.data))
         return rgba, depth
+
+    def canvas_download_rect(self, rect, rgba, depth):
+        """vr_canvas_download_rect: rect = (x0, y0, x1, y1); rgba [W*H, 4] / depth [W*H] full-frame host arrays"""
+        self._ck(self.lib.vr_canvas_download_rect(self.h, int(rect[0]), int(rect[1]), int(rect[2]), int(rect[3]),
+                                                  rgba.ctypes.data, depth.ctypes.data))
 
     def canvas_blend_background(self, bg):
         b = (C.c_float * 4)(*[float(x) for x in bg])

@@ -468,6 +468,25 @@ void VolumeRenderer::DoExecute()
   else RenderMultipleDomainsPerRank();
 }
 
+// A render whose host canvas is still the cleared canvas (Render::ClearCanvas) only needs the pixels inside the
+// screen footprint of the GLOBAL bounds back: everything else the frame leaves as Canvas::Clear left it.
+void VolumeRenderer::DownloadCanvas(Render& r, const vr_camera& cam, bool host_canvas_is_clear)
+{
+  const int W = r.GetWidth(), H = r.GetHeight();
+  if (!host_canvas_is_clear)
+  {
+    m_ctx->Check(vr_canvas_download(m_ctx->h, r.GetColorBuffer().data(), r.GetDepthBuffer().data()));
+    return;
+  }
+  double gb[6];
+  m_bounds.ToArray(gb);
+  int sub[4];
+  vr_find_subset(&cam, W, H, gb, sub);
+  const int x0 = sub[0] & ~3, x1 = std::min(W, (sub[0] + sub[2] + 3) & ~3);
+  m_ctx->Check(vr_canvas_download_rect(m_ctx->h, x0, sub[1], x1, sub[1] + sub[3], r.GetColorBuffer().data(),
+                                       r.GetDepthBuffer().data()));
+}
+
 void VolumeRenderer::RenderOneDomainPerRank()
 {
   const DataSet::Domain& d = m_input->GetDomain(0);
@@ -480,6 +499,7 @@ void VolumeRenderer::RenderOneDomainPerRank()
   {
     const int W = r.GetWidth(), H = r.GetHeight();
     const vr_camera cam = r.GetCamera().ToVR();
+    const bool was_clear = r.IsCleared();
     if (r.IsCleared() && m_do_composite)
     {
       // Canvas::Clear + RenderCells + Image::Init + ImageToCanvas: one launch
@@ -498,7 +518,7 @@ void VolumeRenderer::RenderOneDomainPerRank()
         m_ctx->Check(vr_image_to_canvas_dev(m_ctx->h, static_cast<const uint8_t*>(rgba8), static_cast<const float*>(depth)));
       }
     }
-    m_ctx->Check(vr_canvas_download(m_ctx->h, r.GetColorBuffer().data(), r.GetDepthBuffer().data()));
+    DownloadCanvas(r, cam, was_clear && m_do_composite);
     r.Touch();
   }
 }
@@ -526,7 +546,7 @@ void VolumeRenderer::RenderMultipleDomainsPerRank()
         if (d.Find(m_field_name)) m_ctx->Check(vr_trace_to_partials(m_ctx->h, d.id, &cam, m_sample_dist, rmin, rmax, 1));
       }
       m_ctx->Check(vr_partials_composite_to_canvas(m_ctx->h, &cam, r.IsCleared() ? 1 : 0));
-      m_ctx->Check(vr_canvas_download(m_ctx->h, r.GetColorBuffer().data(), r.GetDepthBuffer().data()));
+      DownloadCanvas(r, cam, r.IsCleared());
       r.Touch();
       continue;
     }
@@ -544,7 +564,7 @@ void VolumeRenderer::RenderMultipleDomainsPerRank()
                                            r.IsCleared() ? 0 : 1));
     // PartialCompositor::composite + partials_to_canvas (VolumeRenderer.cpp:580-595), one kernel
     m_ctx->Check(vr_layers_composite_to_canvas(m_ctx->h, &cam, r.IsCleared() ? 1 : 0));
-    m_ctx->Check(vr_canvas_download(m_ctx->h, r.GetColorBuffer().data(), r.GetDepthBuffer().data()));
+    DownloadCanvas(r, cam, r.IsCleared());
     r.Touch();
   }
 }

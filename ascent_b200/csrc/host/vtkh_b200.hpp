@@ -259,6 +259,7 @@ protected:
   void RenderMultipleDomainsPerRank();
   void CorrectOpacity();
   void UploadInput();
+  void DownloadCanvas(Render& r, const vr_camera& cam, bool host_canvas_is_clear);
   bool m_has_unstructured = false; // SetInput's classification (VolumeRenderer.cpp:874-903)
   std::shared_ptr<Context> m_ctx;
   DataSet* m_input = nullptr;

@@ -784,6 +784,31 @@ extern "C" vr_status vr_canvas_download(vr_ctx* ctx, float* rgba, float* depth)
   return comm_check_errors(ctx);
 }
 
+// Only the rectangle [x0, x1) x [y0, y1) of the canvas, into the same pixels of FULL-FRAME host buffers: a frame
+// that started from Canvas::Clear differs from the cleared canvas (colour 0, depth 1.001 -- which the caller's
+// host canvas already holds after Render::ClearCanvas) only inside the screen footprint of the data, and the
+// 20 B/pixel float canvas is what dominates the read-back (c2: 41 MB for a 10 MB footprint).
+extern "C" vr_status vr_canvas_download_rect(vr_ctx* ctx, int x0, int y0, int x1, int y1, float* rgba, float* depth)
+{
+  VR_ENTER_RO(ctx);
+  REQUIRE(ctx->W > 0, "vr_canvas_download_rect: no canvas yet");
+  const int W = ctx->W, H = ctx->H;
+  x0 = std::max(0, std::min(x0, W)); x1 = std::max(x0, std::min(x1, W));
+  y0 = std::max(0, std::min(y0, H)); y1 = std::max(y0, std::min(y1, H));
+  if (x1 > x0 && y1 > y0)
+  {
+    const size_t at = (size_t)y0 * W + x0;
+    if (rgba)
+      CK(cudaMemcpy2DAsync(rgba + 4 * at, (size_t)W * sizeof(float4), ctx->canvas_rgba + at, (size_t)W * sizeof(float4),
+                           (size_t)(x1 - x0) * sizeof(float4), (size_t)(y1 - y0), cudaMemcpyDeviceToHost, ctx->stream));
+    if (depth)
+      CK(cudaMemcpy2DAsync(depth + at, (size_t)W * sizeof(float), ctx->canvas_depth + at, (size_t)W * sizeof(float),
+                           (size_t)(x1 - x0) * sizeof(float), (size_t)(y1 - y0), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return comm_check_errors(ctx);
+}
+
 extern "C" vr_status vr_canvas_blend_background(vr_ctx* ctx, const float bg_rgba[4])
 {
   VR_ENTER(ctx);

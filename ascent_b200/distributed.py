@@ -560,8 +560,11 @@ def _e2e(ctx, dist, stream, blocks, mine, fields, sp, cam, W, H, rmin, rmax, ren
         h = torch.empty(nvox, dtype=torch.float32, pin_memory=True)
         h.copy_(fields[i])
         host[i] = h.numpy()
-    rgba_h = torch.zeros(H * W * 4, dtype=torch.float32, pin_memory=True).numpy() if rank == 0 else None
-    depth_h = torch.zeros(H * W, dtype=torch.float32, pin_memory=True).numpy() if rank == 0 else None
+    # rank 0's host canvas: the cleared canvas (Render::ClearCanvas); every frame replaces its footprint only
+    rgba_h = torch.zeros(H * W * 4, dtype=torch.float32, pin_memory=True).numpy().reshape(-1, 4) if rank == 0 else None
+    depth_h = torch.full((H * W,), 1.001, dtype=torch.float32, pin_memory=True).numpy() if rank == 0 else None
+    import bench as bench_mod
+    rect = bench_mod.footprint_rect(cam, W, H, sp["bounds"])
 
     def frame(staged):
         for i in mine:
@@ -572,7 +575,7 @@ def _e2e(ctx, dist, stream, blocks, mine, fields, sp, cam, W, H, rmin, rmax, ren
         render()
         composite()
         if rank == 0:
-            ctx.canvas_download(W, H, rgba_h, depth_h)
+            ctx.canvas_download_rect(rect, rgba_h, depth_h)
         else:
             ctx.synchronize()
 
@@ -601,6 +604,10 @@ def _e2e(ctx, dist, stream, blocks, mine, fields, sp, cam, W, H, rmin, rmax, ren
                 moved[name] = int(m.item())
     best = min(modes, key=modes.get)
     dt = modes[best]
+    same = None
+    if rank == 0:
+        full_r, full_d = ctx.canvas_download(W, H)
+        same = bool(np.array_equal(full_r, rgba_h) and np.array_equal(full_d, depth_h))
     # restore the zero-copy device blocks
     for i in mine:
         b = blocks[i]
@@ -608,8 +615,11 @@ def _e2e(ctx, dist, stream, blocks, mine, fields, sp, cam, W, H, rmin, rmax, ren
                           dtype=_lib.VR_F32)
     h2d = {"copy": nvox * 4 * len(blocks), "staged": moved.get("staged", nvox * 4 * len(blocks))}
     return {"value": W * H / dt / 1e6, "unit": "Mrays/s", "ms_per_step": dt * 1e3, "mode": best,
-            "h2d_bytes_per_step": h2d[best], "d2h_bytes_per_step": W * H * 20,
+            "h2d_bytes_per_step": h2d[best],
+            "d2h_bytes_per_step": max(0, rect[2] - rect[0]) * max(0, rect[3] - rect[1]) * 20,
+            "d2h_full_canvas_bytes": W * H * 20, "host_canvas_equals_full_download": same,
             "modes_ms_per_step": {k: v * 1e3 for k, v in modes.items()}, "modes_h2d_bytes": h2d,
             "what": "every rank: vr_block_uniform(pinned host field) per local block (copy: VR_HOST dense upload; "
                     "staged: VR_HOST_STAGED, only the 128-byte lines the rays touch cross PCIe), render, P2P "
-                    "composite; rank 0: vr_canvas_download.  The faster mode is reported"}
+                    "composite; rank 0: vr_canvas_download_rect (the frame's screen footprint into a host canvas that holds the "
+                    "cleared canvas elsewhere; checked against a full download).  The faster mode is reported"}

@@ -152,6 +152,12 @@ VR_API vr_status vr_canvas_clear(vr_ctx* ctx, int width, int height); /* colour 
 VR_API vr_status vr_canvas_upload(vr_ctx* ctx, int width, int height, const float* rgba,
                                   const float* depth);
 VR_API vr_status vr_canvas_download(vr_ctx* ctx, float* rgba, float* depth); /* syncs */
+/* The same for the pixel rectangle [x0, x1) x [y0, y1) only, written into the same pixels of full-frame host
+ * buffers.  A frame that started from Canvas::Clear equals the cleared canvas (colour 0, depth 1.001 -- what the
+ * caller's host canvas holds after Render::ClearCanvas, Render.cpp) outside the screen footprint of the data:
+ * vr_find_subset of the GLOBAL bounds (all ranks' domains, VolumeRenderer::PreExecute has them), united with the
+ * previous frame's footprint when the camera moved.  Syncs.                                              */
+VR_API vr_status vr_canvas_download_rect(vr_ctx* ctx, int x0, int y0, int x1, int y1, float* rgba, float* depth);
 VR_API vr_status vr_canvas_ptrs(vr_ctx* ctx, void** rgba_dev, void** depth_dev);
 /* Frame epilogue on the device (what Scene::Render does with each finished canvas on rank 0,
  * Scene.cpp:236-243, when annotations are off):

@@ -1032,3 +1032,32 @@ def test_png_encoded_on_the_device(ctx, W, H, bg):
     # near the raw size (Huffman-only, like the reference's lodepng settings)
     assert len(png) < (W * H * 4 // 2 if W == 1920 else W * H * 4)
     ctx.block_free(0)
+
+
+@pytest.mark.parametrize("W,H,az", [(640, 360, 0.0), (203, 77, 40.0)])
+def test_footprint_read_back_equals_the_full_canvas(ctx, W, H, az):
+    """vr_canvas_download_rect: a frame that started from Canvas::Clear differs from the cleared canvas only inside
+    the screen footprint of the data, so reading back that rectangle into a host canvas that holds the cleared canvas
+    (Render::ClearCanvas) gives the whole frame -- also when the camera moves, if the previous footprint is included"""
+    import bench
+    dom = datasets.braid_uniform(20, dtype=np.float32)
+    b = datasets.domain_bounds(dom)
+    lut = color_table.parse_color_table(scenes.RAMP_TF).corrected_opacity(100).lut()
+    sd = O.sample_distance(b, 100)
+    rmin, rmax = scenes.field_range([dom])
+    ctx.set_tf(lut)
+    ctx.block_from_domain(0, dom)
+    host_rgba, host_depth = O.new_canvas(W, H)
+    prev = None
+    for k in range(3):
+        cam = O.camera_reset_to_bounds(b)
+        O.camera_azimuth(cam, az + 25.0 * k)
+        O.camera_zoom(cam, 1.0 + 0.4 * k)
+        ctx.trace_to_image(0, cam, W, H, sd, rmin, rmax, write_canvas=True)
+        rect = bench.footprint_rect(cam, W, H, [b])
+        ctx.canvas_download_rect(bench.union_rect(prev, rect), host_rgba, host_depth)
+        prev = rect
+        full_rgba, full_depth = ctx.canvas_download(W, H)
+        assert (rect[2] - rect[0]) * (rect[3] - rect[1]) < W * H
+        assert np.array_equal(host_rgba, full_rgba) and np.array_equal(host_depth, full_depth), k
+    ctx.block_free(0)
