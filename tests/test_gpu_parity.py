@@ -1052,7 +1052,7 @@ def test_footprint_read_back_equals_the_full_canvas(ctx, W, H, az):
     for k in range(3):
         cam = O.camera_reset_to_bounds(b)
         O.camera_azimuth(cam, az + 25.0 * k)
-        O.camera_zoom(cam, 1.0 + 0.4 * k)
+        O.camera_zoom(cam, 0.1 * k)  # (vtkm zoom: factor 4^z)
         ctx.trace_to_image(0, cam, W, H, sd, rmin, rmax, write_canvas=True)
         rect = bench.footprint_rect(cam, W, H, [b])
         ctx.canvas_download_rect(bench.union_rect(prev, rect), host_rgba, host_depth)
