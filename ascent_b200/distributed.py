@@ -452,15 +452,17 @@ def run_bench(args, wl, bench):
                 "per_rank_ms": {"columns": ["total", "render_alone", "composite_in_step", "composite_aligned"],
                                 "rows": per_rank},
                 "nvlink": {"bytes_into_rank0_per_frame": nv_bytes, "pulled": pulled, "pushed_into_rank0": pushed,
-                           "achieved_gbs": nv_bytes / (comp_ms * 1e-3) / 1e9, "peak_gbs": 770.0,
+                           "achieved_gbs": nv_bytes / (ms * 1e-3) / 1e9, "peak_gbs": 770.0,
                            "peak_source": "measured peer copy per direction (B200_PROFILING.md)",
-                           "how": "bytes from the frame's geometry (screen rectangles), time = composite_ms_per_frame",
+                           "how": "bytes from the frame's geometry (screen rectangles); time = the whole frame (ms_per_step): "
+                                  "pushed pixels / layer entries cross NVLink while the trace is still running, so the "
+                                  "exchange kernel's own duration no longer contains the transfer",
                            # hardware counters (NVML NVLINK_THROUGHPUT_DATA_RX/TX, payload, KiB granularity) read on
                            # every rank around the K timed frames of the serial order: bytes per frame per GPU
                            "measured": None if nv_rows[0][0] < 0 else {
                                "rx_bytes_per_frame_by_rank": [round(r[0]) for r in nv_rows],
                                "tx_bytes_per_frame_by_rank": [round(r[1]) for r in nv_rows],
-                               "rank0_rx_gbs": nv_rows[0][0] / (comp_ms * 1e-3) / 1e9,
+                               "rank0_rx_gbs": nv_rows[0][0] / (ms * 1e-3) / 1e9,
                                "source": "NVML field values 139/138 summed over links, delta over the timed frames"}},
                 "nccl_baseline": nccl_base, "exchange_timeline": timeline,
                 "t1_same_run": t1,
