@@ -111,6 +111,9 @@ static int run_render(int num_blocks, int W, int H, const char* out)
   tracer.SetColorTable(color_map);
   tracer.SetInput(&data_set);
   tracer.SetField("point_data_Float64");
+  tracer.SetEncodePNG(true);
+  const float bg[4] = { 0.2f, 0.3f, 0.4f, 1.f };
+  render.SetBackgroundColor(bg);
 
   Scene scene;
   scene.AddRender(render);
@@ -118,6 +121,13 @@ static int run_render(int num_blocks, int W, int H, const char* out)
   scene.Render();
 
   const Render& done = scene.GetRenders()[0];
+  {
+    // Render::Save: the PNG encoded on the device, written next to the raw output
+    FILE* pf = fopen((std::string(out) + ".png").c_str(), "wb");
+    if (!pf) return 2;
+    put(pf, done.GetPNG().data(), done.GetPNG().size());
+    fclose(pf);
+  }
   FILE* f = fopen(out, "wb");
   if (!f) return 2;
   const int hdr[4] = { W, H, num_blocks, tracer.UsedImagePath() ? 1 : 0 };

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -260,6 +261,16 @@ void Render::ClearCanvas()
   std::fill(m_depth->begin(), m_depth->end(), 1.001f);
   m_cleared = true;
 }
+void Render::Save() const
+{
+  if (!m_png || m_png->empty()) throw Error("Render::Save: no PNG encoded (VolumeRenderer::SetEncodePNG)");
+  const std::string path = m_name + ".png";
+  FILE* f = std::fopen(path.c_str(), "wb");
+  if (!f) throw Error("Render::Save: cannot open " + path);
+  const size_t n = std::fwrite(m_png->data(), 1, m_png->size(), f);
+  std::fclose(f);
+  if (n != m_png->size()) throw Error("Render::Save: short write to " + path);
+}
 Render MakeRender(int width, int height, const Camera& camera, const DataSet&, const std::string& image_name)
 {
   if (width <= 0 || height <= 0) throw Error("MakeRender: bad image size");
@@ -270,6 +281,7 @@ Render MakeRender(int width, int height, const Camera& camera, const DataSet&, c
   r.m_name = image_name;
   r.m_rgba = std::make_shared<std::vector<float>>((size_t)width * height * 4, 0.f);
   r.m_depth = std::make_shared<std::vector<float>>((size_t)width * height, 1.001f);
+  r.m_png = std::make_shared<std::vector<uint8_t>>();
   return r;
 }
 
@@ -473,6 +485,15 @@ void VolumeRenderer::DoExecute()
 void VolumeRenderer::DownloadCanvas(Render& r, const vr_camera& cam, bool host_canvas_is_clear)
 {
   const int W = r.GetWidth(), H = r.GetHeight();
+  if (m_encode_png && m_comm.rank == 0)
+  {
+    // Render::RenderBackground + PNGEncoder::Encode on the device canvas: only the file crosses PCIe
+    std::vector<uint8_t>& file = r.GetPNG();
+    file.resize(vr_png_bound(W, H));
+    size_t n = 0;
+    m_ctx->Check(vr_canvas_encode_png(m_ctx->h, r.GetBackgroundColor(), file.data(), file.size(), &n));
+    file.resize(n);
+  }
   if (!host_canvas_is_clear)
   {
     m_ctx->Check(vr_canvas_download(m_ctx->h, r.GetColorBuffer().data(), r.GetDepthBuffer().data()));

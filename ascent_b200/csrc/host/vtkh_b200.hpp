@@ -160,12 +160,21 @@ public:
   void ClearCanvas(); // Canvas::Clear: colour 0, depth 1.001
   bool IsCleared() const { return m_cleared; }
   void Touch() { m_cleared = false; }
+  // Render::RenderBackground + Render::Save (Render.cpp:277-312): the PNG the volume renderer encoded on the device
+  // for this render (VolumeRenderer::SetEncodePNG), over the background colour; Save writes `<image name>.png`
+  void SetBackgroundColor(const float bg[4]) { for (int k = 0; k < 4; ++k) m_bg[k] = bg[k]; }
+  const float* GetBackgroundColor() const { return m_bg; }
+  std::vector<uint8_t>& GetPNG() { return *m_png; }
+  const std::vector<uint8_t>& GetPNG() const { return *m_png; }
+  void Save() const; // throws if no PNG has been encoded
 private:
   friend Render MakeRender(int, int, const Camera&, const DataSet&, const std::string&);
   int m_width = 0, m_height = 0;
   Camera m_camera;
   std::string m_name;
   std::shared_ptr<std::vector<float>> m_rgba, m_depth; // shared like vtkm ArrayHandles: copies alias
+  std::shared_ptr<std::vector<uint8_t>> m_png;
+  float m_bg[4] = { 0.f, 0.f, 0.f, 1.f };
   bool m_cleared = true;
 };
 Render MakeRender(int width, int height, const Camera& camera, const DataSet& data_set, const std::string& image_name);
@@ -240,6 +249,8 @@ public:
   void SetField(const std::string& field_name) { m_field_name = field_name; }
   void SetRange(const Range& range) { m_range = range; }
   void SetDoComposite(bool do_composite) { m_do_composite = do_composite; }
+  // Scene::Render's epilogue (RenderBackground + Save) on the device: each finished render also gets its PNG file
+  void SetEncodePNG(bool on) { m_encode_png = on; }
   void AddRender(Render& render) { m_renders.push_back(render); }
   void SetRenders(const std::vector<Render>& renders) { m_renders = renders; }
   std::vector<Render> GetRenders() const { return m_renders; }
@@ -272,6 +283,7 @@ protected:
   int m_num_samples = 100;
   float m_sample_dist = 0.f;
   bool m_do_composite = true;
+  bool m_encode_png = false;
   bool m_used_path_a = false;
   Comm m_comm;
   bool m_comm_connected = false;

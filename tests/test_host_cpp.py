@@ -142,6 +142,13 @@ def test_reference_volume_test_body_against_oracle(exe, tmp_path, num_blocks):
     d = np.abs(rgba - ref).max(axis=1)
     assert (d <= 1 / 255).mean() >= 0.999 and d.max() <= 3 / 255
     assert (ref[:, 3] > 0).sum() > 10000 and np.array_equal(rgba[:, 3] > 0, ref[:, 3] > 0)
+    # Render::Save: the PNG the renderer encoded on the device = RenderBackground + PNGEncoder's conversion of the
+    # very canvas that came back (oracle's epilogue), rows flipped
+    from PIL import Image
+    png = np.array(Image.open(out + ".png").convert("RGBA"))
+    c = np.ascontiguousarray(rgba, np.float32).copy()
+    O.blend_background(c, (0.2, 0.3, 0.4, 1.0))
+    assert np.array_equal(png, O.encode_rgba8(c, W, H, flip=True))
 
 
 @pytest.mark.gpu
