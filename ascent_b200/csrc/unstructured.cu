@@ -14,8 +14,7 @@
 //   cell id on shared faces); same classification, blend and early termination as the structured sampler; one
 //   partial per ray with alpha >= 0.001, depth = exit distance.
 // Cells are found through uniform bins over the point bounds (ceil(cbrt(n_cells)) per axis), built on the device
-// at publish time: bounds by atomic min/max, per-bin counts (+ every cell's box), a scan, a fill, a per-bin sort by
-// cell id (so the first containing candidate is the lowest-numbered one).  Compiled --fmad=false like the
+// at publish time: bounds by atomic min/max, per-bin counts, a scan, a fill.  Compiled --fmad=false like the
 // sampler: every comparison and every Newton step rounds like the oracle, so partials are bit-identical.
 #include <cmath>
 #include <cstring>
@@ -66,24 +65,27 @@ __device__ __forceinline__ bool solve3(const float a[3], const float b[3], const
 template <int SHAPE>
 __device__ __forceinline__ bool pcoords(const UMeshDev& U, int c, const float p[3], float rst[3])
 {
-  // padded-bounds pre-test from the cell's stored box (the same min / max of its points the oracle computes): most
-  // candidates of a bin end here, 24 contiguous bytes instead of a gather of all their vertices
-  const float* box = U.cell_box + 6 * (size_t)c;
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-  {
-    const float lo = __ldg(box + a), hi = __ldg(box + 3 + a);
-    const float pad = (hi - lo) * kTol;
-    if (p[a] < lo - pad || p[a] > hi + pad) return false;
-  }
   const int* cn = U.conn + (size_t)c * SHAPE;
   float v[SHAPE][3];
+  float lo[3] = { __int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000) };
+  float hi[3] = { __int_as_float(0xff800000), __int_as_float(0xff800000), __int_as_float(0xff800000) };
 #pragma unroll
   for (int k = 0; k < SHAPE; ++k)
   {
     const float* q = U.xyz + 3 * (size_t)__ldg(cn + k);
 #pragma unroll
-    for (int a = 0; a < 3; ++a) v[k][a] = __ldg(q + a);
+    for (int a = 0; a < 3; ++a)
+    {
+      v[k][a] = __ldg(q + a);
+      lo[a] = fminf(lo[a], v[k][a]);
+      hi[a] = fmaxf(hi[a], v[k][a]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    const float pad = (hi[a] - lo[a]) * kTol;
+    if (p[a] < lo[a] - pad || p[a] > hi[a] + pad) return false;
   }
   if (SHAPE == 4)
   {
@@ -127,20 +129,22 @@ __device__ __forceinline__ bool pcoords(const UMeshDev& U, int c, const float p[
   return r >= -kTol && r <= 1.f + kTol && s >= -kTol && s <= 1.f + kTol && t >= -kTol && t <= 1.f + kTol;
 }
 
-// the lowest-numbered cell that contains p, or -1: bin lists are sorted by cell id at build time, so the first
-// candidate that contains the point is the answer
+// the lowest-numbered cell that contains p (bin lists are unordered: every candidate is tested), or -1
 template <int SHAPE>
 __device__ __forceinline__ int locate(const UMeshDev& U, const float p[3], float rst[3])
 {
   const int bx = bin_of(U, 0, p[0]), by = bin_of(U, 1, p[1]), bz = bin_of(U, 2, p[2]);
   const size_t b = ((size_t)bz * U.g[1] + by) * U.g[0] + bx;
   const int k0 = __ldg(U.bin_start + b), k1 = __ldg(U.bin_start + b + 1);
+  int found = -1;
   for (int k = k0; k < k1; ++k)
   {
     const int c = __ldg(U.bin_cells + k);
-    if (pcoords<SHAPE>(U, c, p, rst)) return c;
+    if (found >= 0 && c > found) continue;
+    float q[3];
+    if (pcoords<SHAPE>(U, c, p, q)) { found = c; rst[0] = q[0]; rst[1] = q[1]; rst[2] = q[2]; }
   }
-  return -1;
+  return found;
 }
 
 template <typename FT, int SHAPE, int ASSOC>
@@ -341,8 +345,7 @@ __global__ void ubounds_kernel(const float* __restrict__ xyz, size_t n_points, i
 
 // pass 0: count the cells per bin; pass 1: list them (cursor = running copy of bin_start)
 template <int SHAPE, bool FILL>
-__global__ void ubins_kernel(const __grid_constant__ UMeshDev U, int* __restrict__ count_or_cursor, int* __restrict__ bin_cells,
-                             float* __restrict__ cell_box)
+__global__ void ubins_kernel(const __grid_constant__ UMeshDev U, int* __restrict__ count_or_cursor, int* __restrict__ bin_cells)
 {
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < U.n_cells; c += gridDim.x * blockDim.x)
   {
@@ -353,8 +356,6 @@ __global__ void ubins_kernel(const __grid_constant__ UMeshDev U, int* __restrict
       const float* q = U.xyz + 3 * (size_t)U.conn[(size_t)c * SHAPE + k];
       for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], q[a]); hi[a] = fmaxf(hi[a], q[a]); }
     }
-    if (!FILL)
-      for (int a = 0; a < 3; ++a) { cell_box[6 * (size_t)c + a] = lo[a]; cell_box[6 * (size_t)c + 3 + a] = hi[a]; }
     int b0[3], b1[3];
     for (int a = 0; a < 3; ++a) { b0[a] = bin_of(U, a, lo[a]); b1[a] = bin_of(U, a, hi[a]); }
     for (int z = b0[2]; z <= b1[2]; ++z)
@@ -365,23 +366,6 @@ __global__ void ubins_kernel(const __grid_constant__ UMeshDev U, int* __restrict
           const int at = atomicAdd(count_or_cursor + b, 1);
           if (FILL) bin_cells[at] = c;
         }
-  }
-}
-
-// every bin's list in ascending cell order (the fill's atomics leave them in arrival order): insertion sort, one
-// thread per bin -- lists hold the few cells whose boxes overlap the bin
-__global__ void usort_kernel(const int* __restrict__ bin_start, int* __restrict__ bin_cells, size_t n_bins)
-{
-  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_bins; b += (size_t)gridDim.x * blockDim.x)
-  {
-    const int k0 = bin_start[b], k1 = bin_start[b + 1];
-    for (int i = k0 + 1; i < k1; ++i)
-    {
-      const int v = bin_cells[i];
-      int j = i - 1;
-      while (j >= k0 && bin_cells[j] > v) { bin_cells[j + 1] = bin_cells[j]; --j; }
-      bin_cells[j + 1] = v;
-    }
   }
 }
 
@@ -463,7 +447,6 @@ void preload_unstructured_kernels()
   preload_kernel(ubins_kernel<8, true>);
   preload_kernel(ubins_kernel<4, false>);
   preload_kernel(ubins_kernel<4, true>);
-  preload_kernel(usort_kernel);
   preload_kernel(uscan_kernel);
   cudaGetLastError();
 }
@@ -498,47 +481,37 @@ cudaError_t umesh_bounds(const float* xyz, size_t n_points, int* keys_dev, float
 }
 
 // bins: u.g / u.ginv / u.bmin / u.bmax set by the caller; allocates and fills u.bin_start / u.bin_cells
-cudaError_t umesh_build_bins(UMeshDev& u, int** bin_start_out, int** bin_cells_out, float** cell_box_out, int sm_count,
-                             cudaStream_t s)
+cudaError_t umesh_build_bins(UMeshDev& u, int** bin_start_out, int** bin_cells_out, int sm_count, cudaStream_t s)
 {
   const size_t nb = (size_t)u.g[0] * u.g[1] * u.g[2];
   int *counts = nullptr, *starts = nullptr, *cells = nullptr;
-  float* boxes = nullptr;
   cudaError_t e = cudaMalloc(&counts, (nb + 1) * sizeof(int));
   if (e != cudaSuccess) return e;
   e = cudaMalloc(&starts, (nb + 1) * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&boxes, (size_t)u.n_cells * 6 * sizeof(float));
-  if (e != cudaSuccess) { cudaFree(counts); cudaFree(starts); return e; }
+  if (e != cudaSuccess) { cudaFree(counts); return e; }
   cudaMemsetAsync(counts, 0, (nb + 1) * sizeof(int), s);
   int grid = (u.n_cells + 255) / 256;
   if (grid > sm_count * 8) grid = sm_count * 8;
   if (grid < 1) grid = 1;
-  if (u.shape == 8) ubins_kernel<8, false><<<grid, 256, 0, s>>>(u, counts, nullptr, boxes);
-  else ubins_kernel<4, false><<<grid, 256, 0, s>>>(u, counts, nullptr, boxes);
+  if (u.shape == 8) ubins_kernel<8, false><<<grid, 256, 0, s>>>(u, counts, nullptr);
+  else ubins_kernel<4, false><<<grid, 256, 0, s>>>(u, counts, nullptr);
   uscan_kernel<<<1, 1024, 0, s>>>(counts, starts, nb);
   int total = 0;
   e = cudaMemcpyAsync(&total, starts + nb, sizeof(int), cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   if (e == cudaSuccess) e = cudaMalloc(&cells, (size_t)(total > 0 ? total : 1) * sizeof(int));
-  if (e != cudaSuccess) { cudaFree(counts); cudaFree(starts); cudaFree(boxes); return e; }
+  if (e != cudaSuccess) { cudaFree(counts); cudaFree(starts); return e; }
   // the counts buffer becomes the fill cursor
   cudaMemcpyAsync(counts, starts, (nb + 1) * sizeof(int), cudaMemcpyDeviceToDevice, s);
-  if (u.shape == 8) ubins_kernel<8, true><<<grid, 256, 0, s>>>(u, counts, cells, nullptr);
-  else ubins_kernel<4, true><<<grid, 256, 0, s>>>(u, counts, cells, nullptr);
-  {
-    size_t sgrid = (nb + 255) / 256;
-    if (sgrid > (size_t)sm_count * 8) sgrid = (size_t)sm_count * 8;
-    usort_kernel<<<(unsigned)sgrid, 256, 0, s>>>(starts, cells, nb);
-  }
+  if (u.shape == 8) ubins_kernel<8, true><<<grid, 256, 0, s>>>(u, counts, cells);
+  else ubins_kernel<4, true><<<grid, 256, 0, s>>>(u, counts, cells);
   e = cudaStreamSynchronize(s);
   cudaFree(counts);
-  if (e != cudaSuccess) { cudaFree(starts); cudaFree(cells); cudaFree(boxes); return e; }
+  if (e != cudaSuccess) { cudaFree(starts); cudaFree(cells); return e; }
   u.bin_start = starts;
   u.bin_cells = cells;
-  u.cell_box = boxes;
   *bin_start_out = starts;
   *bin_cells_out = cells;
-  *cell_box_out = boxes;
   return cudaGetLastError();
 }
 } // namespace vr

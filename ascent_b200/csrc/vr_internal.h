@@ -42,8 +42,7 @@ struct UMeshDev
   float bmin[3], bmax[3], ginv[3];
   int g[3];
   const int* bin_start; // g0 g1 g2 + 1
-  const int* bin_cells; // per bin: ascending cell ids
-  const float* cell_box; // n_cells x 6: lo x,y,z, hi x,y,z of each cell's points
+  const int* bin_cells;
 };
 
 // Everything one trace launch needs; passed by value as a __grid_constant__ (trace_multi_kernel reads a device
@@ -130,7 +129,6 @@ struct Block
   void* owned_conn = nullptr;
   int* owned_bin_start = nullptr;
   int* owned_bin_cells = nullptr;
-  float* owned_cell_box = nullptr;
   const void* staged_src = nullptr;   // device-visible alias of the host array
   unsigned char* line_want = nullptr; // lines the next trace will touch (pre-pass output)
   unsigned char* line_have = nullptr; // lines already fetched since the publish
@@ -612,8 +610,7 @@ void preload_unstructured_kernels();
 cudaError_t launch_utrace_partials(const TraceParams& p, const UMeshDev& u, int sm_count, cudaStream_t s);
 cudaError_t umesh_bounds(const float* xyz, size_t n_points, int* keys_dev, float bmin[3], float bmax[3], int sm_count,
                          cudaStream_t s);
-cudaError_t umesh_build_bins(UMeshDev& u, int** bin_start_out, int** bin_cells_out, float** cell_box_out, int sm_count,
-                             cudaStream_t s);
+cudaError_t umesh_build_bins(UMeshDev& u, int** bin_start_out, int** bin_cells_out, int sm_count, cudaStream_t s);
 
 // png.cu
 unsigned png_slot_stride(int W);
