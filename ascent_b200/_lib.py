@@ -37,7 +37,7 @@ SYMBOLS = [
     "vr_sample_distance", "vr_visibility_order", "vr_find_subset", "vr_synth_braid_dev",
     "vr_camera_default", "vr_camera_reset_to_bounds", "vr_camera_azimuth", "vr_camera_elevation",
     "vr_camera_zoom", "vr_camera_cinema", "vr_color_table_sample", "vr_correct_opacity", "vr_comm_timeline",
-    "vr_comm_join", "vr_comm_render_frames", "vr_comm_connect_local", "vr_field_gather_strided", "vr_field_free", "vr_radixk_schedule", "vr_canvas_encode_png", "vr_png_bound", "vr_block_unstructured", "vr_canvas_download_rect",
+    "vr_comm_join", "vr_comm_render_frames", "vr_comm_connect_local", "vr_field_gather_strided", "vr_field_free", "vr_radixk_schedule", "vr_canvas_encode_png", "vr_png_bound", "vr_block_unstructured", "vr_canvas_download_rect", "vr_partials_append",
 ]
 
 
@@ -148,6 +148,7 @@ def load():
         "vr_field_free": (C.c_int, [vp, vp]),
         "vr_canvas_encode_png": (C.c_int, [vp, fp, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
         "vr_png_bound": (C.c_size_t, [C.c_int, C.c_int]),
+        "vr_partials_append": (C.c_int, [vp, vp, C.c_size_t, C.c_int]),
         "vr_canvas_download_rect": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
         "vr_block_unstructured": (C.c_int, [vp, C.c_int, C.c_size_t, vp, C.c_int, C.c_size_t, C.c_int, vp, C.c_int, vp,
                                             C.c_int, C.c_int, C.c_int]),
@@ -423,6 +424,12 @@ class Context:
     def trace_to_partials(self, block_id, cam, sample_dist, rmin, rmax, use_canvas_depth=False):
         self._ck(self.lib.vr_trace_to_partials(self.h, block_id, C.byref(as_camera(cam)), sample_dist,
                                                rmin, rmax, int(use_canvas_depth)))
+
+    def partials_append(self, partials):
+        """vr_partials_append: a host array of PARTIAL_DTYPE from another producer joins the frame's list"""
+        p = np.ascontiguousarray(partials)
+        assert p.dtype == PARTIAL_DTYPE
+        self._ck(self.lib.vr_partials_append(self.h, p.ctypes.data, p.size, VR_HOST))
 
     def partials_count(self):
         n = C.c_size_t()

@@ -580,8 +580,30 @@ __global__ void partials_to_canvas_kernel(const vr_partial* __restrict__ p,
 } // namespace
 
 // ================================================================= launchers
+// vr_partials_append: `n` partials of another producer go behind whatever the frame's list holds
+__global__ void partial_append_kernel(const vr_partial* __restrict__ src, unsigned long long n, vr_partial* __restrict__ list,
+                                      unsigned long long* __restrict__ count, unsigned long long capacity)
+{
+  __shared__ unsigned long long s_base;
+  // one CTA (the lists of an external producer are host-sized): reserve, then copy
+  if (threadIdx.x == 0) s_base = atomicAdd(count, n);
+  __syncthreads();
+  const unsigned long long base = s_base;
+  for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x)
+    if (base + i < capacity) list[base + i] = src[i];
+}
+
+cudaError_t launch_partial_append(const vr_partial* src_dev, size_t n, vr_partial* list, unsigned long long* count,
+                                  size_t capacity, cudaStream_t s)
+{
+  if (n == 0) return cudaSuccess;
+  partial_append_kernel<<<1, 1024, 0, s>>>(src_dev, (unsigned long long)n, list, count, (unsigned long long)capacity);
+  return cudaGetLastError();
+}
+
 void preload_composite_kernels()
 {
+  preload_kernel(partial_append_kernel);
   preload_kernel(canvas_clear_kernel);
   preload_kernel(quantize_kernel);
   preload_kernel(fold_images_kernel);

@@ -1276,6 +1276,45 @@ extern "C" vr_status vr_trace_to_partials(vr_ctx* ctx, int block_id, const vr_ca
   return VR_OK;
 }
 
+// Partials of ANOTHER producer (Devil Ray's volume integrator, dray/rendering/renderer.cpp:309-323, converts its
+// own to apcomp::VolumePartial<float> -- the same 24-byte POD -- before PartialCompositor::composite) join the
+// frame's list and are composited with everything vr_trace_to_partials emitted.
+extern "C" vr_status vr_partials_append(vr_ctx* ctx, const vr_partial* partials, size_t n, int where)
+{
+  VR_ENTER(ctx);
+  REQUIRE(ctx->pW > 0, "vr_partials_append: call vr_partials_begin first");
+  REQUIRE(partials || n == 0, "vr_partials_append: NULL list");
+  REQUIRE(where == VR_HOST || where == VR_DEVICE, "vr_partials_append: where must be VR_HOST or VR_DEVICE");
+  if (n == 0) return VR_OK;
+  CK(cudaSetDevice(ctx->device));
+  const long long n_px = (long long)ctx->pW * ctx->pH;
+  if (where == VR_HOST)
+    for (size_t i = 0; i < n; ++i)
+      REQUIRE(partials[i].pixel_id >= 0 && (long long)partials[i].pixel_id < n_px,
+              "vr_partials_append: pixel id %d outside %dx%d", partials[i].pixel_id, ctx->pW, ctx->pH);
+  ctx->n_partials_host += n;
+  vr_status st = ensure_partials(ctx, ctx->n_partials_host);
+  if (st != VR_OK) return st;
+  const vr_partial* src = partials;
+  vr_partial* tmp = nullptr;
+  if (where == VR_HOST)
+  {
+    CK(cudaMalloc(&tmp, n * sizeof(vr_partial)));
+    cudaError_t e = cudaMemcpyAsync(tmp, partials, n * sizeof(vr_partial), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(tmp); return fail(ctx, VR_ERR_CUDA, "vr_partials_append: %s", cudaGetErrorString(e)); }
+    src = tmp;
+  }
+  cudaError_t e = launch_partial_append(src, n, ctx->partials, ctx->partial_count, ctx->partial_cap, ctx->stream);
+  ctx->launches++;
+  if (tmp)
+  {
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); // (the caller's list may be reused; tmp is freed)
+    cudaFree(tmp);
+  }
+  if (e != cudaSuccess) return fail(ctx, VR_ERR_CUDA, "vr_partials_append: %s", cudaGetErrorString(e));
+  return VR_OK;
+}
+
 extern "C" vr_status vr_partials_count(vr_ctx* ctx, size_t* n)
 {
   VR_ENTER_RO(ctx);

@@ -491,6 +491,8 @@ int launch_partials_pixel_sort(const vr_partial* in, const unsigned long long* c
                                size_t sorted_cap, int* end_out, int* minmax, cudaStream_t s,
                                cudaError_t* err);
 
+cudaError_t launch_partial_append(const vr_partial* src_dev, size_t n, vr_partial* list, unsigned long long* count,
+                                  size_t capacity, cudaStream_t s);
 cudaError_t launch_partials_to_canvas(const vr_partial* p, const unsigned long long* count_dev,
                                       size_t max_n, const ToCanvasParams& tp, float4* canvas,
                                       float* cdepth, cudaStream_t s);

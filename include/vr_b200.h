@@ -232,6 +232,12 @@ VR_API vr_status vr_partials_begin(vr_ctx* ctx, int width, int height);
 VR_API vr_status vr_trace_to_partials(vr_ctx* ctx, int block_id, const vr_camera* cam,
                                       float sample_dist, float range_min, float range_max,
                                       int use_canvas_depth);
+/* Partials of another producer join the frame's list (after vr_partials_begin, in any order with
+ * vr_trace_to_partials): Devil Ray's volume integrator hands apcomp::VolumePartial<float> -- this POD -- to the
+ * same PartialCompositor (dray/rendering/renderer.cpp:309-331), so its lists can be composited here, across ranks
+ * too (vr_comm_composite_partials).  VR_HOST lists are copied (the call then synchronises), VR_DEVICE lists read
+ * in stream order.  Pixel ids are validated for host lists.                                              */
+VR_API vr_status vr_partials_append(vr_ctx* ctx, const vr_partial* partials, size_t n, int where);
 VR_API vr_status vr_partials_count(vr_ctx* ctx, size_t* n); /* syncs */
 VR_API vr_status vr_partials_download(vr_ctx* ctx, vr_partial* out, size_t capacity, size_t* n);
 /* Host-buffer form: library-allocated array, release with vr_free.  Order within the array is

@@ -143,3 +143,38 @@ def test_bad_meshes_are_rejected(ctx):
     pts = np.zeros((8, 3), np.float32)
     with pytest.raises(_lib.VRError):
         ctx.block_unstructured(0, pts, np.full((1, 8), 99, np.int32), np.zeros(8, np.float32))  # index out of range
+
+
+def test_partials_of_another_producer_join_the_frame(ctx):
+    """vr_partials_append (the Devil Ray consumer seam, dray/rendering/renderer.cpp:309-331): a list produced elsewhere
+    -- here by the oracle, for the second of two neighbouring blocks -- is composited together with what
+    vr_trace_to_partials emitted for the first one, exactly like two traced blocks"""
+    doms = datasets.braid_uniform_blocks(10, 2, dtype=np.float32)[:2]
+    gb = datasets.union_bounds([datasets.domain_bounds(d) for d in doms])
+    W, H = 260, 200
+    cam = O.camera_reset_to_bounds(gb)
+    O.camera_azimuth(cam, 35.0)
+    lut = color_table.parse_color_table(scenes.RAMP_TF).corrected_opacity(100).lut()
+    sd = O.sample_distance(gb, 100)
+    rmin, rmax = scenes.field_range(doms)
+    _, depth = O.new_canvas(W, H)
+    p0 = O.render_partials(scenes.oracle_block(doms[0]), cam, W, H, lut, sd, rmin, rmax, depth)
+    p1 = O.render_partials(scenes.oracle_block(doms[1]), cam, W, H, lut, sd, rmin, rmax, depth)
+    want = _sorted(O.composite_partials([p0, p1]))
+    ctx.set_tf(lut)
+    ctx.block_from_domain(0, doms[0])
+    ctx.canvas_clear(W, H)
+    ctx.partials_begin(W, H)
+    ctx.partials_append(p1[:p1.size // 2])
+    ctx.trace_to_partials(0, cam, sd, rmin, rmax, True)
+    ctx.partials_append(p1[p1.size // 2:])
+    ctx.partials_composite()
+    got = _sorted(ctx.partials_download())
+    assert got.size == want.size > 1000
+    assert np.array_equal(got["pixel_id"], want["pixel_id"]) and np.array_equal(got["depth"], want["depth"])
+    assert np.abs(got["rgb"] - want["rgb"]).max() <= 1e-6 and np.abs(got["alpha"] - want["alpha"]).max() <= 1e-6
+    bad = p1[:4].copy()
+    bad["pixel_id"][0] = W * H
+    with pytest.raises(_lib.VRError):
+        ctx.partials_append(bad)
+    ctx.block_free(0)
