@@ -1024,11 +1024,12 @@ static vr_status fill_trace_params(vr_ctx* ctx, int block_id, const vr_camera* c
   }
   p.dbl_inv_w = 2.f / (float)W;
   p.dbl_inv_h = 2.f / (float)H;
-  // VolumeRendererStructured::RenderOnDevice: meshEpsilon = |block extent| * 1e-4
+  // first sample at entry + 1e-4 (absolute; pinned by the reference's goldens through the oracle,
+  // tests/test_oracle_golden.py); |block extent| only feeds the default sample distance
   const hm::Vec3 ext = { { (float)(b.bounds[1] - b.bounds[0]), (float)(b.bounds[3] - b.bounds[2]),
                            (float)(b.bounds[5] - b.bounds[4]) } };
   const float mag = hm::magnitude(ext);
-  p.mesh_eps = mag * 0.0001f;
+  p.mesh_eps = 0.0001f;
   p.sample_dist = sample_dist > 0.f ? sample_dist : mag / 200.f;
   p.range_min = range_min;
   p.inv_delta_scalar = (range_max - range_min) != 0.f ? 1.f / (range_max - range_min) : range_min;

@@ -65,7 +65,7 @@ struct alignas(16) TraceParams
   float dbl_inv_w, dbl_inv_h;
   // K3 (block bounds narrowed to f32)
   float bmin[3], bmax[3];
-  // K4
+  // K4 (mesh_eps: the first sample sits at entry + mesh_eps = entry + 1e-4, absolute)
   float mesh_eps, sample_dist, range_min, inv_delta_scalar;
   // uniform blocks: (float)(dims - 1), (float)(dims - 2) for the locator's upper-face fix-up, and which
   // march the sampler runs.  Sparse: EVERY step of EVERY ray is guaranteed to leave its cell (step >= 2.6

@@ -74,6 +74,16 @@ lib.orc_composite_partials.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
 lib.orc_partial_owner.restype = C.c_int
 lib.orc_num_threads.restype = C.c_int
 lib.orc_set_num_threads.argtypes = [C.c_int]
+lib.orc_set_first_sample_offset.argtypes = [C.c_float, C.c_float]
+lib.orc_set_first_sample_offset.restype = None
+
+
+def set_first_sample_offset(abs_offset=1e-4, extent_rel=0.0):
+    """TEST HOOK: first sample of the structured sampler at entry + abs_offset + extent_rel * |block extent|.
+    The default (1e-4, 0) is the reference's convention (pinned by tests/test_oracle_golden.py, which scans the
+    alternatives through this hook); anything else is for that scan only."""
+    lib.orc_set_first_sample_offset(abs_offset, extent_rel)
+
 if ref is not None:
     ref.ref_composite_partials.restype = C.c_longlong
 

@@ -47,7 +47,7 @@ def main():
         return np.array([[H - y1, H - y0, x0, x1] for (y0, y1, x0, x1) in rects], np.int32)
 
     np.savez_compressed(os.path.join(HERE, "render_0100.npz"), rgb=load("render_0100.png")[..., :3],
-                        rects=flip_rects([(100, 420, 95, 420)], 512))
+                        rects=flip_rects([(100, 420, 95, 419)], 512))  # (column 419 carries an axis tick)
     np.savez_compressed(os.path.join(HERE, "render_1100.npz"), rgb=load("render_1100.png")[..., :3],
                         rects=flip_rects([(130, 380, 170, 330)], 400))
     np.savez_compressed(os.path.join(HERE, "tout_render_mpi_3d_diy_volume100.npz"),

@@ -55,50 +55,73 @@ def test_default_camera_geometry():
     assert abs((sx + sw / 2) - 256) <= 1 and abs((sy + sh / 2) - 256) <= 1
 
 
-@pytest.mark.parametrize("which,name,within1,within2", [(0, "render_0100", 0.99, 0.997), (1, "render_1100", 0.98, 0.995),
-                                                        (2, "tout_render_mpi_3d_diy_volume100", 0.995, 0.998)])
-def test_goldens_pin_the_oracle_far_tighter_than_the_reference_tolerance(golden_dir, which, name, within1, within2):
-    """The reference's PNGCompare only asks for <= 0.1 % (1 %) of pixels off by more than 4/255.  The
-    restated K0-K8 chain actually reproduces the reference's pixels much more closely: >= 98-99.5 % of
-    the annotation-free pixels within 1/255 and >= 99.5 % within 2/255 (the rest sit on silhouette
-    edges).  Asserting that keeps any drift of the restatement from hiding inside the loose tolerance."""
+def _golden_diff(golden_dir, which, name):
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     sc = scenes.multi_render_scene(which) if which < 2 else scenes.mpi_volume_scene()
     _, _, canvas = scenes.oracle_path_a(sc)
-    d = crop_diffs(scenes.png_bytes(canvas, sc["W"], sc["H"]), g["rgb"], g["rects"])
-    assert (d <= 1).mean() >= within1, (d <= 1).mean()
-    assert (d <= 2).mean() >= within2, (d <= 2).mean()
-    assert (d <= 4).mean() >= 0.9995
+    return crop_diffs(scenes.png_bytes(canvas, sc["W"], sc["H"]), g["rgb"], g["rects"])
 
 
-@pytest.mark.parametrize("which,name", [(0, "render_0100"), (1, "render_1100"), (2, "tout_render_mpi_3d_diy_volume100")])
-def test_residual_against_the_goldens_is_unbiased_noise(golden_dir, which, name):
-    """What is left between the restated chain and the reference's PNGs is not a geometric disagreement: a
-    least-squares fit of the per-pixel difference against the golden's image gradients (difference = shift .
-    gradient + bias, the signature of a camera / pixel-centre / FindSubset offset) finds a sub-pixel shift below
-    0.05 px and a bias below 0.15 grey levels, explaining < 5 % of the variance; the RMS difference is below
-    0.7 levels of 255.  The > 1-level differences sit where the IMAGE changes fast (they are 40x more frequent on
-    pixels whose golden gradient exceeds 8 levels/px than on flat ones) in the interior of the volume as much as
-    on its silhouette -- per-ray rounding of sample positions by a different build of VTK-m, not a convention of
-    K0-K8 that the restatement misses."""
-    g = np.load(os.path.join(golden_dir, name + ".npz"))
-    sc = scenes.multi_render_scene(which) if which < 2 else scenes.mpi_volume_scene()
+GOLDENS = [(0, "render_0100"), (1, "render_1100"), (2, "tout_render_mpi_3d_diy_volume100")]
+
+
+@pytest.mark.parametrize("which,name,exact,within1,worst", [(0, "render_0100", 0.998, 0.9999, 1),
+                                                            (1, "render_1100", 1.0, 1.0, 0),
+                                                            (2, "tout_render_mpi_3d_diy_volume100", 0.9995, 0.9995, 2)])
+def test_goldens_pin_the_oracle_uint8_for_uint8(golden_dir, which, name, exact, within1, worst):
+    """The reference's PNGCompare only asks for <= 0.1 % (1 %) of pixels off by more than 4/255.  The restated
+    K0-K8 chain reproduces the reference's PNGs uint8 FOR uint8: every pixel of the render_1100 crop, 99.8 % of
+    render_0100's and 99.95 % of the 2-rank rectilinear scene's, and -- the north star's own bar, here against the
+    reference's images rather than against the oracle -- >= 99.9 % within 1/255 and none beyond 3/255.  What is
+    left is not the volume: render_0100's off-by-one pixels sit exactly on the screen diagonals |x-256| == |y-256|
+    (and two columns) where the golden shows the white bounding-box edges through rays whose opacity stops just short of 1 (green
+    255 instead of 254), the mpi scene's 23 pixels (off by 2) are one 1-pixel-wide line of the same annotation
+    crossing the top of the crops."""
+    d = _golden_diff(golden_dir, which, name)
+    assert (d == 0).mean() >= exact, (d == 0).mean()
+    assert (d <= 1).mean() >= within1 and (d <= 1).mean() >= 0.999, (d <= 1).mean()
+    assert d.max() <= worst <= 3, d.max()
+
+
+def test_render_0100_residual_is_the_bounding_box_annotation(golden_dir):
+    """nearly every pixel of the crop that is not uint8-equal lies on a screen diagonal through the image centre (the
+    receding edges of the bounding box under the default camera) or on the columns x = 256 +- 99 (the vertical
+    edges of its back face); all of them differ by one level, and only in the direction 'golden brighter' (white lines under
+    a not quite opaque volume)"""
+    g = np.load(os.path.join(golden_dir, "render_0100.npz"))
+    sc = scenes.multi_render_scene(0)
     _, _, canvas = scenes.oracle_path_a(sc)
     mine = scenes.png_bytes(canvas, sc["W"], sc["H"])
-    gold = g["rgb"]
-    A, Y = [], []
-    for (y0, y1, x0, x1) in g["rects"]:
-        for ch in range(3):
-            m = mine[y0:y1, x0:x1, ch].astype(float)
-            gd = gold[y0:y1, x0:x1, ch].astype(float)
-            gy, gx = np.gradient(gd)
-            ok = (gd > 2) & (gd < 253) & (m > 2) & (m < 253)  # (saturated channels carry no signal)
-            A.append(np.stack([gx[ok], gy[ok], np.ones(int(ok.sum()))], 1))
-            Y.append((m - gd)[ok])
-    A, Y = np.concatenate(A), np.concatenate(Y)
-    sol = np.linalg.lstsq(A, Y, rcond=None)[0]
-    explained = 1.0 - ((Y - A @ sol) ** 2).sum() / ((Y - Y.mean()) ** 2).sum()
-    assert abs(sol[0]) < 0.05 and abs(sol[1]) < 0.05, sol
-    assert abs(sol[2]) < 0.15, sol
-    assert explained < 0.05, explained
-    assert np.sqrt((Y ** 2).mean()) < 0.7
+    y0, y1, x0, x1 = [int(v) for v in g["rects"][0]]
+    diff = g["rgb"][y0:y1, x0:x1].astype(int) - mine[y0:y1, x0:x1, :3].astype(int)
+    ys, xs = np.nonzero(np.abs(diff).max(axis=2) > 0)
+    assert 0 < ys.size < 300
+    on_diagonal = np.abs(ys + y0 - 256) == np.abs(xs + x0 - 256)
+    on_back_edge = np.abs(xs + x0 - 256) == 99
+    # (the remaining ~30 form a 5-pixel staircase next to the top-left corner: a third line of the annotation)
+    assert (on_diagonal | on_back_edge).mean() > 0.75 and on_diagonal.sum() > 20 and on_back_edge.sum() > 20
+    assert diff.min() == 0 and diff.max() == 1
+
+
+@pytest.mark.parametrize("which,name", GOLDENS)
+def test_first_sample_offset_is_pinned_by_the_goldens(golden_dir, which, name):
+    """The one convention of K4 the goldens decide: the first sample sits at entry + 1e-4, an ABSOLUTE offset.
+    SURVEY appendix B9 recalled 1e-4 * |block extent| (34.6x / 110.9x larger in these scenes); scanning the offset
+    through the oracle's test hook shows the recalled form reproduces only 64-92 % of the goldens' pixels exactly,
+    against 99.8-100 % for the default, and that the match degrades on either side of 1e-4."""
+    from oracle import oracle as O
+
+    def exact(abs_offset, extent_rel):
+        O.set_first_sample_offset(abs_offset, extent_rel)
+        try:
+            return float((_golden_diff(golden_dir, which, name) == 0).mean())
+        finally:
+            O.set_first_sample_offset()
+
+    best = exact(1e-4, 0.0)
+    recalled = exact(0.0, 1e-4)
+    assert best >= 0.998 and recalled < 0.93 and best - recalled > 0.08, (best, recalled)
+    for other in (1e-5, 5e-4, 2e-3):
+        assert exact(other, 0.0) <= best, other
+    if which < 2:  # (the rectilinear scene is flat between 2e-5 and 2e-4; the two braid scenes are not)
+        assert exact(2e-5, 0.0) < best and exact(2.5e-4, 0.0) < best
