@@ -23,7 +23,7 @@ EXTRA = os.environ.get("VR_NVCC_EXTRA", "").split()
 COMMON = EXTRA + ["-O3", "-lineinfo", "-std=c++17", "--fmad=false", "-ccbin", HOSTCXX, "-Xcompiler",
           "-fPIC,-ffp-contract=off,-fvisibility=hidden", "-Xptxas", "-v"]
 SOURCES = ["sampler.cu", "stage.cu", "composite.cu", "layers.cu", "comm.cu", "png.cu", "unstructured.cu", "vr_api.cu"]
-HEADERS = ["vr_internal.h", "vr_host_math.hpp", "vr_color_table.hpp", "vr_radixk.hpp", os.path.join("..", "..", "include", "vr_b200.h")]
+HEADERS = ["vr_internal.h", "vr_host_math.hpp", "vr_color_table.hpp", "vr_radixk.hpp", "vr_umesh_geom.hpp", "vr_umesh_faces.hpp", os.path.join("..", "..", "include", "vr_b200.h")]
 
 
 def _newer(target, deps):

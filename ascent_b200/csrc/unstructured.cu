@@ -4,15 +4,19 @@
 // (src/libs/vtkh/rendering/VolumeRenderer.cpp:182-221: VTK-m's ConnectivityProxy::PartialTrace, then
 // vtkm_to_partials :141-180) and forces path B for the whole scene (:874-903, m_has_unstructured).  VTK-m's
 // ConnectivityTracer is not part of /root/reference, so what this kernel implements is the algorithm restated in
-// oracle/raycast_oracle.c ("N4: unstructured cells"), which is pinned to the reference's golden of this path
-// (tout_multi_topo_single_ghost_vol_render100.png: 99.7 % of the pixels within 1/255) and to the structured
-// sampler on structured meshes:
+// oracle/raycast_oracle.c ("N4: unstructured cells"), whose conventions are the ones the reference's golden of this
+// path decides (tout_multi_topo_single_ghost_vol_render100.png, a box of hexahedra with a notch: 99.9 % of its
+// pixels come out uint8-equal) and which degenerates to the structured sampler on structured meshes:
 //   K1-K3 exactly as sampler.cu (rays over the screen subset of the mesh's point bounds, canvas-depth clamp,
-//   entry/exit of the bounds); first sample at entry + (entry mod sample distance) -- the convention the golden
-//   fixes --, then one sample per sample distance; a sample contributes when it lies inside a cell (hexahedron:
-//   inverse trilinear map by four Newton steps from the cell centre; tetrahedron: barycentric coordinates; lowest
-//   cell id on shared faces); same classification, blend and early termination as the structured sampler; one
-//   partial per ray with alpha >= 0.001, depth = exit distance.
+//   entry/exit of the bounds).  The ray is then cut into the stretches it spends INSIDE the mesh -- from an
+//   entering crossing of the mesh boundary (the external faces, vr_umesh_geom.hpp) to the next leaving one; a ray
+//   that leaves through a concavity and comes back starts a new stretch -- and every stretch is sampled from
+//   entry + (entry mod sample distance), the phase reset at every entry, in steps of the sample distance while the
+//   distance is <= the stretch's end.  A sample contributes when it lies inside a cell (hexahedron: inverse
+//   trilinear map by four Newton steps from the cell centre; tetrahedron: barycentric coordinates; lowest cell id
+//   on shared faces); the table index is v * 1024 clamped to 1023 (the structured sampler: v * 1023); blend and
+//   early termination as in the structured sampler; one partial per ray with alpha >= 0.001, depth = the exit
+//   distance of the bounds.
 // Cells are found through uniform bins over the point bounds (ceil(cbrt(n_cells)) per axis), built on the device
 // at publish time: bounds by atomic min/max, per-bin counts, a scan, a fill.  Compiled --fmad=false like the
 // sampler: every comparison and every Newton step rounds like the oracle, so partials are bit-identical.
@@ -20,6 +24,7 @@
 #include <cstring>
 
 #include "vr_internal.h"
+#include "vr_umesh_geom.hpp"
 
 namespace vr
 {
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(kThreads) utrace_kernel(const __grid_constant_
         dx = dx / sq; dy = dy / sq; dz = dz / sq;
       }
       const float ox = P.origin[0], oy = P.origin[1], oz = P.origin[2];
-      float min_distance = 0.f;
+      float min_distance = 0.f, exit_distance = 0.f;
       // ---------------- K2
       if (P.use_depth)
       {
@@ -216,72 +221,81 @@ __global__ void __launch_bounds__(kThreads) utrace_kernel(const __grid_constant_
         const float xmin = minx * ix - odx, ymin = miny * iy - ody, zmin = minz * iz - odz;
         const float xmax = maxx * ix - odx, ymax = maxy * iy - ody, zmax = maxz * iz - odz;
         min_distance = fmaxf(fmaxf(fmaxf(fminf(ymin, ymax), fminf(xmin, xmax)), fminf(zmin, zmax)), min_distance);
-        const float exit_distance = fminf(fminf(fmaxf(ymin, ymax), fmaxf(xmin, xmax)), fmaxf(zmin, zmax));
+        exit_distance = fminf(fminf(fmaxf(ymin, ymax), fmaxf(xmin, xmax)), fmaxf(zmin, zmax));
         max_distance = fminf(max_distance, exit_distance);
         if (max_distance < min_distance) min_distance = -1.f;
       }
       if (min_distance != -1.f)
       {
-        // first sample: entry + (entry mod sample distance) -- see the file header
-        float distance = min_distance + fmodf(min_distance, sd);
-        float p[3] = { ox + distance * dx, oy + distance * dy, oz + distance * dz };
-        while (!VR_UINB(p[0], p[1], p[2]) && distance < max_distance)
+        // the stretches inside the mesh, each sampled from entry + (entry mod sample distance) -- see the file header
+        const float o3[3] = { ox, oy, oz }, d3[3] = { dx, dy, dz };
+        float hits[kMaxCrossings];
+        const int nh = umesh_collect_crossings<SHAPE>(U, o3, d3, min_distance, exit_distance, hits);
+        bool inside = false, opaque = false;
+        float te = 0.f;
+        for (int h = 0; h < nh && !opaque; ++h)
         {
-          distance += sd;
-          p[0] = ox + distance * dx; p[1] = oy + distance * dy; p[2] = oz + distance * dz;
-        }
-        while (VR_UINB(p[0], p[1], p[2]) && distance < max_distance)
-        {
-          float rst[3];
-          // (tried: testing the previous sample's cell first and taking it when the sample lies well inside -- for
-          // warped hexahedra the inverse trilinear map is not unique, a lower-numbered neighbour can also claim the
-          // point, so the result differed from the full search (2 of the parity tests failed); it also measured
-          // 7x slower, 30 vs 4.4 ms: profiles/r2_v30_unstructured_time_*.json)
-          const int c = locate<SHAPE>(U, p, rst);
-          if (c >= 0)
+          const float key = hits[h];
+          if (key > 0.f)
           {
-            float v;
-            if (ASSOC == VR_CELL) v = ufld<FT>(U.field, c);
-            else
+            if (!inside) { inside = true; te = key; }
+            continue;
+          }
+          if (!inside) continue;
+          inside = false;
+          const float tx = -key;
+          float distance = te + fmodf(te, sd);
+          while (distance <= tx && distance < max_distance && !opaque)
+          {
+            const float p[3] = { ox + distance * dx, oy + distance * dy, oz + distance * dz };
+            float rst[3];
+            // (tried: testing the previous sample's cell first and taking it when the sample lies well inside -- for
+            // warped hexahedra the inverse trilinear map is not unique, a lower-numbered neighbour can also claim the
+            // point, so the result differed from the full search (2 of the parity tests failed); it also measured
+            // 7x slower, 30 vs 4.4 ms: profiles/r2_v30_unstructured_time_*.json)
+            const int c = locate<SHAPE>(U, p, rst);
+            if (c >= 0)
             {
-              const int* cn = U.conn + (size_t)c * SHAPE;
-              if (SHAPE == 4)
-              {
-                const float f0 = ufld<FT>(U.field, __ldg(cn));
-                v = f0 + rst[0] * (ufld<FT>(U.field, __ldg(cn + 1)) - f0) + rst[1] * (ufld<FT>(U.field, __ldg(cn + 2)) - f0) +
-                    rst[2] * (ufld<FT>(U.field, __ldg(cn + 3)) - f0);
-              }
+              float v;
+              if (ASSOC == VR_CELL) v = ufld<FT>(U.field, c);
               else
               {
-                const float s0 = ufld<FT>(U.field, __ldg(cn)), s1 = ufld<FT>(U.field, __ldg(cn + 1 % SHAPE));
-                const float s2 = ufld<FT>(U.field, __ldg(cn + 2)), s3 = ufld<FT>(U.field, __ldg(cn + 3));
-                const float s4 = ufld<FT>(U.field, __ldg(cn + 4 % SHAPE)), s5 = ufld<FT>(U.field, __ldg(cn + 5 % SHAPE));
-                const float s6 = ufld<FT>(U.field, __ldg(cn + 6 % SHAPE)), s7 = ufld<FT>(U.field, __ldg(cn + 7 % SHAPE));
-                const float l76 = s7 + rst[0] * (s6 - s7);
-                const float l45 = s4 + rst[0] * (s5 - s4);
-                const float ltop = l45 + rst[1] * (l76 - l45);
-                const float l01 = s0 + rst[0] * (s1 - s0);
-                const float l32 = s3 + rst[0] * (s2 - s3);
-                const float lbot = l01 + rst[1] * (l32 - l01);
-                v = lbot + rst[2] * (ltop - lbot);
+                const int* cn = U.conn + (size_t)c * SHAPE;
+                if (SHAPE == 4)
+                {
+                  const float f0 = ufld<FT>(U.field, __ldg(cn));
+                  v = f0 + rst[0] * (ufld<FT>(U.field, __ldg(cn + 1)) - f0) + rst[1] * (ufld<FT>(U.field, __ldg(cn + 2)) - f0) +
+                      rst[2] * (ufld<FT>(U.field, __ldg(cn + 3)) - f0);
+                }
+                else
+                {
+                  const float s0 = ufld<FT>(U.field, __ldg(cn)), s1 = ufld<FT>(U.field, __ldg(cn + 1 % SHAPE));
+                  const float s2 = ufld<FT>(U.field, __ldg(cn + 2)), s3 = ufld<FT>(U.field, __ldg(cn + 3));
+                  const float s4 = ufld<FT>(U.field, __ldg(cn + 4 % SHAPE)), s5 = ufld<FT>(U.field, __ldg(cn + 5 % SHAPE));
+                  const float s6 = ufld<FT>(U.field, __ldg(cn + 6 % SHAPE)), s7 = ufld<FT>(U.field, __ldg(cn + 7 % SHAPE));
+                  const float l76 = s7 + rst[0] * (s6 - s7);
+                  const float l45 = s4 + rst[0] * (s5 - s4);
+                  const float ltop = l45 + rst[1] * (l76 - l45);
+                  const float l01 = s0 + rst[0] * (s1 - s0);
+                  const float l32 = s3 + rst[0] * (s2 - s3);
+                  const float lbot = l01 + rst[1] * (l32 - l01);
+                  v = lbot + rst[2] * (ltop - lbot);
+                }
               }
+              v = (v - P.range_min) * P.inv_delta_scalar;
+              const float raw = v * (cms_f + 1.f);
+              float fidx = fminf(fmaxf(raw, 0.f), cms_f);
+              if (raw >= 9.2233720e18f) fidx = 0.f;
+              const float4 sc = s_ulut[(int)fidx];
+              const float alpha = sc.w * (1.f - c3);
+              c0 = c0 + sc.x * alpha;
+              c1 = c1 + sc.y * alpha;
+              c2 = c2 + sc.z * alpha;
+              c3 = alpha + c3;
+              if (c3 >= 1.f) opaque = true;
             }
-            v = (v - P.range_min) * P.inv_delta_scalar;
-            const float raw = v * cms_f;
-            float fidx = fminf(fmaxf(raw, 0.f), cms_f);
-            if (raw >= 9.2233720e18f) fidx = 0.f;
-            const float4 sc = s_ulut[(int)fidx];
-            const float alpha = sc.w * (1.f - c3);
-            c0 = c0 + sc.x * alpha;
-            c1 = c1 + sc.y * alpha;
-            c2 = c2 + sc.z * alpha;
-            c3 = alpha + c3;
-            if (c3 >= 1.f) break;
+            distance += sd;
           }
-          distance += sd;
-          p[0] = p[0] + sd * dx;
-          p[1] = p[1] + sd * dy;
-          p[2] = p[2] + sd * dz;
         }
         c0 = fminf(c0, 1.f); c1 = fminf(c1, 1.f); c2 = fminf(c2, 1.f); c3 = fminf(c3, 1.f);
       }

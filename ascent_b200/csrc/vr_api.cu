@@ -15,6 +15,7 @@
 #include "vr_host_math.hpp"
 #include "vr_internal.h"
 #include "vr_radixk.hpp"
+#include "vr_umesh_faces.hpp"
 
 using namespace vr;
 
@@ -161,6 +162,8 @@ static void free_block(Block& b)
   if (b.owned_conn) cudaFree(b.owned_conn);
   if (b.owned_bin_start) cudaFree(b.owned_bin_start);
   if (b.owned_bin_cells) cudaFree(b.owned_bin_cells);
+  if (b.owned_ext_mask) cudaFree(b.owned_ext_mask);
+  b.owned_ext_mask = nullptr;
   b.owned_xyz = b.owned_conn = nullptr;
   b.owned_bin_start = b.owned_bin_cells = nullptr;
   if (b.line_want) cudaFree(b.line_want);
@@ -576,11 +579,19 @@ extern "C" vr_status vr_block_unstructured(vr_ctx* ctx, int block_id, size_t n_p
   const size_t n_field = assoc == VR_POINT ? n_points : n_cells;
   const size_t fb = n_field * (dtype == VR_F32 ? 4 : 8);
   cudaError_t e = cudaSuccess;
+  std::vector<unsigned char> ext_mask; // which faces of which cells form the mesh boundary (host side, one sort)
   if (where == VR_DEVICE)
   {
     b.um.xyz = static_cast<const float*>(xyz);
     b.um.conn = static_cast<const int*>(connectivity);
     b.um.field = field;
+    std::vector<int> hc(n_cells * (size_t)shape);
+    e = cudaMemcpyAsync(hc.data(), connectivity, hc.size() * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, VR_ERR_CUDA, "vr_block_unstructured: %s", cudaGetErrorString(e));
+    for (size_t i = 0; i < hc.size(); ++i)
+      if (hc[i] < 0 || (size_t)hc[i] >= n_points) return fail(ctx, VR_ERR_INVALID, "vr_block_unstructured: connectivity entry %zu out of range", i);
+    ext_mask = umesh_external_mask(hc.data(), n_cells, shape);
   }
   else
   {
@@ -596,6 +607,7 @@ extern "C" vr_status vr_block_unstructured(vr_ctx* ctx, int block_id, size_t n_p
       if (v < 0 || (size_t)v >= n_points) return fail(ctx, VR_ERR_INVALID, "vr_block_unstructured: connectivity entry %zu out of range", i);
       hc[i] = (int)v;
     }
+    ext_mask = umesh_external_mask(hc.data(), n_cells, shape);
     e = cudaMalloc(&b.owned_xyz, hx.size() * 4);
     if (e == cudaSuccess) e = cudaMalloc(&b.owned_conn, hc.size() * 4);
     if (e == cudaSuccess) e = cudaMalloc(&b.owned_field, fb);
@@ -608,6 +620,11 @@ extern "C" vr_status vr_block_unstructured(vr_ctx* ctx, int block_id, size_t n_p
     b.um.conn = static_cast<const int*>(b.owned_conn);
     b.um.field = b.owned_field;
   }
+  e = cudaMalloc(&b.owned_ext_mask, ext_mask.size());
+  if (e == cudaSuccess) e = cudaMemcpyAsync(b.owned_ext_mask, ext_mask.data(), ext_mask.size(), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { free_block(b); return fail(ctx, VR_ERR_CUDA, "vr_block_unstructured (boundary): %s", cudaGetErrorString(e)); }
+  b.um.ext_mask = b.owned_ext_mask;
   b.um.dtype = dtype;
   b.um.assoc = assoc;
   b.um.shape = shape;

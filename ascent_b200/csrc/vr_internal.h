@@ -43,6 +43,7 @@ struct UMeshDev
   int g[3];
   const int* bin_start; // g0 g1 g2 + 1
   const int* bin_cells;
+  const unsigned char* ext_mask; // n_cells: bit f = face f is external (vr_umesh_faces.hpp)
 };
 
 // Everything one trace launch needs; passed by value as a __grid_constant__ (trace_multi_kernel reads a device
@@ -129,6 +130,7 @@ struct Block
   void* owned_conn = nullptr;
   int* owned_bin_start = nullptr;
   int* owned_bin_cells = nullptr;
+  unsigned char* owned_ext_mask = nullptr;
   const void* staged_src = nullptr;   // device-visible alias of the host array
   unsigned char* line_want = nullptr; // lines the next trace will touch (pre-pass output)
   unsigned char* line_have = nullptr; // lines already fetched since the publish

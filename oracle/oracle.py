@@ -242,7 +242,8 @@ class UMesh(C.Structure):
     _fields_ = [("n_points", C.c_int), ("n_cells", C.c_int), ("shape", C.c_int), ("xyz", C.c_void_p),
                 ("conn", C.c_void_p), ("field", C.c_void_p), ("field_f64", C.c_int), ("cell_assoc", C.c_int),
                 ("bmin", C.c_float * 3), ("bmax", C.c_float * 3), ("ginv", C.c_float * 3), ("g", C.c_int * 3),
-                ("bin_start", C.c_void_p), ("bin_cells", C.c_void_p)]
+                ("bin_start", C.c_void_p), ("bin_cells", C.c_void_p),
+                ("n_ext", C.c_int), ("ext_faces", C.c_void_p), ("ext_cell", C.c_void_p)]
 
 
 class OracleUMesh:
@@ -274,12 +275,13 @@ class OracleUMesh:
         return np.array(out[:], np.float64)
 
 
-def trace_umesh(mesh, cam, W, H, lut, sample_dist, rmin, rmax, canvas_depth=None, keep=True, structured_phase=False):
+def trace_umesh(mesh, cam, W, H, lut, sample_dist, rmin, rmax, canvas_depth=None, keep=True,
+                structured_conventions=False):
     lut = np.ascontiguousarray(lut, np.float32)
     rays = Rays()
     dptr = None if canvas_depth is None else _ptr(canvas_depth, C.c_float)
     lib.orc_trace_umesh(C.byref(mesh.m), C.byref(cam), W, H, _ptr(lut, C.c_float), int(lut.shape[0]),
-                        C.c_float(sample_dist), C.c_float(rmin), C.c_float(rmax), dptr, int(structured_phase),
+                        C.c_float(sample_dist), C.c_float(rmin), C.c_float(rmax), dptr, int(structured_conventions),
                         C.byref(rays))
     return rays, (TraceResult(rays) if keep else None)
 

@@ -842,6 +842,11 @@ typedef struct
   int g[3];
   int* bin_start;       /* g0*g1*g2 + 1 */
   int* bin_cells;
+  /* external faces (orc_umesh_build): faces that belong to exactly one cell.  4 point ids each (a triangle
+   * repeats its last id) + the owning cell */
+  int n_ext;
+  int* ext_faces;
+  int* ext_cell;
 } orc_umesh;
 
 #define UM_TOL 1e-4f
@@ -868,10 +873,126 @@ static inline int um_bin_of(const orc_umesh* m, int a, float x)
   return b;
 }
 
+
+/* Faces of a cell in its own point numbering (VTK hexahedron / tetrahedron).  Which way a face winds does not
+ * matter: a hit is classified against the cell's centroid. */
+static const int UM_HEX_FACES[6][4] = { {0,3,2,1}, {4,5,6,7}, {0,1,5,4}, {1,2,6,5}, {2,3,7,6}, {3,0,4,7} };
+static const int UM_TET_FACES[4][4] = { {0,2,1,1}, {0,1,3,3}, {1,2,3,3}, {2,0,3,3} };
+
+static int um_cmp_face_key(const void* a, const void* b) { return memcmp(a, b, 4 * sizeof(int)); }
+
+/* external faces = faces whose (sorted) point ids occur once over all cells */
+static void um_build_external_faces(orc_umesh* m)
+{
+  const int nfc = m->shape == 8 ? 6 : 4, nv = m->shape == 8 ? 4 : 3;
+  const size_t nf = (size_t)m->n_cells * nfc;
+  int (*key)[6] = (int (*)[6])malloc(sizeof(int[6]) * (nf ? nf : 1)); /* sorted ids x4, cell, face */
+  for (int c = 0; c < m->n_cells; ++c)
+    for (int f = 0; f < nfc; ++f)
+    {
+      int* k = key[(size_t)c * nfc + f];
+      const int* F = m->shape == 8 ? UM_HEX_FACES[f] : UM_TET_FACES[f];
+      for (int i = 0; i < 4; ++i) k[i] = i < nv ? m->conn[(size_t)c * m->shape + F[i]] : -1;
+      for (int i = 0; i < 4; ++i)
+        for (int j = i + 1; j < 4; ++j)
+          if (k[j] < k[i]) { const int t = k[i]; k[i] = k[j]; k[j] = t; }
+      k[4] = c; k[5] = f;
+    }
+  qsort(key, nf, sizeof(int[6]), um_cmp_face_key);
+  m->ext_faces = (int*)malloc(sizeof(int) * 4 * (nf ? nf : 1));
+  m->ext_cell = (int*)malloc(sizeof(int) * (nf ? nf : 1));
+  m->n_ext = 0;
+  for (size_t i = 0; i < nf; )
+  {
+    size_t j = i + 1;
+    while (j < nf && memcmp(key[i], key[j], 4 * sizeof(int)) == 0) ++j;
+    if (j - i == 1)
+    {
+      const int c = key[i][4];
+      const int* F = m->shape == 8 ? UM_HEX_FACES[key[i][5]] : UM_TET_FACES[key[i][5]];
+      for (int q = 0; q < 4; ++q) m->ext_faces[4 * (size_t)m->n_ext + q] = m->conn[(size_t)c * m->shape + F[q]];
+      m->ext_cell[m->n_ext] = c;
+      m->n_ext += 1;
+    }
+    i = j;
+  }
+  free(key);
+}
+
+/* Moeller-Trumbore, f32, edges included (tolerance 1e-6 in the barycentric coordinates); distance > 0 or INFINITY.
+ * n receives the (unnormalised) normal (b - a) x (c - a). */
+static inline float um_tri_hit(const float* o, const float* d, const float* a, const float* b, const float* c, float n[3])
+{
+  const float e1[3] = { b[0] - a[0], b[1] - a[1], b[2] - a[2] }, e2[3] = { c[0] - a[0], c[1] - a[1], c[2] - a[2] };
+  n[0] = e1[1] * e2[2] - e1[2] * e2[1]; n[1] = e1[2] * e2[0] - e1[0] * e2[2]; n[2] = e1[0] * e2[1] - e1[1] * e2[0];
+  const float pv[3] = { d[1] * e2[2] - d[2] * e2[1], d[2] * e2[0] - d[0] * e2[2], d[0] * e2[1] - d[1] * e2[0] };
+  const float det = e1[0] * pv[0] + e1[1] * pv[1] + e1[2] * pv[2];
+  if (fabsf(det) < 1e-12f) return INFINITY;
+  const float inv = 1.f / det;
+  const float tv[3] = { o[0] - a[0], o[1] - a[1], o[2] - a[2] };
+  const float u = (tv[0] * pv[0] + tv[1] * pv[1] + tv[2] * pv[2]) * inv;
+  if (u < -1e-6f || u > 1.f + 1e-6f) return INFINITY;
+  const float qv[3] = { tv[1] * e1[2] - tv[2] * e1[1], tv[2] * e1[0] - tv[0] * e1[2], tv[0] * e1[1] - tv[1] * e1[0] };
+  const float v = (d[0] * qv[0] + d[1] * qv[1] + d[2] * qv[2]) * inv;
+  if (v < -1e-6f || u + v > 1.f + 1e-6f) return INFINITY;
+  const float t = (e2[0] * qv[0] + e2[1] * qv[1] + e2[2] * qv[2]) * inv;
+  return t > 0.f ? t : INFINITY;
+}
+
+#define UM_MAX_HITS 32
+/* Where the ray crosses the mesh boundary: every external face is tested (a quadrilateral as the triangles
+ * (0,1,2) and (0,2,3), the nearer hit counting); a crossing ENTERS the mesh when the ray runs against the face's
+ * outward normal (outward = away from the owning cell's centroid).  Crossings are kept as signed distances
+ * (+t enters, -t leaves), sorted by distance with a leaving crossing before an entering one at the same
+ * distance, bit-identical repeats dropped, the nearest UM_MAX_HITS kept.  Returns their number. */
+static int um_boundary_crossings(const orc_umesh* m, const float* o, const float* d, float* hits)
+{
+  int n = 0;
+  for (int f = 0; f < m->n_ext; ++f)
+  {
+    const int* id = m->ext_faces + 4 * (size_t)f;
+    const float* a = m->xyz + 3 * (size_t)id[0];
+    const float* b = m->xyz + 3 * (size_t)id[1];
+    const float* c = m->xyz + 3 * (size_t)id[2];
+    float nrm[3], n2[3];
+    float t = um_tri_hit(o, d, a, b, c, nrm);
+    if (id[3] != id[2])
+    {
+      const float t2 = um_tri_hit(o, d, a, c, m->xyz + 3 * (size_t)id[3], n2);
+      if (t2 < t) { t = t2; nrm[0] = n2[0]; nrm[1] = n2[1]; nrm[2] = n2[2]; }
+    }
+    if (t == INFINITY) continue;
+    /* centroid of the owning cell: points summed in cell order, times 1/shape */
+    const int* cn = m->conn + (size_t)m->ext_cell[f] * m->shape;
+    float cen[3] = { 0.f, 0.f, 0.f };
+    for (int k = 0; k < m->shape; ++k)
+      for (int q = 0; q < 3; ++q) cen[q] = cen[q] + m->xyz[3 * (size_t)cn[k] + q];
+    const float w = m->shape == 8 ? 0.125f : 0.25f;
+    const float side = nrm[0] * (a[0] - cen[0] * w) + nrm[1] * (a[1] - cen[1] * w) + nrm[2] * (a[2] - cen[2] * w);
+    float dn = d[0] * nrm[0] + d[1] * nrm[1] + d[2] * nrm[2];
+    if (side < 0.f) dn = -dn;
+    const float key = dn < 0.f ? t : -t;
+    /* sorted insertion: by distance, leaving before entering; identical keys once */
+    int at = 0, dup = 0;
+    while (at < n)
+    {
+      const float h = hits[at], ht = fabsf(h);
+      if (h == key) { dup = 1; break; }
+      if (ht > t || (ht == t && key < 0.f)) break;
+      ++at;
+    }
+    if (dup || at >= UM_MAX_HITS) continue;
+    if (n < UM_MAX_HITS) ++n;
+    for (int k = n - 1; k > at; --k) hits[k] = hits[k - 1];
+    hits[at] = key;
+  }
+  return n;
+}
+
 ORC_API void orc_umesh_free(orc_umesh* m)
 {
-  free(m->bin_start); free(m->bin_cells);
-  m->bin_start = m->bin_cells = NULL;
+  free(m->bin_start); free(m->bin_cells); free(m->ext_faces); free(m->ext_cell);
+  m->bin_start = m->bin_cells = m->ext_faces = m->ext_cell = NULL;
 }
 
 /* point bounds, bins per axis = ceil(cbrt(n_cells)) (at most 256), cells listed per bin by ascending id */
@@ -923,6 +1044,7 @@ ORC_API void orc_umesh_build(orc_umesh* m)
     }
     free(cursor);
   }
+  um_build_external_faces(m);
 }
 
 /* 3x3 solve by Cramer's rule: columns a, b, c; rhs r.  returns 0 when singular */
@@ -1008,6 +1130,35 @@ static int um_locate(const orc_umesh* m, const float p[3], float rst[3])
   return -1;
 }
 
+/* (tests) the boundary crossings of n rays (8 floats each: origin, direction, 2 unused), 32 keys per ray */
+ORC_API void orc_umesh_crossings_batch(const orc_umesh* m, const float* rays, int n, float* hits_out, int* counts_out)
+{
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int r = 0; r < n; ++r)
+    counts_out[r] = um_boundary_crossings(m, rays + 8 * (size_t)r, rays + 8 * (size_t)r + 3, hits_out + (size_t)UM_MAX_HITS * r);
+}
+
+/* the field at parametric coordinates rst of cell c */
+static inline float um_value(const orc_umesh* m, int c, const float rst[3])
+{
+  if (m->cell_assoc) return um_fld(m, c);
+  const int* cn = m->conn + (size_t)c * m->shape;
+  if (m->shape == 4)
+  {
+    const float f0 = um_fld(m, cn[0]);
+    return f0 + rst[0] * (um_fld(m, cn[1]) - f0) + rst[1] * (um_fld(m, cn[2]) - f0) + rst[2] * (um_fld(m, cn[3]) - f0);
+  }
+  const float s0 = um_fld(m, cn[0]), s1 = um_fld(m, cn[1]), s2 = um_fld(m, cn[2]), s3 = um_fld(m, cn[3]);
+  const float s4 = um_fld(m, cn[4]), s5 = um_fld(m, cn[5]), s6 = um_fld(m, cn[6]), s7 = um_fld(m, cn[7]);
+  const float l76 = s7 + rst[0] * (s6 - s7);
+  const float l45 = s4 + rst[0] * (s5 - s4);
+  const float ltop = l45 + rst[1] * (l76 - l45);
+  const float l01 = s0 + rst[0] * (s1 - s0);
+  const float l32 = s3 + rst[0] * (s2 - s3);
+  const float lbot = l01 + rst[1] * (l32 - l01);
+  return lbot + rst[2] * (ltop - lbot);
+}
+
 ORC_API void orc_umesh_bounds(const orc_umesh* m, double out[6])
 {
   for (int a = 0; a < 3; ++a) { out[2 * a] = (double)m->bmin[a]; out[2 * a + 1] = (double)m->bmax[a]; }
@@ -1015,7 +1166,7 @@ ORC_API void orc_umesh_bounds(const orc_umesh* m, double out[6])
 
 ORC_API void orc_trace_umesh(const orc_umesh* m, const orc_camera* cam, int W, int H, const float* lut, int lut_size,
                              float sample_dist, float range_min, float range_max, const float* canvas_depth,
-                             int structured_phase, orc_rays* rays)
+                             int structured_conventions, orc_rays* rays)
 {
   double bounds[6];
   orc_umesh_bounds(m, bounds);
@@ -1092,69 +1243,81 @@ ORC_API void orc_trace_umesh(const orc_umesh* m, const orc_camera* cam, int W, i
     if (min_distance == -1.f) continue;
 
     float color[4] = { 0.f, 0.f, 0.f, 0.f };
-    /* First sample: entry + (entry mod sample distance).  This is the convention that reproduces the reference's
-     * golden (fitted per pixel against tout_multi_topo_single_ghost_vol_render100.png: with it 99.7 % of the pixels
-     * are within 1/255; with "entry + eps", as in the structured sampler, only 74 %): VTK-m's ConnectivityTracer
-     * is not available to say why.  fmodf is exact, so CPU and GPU agree bit for bit. */
-    float distance = min_distance + fmodf(min_distance, sample_dist);
-    /* (test hook: the structured sampler's "entry + eps", to show that everything else degenerates to it) */
-    if (structured_phase) distance = min_distance + 0.0001f;
-    float p[3] = { o[0] + distance * d[0], o[1] + distance * d[1], o[2] + distance * d[2] };
     int64_t ns = 0;
-#define UM_INB(q) (!((q)[0] < Xmin || (q)[0] > Xmax) && !((q)[1] < Ymin || (q)[1] > Ymax) && !((q)[2] < Zmin || (q)[2] > Zmax))
-    while (!UM_INB(p) && distance < max_distance)
-    {
-      distance += sample_dist;
-      p[0] = o[0] + distance * d[0]; p[1] = o[1] + distance * d[1]; p[2] = o[2] + distance * d[2];
+    /* one sample at distance t: classify + blend when the point lies in a cell; returns 1 when the ray is opaque.
+     * index_scale: the tracer of explicit cell sets indexes the table with v * 1024 (clamped to 1023), the
+     * structured sampler with v * 1023 -- the ghost-field golden decides (93 % of its pixels are uint8-equal with
+     * 1023, 99.2 % with 1024, everything else unchanged). */
+#define UM_SAMPLE(t, index_scale, opaque)                                                                            \
+    {                                                                                                                \
+      const float q_[3] = { o[0] + (t) * d[0], o[1] + (t) * d[1], o[2] + (t) * d[2] };                               \
+      float rst[3];                                                                                                  \
+      const int c = um_locate(m, q_, rst);                                                                           \
+      if (c >= 0)                                                                                                    \
+      {                                                                                                              \
+        float v = um_value(m, c, rst);                                                                               \
+        v = (v - range_min) * inv_delta_scalar;                                                                      \
+        int64_t ci = (int64_t)(v * (index_scale));                                                                   \
+        if (ci < 0) ci = 0;                                                                                          \
+        if (ci > color_map_size) ci = color_map_size;                                                                \
+        const float* sc = lut + 4 * ci;                                                                              \
+        float alpha = sc[3] * (1.f - color[3]);                                                                      \
+        color[0] = color[0] + sc[0] * alpha;                                                                         \
+        color[1] = color[1] + sc[1] * alpha;                                                                         \
+        color[2] = color[2] + sc[2] * alpha;                                                                         \
+        color[3] = alpha + color[3];                                                                                 \
+        ++ns;                                                                                                        \
+        if (color[3] >= 1.f) (opaque) = 1;                                                                           \
+      }                                                                                                              \
     }
-    while (UM_INB(p) && distance < max_distance)
+    if (!structured_conventions)
     {
-      float rst[3];
-      const int c = um_locate(m, p, rst);
-      if (c >= 0)
+      /* ConnectivityTracer, as the golden of this path shows it (tests/test_oracle_unstructured.py): the ray is cut
+       * into the stretches it spends INSIDE the mesh (from an entering crossing of the mesh boundary to the next
+       * leaving one -- a ray that leaves through a concavity and comes back starts a new stretch); each stretch
+       * is sampled from entry + (entry mod sample distance) -- the phase is reset at every entry -- in steps of the
+       * sample distance while the distance is <= the stretch's end (and short of the canvas-depth limit).  Sample
+       * positions are origin + distance * direction.  fmodf is exact, so CPU and GPU agree bit for bit. */
+      float hits[UM_MAX_HITS];
+      const int nh = um_boundary_crossings(m, o, d, hits);
+      int inside = 0, opaque = 0;
+      float te = 0.f;
+      for (int h = 0; h < nh && !opaque; ++h)
       {
-        float v;
-        if (m->cell_assoc) v = um_fld(m, c);
-        else
+        if (hits[h] > 0.f) { if (!inside) { inside = 1; te = hits[h]; } continue; }
+        if (!inside) continue;
+        inside = 0;
+        const float tx = -hits[h];
+        float t = te + fmodf(te, sample_dist);
+        while (t <= tx && t < max_distance && !opaque)
         {
-          const int* cn = m->conn + (size_t)c * m->shape;
-          if (m->shape == 4)
-          {
-            const float f0 = um_fld(m, cn[0]);
-            v = f0 + rst[0] * (um_fld(m, cn[1]) - f0) + rst[1] * (um_fld(m, cn[2]) - f0) + rst[2] * (um_fld(m, cn[3]) - f0);
-          }
-          else
-          {
-            const float s0 = um_fld(m, cn[0]), s1 = um_fld(m, cn[1]), s2 = um_fld(m, cn[2]), s3 = um_fld(m, cn[3]);
-            const float s4 = um_fld(m, cn[4]), s5 = um_fld(m, cn[5]), s6 = um_fld(m, cn[6]), s7 = um_fld(m, cn[7]);
-            const float l76 = s7 + rst[0] * (s6 - s7);
-            const float l45 = s4 + rst[0] * (s5 - s4);
-            const float ltop = l45 + rst[1] * (l76 - l45);
-            const float l01 = s0 + rst[0] * (s1 - s0);
-            const float l32 = s3 + rst[0] * (s2 - s3);
-            const float lbot = l01 + rst[1] * (l32 - l01);
-            v = lbot + rst[2] * (ltop - lbot);
-          }
+          UM_SAMPLE(t, (float)(color_map_size + 1), opaque);
+          t += sample_dist;
         }
-        v = (v - range_min) * inv_delta_scalar;
-        int64_t ci = (int64_t)(v * (float)color_map_size);
-        if (ci < 0) ci = 0;
-        if (ci > color_map_size) ci = color_map_size;
-        const float* sc = lut + 4 * ci;
-        float alpha = sc[3] * (1.f - color[3]);
-        color[0] = color[0] + sc[0] * alpha;
-        color[1] = color[1] + sc[1] * alpha;
-        color[2] = color[2] + sc[2] * alpha;
-        color[3] = alpha + color[3];
-        ++ns;
-        if (color[3] >= 1.f) break;
       }
-      distance += sample_dist;
-      p[0] = p[0] + sample_dist * d[0];
-      p[1] = p[1] + sample_dist * d[1];
-      p[2] = p[2] + sample_dist * d[2];
     }
+    else
+    {
+      /* TEST HOOK: the structured sampler's conventions (first sample at bounds entry + 1e-4, table index v * 1023,
+       * inside = within the point bounds), to show that everything else degenerates to the structured sampler */
+      float distance = min_distance + 0.0001f;
+      float p[3] = { o[0] + distance * d[0], o[1] + distance * d[1], o[2] + distance * d[2] };
+      int opaque = 0;
+#define UM_INB(q) (!((q)[0] < Xmin || (q)[0] > Xmax) && !((q)[1] < Ymin || (q)[1] > Ymax) && !((q)[2] < Zmin || (q)[2] > Zmax))
+      while (!UM_INB(p) && distance < max_distance)
+      {
+        distance += sample_dist;
+        p[0] = o[0] + distance * d[0]; p[1] = o[1] + distance * d[1]; p[2] = o[2] + distance * d[2];
+      }
+      while (UM_INB(p) && distance < max_distance && !opaque)
+      {
+        UM_SAMPLE(distance, (float)color_map_size, opaque);
+        distance += sample_dist;
+        p[0] = o[0] + distance * d[0]; p[1] = o[1] + distance * d[1]; p[2] = o[2] + distance * d[2];
+      }
 #undef UM_INB
+    }
+#undef UM_SAMPLE
     total_samples += ns;
     rays->rgba[4 * idx + 0] = fminf(color[0], 1.f);
     rays->rgba[4 * idx + 1] = fminf(color[1], 1.f);

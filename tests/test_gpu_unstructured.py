@@ -24,11 +24,15 @@ def _sorted(p):
     return np.sort(p, order=["pixel_id", "depth"])
 
 
-def _warped_mesh(n, seed, dtype):
+def _warped_mesh(n, seed, dtype, hollow=False):
     """braid on an n^3 grid, written as hexahedra whose interior points are pushed off the lattice (general, non
-    axis-aligned hexahedra); the field is sampled at the lattice positions (any values do)"""
+    axis-aligned hexahedra); the field is sampled at the lattice positions (any values do).  hollow: a block of cells
+    is missing from the middle (a cavity: rays enter, leave, enter again) and three from a corner (a notch)"""
     dom = datasets.braid_uniform(n, dtype=dtype)
-    pts, conn = datasets.structured_to_hexes(dom["dims"], dom["origin"], dom["spacing"])
+    drop = ()
+    if hollow:
+        drop = [((k * (n - 1) + j) * (n - 1) + i) for k in range(4, 6) for j in range(3, 6) for i in range(2, 6)] + [0, 1, n - 1]
+    pts, conn = datasets.structured_to_hexes(dom["dims"], dom["origin"], dom["spacing"], drop_cells=drop)
     g = np.random.default_rng(seed)
     idx = np.arange(pts.shape[0])
     i, j, k = idx % n, (idx // n) % n, idx // (n * n)
@@ -39,10 +43,29 @@ def _warped_mesh(n, seed, dtype):
     return dom, pts, conn
 
 
-@pytest.mark.parametrize("shape,dtype,assoc,az", [("hex", np.float32, "point", 25.0), ("hex", np.float64, "cell", -50.0),
-                                                   ("tet", np.float32, "point", 130.0), ("tet", np.float64, "cell", 10.0)])
-def test_partials_bit_exact_against_the_oracle(ctx, shape, dtype, assoc, az):
-    dom, pts, conn = _warped_mesh(11, 3, dtype)
+def _same(got, want, what):
+    """bit equality with a diagnosis instead of a bare False"""
+    if got.size != want.size:
+        common = np.intersect1d(got["pixel_id"], want["pixel_id"]).size
+        raise AssertionError("%s: %d partials, oracle %d (%d pixels in common)" % (what, got.size, want.size, common))
+    for f in ("pixel_id", "depth", "rgb", "alpha"):
+        a, b = got[f], want[f]
+        if not np.array_equal(a, b):
+            bad = np.nonzero((a != b).reshape(a.shape[0], -1).any(axis=1))[0]
+            raise AssertionError("%s: %s differs in %d of %d partials; first: pixel %d got %s want %s (alpha %s / %s)" % (
+                what, f, bad.size, a.shape[0], int(want["pixel_id"][bad[0]]), a[bad[0]], b[bad[0]],
+                got["alpha"][bad[0]], want["alpha"][bad[0]]))
+
+
+@pytest.mark.parametrize("shape,dtype,assoc,az,hollow", [("hex", np.float32, "point", 25.0, False),
+                                                          ("hex", np.float64, "cell", -50.0, False),
+                                                          ("tet", np.float32, "point", 130.0, False),
+                                                          ("tet", np.float64, "cell", 10.0, False),
+                                                          ("hex", np.float32, "point", 200.0, True),
+                                                          ("tet", np.float32, "point", -20.0, True),
+                                                          ("hex", np.float64, "cell", 0.0, True)])
+def test_partials_bit_exact_against_the_oracle(ctx, shape, dtype, assoc, az, hollow):
+    dom, pts, conn = _warped_mesh(11, 3, dtype, hollow)
     if shape == "tet":
         conn = datasets.hexes_to_tets(conn)
     g = np.random.default_rng(5)
@@ -62,9 +85,8 @@ def test_partials_bit_exact_against_the_oracle(ctx, shape, dtype, assoc, az):
                            assoc=_lib.VR_CELL if assoc == "cell" else _lib.VR_POINT)
     assert np.allclose(ctx.block_bounds(0), um.bounds())
     got = _sorted(ctx.render_partials(0, cam, W, H, sd, rmin, rmax, None))
-    assert got.size == want.size > 5000
-    assert np.array_equal(got["pixel_id"], want["pixel_id"]) and np.array_equal(got["depth"], want["depth"])
-    assert np.array_equal(got["rgb"], want["rgb"]) and np.array_equal(got["alpha"], want["alpha"])
+    assert want.size > 5000
+    _same(got, want, "%s %s hollow=%s" % (shape, assoc, hollow))
     # the other entry points refuse an unstructured block, as the reference never renders one to a canvas directly
     ctx.canvas_clear(W, H)
     with pytest.raises(_lib.VRError):
@@ -75,7 +97,7 @@ def test_partials_bit_exact_against_the_oracle(ctx, shape, dtype, assoc, az):
 def test_ghost_field_golden_through_the_abi(ctx, golden_dir):
     """t_ascent_multi_topo.cpp:181-252 end to end on the GPU: unstructured partials -> PartialCompositor ->
     partials_to_canvas -> background + uint8, against the oracle (bit-exact canvas) and against the reference's own
-    PNG at the reference's tolerance and at what the restatement achieves (99.7 % of the pixels within 1/255)"""
+    PNG at the reference's tolerance and at what the restatement achieves (99.9 % of the pixels uint8-equal)"""
     sc = scenes.ghost_volume_scene()
     W, H = sc["W"], sc["H"]
     _, o_rgba, o_depth = scenes.oracle_unstructured_path_b(sc)
@@ -93,7 +115,7 @@ def test_ghost_field_golden_through_the_abi(ctx, golden_dir):
     g = np.load(os.path.join(golden_dir, "tout_multi_topo_single_ghost_vol_render100.npz"))["rgb"].astype(int)
     mine = np.asarray(ctx.canvas_download_rgba8(W, H, (0., 0., 0., 1.), flip=False)).reshape(H, W, 4)[..., :3].astype(int)
     d = np.abs(mine - g).max(axis=2)
-    assert (d > 4).mean() <= 0.004 and (d <= 1).mean() >= 0.995
+    assert (d > 4).mean() <= 0.0005 and (d == 0).mean() >= 0.999
     ctx.block_free(0)
 
 

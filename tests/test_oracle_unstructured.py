@@ -2,11 +2,13 @@
 
 VTK-m's ConnectivityTracer is absent from /root/reference, so the restatement is pinned from two sides:
   * against the reference's golden of the unstructured path, tout_multi_topo_single_ghost_vol_render100.png
-    (annotation-free, whole 1024^2 frame), at the reference's own tolerance (<= 2 % of the pixels off by more than
-    4/255, t_ascent_multi_topo.cpp:246) and far tighter -- which is also what fixes the one convention that could
-    not be known otherwise, where the first sample of a ray sits;
+    (annotation-free, whole 1024^2 frame: a box of hexahedra with a two-cell notch), which the restatement
+    reproduces uint8 for uint8 on 99.9 % of the frame -- and which is what decides the three conventions that could
+    not be known otherwise: the ray is sampled stretch by stretch inside the mesh (entering through an external
+    face, leaving through one, re-entering behind a concavity), every stretch starts at entry + (entry mod sample
+    distance), and the transfer-function table is indexed with v * 1024 (clamped), not v * 1023;
   * against the structured sampler (itself pinned to three goldens): on a structured mesh written out as
-    hexahedra, with the first sample put where the structured sampler puts it, the two agree to rounding."""
+    hexahedra, with the structured sampler's conventions switched in, the two agree to rounding."""
 import os
 
 import numpy as np
@@ -16,6 +18,17 @@ from oracle import oracle as O
 import scenes
 
 
+def _ghost_frame(sc, **kw):
+    W, H = sc["W"], sc["H"]
+    um = O.OracleUMesh(sc["points"], sc["conn"], sc["field"])
+    rays, _ = O.trace_umesh(um, sc["cam"], W, H, sc["lut"], sc["sample_dist"], sc["rmin"], sc["rmax"], keep=False, **kw)
+    rgba, depth = O.new_canvas(W, H)
+    O.lib.orc_write_to_canvas(O.C.byref(rays), O.C.byref(sc["cam"]), W, H, O._ptr(rgba, O.C.c_float),
+                              O._ptr(depth, O.C.c_float))
+    O.rays_free(rays)
+    return scenes.png_bytes(rgba, W, H)[..., :3].astype(int)
+
+
 def test_ghost_volume_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "tout_multi_topo_single_ghost_vol_render100.npz"))["rgb"].astype(int)
     sc = scenes.ghost_volume_scene()
@@ -23,26 +36,24 @@ def test_ghost_volume_golden(golden_dir):
     mine = scenes.png_bytes(rgba, sc["W"], sc["H"])[..., :3].astype(int)
     d = np.abs(mine - g).max(axis=2)
     assert (d > 4).mean() <= 0.02            # the reference test's own criterion
-    assert (d > 4).mean() <= 0.004           # what the restatement achieves: 0.23 %
-    assert (d <= 1).mean() >= 0.995          # 99.7 % of ALL pixels within 1/255
+    assert (d > 4).mean() <= 0.0005          # what the restatement achieves: 0.036 %
+    assert (d == 0).mean() >= 0.999          # 99.94 % of ALL pixels uint8-equal
     covered = g.sum(axis=2) > 0
-    assert (d[covered] <= 1).mean() >= 0.99  # ... and of the pixels the volume covers
+    assert (d[covered] == 0).mean() >= 0.998 and (d[covered] <= 1).mean() >= 0.999
+    # what is left: two strips 2-4 pixels wide where rays graze the side walls of the notch (the reference takes up
+    # to four samples fewer there) and ~200 isolated pixels one level off
+    ys, xs = np.nonzero(d > 1)
+    assert ys.size < 600 and ((xs >= 700) & (ys <= 260)).mean() > 0.98
 
 
-def test_first_sample_convention_is_what_the_golden_fixes(golden_dir):
-    """with the structured sampler's 'entry + eps' the same scene misses the golden by 12 % of the pixels"""
+def test_conventions_the_golden_fixes(golden_dir):
+    """with the structured sampler's conventions (first sample at bounds entry + 1e-4, table index v * 1023, no
+    stretches) the same scene misses the golden on most pixels"""
     g = np.load(os.path.join(golden_dir, "tout_multi_topo_single_ghost_vol_render100.npz"))["rgb"].astype(int)
     sc = scenes.ghost_volume_scene()
-    W, H = sc["W"], sc["H"]
-    um = O.OracleUMesh(sc["points"], sc["conn"], sc["field"])
-    rays, _ = O.trace_umesh(um, sc["cam"], W, H, sc["lut"], sc["sample_dist"], sc["rmin"], sc["rmax"], keep=False,
-                            structured_phase=True)
-    rgba, depth = O.new_canvas(W, H)
-    O.lib.orc_write_to_canvas(O.C.byref(rays), O.C.byref(sc["cam"]), W, H, O._ptr(rgba, O.C.c_float),
-                              O._ptr(depth, O.C.c_float))
-    O.rays_free(rays)
-    d = np.abs(scenes.png_bytes(rgba, W, H)[..., :3].astype(int) - g).max(axis=2)
-    assert (d > 4).mean() > 0.08
+    d = np.abs(_ghost_frame(sc, structured_conventions=True) - g).max(axis=2)
+    covered = g.sum(axis=2) > 0
+    assert (d > 4).mean() > 0.08 and (d[covered] == 0).mean() < 0.5
 
 
 def test_hexahedra_of_a_structured_grid_degenerate_to_the_structured_sampler():
@@ -59,7 +70,7 @@ def test_hexahedra_of_a_structured_grid_degenerate_to_the_structured_sampler():
     O.rays_free(r0)
     pts, conn = datasets.structured_to_hexes(dom["dims"], dom["origin"], dom["spacing"])
     um = O.OracleUMesh(pts, conn, dom["field"].reshape(-1))
-    r1, t1 = O.trace_umesh(um, cam, W, H, lut, sd, rmin, rmax, structured_phase=True)
+    r1, t1 = O.trace_umesh(um, cam, W, H, lut, sd, rmin, rmax, structured_conventions=True)
     O.rays_free(r1)
     assert t0.subset == t1.subset and t0.n_samples == t1.n_samples
     d = np.abs(t0.rgba - t1.rgba).max(axis=1)
