@@ -549,6 +549,20 @@ extern "C" vr_status vr_block_rectilinear(vr_ctx* ctx, int block_id, const int d
   return VR_OK;
 }
 
+static const std::vector<unsigned char>& cached_external_mask(vr_ctx* ctx, int block_id, const int* conn, size_t n_cells, int shape)
+{
+  auto& c = ctx->umask_cache[block_id];
+  const unsigned long long h = umesh_conn_hash(conn, n_cells * (size_t)shape);
+  if (c.mask.size() != n_cells || c.n_cells != n_cells || c.shape != shape || c.hash != h)
+  {
+    c.mask = umesh_external_mask(conn, n_cells, shape);
+    c.hash = h;
+    c.n_cells = n_cells;
+    c.shape = shape;
+  }
+  return c.mask;
+}
+
 // N4: an explicit cell set.  Coordinates and connectivity are narrowed to f32 / int32 on the way in (VTK-m's
 // unstructured tracer works in f32 as well); the cell locator is built on the device.
 extern "C" vr_status vr_block_unstructured(vr_ctx* ctx, int block_id, size_t n_points, const void* xyz, int coord_dtype,
@@ -591,7 +605,7 @@ extern "C" vr_status vr_block_unstructured(vr_ctx* ctx, int block_id, size_t n_p
     if (e != cudaSuccess) return fail(ctx, VR_ERR_CUDA, "vr_block_unstructured: %s", cudaGetErrorString(e));
     for (size_t i = 0; i < hc.size(); ++i)
       if (hc[i] < 0 || (size_t)hc[i] >= n_points) return fail(ctx, VR_ERR_INVALID, "vr_block_unstructured: connectivity entry %zu out of range", i);
-    ext_mask = umesh_external_mask(hc.data(), n_cells, shape);
+    ext_mask = cached_external_mask(ctx, block_id, hc.data(), n_cells, shape);
   }
   else
   {
@@ -607,7 +621,7 @@ extern "C" vr_status vr_block_unstructured(vr_ctx* ctx, int block_id, size_t n_p
       if (v < 0 || (size_t)v >= n_points) return fail(ctx, VR_ERR_INVALID, "vr_block_unstructured: connectivity entry %zu out of range", i);
       hc[i] = (int)v;
     }
-    ext_mask = umesh_external_mask(hc.data(), n_cells, shape);
+    ext_mask = cached_external_mask(ctx, block_id, hc.data(), n_cells, shape);
     e = cudaMalloc(&b.owned_xyz, hx.size() * 4);
     if (e == cudaSuccess) e = cudaMalloc(&b.owned_conn, hc.size() * 4);
     if (e == cudaSuccess) e = cudaMalloc(&b.owned_field, fb);
@@ -669,6 +683,7 @@ extern "C" vr_status vr_block_free(vr_ctx* ctx, int block_id)
   CK(cudaStreamSynchronize(ctx->stream));
   free_block(it->second);
   ctx->blocks.erase(it);
+  ctx->umask_cache.erase(block_id);
   return VR_OK;
 }
 

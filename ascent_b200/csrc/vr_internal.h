@@ -251,6 +251,10 @@ struct vr_ctx
   bool no_brick = false;      // never select the brick march (A/B runs)
 
   std::map<int, vr::Block> blocks;
+  // vr_block_unstructured: the external-face mask of the last publish per block id, reused while the
+  // connectivity (its FNV-1a hash, size and cell shape) stays the same -- static topology republished every cycle
+  struct UMaskCache { unsigned long long hash = 0; size_t n_cells = 0; int shape = 0; std::vector<unsigned char> mask; };
+  std::map<int, UMaskCache> umask_cache;
   float4* lut = nullptr;
   int lut_size = 0;
 
