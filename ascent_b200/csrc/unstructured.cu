@@ -383,6 +383,18 @@ __global__ void ubins_kernel(const __grid_constant__ UMeshDev U, int* __restrict
   }
 }
 
+// which bins list a cell that owns an external face (the boundary crossings only look at those)
+__global__ void ubinflag_kernel(const int* __restrict__ bin_start, const int* __restrict__ bin_cells,
+                                const unsigned char* __restrict__ ext_mask, unsigned char* __restrict__ bin_ext, size_t n_bins)
+{
+  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_bins; b += (size_t)gridDim.x * blockDim.x)
+  {
+    unsigned char any = 0;
+    for (int k = bin_start[b]; k < bin_start[b + 1] && !any; ++k) any = ext_mask[bin_cells[k]] ? 1 : 0;
+    bin_ext[b] = any;
+  }
+}
+
 // exclusive scan of n counts into n + 1 starts, one CTA (publish-time work: n = bins ~ cells)
 __global__ void __launch_bounds__(1024) uscan_kernel(const int* __restrict__ counts, int* __restrict__ starts, size_t n)
 {
@@ -462,6 +474,7 @@ void preload_unstructured_kernels()
   preload_kernel(ubins_kernel<4, false>);
   preload_kernel(ubins_kernel<4, true>);
   preload_kernel(uscan_kernel);
+  preload_kernel(ubinflag_kernel);
   cudaGetLastError();
 }
 
@@ -494,8 +507,10 @@ cudaError_t umesh_bounds(const float* xyz, size_t n_points, int* keys_dev, float
   return cudaGetLastError();
 }
 
-// bins: u.g / u.ginv / u.bmin / u.bmax set by the caller; allocates and fills u.bin_start / u.bin_cells
-cudaError_t umesh_build_bins(UMeshDev& u, int** bin_start_out, int** bin_cells_out, int sm_count, cudaStream_t s)
+// bins: u.g / u.ginv / u.bmin / u.bmax / u.ext_mask set by the caller; allocates and fills u.bin_start / u.bin_cells /
+// u.bin_ext
+cudaError_t umesh_build_bins(UMeshDev& u, int** bin_start_out, int** bin_cells_out, unsigned char** bin_ext_out, int sm_count,
+                             cudaStream_t s)
 {
   const size_t nb = (size_t)u.g[0] * u.g[1] * u.g[2];
   int *counts = nullptr, *starts = nullptr, *cells = nullptr;
@@ -519,13 +534,23 @@ cudaError_t umesh_build_bins(UMeshDev& u, int** bin_start_out, int** bin_cells_o
   cudaMemcpyAsync(counts, starts, (nb + 1) * sizeof(int), cudaMemcpyDeviceToDevice, s);
   if (u.shape == 8) ubins_kernel<8, true><<<grid, 256, 0, s>>>(u, counts, cells);
   else ubins_kernel<4, true><<<grid, 256, 0, s>>>(u, counts, cells);
-  e = cudaStreamSynchronize(s);
+  unsigned char* flags = nullptr;
+  e = cudaMalloc(&flags, nb);
+  if (e == cudaSuccess)
+  {
+    size_t fgrid = (nb + 255) / 256;
+    if (fgrid > (size_t)sm_count * 8) fgrid = (size_t)sm_count * 8;
+    ubinflag_kernel<<<(unsigned)fgrid, 256, 0, s>>>(starts, cells, u.ext_mask, flags, nb);
+    e = cudaStreamSynchronize(s);
+  }
   cudaFree(counts);
-  if (e != cudaSuccess) { cudaFree(starts); cudaFree(cells); return e; }
+  if (e != cudaSuccess) { cudaFree(starts); cudaFree(cells); if (flags) cudaFree(flags); return e; }
   u.bin_start = starts;
   u.bin_cells = cells;
+  u.bin_ext = flags;
   *bin_start_out = starts;
   *bin_cells_out = cells;
+  *bin_ext_out = flags;
   return cudaGetLastError();
 }
 } // namespace vr

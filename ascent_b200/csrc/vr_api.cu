@@ -163,7 +163,8 @@ static void free_block(Block& b)
   if (b.owned_bin_start) cudaFree(b.owned_bin_start);
   if (b.owned_bin_cells) cudaFree(b.owned_bin_cells);
   if (b.owned_ext_mask) cudaFree(b.owned_ext_mask);
-  b.owned_ext_mask = nullptr;
+  if (b.owned_bin_ext) cudaFree(b.owned_bin_ext);
+  b.owned_ext_mask = b.owned_bin_ext = nullptr;
   b.owned_xyz = b.owned_conn = nullptr;
   b.owned_bin_start = b.owned_bin_cells = nullptr;
   if (b.line_want) cudaFree(b.line_want);
@@ -662,8 +663,8 @@ extern "C" vr_status vr_block_unstructured(vr_ctx* ctx, int block_id, size_t n_p
     b.dev.min_point[a] = b.um.bmin[a];
     b.dev.max_point[a] = b.um.bmax[a];
   }
-  e = umesh_build_bins(b.um, &b.owned_bin_start, &b.owned_bin_cells, ctx->sm_count, ctx->stream);
-  ctx->launches += 4;
+  e = umesh_build_bins(b.um, &b.owned_bin_start, &b.owned_bin_cells, &b.owned_bin_ext, ctx->sm_count, ctx->stream);
+  ctx->launches += 5;
   if (e != cudaSuccess) { free_block(b); return fail(ctx, VR_ERR_CUDA, "vr_block_unstructured (bins): %s", cudaGetErrorString(e)); }
   auto it = ctx->blocks.find(block_id);
   if (it != ctx->blocks.end())

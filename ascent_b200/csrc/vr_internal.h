@@ -44,6 +44,7 @@ struct UMeshDev
   const int* bin_start; // g0 g1 g2 + 1
   const int* bin_cells;
   const unsigned char* ext_mask; // n_cells: bit f = face f is external (vr_umesh_faces.hpp)
+  const unsigned char* bin_ext;  // g0 g1 g2: the bin lists a cell with an external face
 };
 
 // Everything one trace launch needs; passed by value as a __grid_constant__ (trace_multi_kernel reads a device
@@ -131,6 +132,7 @@ struct Block
   int* owned_bin_start = nullptr;
   int* owned_bin_cells = nullptr;
   unsigned char* owned_ext_mask = nullptr;
+  unsigned char* owned_bin_ext = nullptr;
   const void* staged_src = nullptr;   // device-visible alias of the host array
   unsigned char* line_want = nullptr; // lines the next trace will touch (pre-pass output)
   unsigned char* line_have = nullptr; // lines already fetched since the publish
@@ -618,7 +620,8 @@ void preload_unstructured_kernels();
 cudaError_t launch_utrace_partials(const TraceParams& p, const UMeshDev& u, int sm_count, cudaStream_t s);
 cudaError_t umesh_bounds(const float* xyz, size_t n_points, int* keys_dev, float bmin[3], float bmax[3], int sm_count,
                          cudaStream_t s);
-cudaError_t umesh_build_bins(UMeshDev& u, int** bin_start_out, int** bin_cells_out, int sm_count, cudaStream_t s);
+cudaError_t umesh_build_bins(UMeshDev& u, int** bin_start_out, int** bin_cells_out, unsigned char** bin_ext_out, int sm_count,
+                             cudaStream_t s);
 
 // png.cu
 unsigned png_slot_stride(int W);

@@ -189,6 +189,7 @@ VR_HD int umesh_collect_crossings(const M& U, const float o[3], const float d[3]
         int ix[3];
         ix[A] = k; ix[B] = jb; ix[C] = jc;
         const size_t bin = ((size_t)ix[2] * U.g[1] + ix[1]) * U.g[0] + ix[0];
+        if (!VR_LD(U.bin_ext + bin)) continue; // no cell of this bin touches the mesh boundary (most bins)
         const int q0 = VR_LD(U.bin_start + bin), q1 = VR_LD(U.bin_start + bin + 1);
         for (int q = q0; q < q1; ++q)
         {

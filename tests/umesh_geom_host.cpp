@@ -19,6 +19,7 @@ struct HostMesh
   int g[3];
   const int* bin_start;
   const int* bin_cells;
+  const unsigned char* bin_ext;
 };
 
 template <int SHAPE>
@@ -92,6 +93,12 @@ extern "C" int umesh_crossings_host(const float* xyz, int n_points, const int* c
   else build_bins<4>(U, n_cells, start, cells);
   U.bin_start = start.data();
   U.bin_cells = cells.data();
+  // (csrc/unstructured.cu, ubinflag_kernel) which bins list a cell with an external face
+  std::vector<unsigned char> flags(start.size() - 1, 0);
+  for (size_t b = 0; b + 1 < start.size(); ++b)
+    for (int k = start[b]; k < start[b + 1]; ++k)
+      if (mask[(size_t)cells[(size_t)k]]) flags[b] = 1;
+  U.bin_ext = flags.data();
   for (int r = 0; r < n_rays; ++r)
   {
     const float* q = rays + 8 * (size_t)r;
