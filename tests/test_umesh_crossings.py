@@ -112,3 +112,30 @@ def test_warped_cells_and_a_hollow_mesh(host_lib, shape):
     um = O.OracleUMesh(pts, conn, dom["field"].reshape(-1))
     b = [pts[:, 0].min(), pts[:, 0].max(), pts[:, 1].min(), pts[:, 1].max(), pts[:, 2].min(), pts[:, 2].max()]
     assert _check(host_lib, um, _cams(b), 128, 96, bins=(0, 2, 17)) > 10000
+
+
+def test_more_crossings_than_the_list_holds(host_lib):
+    """20 slabs of cells separated by gaps: a ray along z crosses the boundary 40 times, the list keeps the nearest
+    32 on both sides (oracle: brute force; product: bin traversal) -- and the stretches they describe"""
+    dims, origin, spacing = (4, 4, 41), (-1.5, -1.5, -20.0), (1.0, 1.0, 1.0)
+    ncx, ncy, ncz = 3, 3, 40
+    drop = [((k * ncy + j) * ncx + i) for k in range(1, ncz, 2) for j in range(ncy) for i in range(ncx)]
+    pts, conn = datasets.structured_to_hexes(dims, origin, spacing, drop_cells=drop)
+    field = np.zeros(pts.shape[0], np.float32)
+    um = O.OracleUMesh(pts, conn, field)
+    b = [-1.5, 1.5, -1.5, 1.5, -20.0, 20.0]
+    cam = O.camera_reset_to_bounds(b)          # looks down -z: rays run along the slabs' normal
+    rays = _rays(um, cam, 96, 96)
+    want, want_n, got, got_n, _ = _both(host_lib, um, rays, 0)
+    assert want_n.max() == 32 and (want_n == 32).sum() > 10
+    assert np.array_equal(want_n, got_n) and np.array_equal(want.view(np.uint32), got.view(np.uint32))
+    full = want[want_n == 32]
+    assert (full[:, 0::2] > 0).all() and (full[:, 1::2] < 0).all()        # enter, leave, enter, leave ...
+    assert (np.diff(np.abs(full), axis=1) > 0).all()                      # ... in order of distance
+    cam2 = O.camera_reset_to_bounds(b)
+    O.camera_azimuth(cam2, 35.0)
+    O.camera_elevation(cam2, 15.0)
+    rays = _rays(um, cam2, 96, 96)
+    for bins in (0, 5):
+        want, want_n, got, got_n, _ = _both(host_lib, um, rays, bins)
+        assert np.array_equal(want_n, got_n) and np.array_equal(want.view(np.uint32), got.view(np.uint32))
