@@ -1064,6 +1064,22 @@ static vr_status fill_trace_params(vr_ctx* ctx, int block_id, const vr_camera* c
   const float mag = hm::magnitude(ext);
   p.mesh_eps = 0.0001f;
   p.sample_dist = sample_dist > 0.f ? sample_dist : mag / 200.f;
+  {
+    // every sampling loop ends because the distance grows: a step that no longer changes a float of the size of
+    // the distance to the far side of the block (zero extent with no sample distance given, or a sample count in
+    // the millions) would spin on the device for ever -- refuse it here
+    float far2 = 0.f;
+    for (int k = 0; k < 3; ++k)
+    {
+      const float a = std::fabs((float)b.bounds[2 * k] - cam->position[k]);
+      const float c = std::fabs((float)b.bounds[2 * k + 1] - cam->position[k]);
+      far2 += std::max(a, c) * std::max(a, c);
+    }
+    const float far_side = std::sqrt(far2);
+    REQUIRE(std::isfinite(p.sample_dist) && p.sample_dist > 0.f && !(p.sample_dist < far_side * 2.5e-7f), // (two ulps of the largest distance)
+            "trace: sample distance %g is too small for a block %g away from the camera", (double)p.sample_dist,
+            (double)far_side);
+  }
   p.range_min = range_min;
   p.inv_delta_scalar = (range_max - range_min) != 0.f ? 1.f / (range_max - range_min) : range_min;
   p.march = 0;

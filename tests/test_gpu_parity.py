@@ -953,6 +953,15 @@ def test_errors_are_reported_not_thrown(ctx):
         ctx.set_tf(np.zeros((1, 4), np.float32))
     with pytest.raises(_lib.VRError):
         ctx.block_uniform(0, (1, 4, 4), [0, 0, 0], [1, 1, 1], np.zeros(16, np.float32))
+    # a sample distance too small to advance a float distance would spin on the device: refused on the host
+    dom = datasets.braid_uniform(8)
+    b = datasets.domain_bounds(dom)
+    ctx.set_tf(np.ones((16, 4), np.float32))
+    ctx.block_from_domain(1, dom)
+    ctx.canvas_clear(64, 64)
+    with pytest.raises(_lib.VRError):
+        ctx.trace_to_canvas(1, O.camera_reset_to_bounds(b), 1e-9, 0., 1., False)
+    ctx.trace_to_canvas(1, O.camera_reset_to_bounds(b), 0.3, 0., 1., False)
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
