@@ -125,3 +125,18 @@ def test_first_sample_offset_is_pinned_by_the_goldens(golden_dir, which, name):
         assert exact(other, 0.0) <= best, other
     if which < 2:  # (the rectilinear scene is flat between 2e-5 and 2e-4; the two braid scenes are not)
         assert exact(2e-5, 0.0) < best and exact(2.5e-4, 0.0) < best
+
+
+@pytest.mark.parametrize("which,name", GOLDENS)
+def test_table_index_scale_is_pinned_by_the_goldens(golden_dir, which, name):
+    """the structured sampler indexes the 1024-entry table with v * 1023; with v * 1024 -- the convention the
+    reference's tracer of explicit cell sets turns out to use (tests/test_oracle_unstructured.py) -- the goldens of
+    the structured path are missed on a large share of the pixels"""
+    from oracle import oracle as O
+    best = float((_golden_diff(golden_dir, which, name) == 0).mean())
+    O.lib.orc_set_structured_index_extra(1)
+    try:
+        other = float((_golden_diff(golden_dir, which, name) == 0).mean())
+    finally:
+        O.lib.orc_set_structured_index_extra(0)
+    assert best >= 0.998 and other < best - 0.05, (best, other)
