@@ -164,7 +164,6 @@ __global__ void __launch_bounds__(kThreads) utrace_kernel(const __grid_constant_
   const float sd = P.sample_dist;
   const float minx = P.bmin[0], miny = P.bmin[1], minz = P.bmin[2];
   const float maxx = P.bmax[0], maxy = P.bmax[1], maxz = P.bmax[2];
-#define VR_UINB(x, y, z) (!((x) < minx || (x) > maxx) && !((y) < miny || (y) > maxy) && !((z) < minz || (z) > maxz))
   for (;;)
   {
     unsigned tile = 0;
@@ -321,7 +320,6 @@ __global__ void __launch_bounds__(kThreads) utrace_kernel(const __grid_constant_
       }
     }
   }
-#undef VR_UINB
 }
 
 // ---- locator build
