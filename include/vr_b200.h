@@ -121,7 +121,8 @@ VR_API vr_status vr_block_rectilinear(vr_ctx* ctx, int block_id, const int dims[
  * coordinates and 64-bit indices are narrowed to f32 / int32); VR_DEVICE: adopted in place (f32 coordinates and
  * 32-bit connectivity only).  The cell locator (uniform bins over the point bounds) is built on the device by this
  * call, the mesh boundary (which faces belong to one cell only: a ray is sampled only along the stretches between
- * an entering and a leaving crossing of that boundary, concavities and cavities included) on the host; the call
+ * an entering and a leaving crossing of that boundary, concavities and cavities included; the nearest 32
+ * crossings of a ray are kept) on the host, once per connectivity (reused while it does not change); the call
  * synchronises.  Algorithm and how it is pinned without VTK-m: DESIGN.md section 4.5.                       */
 enum { VR_TETRA = 10, VR_HEXAHEDRON = 12 }; /* VTK / vtkm::CellShape ids */
 VR_API vr_status vr_block_unstructured(vr_ctx* ctx, int block_id, size_t n_points, const void* xyz, int coord_dtype,
