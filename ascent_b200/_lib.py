@@ -38,6 +38,7 @@ SYMBOLS = [
     "vr_camera_default", "vr_camera_reset_to_bounds", "vr_camera_azimuth", "vr_camera_elevation",
     "vr_camera_zoom", "vr_camera_cinema", "vr_color_table_sample", "vr_correct_opacity", "vr_comm_timeline",
     "vr_comm_join", "vr_comm_render_frames", "vr_comm_connect_local", "vr_field_gather_strided", "vr_field_free", "vr_radixk_schedule", "vr_canvas_encode_png", "vr_png_bound", "vr_block_unstructured", "vr_canvas_download_rect", "vr_partials_append",
+    "vr_set_first_sample_offset",
 ]
 
 
@@ -130,6 +131,7 @@ def load():
         "vr_comm_composite_partials_to_canvas": (C.c_int, [vp, cam]),
         "vr_image_ptrs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "vr_sample_distance": (C.c_float, [dp, C.c_float]),
+        "vr_set_first_sample_offset": (C.c_int, [vp, C.c_float, C.c_float]),
         "vr_visibility_order": (None, [dp, C.c_int, cam, ip]),
         "vr_find_subset": (None, [cam, C.c_int, C.c_int, dp, ip]),
         "vr_synth_braid_dev": (C.c_int, [vp, vp, C.c_int, ip, ip, ip]),
@@ -353,6 +355,10 @@ class Context:
         lut = np.ascontiguousarray(lut, np.float32)
         assert lut.ndim == 2 and lut.shape[1] == 4
         self._ck(self.lib.vr_set_tf(self.h, lut.ctypes.data_as(C.POINTER(C.c_float)), lut.shape[0]))
+
+    def set_first_sample_offset(self, abs_offset=0.0, extent_rel=1e-4):
+        """first sample at entry + abs_offset + extent_rel * |block extent| (default: VTK-m's meshEpsilon)"""
+        self._ck(self.lib.vr_set_first_sample_offset(self.h, C.c_float(abs_offset), C.c_float(extent_rel)))
 
     # -- canvas
     def canvas_clear(self, W, H):

@@ -1057,12 +1057,12 @@ static vr_status fill_trace_params(vr_ctx* ctx, int block_id, const vr_camera* c
   }
   p.dbl_inv_w = 2.f / (float)W;
   p.dbl_inv_h = 2.f / (float)H;
-  // first sample at entry + 1e-4 (absolute; pinned by the reference's goldens through the oracle,
-  // tests/test_oracle_golden.py); |block extent| only feeds the default sample distance
+  // first sample at entry + meshEpsilon = |block extent| * 1e-4 (VolumeRendererStructured::RenderOnDevice of the
+  // pinned VTK-m; vr_set_first_sample_offset selects the older generation's 1e-4 absolute)
   const hm::Vec3 ext = { { (float)(b.bounds[1] - b.bounds[0]), (float)(b.bounds[3] - b.bounds[2]),
                            (float)(b.bounds[5] - b.bounds[4]) } };
   const float mag = hm::magnitude(ext);
-  p.mesh_eps = 0.0001f;
+  p.mesh_eps = ctx->first_sample_abs + ctx->first_sample_rel * mag;
   p.sample_dist = sample_dist > 0.f ? sample_dist : mag / 200.f;
   {
     // every sampling loop ends because the distance grows: a step that no longer changes a float of the size of
@@ -2091,6 +2091,16 @@ extern "C" vr_status vr_composite_partials(vr_ctx* ctx, const vr_partial* in, si
 }
 
 // ================================================================= host-side helpers
+extern "C" vr_status vr_set_first_sample_offset(vr_ctx* ctx, float abs_offset, float extent_rel)
+{
+  VR_ENTER_RO(ctx);
+  REQUIRE(std::isfinite(abs_offset) && std::isfinite(extent_rel) && abs_offset >= 0.f && extent_rel >= 0.f,
+          "vr_set_first_sample_offset: offsets must be finite and >= 0");
+  ctx->first_sample_abs = abs_offset;
+  ctx->first_sample_rel = extent_rel;
+  return VR_OK;
+}
+
 extern "C" float vr_sample_distance(const double gb[6], float samples)
 {
   // VolumeRenderer::PreExecute, VolumeRenderer.cpp:606-611

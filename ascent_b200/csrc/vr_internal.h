@@ -67,7 +67,7 @@ struct alignas(16) TraceParams
   float dbl_inv_w, dbl_inv_h;
   // K3 (block bounds narrowed to f32)
   float bmin[3], bmax[3];
-  // K4 (mesh_eps: the first sample sits at entry + mesh_eps = entry + 1e-4, absolute)
+  // K4 (mesh_eps: the first sample sits at entry + mesh_eps; |extent| * 1e-4 unless vr_set_first_sample_offset says otherwise)
   float mesh_eps, sample_dist, range_min, inv_delta_scalar;
   // uniform blocks: (float)(dims - 1), (float)(dims - 2) for the locator's upper-face fix-up, and which
   // march the sampler runs.  Sparse: EVERY step of EVERY ray is guaranteed to leave its cell (step >= 2.6
@@ -253,6 +253,7 @@ struct vr_ctx
   bool no_brick = false;      // never select the brick march (A/B runs)
 
   std::map<int, vr::Block> blocks;
+  float first_sample_abs = 0.f, first_sample_rel = 0.0001f; // vr_set_first_sample_offset
   // vr_block_unstructured: the external-face mask of the last publish per block id, reused while the
   // connectivity (its FNV-1a hash, size and cell shape) stays the same -- static topology republished every cycle
   struct UMaskCache { unsigned long long hash = 0; size_t n_cells = 0; int shape = 0; std::vector<unsigned char> mask; };

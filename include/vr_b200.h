@@ -147,6 +147,12 @@ VR_API vr_status vr_block_bounds(vr_ctx* ctx, int block_id, double out[6]);
  * The 1024 x float4 table Mapper::SetActiveColorTable / convert_table build on the host
  * (VolumeRenderer.cpp:64-91, :518): already opacity-corrected and uint8-rounded.             */
 VR_API vr_status vr_set_tf(vr_ctx* ctx, const float* rgba, int n_entries);
+/* Where the structured sampler puts a ray's first sample: entry + abs_offset + extent_rel * |block extent|.
+ * Default (0, 1e-4): VolumeRendererStructured's meshEpsilon of the VTK-m the reference pins (v2.1.0).  (1e-4, 0) is
+ * what an older generation of VTK-m did -- the one that rendered the reference's three pure-volume golden images,
+ * which this library then reproduces uint8 for uint8.  Applies to the traces issued after the
+ * call; unstructured blocks are not affected.                                                            */
+VR_API vr_status vr_set_first_sample_offset(vr_ctx* ctx, float abs_offset, float extent_rel);
 
 /* ------------------------------------------------------------------ device canvas
  * The context keeps one float canvas (RGBA f32 + depth f32, W x H) in HBM: the stand-in for

@@ -78,10 +78,10 @@ lib.orc_set_first_sample_offset.argtypes = [C.c_float, C.c_float]
 lib.orc_set_first_sample_offset.restype = None
 
 
-def set_first_sample_offset(abs_offset=1e-4, extent_rel=0.0):
-    """TEST HOOK: first sample of the structured sampler at entry + abs_offset + extent_rel * |block extent|.
-    The default (1e-4, 0) is the reference's convention (pinned by tests/test_oracle_golden.py, which scans the
-    alternatives through this hook); anything else is for that scan only."""
+def set_first_sample_offset(abs_offset=0.0, extent_rel=1e-4):
+    """First sample of the structured sampler at entry + abs_offset + extent_rel * |block extent|.  Default (0, 1e-4):
+    VTK-m's meshEpsilon form (the pinned v2.1.0; decided by the newest golden).  (1e-4, 0): the older generation of
+    VTK-m that rendered the reference's three pure-volume goldens.  tests/test_oracle_golden.py pins both."""
     lib.orc_set_first_sample_offset(abs_offset, extent_rel)
 
 if ref is not None:

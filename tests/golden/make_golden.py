@@ -8,8 +8,9 @@ Sources (all under /root/reference/src/tests/_baseline_images/):
                                                               zbuffer}{,_mpi}.cpp
   render_0100.png, render_1100.png   <- t_ascent_render_3d.cpp:1643-1780 (test_render_3d_multi_render)
   tout_render_mpi_3d_diy_volume100.png <- t_ascent_mpi_render_3d.cpp:284-388
-  tout_render_3d_multi_default_runtime100.png <- t_ascent_render_3d.cpp:1017-1122 (colour bars only: the
-      scene itself needs the contour filter and the surface ray tracer, which are outside the volume path)
+  tout_render_3d_multi_default_runtime100.png <- t_ascent_render_3d.cpp:1017-1122 (colour bars, and the pixels
+      whose rays meet no contour surface: the scene's opaque part needs the contour filter and the surface ray
+      tracer, which are outside the volume path)
 
 Colour bars: VTK-m's ColorBarAnnotation draws ColorTable::Sample(bar height) of the plot's table into
 the image (one table sample per pixel row), so one pixel column of a bar is a golden vector for K8:
@@ -55,6 +56,9 @@ def main():
                         rects=flip_rects([(200, 350, 100, 250), (170, 350, 262, 420)], 512))
     vol = load("tout_render_mpi_3d_diy_volume100.png")
     multi = load("tout_render_3d_multi_default_runtime100.png")
+    # the whole frame of the pseudocolor + volume golden: where no ray meets the contour surface the pixels are the
+    # volume plot's alone (tests/test_oracle_golden.py finds those pixels itself)
+    np.savez_compressed(os.path.join(HERE, "tout_render_3d_multi_default_runtime100.npz"), rgb=multi[..., :3])
     # (arrays are un-flipped: row index grows upwards, like the table position along a vertical bar)
     np.savez_compressed(os.path.join(HERE, "colorbars.npz"),
                         cool_to_warm_179=vol[512 - 230:512 - 51, 481, :3],

@@ -148,7 +148,8 @@ def test_numpy_restatement_matches_the_c_oracle_bit_for_bit(kind, cell_assoc, az
     o = [f32(v) for v in cam.position]
     lo = [f32(b[0]), f32(b[2]), f32(b[4])]
     hi = [f32(b[1]), f32(b[3]), f32(b[5])]
-    eps = f32(0.0001)  # first sample at entry + 1e-4, absolute (pinned by the goldens, test_oracle_golden.py)
+    ext = [f32(b[1] - b[0]), f32(b[3] - b[2]), f32(b[5] - b[4])]
+    eps = f32(np.sqrt(ext[0] * ext[0] + ext[1] * ext[1] + ext[2] * ext[2])) * f32(0.0001)  # meshEpsilon (the default)
     hit = 0
     with np.errstate(over="ignore", invalid="ignore"):
         for r in range(res.n):
